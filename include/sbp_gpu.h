@@ -1,0 +1,199 @@
+/*
+ * sbp_gpu.h -- C ABI of libsbpgpu.so, the B200 (sm_100a) implementation of the
+ * collision-checking / nearest-neighbour hot path of soraxas/sbp-env.
+ *
+ * Every entry point replaces one reference interface; the citation after
+ * "replaces:" is file:line under /root/reference/sbp_env/.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types.
+ *  - every function returns int32 status: 0 = SBP_OK, negative = error;
+ *    sbp_last_error() returns a thread-local description of the last failure.
+ *  - pointers marked "device" are raw CUDA addresses in the context's device
+ *    (e.g. torch.Tensor.data_ptr()); the caller owns every buffer it passes.
+ *  - device entry points are asynchronous on the context's stream and never
+ *    synchronise; the *_host entry points copy in, launch, copy out and
+ *    synchronise the stream before returning.
+ *  - the library owns handles until the matching *_destroy.
+ *  - there is no CPU implementation behind any of these calls: without a CUDA
+ *    device sbp_ctx_create fails and nothing else can be called.
+ */
+#ifndef SBP_GPU_H
+#define SBP_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBP_ABI_VERSION 1
+
+/* status codes */
+#define SBP_OK 0
+#define SBP_ERR_CUDA (-1)      /* a CUDA runtime call failed */
+#define SBP_ERR_ARG (-2)       /* invalid argument */
+#define SBP_ERR_NODEV (-3)     /* no usable CUDA device */
+#define SBP_ERR_CAPACITY (-4)  /* caller buffer / node store too small */
+
+/* bits OR-ed into the `flags` word by the collision kernels: what CPython would
+ * raise for that batch (collisionChecker.py:151, :173-174, :400) */
+#define SBP_FLAG_NAN 1       /* int(nan)           -> ValueError   */
+#define SBP_FLAG_OVERFLOW 2  /* int(+-inf), or an index in [2^63,2^64) -> OverflowError */
+
+/* values written to the `out` bytes of the arm entry points */
+#define SBP_FREE 1
+#define SBP_BLOCKED 0
+#define SBP_AMBIGUOUS 2 /* a forward-kinematics point lies within the fp64 guard band of a
+                           pixel boundary: resolve with sbp_arm_resolve_host */
+
+/* near(): which distance and which comparison */
+#define SBP_METRIC_FULL 0 /* np.linalg.norm over all d dims (prmPlanner.py:39, rrtPlanner.py:278) */
+#define SBP_METRIC_XY 1   /* first two dims only, engine.euclidean_dist (engine.py:13-24)        */
+#define SBP_CMP_LT 0      /* d <  r  (prmPlanner.py:42, birrtPlanner.py:85, rrdtPlanner.py:713)  */
+#define SBP_CMP_LE 1      /* d <= r  (rrtPlanner.py:179, :238, :259)                             */
+
+typedef struct sbp_ctx sbp_ctx;
+typedef struct sbp_map sbp_map;
+typedef struct sbp_nodes sbp_nodes;
+
+int32_t sbp_abi_version(void);
+const char *sbp_last_error(void);
+
+/* ---- context ------------------------------------------------------------- */
+/* stream_or_null: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream);
+ * NULL creates a private non-blocking stream owned by the context. */
+int32_t sbp_ctx_create(int32_t device, void *stream_or_null, sbp_ctx **out);
+int32_t sbp_ctx_destroy(sbp_ctx *ctx);
+int32_t sbp_ctx_set_stream(sbp_ctx *ctx, void *stream);
+int32_t sbp_ctx_sync(sbp_ctx *ctx);
+/* number of SMs of the context's device and kernels launched so far */
+int32_t sbp_ctx_info(sbp_ctx *ctx, int32_t *sm_count, int64_t *launches);
+
+/* ---- occupancy map -------------------------------------------------------
+ * replaces: ImgCollisionChecker.__init__ / RobotArm4dCollisionChecker.__init__
+ * storage of `_img` (collisionChecker.py:101-108, :319-340).
+ * free_xy: HOST bytes, the checker's `_img` laid out [W][H] row-major, non-zero
+ * byte = free (`_img[x, y] == 1`).  The map is bit-packed on the device into
+ * 8x8-pixel 64-bit tiles, 2x2 tiles (16x16 px) per 32-byte sector. */
+int32_t sbp_map_create(sbp_ctx *ctx, const uint8_t *free_xy, int32_t W, int32_t H,
+                       sbp_map **out);
+/* same, from a DEVICE byte grid (for procedurally generated 8k-32k maps) */
+int32_t sbp_map_create_device(sbp_ctx *ctx, const uint8_t *free_xy_device, int32_t W,
+                              int32_t H, sbp_map **out);
+int32_t sbp_map_destroy(sbp_map *map);
+int32_t sbp_map_info(sbp_map *map, int32_t *W, int32_t *H, int64_t *packed_bytes,
+                     int32_t *smem_resident);
+
+/* ---- 2-D image-space checker ---------------------------------------------- */
+/* replaces: ImgCollisionChecker.feasible (collisionChecker.py:147-153),
+ * batched.  P: device [n][2] fp64.  out: device n bytes (1 free / 0 blocked).
+ * flags: device int32 (nullable), SBP_FLAG_* bits are OR-ed in. */
+int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint8_t *out,
+                       int32_t *flags);
+/* replaces: ImgCollisionChecker.visible + get_line (collisionChecker.py:134-145,
+ * :155-215), batched: integer Bresenham between int()-truncated endpoints, all
+ * pixels free.  An edge with a NaN endpoint yields 0 (ValueError is caught at
+ * :143-144) and sets SBP_FLAG_NAN; +-inf sets SBP_FLAG_OVERFLOW.
+ * px_tested: device uint64 (nullable) += pixel tests actually executed. */
+int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q, int64_t n,
+                      uint8_t *out, int32_t *flags, uint64_t *px_tested);
+/* replaces: ImgCollisionChecker.get_coor_before_collision (collisionChecker.py:118-132),
+ * batched: out_xy device [n][2] int32 = first blocked pixel walking start->end,
+ * or the end pixel when the line is free. */
+int32_t sbp_first_blocked2d(sbp_map *map, const double *P, const double *Q, int64_t n,
+                            int32_t *out_xy, int32_t *flags);
+
+/* ---- 4-DoF stick arm checker ---------------------------------------------- */
+/* replaces: RobotArm4dCollisionChecker.feasible + get_pt_from_angle_and_length +
+ * _pt_feasible (collisionChecker.py:393-441), batched.  C: device [n][4] fp64
+ * (x, y, r0, r1).  out: SBP_FREE / SBP_BLOCKED / SBP_AMBIGUOUS per config. */
+int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const double *C, int64_t n,
+                         uint8_t *out, int32_t *flags);
+/* replaces: RobotArm4dCollisionChecker.visible + _interpolate_configs +
+ * create_ranges (collisionChecker.py:346-391), batched.  C1, C2: device [n][4].
+ * cfg_tested: device uint64 (nullable) += interpolated configs evaluated. */
+int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const double *C1,
+                        const double *C2, int64_t n, uint8_t *out, int32_t *flags,
+                        uint64_t *cfg_tested);
+/* Exact resolution of SBP_AMBIGUOUS entries with the host libm cos/sin (the same
+ * libm CPython's math.cos/sin call, collisionChecker.py:437-440).  All pointers
+ * HOST.  C2 == NULL resolves configs (feasible), otherwise edges (visible).
+ * Only entries equal to SBP_AMBIGUOUS are touched.  *resolved (nullable) counts them. */
+int32_t sbp_arm_resolve_host(sbp_map *map, double L0, double L1, const double *C1,
+                             const double *C2, int64_t n, uint8_t *inout,
+                             int64_t *resolved);
+
+/* ---- host-buffer forms (what the Python plugin calls for user arrays) ------
+ * Same semantics as above with HOST pointers; H2D copy, kernel(s), D2H copy and a
+ * stream synchronise happen inside.  *flags receives the SBP_FLAG_* bits.
+ * The arm forms also run sbp_arm_resolve_host, so out is 0/1 only. */
+int32_t sbp_feasible2d_host(sbp_map *map, const double *P, int64_t n, uint8_t *out,
+                            int32_t *flags);
+int32_t sbp_visible2d_host(sbp_map *map, const double *P, const double *Q, int64_t n,
+                           uint8_t *out, int32_t *flags);
+int32_t sbp_first_blocked2d_host(sbp_map *map, const double *P, const double *Q, int64_t n,
+                                 int32_t *out_xy, int32_t *flags);
+int32_t sbp_arm_feasible_host(sbp_map *map, double L0, double L1, const double *C,
+                              int64_t n, uint8_t *out, int32_t *flags, int64_t *n_ambiguous);
+int32_t sbp_arm_visible_host(sbp_map *map, double L0, double L1, const double *C1,
+                             const double *C2, int64_t n, uint8_t *out, int32_t *flags,
+                             int64_t *n_ambiguous);
+
+/* ---- node store: device-resident, append-only ------------------------------
+ * replaces: the planners' pre-allocated `poses` arrays and their appends
+ * (rrtPlanner.py:24-26, :106-113; birrtPlanner.py:24-31; rrdtPlanner.py:858-887). */
+int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, sbp_nodes **out);
+int32_t sbp_nodes_destroy(sbp_nodes *nodes);
+/* X: [m][d] fp64, row-major; on_device selects the address space of X.
+ * Grows the store (capacity doubling) when needed. */
+int32_t sbp_nodes_append(sbp_nodes *nodes, const double *X, int64_t m, int32_t on_device);
+int32_t sbp_nodes_size(sbp_nodes *nodes, int64_t *n);
+/* keep only the first n nodes (n <= size) */
+int32_t sbp_nodes_truncate(sbp_nodes *nodes, int64_t n);
+/* copy rows [first, first+count) back to HOST as [count][d] */
+int32_t sbp_nodes_read(sbp_nodes *nodes, int64_t first, int64_t count, double *out_host);
+/* same into a DEVICE buffer [count][d] (asynchronous; e.g. to query the store with
+ * its own rows, PRMPlanner.build_graph's outer loop, prmPlanner.py:91-92) */
+int32_t sbp_nodes_rows_device(sbp_nodes *nodes, int64_t first, int64_t count, double *out_device);
+
+/* replaces: RRTPlanner.find_nearest_neighbour_idx (rrtPlanner.py:268-279) for
+ * k = 1 and the np.argsort(distances)[:k] candidate lists (rrtPlanner.py:151-152,
+ * :226-227) for k > 1: brute force over all nodes, d = sqrt_rn of the
+ * left-to-right unfused sum of squares over all dims, ordered by (d, index).
+ * X: device [m][dim].  idx: device [m][k] int64, dist: device [m][k] fp64
+ * (nullable); rows are padded with -1 / +inf when size < k.  1 <= k <= 64.
+ * precision: 64 only (bit-exact); 32 is reserved. */
+int32_t sbp_nodes_knn(sbp_nodes *nodes, const double *X, int64_t m, int32_t k,
+                      int32_t precision, int64_t *idx, double *dist);
+/* replaces: prmPlanner.nearest_neighbours (prmPlanner.py:28-44; FULL, LT), the
+ * radius gates of choose_least_cost_parent / rewire (rrtPlanner.py:177-181,
+ * :236-239; XY, LE), birrtPlanner.py:82-85, rrdtPlanner.py:704-713.
+ * CSR output, node indices ascending within each row.  row_ptr: device [m+1]
+ * int64.  idx: device [idx_capacity] int64 (nullable -> count only).
+ * *needed: device int64 = total number of neighbours.  When needed >
+ * idx_capacity only row_ptr / needed are valid. */
+int32_t sbp_nodes_near(sbp_nodes *nodes, const double *X, int64_t m, double r,
+                       int32_t metric, int32_t closed, int64_t *row_ptr, int64_t *idx,
+                       int64_t idx_capacity, int64_t *needed);
+
+/* host-buffer forms of the queries */
+int32_t sbp_nodes_knn_host(sbp_nodes *nodes, const double *X, int64_t m, int32_t k,
+                           int32_t precision, int64_t *idx, double *dist);
+/* two-call protocol: idx == NULL returns row_ptr and *needed only */
+int32_t sbp_nodes_near_host(sbp_nodes *nodes, const double *X, int64_t m, double r,
+                            int32_t metric, int32_t closed, int64_t *row_ptr, int64_t *idx,
+                            int64_t idx_capacity, int64_t *needed);
+
+/* ---- batched planner primitives ------------------------------------------- */
+/* Gather the endpoints of candidate edges (i -> nbr[i][j]) from the node store
+ * into P, Q ([m*k][d] device) for a following sbp_visible2d / sbp_arm_visible:
+ * the batched form of PRMPlanner.build_graph's inner loop (prmPlanner.py:91-101).
+ * Entries with nbr < 0 or nbr == self produce valid = 0 and a degenerate edge. */
+int32_t sbp_nodes_gather_edges(sbp_nodes *nodes, const int64_t *nbr, int64_t m, int32_t k,
+                               int64_t first_row, double *P, double *Q, uint8_t *valid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBP_GPU_H */

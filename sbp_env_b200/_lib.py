@@ -1,0 +1,104 @@
+"""ctypes binding of ``libsbpgpu.so`` (C ABI declared in ``include/sbp_gpu.h``).
+
+There is deliberately no fallback: if the CUDA library is missing or no B200 is
+visible, every entry point of this package raises.  Nothing here (or anywhere in
+the package) imports ``oracle/``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsbpgpu.so")
+
+SBP_OK = 0
+FLAG_NAN = 1
+FLAG_OVERFLOW = 2
+FREE, BLOCKED, AMBIGUOUS = 1, 0, 2
+METRIC = {"full": 0, "xy": 1}
+
+
+class SbpGpuError(RuntimeError):
+    """A libsbpgpu call failed (or the library / a CUDA device is missing)."""
+
+
+_lib = None
+
+_i32, _i64, _dbl, _vp = C.c_int32, C.c_int64, C.c_double, C.c_void_p
+_pp = C.POINTER(C.c_void_p)
+
+# name -> argtypes; every function returns int32 status unless listed in _RESTYPE
+_SIGNATURES = {
+    "sbp_abi_version": [],
+    "sbp_last_error": [],
+    "sbp_ctx_create": [_i32, _vp, _pp],
+    "sbp_ctx_destroy": [_vp],
+    "sbp_ctx_set_stream": [_vp, _vp],
+    "sbp_ctx_sync": [_vp],
+    "sbp_ctx_info": [_vp, C.POINTER(_i32), C.POINTER(_i64)],
+    "sbp_map_create": [_vp, _vp, _i32, _i32, _pp],
+    "sbp_map_create_device": [_vp, _vp, _i32, _i32, _pp],
+    "sbp_map_destroy": [_vp],
+    "sbp_map_info": [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i64), C.POINTER(_i32)],
+    "sbp_feasible2d": [_vp, _vp, _i64, _vp, _vp],
+    "sbp_visible2d": [_vp, _vp, _vp, _i64, _vp, _vp, _vp],
+    "sbp_first_blocked2d": [_vp, _vp, _vp, _i64, _vp, _vp],
+    "sbp_arm_feasible": [_vp, _dbl, _dbl, _vp, _i64, _vp, _vp],
+    "sbp_arm_visible": [_vp, _dbl, _dbl, _vp, _vp, _i64, _vp, _vp, _vp],
+    "sbp_arm_resolve_host": [_vp, _dbl, _dbl, _vp, _vp, _i64, _vp, C.POINTER(_i64)],
+    "sbp_feasible2d_host": [_vp, _vp, _i64, _vp, C.POINTER(_i32)],
+    "sbp_visible2d_host": [_vp, _vp, _vp, _i64, _vp, C.POINTER(_i32)],
+    "sbp_first_blocked2d_host": [_vp, _vp, _vp, _i64, _vp, C.POINTER(_i32)],
+    "sbp_arm_feasible_host": [_vp, _dbl, _dbl, _vp, _i64, _vp, C.POINTER(_i32), C.POINTER(_i64)],
+    "sbp_arm_visible_host": [_vp, _dbl, _dbl, _vp, _vp, _i64, _vp, C.POINTER(_i32), C.POINTER(_i64)],
+    "sbp_nodes_create": [_vp, _i32, _i64, _pp],
+    "sbp_nodes_destroy": [_vp],
+    "sbp_nodes_append": [_vp, _vp, _i64, _i32],
+    "sbp_nodes_size": [_vp, C.POINTER(_i64)],
+    "sbp_nodes_truncate": [_vp, _i64],
+    "sbp_nodes_read": [_vp, _i64, _i64, _vp],
+    "sbp_nodes_rows_device": [_vp, _i64, _i64, _vp],
+    "sbp_nodes_knn": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "sbp_nodes_near": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, _vp],
+    "sbp_nodes_knn_host": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "sbp_nodes_near_host": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, C.POINTER(_i64)],
+    "sbp_nodes_gather_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp],
+    "sbp_tune": [C.c_char_p, _i64],
+}
+_RESTYPE = {"sbp_last_error": C.c_char_p}
+
+#: entry points declared in include/sbp_gpu.h (sbp_tune is an undeclared tuning hook)
+ABI_SYMBOLS = tuple(k for k in _SIGNATURES if k != "sbp_tune")
+
+
+def load():
+    """Load libsbpgpu.so; raise ``SbpGpuError`` (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SbpGpuError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  sbp_env_b200 has no CPU implementation."
+        )
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover - depends on the box
+        raise SbpGpuError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, argtypes in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, _i32)
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    msg = load().sbp_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != SBP_OK:
+        raise SbpGpuError(f"{what or 'libsbpgpu'} failed (status {rc}): {last_error()}")

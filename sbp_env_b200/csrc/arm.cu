@@ -1,0 +1,397 @@
+// arm.cu -- K3: 4-DoF stick-arm link sweeps against the occupancy grid.
+//
+// Reference behaviour restated (file:line under /root/reference/sbp_env/):
+//   RobotArm4dCollisionChecker.feasible               collisionChecker.py:404-426
+//   .get_pt_from_angle_and_length                     collisionChecker.py:428-441
+//   ._pt_feasible                                     collisionChecker.py:393-402
+//   ._get_line (Bresenham, list variant)              collisionChecker.py:443-503
+//   .create_ranges / ._interpolate_configs / .visible collisionChecker.py:346-391
+//
+// fp64 policy.  The angle lerp is three separately rounded fp64
+// operations and is reproduced bit-for-bit with __dmul_rn/__dadd_rn.  The forward
+// kinematics go through cos/sin: the reference calls glibc (<= 1 ulp), the device
+// libdevice (<= 2 ulp), so the two can differ in the last bits of
+// pt + L*cos(a).  That only matters when such a coordinate lies within a few ulp
+// of an integer, where int() may truncate differently.  Every FK coordinate is
+// therefore compared with a guard band ~100x wider than the worst-case
+// discrepancy; a config inside the band is not decided on the device.  The result
+// byte is SBP_AMBIGUOUS unless another, unambiguous config already blocks the
+// edge, and sbp_arm_resolve_host() settles it with the host libm (the very libm
+// CPython's math.cos/sin call).  On uniform random configs the band is hit
+// ~1e-8 of the time; exact multiples of pi/2 on integer bases hit it always.
+#include <math.h>
+
+#include "common.cuh"
+
+// Sequential Bresenham walk of one link; all pixels free?  Order is irrelevant
+// for the boolean, so the canonical traversal is walked directly.
+template <bool SMEM>
+__device__ __forceinline__ bool link_free(const uint32_t *words, const MapView &mv, int x1, int y1,
+                                          int x2, int y2) {
+    int dx = x2 - x1, dy = y2 - y1;
+    bool steep = abs(dy) > abs(dx);                     // :467
+    int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;     // :470-472
+    int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+    if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }  // :476-479
+    int da = a2 - a1, adb = abs(b2 - b1);               // :482-483
+    int err = da >> 1;                                  // int(dx / 2.0), :486
+    int ystep = b1 < b2 ? 1 : -1;                       // :487
+    int b = b1;
+    for (int a = a1; a <= a2; ++a) {                    // :492-498
+        int x = steep ? b : a, y = steep ? a : b;
+        if (!map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H))) return false;
+        err -= adb;
+        if (err < 0) { b += ystep; err += da; }
+    }
+    return true;
+}
+
+// |v - nearest integer| within the guard band?  The band covers the discrepancy
+// between glibc and libdevice cos/sin propagated through pt + L*c (see header).
+__device__ __forceinline__ bool near_pixel_boundary(double v, double L) {
+    double guard = (fabs(v) + fabs(L) + 1.0) * 5.6843418860808015e-14;  // 2^-44
+    return fabs(v - rint(v)) <= guard;
+}
+
+// One configuration: 1 free, 0 blocked, 2 ambiguous.  flag receives SBP_FLAG_*.
+template <bool SMEM>
+__device__ __forceinline__ int arm_config(const uint32_t *words, const MapView &mv, double L0,
+                                          double L1, double bx, double by, double r0, double r1,
+                                          int &flag) {
+    // math.cos(+-inf) raises ValueError("math domain error"); nan propagates to int(nan)
+    if (isinf(r0) || isinf(r1) || r0 != r0 || r1 != r1) { flag |= SBP_FLAG_NAN; return 0; }
+    double s0, c0, s1, c1;
+    sincos(r0, &s0, &c0);
+    sincos(r1, &s1, &c1);
+    double p2x = __dadd_rn(bx, __dmul_rn(L0, c0));      // :438
+    double p2y = __dadd_rn(by, __dmul_rn(L0, s0));      // :439
+    double p3x = __dadd_rn(p2x, __dmul_rn(L1, c1));     // :417-419
+    double p3y = __dadd_rn(p2y, __dmul_rn(L1, s1));
+    TruncResult tbx = trunc_index(bx, mv.W), tby = trunc_index(by, mv.H);
+    int f = tbx.flag ? tbx.flag : tby.flag;
+    if (f) { flag |= f; return 0; }
+    // the base pixel is exact: when it is outside the index range the first tested
+    // pixel fails whatever the FK says
+    if (!tbx.in_range || !tby.in_range) return 0;
+    bool amb1 = near_pixel_boundary(p2x, L0) || near_pixel_boundary(p2y, L0);
+    TruncResult t2x = trunc_index(p2x, mv.W), t2y = trunc_index(p2y, mv.H);
+    if (t2x.flag || t2y.flag) { flag |= t2x.flag ? t2x.flag : t2y.flag; return 0; }
+    if (amb1) return 2;
+    if (!t2x.in_range || !t2y.in_range) return 0;       // end pixel of link 1 is out of range
+    if (!link_free<SMEM>(words, mv, tbx.i, tby.i, t2x.i, t2y.i)) return 0;   // :413-415
+    bool amb2 = near_pixel_boundary(p3x, L1) || near_pixel_boundary(p3y, L1);
+    TruncResult t3x = trunc_index(p3x, mv.W), t3y = trunc_index(p3y, mv.H);
+    if (t3x.flag || t3y.flag) { flag |= t3x.flag ? t3x.flag : t3y.flag; return 0; }
+    if (amb2) return 2;
+    if (!t3x.in_range || !t3y.in_range) return 0;
+    return link_free<SMEM>(words, mv, t2x.i, t2y.i, t3x.i, t3y.i) ? 1 : 0;   // :422-424
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_arm_feasible(MapView mv, double L0, double L1, const double4 *__restrict__ C, int64_t n,
+               uint8_t *__restrict__ out, int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    int myflag = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double4 c = C[i];
+        out[i] = (uint8_t)arm_config<SMEM>(words, mv, L0, L1, c.x, c.y, c.z, c.w, myflag);
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
+// visible: a group of G lanes owns one edge; lane j evaluates interpolated
+// configs j, j+G, ... (one config = base pixel o of the base Bresenham line in
+// start->end order + lerped angles), ballot for the early exit.
+template <int G, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(1024)
+k_arm_visible(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
+              const double4 *__restrict__ C2, int64_t n, uint8_t *__restrict__ out,
+              int32_t *__restrict__ flags, unsigned long long *__restrict__ cfg_tested) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int j = lane & (G - 1);
+    const int gshift = lane & ~(G - 1);
+    const unsigned gmask_bits = G == 32 ? FULL : ((1u << G) - 1u);
+    const int64_t groups_per_grid = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t n_round = ((n + (32 / G) - 1) / (32 / G)) * (32 / G);
+    int myflag = 0;
+    unsigned long long tested = 0;
+
+    for (int64_t eidx = gid; eidx < n_round; eidx += groups_per_grid) {
+        const bool valid = eidx < n;
+        double4 a = make_double4(0, 0, 0, 0), b = make_double4(0, 0, 0, 0);
+        if (valid) { a = C1[eidx]; b = C2[eidx]; }
+        // base line between int()-truncated base points (:373, :461-462)
+        TruncResult t0 = trunc_index(a.x, mv.W), t1 = trunc_index(a.y, mv.H);
+        TruncResult t2 = trunc_index(b.x, mv.W), t3 = trunc_index(b.y, mv.H);
+        int f = t0.flag ? t0.flag : t1.flag ? t1.flag : t2.flag ? t2.flag : t3.flag;
+        if (!f && (isinf(a.z) || isinf(a.w) || isinf(b.z) || isinf(b.w) || a.z != a.z ||
+                   a.w != a.w || b.z != b.z || b.w != b.w))
+            f = SBP_FLAG_NAN;
+        if (valid) myflag |= f;
+        // config 0 / config N-1 sit on the base end pixels: an out-of-range base
+        // endpoint blocks the edge
+        bool walk = valid && !f && t0.in_range && t1.in_range && t2.in_range && t3.in_range;
+        int x1 = t0.i, y1 = t1.i, x2 = t2.i, y2 = t3.i;
+        int dx = x2 - x1, dy = y2 - y1;
+        bool steep = abs(dy) > abs(dx);
+        int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+        int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+        bool swapped = a1 > a2;
+        if (swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+        uint32_t da = (uint32_t)(a2 - a1), adb = (uint32_t)abs(b2 - b1);
+        int ystep = b1 < b2 ? 1 : -1;
+        const uint32_t npx = da + 1u;
+        const uint32_t N = npx < 2u ? 2u : npx;                     // :375-377
+        const uint32_t c = da ? da - 1u - (da >> 1) : 0u;
+        // create_ranges (:363-364): steps = (1.0/(N-1))*(stop-start); rot = steps*i + start
+        const double inv = __ddiv_rn(1.0, (double)(N - 1u));
+        const double st0 = __dmul_rn(inv, __dsub_rn(b.z, a.z));
+        const double st1 = __dmul_rn(inv, __dsub_rn(b.w, a.w));
+
+        int state = walk ? 1 : 0;   // 1 free so far, 0 blocked, 2 ambiguous seen
+        bool done = !walk;
+        uint32_t o = (uint32_t)j;
+        while (true) {
+            bool act = !done && o < N;
+            int r = 1;
+            if (act) {
+                uint32_t po = npx == 1u ? 0u : o;                   // duplicated single pixel
+                uint64_t ci = swapped ? (uint64_t)(npx - 1u - po) : (uint64_t)po;
+                uint32_t k = da ? (uint32_t)((ci * adb + c) / da) : 0u;
+                int aa = a1 + (int)ci, bb = b1 + ystep * (int)k;
+                double bx = (double)(steep ? bb : aa), by = (double)(steep ? aa : bb);
+                double r0 = __dadd_rn(__dmul_rn(st0, (double)o), a.z);
+                double r1 = __dadd_rn(__dmul_rn(st1, (double)o), a.w);
+                r = arm_config<SMEM>(words, mv, L0, L1, bx, by, r0, r1, myflag);
+                if (COUNT) tested += 1ull;
+            }
+            unsigned blocked = (__ballot_sync(FULL, act && r == 0) >> gshift) & gmask_bits;
+            unsigned ambig = (__ballot_sync(FULL, act && r == 2) >> gshift) & gmask_bits;
+            if (ambig && state == 1) state = 2;
+            if (blocked) { state = 0; done = true; }     // an unambiguous block decides the edge
+            o += (uint32_t)G;
+            if (o >= N) done = true;
+            if (!__any_sync(FULL, !done)) break;
+        }
+        if (valid && j == 0) out[eidx] = (uint8_t)state;
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(FULL, tested, o);
+        if (lane == 0 && tested && cfg_tested) atomicAdd(cfg_tested, tested);
+    }
+}
+
+// ------------------------------------------------------------ launchers -----
+extern int g_force_global;
+int g_arm_group = 0;   // 0 = auto
+
+static void arm_cfg(const sbp_map *m, bool smem, int &grid, int &threads, size_t &bytes) {
+    const sbp_ctx *ctx = m->ctx;
+    if (smem) {
+        bytes = (size_t)m->packed_bytes;
+        int per_sm = (int)((size_t)(228 * 1024) / (bytes + 2048));
+        per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
+        threads = per_sm <= 2 ? 1024 : 512;
+        grid = ctx->sm_count * per_sm;
+    } else {
+        bytes = 0;
+        threads = 256;
+        grid = ctx->sm_count * 8;
+    }
+}
+
+extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const double *C,
+                                    int64_t n, uint8_t *out, int32_t *flags) {
+    SBP_REQUIRE(map && (n == 0 || (C && out)), "sbp_arm_feasible: NULL argument");
+    SBP_REQUIRE(n >= 0, "sbp_arm_feasible: n < 0");
+    if (n == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    bool smem = !g_force_global && map->smem_resident &&
+                n * 64 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
+    int grid, threads; size_t bytes;
+    arm_cfg(map, smem, grid, threads, bytes);
+    int64_t need = (n + threads - 1) / threads;
+    if (need < grid) grid = (int)need;
+    if (smem) {
+        if (bytes > 48 * 1024)
+            SBP_CUDA(cudaFuncSetAttribute(k_arm_feasible<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        k_arm_feasible<true><<<grid, threads, bytes, ctx->stream>>>(map->view, L0, L1, (const double4 *)C, n, out, flags);
+    } else {
+        k_arm_feasible<false><<<grid, threads, 0, ctx->stream>>>(map->view, L0, L1, (const double4 *)C, n, out, flags);
+    }
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+template <int G>
+static int32_t launch_arm_visible(sbp_map *map, double L0, double L1, const double *C1,
+                                  const double *C2, int64_t n, uint8_t *out, int32_t *flags,
+                                  unsigned long long *cnt, bool smem) {
+    sbp_ctx *ctx = map->ctx;
+    int grid, threads; size_t bytes;
+    arm_cfg(map, smem, grid, threads, bytes);
+    int64_t need = (n * G + threads - 1) / threads;
+    if (need < grid) grid = (int)need;
+    const double4 *c1 = (const double4 *)C1, *c2 = (const double4 *)C2;
+#define SBP_LAUNCH_ARM(SM, CT)                                                                    \
+    do {                                                                                           \
+        if (bytes > 48 * 1024)                                                                     \
+            SBP_CUDA(cudaFuncSetAttribute(k_arm_visible<G, SM, CT>,                                \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+        k_arm_visible<G, SM, CT><<<grid, threads, bytes, ctx->stream>>>(map->view, L0, L1, c1, c2, \
+                                                                        n, out, flags, cnt);       \
+    } while (0)
+    if (smem) { if (cnt) SBP_LAUNCH_ARM(true, true); else SBP_LAUNCH_ARM(true, false); }
+    else      { if (cnt) SBP_LAUNCH_ARM(false, true); else SBP_LAUNCH_ARM(false, false); }
+#undef SBP_LAUNCH_ARM
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const double *C1,
+                                   const double *C2, int64_t n, uint8_t *out, int32_t *flags,
+                                   uint64_t *cfg_tested) {
+    SBP_REQUIRE(map && (n == 0 || (C1 && C2 && out)), "sbp_arm_visible: NULL argument");
+    SBP_REQUIRE(n >= 0, "sbp_arm_visible: n < 0");
+    if (n == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    bool smem = !g_force_global && map->smem_resident &&
+                n * 64 >= map->packed_bytes * (int64_t)ctx->sm_count / 16;
+    unsigned long long *cnt = (unsigned long long *)cfg_tested;
+    int G = g_arm_group ? g_arm_group : 8;
+    switch (G) {
+        case 4: return launch_arm_visible<4>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
+        case 8: return launch_arm_visible<8>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
+        case 16: return launch_arm_visible<16>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
+        case 32: return launch_arm_visible<32>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
+        default: sbp_set_error("arm_group must be 4, 8, 16 or 32"); return SBP_ERR_ARG;
+    }
+}
+
+// ------------------------------------------- host guard-band resolution -----
+// Exact re-evaluation of the few SBP_AMBIGUOUS entries with the host libm.  This
+// is not a CPU implementation of the path: it decides only entries the device
+// declined to decide, using the host copy of the same packed map.
+namespace {
+
+struct HostMap {
+    const uint32_t *w;
+    int W, H, SX;
+    bool free_at(int64_t x, int64_t y) const {
+        if (x < -W || x >= W || y < -H || y >= H) return false;
+        if (x < 0) x += W;
+        if (y < 0) y += H;
+        uint32_t sec = (uint32_t)(y >> 4) * (uint32_t)SX + (uint32_t)(x >> 4);
+        uint32_t wi = sec * 8u + (uint32_t)(((y >> 3) & 1) * 4 + ((x >> 3) & 1) * 2 + ((y >> 2) & 1));
+        return (w[wi] >> (((y & 3) << 3) | (x & 7))) & 1u;
+    }
+};
+
+bool host_trunc(double v, int64_t &o) {
+    if (!(fabs(v) < 4.0e18)) return false;
+    o = (int64_t)v;
+    return true;
+}
+
+bool host_link_free(const HostMap &m, int64_t x1, int64_t y1, int64_t x2, int64_t y2) {
+    if (!m.free_at(x1, y1) || !m.free_at(x2, y2)) return false;   // endpoints are pixels
+    int64_t dx = x2 - x1, dy = y2 - y1;
+    bool steep = llabs(dy) > llabs(dx);
+    int64_t a1 = steep ? y1 : x1, b1 = steep ? x1 : y1, a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+    if (a1 > a2) { int64_t t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+    int64_t da = a2 - a1, adb = llabs(b2 - b1), err = da / 2, ystep = b1 < b2 ? 1 : -1, b = b1;
+    for (int64_t a = a1; a <= a2; ++a) {
+        if (!m.free_at(steep ? b : a, steep ? a : b)) return false;
+        err -= adb;
+        if (err < 0) { b += ystep; err += da; }
+    }
+    return true;
+}
+
+bool host_config_free(const HostMap &m, double L0, double L1, double bx, double by, double r0,
+                      double r1) {
+    double p2x = bx + L0 * cos(r0), p2y = by + L0 * sin(r0);
+    int64_t ax, ay, cx, cy, ex, ey;
+    if (!host_trunc(bx, ax) || !host_trunc(by, ay) || !host_trunc(p2x, cx) || !host_trunc(p2y, cy))
+        return false;
+    if (!host_link_free(m, ax, ay, cx, cy)) return false;
+    double p3x = p2x + L1 * cos(r1), p3y = p2y + L1 * sin(r1);
+    if (!host_trunc(p3x, ex) || !host_trunc(p3y, ey)) return false;
+    return host_link_free(m, cx, cy, ex, ey);
+}
+
+bool host_edge_free(const HostMap &m, double L0, double L1, const double *a, const double *b) {
+    int64_t x1, y1, x2, y2;
+    if (!host_trunc(a[0], x1) || !host_trunc(a[1], y1) || !host_trunc(b[0], x2) ||
+        !host_trunc(b[1], y2))
+        return false;
+    if (!m.free_at(x1, y1) || !m.free_at(x2, y2)) return false;
+    int64_t dx = x2 - x1, dy = y2 - y1;
+    bool steep = llabs(dy) > llabs(dx);
+    int64_t a1 = steep ? y1 : x1, b1 = steep ? x1 : y1, a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+    bool swapped = a1 > a2;
+    if (swapped) { int64_t t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+    int64_t da = a2 - a1, adb = llabs(b2 - b1), ystep = b1 < b2 ? 1 : -1;
+    int64_t npx = da + 1, N = npx < 2 ? 2 : npx, c = da ? da - 1 - da / 2 : 0;
+    double inv = 1.0 / (double)(N - 1);
+    double st0 = inv * (b[2] - a[2]), st1 = inv * (b[3] - a[3]);
+    for (int64_t o = 0; o < N; ++o) {
+        int64_t po = npx == 1 ? 0 : o;
+        int64_t ci = swapped ? npx - 1 - po : po;
+        int64_t k = da ? (ci * adb + c) / da : 0;
+        int64_t aa = a1 + ci, bb = b1 + ystep * k;
+        double m0 = st0 * (double)o, m1 = st1 * (double)o;   // separately rounded (-fmad=false)
+        double r0 = m0 + a[2], r1 = m1 + a[3];
+        if (!host_config_free(m, L0, L1, (double)(steep ? bb : aa), (double)(steep ? aa : bb), r0, r1))
+            return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+static int32_t ensure_host_words(sbp_map *map) {
+    if (!map->h_words.empty()) return SBP_OK;
+    map->h_words.resize(map->view.n_words);
+    SBP_CUDA(cudaMemcpyAsync(map->h_words.data(), map->d_words, (size_t)map->view.n_words * 4,
+                             cudaMemcpyDeviceToHost, map->ctx->stream));
+    SBP_CUDA(cudaStreamSynchronize(map->ctx->stream));
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_arm_resolve_host(sbp_map *map, double L0, double L1, const double *C1,
+                                        const double *C2, int64_t n, uint8_t *inout,
+                                        int64_t *resolved) {
+    SBP_REQUIRE(map && (n == 0 || (C1 && inout)), "sbp_arm_resolve_host: NULL argument");
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (inout[i] != SBP_AMBIGUOUS) continue;
+        if (cnt == 0) {
+            int32_t rc = ensure_host_words(map);
+            if (rc) return rc;
+        }
+        HostMap hm{map->h_words.data(), map->view.W, map->view.H, map->view.SX};
+        const double *a = C1 + 4 * i;
+        bool ok = C2 ? host_edge_free(hm, L0, L1, a, C2 + 4 * i)
+                     : host_config_free(hm, L0, L1, a[0], a[1], a[2], a[3]);
+        inout[i] = ok ? SBP_FREE : SBP_BLOCKED;
+        ++cnt;
+    }
+    if (resolved) *resolved = cnt;
+    return SBP_OK;
+}

@@ -1,0 +1,358 @@
+// collide2d.cu -- K1 point feasibility, K2 segment-vs-grid visibility (integer
+// Bresenham), K2b first-blocked-pixel, for the 2-D image-space checker.
+//
+// Reference behaviour restated by these kernels (file:line under
+// /root/reference/sbp_env/):
+//   ImgCollisionChecker.feasible                     collisionChecker.py:147-153
+//   ImgCollisionChecker.visible                      collisionChecker.py:134-145
+//   ImgCollisionChecker.get_line (Bresenham)         collisionChecker.py:155-215
+//   ImgCollisionChecker.get_coor_before_collision    collisionChecker.py:118-132
+//
+// Bresenham without the serial loop.  After the reference's steep swap (:179-184)
+// and order swap (:187-191) the i-th pixel of the canonical traversal is
+//     a_i = a1 + i,   b_i = b1 + ystep * floor((i*|db| + c) / da),
+//     c = da - 1 - floor(da / 2),  da = a2 - a1 >= |db|
+// (error starts at floor(da/2) (:198), loses |db| per step and gains da whenever
+// it went negative (:207-210), so it stays in [0, da) and the number of minor
+// steps before pixel i is the smallest k with floor(da/2) - i*|db| + k*da >= 0).
+// A group of G lanes owns one edge; lane j tests pixels j, j+G, ... and carries
+// (k, rem) = divmod(i*|db| + c, da) forward by adding divmod(G*|db|, da), so the
+// inner loop has no division.  A ballot per step gives the early exit.
+#include "common.cuh"
+
+struct Edge2D {
+    int a1, b1;        // canonical start (major, minor)
+    uint32_t da, adb;  // major extent, |minor extent|
+    int ystep;
+    bool steep, swapped;
+    bool walk;         // both endpoints inside the index range: pixels must be tested
+    int flag;          // SBP_FLAG_* bits
+    int x1, y1, x2, y2;
+};
+
+__device__ __forceinline__ Edge2D make_edge(double px, double py, double qx, double qy, int W,
+                                            int H) {
+    Edge2D e;
+    TruncResult t0 = trunc_index(px, W), t1 = trunc_index(py, H);   // x1, y1 = map(int, start)
+    TruncResult t2 = trunc_index(qx, W), t3 = trunc_index(qy, H);   // x2, y2 = map(int, end)
+    // CPython raises at the first offending conversion (:173-174)
+    e.flag = t0.flag ? t0.flag : t1.flag ? t1.flag : t2.flag ? t2.flag : t3.flag;
+    // both endpoints are members of the pixel list (:204-206): an endpoint outside
+    // the index range makes the all-of False without walking
+    e.walk = t0.in_range && t1.in_range && t2.in_range && t3.in_range;
+    e.x1 = t0.i; e.y1 = t1.i; e.x2 = t2.i; e.y2 = t3.i;
+    int dx = e.x2 - e.x1, dy = e.y2 - e.y1;
+    e.steep = abs(dy) > abs(dx);                                      // :179
+    int a1 = e.steep ? e.y1 : e.x1, b1 = e.steep ? e.x1 : e.y1;       // :182-184
+    int a2 = e.steep ? e.y2 : e.x2, b2 = e.steep ? e.x2 : e.y2;
+    e.swapped = a1 > a2;                                              // :188-191
+    if (e.swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+    e.a1 = a1; e.b1 = b1;
+    e.da = (uint32_t)(a2 - a1);                                       // :194
+    e.adb = (uint32_t)abs(b2 - b1);                                   // :195, :207
+    e.ystep = b1 < b2 ? 1 : -1;                                       // :199
+    return e;
+}
+
+// ---------------------------------------------------------------- K1 -------
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_feasible2d(MapView mv, const double2 *__restrict__ P, int64_t n, uint8_t *__restrict__ out,
+             int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    int myflag = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double2 p = P[i];
+        TruncResult tx = trunc_index(p.x, mv.W), ty = trunc_index(p.y, mv.H);
+        int f = tx.flag ? tx.flag : ty.flag;
+        // numpy quirk pinned by tests/golden/img_cc.npz: an index in [2^63, 2^64)
+        // raises OverflowError instead of IndexError
+        if (!f && ((p.x >= 9223372036854775808.0 && p.x < 18446744073709551616.0) ||
+                   (p.y >= 9223372036854775808.0 && p.y < 18446744073709551616.0)))
+            f = SBP_FLAG_OVERFLOW;
+        myflag |= f;
+        bool ok = false;
+        if (!f && tx.in_range && ty.in_range)
+            ok = map_free<!SMEM>(words, mv.SX, wrap_index(tx.i, mv.W), wrap_index(ty.i, mv.H));
+        out[i] = ok ? 1 : 0;
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
+// ---------------------------------------------------------------- K2 -------
+template <int G, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(1024)
+k_visible2d(MapView mv, const double2 *__restrict__ P, const double2 *__restrict__ Q, int64_t n,
+            uint8_t *__restrict__ out, int32_t *__restrict__ flags,
+            unsigned long long *__restrict__ px_tested) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int j = lane & (G - 1);               // lane within the edge group
+    const int gshift = lane & ~(G - 1);         // first lane of my group
+    const unsigned gmask_bits = G == 32 ? FULL : ((1u << G) - 1u);
+    const int64_t groups_per_grid = ((int64_t)gridDim.x * blockDim.x) / G;
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    // all lanes of a warp run the same number of outer iterations
+    const int64_t n_round = ((n + (32 / G) - 1) / (32 / G)) * (32 / G);
+    int myflag = 0;
+    unsigned long long tested = 0;
+
+    for (int64_t eidx = gid; eidx < n_round; eidx += groups_per_grid) {
+        const bool valid = eidx < n;
+        double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+        if (valid) { p = P[eidx]; q = Q[eidx]; }
+        Edge2D e = make_edge(p.x, p.y, q.x, q.y, mv.W, mv.H);
+        myflag |= valid ? e.flag : 0;
+        bool result = valid && e.walk;          // stays true until a blocked pixel shows up
+        const uint32_t npx = e.da + 1u;         // max(|dx|,|dy|) + 1 pixels (:204)
+        // lane j starts at pixel j:  (k, rem) = divmod(j*|db| + c, da)
+        uint32_t k = 0, rem = 0, sq = 0, sr = 0;
+        if (e.da != 0u) {
+            uint32_t c = e.da - 1u - (e.da >> 1);
+            uint32_t u = (uint32_t)j * e.adb + c;
+            k = u / e.da; rem = u - k * e.da;
+            uint32_t s = (uint32_t)G * e.adb;
+            sq = s / e.da; sr = s - sq * e.da;
+        }
+        uint32_t i = (uint32_t)j;
+        bool done = !result;
+        while (true) {
+            bool act = !done && i < npx;
+            bool blocked = false;
+            if (act) {
+                int a = e.a1 + (int)i;
+                int b = e.b1 + e.ystep * (int)k;
+                int x = e.steep ? b : a, y = e.steep ? a : b;       // :205
+                x = wrap_index(x, mv.W); y = wrap_index(y, mv.H);
+                blocked = !map_free<!SMEM>(words, mv.SX, x, y);     // :141, :151
+            }
+            unsigned bal = __ballot_sync(FULL, blocked);
+            if (COUNT) tested += act ? 1ull : 0ull;
+            if ((bal >> gshift) & gmask_bits) { result = false; done = true; }
+            i += (uint32_t)G;
+            k += sq; rem += sr;
+            if (rem >= e.da && e.da != 0u) { rem -= e.da; ++k; }
+            if (i >= npx) done = true;
+            if (!__any_sync(FULL, !done)) break;
+        }
+        if (valid && j == 0) out[eidx] = result ? 1 : 0;
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(FULL, tested, o);
+        if (lane == 0 && tested && px_tested) atomicAdd(px_tested, tested);
+    }
+}
+
+// --------------------------------------------------------------- K2b -------
+// First blocked pixel in start->end order (or the end pixel).  One warp per edge,
+// lanes take consecutive ORIGINAL indices o; the canonical index is o or
+// npx-1-o when the order swap happened (points.reverse(), :213-214).  Unlike
+// `visible`, the walk must be followed across the edge of the index range (the
+// reported pixel is the first one that is out of range or blocked, un-wrapped as
+// get_line produced it), so endpoints are truncated to wide integers here;
+// |coordinate| >= 2^30 is reported as unsupported (INT32_MIN sentinel) -- the
+// reference would have to materialise a list of >= 2^30 tuples for such a call.
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_first_blocked2d(MapView mv, const double2 *__restrict__ P, const double2 *__restrict__ Q,
+                  int64_t n, int32_t *__restrict__ out_xy, int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double LIM = 1073741824.0;  // 2^30
+    int myflag = 0;
+    for (int64_t eidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; eidx < n;
+         eidx += warps) {
+        double2 p = P[eidx], q = Q[eidx];
+        double v[4] = {p.x, p.y, q.x, q.y};
+        int flag = 0;
+        bool wide_ok = true;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (!flag) flag = v[t] != v[t] ? SBP_FLAG_NAN : isinf(v[t]) ? SBP_FLAG_OVERFLOW : 0;
+            wide_ok = wide_ok && (fabs(v[t]) < LIM);
+        }
+        myflag |= flag;
+        int rx = INT32_MIN, ry = INT32_MIN;
+        if (!flag && wide_ok) {
+            int x1 = __double2int_rz(v[0]), y1 = __double2int_rz(v[1]);
+            int x2 = __double2int_rz(v[2]), y2 = __double2int_rz(v[3]);
+            int dx = x2 - x1, dy = y2 - y1;
+            bool steep = abs(dy) > abs(dx);
+            int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+            int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+            bool swapped = a1 > a2;
+            if (swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+            uint32_t da = (uint32_t)(a2 - a1), adb = (uint32_t)abs(b2 - b1);
+            int ystep = b1 < b2 ? 1 : -1;
+            const int64_t npx = (int64_t)da + 1;
+            const uint32_t c = da ? da - 1u - (da >> 1) : 0u;
+            rx = x2; ry = y2;                      // free line: endPos = last pixel (:127-132)
+            for (int64_t base = 0; base < npx; base += 32) {
+                int64_t o = base + lane;
+                bool blocked = false;
+                int x = 0, y = 0;
+                if (o < npx) {
+                    uint64_t ci = swapped ? (uint64_t)(npx - 1 - o) : (uint64_t)o;
+                    uint32_t k = da ? (uint32_t)((ci * adb + c) / da) : 0u;
+                    int a = a1 + (int)ci, b = b1 + ystep * (int)k;
+                    x = steep ? b : a; y = steep ? a : b;
+                    bool inr = x >= -mv.W && x < mv.W && y >= -mv.H && y < mv.H;
+                    blocked = !inr || !map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W),
+                                                       wrap_index(y, mv.H));
+                }
+                unsigned bal = __ballot_sync(FULL, blocked);
+                if (bal) {
+                    int src = __ffs(bal) - 1;
+                    rx = __shfl_sync(FULL, x, src);
+                    ry = __shfl_sync(FULL, y, src);
+                    break;
+                }
+            }
+        }
+        if (lane == 0) { out_xy[2 * eidx] = rx; out_xy[2 * eidx + 1] = ry; }
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
+// ------------------------------------------------------------ launchers -----
+struct LaunchCfg { int grid, threads; size_t smem; };
+
+static LaunchCfg cfg_for(const sbp_map *m, bool smem_path) {
+    LaunchCfg c;
+    const sbp_ctx *ctx = m->ctx;
+    if (smem_path) {
+        c.smem = (size_t)m->packed_bytes;
+        int per_sm = (int)((size_t)(228 * 1024) / (c.smem + 2048));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        c.threads = per_sm <= 2 ? 1024 : 512;
+        c.grid = ctx->sm_count * per_sm;
+    } else {
+        c.smem = 0;
+        c.threads = 256;
+        c.grid = ctx->sm_count * 8;
+    }
+    return c;
+}
+
+template <typename K>
+static int32_t set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024)
+        SBP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint8_t *out,
+                                  int32_t *flags) {
+    SBP_REQUIRE(map && (n == 0 || (P && out)), "sbp_feasible2d: NULL argument");
+    SBP_REQUIRE(n >= 0, "sbp_feasible2d: n < 0");
+    if (n == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    // staging the map pays off only when the batch is large compared to the map
+    bool smem = map->smem_resident && n * 16 >= map->packed_bytes * (int64_t)ctx->sm_count;
+    LaunchCfg c = cfg_for(map, smem);
+    int64_t need = (n + c.threads - 1) / c.threads;
+    if (need < c.grid) c.grid = (int)need;
+    if (smem) {
+        int32_t rc = set_smem(k_feasible2d<true>, c.smem);
+        if (rc) return rc;
+        k_feasible2d<true><<<c.grid, c.threads, c.smem, ctx->stream>>>(map->view, (const double2 *)P, n, out, flags);
+    } else {
+        k_feasible2d<false><<<c.grid, c.threads, 0, ctx->stream>>>(map->view, (const double2 *)P, n, out, flags);
+    }
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+int g_visible_group = 0;   // 0 = auto; 4/8/16/32 force a group width (tuning knob)
+int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
+
+extern "C" int32_t sbp_tune(const char *key, int64_t value) {
+    if (!strcmp(key, "visible_group")) { g_visible_group = (int)value; return SBP_OK; }
+    if (!strcmp(key, "force_global")) { g_force_global = (int)value; return SBP_OK; }
+    sbp_set_error("sbp_tune: unknown key %s", key);
+    return SBP_ERR_ARG;
+}
+
+template <int G>
+static int32_t launch_visible(sbp_map *map, const double *P, const double *Q, int64_t n,
+                              uint8_t *out, int32_t *flags, unsigned long long *px, bool smem) {
+    sbp_ctx *ctx = map->ctx;
+    LaunchCfg c = cfg_for(map, smem);
+    int64_t need = (n * G + c.threads - 1) / c.threads;
+    if (need < c.grid) c.grid = (int)need;
+    const double2 *p2 = (const double2 *)P, *q2 = (const double2 *)Q;
+#define SBP_LAUNCH_VIS(SM, CT)                                                                   \
+    do {                                                                                          \
+        int32_t rc = set_smem(k_visible2d<G, SM, CT>, c.smem);                                    \
+        if (rc) return rc;                                                                        \
+        k_visible2d<G, SM, CT><<<c.grid, c.threads, c.smem, ctx->stream>>>(map->view, p2, q2, n,  \
+                                                                            out, flags, px);      \
+    } while (0)
+    if (smem) { if (px) SBP_LAUNCH_VIS(true, true); else SBP_LAUNCH_VIS(true, false); }
+    else      { if (px) SBP_LAUNCH_VIS(false, true); else SBP_LAUNCH_VIS(false, false); }
+#undef SBP_LAUNCH_VIS
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q, int64_t n,
+                                 uint8_t *out, int32_t *flags, uint64_t *px_tested) {
+    SBP_REQUIRE(map && (n == 0 || (P && Q && out)), "sbp_visible2d: NULL argument");
+    SBP_REQUIRE(n >= 0, "sbp_visible2d: n < 0");
+    if (n == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    bool smem = !g_force_global && map->smem_resident &&
+                n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
+    unsigned long long *px = (unsigned long long *)px_tested;
+    int G = g_visible_group ? g_visible_group : 8;
+    switch (G) {
+        case 4: return launch_visible<4>(map, P, Q, n, out, flags, px, smem);
+        case 8: return launch_visible<8>(map, P, Q, n, out, flags, px, smem);
+        case 16: return launch_visible<16>(map, P, Q, n, out, flags, px, smem);
+        case 32: return launch_visible<32>(map, P, Q, n, out, flags, px, smem);
+        default: sbp_set_error("visible_group must be 4, 8, 16 or 32"); return SBP_ERR_ARG;
+    }
+}
+
+extern "C" int32_t sbp_first_blocked2d(sbp_map *map, const double *P, const double *Q, int64_t n,
+                                       int32_t *out_xy, int32_t *flags) {
+    SBP_REQUIRE(map && (n == 0 || (P && Q && out_xy)), "sbp_first_blocked2d: NULL argument");
+    SBP_REQUIRE(n >= 0, "sbp_first_blocked2d: n < 0");
+    if (n == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    bool smem = !g_force_global && map->smem_resident &&
+                n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
+    LaunchCfg c = cfg_for(map, smem);
+    int64_t need = (n * 32 + c.threads - 1) / c.threads;
+    if (need < c.grid) c.grid = (int)need;
+    if (smem) {
+        int32_t rc = set_smem(k_first_blocked2d<true>, c.smem);
+        if (rc) return rc;
+        k_first_blocked2d<true><<<c.grid, c.threads, c.smem, ctx->stream>>>(
+            map->view, (const double2 *)P, (const double2 *)Q, n, out_xy, flags);
+    } else {
+        k_first_blocked2d<false><<<c.grid, c.threads, 0, ctx->stream>>>(
+            map->view, (const double2 *)P, (const double2 *)Q, n, out_xy, flags);
+    }
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}

@@ -1,0 +1,188 @@
+// common.cuh -- shared host/device plumbing of libsbpgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sbp_gpu.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsbpgpu is written for sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------- errors ----
+void sbp_set_error(const char *fmt, ...);
+
+#define SBP_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            sbp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,              \
+                          cudaGetErrorString(e__));                                 \
+            return SBP_ERR_CUDA;                                                    \
+        }                                                                           \
+    } while (0)
+
+#define SBP_REQUIRE(cond, msg)                                                      \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            sbp_set_error("%s:%d %s", __FILE__, __LINE__, msg);                     \
+            return SBP_ERR_ARG;                                                     \
+        }                                                                           \
+    } while (0)
+
+// ------------------------------------------------------------- handles -----
+struct sbp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    int max_smem_optin = 0;
+    int64_t launches = 0;
+    // growable scratch for the *_host entry points and internal work-spaces
+    void *d_scratch[8] = {};
+    size_t d_scratch_bytes[8] = {};
+    int32_t *d_flags = nullptr;      // 16 x int32
+    int32_t *h_flags = nullptr;      // pinned mirror
+};
+
+int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out);
+
+// Device view of the bit-packed occupancy map.
+//   pixel (x, y), 0 <= x < W, 0 <= y < H  (the reference's `_img[x, y]`)
+//   sector  = (y >> 4) * SX + (x >> 4)               16x16 px = 32 B
+//   word32  = sector * 8 + ((y >> 3) & 1) * 4 + ((x >> 3) & 1) * 2 + ((y >> 2) & 1)
+//   bit     = ((y & 3) << 3) | (x & 7)               1 = free
+// i.e. each 64-bit pair of words is one 8x8-pixel tile, 4 tiles per sector.
+struct MapView {
+    const uint32_t *words;
+    int32_t W, H;
+    int32_t SX, SY;       // sectors per row / column
+    uint32_t n_words;     // 32-bit words (multiple of 8)
+};
+
+struct sbp_map {
+    sbp_ctx *ctx = nullptr;
+    MapView view{};
+    uint32_t *d_words = nullptr;
+    std::vector<uint32_t> h_words;   // host mirror (arm guard-band resolution)
+    int64_t packed_bytes = 0;
+    bool smem_resident = false;      // whole map fits one CTA's shared memory
+};
+
+struct sbp_nodes {
+    sbp_ctx *ctx = nullptr;
+    int d = 0;
+    int64_t n = 0;
+    int64_t capacity = 0;
+    double *d_soa = nullptr;         // [d][capacity] fp64, structure of arrays
+};
+
+// --------------------------------------------------------- device helpers ---
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t map_word_index(int SX, int x, int y) {
+    uint32_t sec = (uint32_t)(y >> 4) * (uint32_t)SX + (uint32_t)(x >> 4);
+    return sec * 8u + (uint32_t)(((y >> 3) & 1) * 4 + ((x >> 3) & 1) * 2 + ((y >> 2) & 1));
+}
+
+__device__ __forceinline__ uint32_t map_bit_index(int x, int y) {
+    return (uint32_t)(((y & 3) << 3) | (x & 7));
+}
+
+// `words` may point to shared or global memory (generic address).
+template <bool GLOBAL_LDG>
+__device__ __forceinline__ bool map_free(const uint32_t *words, int SX, int x, int y) {
+    uint32_t wi = map_word_index(SX, x, y);
+    uint32_t w = GLOBAL_LDG ? __ldg(words + wi) : words[wi];
+    return (w >> map_bit_index(x, y)) & 1u;
+}
+
+// numpy index semantics of `_img[x, y]`: valid iff -W <= i < W,
+// negative indices wrap once.  Caller guarantees the range; this only wraps.
+__device__ __forceinline__ int wrap_index(int i, int n) { return i < 0 ? i + n : i; }
+
+// CPython int(float) on the device: truncation toward zero, with the
+// non-finite classes reported.  `v` outside (-(n+1), n) is out of the index
+// range of an axis of length n whatever its exact value, so the saturating
+// conversion is only used for in-range values.
+struct TruncResult {
+    int i;          // truncated value (valid only when in_range)
+    bool in_range;  // -n <= trunc(v) < n
+    int flag;       // 0, SBP_FLAG_NAN, SBP_FLAG_OVERFLOW
+};
+
+__device__ __forceinline__ TruncResult trunc_index(double v, int n) {
+    TruncResult r;
+    r.flag = 0;
+    if (v != v) r.flag = SBP_FLAG_NAN;
+    else if (isinf(v)) r.flag = SBP_FLAG_OVERFLOW;
+    r.in_range = (v > -(double)(n + 1)) && (v < (double)n);  // false for NaN
+    r.i = r.in_range ? __double2int_rz(v) : 0;
+    return r;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine; SASS: UBLKCP) ------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                         uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+// Stage the whole packed map into shared memory with the bulk-copy engine.
+// Called by all threads of the CTA; returns after the bytes have landed.
+__device__ __forceinline__ void stage_map_to_smem(uint32_t *smap, const MapView &mv,
+                                                  uint64_t *bar) {
+    const uint32_t total = mv.n_words * 4u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, total);
+        // one bulk copy moves at most 2^20-16 bytes; chunk to be safe
+        const uint32_t CH = 32768u;
+        for (uint32_t off = 0; off < total; off += CH) {
+            uint32_t b = total - off < CH ? total - off : CH;
+            bulk_g2s((char *)smap + off, (const char *)mv.words + off, b, bar);
+        }
+    }
+    mbar_wait(bar, 0);
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,221 @@
+// map.cu -- context and occupancy-map handles; K6 map bit-pack kernel.
+//
+// Replaces the storage side of ImgCollisionChecker.__init__ /
+// RobotArm4dCollisionChecker.__init__ (/root/reference/sbp_env/collisionChecker.py
+// :101-108, :319-340): the reference keeps `_img` as a W x H float64 array of
+// {0., 1.}; here it is 1 bit per pixel in 8x8 tiles (layout in common.cuh).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void sbp_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *sbp_last_error(void) { return g_err; }
+extern "C" int32_t sbp_abi_version(void) { return SBP_ABI_VERSION; }
+
+// ------------------------------------------------------------- context -----
+extern "C" int32_t sbp_ctx_create(int32_t device, void *stream_or_null, sbp_ctx **out) {
+    SBP_REQUIRE(out != nullptr, "sbp_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        sbp_set_error("no CUDA device available (%s); libsbpgpu has no CPU path",
+                      e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return SBP_ERR_NODEV;
+    }
+    SBP_REQUIRE(device >= 0 && device < count, "sbp_ctx_create: bad device ordinal");
+    SBP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SBP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        sbp_set_error("device %d is sm_%d%d; libsbpgpu is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        return SBP_ERR_NODEV;
+    }
+    sbp_ctx *ctx = new sbp_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (stream_or_null) {
+        ctx->stream = (cudaStream_t)stream_or_null;
+    } else {
+        SBP_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    SBP_CUDA(cudaMalloc(&ctx->d_flags, 16 * sizeof(int32_t)));
+    SBP_CUDA(cudaMemset(ctx->d_flags, 0, 16 * sizeof(int32_t)));
+    SBP_CUDA(cudaMallocHost(&ctx->h_flags, 16 * sizeof(int32_t)));
+    *out = ctx;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_ctx_destroy(sbp_ctx *ctx) {
+    if (!ctx) return SBP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int i = 0; i < 8; ++i)
+        if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
+    if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_ctx_set_stream(sbp_ctx *ctx, void *stream) {
+    SBP_REQUIRE(ctx != nullptr, "sbp_ctx_set_stream: ctx is NULL");
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->own_stream = false;
+    }
+    ctx->stream = (cudaStream_t)stream;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_ctx_sync(sbp_ctx *ctx) {
+    SBP_REQUIRE(ctx != nullptr, "sbp_ctx_sync: ctx is NULL");
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_ctx_info(sbp_ctx *ctx, int32_t *sm_count, int64_t *launches) {
+    SBP_REQUIRE(ctx != nullptr, "sbp_ctx_info: ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (launches) *launches = ctx->launches;
+    return SBP_OK;
+}
+
+int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->d_scratch_bytes[slot] < bytes) {
+        // stream-ordered users of the old buffer must finish before it is freed
+        SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_scratch[slot]) SBP_CUDA(cudaFree(ctx->d_scratch[slot]));
+        ctx->d_scratch[slot] = nullptr;
+        ctx->d_scratch_bytes[slot] = 0;
+        size_t want = bytes + bytes / 4;
+        want = (want + 255) & ~(size_t)255;
+        SBP_CUDA(cudaMalloc(&ctx->d_scratch[slot], want));
+        ctx->d_scratch_bytes[slot] = want;
+    }
+    *out = ctx->d_scratch[slot];
+    return SBP_OK;
+}
+
+// --------------------------------------------------------- K6: bit-pack -----
+// One thread builds one 32-bit word = 8 (x) x 4 (y) pixels.  The input is the
+// reference's `_img` order, byte (x, y) at x * H + y, so the four y-neighbours
+// of a column are contiguous.
+__global__ void k_pack_map(const uint8_t *__restrict__ free_xy, int W, int H, int SX,
+                           uint32_t n_words, uint32_t *__restrict__ words) {
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words;
+         wi += gridDim.x * blockDim.x) {
+        uint32_t sec = wi >> 3, sub = wi & 7u;
+        int sx = (int)(sec % (uint32_t)SX), sy = (int)(sec / (uint32_t)SX);
+        int x0 = sx * 16 + (int)((sub >> 1) & 1u) * 8;
+        int y0 = sy * 16 + (int)((sub >> 2) & 1u) * 8 + (int)(sub & 1u) * 4;
+        uint32_t w = 0;
+#pragma unroll
+        for (int dx = 0; dx < 8; ++dx) {
+            int x = x0 + dx;
+#pragma unroll
+            for (int dy = 0; dy < 4; ++dy) {
+                int y = y0 + dy;
+                if (x < W && y < H && free_xy[(size_t)x * (size_t)H + (size_t)y] != 0)
+                    w |= 1u << ((dy << 3) | dx);
+            }
+        }
+        words[wi] = w;
+    }
+}
+
+static int32_t map_create_common(sbp_ctx *ctx, const uint8_t *d_free_xy, int32_t W, int32_t H,
+                                 sbp_map **out) {
+    sbp_map *m = new sbp_map();
+    m->ctx = ctx;
+    int SX = (W + 15) / 16, SY = (H + 15) / 16;
+    uint64_t n_words64 = (uint64_t)SX * (uint64_t)SY * 8ull;
+    if (n_words64 > 0xffffffffull / 4ull) {
+        delete m;
+        sbp_set_error("map %dx%d too large for 32-bit word indexing", W, H);
+        return SBP_ERR_ARG;
+    }
+    uint32_t n_words = (uint32_t)n_words64;
+    SBP_CUDA(cudaMalloc(&m->d_words, (size_t)n_words * 4));
+    m->view.words = m->d_words;
+    m->view.W = W;
+    m->view.H = H;
+    m->view.SX = SX;
+    m->view.SY = SY;
+    m->view.n_words = n_words;
+    m->packed_bytes = (int64_t)n_words * 4;
+    // shared-memory residency: leave room for the barrier and per-CTA bookkeeping
+    m->smem_resident = (size_t)m->packed_bytes + 1024 <= (size_t)ctx->max_smem_optin;
+    int threads = 256;
+    int blocks = (int)((n_words + threads - 1) / threads);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    k_pack_map<<<blocks, threads, 0, ctx->stream>>>(d_free_xy, W, H, SX, n_words, m->d_words);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    *out = m;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_map_create(sbp_ctx *ctx, const uint8_t *free_xy, int32_t W, int32_t H,
+                                  sbp_map **out) {
+    SBP_REQUIRE(ctx && free_xy && out, "sbp_map_create: NULL argument");
+    SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "sbp_map_create: 1 <= W,H <= 65536");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    uint8_t *d_in = nullptr;
+    size_t bytes = (size_t)W * (size_t)H;
+    SBP_CUDA(cudaMalloc(&d_in, bytes));
+    cudaError_t e = cudaMemcpyAsync(d_in, free_xy, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    int32_t rc = SBP_OK;
+    if (e != cudaSuccess) {
+        sbp_set_error("sbp_map_create: H2D copy failed: %s", cudaGetErrorString(e));
+        rc = SBP_ERR_CUDA;
+    } else {
+        rc = map_create_common(ctx, d_in, W, H, out);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    return rc;
+}
+
+extern "C" int32_t sbp_map_create_device(sbp_ctx *ctx, const uint8_t *free_xy_device, int32_t W,
+                                         int32_t H, sbp_map **out) {
+    SBP_REQUIRE(ctx && free_xy_device && out, "sbp_map_create_device: NULL argument");
+    SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536,
+                "sbp_map_create_device: 1 <= W,H <= 65536");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int32_t rc = map_create_common(ctx, free_xy_device, W, H, out);
+    if (rc == SBP_OK) SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return rc;
+}
+
+extern "C" int32_t sbp_map_destroy(sbp_map *map) {
+    if (!map) return SBP_OK;
+    cudaSetDevice(map->ctx->device);
+    cudaStreamSynchronize(map->ctx->stream);
+    if (map->d_words) cudaFree(map->d_words);
+    delete map;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_map_info(sbp_map *map, int32_t *W, int32_t *H, int64_t *packed_bytes,
+                                int32_t *smem_resident) {
+    SBP_REQUIRE(map != nullptr, "sbp_map_info: map is NULL");
+    if (W) *W = map->view.W;
+    if (H) *H = map->view.H;
+    if (packed_bytes) *packed_bytes = map->packed_bytes;
+    if (smem_resident) *smem_resident = map->smem_resident ? 1 : 0;
+    return SBP_OK;
+}

@@ -1,0 +1,777 @@
+// nodes.cu -- device-resident append-only node store; K4 brute-force kNN with
+// per-thread top-k and shuffle merge; K5 radius query with ordered compaction.
+//
+// Reference behaviour restated (file:line under /root/reference/sbp_env/):
+//   planners' `poses` arrays and appends      planners/rrtPlanner.py:24-26, :106-113
+//   RRTPlanner.find_nearest_neighbour_idx     planners/rrtPlanner.py:268-279
+//   np.argsort(distances)[:20] candidates     planners/rrtPlanner.py:151-152, :226-227
+//   prmPlanner.nearest_neighbours             planners/prmPlanner.py:28-44
+//   radius gate on engine.dist                planners/rrtPlanner.py:177-181, engine.py:13-24
+//
+// Distance semantics: d = sqrt_rn(((dx*dx + dy*dy) + dz*dz) + ...),
+// every operation rounded separately (no FMA), which is bit-identical to
+// np.linalg.norm(poses - q, axis=1) for d <= 8.  Results are ordered by
+// (d, index) with d the ROUNDED square root: distinct d^2 may collapse to one d,
+// in which case the lower index wins, exactly like np.argmin / a stable argsort.
+// The hot loop compares d^2 against round-up(d_k * d_k): sqrt_rn is monotone, so
+// a candidate with d^2 >= that bound cannot have sqrt < d_k; only candidates
+// below it take the slow path that computes the square root.
+#include <math.h>
+
+#include "common.cuh"
+
+#define KNN_TPB 128        // queries per CTA in the batched kernel
+#define KNN_TILE 1024      // nodes staged in shared memory per step
+#define WIDE_TPB 256
+
+// ------------------------------------------------------------ node store ----
+extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, sbp_nodes **out) {
+    SBP_REQUIRE(ctx && out, "sbp_nodes_create: NULL argument");
+    SBP_REQUIRE(d >= 1 && d <= 8, "sbp_nodes_create: 1 <= d <= 8");
+    SBP_REQUIRE(capacity >= 0 && capacity < ((int64_t)1 << 31), "sbp_nodes_create: bad capacity");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_nodes *s = new sbp_nodes();
+    s->ctx = ctx;
+    s->d = d;
+    s->capacity = capacity < 1024 ? 1024 : capacity;
+    cudaError_t e = cudaMalloc(&s->d_soa, (size_t)s->capacity * d * sizeof(double));
+    if (e != cudaSuccess) {
+        delete s;
+        sbp_set_error("sbp_nodes_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+        return SBP_ERR_CUDA;
+    }
+    *out = s;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_destroy(sbp_nodes *s) {
+    if (!s) return SBP_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    if (s->d_soa) cudaFree(s->d_soa);
+    delete s;
+    return SBP_OK;
+}
+
+__global__ void k_aos_to_soa(const double *__restrict__ X, int64_t m, int d, double *__restrict__ soa,
+                             int64_t capacity, int64_t offset) {
+    int64_t total = m * d;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = t / d;
+        int j = (int)(t - row * d);
+        soa[(int64_t)j * capacity + offset + row] = X[t];
+    }
+}
+
+__global__ void k_soa_to_aos(const double *__restrict__ soa, int64_t capacity, int64_t first,
+                             int64_t count, int d, double *__restrict__ X) {
+    int64_t total = count * d;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = t / d;
+        int j = (int)(t - row * d);
+        X[t] = soa[(int64_t)j * capacity + first + row];
+    }
+}
+
+static int32_t nodes_grow(sbp_nodes *s, int64_t need) {
+    if (need <= s->capacity) return SBP_OK;
+    int64_t cap = s->capacity;
+    while (cap < need) cap *= 2;
+    SBP_REQUIRE(cap < ((int64_t)1 << 31), "node store limited to 2^31-1 nodes");
+    double *nw = nullptr;
+    SBP_CUDA(cudaMalloc(&nw, (size_t)cap * s->d * sizeof(double)));
+    for (int j = 0; j < s->d; ++j)
+        SBP_CUDA(cudaMemcpyAsync(nw + (int64_t)j * cap, s->d_soa + (int64_t)j * s->capacity,
+                                 (size_t)s->n * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 s->ctx->stream));
+    SBP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    SBP_CUDA(cudaFree(s->d_soa));
+    s->d_soa = nw;
+    s->capacity = cap;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_append(sbp_nodes *s, const double *X, int64_t m, int32_t on_device) {
+    SBP_REQUIRE(s && (m == 0 || X), "sbp_nodes_append: NULL argument");
+    SBP_REQUIRE(m >= 0, "sbp_nodes_append: m < 0");
+    if (m == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int32_t rc = nodes_grow(s, s->n + m);
+    if (rc) return rc;
+    const double *src = X;
+    if (!on_device) {
+        void *stage = nullptr;
+        rc = sbp_ctx_scratch(ctx, 7, (size_t)m * s->d * sizeof(double), &stage);
+        if (rc) return rc;
+        SBP_CUDA(cudaMemcpyAsync(stage, X, (size_t)m * s->d * sizeof(double), cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        src = (const double *)stage;
+    }
+    int64_t total = m * s->d;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_aos_to_soa<<<blocks, 256, 0, ctx->stream>>>(src, m, s->d, s->d_soa, s->capacity, s->n);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    // a pageable host source may be reused by the caller right after return
+    if (!on_device) SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    s->n += m;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_size(sbp_nodes *s, int64_t *n) {
+    SBP_REQUIRE(s && n, "sbp_nodes_size: NULL argument");
+    *n = s->n;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_truncate(sbp_nodes *s, int64_t n) {
+    SBP_REQUIRE(s, "sbp_nodes_truncate: NULL argument");
+    SBP_REQUIRE(n >= 0 && n <= s->n, "sbp_nodes_truncate: n out of range");
+    s->n = n;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_read(sbp_nodes *s, int64_t first, int64_t count, double *out_host) {
+    SBP_REQUIRE(s && (count == 0 || out_host), "sbp_nodes_read: NULL argument");
+    SBP_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "sbp_nodes_read: range");
+    if (count == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    void *stage = nullptr;
+    int32_t rc = sbp_ctx_scratch(ctx, 7, (size_t)count * s->d * sizeof(double), &stage);
+    if (rc) return rc;
+    int64_t total = count * s->d;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_soa_to_aos<<<blocks, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, first, count, s->d,
+                                                  (double *)stage);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    SBP_CUDA(cudaMemcpyAsync(out_host, stage, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_nodes_rows_device(sbp_nodes *s, int64_t first, int64_t count,
+                                         double *out_device) {
+    SBP_REQUIRE(s && (count == 0 || out_device), "sbp_nodes_rows_device: NULL argument");
+    SBP_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "sbp_nodes_rows_device: range");
+    if (count == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int64_t total = count * s->d;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_soa_to_aos<<<blocks, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, first, count, s->d,
+                                                  out_device);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+// --------------------------------------------------------- distance core ----
+template <int D>
+__device__ __forceinline__ double dist2_full(const double (&p)[D], const double (&q)[D]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        double df = __dsub_rn(p[j], q[j]);        // poses - pos
+        double sq = __dmul_rn(df, df);
+        acc = j == 0 ? sq : __dadd_rn(acc, sq);   // left-to-right, unfused
+    }
+    return acc;
+}
+
+// Per-thread sorted list of the K best (d, idx), d ascending, ties keep arrival
+// order (callers feed indices in ascending order, so ties keep the lower index).
+template <int K>
+struct TopK {
+    double d[K];
+    int32_t i[K];
+    double bound2;   // round-up(d[K-1]^2): candidates with d^2 >= bound2 are rejected
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int t = 0; t < K; ++t) { d[t] = INFINITY; i[t] = -1; }
+        bound2 = INFINITY;
+    }
+    __device__ __forceinline__ void offer(double d2, int32_t idx) {
+        if (d2 < bound2) {
+            double dd = __dsqrt_rn(d2);
+            if (dd < d[K - 1]) {
+                bool placed = false;
+#pragma unroll
+                for (int t = K - 1; t >= 0; --t) {
+                    if (!placed) {
+                        if (t > 0 && dd < d[t - 1]) { d[t] = d[t - 1]; i[t] = i[t - 1]; }
+                        else { d[t] = dd; i[t] = idx; placed = true; }
+                    }
+                }
+                bound2 = __dmul_ru(d[K - 1], d[K - 1]);
+            }
+        }
+    }
+    // remove the head (used by the block merge)
+    __device__ __forceinline__ void pop() {
+#pragma unroll
+        for (int t = 0; t + 1 < K; ++t) { d[t] = d[t + 1]; i[t] = i[t + 1]; }
+        d[K - 1] = INFINITY; i[K - 1] = -1;
+    }
+};
+
+// ---------------------------------------------- K4a: batched, thread/query ---
+// grid = (ceil(m / KNN_TPB), S).  CTA (bx, s) scans node chunk s for its 128
+// queries; node tiles are staged in shared memory (SoA) and read by broadcast.
+template <int D, int K>
+__global__ void __launch_bounds__(KNN_TPB)
+k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
+              const double *__restrict__ X, int64_t m, double *__restrict__ pd,
+              int32_t *__restrict__ pi) {
+    __shared__ double tile[D][KNN_TILE];
+    const int64_t q = (int64_t)blockIdx.x * KNN_TPB + threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t chunk = (n + S - 1) / S;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = q < m ? X[q * D + j] : 0.0;
+    TopK<K> top;
+    top.init();
+    for (int64_t t0 = c0; t0 < c1; t0 += KNN_TILE) {
+        int cnt = (int)(c1 - t0 < KNN_TILE ? c1 - t0 : KNN_TILE);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            for (int t = threadIdx.x; t < cnt; t += KNN_TPB)
+                tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
+        __syncthreads();
+#pragma unroll 4
+        for (int t = 0; t < cnt; ++t) {
+            double pv[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) pv[j] = tile[j][t];
+            top.offer(dist2_full<D>(pv, qv), (int32_t)(t0 + t));
+        }
+    }
+    if (q < m) {
+        int64_t base = (q * S + s) * K;
+#pragma unroll
+        for (int t = 0; t < K; ++t) { pd[base + t] = top.d[t]; pi[base + t] = top.i[t]; }
+    }
+}
+
+// ------------------------------------------------- K4b: wide, CTA/(q,chunk) ---
+// For few queries over many nodes (RRT nearest / argsort[:20]): threads stride
+// the chunk with coalesced SoA loads, then the CTA merges its per-thread lists by
+// repeatedly extracting the (d, idx)-smallest head with warp shuffles.
+template <int D, int K>
+__global__ void __launch_bounds__(WIDE_TPB)
+k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
+           const double *__restrict__ X, int64_t m, double *__restrict__ pd,
+           int32_t *__restrict__ pi) {
+    const int64_t q = blockIdx.x;
+    const int s = blockIdx.y;
+    const int64_t chunk = (n + S - 1) / S;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
+    TopK<K> top;
+    top.init();
+    for (int64_t t = c0 + threadIdx.x; t < c1; t += WIDE_TPB) {
+        double pv[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
+        top.offer(dist2_full<D>(pv, qv), (int32_t)t);
+    }
+    // block merge: K rounds of argmin over the heads, key (d, idx)
+    __shared__ double wd[WIDE_TPB / 32];
+    __shared__ int32_t wi[WIDE_TPB / 32];
+    __shared__ int wl[WIDE_TPB / 32];
+    __shared__ int win_thread;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t base = (q * S + s) * K;
+    for (int r = 0; r < K; ++r) {
+        double bd = top.d[0];
+        int32_t bi = top.i[0];
+        int bl = threadIdx.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double od = __shfl_xor_sync(FULL, bd, o);
+            int32_t oi = __shfl_xor_sync(FULL, bi, o);
+            int ol = __shfl_xor_sync(FULL, bl, o);
+            // empty heads (idx -1, d inf) lose against anything real
+            bool take = (oi >= 0) && (bi < 0 || od < bd || (od == bd && oi < bi));
+            if (take) { bd = od; bi = oi; bl = ol; }
+        }
+        if (lane == 0) { wd[warp] = bd; wi[warp] = bi; wl[warp] = bl; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double fd = wd[0]; int32_t fi = wi[0]; int fl = wl[0];
+            for (int w = 1; w < WIDE_TPB / 32; ++w) {
+                bool take = (wi[w] >= 0) && (fi < 0 || wd[w] < fd || (wd[w] == fd && wi[w] < fi));
+                if (take) { fd = wd[w]; fi = wi[w]; fl = wl[w]; }
+            }
+            pd[base + r] = fi >= 0 ? fd : INFINITY;
+            pi[base + r] = fi;
+            win_thread = fi >= 0 ? fl : -1;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x == win_thread) top.pop();
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------- K4c: chunk merge ------
+// One thread per query merges S sorted partial lists (chunk s holds indices below
+// chunk s+1, so on equal d the lower chunk wins) into the final [m][k] rows.
+__global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__restrict__ pi, int64_t m,
+                            int S, int K, int k, int64_t *__restrict__ idx,
+                            double *__restrict__ dist) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const double *d0 = pd + q * S * K;
+    const int32_t *i0 = pi + q * S * K;
+    if (S == 1) {
+        for (int t = 0; t < k; ++t) {
+            idx[q * k + t] = i0[t];
+            if (dist) dist[q * k + t] = i0[t] >= 0 ? d0[t] : INFINITY;
+        }
+        return;
+    }
+    unsigned char head[64];
+    for (int s = 0; s < S; ++s) head[s] = 0;
+    for (int t = 0; t < k; ++t) {
+        int best = -1;
+        double bd = INFINITY;
+        for (int s = 0; s < S; ++s) {
+            int h = head[s];
+            if (h >= K) continue;
+            int32_t ci = i0[s * K + h];
+            if (ci < 0) continue;
+            double cd = d0[s * K + h];
+            if (best < 0 || cd < bd) { best = s; bd = cd; }
+        }
+        if (best < 0) {
+            idx[q * k + t] = -1;
+            if (dist) dist[q * k + t] = INFINITY;
+        } else {
+            idx[q * k + t] = i0[best * K + head[best]];
+            if (dist) dist[q * k + t] = bd;
+            head[best]++;
+        }
+    }
+}
+
+template <int D, int K>
+static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
+                          double *dist) {
+    sbp_ctx *ctx = s->ctx;
+    const int64_t n = s->n;
+    bool wide = m < 256;
+    int S;
+    if (wide) {
+        int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
+        int64_t maxs = (n + 2047) / 2048;
+        S = (int)(want < maxs ? want : maxs);
+    } else {
+        int64_t tiles = (m + KNN_TPB - 1) / KNN_TPB;
+        int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+        int64_t maxs = (n + 4 * KNN_TILE - 1) / (4 * KNN_TILE);
+        S = (int)(want < maxs ? want : maxs);
+    }
+    if (S < 1) S = 1;
+    if (S > 64) S = 64;
+    void *pd = nullptr, *pi = nullptr;
+    int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)m * S * K * sizeof(double), &pd);
+    if (rc) return rc;
+    rc = sbp_ctx_scratch(ctx, 1, (size_t)m * S * K * sizeof(int32_t), &pi);
+    if (rc) return rc;
+    if (wide) {
+        dim3 grid((unsigned)m, (unsigned)S);
+        k_knn_wide<D, K><<<grid, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+                                                              (double *)pd, (int32_t *)pi);
+    } else {
+        dim3 grid((unsigned)((m + KNN_TPB - 1) / KNN_TPB), (unsigned)S);
+        k_knn_batched<D, K><<<grid, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+                                                                (double *)pd, (int32_t *)pi);
+    }
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    k_knn_merge<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
+        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+template <int D>
+static int32_t knn_dispatch_k(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
+                              double *dist) {
+    if (k <= 1) return knn_launch<D, 1>(s, X, m, k, idx, dist);
+    if (k <= 4) return knn_launch<D, 4>(s, X, m, k, idx, dist);
+    if (k <= 8) return knn_launch<D, 8>(s, X, m, k, idx, dist);
+    if (k <= 16) return knn_launch<D, 16>(s, X, m, k, idx, dist);
+    return knn_launch<D, 32>(s, X, m, k, idx, dist);
+}
+
+__global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        idx[t] = -1;
+        if (dist) dist[t] = INFINITY;
+    }
+}
+
+extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32_t k,
+                                 int32_t precision, int64_t *idx, double *dist) {
+    SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_knn: NULL argument");
+    SBP_REQUIRE(m >= 0, "sbp_nodes_knn: m < 0");
+    SBP_REQUIRE(k >= 1 && k <= 32, "sbp_nodes_knn: 1 <= k <= 32");
+    SBP_REQUIRE(precision == 64, "sbp_nodes_knn: only the bit-exact fp64 path exists (precision=64)");
+    if (m == 0) return SBP_OK;
+    SBP_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->n == 0) {
+        k_fill_empty_knn<<<64, 256, 0, s->ctx->stream>>>(m * k, idx, dist);
+        s->ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
+    switch (s->d) {
+        case 2: return knn_dispatch_k<2>(s, X, m, k, idx, dist);
+        case 3: return knn_dispatch_k<3>(s, X, m, k, idx, dist);
+        case 4: return knn_dispatch_k<4>(s, X, m, k, idx, dist);
+        case 6: return knn_dispatch_k<6>(s, X, m, k, idx, dist);
+        default:
+            sbp_set_error("sbp_nodes_knn: dimension %d not instantiated (2, 3, 4, 6)", s->d);
+            return SBP_ERR_ARG;
+    }
+}
+
+// --------------------------------------------------------- K5: radius -------
+// Membership is decided on d^2 against a host-computed threshold (see
+// near_threshold below), so no square root is evaluated per pair.
+template <int D, bool XY>
+__device__ __forceinline__ double near_d2(const double (&p)[D], const double (&q)[D]) {
+    if (XY) {
+        // engine.euclidean_dist (engine.py:23-24): p = p1 - p2 (query - node), first
+        // two coordinates only.  The reference squares with libm pow, which differs
+        // from the correctly rounded product by 1 ulp for ~0.1% of inputs (SURVEY.md
+        // D4): "parity unpinned at the last bit" for this metric.
+        double a = __dsub_rn(q[0], p[0]), b = __dsub_rn(q[1], p[1]);
+        return __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+    }
+    return dist2_full<D>(p, q);
+}
+
+__device__ __forceinline__ bool near_in(double d2, double thr, int closed) {
+    return closed ? (d2 <= thr) : (d2 < thr);
+}
+
+// wide: CTA per (query, chunk).  PASS 0 counts, PASS 1 writes indices in order.
+template <int D, bool XY, int PASS>
+__global__ void __launch_bounds__(WIDE_TPB)
+k_near_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
+            const double *__restrict__ X, int64_t m, double thr, int closed,
+            int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+            int64_t *__restrict__ idx, int64_t idx_capacity, const int64_t *__restrict__ needed) {
+    const int64_t q = blockIdx.x;
+    const int s = blockIdx.y;
+    if (PASS == 1 && *needed > idx_capacity) return;
+    const int64_t chunk = (n + S - 1) / S;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    constexpr int DD = XY ? 2 : D;
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = j < DD ? X[q * D + j] : 0.0;
+    __shared__ int wsum[WIDE_TPB / 32];
+    __shared__ int64_t base_s;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t mycount = 0;
+    if (PASS == 1 && threadIdx.x == 0) base_s = offsets[q * S + s];
+    if (PASS == 1) __syncthreads();
+    for (int64_t t0 = c0; t0 < c1; t0 += WIDE_TPB) {
+        int64_t t = t0 + threadIdx.x;
+        bool in = false;
+        if (t < c1) {
+            double pv[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) pv[j] = j < DD ? soa[(int64_t)j * capacity + t] : 0.0;
+            in = near_in(near_d2<D, XY>(pv, qv), thr, closed);
+        }
+        if (PASS == 0) {
+            mycount += in ? 1 : 0;
+        } else {
+            unsigned bal = __ballot_sync(FULL, in);
+            int pre = __popc(bal & ((1u << lane) - 1u));
+            if (lane == 0) wsum[warp] = __popc(bal);
+            __syncthreads();
+            int woff = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < WIDE_TPB / 32; ++w) {
+                int v = wsum[w];
+                if (w < warp) woff += v;
+                tot += v;
+            }
+            int64_t b = base_s;
+            if (in) idx[b + woff + pre] = t;
+            __syncthreads();
+            if (threadIdx.x == 0) base_s = b + tot;
+            __syncthreads();
+        }
+    }
+    if (PASS == 0) {
+        for (int o = 16; o > 0; o >>= 1) mycount += __shfl_down_sync(FULL, mycount, o);
+        __shared__ int64_t wc[WIDE_TPB / 32];
+        if (lane == 0) wc[warp] = mycount;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int64_t tot = 0;
+            for (int w = 0; w < WIDE_TPB / 32; ++w) tot += wc[w];
+            counts[q * S + s] = tot;
+        }
+    }
+}
+
+// batched: thread per query over shared-memory node tiles.
+template <int D, bool XY, int PASS>
+__global__ void __launch_bounds__(KNN_TPB)
+k_near_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
+               const double *__restrict__ X, int64_t m, double thr, int closed,
+               int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+               int64_t *__restrict__ idx, int64_t idx_capacity,
+               const int64_t *__restrict__ needed) {
+    constexpr int DD = XY ? 2 : D;
+    __shared__ double tile[DD][KNN_TILE];
+    if (PASS == 1 && *needed > idx_capacity) return;
+    const int64_t q = (int64_t)blockIdx.x * KNN_TPB + threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t chunk = (n + S - 1) / S;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = (q < m && j < DD) ? X[q * D + j] : 0.0;
+    int64_t cnt_or_pos = 0;
+    if (PASS == 1 && q < m) cnt_or_pos = offsets[q * S + s];
+    for (int64_t t0 = c0; t0 < c1; t0 += KNN_TILE) {
+        int cnt = (int)(c1 - t0 < KNN_TILE ? c1 - t0 : KNN_TILE);
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < DD; ++j)
+            for (int t = threadIdx.x; t < cnt; t += KNN_TPB)
+                tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
+        __syncthreads();
+        if (q < m) {
+#pragma unroll 4
+            for (int t = 0; t < cnt; ++t) {
+                double pv[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][t] : 0.0;
+                bool in = near_in(near_d2<D, XY>(pv, qv), thr, closed);
+                if (PASS == 0) cnt_or_pos += in ? 1 : 0;
+                else if (in) idx[cnt_or_pos++] = t0 + t;
+            }
+        }
+    }
+    if (PASS == 0 && q < m) counts[q * S + s] = cnt_or_pos;
+}
+
+// Exclusive scan of counts[L] (single CTA; L = m*S) -> offsets[L]; row_ptr[q] =
+// offsets[q*S], row_ptr[m] = total, *needed = total.
+__global__ void __launch_bounds__(1024)
+k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
+              int64_t *__restrict__ offsets, int64_t *__restrict__ row_ptr,
+              int64_t *__restrict__ needed) {
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x;
+    const int64_t seg = (L + 1023) / 1024;
+    const int64_t a = (int64_t)tid * seg, b = a + seg < L ? a + seg : L;
+    int64_t sum = 0;
+    for (int64_t t = a; t < b; ++t) sum += counts[t];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int64_t v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int64_t run = part[tid] - sum;   // exclusive prefix of my segment
+    for (int64_t t = a; t < b; ++t) {
+        offsets[t] = run;
+        if (t % S == 0) row_ptr[t / S] = run;
+        run += counts[t];
+    }
+    if (tid == 1023) {
+        row_ptr[m] = part[1023];
+        *needed = part[1023];
+    }
+}
+
+// Smallest fp64 t with sqrt_rn(t) >= r  (d < r  <=>  d^2 < t), and largest t with
+// sqrt_rn(t) <= r  (d <= r <=> d^2 <= t); SURVEY.md H5.  Host sqrt is IEEE
+// correctly rounded, like __dsqrt_rn.
+static void near_threshold(double r, int closed, double *thr, int *closed_out) {
+    *closed_out = closed;
+    if (r != r) { *thr = -1.0; *closed_out = 0; return; }            // nan: nothing matches
+    if (r < 0) { *thr = -1.0; *closed_out = 0; return; }             // d >= 0 always
+    if (isinf(r)) { *thr = INFINITY; *closed_out = 1; return; }      // finite d always matches
+    double s = r * r;
+    if (isinf(s)) { *thr = INFINITY; *closed_out = 1; return; }
+    if (!closed) {
+        while (s > 0 && sqrt(s) >= r) s = nextafter(s, -INFINITY);
+        while (sqrt(nextafter(s, INFINITY)) < r) s = nextafter(s, INFINITY);
+        // now sqrt(s) < r (or s == 0) and sqrt(next(s)) >= r
+        *thr = (sqrt(s) >= r) ? s : nextafter(s, INFINITY);
+    } else {
+        while (sqrt(s) > r) s = nextafter(s, -INFINITY);
+        while (sqrt(nextafter(s, INFINITY)) <= r) s = nextafter(s, INFINITY);
+        *thr = s;
+    }
+}
+
+template <int D, bool XY>
+static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr, int closed,
+                           int64_t *row_ptr, int64_t *idx, int64_t idx_capacity, int64_t *needed) {
+    sbp_ctx *ctx = s->ctx;
+    const int64_t n = s->n;
+    bool wide = m < 256;
+    int S;
+    if (wide) {
+        int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
+        int64_t maxs = (n + 2047) / 2048;
+        S = (int)(want < maxs ? want : maxs);
+    } else {
+        int64_t tiles = (m + KNN_TPB - 1) / KNN_TPB;
+        int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+        int64_t maxs = (n + 4 * KNN_TILE - 1) / (4 * KNN_TILE);
+        S = (int)(want < maxs ? want : maxs);
+    }
+    if (S < 1) S = 1;
+    if (S > 1024) S = 1024;
+    const int64_t L = m * S;
+    void *ws = nullptr;
+    int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
+    if (rc) return rc;
+    int64_t *counts = (int64_t *)ws, *offsets = counts + L;
+    dim3 gw((unsigned)m, (unsigned)S), gb((unsigned)((m + KNN_TPB - 1) / KNN_TPB), (unsigned)S);
+    if (wide)
+        k_near_wide<D, XY, 0><<<gw, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m, thr,
+                                                                closed, counts, offsets, idx,
+                                                                idx_capacity, needed);
+    else
+        k_near_batched<D, XY, 0><<<gb, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+                                                                  thr, closed, counts, offsets, idx,
+                                                                  idx_capacity, needed);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, L, S, m, offsets, row_ptr, needed);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    if (idx && idx_capacity > 0) {
+        if (wide)
+            k_near_wide<D, XY, 1><<<gw, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+                                                                    thr, closed, counts, offsets, idx,
+                                                                    idx_capacity, needed);
+        else
+            k_near_batched<D, XY, 1><<<gb, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X,
+                                                                      m, thr, closed, counts, offsets,
+                                                                      idx, idx_capacity, needed);
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+    }
+    return SBP_OK;
+}
+
+__global__ void k_zero_rowptr(int64_t m, int64_t *row_ptr, int64_t *needed) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= m;
+         t += (int64_t)gridDim.x * blockDim.x)
+        row_ptr[t] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *needed = 0;
+}
+
+extern "C" int32_t sbp_nodes_near(sbp_nodes *s, const double *X, int64_t m, double r,
+                                  int32_t metric, int32_t closed, int64_t *row_ptr, int64_t *idx,
+                                  int64_t idx_capacity, int64_t *needed) {
+    SBP_REQUIRE(s && row_ptr && needed && (m == 0 || X), "sbp_nodes_near: NULL argument");
+    SBP_REQUIRE(m >= 0 && idx_capacity >= 0, "sbp_nodes_near: negative size");
+    SBP_REQUIRE(metric == SBP_METRIC_FULL || metric == SBP_METRIC_XY, "sbp_nodes_near: bad metric");
+    SBP_REQUIRE(metric == SBP_METRIC_FULL || s->d >= 2, "sbp_nodes_near: XY metric needs d >= 2");
+    SBP_CUDA(cudaSetDevice(s->ctx->device));
+    double thr;
+    int cl;
+    near_threshold(r, closed ? 1 : 0, &thr, &cl);
+    if (m == 0 || s->n == 0) {
+        k_zero_rowptr<<<64, 256, 0, s->ctx->stream>>>(m, row_ptr, needed);
+        s->ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
+#define SBP_NEAR_CASE(DV)                                                                        \
+    case DV:                                                                                      \
+        return metric == SBP_METRIC_XY                                                            \
+                   ? near_launch<DV, true>(s, X, m, thr, cl, row_ptr, idx, idx_capacity, needed)  \
+                   : near_launch<DV, false>(s, X, m, thr, cl, row_ptr, idx, idx_capacity, needed);
+    switch (s->d) {
+        SBP_NEAR_CASE(2)
+        SBP_NEAR_CASE(3)
+        SBP_NEAR_CASE(4)
+        SBP_NEAR_CASE(6)
+        default:
+            sbp_set_error("sbp_nodes_near: dimension %d not instantiated (2, 3, 4, 6)", s->d);
+            return SBP_ERR_ARG;
+    }
+#undef SBP_NEAR_CASE
+}
+
+// -------------------------------------------- batched planner primitives -----
+// Endpoints of candidate edges (row i -> nbr[i][j]) for a following visible call:
+// the batched form of PRMPlanner.build_graph's inner loop (prmPlanner.py:91-101),
+// which calls visible(m_g.pos, v.pos): P = neighbour, Q = row node.
+__global__ void k_gather_edges(const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
+                               const int64_t *__restrict__ nbr, int64_t m, int k, int64_t first_row,
+                               double *__restrict__ P, double *__restrict__ Q,
+                               uint8_t *__restrict__ valid) {
+    int64_t total = m * k;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t row = first_row + t / k;
+        int64_t nb = nbr[t];
+        bool ok = nb >= 0 && nb < n && nb != row && row < n;
+        int64_t src = ok ? nb : (row < n ? row : 0);
+        int64_t dst = row < n ? row : 0;
+        for (int j = 0; j < d; ++j) {
+            P[t * d + j] = soa[(int64_t)j * capacity + src];
+            Q[t * d + j] = soa[(int64_t)j * capacity + dst];
+        }
+        if (valid) valid[t] = ok ? 1 : 0;
+    }
+}
+
+extern "C" int32_t sbp_nodes_gather_edges(sbp_nodes *s, const int64_t *nbr, int64_t m, int32_t k,
+                                          int64_t first_row, double *P, double *Q,
+                                          uint8_t *valid) {
+    SBP_REQUIRE(s && (m == 0 || (nbr && P && Q)), "sbp_nodes_gather_edges: NULL argument");
+    SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_nodes_gather_edges: bad sizes");
+    if (m == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int64_t total = m * k;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_gather_edges<<<blocks, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d, nbr, m, k,
+                                                    first_row, P, Q, valid);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}

@@ -1,0 +1,179 @@
+"""Device-resident, append-only node array with brute-force nearest / kNN / radius
+queries: the GPU twin of the planners' ``poses`` arrays.
+
+Reference call sites replaced (file:line under /root/reference/sbp_env/planners/):
+
+  poses = np.empty((2*max_nodes+50, d)); poses[len(nodes)] = pos    rrtPlanner.py:24-26, :106-113
+  find_nearest_neighbour_idx(pos, poses)                            rrtPlanner.py:268-279
+  np.argsort(np.linalg.norm(poses - pos, axis=1))[:20]              rrtPlanner.py:151-152, :226-227
+  nearest_neighbours(nodes, poses, pos, radius)                     prmPlanner.py:28-44
+  engine.dist(new, p) <= radius gate                                rrtPlanner.py:177-181
+  cross-tree nearest of Bi-RRT                                      birrtPlanner.py:82-85
+  per-tree arrays and bulk extend of RRdT*                          rrdtPlanner.py:858-887
+
+Contract: fp64, d = sqrt_rn of the left-to-right unfused sum
+of squares over ALL dims (``metric="full"``) or the first two dims only
+(``metric="xy"``, the ``engine.dist`` form); results ordered by (d, index); radius
+rows are index-ascending; ``closed`` selects ``<=`` instead of ``<``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .runtime import _is_torch_tensor, as_device_f64, as_host_f64, get_context, ptr
+
+
+class NodeStore:
+    def __init__(self, dim: int, capacity: int = 1024, device: int = 0):
+        self.dim = int(dim)
+        self.ctx = get_context(device)
+        h = C.c_void_p()
+        check(_lib.load().sbp_nodes_create(self.ctx.handle, self.dim, int(capacity), C.byref(h)),
+              "sbp_nodes_create")
+        self._h = h
+
+    # ---- growth ------------------------------------------------------------------
+    def append(self, x) -> int:
+        """``poses[len(nodes)] = pos`` (rrtPlanner.py:112); returns the new node's index."""
+        n = len(self)
+        self.extend(np.asarray(x, dtype=np.float64).reshape(1, self.dim))
+        return n
+
+    def extend(self, X) -> None:
+        """Bulk append of rows (RRdT* ``extend_tree``, rrdtPlanner.py:878-887)."""
+        if _is_torch_tensor(X):
+            self.ctx.use_torch_stream()
+            X = as_device_f64(X, self.dim)
+            check(_lib.load().sbp_nodes_append(self._h, ptr(X), X.shape[0], 1), "sbp_nodes_append")
+        else:
+            X = as_host_f64(X, self.dim)
+            check(_lib.load().sbp_nodes_append(self._h, ptr(X), len(X), 0), "sbp_nodes_append")
+
+    def truncate(self, n: int) -> None:
+        check(_lib.load().sbp_nodes_truncate(self._h, int(n)), "sbp_nodes_truncate")
+
+    def __len__(self) -> int:
+        n = C.c_int64()
+        check(_lib.load().sbp_nodes_size(self._h, C.byref(n)), "sbp_nodes_size")
+        return int(n.value)
+
+    @property
+    def poses(self) -> np.ndarray:
+        """Host copy of ``poses[:n]`` (parity dumps)."""
+        n = len(self)
+        out = np.empty((n, self.dim), np.float64)
+        if n:
+            check(_lib.load().sbp_nodes_read(self._h, 0, n, ptr(out)), "sbp_nodes_read")
+        return out
+
+    def rows_device(self, first: int = 0, count: int = None):
+        """CUDA tensor [count][d] holding stored rows first..first+count (no host trip)."""
+        import torch
+
+        self.ctx.use_torch_stream()
+        count = len(self) - first if count is None else int(count)
+        out = torch.empty((count, self.dim), dtype=torch.float64,
+                          device=torch.device("cuda", self.ctx.device))
+        check(_lib.load().sbp_nodes_rows_device(self._h, int(first), count, ptr(out)),
+              "sbp_nodes_rows_device")
+        return out
+
+    # ---- queries -------------------------------------------------------------------
+    def nearest(self, x) -> int:
+        """``np.argmin(np.linalg.norm(poses - pos, axis=1))`` (rrtPlanner.py:278-279)."""
+        idx, _ = self.knn(np.asarray(x, dtype=np.float64).reshape(1, self.dim), 1)
+        return int(idx[0, 0])
+
+    def knn(self, X, k: int, return_dist: bool = True):
+        """k nearest nodes of every row of X, ordered by (distance, index).
+
+        numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.
+        Returns ``(idx int64 [m][k], dist fp64 [m][k])``; rows are padded with
+        ``-1`` / ``inf`` when fewer than k nodes are stored."""
+        k = int(k)
+        if _is_torch_tensor(X):
+            import torch
+
+            self.ctx.use_torch_stream()
+            X = as_device_f64(X, self.dim)
+            m = X.shape[0]
+            idx = torch.empty((m, k), dtype=torch.int64, device=X.device)
+            dist = torch.empty((m, k), dtype=torch.float64, device=X.device) if return_dist else None
+            check(_lib.load().sbp_nodes_knn(self._h, ptr(X), m, k, 64, ptr(idx), ptr(dist)),
+                  "sbp_nodes_knn")
+            return idx, dist
+        X = as_host_f64(X, self.dim)
+        m = len(X)
+        idx = np.empty((m, k), np.int64)
+        dist = np.empty((m, k), np.float64) if return_dist else None
+        check(_lib.load().sbp_nodes_knn_host(self._h, ptr(X), m, k, 64, ptr(idx), ptr(dist)),
+              "sbp_nodes_knn_host")
+        return idx, dist
+
+    def near(self, X, r: float, metric: str = "full", closed: bool = False):
+        """All nodes within radius r of every row of X, as CSR ``(row_ptr, idx)`` with
+        node indices ascending in each row (the order of the reference's loops,
+        prmPlanner.py:40-44, rrtPlanner.py:176-187).
+
+        ``metric="full", closed=False`` is ``prmPlanner.nearest_neighbours``;
+        ``metric="xy", closed=True`` is the ``engine.dist(...) <= radius`` gate."""
+        met = _lib.METRIC[metric]
+        lib = _lib.load()
+        if _is_torch_tensor(X):
+            import torch
+
+            self.ctx.use_torch_stream()
+            X = as_device_f64(X, self.dim)
+            m = X.shape[0]
+            row_ptr = torch.empty(m + 1, dtype=torch.int64, device=X.device)
+            needed = torch.zeros(1, dtype=torch.int64, device=X.device)
+            check(lib.sbp_nodes_near(self._h, ptr(X), m, float(r), met, int(bool(closed)),
+                                     ptr(row_ptr), None, 0, ptr(needed)), "sbp_nodes_near")
+            total = int(needed.item())            # the size of the answer has to reach the host
+            idx = torch.empty(max(total, 1), dtype=torch.int64, device=X.device)
+            if total:
+                check(lib.sbp_nodes_near(self._h, ptr(X), m, float(r), met, int(bool(closed)),
+                                         ptr(row_ptr), ptr(idx), total, ptr(needed)), "sbp_nodes_near")
+            return row_ptr, idx[:total]
+        X = as_host_f64(X, self.dim)
+        m = len(X)
+        row_ptr = np.empty(m + 1, np.int64)
+        needed = C.c_int64(0)
+        check(lib.sbp_nodes_near_host(self._h, ptr(X), m, float(r), met, int(bool(closed)),
+                                      ptr(row_ptr), None, 0, C.byref(needed)), "sbp_nodes_near_host")
+        total = int(needed.value)
+        idx = np.empty(max(total, 1), np.int64)
+        if total:
+            check(lib.sbp_nodes_near_host(self._h, ptr(X), m, float(r), met, int(bool(closed)),
+                                          ptr(row_ptr), ptr(idx), total, C.byref(needed)),
+                  "sbp_nodes_near_host")
+        return row_ptr, idx[:total]
+
+    # ---- batched planner primitive ---------------------------------------------------
+    def gather_edges(self, nbr, first_row: int = 0):
+        """Device-side endpoints of the candidate edges ``row -> nbr[row][j]``:
+        ``(P, Q, valid)`` with P = neighbour pose, Q = row pose, the argument order of
+        ``cc.visible(m_g.pos, v.pos)`` in PRMPlanner.build_graph (prmPlanner.py:97)."""
+        import torch
+
+        self.ctx.use_torch_stream()
+        nbr = nbr.contiguous()
+        m, k = nbr.shape
+        P = torch.empty((m * k, self.dim), dtype=torch.float64, device=nbr.device)
+        Q = torch.empty((m * k, self.dim), dtype=torch.float64, device=nbr.device)
+        valid = torch.empty(m * k, dtype=torch.uint8, device=nbr.device)
+        check(_lib.load().sbp_nodes_gather_edges(self._h, ptr(nbr), m, k, int(first_row), ptr(P),
+                                                 ptr(Q), ptr(valid)), "sbp_nodes_gather_edges")
+        return P, Q, valid
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None:
+                _lib.load().sbp_nodes_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass

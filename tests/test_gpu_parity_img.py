@@ -1,0 +1,215 @@
+"""-m gpu: the CUDA path (through the C ABI) against the golden fixtures and the
+oracle for the 2-D image-space checker.  Bit-exact booleans and pixels."""
+import copy
+import pickle
+from unittest.mock import MagicMock
+
+import numpy as np
+import pytest
+
+import c_oracle as orc
+from _util import golden, kat_png, load_map, map_png, unpack
+
+pytestmark = pytest.mark.gpu
+EPS = 1e-5
+
+
+def _pair(a, b):
+    return np.array(a, float) + EPS, np.array(b, float) - EPS
+
+
+@pytest.fixture(scope="module")
+def sg():
+    import sbp_env_b200
+
+    return sbp_env_b200
+
+
+@pytest.fixture(scope="module")
+def kat(sg):
+    return sg.ImgCollisionChecker(kat_png())
+
+
+def test_reference_kat(sg, kat):
+    # tests/test_image_space_collision_checker.py:33-60 of the reference, verbatim cases
+    target = (np.array([[255, 255, 0, 0, 100, 200]] * 4) == 255).astype(kat.image.dtype)
+    assert np.isclose(kat.image, target).all()
+    assert kat.get_coor_before_collision(*_pair([0, 2], [2, 6])) == (1, 4)
+    assert kat.get_coor_before_collision(*_pair([0, 2], [2, 4])) == (1, 3)
+    assert kat.visible(*_pair([0, 2], [2, 4]))
+    assert kat.visible(*_pair([0, 2], [0, 4]))
+    assert not kat.visible(*_pair([0, 2], [2, 6]))
+    assert not kat.visible(*_pair([0, 0], [4, 0]))
+    for p in [(1.5, 0.5), (1.5, 3.5), (1.78, 2.5)]:
+        assert kat.feasible(p)
+    for p in [(3.5, 0.5), (-1.5, 3.5), (1.78, 4.5)]:
+        assert not kat.feasible(p)
+    assert sg.ImgCollisionChecker.get_line((0, 0), (3, 4)) == [(0, 0), (1, 1), (1, 2), (2, 3), (3, 4)]
+    assert sg.ImgCollisionChecker.get_line((3, 4), (0, 0)) == [(3, 4), (2, 3), (1, 2), (1, 1), (0, 0)]
+
+
+def test_wraparound_and_errors(kat):
+    # numpy negative-index wrap-around, NaN / inf behaviour
+    assert kat.feasible((-6.0, 0.5))          # wraps to x = 0
+    assert not kat.feasible((-7.0, 0.5))      # IndexError -> False
+    with pytest.raises(ValueError):
+        kat.feasible((float("nan"), 0.5))
+    with pytest.raises(OverflowError):
+        kat.feasible((float("inf"), 0.5))
+    with pytest.raises(OverflowError):
+        kat.feasible((2.0 ** 63, 0.5))        # numpy quirk pinned by the golden fixture
+    assert not kat.feasible((2.0 ** 64, 0.5))
+    assert kat.visible((float("nan"), 0.5), (1.0, 1.0)) is False
+    with pytest.raises(OverflowError):
+        kat.visible((float("inf"), 0.5), (1.0, 1.0))
+    with pytest.raises(ValueError):
+        kat.get_coor_before_collision((float("nan"), 0.5), (1.0, 1.0))
+
+
+@pytest.mark.parametrize("name", ["room1", "intel_lab", "maze1", "noise", "kat4x6"])
+def test_golden_img(sg, name):
+    g = golden("img_cc")
+    cc = sg.ImgCollisionChecker(kat_png() if name == "kat4x6" else map_png(name))
+    assert cc._img.shape == load_map(name).shape
+    P, Q = g[name + "_P"], g[name + "_Q"]
+    assert np.array_equal(cc.visible_batch(P, Q), unpack(g[name + "_visible"], len(P)))
+    pts, st = g[name + "_pts"], g[name + "_feasible_status"]
+    ok = st == 0
+    assert np.array_equal(cc.feasible_batch(pts[ok]), unpack(g[name + "_feasible"], len(pts))[ok])
+    with pytest.raises(OverflowError):
+        cc.feasible_batch(pts[~ok])
+    sel = g[name + "_cbc_sel"]
+    assert np.array_equal(cc.first_blocked_batch(P[sel], Q[sel]), g[name + "_cbc"])
+
+
+@pytest.mark.parametrize("group", [4, 8, 16, 32])
+@pytest.mark.parametrize("force_global", [0, 1])
+def test_all_kernel_variants_agree(sg, group, force_global):
+    """Every (lanes-per-edge, map-in-smem / map-in-L2) instantiation gives the same bits."""
+    from sbp_env_b200 import _lib
+
+    g = golden("img_cc")
+    cc = sg.ImgCollisionChecker(map_png("room1"))
+    P, Q = g["room1_P"], g["room1_Q"]
+    P, Q = np.tile(P, (8, 1)), np.tile(Q, (8, 1))
+    lib = _lib.load()
+    try:
+        lib.sbp_tune(b"visible_group", group)
+        lib.sbp_tune(b"force_global", force_global)
+        got = cc.visible_batch(P, Q)
+    finally:
+        lib.sbp_tune(b"visible_group", 0)
+        lib.sbp_tune(b"force_global", 0)
+    assert np.array_equal(got, np.tile(unpack(g["room1_visible"], len(g["room1_P"])), 8))
+
+
+@pytest.mark.parametrize("name", ["room1", "intel_lab", "maze1", "maze2", "4d", "noise", "test", "blank"])
+def test_random_edges_vs_oracle(sg, name):
+    free = load_map(name)
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png(name))
+    om = orc.Map(free)
+    rng = np.random.default_rng(hash(name) % 2 ** 31)
+    n = 300_000
+    P = (rng.random((n, 2)) * 1.2 - 0.1) * [W, H]
+    Q = (rng.random((n, 2)) * 1.2 - 0.1) * [W, H]
+    short = slice(0, n // 2)
+    Q[short] = P[short] + rng.standard_normal((n // 2, 2)) * 8
+    P[-1000:] -= [W, H]                       # negative (wrapping) region
+    assert np.array_equal(cc.visible_batch(P, Q), om.visible2d(P, Q))
+    assert np.array_equal(cc.feasible_batch(P), om.feasible2d(P))
+    sel = slice(0, 20000)
+    assert np.array_equal(cc.first_blocked_batch(P[sel], Q[sel]), om.coor_before_collision(P[sel], Q[sel]))
+
+
+def test_device_pointer_path_and_counter(sg):
+    import torch
+
+    free = load_map("maze1")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("maze1"))
+    om = orc.Map(free)
+    rng = np.random.default_rng(5)
+    n = 100_000
+    P, Q = rng.random((n, 2)) * [W, H], rng.random((n, 2)) * [W, H]
+    dP, dQ = torch.from_numpy(P).cuda(), torch.from_numpy(Q).cuda()
+    exp, full, tested = om.visible2d(P, Q, return_counts=True)
+    assert np.array_equal(cc.visible_batch(dP, dQ).cpu().numpy(), exp)
+    assert np.array_equal(cc.feasible_batch(dP).cpu().numpy(), om.feasible2d(P))
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    cc._visible_device(dP, dQ, px_tested=cnt)
+    got = int(cnt.item())
+    # the kernel tests pixels in chunks of G lanes: between the reference's
+    # until-first-hit count and the full line length
+    assert got <= int(full.sum())
+    assert got > 0
+
+
+def test_synthetic_large_grid_l2_path(sg):
+    """A 4096^2 blocky-noise grid (SURVEY.md 8(d) style): too big for shared memory, so
+    the L2 / global path is exercised; built on the device, checked against the oracle."""
+    import torch
+
+    rng = np.random.default_rng(4096)
+    coarse = rng.random((64, 64)) < 0.75
+    free = np.kron(coarse, np.ones((64, 64), bool))
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker.from_free_mask(torch.from_numpy(free.astype(np.uint8)).cuda())
+    assert not cc.device_map.info()["smem_resident"]
+    om = orc.Map(free)
+    n = 200_000
+    P, Q = rng.random((n, 2)) * [W, H], rng.random((n, 2)) * [W, H]
+    Q[: n // 2] = P[: n // 2] + rng.standard_normal((n // 2, 2)) * 40
+    assert np.array_equal(cc.visible_batch(P, Q), om.visible2d(P, Q))
+    assert np.array_equal(cc.feasible_batch(P), om.feasible2d(P))
+
+
+def test_properties_at_scale(sg):
+    """Size-independent properties on 4M edges: direction symmetry of the 2-D line
+    (SURVEY.md section 7), blank map => visible iff both endpoints in range, and
+    idempotence."""
+    free = load_map("intel_lab")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("intel_lab"))
+    rng = np.random.default_rng(11)
+    n = 4_000_000
+    P, Q = rng.random((n, 2)) * [W, H], rng.random((n, 2)) * [W, H]
+    a = cc.visible_batch(P, Q)
+    assert np.array_equal(a, cc.visible_batch(Q, P))
+    assert np.array_equal(a, cc.visible_batch(P, Q))
+    # visible => both endpoints feasible
+    fp, fq = cc.feasible_batch(P), cc.feasible_batch(Q)
+    assert not (a & ~(fp & fq)).any()
+    # zero-length edges == feasible
+    assert np.array_equal(cc.visible_batch(P, P), fp)
+    allfree = sg.ImgCollisionChecker.from_free_mask(np.ones((W, H), np.uint8))
+    P2 = (rng.random((100000, 2)) * 1.4 - 0.2) * [W, H]
+    Q2 = (rng.random((100000, 2)) * 1.4 - 0.2) * [W, H]
+    inr = lambda A: (A[:, 0] > -W - 1) & (A[:, 0] < W) & (A[:, 1] > -H - 1) & (A[:, 1] < H)
+    assert np.array_equal(allfree.visible_batch(P2, Q2), inr(P2) & inr(Q2))
+
+
+def test_stats_mock_deepcopy_pickle(sg):
+    sg.Stats.clear_instance()
+    cc = sg.ImgCollisionChecker(kat_png())
+    st = sg.Stats.get_instance()
+    assert cc.stats is st
+    cc.visible((0.5, 2.5), (1.5, 3.5))
+    cc.feasible((1.5, 0.5))
+    assert (st.visible_cnt, st.feasible_cnt) == (1, 1)
+    cc.visible_batch(np.zeros((7, 2)), np.ones((7, 2)))
+    cc.feasible_batch(np.zeros((5, 2)))
+    assert (st.visible_cnt, st.feasible_cnt) == (8, 6)
+    cc2 = copy.deepcopy(cc)                                    # tests/test_rrtPlanner.py:17
+    assert cc2.visible((0.5, 2.5), (1.5, 3.5))
+    assert cc2.device_map is cc.device_map
+    cc3 = pickle.loads(pickle.dumps(cc))
+    assert cc3.visible((0.5, 2.5), (1.5, 3.5)) and not cc3.feasible((3.5, 0.5))
+    cc2.visible = MagicMock(return_value=False)                # tests/test_rrtPlanner.py:31-33
+    assert not cc2.visible_batch(np.zeros((3, 2)), np.ones((3, 2))).any()
+    assert cc2.visible.call_count == 3
+
+
+def test_empty_batches(kat):
+    assert kat.visible_batch(np.zeros((0, 2)), np.zeros((0, 2))).shape == (0,)
+    assert kat.feasible_batch(np.zeros((0, 2))).shape == (0,)

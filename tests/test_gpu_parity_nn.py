@@ -1,0 +1,147 @@
+"""-m gpu: node store, nearest / kNN / radius queries against golden fixtures and the
+oracle.  Index sets bit-exact, fp64 distances bit-exact."""
+import numpy as np
+import pytest
+
+import c_oracle as orc
+from _util import golden, load_map, map_png
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sg():
+    import sbp_env_b200
+
+    return sbp_env_b200
+
+
+def test_reference_kat_nearest(sg):
+    # tests/test_rrtPlanner.py:136-148
+    poses = np.array([[0, 0], [1, 1], [2, 2], [3, 3.0]])
+    t = sg.NodeStore(2)
+    for p in poses:
+        t.append(p)
+    assert len(t) == 4 and np.array_equal(t.poses, poses)
+    for i, p in enumerate(poses):
+        assert t.nearest(p + 1e-2) == i
+
+
+@pytest.mark.parametrize("d", [2, 3, 4])
+def test_golden_nn(sg, d):
+    g = golden("nn")
+    poses, X = g[f"d{d}_poses"], g[f"d{d}_X"]
+    t = sg.NodeStore(d, capacity=16)          # forces capacity growth
+    t.extend(poses[:1000])
+    t.extend(poses[1000:])
+    assert np.array_equal(t.poses, poses)
+    idx, dist = t.knn(X, 1)
+    assert np.array_equal(idx[:, 0], g[f"d{d}_nearest"])
+    for k in (20, 7, 32):
+        idx, dist = t.knn(X, k)
+        if k <= 20:
+            assert np.array_equal(idx, g[f"d{d}_knn20"][:, :k])
+            assert np.array_equal(dist, g[f"d{d}_knn20_dist"][:, :k])
+        else:
+            oi, od = orc.knn(poses, X, k)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+    for ri in (0, 1):
+        rp, ix = t.near(X, float(g[f"d{d}_prm_r{ri}"]), "full", closed=False)
+        assert np.array_equal(rp, g[f"d{d}_prm_r{ri}_off"])
+        assert np.array_equal(ix, g[f"d{d}_prm_r{ri}_idx"])
+    mm = len(g[f"d{d}_xy_off"]) - 1
+    rp, ix = t.near(X[:mm], float(g[f"d{d}_xy_r"]), "xy", closed=True)
+    # engine.dist squares through libm pow: <= 1 ulp from the product, so
+    # membership can only differ for a distance within 1 ulp of r -- none in this fixture
+    assert np.array_equal(rp, g[f"d{d}_xy_off"])
+    assert np.array_equal(ix, g[f"d{d}_xy_idx"])
+
+
+@pytest.mark.parametrize("d,n,m,k", [(2, 50_000, 3000, 11), (2, 300_000, 5, 20), (4, 40_000, 700, 4),
+                                     (2, 1, 10, 3), (3, 7, 300, 16), (6, 5000, 40, 2)])
+def test_knn_vs_oracle(sg, d, n, m, k):
+    """Both kernels (thread-per-query batched with chunk merge; CTA-per-query wide)."""
+    rng = np.random.default_rng(d * 1000 + k)
+    poses = rng.random((n, d)) * 300
+    poses[: n // 10] = np.floor(poses[: n // 10] / 10) * 10      # exact ties
+    X = rng.random((m, d)) * 300
+    X[: m // 3] = np.floor(X[: m // 3] / 10) * 10 + 5
+    t = sg.NodeStore(d)
+    t.extend(poses)
+    idx, dist = t.knn(X, k)
+    oi, od = orc.knn(poses, X, k)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(dist, od)
+
+
+@pytest.mark.parametrize("metric,closed", [("full", False), ("full", True), ("xy", True), ("xy", False)])
+@pytest.mark.parametrize("d,n,m", [(2, 60_000, 1500), (2, 400_000, 3), (4, 30_000, 2)])
+def test_near_vs_oracle(sg, metric, closed, d, n, m):
+    rng = np.random.default_rng(n + m)
+    poses = np.floor(rng.random((n, d)) * 400)                    # integer lattice: d == r happens
+    X = np.floor(rng.random((m, d)) * 400)
+    t = sg.NodeStore(d)
+    t.extend(poses)
+    for r in (5.0, 13.0, 0.0):                                    # 5 and 13 are hypotenuses
+        rp, ix = t.near(X, r, metric, closed)
+        orp, oix = orc.near(poses, X, r, metric, closed)
+        assert np.array_equal(rp, orp), (r, metric, closed)
+        assert np.array_equal(ix, oix)
+
+
+def test_threshold_boundaries(sg):
+    """d < r vs d <= r decided on d^2, at radii straddling rounded sqrts."""
+    rng = np.random.default_rng(2)
+    poses = rng.random((5000, 2)) * 50
+    q = rng.random((1, 2)) * 50
+    t = sg.NodeStore(2)
+    t.extend(poses)
+    d = np.sort(np.linalg.norm(poses - q, axis=1))
+    for r in [d[10], np.nextafter(d[10], 0), np.nextafter(d[10], 99), d[777], 1e-300, 1e300, float("inf")]:
+        for closed in (False, True):
+            rp, ix = t.near(q, float(r), "full", closed)
+            orp, oix = orc.near(poses, q, float(r), "full", closed)
+            assert np.array_equal(ix, oix), (r, closed)
+
+
+def test_device_tensors_and_prm_connect(sg):
+    import torch
+
+    free = load_map("intel_lab")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("intel_lab"))
+    om = orc.Map(free)
+    rng = np.random.default_rng(0)
+    pts = rng.random((30000, 2)) * [W, H]
+    pts = pts[om.feasible2d(pts)][:8000]
+    pts[100] = pts[50]                                           # a duplicated node
+    t = sg.NodeStore(2)
+    t.extend(torch.from_numpy(pts).cuda())
+    k = 10
+    nbr, vis, dist = sg.prm_connect_knn(cc, t, k, return_dist=True)
+    nbr, vis = nbr.cpu().numpy(), vis.cpu().numpy()
+    oi, od = orc.knn(pts, pts, k + 1)
+    for v in range(len(pts)):
+        row = oi[v].tolist()
+        row.remove(v) if v in row else row.pop()
+        assert nbr[v].tolist() == row, v
+    exp = om.visible2d(pts[nbr.reshape(-1)], np.repeat(pts, k, axis=0)).reshape(-1, k)
+    exp &= nbr != np.arange(len(pts))[:, None]
+    assert np.array_equal(vis, exp)
+    # a shard of the rows gives the same rows
+    nbr2, vis2 = sg.prm_connect_knn(cc, t, k, rows=(1234, 500))
+    assert np.array_equal(nbr2.cpu().numpy(), nbr[1234:1734])
+    assert np.array_equal(vis2.cpu().numpy(), vis[1234:1734])
+    src, dst = sg.roadmap_edges_to_host(nbr, vis)
+    assert len(src) == int(vis.sum())
+
+
+def test_empty_store_and_truncate(sg):
+    t = sg.NodeStore(2)
+    idx, dist = t.knn(np.zeros((3, 2)), 2)
+    assert (idx == -1).all() and np.isinf(dist).all()
+    rp, ix = t.near(np.zeros((3, 2)), 5.0)
+    assert rp.tolist() == [0, 0, 0, 0] and len(ix) == 0
+    t.extend(np.arange(20, dtype=float).reshape(10, 2))
+    t.truncate(4)
+    assert len(t) == 4 and t.nearest([100.0, 100.0]) == 3
