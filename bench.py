@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path on BASELINE.json configs[1]: PRM roadmap connection on
+maps/intel_lab (579x581), 50 000 free samples, k = 10 nearest neighbours, the
+500 000 candidate edges checked through visible_batch.
+
+One step = one pass of the hot path over one batch: brute-force fp64 kNN of 50 000
+rows against the 50 000-node roadmap (2.5e9 distance evaluations), edge gather, and
+integer-Bresenham visibility of the 500 000 candidate edges.  At N GPUs (weak
+scaling) rank 0's batch is the roadmap's own nodes (= PRM build, self excluded) and
+rank r > 0 connects a further batch of 50 000 free samples to the replicated
+roadmap; the per-rank neighbour/visibility blocks are all-gathered (NCCL) inside the
+step -- the only collective, used to assemble the adjacency.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`--impl reference` times the CPU restatement of the reference (oracle/, all host
+threads) on the same workload, bounded sample per step.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_NODES = 50_000
+K_NN = 10
+MAP = "intel_lab"
+METRIC = "edge collision checks/sec (PRM candidate edges: brute-force kNN connect + visible_batch)"
+UNIT = "edges/s"
+WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
+            "candidate edges per step (kNN 2.5e9 fp64 distance evals + Bresenham visible_batch)")
+
+
+def load_free():
+    from _util import load_map
+
+    return load_map(MAP)            # bool [W][H], the reference's `_img == 1`
+
+
+def draw_free_samples(free, n, seed, feasible_fn):
+    """First n accepted of default_rng(seed).random((., 2)) * [W, H] filtered by
+    feasible."""
+    W, H = free.shape
+    rng = np.random.default_rng(seed)
+    out = []
+    have = 0
+    while have < n:
+        c = rng.random((2 * n, 2)) * [W, H]
+        c = c[feasible_fn(c)]
+        out.append(c)
+        have += len(c)
+    return np.ascontiguousarray(np.concatenate(out)[:n])
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, mxc = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                    "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            sm = [float(x[1].split(",")[1]) for x in self.rows[-3:] if len(x[1].split(",")) > 2] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ ours -----
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import sbp_env_b200 as sg
+    from sbp_env_b200 import _lib
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    free = load_free()
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8), device=local)
+    ctx = cc.device_map.ctx
+    nodes = draw_free_samples(free, N_NODES, 0, cc.feasible_batch)
+    tree = sg.NodeStore(2, capacity=N_NODES, device=local)
+    tree.extend(nodes)
+    if rank == 0:
+        batch_host, queries = nodes, None
+    else:
+        batch_host = draw_free_samples(free, N_NODES, 100 + rank, cc.feasible_batch)
+        queries = torch.from_numpy(batch_host).to(dev)
+    m, k = N_NODES, K_NN
+    edges_per_rank = m * k
+    gathered = {}
+
+    names = ("knn", "edges", "visible", "gather")
+
+    def step(ev=None):
+        idx = [0]
+
+        def mark(_name):
+            if ev is not None:
+                ev[idx[0]].record()
+                idx[0] += 1
+
+        nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
+        if world > 1:
+            nb_all = torch.empty((world * m, k), dtype=torch.int64, device=dev)
+            vs_all = torch.empty((world * m, k), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(nb_all, nbr)
+            dist.all_gather_into_tensor(vs_all, vis.to(torch.uint8))
+            gathered["nbr"], gathered["vis"] = nb_all, vs_all
+        else:
+            gathered["nbr"], gathered["vis"] = nbr, vis
+        mark("gather")
+        return nbr, vis
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in names] for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.zero_()                      # evict L2 between timed iterations (not timed)
+        starts[s].record()
+        step(phase_ev[s])
+        ends[s].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    launches = ctx.launches - launches0
+    step_ms = np.array([starts[s].elapsed_time(ends[s]) for s in range(args.steps)])
+    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    ph = {}
+    for i, nme in enumerate(names):
+        prev = [starts[s] if i == 0 else phase_ev[s][i - 1] for s in range(args.steps)]
+        ph[nme] = float(np.mean([prev[s].elapsed_time(phase_ev[s][i]) for s in range(args.steps)]))
+
+    # parity spot check of the timed configuration (outside the timed region)
+    nbr, vis = step()
+    torch.cuda.synchronize()
+    n_vis = int(vis.sum().item())
+
+    # ---- end to end through the public API with host buffers -------------------
+    pinned = torch.from_numpy(batch_host).pin_memory()
+    nbr_h = torch.empty((m, k), dtype=torch.int64).pin_memory()
+    vis_h = torch.empty((m, k), dtype=torch.bool).pin_memory()
+    tree2 = sg.NodeStore(2, capacity=N_NODES, device=local) if rank == 0 else None
+
+    def e2e_step():
+        x = pinned.to(dev, non_blocking=True)              # H2D of this step's samples
+        if rank == 0:
+            tree2.truncate(0)
+            tree2.extend(x)                                # roadmap rebuilt from the samples
+            nb, vs = sg.prm_connect_knn(cc, tree2, k)
+        else:
+            nb, vs = sg.prm_connect_knn(cc, tree, k, queries=x)
+        nbr_h.copy_(nb, non_blocking=True)                 # D2H of the adjacency block
+        vis_h.copy_(vs, non_blocking=True)
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for s in range(args.steps):
+        flush.zero_()
+        e_s[s].record()
+        e2e_step()
+        e_e[s].record()
+    torch.cuda.synchronize()
+    e2e_ms = torch.tensor([sum(e_s[s].elapsed_time(e_e[s]) for s in range(args.steps))], device=dev,
+                          dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    e2e_ms = float(e2e_ms.item())
+    assert int(vis_h.sum()) == n_vis, "e2e result differs from the device-resident run"
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+    evals = float(m) * float(len(tree))
+    knn_s = ph["knn"] / 1e3
+    q_tile = 128
+    alg_bytes = evals * 8 * 2 / q_tile + m * 16 + m * (k + 1) * 8     # node stream + queries + idx out
+    roof = {"kernel": "k_knn_batched<2,16> (+k_knn_merge), the 'knn' phase", "bound": "hbm",
+            "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "note": "brute-force kNN with 128 queries sharing each streamed node is fp64-issue bound, "
+                    "not HBM bound: see alu"}
+
+    import ctypes as C
+
+    lib = _lib.load()
+
+    def mb(which, nbytes, iters):
+        ms, units = C.c_double(), C.c_double()
+        _lib.check(lib.sbp_microbench(ctx.handle, which, nbytes, iters, C.byref(ms), C.byref(units)))
+        return units.value / (ms.value / 1e3)
+
+    fp64_peak = mb(2, 0, 4096)
+    roof["alu"] = {"fp64_ops_per_eval": 6, "achieved_fp64_ops_per_s": evals * 6 / knn_s,
+                   "measured_peak_unfused_fp64_ops_per_s": fp64_peak,
+                   "frac": evals * 6 / knn_s / fp64_peak}
+
+    # ---- micro: uniform random edge batches on the same map ------
+    micro = {}
+    smem_gather = mb(0, int(cc.device_map.info()["packed_bytes"]), 2048)
+    l2_gather = mb(1, 64 << 20, 512)
+    hbm_gather = mb(1, 8 << 30, 512)
+    micro["measured_gather_peaks"] = {"smem_random_word_gathers_per_s": smem_gather,
+                                      "l2_random_sector_gathers_per_s_64MiB": l2_gather,
+                                      "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
+
+    def time_visible(P, Q, iters=5):
+        cc.visible_batch(P, Q)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a.record()
+            r = cc.visible_batch(P, Q)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        px = (torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
+                            (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item()
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+        cc._visible_device(P, Q, px_tested=cnt)
+        t = float(np.median(ts)) / 1e3
+        n = P.shape[0]
+        ab = 33.0 * n + 0.125 * px
+        return {"edges": n, "ms": t * 1e3, "interpolants_full_line": px,
+                "interpolants_per_s": px / t, "pixel_tests_executed": int(cnt.item()),
+                "pixel_tests_per_s": int(cnt.item()) / t, "edges_per_s": n / t,
+                "visible_fraction": float(r.float().mean().item()),
+                "algorithmic_GBps": ab / t / 1e9, "hbm_frac": ab / t / 1e9 / hbm_peak}
+
+    n_u = 1 << 24
+    P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+    Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+    micro["uniform_2^24_edges"] = time_visible(P, Q)
+    fr = torch.from_numpy(nodes).to(dev)
+    for L in (8, 32, 128):
+        n_b = 1 << 22
+        base = fr[torch.randint(0, len(nodes), (n_b,), generator=g, device=dev)]
+        ang = torch.rand(n_b, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi)
+        Qb = base + torch.stack([ang.cos(), ang.sin()], 1) * L
+        micro[f"free_start_len{L}_2^22_edges"] = time_visible(base, Qb)
+    del P, Q
+
+    # single-query nearest over a 1M-node tree (RRT-style, latency bound)
+    big = sg.NodeStore(2, capacity=1 << 20, device=local)
+    big.extend(torch.rand((1 << 20, 2), generator=g, device=dev, dtype=torch.float64) * scale)
+    q1 = torch.rand((1, 2), generator=g, device=dev, dtype=torch.float64) * scale
+    big.knn(q1, 1)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(50):
+        big.knn(q1, 1)
+    b.record()
+    torch.cuda.synchronize()
+    t1 = a.elapsed_time(b) / 50 / 1e3
+    micro["nearest_1q_over_2^20_nodes"] = {"ms": t1 * 1e3, "dist_evals_per_s": (1 << 20) / t1,
+                                           "node_stream_GBps": (1 << 20) * 16 / t1 / 1e9}
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+    cpu = cpu_prm_sample(free, nodes, target_s=12.0) if world == 1 else None
+
+    out = {
+        "metric": METRIC, "value": world * edges_per_rank * args.steps / (total_ms / 1e3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map": "intel_lab 579x581 (occupancy fixture tests/golden/maps.npz)",
+                   "nodes": N_NODES, "k": K_NN, "edges_per_step_per_gpu": edges_per_rank,
+                   "dist_evals_per_step_per_gpu": evals, "l2": "flushed (256 MiB write) between timed steps",
+                   "multi_gpu": "rank r connects batch r of 50000 samples to the replicated roadmap; "
+                                "NCCL all-gather of the neighbour/visibility blocks inside the step"},
+        "clocks": clocks,
+        "e2e": {"value": world * edges_per_rank * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+                "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(pinned.numel() * 8),
+                "d2h_bytes_per_step": int(nbr_h.numel() * 8 + vis_h.numel())},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "phases_ms": ph,
+        "submetrics": {"knn_dist_evals_per_s_per_gpu": evals / knn_s,
+                       "visible_batch_edges_per_s_per_gpu": edges_per_rank / (ph["visible"] / 1e3),
+                       "prm_build_ms": total_ms / args.steps,
+                       "roadmap_edges_visible": n_vis},
+        "micro": micro,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------ CPU legs --------
+def cpu_prm_rows(om, nodes, first, count, k):
+    """The oracle port of the step for `count` rows: kNN (k+1, self dropped) + visible."""
+    import c_oracle as orc
+
+    idx, _ = orc.knn(nodes, nodes[first:first + count], k + 1)
+    rows = np.arange(first, first + count)[:, None]
+    is_self = idx == rows
+    drop = np.where(is_self.any(1), is_self.argmax(1), k)
+    keep = np.ones_like(idx, bool)
+    keep[np.arange(count), drop] = False
+    nbr = idx[keep].reshape(count, k)
+    vis = om.visible2d(nodes[nbr.reshape(-1)], np.repeat(nodes[first:first + count], k, axis=0))
+    return nbr, vis.reshape(count, k)
+
+
+def cpu_prm_sample(free, nodes, target_s):
+    import c_oracle as orc
+
+    cores = os.cpu_count() or 1
+    orc.set_threads(cores)
+    om = orc.Map(free)
+    t0 = time.perf_counter()
+    cpu_prm_rows(om, nodes, 0, 256, K_NN)
+    probe = time.perf_counter() - t0
+    rows = int(min(len(nodes), max(256, 256 * target_s / max(probe, 1e-4))))
+    t0 = time.perf_counter()
+    cpu_prm_rows(om, nodes, 0, rows, K_NN)
+    dt = time.perf_counter() - t0
+    return {"value": rows * K_NN / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"first {rows} of {len(nodes)} rows of the same workload (kNN k+1 against all "
+                      f"{len(nodes)} nodes + visible of their {rows * K_NN} edges), oracle/oracle.c with "
+                      f"OpenMP on {cores} threads, {dt:.2f} s"}
+
+
+def run_reference(args):
+    """The reference's algorithm on the host cores (oracle C port, all threads)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    import c_oracle as orc
+
+    cores = os.cpu_count() or 1
+    orc.set_threads(cores)
+    free = load_free()
+    om = orc.Map(free)
+    nodes = draw_free_samples(free, N_NODES, 0, om.feasible2d)
+    t0 = time.perf_counter()
+    cpu_prm_rows(om, nodes, 0, 256, K_NN)
+    probe = time.perf_counter() - t0
+    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
+    rows = int(min(len(nodes), max(256, 256 * min(budget, 6.0) / max(probe, 1e-4))))
+    for _ in range(args.warmup):
+        cpu_prm_rows(om, nodes, 0, rows, K_NN)
+    ts = []
+    for s in range(args.steps):
+        first = (s * rows) % max(1, len(nodes) - rows)
+        t0 = time.perf_counter()
+        cpu_prm_rows(om, nodes, first, rows, K_NN)
+        ts.append(time.perf_counter() - t0)
+    val = rows * K_NN * len(ts) / sum(ts)
+    sample = (f"{rows} of {len(nodes)} rows per step (kNN k+1 against all nodes + visible of "
+              f"{rows * K_NN} edges), oracle/oracle.c OpenMP x{cores}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "nodes": N_NODES, "k": K_NN},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -192,6 +192,17 @@ int32_t sbp_nodes_near_host(sbp_nodes *nodes, const double *X, int64_t m, double
  * Entries with nbr < 0 or nbr == self produce valid = 0 and a degenerate edge. */
 int32_t sbp_nodes_gather_edges(sbp_nodes *nodes, const int64_t *nbr, int64_t m, int32_t k,
                                int64_t first_row, double *P, double *Q, uint8_t *valid);
+/* kNN rows -> candidate-edge batch in one pass (all pointers device).
+ *  X == NULL: row i is stored node first_row+i; its own entry (`m_g is v`,
+ *    prmPlanner.py:94-95) is dropped from nbr_in [m][k_in] -- the column equal to the
+ *    row index if present, else the last column -- leaving k_out = k_in-1 columns.
+ *  X != NULL: row i is the external query X[i] ([m][d]); k_out = k_in columns
+ *    (connecting new samples / start / goal to the roadmap, prmPlanner.py:131-138).
+ * Writes nbr_out [m][k_out], P = neighbour pose, Q = row pose ([m*k_out][d]) and
+ * valid [m*k_out] (0 where the neighbour slot is empty). */
+int32_t sbp_nodes_knn_edges(sbp_nodes *nodes, const int64_t *nbr_in, int64_t m, int32_t k_in,
+                            int64_t first_row, const double *X, int64_t *nbr_out, double *P,
+                            double *Q, uint8_t *valid);
 
 #ifdef __cplusplus
 }

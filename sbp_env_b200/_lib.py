@@ -64,12 +64,15 @@ _SIGNATURES = {
     "sbp_nodes_knn_host": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "sbp_nodes_near_host": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, C.POINTER(_i64)],
     "sbp_nodes_gather_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp],
+    "sbp_nodes_knn_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "sbp_tune": [C.c_char_p, _i64],
+    "sbp_microbench": [_vp, _i32, _i64, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
 }
 _RESTYPE = {"sbp_last_error": C.c_char_p}
 
-#: entry points declared in include/sbp_gpu.h (sbp_tune is an undeclared tuning hook)
-ABI_SYMBOLS = tuple(k for k in _SIGNATURES if k != "sbp_tune")
+#: entry points declared in include/sbp_gpu.h (sbp_tune / sbp_microbench are undeclared
+#: tuning / measurement hooks)
+ABI_SYMBOLS = tuple(k for k in _SIGNATURES if k not in ("sbp_tune", "sbp_microbench"))
 
 
 def load():

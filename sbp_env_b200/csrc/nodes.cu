@@ -775,3 +775,59 @@ extern "C" int32_t sbp_nodes_gather_edges(sbp_nodes *s, const int64_t *nbr, int6
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
 }
+
+// kNN rows -> candidate edges, self entry dropped (see sbp_gpu.h).  One thread per
+// (row, output column): the position of the self column is found by a short scan of
+// the row's k_in entries.
+__global__ void k_knn_edges(const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
+                            const int64_t *__restrict__ nbr_in, int64_t m, int k_in, int k_out,
+                            int64_t first_row, const double *__restrict__ X,
+                            int64_t *__restrict__ nbr_out, double *__restrict__ P,
+                            double *__restrict__ Q, uint8_t *__restrict__ valid) {
+    int64_t total = m * k_out;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = t / k_out;
+        int j = (int)(t - i * k_out);
+        const int64_t *row = nbr_in + i * k_in;
+        int src_col = j;
+        int64_t self = -1;
+        if (!X) {
+            self = first_row + i;
+            int drop = k_in - 1;
+            for (int c = 0; c < k_in; ++c)
+                if (row[c] == self) { drop = c; break; }
+            src_col = j < drop ? j : j + 1;
+        }
+        int64_t nb = row[src_col];
+        bool ok = nb >= 0 && nb < n;
+        nbr_out[t] = nb;
+        for (int c = 0; c < d; ++c) {
+            double qv = X ? X[i * d + c] : soa[(int64_t)c * capacity + self];
+            P[t * d + c] = ok ? soa[(int64_t)c * capacity + nb] : qv;
+            Q[t * d + c] = qv;
+        }
+        valid[t] = ok ? 1 : 0;
+    }
+}
+
+extern "C" int32_t sbp_nodes_knn_edges(sbp_nodes *s, const int64_t *nbr_in, int64_t m,
+                                       int32_t k_in, int64_t first_row, const double *X,
+                                       int64_t *nbr_out, double *P, double *Q, uint8_t *valid) {
+    SBP_REQUIRE(s && (m == 0 || (nbr_in && nbr_out && P && Q && valid)),
+                "sbp_nodes_knn_edges: NULL argument");
+    int k_out = X ? k_in : k_in - 1;
+    SBP_REQUIRE(m >= 0 && k_out >= 1, "sbp_nodes_knn_edges: bad sizes");
+    SBP_REQUIRE(X || (first_row >= 0 && first_row + m <= s->n), "sbp_nodes_knn_edges: row range");
+    if (m == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int64_t total = m * k_out;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    k_knn_edges<<<blocks, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d, nbr_in, m, k_in,
+                                                 k_out, first_row, X, nbr_out, P, Q, valid);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}

@@ -170,6 +170,29 @@ class NodeStore:
                                                  ptr(Q), ptr(valid)), "sbp_nodes_gather_edges")
         return P, Q, valid
 
+    def knn_edges(self, nbr_in, first_row: int = 0, queries=None):
+        """kNN rows -> candidate-edge batch in one launch: ``(nbr, P, Q, valid)``.
+
+        Without ``queries`` row i is stored node ``first_row + i`` and its own entry is
+        dropped (``m_g is v``, prmPlanner.py:94-95): k_out = k_in - 1.  With ``queries``
+        ([m][d] CUDA tensor of external points) all k_in columns are kept."""
+        import torch
+
+        self.ctx.use_torch_stream()
+        nbr_in = nbr_in.contiguous()
+        m, k_in = nbr_in.shape
+        k_out = k_in if queries is not None else k_in - 1
+        dev = nbr_in.device
+        nbr = torch.empty((m, k_out), dtype=torch.int64, device=dev)
+        P = torch.empty((m * k_out, self.dim), dtype=torch.float64, device=dev)
+        Q = torch.empty((m * k_out, self.dim), dtype=torch.float64, device=dev)
+        valid = torch.empty(m * k_out, dtype=torch.uint8, device=dev)
+        X = as_device_f64(queries, self.dim) if queries is not None else None
+        check(_lib.load().sbp_nodes_knn_edges(self._h, ptr(nbr_in), m, k_in, int(first_row), ptr(X),
+                                              ptr(nbr), ptr(P), ptr(Q), ptr(valid)),
+              "sbp_nodes_knn_edges")
+        return nbr, P, Q, valid
+
     def __del__(self):
         try:
             if getattr(self, "_h", None) is not None:

@@ -32,7 +32,8 @@ def near(tree, X, r, metric="full", closed=False):
     return tree.near(X, r, metric=metric, closed=closed)
 
 
-def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False):
+def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, queries=None,
+                    mark=None):
     """Candidate roadmap edges of every stored node to its k nearest other nodes and
     their visibility, entirely on the device.
 
@@ -44,29 +45,38 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False):
 
     :param rows: optional ``(first, count)`` to process a slice of the nodes (the
         multi-GPU shard of this rank); neighbours are still searched among all nodes.
+    :param queries: optional CUDA tensor [m][d] of external samples to connect to the
+        stored roadmap instead of the stored rows (no self entry to drop).
+    :param mark: optional callable ``mark(name)`` invoked between the phases
+        ("knn", "edges", "visible") on the launching stream (bench.py records CUDA
+        events there).
     :return: ``nbr`` int64 [m][k] (CUDA), ``vis`` bool [m][k] (CUDA) and optionally
-        ``dist`` fp64 [m][k].
+        ``dist`` fp64 [m][k] (only for ``queries``; stored rows include the self column).
     """
-    import torch
-
-    n = len(tree)
-    first, count = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
-    dev = torch.device("cuda", tree.ctx.device)
     tree.ctx.use_torch_stream()
-    X = tree.rows_device(first, count)
-    idx, dist = tree.knn(X, k + 1, return_dist=return_dist)
-    row_ids = torch.arange(first, first + count, device=dev, dtype=torch.int64).unsqueeze(1)
-    is_self = idx == row_ids
-    # drop the self column if present, else the farthest column
-    drop = torch.where(is_self.any(1), is_self.to(torch.int8).argmax(1),
-                       torch.full((count,), k, device=dev, dtype=torch.int64))
-    keep = torch.ones_like(idx, dtype=torch.bool)
-    keep.scatter_(1, drop.unsqueeze(1), False)
-    nbr = idx[keep].reshape(count, k)
-    P, Q, valid = tree.gather_edges(nbr, first_row=first)
+    if queries is not None:
+        X = queries
+        count = X.shape[0]
+        idx, dist = tree.knn(X, k, return_dist=return_dist)
+        if mark:
+            mark("knn")
+        nbr, P, Q, valid = tree.knn_edges(idx, queries=X)
+    else:
+        n = len(tree)
+        first, count = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+        X = tree.rows_device(first, count)
+        idx, dist = tree.knn(X, k + 1, return_dist=False)
+        if mark:
+            mark("knn")
+        nbr, P, Q, valid = tree.knn_edges(idx, first_row=first)
+        dist = None
+    if mark:
+        mark("edges")
     vis = cc.visible_batch(P, Q).reshape(count, k) & valid.bool().reshape(count, k)
+    if mark:
+        mark("visible")
     if return_dist:
-        return nbr, vis, dist[keep].reshape(count, k)
+        return nbr, vis, dist
     return nbr, vis
 
 

@@ -118,7 +118,7 @@ def test_device_tensors_and_prm_connect(sg):
     t = sg.NodeStore(2)
     t.extend(torch.from_numpy(pts).cuda())
     k = 10
-    nbr, vis, dist = sg.prm_connect_knn(cc, t, k, return_dist=True)
+    nbr, vis = sg.prm_connect_knn(cc, t, k)
     nbr, vis = nbr.cpu().numpy(), vis.cpu().numpy()
     oi, od = orc.knn(pts, pts, k + 1)
     for v in range(len(pts)):
@@ -145,3 +145,23 @@ def test_empty_store_and_truncate(sg):
     t.extend(np.arange(20, dtype=float).reshape(10, 2))
     t.truncate(4)
     assert len(t) == 4 and t.nearest([100.0, 100.0]) == 3
+
+
+def test_prm_connect_external_queries(sg):
+    import torch
+
+    free = load_map("maze1")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("maze1"))
+    om = orc.Map(free)
+    rng = np.random.default_rng(9)
+    nodes = rng.random((5000, 2)) * [W, H]
+    X = rng.random((700, 2)) * [W, H]
+    t = sg.NodeStore(2)
+    t.extend(nodes)
+    k = 6
+    nbr, vis, dist = sg.prm_connect_knn(cc, t, k, queries=torch.from_numpy(X).cuda(), return_dist=True)
+    oi, od = orc.knn(nodes, X, k)
+    assert np.array_equal(nbr.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
+    exp = om.visible2d(nodes[oi.reshape(-1)], np.repeat(X, k, axis=0)).reshape(-1, k)
+    assert np.array_equal(vis.cpu().numpy(), exp)
