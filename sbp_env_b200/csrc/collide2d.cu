@@ -153,6 +153,138 @@ k_visible2d(MapView mv, const double2 *__restrict__ P, const double2 *__restrict
     }
 }
 
+// ------------------------------------------------------ K2 (adaptive) -------
+// Lane-per-edge first, warp-per-edge for the stragglers.
+//   phase A  every lane owns one edge of a 32-edge batch: coalesced endpoint loads,
+//            truncation / range check / canonicalisation once per edge (not once per
+//            lane group), the END pixel tested first (a blocked endpoint is the most
+//            likely early exit), then the classic error-accumulating walk from the
+//            canonical start -- no division, ~16 instructions per pixel per lane.
+//   phase B  as soon as fewer than COOP_BELOW lanes are still walking (the rest have
+//            finished or hit an obstacle) the survivors are finished one at a time by
+//            the whole warp: their walk state is broadcast with shuffles and lane j
+//            tests pixel j, j+32, ... of the remainder via the closed form
+//            m_j = floor((j*|db| + da-1-err) / da), ballot for the early exit.
+// Batches of equal-length edges (PRM k-NN candidates) therefore run entirely in the
+// divergence-free phase A; heavy-tailed batches (uniform random edges) hand their few
+// long edges to phase B instead of idling 31 lanes behind them.
+template <bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(1024)
+k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *__restrict__ Q,
+                     int64_t n, uint8_t *__restrict__ out, int32_t *__restrict__ flags,
+                     unsigned long long *__restrict__ px_tested, int COOP_BELOW) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t n_round = (n + 31) & ~(int64_t)31;       // whole warps iterate together
+    int myflag = 0;
+    unsigned long long tested = 0;
+
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
+    if (e < n) { p = P[e]; q = Q[e]; }
+    for (; e < n_round; e += stride) {
+        const bool valid = e < n;
+        const double2 cp = p, cq = q;
+        const int64_t en = e + stride;                      // prefetch the next batch
+        if (en < n) { p = P[en]; q = Q[en]; }
+
+        Edge2D ed = make_edge(cp.x, cp.y, cq.x, cq.y, mv.W, mv.H);
+        if (valid) myflag |= ed.flag;
+        bool result = valid && ed.walk;
+        // end pixel first (:204-206: it is a member of the list)
+        if (result) {
+            result = map_free<!SMEM>(words, mv.SX, wrap_index(ed.x2, mv.W), wrap_index(ed.y2, mv.H));
+            if (COUNT) tested += 1ull;
+        }
+        int a = ed.a1, b = ed.b1;
+        const int a2 = ed.a1 + (int)ed.da;
+        int err = (int)(ed.da >> 1);                        // :198
+        bool active = result;
+        unsigned bal;
+        // ---- phase A ---------------------------------------------------------
+        // Hand-over rule: finishing sequentially costs ~18 instructions per step for
+        // the longest remaining walk; finishing the walkers one by one with the whole
+        // warp costs ~45 + 25*ceil(L/32) each.  The break-even number of walkers grows
+        // with the remaining length (measured: 1 at 4 px, ~5 at 16 px, 12-16 from
+        // 64 px on), approximated by L/4 capped at COOP_BELOW; re-evaluated every 4
+        // steps with one REDUX.
+        while (true) {
+            bal = __ballot_sync(FULL, active);
+            const int nact = __popc(bal);
+            if (nact == 0) break;
+            const int lmax = __reduce_max_sync(FULL, active ? a2 - a + 1 : 0);
+            int thr = lmax >> 2;
+            thr = thr < 1 ? 1 : thr > COOP_BELOW ? COOP_BELOW : thr;
+            if (nact < thr) break;
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                if (active) {
+                    int x = ed.steep ? b : a, y = ed.steep ? a : b;          // :205
+                    bool fr = map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H));
+                    if (COUNT) tested += 1ull;
+                    err -= (int)ed.adb;                                      // :207-210
+                    if (err < 0) { b += ed.ystep; err += (int)ed.da; }
+                    ++a;
+                    if (!fr) { result = false; active = false; }
+                    else if (a > a2) active = false;
+                }
+            }
+        }
+        // ---- phase B ---------------------------------------------------------
+        while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const int s_a = __shfl_sync(FULL, a, src), s_b = __shfl_sync(FULL, b, src);
+            const int s_err = __shfl_sync(FULL, err, src);
+            const uint32_t s_da = __shfl_sync(FULL, ed.da, src), s_adb = __shfl_sync(FULL, ed.adb, src);
+            const int s_pack = __shfl_sync(FULL, (ed.ystep > 0 ? 1 : 0) | (ed.steep ? 2 : 0), src);
+            const int s_a2 = __shfl_sync(FULL, a2, src);
+            const int ystep = (s_pack & 1) ? 1 : -1;
+            const bool steep = (s_pack & 2) != 0;
+            const uint32_t left = (uint32_t)(s_a2 - s_a + 1);           // pixels still to test (>= 1)
+            // lane j: m = floor((j*adb + da-1-err) / da); stride 32: (sq, sr) = divmod(32*adb, da)
+            uint32_t m = 0, rem = 0, sq = 0, sr = 0;
+            if (s_da != 0u) {
+                const double inv = 1.0 / (double)s_da;
+                unsigned long long u = (unsigned long long)lane * s_adb + (s_da - 1u - (uint32_t)s_err);
+                unsigned long long qq = (unsigned long long)((double)u * inv);
+                long long r = (long long)u - (long long)qq * (long long)s_da;
+                if (r < 0) { --qq; r += s_da; } else if (r >= (long long)s_da) { ++qq; r -= s_da; }
+                m = (uint32_t)qq; rem = (uint32_t)r;
+                uint32_t s32 = 32u * s_adb;
+                sq = s32 / s_da; sr = s32 - sq * s_da;
+            }
+            bool hit = false;
+            for (uint32_t base = 0; base < left; base += 32u) {
+                const uint32_t j = base + (uint32_t)lane;
+                bool blk = false;
+                if (j < left) {
+                    int aa = s_a + (int)j, bb = s_b + ystep * (int)m;
+                    int x = steep ? bb : aa, y = steep ? aa : bb;
+                    blk = !map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H));
+                    if (COUNT) tested += 1ull;
+                }
+                if (__any_sync(FULL, blk)) { hit = true; break; }
+                m += sq; rem += sr;
+                if (rem >= s_da && s_da != 0u) { rem -= s_da; ++m; }
+            }
+            if (lane == src) result = !hit;
+        }
+        if (valid) out[e] = result ? 1 : 0;
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(FULL, tested, o);
+        if (lane == 0 && tested && px_tested) atomicAdd(px_tested, tested);
+    }
+}
+
 // --------------------------------------------------------------- K2b -------
 // First blocked pixel in start->end order (or the end pixel).  One warp per edge,
 // lanes take consecutive ORIGINAL indices o; the canonical index is o or
@@ -280,11 +412,15 @@ extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint
     return SBP_OK;
 }
 
-int g_visible_group = 0;   // 0 = auto; 4/8/16/32 force a group width (tuning knob)
+int g_visible_group = 0;   // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
+int g_coop_below = 12;     // adaptive kernel: cap of the hand-over threshold (walkers)
 int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
+extern int g_knn_chunks;
 
 extern "C" int32_t sbp_tune(const char *key, int64_t value) {
     if (!strcmp(key, "visible_group")) { g_visible_group = (int)value; return SBP_OK; }
+    if (!strcmp(key, "coop_below")) { g_coop_below = (int)value; return SBP_OK; }
+    if (!strcmp(key, "knn_chunks")) { g_knn_chunks = (int)value; return SBP_OK; }
     if (!strcmp(key, "force_global")) { g_force_global = (int)value; return SBP_OK; }
     sbp_set_error("sbp_tune: unknown key %s", key);
     return SBP_ERR_ARG;
@@ -322,13 +458,39 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
     bool smem = !g_force_global && map->smem_resident &&
                 n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
     unsigned long long *px = (unsigned long long *)px_tested;
-    int G = g_visible_group ? g_visible_group : 8;
-    switch (G) {
+    if (g_visible_group == 0) {
+        LaunchCfg c;
+        c.smem = smem ? (size_t)map->packed_bytes : 0;
+        c.threads = (smem && c.smem > 110 * 1024) ? 1024 : 512;
+        c.grid = 0;
+        int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
+        const double2 *p2 = (const double2 *)P, *q2 = (const double2 *)Q;
+#define SBP_LAUNCH_ADP(SM, CT)                                                                    \
+    do {                                                                                           \
+        int32_t rc = set_smem(k_visible2d_adaptive<SM, CT>, c.smem);                               \
+        if (rc) return rc;                                                                         \
+        int per_sm = 0;                                                                            \
+        SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
+            &per_sm, k_visible2d_adaptive<SM, CT>, c.threads, c.smem));                            \
+        c.grid = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);                                        \
+        int64_t need = (n + c.threads - 1) / c.threads;                                            \
+        if (need < c.grid) c.grid = (int)need;                                                     \
+        k_visible2d_adaptive<SM, CT><<<c.grid, c.threads, c.smem, ctx->stream>>>(                  \
+            map->view, p2, q2, n, out, flags, px, coop);                                           \
+    } while (0)
+        if (smem) { if (px) SBP_LAUNCH_ADP(true, true); else SBP_LAUNCH_ADP(true, false); }
+        else      { if (px) SBP_LAUNCH_ADP(false, true); else SBP_LAUNCH_ADP(false, false); }
+#undef SBP_LAUNCH_ADP
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
+    switch (g_visible_group) {
         case 4: return launch_visible<4>(map, P, Q, n, out, flags, px, smem);
         case 8: return launch_visible<8>(map, P, Q, n, out, flags, px, smem);
         case 16: return launch_visible<16>(map, P, Q, n, out, flags, px, smem);
         case 32: return launch_visible<32>(map, P, Q, n, out, flags, px, smem);
-        default: sbp_set_error("visible_group must be 4, 8, 16 or 32"); return SBP_ERR_ARG;
+        default: sbp_set_error("visible_group must be 0, 4, 8, 16 or 32"); return SBP_ERR_ARG;
     }
 }
 

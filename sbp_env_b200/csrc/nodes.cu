@@ -20,7 +20,7 @@
 
 #include "common.cuh"
 
-#define KNN_TPB 128        // queries per CTA in the batched kernel
+#define KNN_TPB 128        // queries per CTA in the batched radius kernel
 #define KNN_TILE 1024      // nodes staged in shared memory per step
 #define WIDE_TPB 256
 
@@ -215,6 +215,19 @@ struct TopK {
             }
         }
     }
+    // insert an already square-rooted distance (merging partial lists)
+    __device__ __forceinline__ void offer_sorted(double dd, int32_t idx) {
+        if (dd < d[K - 1]) {
+            bool placed = false;
+#pragma unroll
+            for (int t = K - 1; t >= 0; --t) {
+                if (!placed) {
+                    if (t > 0 && dd < d[t - 1]) { d[t] = d[t - 1]; i[t] = i[t - 1]; }
+                    else { d[t] = dd; i[t] = idx; placed = true; }
+                }
+            }
+        }
+    }
     // remove the head (used by the block merge)
     __device__ __forceinline__ void pop() {
 #pragma unroll
@@ -226,13 +239,14 @@ struct TopK {
 // ---------------------------------------------- K4a: batched, thread/query ---
 // grid = (ceil(m / KNN_TPB), S).  CTA (bx, s) scans node chunk s for its 128
 // queries; node tiles are staged in shared memory (SoA) and read by broadcast.
-template <int D, int K>
-__global__ void __launch_bounds__(KNN_TPB)
+template <int D, int K, int TPB>
+__global__ void __launch_bounds__(TPB)
 k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
               const double *__restrict__ X, int64_t m, double *__restrict__ pd,
               int32_t *__restrict__ pi) {
-    __shared__ double tile[D][KNN_TILE];
-    const int64_t q = (int64_t)blockIdx.x * KNN_TPB + threadIdx.x;
+    constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
+    __shared__ double tile[D][TILE];
+    const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int s = blockIdx.y;
     const int64_t chunk = (n + S - 1) / S;
     const int64_t c0 = (int64_t)s * chunk;
@@ -242,20 +256,56 @@ k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S
     for (int j = 0; j < D; ++j) qv[j] = q < m ? X[q * D + j] : 0.0;
     TopK<K> top;
     top.init();
-    for (int64_t t0 = c0; t0 < c1; t0 += KNN_TILE) {
-        int cnt = (int)(c1 - t0 < KNN_TILE ? c1 - t0 : KNN_TILE);
+    for (int64_t t0 = c0; t0 < c1; t0 += TILE) {
+        int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            for (int t = threadIdx.x; t < cnt; t += KNN_TPB)
+            for (int t = threadIdx.x; t < cnt; t += TPB)
                 tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
         __syncthreads();
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            double pv[D];
+        // Two-phase scan per block of 32 nodes.  Phase 1 is branch-free: six fp64
+        // instructions per pair plus one predicated bit-set, with the top-k state
+        // read-only (a fused scan+insert loop made ptxas copy the whole list between
+        // unrolled iterations: ~45 instructions per pair).  Phase 2 revisits only the
+        // flagged nodes; the bound can only have tightened meanwhile, and offer()
+        // re-checks it, so stale flags are harmless.
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+            const int bn = cnt - b0 < 32 ? cnt - b0 : 32;
+            const double bound2 = top.bound2;
+            uint32_t mask = 0;
+            if (bn == 32) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) pv[j] = tile[j][t];
-            top.offer(dist2_full<D>(pv, qv), (int32_t)(t0 + t));
+                for (int t = 0; t < 32; ++t) {
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                    mask |= (dist2_full<D>(pv, qv) < bound2) ? (1u << t) : 0u;
+                }
+            } else {
+                for (int t = 0; t < bn; ++t) {
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                    mask |= (dist2_full<D>(pv, qv) < bound2) ? (1u << t) : 0u;
+                }
+            }
+            // lock-step over the warp: round r inserts every lane's r-th flagged node,
+            // so insertions of different queries share one pass through offer()
+            while (__any_sync(0xffffffffu, mask != 0u)) {
+                double d2 = INFINITY;
+                int32_t id = -1;
+                if (mask) {
+                    const int t = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                    d2 = dist2_full<D>(pv, qv);
+                    id = (int32_t)(t0 + b0 + t);
+                }
+                top.offer(d2, id);
+            }
         }
     }
     if (q < m) {
@@ -269,36 +319,20 @@ k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S
 // For few queries over many nodes (RRT nearest / argsort[:20]): threads stride
 // the chunk with coalesced SoA loads, then the CTA merges its per-thread lists by
 // repeatedly extracting the (d, idx)-smallest head with warp shuffles.
-template <int D, int K>
-__global__ void __launch_bounds__(WIDE_TPB)
-k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
-           const double *__restrict__ X, int64_t m, double *__restrict__ pd,
-           int32_t *__restrict__ pi) {
-    const int64_t q = blockIdx.x;
-    const int s = blockIdx.y;
-    const int64_t chunk = (n + S - 1) / S;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    double qv[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
-    TopK<K> top;
-    top.init();
-    for (int64_t t = c0 + threadIdx.x; t < c1; t += WIDE_TPB) {
-        double pv[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
-        top.offer(dist2_full<D>(pv, qv), (int32_t)t);
-    }
-    // block merge: K rounds of argmin over the heads, key (d, idx)
+
+// K rounds of block-wide argmin over the list heads, key (d, idx).  Round r's winner
+// goes to the partial buffers (pd/pi) or, when idx64 is given, to the final row.
+template <int K>
+__device__ __forceinline__ void block_merge_topk(TopK<K> &top, double *pd, int32_t *pi,
+                                                 int64_t *idx64, double *dist, int k_out) {
     __shared__ double wd[WIDE_TPB / 32];
     __shared__ int32_t wi[WIDE_TPB / 32];
     __shared__ int wl[WIDE_TPB / 32];
     __shared__ int win_thread;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (q * S + s) * K;
-    for (int r = 0; r < K; ++r) {
+    const int rounds = idx64 ? k_out : K;
+    for (int r = 0; r < rounds; ++r) {
         double bd = top.d[0];
         int32_t bi = top.i[0];
         int bl = threadIdx.x;
@@ -319,14 +353,83 @@ k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
                 bool take = (wi[w] >= 0) && (fi < 0 || wd[w] < fd || (wd[w] == fd && wi[w] < fi));
                 if (take) { fd = wd[w]; fi = wi[w]; fl = wl[w]; }
             }
-            pd[base + r] = fi >= 0 ? fd : INFINITY;
-            pi[base + r] = fi;
+            if (idx64) {
+                idx64[r] = fi;
+                if (dist) dist[r] = fi >= 0 ? fd : INFINITY;
+            } else {
+                pd[r] = fi >= 0 ? fd : INFINITY;
+                pi[r] = fi;
+            }
             win_thread = fi >= 0 ? fl : -1;
         }
         __syncthreads();
         if ((int)threadIdx.x == win_thread) top.pop();
         __syncthreads();
     }
+}
+
+template <int D, int K>
+__global__ void __launch_bounds__(WIDE_TPB)
+k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
+           const double *__restrict__ X, int64_t m, double *__restrict__ pd,
+           int32_t *__restrict__ pi, int64_t *__restrict__ idx, double *__restrict__ dist,
+           int k_out) {
+    const int64_t q = blockIdx.x;
+    const int s = blockIdx.y;
+    const int64_t chunk = (n + S - 1) / S;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
+    TopK<K> top;
+    top.init();
+    // blocks of UNR nodes per thread: all loads issued first (memory-level
+    // parallelism), flags gathered branch-free, flagged nodes inserted afterwards
+    constexpr int UNR = 8;
+    for (int64_t t0 = c0 + threadIdx.x; t0 < c1; t0 += (int64_t)WIDE_TPB * UNR) {
+        double pv[UNR][D];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            int64_t t = t0 + (int64_t)u * WIDE_TPB;
+#pragma unroll
+            for (int j = 0; j < D; ++j) pv[u][j] = t < c1 ? soa[(int64_t)j * capacity + t] : INFINITY;
+        }
+        double d2[UNR];
+        uint32_t mask = 0;
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            d2[u] = dist2_full<D>(pv[u], qv);      // inf for the padding slots: never flagged
+            mask |= (d2[u] < top.bound2) ? (1u << u) : 0u;
+        }
+        if (mask) {
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (mask & (1u << u)) top.offer(d2[u], (int32_t)(t0 + (int64_t)u * WIDE_TPB));
+        }
+    }
+    if (S == 1) block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
+    else block_merge_topk<K>(top, pd + (q * S + s) * K, pi + (q * S + s) * K, nullptr, nullptr, 0);
+}
+
+// Second level of the wide path: one CTA per query merges its S partial lists
+// (S up to 1024; thread t takes lists t, t+256, ...; ascending chunk order keeps
+// the lower index first among equal distances).
+template <int K>
+__global__ void __launch_bounds__(WIDE_TPB)
+k_knn_merge_wide(const double *__restrict__ pd, const int32_t *__restrict__ pi, int S, int k_out,
+                 int64_t *__restrict__ idx, double *__restrict__ dist) {
+    const int64_t q = blockIdx.x;
+    TopK<K> top;
+    top.init();
+    for (int s = threadIdx.x; s < S; s += WIDE_TPB) {
+        const double *d0 = pd + (q * S + s) * K;
+        const int32_t *i0 = pi + (q * S + s) * K;
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+            if (i0[t] >= 0) top.offer_sorted(d0[t], i0[t]);
+    }
+    block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
 }
 
 // ----------------------------------------------------- K4c: chunk merge ------
@@ -370,25 +473,34 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
     }
 }
 
+int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
+
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
                           double *dist) {
     sbp_ctx *ctx = s->ctx;
     const int64_t n = s->n;
     bool wide = m < 256;
-    int S;
+    int S, tpb = 128;
     if (wide) {
         int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
         int64_t maxs = (n + 2047) / 2048;
         S = (int)(want < maxs ? want : maxs);
     } else {
-        int64_t tiles = (m + KNN_TPB - 1) / KNN_TPB;
-        int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
-        int64_t maxs = (n + 4 * KNN_TILE - 1) / (4 * KNN_TILE);
+        // queries per CTA: 128, or 32 when single-warp CTAs balance the SMs better
+        // (work per SM is ceil(tiles / SMs) * tpb query rows)
+        int64_t sm = ctx->sm_count;
+        int64_t w128 = ((m + 127) / 128 + sm - 1) / sm * 128;
+        int64_t w32 = ((m + 31) / 32 + sm - 1) / sm * 32;
+        tpb = (w32 * 100 < w128 * 95) ? 32 : 128;
+        int64_t tiles = (m + tpb - 1) / tpb;
+        int64_t want = (2 * sm + tiles - 1) / tiles;
+        int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
     }
+    if (!wide && g_knn_chunks > 0) S = g_knn_chunks;
     if (S < 1) S = 1;
-    if (S > 64) S = 64;
+    if (S > (wide ? 1024 : 64)) S = wide ? 1024 : 64;
     void *pd = nullptr, *pi = nullptr;
     int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)m * S * K * sizeof(double), &pd);
     if (rc) return rc;
@@ -397,10 +509,24 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     if (wide) {
         dim3 grid((unsigned)m, (unsigned)S);
         k_knn_wide<D, K><<<grid, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+                                                              (double *)pd, (int32_t *)pi, idx, dist, k);
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        if (S > 1) {
+            k_knn_merge_wide<K><<<(unsigned)m, WIDE_TPB, 0, ctx->stream>>>(
+                (const double *)pd, (const int32_t *)pi, S, k, idx, dist);
+            ctx->launches++;
+            SBP_CUDA(cudaGetLastError());
+        }
+        return SBP_OK;
+    }
+    if (tpb == 32) {
+        dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
+        k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
                                                               (double *)pd, (int32_t *)pi);
     } else {
-        dim3 grid((unsigned)((m + KNN_TPB - 1) / KNN_TPB), (unsigned)S);
-        k_knn_batched<D, K><<<grid, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
+        dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
+        k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
                                                                 (double *)pd, (int32_t *)pi);
     }
     ctx->launches++;
@@ -415,10 +541,14 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
 template <int D>
 static int32_t knn_dispatch_k(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
                               double *dist) {
+    // list length K >= k; 11 and 21 are the PRM / RRT* cases (k = 10 or 20 plus self)
     if (k <= 1) return knn_launch<D, 1>(s, X, m, k, idx, dist);
+    if (k <= 2) return knn_launch<D, 2>(s, X, m, k, idx, dist);
     if (k <= 4) return knn_launch<D, 4>(s, X, m, k, idx, dist);
     if (k <= 8) return knn_launch<D, 8>(s, X, m, k, idx, dist);
+    if (k <= 11) return knn_launch<D, 11>(s, X, m, k, idx, dist);
     if (k <= 16) return knn_launch<D, 16>(s, X, m, k, idx, dist);
+    if (k <= 21) return knn_launch<D, 21>(s, X, m, k, idx, dist);
     return knn_launch<D, 32>(s, X, m, k, idx, dist);
 }
 
@@ -654,7 +784,7 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
     } else {
         int64_t tiles = (m + KNN_TPB - 1) / KNN_TPB;
         int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
-        int64_t maxs = (n + 4 * KNN_TILE - 1) / (4 * KNN_TILE);
+        int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
     }
     if (S < 1) S = 1;

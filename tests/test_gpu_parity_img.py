@@ -82,10 +82,12 @@ def test_golden_img(sg, name):
     assert np.array_equal(cc.first_blocked_batch(P[sel], Q[sel]), g[name + "_cbc"])
 
 
-@pytest.mark.parametrize("group", [4, 8, 16, 32])
+@pytest.mark.parametrize("group,coop", [(4, 8), (8, 8), (16, 8), (32, 8), (0, 1), (0, 4), (0, 8), (0, 16), (0, 33)])
 @pytest.mark.parametrize("force_global", [0, 1])
-def test_all_kernel_variants_agree(sg, group, force_global):
-    """Every (lanes-per-edge, map-in-smem / map-in-L2) instantiation gives the same bits."""
+def test_all_kernel_variants_agree(sg, group, coop, force_global):
+    """Every kernel variant -- adaptive (group 0) from pure lane-per-edge (coop 1) to pure
+    warp-per-edge (coop 33), the lane-group kernels, map in smem / in L2 -- gives the
+    same bits."""
     from sbp_env_b200 import _lib
 
     g = golden("img_cc")
@@ -95,10 +97,12 @@ def test_all_kernel_variants_agree(sg, group, force_global):
     lib = _lib.load()
     try:
         lib.sbp_tune(b"visible_group", group)
+        lib.sbp_tune(b"coop_below", coop)
         lib.sbp_tune(b"force_global", force_global)
         got = cc.visible_batch(P, Q)
     finally:
         lib.sbp_tune(b"visible_group", 0)
+        lib.sbp_tune(b"coop_below", 12)
         lib.sbp_tune(b"force_global", 0)
     assert np.array_equal(got, np.tile(unpack(g["room1_visible"], len(g["room1_P"])), 8))
 
