@@ -265,9 +265,11 @@ def run_ours(args):
     knn_s = ph["knn"] / 1e3
     q_tile = 128
     alg_bytes = evals * 8 * 2 / q_tile + m * 16 + m * (k + 1) * 8     # node stream + queries + idx out
-    roof = {"kernel": "k_knn_batched<2,16> (+k_knn_merge), the 'knn' phase", "bound": "hbm",
-            "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
+    # workload, from the ncu --set full capture summarised in profiles/r1_knn_batched_full.txt
+    roof = {"kernel": "k_knn_batched<2,11,32> (+k_soa_to_aos, k_knn_merge): the 'knn' phase, 97% of the step",
+            "bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": 1626880, "peak_source": peak_src,
             "note": "brute-force kNN with 128 queries sharing each streamed node is fp64-issue bound, "
                     "not HBM bound: see alu"}
 
