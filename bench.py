@@ -64,54 +64,69 @@ def draw_free_samples(free, n, seed, feasible_fn):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~2 ms period;
+    falls back to one `nvidia-smi` query when pynvml is unavailable)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.gpu, self.samples, self.stop_flag, self.t, self.h = gpu_index, [], False, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map through it when set
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nv = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+        def pump():
+            nv = self.nv
+            while not self.stop_flag:
+                try:
+                    clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                        nv, "nvmlDeviceGetCurrentClocksEventReasons") else \
+                        nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.samples.append((time.time(), clk, rs))
+                except Exception:
+                    pass
+                time.sleep(0.002)
+
+        self.t = threading.Thread(target=pump, daemon=True)
+        self.t.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
+        self.stop_flag = True
+        if self.t is not None:
+            self.t.join(1.0)
+        if self.nv is None or not self.samples:
             try:
-                clk, mxc = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            mx = mxc
-            if t0 - 0.05 <= ts <= t1 + 0.15:
-                sm.append(clk)
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                    "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:
-            sm = [float(x[1].split(",")[1]) for x in self.rows[-3:] if len(x[1].split(",")) > 2] or [0.0]
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                o = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm",
+                                    "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                   capture_output=True, text=True, timeout=10).stdout.split(",")
+                return {"sm_mhz": float(o[0]), "sm_max_mhz": float(o[1]), "reasons": [],
+                        "samples": 0, "note": "single nvidia-smi query after the timed region"}
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"]}
+        nv = self.nv
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        inside = [(c, r) for ts, c, r in self.samples if t0 <= ts <= t1] or [(c, r) for _, c, r in self.samples[-3:]]
+        reasons = set()
+        for _, r in inside:
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([c for c, _ in inside])), "sm_max_mhz": float(mx),
+                "reasons": sorted(reasons), "samples": len(inside)}
 
 
 # ------------------------------------------------------------------ ours -----
@@ -288,70 +303,72 @@ def run_ours(args):
                    "frac": evals * 6 / knn_s / fp64_peak}
 
     # ---- micro: uniform random edge batches on the same map ------
-    micro = {}
-    smem_gather = mb(0, int(cc.device_map.info()["packed_bytes"]), 2048)
-    l2_gather = mb(1, 64 << 20, 512)
-    hbm_gather = mb(1, 8 << 30, 512)
-    micro["measured_gather_peaks"] = {"smem_random_word_gathers_per_s": smem_gather,
-                                      "l2_random_sector_gathers_per_s_64MiB": l2_gather,
-                                      "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}
-    g = torch.Generator(device=dev)
-    g.manual_seed(4)
-    scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
+    micro = None
+    if world == 1:        # N = 1 only: keeps the N > 1 runs short
+        micro = {}
+        smem_gather = mb(0, int(cc.device_map.info()["packed_bytes"]), 2048)
+        l2_gather = mb(1, 64 << 20, 512)
+        hbm_gather = mb(1, 8 << 30, 512)
+        micro["measured_gather_peaks"] = {"smem_random_word_gathers_per_s": smem_gather,
+                                          "l2_random_sector_gathers_per_s_64MiB": l2_gather,
+                                          "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}
+        g = torch.Generator(device=dev)
+        g.manual_seed(4)
+        scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
 
-    def time_visible(P, Q, iters=5):
-        cc.visible_batch(P, Q)
+        def time_visible(P, Q, iters=5):
+            cc.visible_batch(P, Q)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts = []
+            for _ in range(iters):
+                flush.zero_()
+                a.record()
+                r = cc.visible_batch(P, Q)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            px = (torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
+                                (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item()
+            cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+            cc._visible_device(P, Q, px_tested=cnt)
+            t = float(np.median(ts)) / 1e3
+            n = P.shape[0]
+            ab = 33.0 * n + 0.125 * px
+            return {"edges": n, "ms": t * 1e3, "interpolants_full_line": px,
+                    "interpolants_per_s": px / t, "pixel_tests_executed": int(cnt.item()),
+                    "pixel_tests_per_s": int(cnt.item()) / t, "edges_per_s": n / t,
+                    "visible_fraction": float(r.float().mean().item()),
+                    "algorithmic_GBps": ab / t / 1e9, "hbm_frac": ab / t / 1e9 / hbm_peak}
+
+        n_u = 1 << 24
+        P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+        Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+        micro["uniform_2^24_edges"] = time_visible(P, Q)
+        fr = torch.from_numpy(nodes).to(dev)
+        for L in (8, 32, 128):
+            n_b = 1 << 22
+            base = fr[torch.randint(0, len(nodes), (n_b,), generator=g, device=dev)]
+            ang = torch.rand(n_b, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi)
+            Qb = base + torch.stack([ang.cos(), ang.sin()], 1) * L
+            micro[f"free_start_len{L}_2^22_edges"] = time_visible(base, Qb)
+        del P, Q
+
+        # single-query nearest over a 1M-node tree (RRT-style, latency bound)
+        big = sg.NodeStore(2, capacity=1 << 20, device=local)
+        big.extend(torch.rand((1 << 20, 2), generator=g, device=dev, dtype=torch.float64) * scale)
+        q1 = torch.rand((1, 2), generator=g, device=dev, dtype=torch.float64) * scale
+        big.knn(q1, 1)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ts = []
-        for _ in range(iters):
-            flush.zero_()
-            a.record()
-            r = cc.visible_batch(P, Q)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        px = (torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
-                            (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item()
-        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-        cc._visible_device(P, Q, px_tested=cnt)
-        t = float(np.median(ts)) / 1e3
-        n = P.shape[0]
-        ab = 33.0 * n + 0.125 * px
-        return {"edges": n, "ms": t * 1e3, "interpolants_full_line": px,
-                "interpolants_per_s": px / t, "pixel_tests_executed": int(cnt.item()),
-                "pixel_tests_per_s": int(cnt.item()) / t, "edges_per_s": n / t,
-                "visible_fraction": float(r.float().mean().item()),
-                "algorithmic_GBps": ab / t / 1e9, "hbm_frac": ab / t / 1e9 / hbm_peak}
-
-    n_u = 1 << 24
-    P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
-    Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
-    micro["uniform_2^24_edges"] = time_visible(P, Q)
-    fr = torch.from_numpy(nodes).to(dev)
-    for L in (8, 32, 128):
-        n_b = 1 << 22
-        base = fr[torch.randint(0, len(nodes), (n_b,), generator=g, device=dev)]
-        ang = torch.rand(n_b, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi)
-        Qb = base + torch.stack([ang.cos(), ang.sin()], 1) * L
-        micro[f"free_start_len{L}_2^22_edges"] = time_visible(base, Qb)
-    del P, Q
-
-    # single-query nearest over a 1M-node tree (RRT-style, latency bound)
-    big = sg.NodeStore(2, capacity=1 << 20, device=local)
-    big.extend(torch.rand((1 << 20, 2), generator=g, device=dev, dtype=torch.float64) * scale)
-    q1 = torch.rand((1, 2), generator=g, device=dev, dtype=torch.float64) * scale
-    big.knn(q1, 1)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(50):
-        big.knn(q1, 1)
-    b.record()
-    torch.cuda.synchronize()
-    t1 = a.elapsed_time(b) / 50 / 1e3
-    micro["nearest_1q_over_2^20_nodes"] = {"ms": t1 * 1e3, "dist_evals_per_s": (1 << 20) / t1,
-                                           "node_stream_GBps": (1 << 20) * 16 / t1 / 1e9}
+        a.record()
+        for _ in range(50):
+            big.knn(q1, 1)
+        b.record()
+        torch.cuda.synchronize()
+        t1 = a.elapsed_time(b) / 50 / 1e3
+        micro["nearest_1q_over_2^20_nodes"] = {"ms": t1 * 1e3, "dist_evals_per_s": (1 << 20) / t1,
+                                               "node_stream_GBps": (1 << 20) * 16 / t1 / 1e9}
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = cpu_prm_sample(free, nodes, target_s=12.0) if world == 1 else None

@@ -204,6 +204,31 @@ int32_t sbp_nodes_knn_edges(sbp_nodes *nodes, const int64_t *nbr_in, int64_t m, 
                             int64_t first_row, const double *X, int64_t *nbr_out, double *P,
                             double *Q, uint8_t *valid);
 
+/* Fused radius query + edge visibility in ONE launch, for the sequential planners.
+ * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:
+ * engine.dist(new,p) <= radius and cc.visible(new.pos, p.pos)), rewire
+ * (rrtPlanner.py:250-266: cc.visible(n.pos, new.pos)), PRMPlanner.get_nearest_free
+ * (prmPlanner.py:103-126) and the Bi-RRT join test (birrtPlanner.py:82-87).
+ * X: device [m][d] queries.  For every stored node within r of X[i] (metric / closed as
+ * in sbp_nodes_near) the edge is checked on the spot: direction 0 = visible(X[i] -> node),
+ * 1 = visible(node -> X[i]); arm = 0 uses the 2-D image checker on the first two
+ * coordinates, arm = 1 (d == 4) the stick-arm checker with link lengths L0, L1.
+ * out_idx / out_vis: device [m][cap], hits of query i in ARRIVAL order (unordered);
+ * out_vis holds SBP_FREE / SBP_BLOCKED / SBP_AMBIGUOUS.  count: device int32 [m], total
+ * hits per query (may exceed cap: then only cap were stored). */
+int32_t sbp_nodes_near_visible(sbp_nodes *nodes, sbp_map *map, int32_t arm, double L0, double L1,
+                               const double *X, int64_t m, double r, int32_t metric,
+                               int32_t closed, int32_t direction, int64_t *out_idx,
+                               uint8_t *out_vis, int32_t cap, int32_t *count, int32_t *flags);
+/* Host form for one query x (HOST [d]); hits come back sorted by node index (the order of
+ * the reference's loops) with guard-band entries already resolved.  *n_hits > cap returns
+ * SBP_ERR_CAPACITY: call again with a larger buffer. */
+int32_t sbp_nodes_near_visible_host(sbp_nodes *nodes, sbp_map *map, int32_t arm, double L0,
+                                    double L1, const double *x, double r, int32_t metric,
+                                    int32_t closed, int32_t direction, int64_t *out_idx,
+                                    uint8_t *out_vis, int32_t cap, int32_t *n_hits,
+                                    int32_t *flags);
+
 #ifdef __cplusplus
 }
 #endif

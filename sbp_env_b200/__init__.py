@@ -11,6 +11,7 @@ from .engine import Engine, ImageEngine, RobotArmEngine, euclidean_dist  # noqa:
 from .node_store import NodeStore  # noqa: F401
 from .planning import (feasible_batch, knn, near, prm_connect_knn,  # noqa: F401
                        roadmap_edges_to_host, visible_batch)
+from . import distributed, planner_ops  # noqa: F401
 from .stats import Stats  # noqa: F401
 
 __version__ = "0.1.0"

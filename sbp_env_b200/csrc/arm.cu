@@ -22,70 +22,7 @@
 #include <math.h>
 
 #include "common.cuh"
-
-// Sequential Bresenham walk of one link; all pixels free?  Order is irrelevant
-// for the boolean, so the canonical traversal is walked directly.
-template <bool SMEM>
-__device__ __forceinline__ bool link_free(const uint32_t *words, const MapView &mv, int x1, int y1,
-                                          int x2, int y2) {
-    int dx = x2 - x1, dy = y2 - y1;
-    bool steep = abs(dy) > abs(dx);                     // :467
-    int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;     // :470-472
-    int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
-    if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }  // :476-479
-    int da = a2 - a1, adb = abs(b2 - b1);               // :482-483
-    int err = da >> 1;                                  // int(dx / 2.0), :486
-    int ystep = b1 < b2 ? 1 : -1;                       // :487
-    int b = b1;
-    for (int a = a1; a <= a2; ++a) {                    // :492-498
-        int x = steep ? b : a, y = steep ? a : b;
-        if (!map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H))) return false;
-        err -= adb;
-        if (err < 0) { b += ystep; err += da; }
-    }
-    return true;
-}
-
-// |v - nearest integer| within the guard band?  The band covers the discrepancy
-// between glibc and libdevice cos/sin propagated through pt + L*c (see header).
-__device__ __forceinline__ bool near_pixel_boundary(double v, double L) {
-    double guard = (fabs(v) + fabs(L) + 1.0) * 5.6843418860808015e-14;  // 2^-44
-    return fabs(v - rint(v)) <= guard;
-}
-
-// One configuration: 1 free, 0 blocked, 2 ambiguous.  flag receives SBP_FLAG_*.
-template <bool SMEM>
-__device__ __forceinline__ int arm_config(const uint32_t *words, const MapView &mv, double L0,
-                                          double L1, double bx, double by, double r0, double r1,
-                                          int &flag) {
-    // math.cos(+-inf) raises ValueError("math domain error"); nan propagates to int(nan)
-    if (isinf(r0) || isinf(r1) || r0 != r0 || r1 != r1) { flag |= SBP_FLAG_NAN; return 0; }
-    double s0, c0, s1, c1;
-    sincos(r0, &s0, &c0);
-    sincos(r1, &s1, &c1);
-    double p2x = __dadd_rn(bx, __dmul_rn(L0, c0));      // :438
-    double p2y = __dadd_rn(by, __dmul_rn(L0, s0));      // :439
-    double p3x = __dadd_rn(p2x, __dmul_rn(L1, c1));     // :417-419
-    double p3y = __dadd_rn(p2y, __dmul_rn(L1, s1));
-    TruncResult tbx = trunc_index(bx, mv.W), tby = trunc_index(by, mv.H);
-    int f = tbx.flag ? tbx.flag : tby.flag;
-    if (f) { flag |= f; return 0; }
-    // the base pixel is exact: when it is outside the index range the first tested
-    // pixel fails whatever the FK says
-    if (!tbx.in_range || !tby.in_range) return 0;
-    bool amb1 = near_pixel_boundary(p2x, L0) || near_pixel_boundary(p2y, L0);
-    TruncResult t2x = trunc_index(p2x, mv.W), t2y = trunc_index(p2y, mv.H);
-    if (t2x.flag || t2y.flag) { flag |= t2x.flag ? t2x.flag : t2y.flag; return 0; }
-    if (amb1) return 2;
-    if (!t2x.in_range || !t2y.in_range) return 0;       // end pixel of link 1 is out of range
-    if (!link_free<SMEM>(words, mv, tbx.i, tby.i, t2x.i, t2y.i)) return 0;   // :413-415
-    bool amb2 = near_pixel_boundary(p3x, L1) || near_pixel_boundary(p3y, L1);
-    TruncResult t3x = trunc_index(p3x, mv.W), t3y = trunc_index(p3y, mv.H);
-    if (t3x.flag || t3y.flag) { flag |= t3x.flag ? t3x.flag : t3y.flag; return 0; }
-    if (amb2) return 2;
-    if (!t3x.in_range || !t3y.in_range) return 0;
-    return link_free<SMEM>(words, mv, t2x.i, t2y.i, t3x.i, t3y.i) ? 1 : 0;   // :422-424
-}
+#include "device_fns.cuh"
 
 template <bool SMEM>
 __global__ void __launch_bounds__(1024)

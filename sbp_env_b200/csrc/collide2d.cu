@@ -19,40 +19,7 @@
 // (k, rem) = divmod(i*|db| + c, da) forward by adding divmod(G*|db|, da), so the
 // inner loop has no division.  A ballot per step gives the early exit.
 #include "common.cuh"
-
-struct Edge2D {
-    int a1, b1;        // canonical start (major, minor)
-    uint32_t da, adb;  // major extent, |minor extent|
-    int ystep;
-    bool steep, swapped;
-    bool walk;         // both endpoints inside the index range: pixels must be tested
-    int flag;          // SBP_FLAG_* bits
-    int x1, y1, x2, y2;
-};
-
-__device__ __forceinline__ Edge2D make_edge(double px, double py, double qx, double qy, int W,
-                                            int H) {
-    Edge2D e;
-    TruncResult t0 = trunc_index(px, W), t1 = trunc_index(py, H);   // x1, y1 = map(int, start)
-    TruncResult t2 = trunc_index(qx, W), t3 = trunc_index(qy, H);   // x2, y2 = map(int, end)
-    // CPython raises at the first offending conversion (:173-174)
-    e.flag = t0.flag ? t0.flag : t1.flag ? t1.flag : t2.flag ? t2.flag : t3.flag;
-    // both endpoints are members of the pixel list (:204-206): an endpoint outside
-    // the index range makes the all-of False without walking
-    e.walk = t0.in_range && t1.in_range && t2.in_range && t3.in_range;
-    e.x1 = t0.i; e.y1 = t1.i; e.x2 = t2.i; e.y2 = t3.i;
-    int dx = e.x2 - e.x1, dy = e.y2 - e.y1;
-    e.steep = abs(dy) > abs(dx);                                      // :179
-    int a1 = e.steep ? e.y1 : e.x1, b1 = e.steep ? e.x1 : e.y1;       // :182-184
-    int a2 = e.steep ? e.y2 : e.x2, b2 = e.steep ? e.x2 : e.y2;
-    e.swapped = a1 > a2;                                              // :188-191
-    if (e.swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
-    e.a1 = a1; e.b1 = b1;
-    e.da = (uint32_t)(a2 - a1);                                       // :194
-    e.adb = (uint32_t)abs(b2 - b1);                                   // :195, :207
-    e.ystep = b1 < b2 ? 1 : -1;                                       // :199
-    return e;
-}
+#include "device_fns.cuh"
 
 // ---------------------------------------------------------------- K1 -------
 template <bool SMEM>

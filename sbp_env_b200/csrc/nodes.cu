@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "device_fns.cuh"
 
 #define KNN_TPB 128        // queries per CTA in the batched radius kernel
 #define KNN_TILE 1024      // nodes staged in shared memory per step
@@ -175,18 +176,6 @@ extern "C" int32_t sbp_nodes_rows_device(sbp_nodes *s, int64_t first, int64_t co
 }
 
 // --------------------------------------------------------- distance core ----
-template <int D>
-__device__ __forceinline__ double dist2_full(const double (&p)[D], const double (&q)[D]) {
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        double df = __dsub_rn(p[j], q[j]);        // poses - pos
-        double sq = __dmul_rn(df, df);
-        acc = j == 0 ? sq : __dadd_rn(acc, sq);   // left-to-right, unfused
-    }
-    return acc;
-}
-
 // Per-thread sorted list of the K best (d, idx), d ascending, ties keep arrival
 // order (callers feed indices in ascending order, so ties keep the lower index).
 template <int K>
@@ -588,23 +577,6 @@ extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32
 // --------------------------------------------------------- K5: radius -------
 // Membership is decided on d^2 against a host-computed threshold (see
 // near_threshold below), so no square root is evaluated per pair.
-template <int D, bool XY>
-__device__ __forceinline__ double near_d2(const double (&p)[D], const double (&q)[D]) {
-    if (XY) {
-        // engine.euclidean_dist (engine.py:23-24): p = p1 - p2 (query - node), first
-        // two coordinates only.  The reference squares with libm pow, which differs
-        // from the correctly rounded product by 1 ulp for ~0.1% of inputs (SURVEY.md
-        // D4): "parity unpinned at the last bit" for this metric.
-        double a = __dsub_rn(q[0], p[0]), b = __dsub_rn(q[1], p[1]);
-        return __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
-    }
-    return dist2_full<D>(p, q);
-}
-
-__device__ __forceinline__ bool near_in(double d2, double thr, int closed) {
-    return closed ? (d2 <= thr) : (d2 < thr);
-}
-
 // wide: CTA per (query, chunk).  PASS 0 counts, PASS 1 writes indices in order.
 template <int D, bool XY, int PASS>
 __global__ void __launch_bounds__(WIDE_TPB)
@@ -745,28 +717,6 @@ k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
     if (tid == 1023) {
         row_ptr[m] = part[1023];
         *needed = part[1023];
-    }
-}
-
-// Smallest fp64 t with sqrt_rn(t) >= r  (d < r  <=>  d^2 < t), and largest t with
-// sqrt_rn(t) <= r  (d <= r <=> d^2 <= t); SURVEY.md H5.  Host sqrt is IEEE
-// correctly rounded, like __dsqrt_rn.
-static void near_threshold(double r, int closed, double *thr, int *closed_out) {
-    *closed_out = closed;
-    if (r != r) { *thr = -1.0; *closed_out = 0; return; }            // nan: nothing matches
-    if (r < 0) { *thr = -1.0; *closed_out = 0; return; }             // d >= 0 always
-    if (isinf(r)) { *thr = INFINITY; *closed_out = 1; return; }      // finite d always matches
-    double s = r * r;
-    if (isinf(s)) { *thr = INFINITY; *closed_out = 1; return; }
-    if (!closed) {
-        while (s > 0 && sqrt(s) >= r) s = nextafter(s, -INFINITY);
-        while (sqrt(nextafter(s, INFINITY)) < r) s = nextafter(s, INFINITY);
-        // now sqrt(s) < r (or s == 0) and sqrt(next(s)) >= r
-        *thr = (sqrt(s) >= r) ? s : nextafter(s, INFINITY);
-    } else {
-        while (sqrt(s) > r) s = nextafter(s, -INFINITY);
-        while (sqrt(nextafter(s, INFINITY)) <= r) s = nextafter(s, INFINITY);
-        *thr = s;
     }
 }
 

@@ -35,6 +35,10 @@ class NodeStore:
         check(_lib.load().sbp_nodes_create(self.ctx.handle, self.dim, int(capacity), C.byref(h)),
               "sbp_nodes_create")
         self._h = h
+        # host mirror of the poses (the planners keep `poses` on the host anyway); it lets
+        # the per-node host arithmetic (costs, step_from_to) avoid device reads
+        self._mirror = np.empty((max(int(capacity), 16), self.dim), np.float64)
+        self._mirror_n = 0          # rows valid in the mirror; < len(self) after device extends
 
     # ---- growth ------------------------------------------------------------------
     def append(self, x) -> int:
@@ -51,10 +55,35 @@ class NodeStore:
             check(_lib.load().sbp_nodes_append(self._h, ptr(X), X.shape[0], 1), "sbp_nodes_append")
         else:
             X = as_host_f64(X, self.dim)
+            n0 = len(self)
             check(_lib.load().sbp_nodes_append(self._h, ptr(X), len(X), 0), "sbp_nodes_append")
+            if self._mirror_n == n0:                      # mirror was complete: keep it so
+                need = n0 + len(X)
+                if need > len(self._mirror):
+                    grown = np.empty((max(need, 2 * len(self._mirror)), self.dim), np.float64)
+                    grown[:n0] = self._mirror[:n0]
+                    self._mirror = grown
+                self._mirror[n0:need] = X
+                self._mirror_n = need
 
     def truncate(self, n: int) -> None:
         check(_lib.load().sbp_nodes_truncate(self._h, int(n)), "sbp_nodes_truncate")
+        self._mirror_n = min(self._mirror_n, int(n))
+
+    def poses_rows(self, idx) -> np.ndarray:
+        """Host copy of the given rows ([len(idx)][d]); served from the host mirror when
+        the store was filled from host arrays, else read back from the device."""
+        idx = np.asarray(idx, dtype=np.int64).reshape(-1)
+        if len(idx) == 0:
+            return np.empty((0, self.dim), np.float64)
+        if self._mirror_n == len(self):
+            return self._mirror[idx]
+        out = np.empty((len(idx), self.dim), np.float64)
+        row = np.empty(self.dim, np.float64)
+        for j, i in enumerate(idx):
+            check(_lib.load().sbp_nodes_read(self._h, int(i), 1, ptr(row)), "sbp_nodes_read")
+            out[j] = row
+        return out
 
     def __len__(self) -> int:
         n = C.c_int64()
@@ -169,6 +198,42 @@ class NodeStore:
         check(_lib.load().sbp_nodes_gather_edges(self._h, ptr(nbr), m, k, int(first_row), ptr(P),
                                                  ptr(Q), ptr(valid)), "sbp_nodes_gather_edges")
         return P, Q, valid
+
+    def near_visible(self, cc, x, r: float, metric: str = "xy", closed: bool = True,
+                     direction: int = 0, cap: int = 256):
+        """Nodes within radius r of the single configuration x together with the
+        visibility of the connecting edge, in ONE kernel launch: ``(idx, vis)`` sorted by
+        node index (the order of the reference's loops).
+
+        ``direction=0`` checks ``cc.visible(x, node)`` (rrtPlanner.py:179-181,
+        prmPlanner.py:116); ``direction=1`` checks ``cc.visible(node, x)`` (rrtPlanner.py:239,
+        :260).  ``cc`` is the GPU checker whose map lives on the same device; the arm
+        checker is used with its link lengths.  ``cc.stats.visible_cnt`` is advanced by the
+        number of edges checked, as the reference's loop would."""
+        arm = hasattr(cc, "stick_robot_length_config")
+        L0, L1 = (float(v) for v in cc.stick_robot_length_config[:2]) if arm else (0.0, 0.0)
+        xh = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(self.dim))
+        lib = _lib.load()
+        while True:
+            idx = np.empty(cap, np.int64)
+            vis = np.empty(cap, np.uint8)
+            hits, flags = C.c_int32(0), C.c_int32(0)
+            rc = lib.sbp_nodes_near_visible_host(self._h, cc.device_map.handle, int(arm), L0, L1,
+                                                 ptr(xh), float(r), _lib.METRIC[metric],
+                                                 int(bool(closed)), int(direction), ptr(idx), ptr(vis),
+                                                 cap, C.byref(hits), C.byref(flags))
+            if rc == -4 and hits.value > cap:            # SBP_ERR_CAPACITY: grow and retry
+                cap = int(hits.value) * 2
+                continue
+            check(rc, "sbp_nodes_near_visible_host")
+            break
+        from .runtime import raise_for_flags
+
+        # the image checker swallows NaN (ValueError caught, collisionChecker.py:143-144)
+        raise_for_flags(flags.value, "visible", nan_is_error=arm)
+        n = int(hits.value)
+        cc.stats.visible_cnt += n
+        return idx[:n].copy(), vis[:n].astype(bool)
 
     def knn_edges(self, nbr_in, first_row: int = 0, queries=None):
         """kNN rows -> candidate-edge batch in one launch: ``(nbr, P, Q, valid)``.
