@@ -1,0 +1,208 @@
+"""Build-container only (needs /root/reference; skipped on the GPU box): drives the
+UNMODIFIED reference planners (Env, RRT*, Bi-RRT*, Informed RRT*, PRM, the 4-D arm)
+through the Python boundary classes of sbp_env_b200 and checks that whole seeded runs
+are identical to runs with the reference's own checker -- node arrays, c_max and the
+Stats counters.
+
+There is no CUDA device here, so the device layer (libsbpgpu through ctypes) is
+replaced by the oracle for these tests: what is being tested is the drop-in contract of
+the classes (signatures, Stats accounting, deepcopy, attribute surface, error
+behaviour) inside the reference's own control flow.  The kernels themselves are tested
+against the same oracle by the -m gpu suite.
+"""
+import copy
+import os
+from functools import partialmethod
+
+import numpy as np
+import pytest
+
+import c_oracle as orc
+import ref_shims
+from _util import reference_present
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not reference_present(), reason="needs /root/reference")]
+
+
+class FakeDeviceMap:
+    """Stands in for runtime.DeviceMap: keeps the occupancy grid for the oracle."""
+
+    def __init__(self, free_xy, device=0):
+        self.om = orc.Map(np.asarray(free_xy) == 1)
+        self.W, self.H = self.om.W, self.om.H
+
+
+@pytest.fixture()
+def ref(monkeypatch):
+    sbp_env = ref_shims.import_reference()
+    from tqdm import tqdm
+
+    monkeypatch.setattr(tqdm, "__init__", partialmethod(tqdm.__init__, disable=True))
+    import sbp_env_b200.collision_checker as gcc
+    from sbp_env_b200.runtime import raise_for_flags
+
+    monkeypatch.setattr(gcc, "DeviceMap", FakeDeviceMap)
+
+    def img_feasible(self, P):
+        out, st = self.device_map.om.feasible2d(P, return_status=True)
+        raise_for_flags(int(np.bitwise_or.reduce(st)) if len(st) else 0, "feasible")
+        return out
+
+    def img_visible(self, P, Q):
+        out, st = self.device_map.om.visible2d(P, Q, return_status=True)
+        raise_for_flags(int(np.bitwise_or.reduce(st)) if len(st) else 0, "visible", nan_is_error=False)
+        return out
+
+    def img_first(self, P, Q, with_counts=False):
+        out = self.device_map.om.coor_before_collision(P, Q).astype(np.int32)
+        if not with_counts:
+            return out
+        ex = np.maximum(np.abs(out[:, 0] - np.trunc(P[:, 0])), np.abs(out[:, 1] - np.trunc(P[:, 1]))) + 1
+        return out, ex.astype(np.int64)
+
+    def arm_feasible(self, C4):
+        L0, L1 = self._lengths()
+        out, st = self.device_map.om.arm_feasible(C4, L0, L1, return_status=True)
+        raise_for_flags(int(np.bitwise_or.reduce(st)) if len(st) else 0, "feasible")
+        return out
+
+    def arm_visible(self, C1, C2):
+        L0, L1 = self._lengths()
+        out, st = self.device_map.om.arm_visible(C1, C2, L0, L1, return_status=True)
+        raise_for_flags(int(np.bitwise_or.reduce(st)) if len(st) else 0, "visible")
+        return out
+
+    monkeypatch.setattr(gcc.ImgCollisionChecker, "_feasible_host", img_feasible)
+    monkeypatch.setattr(gcc.ImgCollisionChecker, "_visible_host", img_visible)
+    monkeypatch.setattr(gcc.ImgCollisionChecker, "_first_blocked_host", img_first)
+    monkeypatch.setattr(gcc.RobotArm4dCollisionChecker, "_feasible_host", arm_feasible)
+    monkeypatch.setattr(gcc.RobotArm4dCollisionChecker, "_visible_host", arm_visible)
+    from sbp_env.utils.common import Stats
+
+    Stats.clear_instance()
+    yield sbp_env
+    Stats.clear_instance()
+
+
+def make_args(planner_id, engine_factory, start, goal, max_nodes, **kw):
+    from sbp_env.utils import planner_registry
+    from sbp_env.utils.common import PlanningOptions
+    import sbp_env.planners  # noqa: F401 - fills the registries
+    import sbp_env.samplers  # noqa: F401
+
+    pdp = planner_registry.PLANNERS[planner_id]
+    opts = dict(always_refresh=False, epsilon=None, goalBias=0.03, start_pt=start, goal_pt=goal,
+                goal_radius=None, ignore_step_size=False, max_number_nodes=max_nodes, no_display=True,
+                planner_data_pack=pdp, sampler_data_pack=planner_registry.SAMPLERS[pdp.sampler_id],
+                radius=None, rrdt_proposal_distribution="dynamic-vonmises", scaling=1.5,
+                showSampledPoint=False, skip_optimality=False)
+    opts.update(kw)
+    args = PlanningOptions(**opts)
+    args.engine = engine_factory(args)
+    return args
+
+
+def run(planner_id, engine_factory, swap_cc, start, goal, max_nodes, **kw):
+    from sbp_env.env import Env
+    from sbp_env.utils.common import Stats
+
+    Stats.clear_instance()
+    args = make_args(planner_id, engine_factory, start, goal, max_nodes, **kw)
+    if swap_cc is not None:
+        args.engine.cc = swap_cc(args.engine.cc)
+    env = Env(args, fixed_seed=0)
+    stats = env.run()
+    pl = env.planner
+    n = len(pl.nodes)
+    return dict(poses=np.array(pl.poses[:n]), c_max=pl.c_max, n=n,
+                counters=(stats.visible_cnt, stats.feasible_cnt, stats.valid_sample,
+                          stats.invalid_samples_obstacles, stats.invalid_samples_connections),
+                env=env)
+
+
+def _same(a, b):
+    assert a["n"] == b["n"]
+    assert np.array_equal(a["poses"], b["poses"])
+    assert a["c_max"] == b["c_max"]
+    assert a["counters"] == b["counters"]
+
+
+@pytest.mark.parametrize("planner_id", ["rrt", "birrt", "informedrrt"])
+def test_seeded_2d_runs_identical(ref, planner_id):
+    from sbp_env import engine
+    from sbp_env_b200 import ImgCollisionChecker
+
+    img = ref_shims.reference_map_path("room1.png")
+    fac = lambda args: engine.ImageEngine(args, img)
+    a = run(planner_id, fac, None, "100,100", "350,350", 250)
+    b = run(planner_id, fac, lambda cc: ImgCollisionChecker(cc.image_fname), "100,100", "350,350", 250)
+    _same(a, b)
+    assert a["counters"][2] >= 250            # valid samples (Bi-RRT splits them over two trees)
+
+
+def test_seeded_arm_run_identical(ref):
+    from sbp_env import engine
+    from sbp_env_b200 import RobotArm4dCollisionChecker
+
+    img = ref_shims.reference_map_path("4d.png")
+    kw = dict(rover_arm_robot_lengths=(30.0, 30.0))
+    fac = lambda args: engine.RobotArmEngine(args, img)
+    start, goal = "652.249,276.262,-2.884,-3.038", "832.789,934.662,0.670,1.442"
+    swap = lambda cc: RobotArm4dCollisionChecker(cc.image_fname, stick_robot_length_config=cc.stick_robot_length_config)
+    a = run("birrt", fac, None, start, goal, 120, **kw)
+    b = run("birrt", fac, swap, start, goal, 120, **kw)
+    _same(a, b)
+
+
+def test_engine_mirrors_and_prm(ref):
+    """The Engine look-alikes carry an unmodified reference PRM run: sampling, build_graph
+    (radius PRM*, prmPlanner.py:80-101) and get_solution."""
+    from sbp_env import engine
+    import sbp_env_b200 as sg
+
+    img = ref_shims.reference_map_path("maze1.png")
+    ref_engine = lambda args: engine.ImageEngine(args, img)
+    my_engine = lambda args: sg.ImageEngine(args, img)
+    outs = []
+    for fac in (ref_engine, my_engine):
+        r = run("prm", fac, None, "25,25", "290,290", 60)
+        pl = r["env"].planner
+        pl.build_graph()
+        sol = pl.get_solution()
+        outs.append((r, sorted((tuple(u.pos), tuple(v.pos)) for u, v in pl.graph.edges()), sol))
+        e = r["env"].args.engine
+        assert e.get_dimension() == 2 and e.lower.tolist() == [0, 0] and e.upper.tolist() == [322, 322]
+        assert e.dist(np.array([0.0, 0.0]), np.array([3.0, 4.0])) == 5.0
+    _same(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1] and len(outs[0][1]) > 0
+    assert outs[0][2] == outs[1][2]
+
+
+def test_checker_surface_matches_reference(ref):
+    """Attribute surface, Stats binding, deepcopy and error behaviour side by side."""
+    from sbp_env.collisionChecker import ImgCollisionChecker as RefCC
+    from sbp_env.utils.common import Stats
+    from sbp_env_b200 import ImgCollisionChecker as GpuCC
+
+    img = ref_shims.reference_map_path("room1.png")
+    Stats.clear_instance()
+    r, g = RefCC(img), GpuCC(img)
+    assert g.stats is r.stats is Stats.get_instance()             # same singleton
+    assert np.array_equal(r._img, g._img) and r._img.dtype == g._img.dtype
+    assert np.array_equal(r.image, g.image) and r.image_fname == g.image_fname
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        p, q = rng.random(2) * [700, 500] - 60, rng.random(2) * [700, 500] - 60
+        assert bool(r.feasible(p)) == bool(g.feasible(p))
+        assert bool(r.visible(p, q)) == bool(g.visible(p, q))
+        assert tuple(r.get_coor_before_collision(p, q)) == g.get_coor_before_collision(p, q)
+        assert r.get_line(p, q) == g.get_line(p, q)
+    assert Stats.get_instance().visible_cnt == 600
+    for bad, exc in (((float("nan"), 1.0), ValueError), ((float("inf"), 1.0), OverflowError)):
+        for cc in (r, g):
+            with pytest.raises(exc):
+                cc.feasible(bad)
+    assert r.visible((float("nan"), 1.0), (5.0, 5.0)) is False and g.visible((float("nan"), 1.0), (5.0, 5.0)) is False
+    g2 = copy.deepcopy(g)
+    assert g2.visible((100, 100), (105, 104)) == r.visible((100, 100), (105, 104))
