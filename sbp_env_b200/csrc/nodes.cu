@@ -644,18 +644,20 @@ k_near_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
     }
 }
 
-// batched: thread per query over shared-memory node tiles.
-template <int D, bool XY, int PASS>
-__global__ void __launch_bounds__(KNN_TPB)
+// batched: thread per query over shared-memory node tiles; same branch-free 32-node
+// blocks as the kNN scan (flags gathered in a mask, then counted or written in order).
+template <int D, bool XY, int PASS, int TPB>
+__global__ void __launch_bounds__(TPB)
 k_near_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
                const double *__restrict__ X, int64_t m, double thr, int closed,
                int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
                int64_t *__restrict__ idx, int64_t idx_capacity,
                const int64_t *__restrict__ needed) {
     constexpr int DD = XY ? 2 : D;
-    __shared__ double tile[DD][KNN_TILE];
+    constexpr int TILE = TPB * 8;
+    __shared__ double tile[DD][TILE];
     if (PASS == 1 && *needed > idx_capacity) return;
-    const int64_t q = (int64_t)blockIdx.x * KNN_TPB + threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int s = blockIdx.y;
     const int64_t chunk = (n + S - 1) / S;
     const int64_t c0 = (int64_t)s * chunk;
@@ -665,23 +667,41 @@ k_near_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int 
     for (int j = 0; j < D; ++j) qv[j] = (q < m && j < DD) ? X[q * D + j] : 0.0;
     int64_t cnt_or_pos = 0;
     if (PASS == 1 && q < m) cnt_or_pos = offsets[q * S + s];
-    for (int64_t t0 = c0; t0 < c1; t0 += KNN_TILE) {
-        int cnt = (int)(c1 - t0 < KNN_TILE ? c1 - t0 : KNN_TILE);
+    for (int64_t t0 = c0; t0 < c1; t0 += TILE) {
+        int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < DD; ++j)
-            for (int t = threadIdx.x; t < cnt; t += KNN_TPB)
+            for (int t = threadIdx.x; t < cnt; t += TPB)
                 tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
         __syncthreads();
-        if (q < m) {
-#pragma unroll 4
-            for (int t = 0; t < cnt; ++t) {
-                double pv[D];
+        for (int b0 = 0; b0 < cnt; b0 += 32) {
+            const int bn = cnt - b0 < 32 ? cnt - b0 : 32;
+            uint32_t mask = 0;
+            if (bn == 32) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][t] : 0.0;
-                bool in = near_in(near_d2<D, XY>(pv, qv), thr, closed);
-                if (PASS == 0) cnt_or_pos += in ? 1 : 0;
-                else if (in) idx[cnt_or_pos++] = t0 + t;
+                for (int t = 0; t < 32; ++t) {
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][b0 + t] : 0.0;
+                    mask |= near_in(near_d2<D, XY>(pv, qv), thr, closed) ? (1u << t) : 0u;
+                }
+            } else {
+                for (int t = 0; t < bn; ++t) {
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][b0 + t] : 0.0;
+                    mask |= near_in(near_d2<D, XY>(pv, qv), thr, closed) ? (1u << t) : 0u;
+                }
+            }
+            if (PASS == 0) {
+                cnt_or_pos += __popc(mask);
+            } else if (q < m) {
+                while (mask) {                                   // ascending node index
+                    const int t = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    idx[cnt_or_pos++] = t0 + b0 + t;
+                }
             }
         }
     }
@@ -726,14 +746,19 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
     sbp_ctx *ctx = s->ctx;
     const int64_t n = s->n;
     bool wide = m < 256;
-    int S;
+    int S, tpb = 128;
     if (wide) {
         int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
         int64_t maxs = (n + 2047) / 2048;
         S = (int)(want < maxs ? want : maxs);
     } else {
-        int64_t tiles = (m + KNN_TPB - 1) / KNN_TPB;
-        int64_t want = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+        int64_t sm = ctx->sm_count;
+        int64_t w128 = ((m + 127) / 128 + sm - 1) / sm * 128;
+        int64_t w32 = ((m + 31) / 32 + sm - 1) / sm * 32;
+        tpb = (w32 * 100 < w128 * 95) ? 32 : 128;
+        int64_t tiles = (m + tpb - 1) / tpb;
+        // no per-chunk restart cost here (unlike the kNN lists): aim for >= 24 warps per SM
+        int64_t want = (24 * sm * 32 / tpb + tiles - 1) / tiles;
         int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
     }
@@ -744,15 +769,24 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
     int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
     if (rc) return rc;
     int64_t *counts = (int64_t *)ws, *offsets = counts + L;
-    dim3 gw((unsigned)m, (unsigned)S), gb((unsigned)((m + KNN_TPB - 1) / KNN_TPB), (unsigned)S);
+    dim3 gw((unsigned)m, (unsigned)S), gb((unsigned)((m + tpb - 1) / tpb), (unsigned)S);
+#define NEAR_BATCHED(PASSV)                                                                        \
+    do {                                                                                            \
+        if (tpb == 32)                                                                              \
+            k_near_batched<D, XY, PASSV, 32><<<gb, 32, 0, ctx->stream>>>(                           \
+                s->d_soa, s->capacity, n, S, X, m, thr, closed, counts, offsets, idx, idx_capacity, \
+                needed);                                                                            \
+        else                                                                                        \
+            k_near_batched<D, XY, PASSV, 128><<<gb, 128, 0, ctx->stream>>>(                         \
+                s->d_soa, s->capacity, n, S, X, m, thr, closed, counts, offsets, idx, idx_capacity, \
+                needed);                                                                            \
+    } while (0)
     if (wide)
         k_near_wide<D, XY, 0><<<gw, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m, thr,
                                                                 closed, counts, offsets, idx,
                                                                 idx_capacity, needed);
     else
-        k_near_batched<D, XY, 0><<<gb, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
-                                                                  thr, closed, counts, offsets, idx,
-                                                                  idx_capacity, needed);
+        NEAR_BATCHED(0);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, L, S, m, offsets, row_ptr, needed);
@@ -764,12 +798,11 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
                                                                     thr, closed, counts, offsets, idx,
                                                                     idx_capacity, needed);
         else
-            k_near_batched<D, XY, 1><<<gb, KNN_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X,
-                                                                      m, thr, closed, counts, offsets,
-                                                                      idx, idx_capacity, needed);
+            NEAR_BATCHED(1);
         ctx->launches++;
         SBP_CUDA(cudaGetLastError());
     }
+#undef NEAR_BATCHED
     return SBP_OK;
 }
 

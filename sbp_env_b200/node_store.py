@@ -160,11 +160,16 @@ class NodeStore:
             m = X.shape[0]
             row_ptr = torch.empty(m + 1, dtype=torch.int64, device=X.device)
             needed = torch.zeros(1, dtype=torch.int64, device=X.device)
+            # one call (count -> scan -> ordered fill) into a generously sized buffer; the
+            # size of the answer has to reach the host anyway, and only an overflow costs a
+            # second call
+            cap = max(1 << 20, 64 * m)
+            idx = torch.empty(cap, dtype=torch.int64, device=X.device)
             check(lib.sbp_nodes_near(self._h, ptr(X), m, float(r), met, int(bool(closed)),
-                                     ptr(row_ptr), None, 0, ptr(needed)), "sbp_nodes_near")
-            total = int(needed.item())            # the size of the answer has to reach the host
-            idx = torch.empty(max(total, 1), dtype=torch.int64, device=X.device)
-            if total:
+                                     ptr(row_ptr), ptr(idx), cap, ptr(needed)), "sbp_nodes_near")
+            total = int(needed.item())
+            if total > cap:
+                idx = torch.empty(total, dtype=torch.int64, device=X.device)
                 check(lib.sbp_nodes_near(self._h, ptr(X), m, float(r), met, int(bool(closed)),
                                          ptr(row_ptr), ptr(idx), total, ptr(needed)), "sbp_nodes_near")
             return row_ptr, idx[:total]

@@ -87,3 +87,27 @@ def roadmap_edges_to_host(nbr, vis, first_row: int = 0):
     rows = np.repeat(np.arange(first_row, first_row + nbr.shape[0], dtype=np.int64), nbr.shape[1])
     sel = vis.reshape(-1)
     return nbr.reshape(-1)[sel], rows[sel]
+
+
+def prm_connect_radius(cc, tree, radius: float):
+    """The reference's own PRM* connection rule in two launches: for every stored node v,
+    ``nearest_neighbours(nodes, poses, v.pos, radius)`` (all dims, strict ``<``,
+    index-ascending, prmPlanner.py:28-44, :92) minus v itself (``m_g is v``, :94-95), and
+    ``cc.visible(m_g.pos, v.pos)`` for each pair (:97).
+
+    Returns CUDA tensors ``(src, dst, vis)``: candidate directed edges m_g -> v in the
+    order the reference's double loop visits them, and their visibility.  (at
+    the reference's gamma the radius exceeds every shipped map, i.e. this is the complete
+    graph; use it with small n or a sane radius.)"""
+    import torch
+
+    tree.ctx.use_torch_stream()
+    n = len(tree)
+    X = tree.rows_device(0, n)
+    row_ptr, idx = tree.near(X, radius, metric="full", closed=False)
+    dev = X.device
+    dst = torch.repeat_interleave(torch.arange(n, device=dev, dtype=torch.int64), row_ptr[1:] - row_ptr[:-1])
+    keep = idx != dst                      # drop v itself; duplicates of v at other indices stay
+    src, dst = idx[keep], dst[keep]
+    vis = cc.visible_batch(X[src].contiguous(), X[dst].contiguous())
+    return src, dst, vis

@@ -165,3 +165,40 @@ def test_prm_connect_external_queries(sg):
     assert np.array_equal(nbr.cpu().numpy(), oi) and np.array_equal(dist.cpu().numpy(), od)
     exp = om.visible2d(nodes[oi.reshape(-1)], np.repeat(X, k, axis=0)).reshape(-1, k)
     assert np.array_equal(vis.cpu().numpy(), exp)
+
+
+def test_prm_connect_radius_is_the_reference_double_loop(sg):
+    """prmPlanner.py:91-101 restated: for v in nodes: for m_g in near(v, r): skip self;
+    visible(m_g, v)."""
+    free = load_map("maze2")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("maze2"))
+    om = orc.Map(free)
+    rng = np.random.default_rng(21)
+    pts = rng.random((3000, 2)) * [W, H]
+    pts = pts[om.feasible2d(pts)][:1200]
+    pts[40] = pts[10]                                     # duplicate of another node: NOT skipped
+    t = sg.NodeStore(2)
+    t.extend(pts)
+    r = 30.0
+    src, dst, vis = sg.prm_connect_radius(cc, t, r)
+    es, ed = [], []
+    for v in range(len(pts)):
+        d = np.linalg.norm(pts - pts[v], axis=1)
+        for m_g in np.flatnonzero(d < r):
+            if m_g != v:
+                es.append(m_g); ed.append(v)
+    assert src.cpu().numpy().tolist() == es and dst.cpu().numpy().tolist() == ed
+    assert np.array_equal(vis.cpu().numpy(), om.visible2d(pts[es], pts[ed]))
+
+
+def test_arm_checker_map_mat_path(sg):
+    """RobotArm4dCollisionChecker(map_mat=...) (collisionChecker.py:333-334)."""
+    free = load_map("maze1")
+    mat = free.T.astype(np.float64) * 255.0               # an image-like [H][W] matrix
+    cc = sg.RobotArm4dCollisionChecker(None, map_mat=mat, stick_robot_length_config=[9.0, 4.0])
+    assert cc._img.shape == free.shape and cc._img.dtype.kind == "i"
+    om = orc.Map(free)
+    rng = np.random.default_rng(8)
+    C = rng.random((5000, 4)) * [free.shape[0], free.shape[1], 6, 6] - [0, 0, 3, 3]
+    assert np.array_equal(cc.feasible_batch(C), om.arm_feasible(C, 9.0, 4.0))
