@@ -80,6 +80,8 @@ struct sbp_nodes {
     int64_t n = 0;
     int64_t capacity = 0;
     double *d_soa = nullptr;         // [d][capacity] fp64, structure of arrays
+    float *d_soa32 = nullptr;        // fp32 shadow (kNN prefilter only; never decides a result)
+    double *d_maxabs = nullptr;      // device scalar: max |coordinate| ever appended (inf if non-finite)
 };
 
 // --------------------------------------------------------- device helpers ---

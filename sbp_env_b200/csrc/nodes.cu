@@ -36,6 +36,9 @@ extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, s
     s->d = d;
     s->capacity = capacity < 1024 ? 1024 : capacity;
     cudaError_t e = cudaMalloc(&s->d_soa, (size_t)s->capacity * d * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_soa32, (size_t)s->capacity * d * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_maxabs, sizeof(double));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_maxabs, 0, sizeof(double), ctx->stream);
     if (e != cudaSuccess) {
         delete s;
         sbp_set_error("sbp_nodes_create: cudaMalloc failed: %s", cudaGetErrorString(e));
@@ -50,19 +53,34 @@ extern "C" int32_t sbp_nodes_destroy(sbp_nodes *s) {
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->d_soa) cudaFree(s->d_soa);
+    if (s->d_soa32) cudaFree(s->d_soa32);
+    if (s->d_maxabs) cudaFree(s->d_maxabs);
     delete s;
     return SBP_OK;
 }
 
 __global__ void k_aos_to_soa(const double *__restrict__ X, int64_t m, int d, double *__restrict__ soa,
+                             float *__restrict__ soa32, double *__restrict__ maxabs,
                              int64_t capacity, int64_t offset) {
     int64_t total = m * d;
+    double mx = 0.0;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
         int64_t row = t / d;
         int j = (int)(t - row * d);
-        soa[(int64_t)j * capacity + offset + row] = X[t];
+        double v = X[t];
+        soa[(int64_t)j * capacity + offset + row] = v;
+        soa32[(int64_t)j * capacity + offset + row] = (float)v;
+        double av = (v != v) ? INFINITY : fabs(v);
+        mx = av > mx ? av : mx;
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        double other = __shfl_down_sync(0xffffffffu, mx, o);
+        mx = other > mx ? other : mx;
+    }
+    // non-negative doubles order like their bit patterns
+    if ((threadIdx.x & 31) == 0 && mx > 0.0)
+        atomicMax((unsigned long long *)maxabs, (unsigned long long)__double_as_longlong(mx));
 }
 
 __global__ void k_soa_to_aos(const double *__restrict__ soa, int64_t capacity, int64_t first,
@@ -82,14 +100,22 @@ static int32_t nodes_grow(sbp_nodes *s, int64_t need) {
     while (cap < need) cap *= 2;
     SBP_REQUIRE(cap < ((int64_t)1 << 31), "node store limited to 2^31-1 nodes");
     double *nw = nullptr;
+    float *nw32 = nullptr;
     SBP_CUDA(cudaMalloc(&nw, (size_t)cap * s->d * sizeof(double)));
-    for (int j = 0; j < s->d; ++j)
+    SBP_CUDA(cudaMalloc(&nw32, (size_t)cap * s->d * sizeof(float)));
+    for (int j = 0; j < s->d; ++j) {
         SBP_CUDA(cudaMemcpyAsync(nw + (int64_t)j * cap, s->d_soa + (int64_t)j * s->capacity,
                                  (size_t)s->n * sizeof(double), cudaMemcpyDeviceToDevice,
                                  s->ctx->stream));
+        SBP_CUDA(cudaMemcpyAsync(nw32 + (int64_t)j * cap, s->d_soa32 + (int64_t)j * s->capacity,
+                                 (size_t)s->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 s->ctx->stream));
+    }
     SBP_CUDA(cudaStreamSynchronize(s->ctx->stream));
     SBP_CUDA(cudaFree(s->d_soa));
+    SBP_CUDA(cudaFree(s->d_soa32));
     s->d_soa = nw;
+    s->d_soa32 = nw32;
     s->capacity = cap;
     return SBP_OK;
 }
@@ -114,7 +140,8 @@ extern "C" int32_t sbp_nodes_append(sbp_nodes *s, const double *X, int64_t m, in
     int64_t total = m * s->d;
     int blocks = (int)((total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    k_aos_to_soa<<<blocks, 256, 0, ctx->stream>>>(src, m, s->d, s->d_soa, s->capacity, s->n);
+    k_aos_to_soa<<<blocks, 256, 0, ctx->stream>>>(src, m, s->d, s->d_soa, s->d_soa32, s->d_maxabs,
+                                                  s->capacity, s->n);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     // a pageable host source may be reused by the caller right after return
@@ -182,41 +209,44 @@ template <int K>
 struct TopK {
     double d[K];
     int32_t i[K];
-    double bound2;   // round-up(d[K-1]^2): candidates with d^2 >= bound2 are rejected
-    __device__ __forceinline__ void init() {
+    double bound2;   // round-up(d[K-1]^2): candidates with d^2 > bound2 are rejected
+    double seed2;    // a-priori bound used while the list is not full (inf = none)
+    __device__ __forceinline__ void init(double seed = INFINITY) {
 #pragma unroll
         for (int t = 0; t < K; ++t) { d[t] = INFINITY; i[t] = -1; }
-        bound2 = INFINITY;
+        bound2 = seed2 = seed;
+    }
+    // Empty slots are (inf, -1) and rank after every real entry, including real entries
+    // whose distance is +inf (fp64 overflow of d^2): those fill the list in index order,
+    // as a stable argsort of an all-inf row does.
+    //
+    // Branch-free sorted insertion: r_t = "entry t ranks before the new one" (real and
+    // d[t] <= dd; ties keep the earlier arrival = lower index) is a prefix of trues, and
+    //     new[t] = r_t ? old[t] : (r_{t-1} ? (dd, idx) : old[t-1]).
+    // Pure predicate/select code, ~8 instructions per slot (the earlier `if (!placed)`
+    // formulation made ptxas copy the whole list per step: ~30 instructions per slot).
+    __device__ __forceinline__ void insert_sorted(double dd, int32_t idx) {
+        bool r_cur = i[K - 1] >= 0 && d[K - 1] <= dd;        // r_{K-1}: true => list full, no room
+#pragma unroll
+        for (int t = K - 1; t >= 1; --t) {
+            const bool r_prev = i[t - 1] >= 0 && d[t - 1] <= dd;
+            const double nd = r_prev ? dd : d[t - 1];
+            const int32_t ni = r_prev ? idx : i[t - 1];
+            d[t] = r_cur ? d[t] : nd;
+            i[t] = r_cur ? i[t] : ni;
+            r_cur = r_prev;
+        }
+        d[0] = r_cur ? d[0] : dd;
+        i[0] = r_cur ? i[0] : idx;
     }
     __device__ __forceinline__ void offer(double d2, int32_t idx) {
-        if (d2 < bound2) {
-            double dd = __dsqrt_rn(d2);
-            if (dd < d[K - 1]) {
-                bool placed = false;
-#pragma unroll
-                for (int t = K - 1; t >= 0; --t) {
-                    if (!placed) {
-                        if (t > 0 && dd < d[t - 1]) { d[t] = d[t - 1]; i[t] = i[t - 1]; }
-                        else { d[t] = dd; i[t] = idx; placed = true; }
-                    }
-                }
-                bound2 = __dmul_ru(d[K - 1], d[K - 1]);
-            }
+        if (d2 <= bound2 && idx >= 0) {
+            insert_sorted(__dsqrt_rn(d2), idx);
+            bound2 = i[K - 1] < 0 ? seed2 : __dmul_ru(d[K - 1], d[K - 1]);
         }
     }
     // insert an already square-rooted distance (merging partial lists)
-    __device__ __forceinline__ void offer_sorted(double dd, int32_t idx) {
-        if (dd < d[K - 1]) {
-            bool placed = false;
-#pragma unroll
-            for (int t = K - 1; t >= 0; --t) {
-                if (!placed) {
-                    if (t > 0 && dd < d[t - 1]) { d[t] = d[t - 1]; i[t] = i[t - 1]; }
-                    else { d[t] = dd; i[t] = idx; placed = true; }
-                }
-            }
-        }
-    }
+    __device__ __forceinline__ void offer_sorted(double dd, int32_t idx) { insert_sorted(dd, idx); }
     // remove the head (used by the block merge)
     __device__ __forceinline__ void pop() {
 #pragma unroll
@@ -226,61 +256,125 @@ struct TopK {
 };
 
 // ---------------------------------------------- K4a: batched, thread/query ---
-// grid = (ceil(m / KNN_TPB), S).  CTA (bx, s) scans node chunk s for its 128
-// queries; node tiles are staged in shared memory (SoA) and read by broadcast.
+// grid = (ceil(m / TPB), S).  CTA (bx, s) scans node chunk s for its TPB queries; node
+// tiles are staged in shared memory (SoA) and read by broadcast.
+//
+// Two-phase scan per block of 32 nodes.  Phase 1 is branch-free with the top-k state
+// read-only (a fused scan+insert loop made ptxas copy the whole list between unrolled
+// iterations: ~45 instructions per pair) and only FLAGS candidates in a 32-bit mask.
+// Phase 2 revisits the flagged nodes in lock-step over the warp and decides them exactly
+// in fp64 (offer()); stale or spurious flags are harmless because offer() re-checks.
+//
+// fp32 prefilter (default).  Phase 1 runs on an fp32 shadow of the nodes: d2f =
+// fma(dy,dy,dx*dx) is compared with a per-query threshold thr_f that is CONSERVATIVE:
+// with u = 2^-24, M = max |coordinate| and a = 4*M*u*sqrt(D) (conversion + subtraction
+// error of every component), the fp32 value of a pair whose exact distance is r satisfies
+// d2f <= (r + a)^2 (1+u)^D, so every pair with fp64 d^2 < bound2 has
+// d2f <= thr_f := round_up((sqrt(bound2) + a)^2 (1 + 1e-6)).  The prefilter can therefore
+// only add false positives (a relative band of ~1e-6), never lose a neighbour; results
+// stay bit-exact while the scan moves from the fp64 pipe (64 lanes/SM) to the fp32 pipe
+// (128 lanes/SM).  It is bypassed (pure fp64 scan) when coordinates are too large for
+// fp32 squares (M >= 1e15) or when sbp_tune("knn_prefilter", 0) is set.
+__device__ __forceinline__ float knn_thr32(double bound2, double a) {
+    if (!(bound2 < INFINITY)) return INFINITY;
+    double r = sqrt(bound2) + a;
+    return __double2float_ru(r * r * (1.0 + 1e-6));
+}
+
 template <int D, int K, int TPB>
 __global__ void __launch_bounds__(TPB)
-k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
-              const double *__restrict__ X, int64_t m, double *__restrict__ pd,
-              int32_t *__restrict__ pi) {
+k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
+              const double *__restrict__ maxabs, int prefilter, int64_t capacity, int64_t n, int S,
+              const double *__restrict__ X, int64_t m, const double *__restrict__ seed2,
+              double *__restrict__ pd, int32_t *__restrict__ pi) {
     constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
-    __shared__ double tile[D][TILE];
+    __shared__ double tile[D][TILE];  // fp64 tile, or the fp32 tile in the same storage
+    float(*tile32)[TILE] = reinterpret_cast<float(*)[TILE]>(&tile[0][0]);
     const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
     const int s = blockIdx.y;
     const int64_t chunk = (n + S - 1) / S;
     const int64_t c0 = (int64_t)s * chunk;
     const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
     double qv[D];
+    float qf[D];
+    double qmax = 0.0;
 #pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = q < m ? X[q * D + j] : 0.0;
+    for (int j = 0; j < D; ++j) {
+        qv[j] = q < m ? X[q * D + j] : 0.0;
+        qf[j] = (float)qv[j];
+        double av = qv[j] != qv[j] ? INFINITY : fabs(qv[j]);
+        qmax = av > qmax ? av : qmax;
+    }
+    const double M = *maxabs;
+    const bool use32 = prefilter && M < 1e15;              // block-uniform
+    const double mm = M > qmax ? M : qmax;
+    const bool lane32 = mm < 1e15;                         // this lane's fp32 squares are safe
+    const double a_err = 4.0 * mm * 5.9604644775390625e-8 * sqrt((double)D) * (1.0 + 1e-6);
     TopK<K> top;
-    top.init();
+    top.init((seed2 && q < m) ? seed2[q] : INFINITY);
+    float thr_f = (use32 && lane32) ? knn_thr32(top.bound2, a_err) : INFINITY;
     for (int64_t t0 = c0; t0 < c1; t0 += TILE) {
         int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         __syncthreads();
+        if (use32) {
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            for (int t = threadIdx.x; t < cnt; t += TPB)
-                tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
+            for (int j = 0; j < D; ++j)
+                for (int t = threadIdx.x; t < cnt; t += TPB)
+                    tile32[j][t] = soa32[(int64_t)j * capacity + t0 + t];
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                for (int t = threadIdx.x; t < cnt; t += TPB)
+                    tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
+        }
         __syncthreads();
-        // Two-phase scan per block of 32 nodes.  Phase 1 is branch-free: six fp64
-        // instructions per pair plus one predicated bit-set, with the top-k state
-        // read-only (a fused scan+insert loop made ptxas copy the whole list between
-        // unrolled iterations: ~45 instructions per pair).  Phase 2 revisits only the
-        // flagged nodes; the bound can only have tightened meanwhile, and offer()
-        // re-checks it, so stale flags are harmless.
         for (int b0 = 0; b0 < cnt; b0 += 32) {
             const int bn = cnt - b0 < 32 ? cnt - b0 : 32;
             const double bound2 = top.bound2;
             uint32_t mask = 0;
-            if (bn == 32) {
+            if (use32) {
+                if (bn == 32) {
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    double pv[D];
+                    for (int t = 0; t < 32; ++t) {
+                        float sf = 0.f;
 #pragma unroll
-                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
-                    mask |= (dist2_full<D>(pv, qv) < bound2) ? (1u << t) : 0u;
+                        for (int j = 0; j < D; ++j) {
+                            float df = tile32[j][b0 + t] - qf[j];
+                            sf = j == 0 ? df * df : fmaf(df, df, sf);
+                        }
+                        mask |= (sf <= thr_f) ? (1u << t) : 0u;
+                    }
+                } else {
+                    for (int t = 0; t < bn; ++t) {
+                        float sf = 0.f;
+#pragma unroll
+                        for (int j = 0; j < D; ++j) {
+                            float df = tile32[j][b0 + t] - qf[j];
+                            sf = j == 0 ? df * df : fmaf(df, df, sf);
+                        }
+                        mask |= (sf <= thr_f) ? (1u << t) : 0u;
+                    }
                 }
             } else {
-                for (int t = 0; t < bn; ++t) {
-                    double pv[D];
+                if (bn == 32) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
-                    mask |= (dist2_full<D>(pv, qv) < bound2) ? (1u << t) : 0u;
+                    for (int t = 0; t < 32; ++t) {
+                        double pv[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                        mask |= (dist2_full<D>(pv, qv) <= bound2) ? (1u << t) : 0u;
+                    }
+                } else {
+                    for (int t = 0; t < bn; ++t) {
+                        double pv[D];
+#pragma unroll
+                        for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                        mask |= (dist2_full<D>(pv, qv) <= bound2) ? (1u << t) : 0u;
+                    }
                 }
             }
-            // lock-step over the warp: round r inserts every lane's r-th flagged node,
-            // so insertions of different queries share one pass through offer()
+            // lock-step over the warp: round r decides every lane's r-th flagged node, so
+            // insertions of different queries share one pass through offer()
             while (__any_sync(0xffffffffu, mask != 0u)) {
                 double d2 = INFINITY;
                 int32_t id = -1;
@@ -289,12 +383,14 @@ k_knn_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S
                     mask &= mask - 1;
                     double pv[D];
 #pragma unroll
-                    for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
+                    for (int j = 0; j < D; ++j)
+                        pv[j] = use32 ? soa[(int64_t)j * capacity + t0 + b0 + t] : tile[j][b0 + t];
                     d2 = dist2_full<D>(pv, qv);
                     id = (int32_t)(t0 + b0 + t);
                 }
                 top.offer(d2, id);
             }
+            if (use32 && top.bound2 != bound2) thr_f = lane32 ? knn_thr32(top.bound2, a_err) : INFINITY;
         }
     }
     if (q < m) {
@@ -388,8 +484,8 @@ k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
         uint32_t mask = 0;
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-            d2[u] = dist2_full<D>(pv[u], qv);      // inf for the padding slots: never flagged
-            mask |= (d2[u] < top.bound2) ? (1u << u) : 0u;
+            d2[u] = dist2_full<D>(pv[u], qv);
+            mask |= (t0 + (int64_t)u * WIDE_TPB < c1 && d2[u] <= top.bound2) ? (1u << u) : 0u;
         }
         if (mask) {
 #pragma unroll
@@ -462,7 +558,229 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
     }
 }
 
+// ---------------------------------------------------- kNN seeding (d = 2) ----
+// An a-priori upper bound of each query's K-th neighbour distance, so that the brute
+// force scan does not spend K*ln(N/K) list insertions per query discovering it.  Nodes
+// are counted into a uniform G x G grid over their bounding box; a query grows a square
+// block of cells around its own cell until the block holds >= K nodes; every node of the
+// block lies within B = distance from the query to the farthest corner of the block, so
+// the K-th nearest distance is <= B and no node farther than B can be among the K nearest.
+// B^2 is inflated by 1e-9 (cell-assignment rounding, and distinct d^2 that collapse to one
+// rounded square root).  The scan still evaluates every (query, node) pair; only the
+// number of candidates that reach the exact fp64 insertion path shrinks (~9.4K -> ~2K).
+#define BOUNDS_BLOCKS 128
+// per-block partial bounding boxes [BOUNDS_BLOCKS][4] = (min x, max x, min y, max y)
+__global__ void __launch_bounds__(256)
+k_bounds2d_partial(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                   double *__restrict__ partial) {
+    __shared__ double sh[4][8];
+    double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
+        double x = soa[t], y = soa[capacity + t];
+        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mnx = fmin(mnx, __shfl_down_sync(0xffffffffu, mnx, o));
+        mxx = fmax(mxx, __shfl_down_sync(0xffffffffu, mxx, o));
+        mny = fmin(mny, __shfl_down_sync(0xffffffffu, mny, o));
+        mxy = fmax(mxy, __shfl_down_sync(0xffffffffu, mxy, o));
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][w] = mnx; sh[1][w] = mxx; sh[2][w] = mny; sh[3][w] = mxy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) {
+            mnx = fmin(mnx, sh[0][i]); mxx = fmax(mxx, sh[1][i]);
+            mny = fmin(mny, sh[2][i]); mxy = fmax(mxy, sh[3][i]);
+        }
+        double *o = partial + 4 * blockIdx.x;
+        o[0] = mnx; o[1] = mxx; o[2] = mny; o[3] = mxy;
+    }
+}
+
+// every block of the histogram kernel folds the partials itself (block 0 publishes b4)
+__device__ __forceinline__ void fold_bounds(const double *__restrict__ partial, int nb, double *sh4) {
+    if (threadIdx.x < 32) {
+        double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+        for (int i = threadIdx.x; i < nb; i += 32) {
+            mnx = fmin(mnx, partial[4 * i]); mxx = fmax(mxx, partial[4 * i + 1]);
+            mny = fmin(mny, partial[4 * i + 2]); mxy = fmax(mxy, partial[4 * i + 3]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fmin(mnx, __shfl_down_sync(0xffffffffu, mnx, o));
+            mxx = fmax(mxx, __shfl_down_sync(0xffffffffu, mxx, o));
+            mny = fmin(mny, __shfl_down_sync(0xffffffffu, mny, o));
+            mxy = fmax(mxy, __shfl_down_sync(0xffffffffu, mxy, o));
+        }
+        if (threadIdx.x == 0) { sh4[0] = mnx; sh4[1] = mxx; sh4[2] = mny; sh4[3] = mxy; }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int cell_of(double v, double mn, double mx, int G) {
+    double w = mx - mn;
+    if (!(w > 0.0)) return 0;
+    double c = floor((v - mn) * ((double)G / w));
+    return c < 0.0 ? 0 : c > (double)(G - 1) ? G - 1 : (int)c;      // NaN -> 0
+}
+
+__global__ void k_cell_hist(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                            const double *__restrict__ partial, int nb, double *__restrict__ b4,
+                            int G, int32_t *__restrict__ cells) {
+    __shared__ double sb[4];
+    fold_bounds(partial, nb, sb);
+    if (blockIdx.x == 0 && threadIdx.x < 4) b4[threadIdx.x] = sb[threadIdx.x];
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int cx = cell_of(soa[t], sb[0], sb[1], G), cy = cell_of(soa[capacity + t], sb[2], sb[3], G);
+        atomicAdd(cells + (int64_t)cy * G + cx, 1);
+    }
+}
+
+// exclusive scan of the cell counts (single CTA, coalesced tiles of 4096) -> cell starts,
+// and a second copy used as the scatter cursor
+__global__ void __launch_bounds__(1024)
+k_cell_scan(const int32_t *__restrict__ cells, int64_t L, int32_t *__restrict__ start,
+            int32_t *__restrict__ cursor) {
+    __shared__ int32_t wsum[32];
+    __shared__ int32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < L; base += 4096) {
+        const int64_t i0 = base + (int64_t)tid * 4;
+        int32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i0 + j < L ? cells[i0 + j] : 0;
+        int32_t tsum = v[0] + v[1] + v[2] + v[3];
+        int32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) wsum[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            int32_t x = wsum[lane], xi = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t u = __shfl_up_sync(0xffffffffu, xi, o);
+                if (lane >= o) xi += u;
+            }
+            wsum[lane] = xi - x;                         // exclusive warp offsets
+        }
+        __syncthreads();
+        const int32_t carry = carry_s;
+        int32_t run = carry + wsum[w] + inc - tsum;      // exclusive prefix of my 4 elements
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
+            run += v[j];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = run;                  // total so far
+        __syncthreads();
+    }
+    if (tid == 0) start[L] = carry_s;
+}
+
+__global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                               const double *__restrict__ b4, int G, int32_t *__restrict__ cursor,
+                               int32_t *__restrict__ ids) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int cx = cell_of(soa[t], b4[0], b4[1], G), cy = cell_of(soa[capacity + t], b4[2], b4[3], G);
+        ids[atomicAdd(cursor + (int64_t)cy * G + cx, 1)] = (int32_t)t;
+    }
+}
+
+// seed2[q] = K-th smallest exact fp64 d^2 among (up to 64) nodes of the block of cells around
+// the query -- a subset of the nodes, so an upper bound of the true K-th smallest -- inflated
+// by 1e-9.  One warp per query: the lanes gather the candidates in parallel and select the
+// K-th smallest by rank counting over shuffles.  The order of nodes inside a cell is
+// arbitrary and irrelevant: only the K-th smallest value is used.
+__global__ void __launch_bounds__(256)
+k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
+           const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
+           const int32_t *__restrict__ ids, int K, double *__restrict__ seed2) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= m) return;
+    const double qv[2] = {X[2 * q], X[2 * q + 1]};
+    const double mnx = b4[0], mxx = b4[1], mny = b4[2], mxy = b4[3];
+    double out = INFINITY;
+    if (qv[0] == qv[0] && qv[1] == qv[1] && mnx <= mxx && mny <= mxy) {
+        const int cx = cell_of(qv[0], mnx, mxx, G), cy = cell_of(qv[1], mny, mxy, G);
+        for (int r = 1; r <= 8; ++r) {
+            const int x0 = cx - r < 0 ? 0 : cx - r, x1 = cx + r > G - 1 ? G - 1 : cx + r;
+            const int y0 = cy - r < 0 ? 0 : cy - r, y1 = cy + r > G - 1 ? G - 1 : cy + r;
+            // lane t owns row y0 + t of the block (<= 17 rows)
+            int32_t e0 = 0, len = 0;
+            if (y0 + lane <= y1) {
+                e0 = start[(int64_t)(y0 + lane) * G + x0];
+                len = start[(int64_t)(y0 + lane) * G + x1 + 1] - e0;
+            }
+            int32_t inc = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t u = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += u;
+            }
+            const int32_t cnt = __shfl_sync(FULL, inc, 31);
+            const bool all = x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1;
+            if (cnt >= K) {
+                // flat candidate f (< min(cnt, 64)) lives in the row whose inclusive prefix first exceeds f
+                double v[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int f = lane + 32 * j;
+                    int32_t e = -1;
+                    for (int row = 0; row <= y1 - y0; ++row) {
+                        const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
+                        const int32_t re0 = __shfl_sync(FULL, e0, row);
+                        if (e < 0 && f < rinc && f < cnt) e = re0 + (f - (rinc - rlen));
+                    }
+                    v[j] = INFINITY;
+                    if (e >= 0) {
+                        const int32_t t = ids[e];
+                        const double pv[2] = {soa[t], soa[capacity + t]};
+                        v[j] = dist2_full<2>(pv, qv);
+                    }
+                }
+                // rank of each held value among the 64 (ties by position); the K-th smallest
+                // is the one with rank K-1
+                int rank[2] = {0, 0};
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    for (int src = 0; src < 32; ++src) {
+                        const double w = __shfl_sync(FULL, v[jj], src);
+                        const int wpos = src + 32 * jj;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const int mypos = lane + 32 * j;
+                            rank[j] += (w < v[j] || (w == v[j] && wpos < mypos)) ? 1 : 0;
+                        }
+                    }
+                }
+                double kth = -1.0;
+                if (rank[0] == K - 1) kth = v[0];
+                if (rank[1] == K - 1) kth = v[1];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(FULL, kth, o));
+                out = kth * (1.0 + 1e-9) + 1e-300;
+                break;
+            }
+            if (all) break;                            // fewer than K nodes in total
+        }
+    }
+    if (lane == 0) seed2[q] = out;
+}
+
+int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
 int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
+int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -509,14 +827,46 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         }
         return SBP_OK;
     }
+    const double *seed = nullptr;
+    if (D == 2 && g_knn_seed && n >= 2048) {
+        int G = (int)ceil(sqrt(2.0 * (double)n));
+        if (G > 2048) G = 2048;
+        const int64_t L = (int64_t)G * G;
+        void *cellbuf = nullptr, *seedbuf = nullptr;
+        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][cells L][start L+1][cursor L][ids n]
+        const size_t hdr = (4 + 4 * BOUNDS_BLOCKS) * sizeof(double);
+        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(3 * L + 1 + n) * sizeof(int32_t), &cellbuf);
+        if (rc) return rc;
+        rc = sbp_ctx_scratch(ctx, 6, (size_t)m * sizeof(double), &seedbuf);
+        if (rc) return rc;
+        double *b4 = (double *)cellbuf;
+        int32_t *cells = (int32_t *)((char *)cellbuf + hdr), *start = cells + L, *cursor = start + L + 1,
+                *ids = cursor + L;
+        SBP_CUDA(cudaMemsetAsync(cells, 0, (size_t)L * sizeof(int32_t), ctx->stream));
+        double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
+        k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
+        int hb = (int)((n + 255) / 256);
+        if (hb > ctx->sm_count * 8) hb = ctx->sm_count * 8;
+        k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,
+                                                 cells);
+        k_cell_scan<<<1, 1024, 0, ctx->stream>>>(cells, L, start, cursor);
+        k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
+        k_knn_seed<<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
+        ctx->launches += 5;
+        SBP_CUDA(cudaGetLastError());
+        seed = (const double *)seedbuf;
+    }
     if (tpb == 32) {
         dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
-        k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
-                                                              (double *)pd, (int32_t *)pi);
+        k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
+                                                              g_knn_prefilter, s->capacity, n, S, X,
+                                                              m, seed, (double *)pd, (int32_t *)pi);
     } else {
         dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
-        k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
-                                                                (double *)pd, (int32_t *)pi);
+        k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
+                                                                g_knn_prefilter, s->capacity, n, S,
+                                                                X, m, seed, (double *)pd, (int32_t *)pi);
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());

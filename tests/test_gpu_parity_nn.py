@@ -202,3 +202,84 @@ def test_arm_checker_map_mat_path(sg):
     rng = np.random.default_rng(8)
     C = rng.random((5000, 4)) * [free.shape[0], free.shape[1], 6, 6] - [0, 0, 3, 3]
     assert np.array_equal(cc.feasible_batch(C), om.arm_feasible(C, 9.0, 4.0))
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 0.0), (1e3, 0.0), (1e6, 0.0), (1e9, 0.0), (1e14, 0.0),
+                                          (1e16, 0.0), (1e200, 0.0), (1.0, 1e6), (1e-3, 4096.0),
+                                          (1e-9, 1.0)])
+def test_knn_fp32_prefilter_never_changes_results(sg, scale, offset):
+    """The fp32 prefilter of the batched kNN scan is conservative: at every coordinate
+    magnitude -- including clouds that fp32 cannot resolve at all (offset >> spread) and
+    magnitudes where it is bypassed (>= 1e15) -- indices and fp64 distances are those of the
+    oracle, and identical with the prefilter switched off."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(int(abs(np.log10(scale)) * 7 + offset) % 2 ** 31)
+    n, m, k = 6000, 800, 11
+    poses = rng.random((n, 2)) * scale + offset
+    poses[:300] = np.round(poses[:300] / scale * 8) / 8 * scale          # exact ties
+    X = rng.random((m, 2)) * scale + offset
+    t = sg.NodeStore(2)
+    t.extend(poses)
+    oi, od = orc.knn(poses, X, k)
+    lib = _lib.load()
+    try:
+        for pf in (1, 0):
+            lib.sbp_tune(b"knn_prefilter", pf)
+            idx, dist = t.knn(X, k)
+            assert np.array_equal(idx, oi), (scale, offset, pf)
+            assert np.array_equal(dist, od), (scale, offset, pf)
+    finally:
+        lib.sbp_tune(b"knn_prefilter", 1)
+
+
+def test_knn_prefilter_with_queries_far_outside_the_cloud(sg):
+    rng = np.random.default_rng(77)
+    poses = rng.random((5000, 4)) * 100
+    X = np.concatenate([rng.random((300, 4)) * 100, rng.random((300, 4)) * 1e7, -rng.random((300, 4)) * 1e17,
+                        rng.random((100, 4)) * 1e300])
+    t = sg.NodeStore(4)
+    t.extend(poses)
+    idx, dist = t.knn(X, 5)
+    oi, od = orc.knn(poses, X, 5)
+    assert np.array_equal(idx, oi) and np.array_equal(dist, od)
+
+
+@pytest.mark.parametrize("layout", ["uniform", "clustered", "duplicates", "line", "outliers"])
+def test_knn_grid_seed_never_changes_results(sg, layout):
+    """The grid-seeded a-priori bound (d = 2) only prunes insertions: results equal the
+    oracle's and the unseeded scan's on benign and on adversarial point layouts."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(len(layout))
+    n, m, k = 20000, 1500, 11
+    if layout == "uniform":
+        poses = rng.random((n, 2)) * 600
+    elif layout == "clustered":
+        c = rng.random((20, 2)) * 600
+        poses = c[rng.integers(0, 20, n)] + rng.standard_normal((n, 2)) * 0.5
+    elif layout == "duplicates":
+        poses = np.floor(rng.random((n, 2)) * 12) * 50.0          # 144 distinct positions
+    elif layout == "line":
+        poses = np.stack([rng.random(n) * 600, np.full(n, 123.25)], 1)   # zero extent in y
+    else:
+        poses = rng.random((n, 2)) * 10
+        poses[:5] = [[1e9, 1e9], [-1e9, 3.0], [5.0, 1e12], [0.0, 0.0], [10.0, 10.0]]
+    X = np.concatenate([poses[rng.integers(0, n, m // 2)] + rng.standard_normal((m // 2, 2)) * 0.3,
+                        rng.random((m - m // 2, 2)) * 900 - 150])
+    t = sg.NodeStore(2)
+    t.extend(poses)
+    oi, od = orc.knn(poses, X, k)
+    lib = _lib.load()
+    try:
+        for seed in (1, 0):
+            lib.sbp_tune(b"knn_seed", seed)
+            for kk in (k, 10, 1, 20):
+                idx, dist = t.knn(X, kk)
+                if kk == k:
+                    assert np.array_equal(idx, oi) and np.array_equal(dist, od), (layout, seed)
+                else:
+                    ei, ed = orc.knn(poses, X, kk)
+                    assert np.array_equal(idx, ei) and np.array_equal(dist, ed), (layout, seed, kk)
+    finally:
+        lib.sbp_tune(b"knn_seed", 1)
