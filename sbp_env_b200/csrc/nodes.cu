@@ -534,6 +534,37 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
         }
         return;
     }
+    if (S <= 4) {
+        // few chunks (the seeded batched path uses 1-4): head pointers stay in registers and
+        // each list's current head is cached, so a round is S compares and one reload
+        int h[4] = {0, 0, 0, 0};
+        double hd[4];
+        int32_t hi[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            hi[s] = s < S ? i0[s * K] : -1;
+            hd[s] = s < S ? d0[s * K] : INFINITY;
+        }
+        for (int t = 0; t < k; ++t) {
+            int best = -1;
+            double bd = INFINITY;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (hi[s] >= 0 && (best < 0 || hd[s] < bd)) { best = s; bd = hd[s]; }
+            int64_t oi = -1;
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+                if (s == best) {
+                    oi = hi[s];
+                    ++h[s];
+                    hi[s] = h[s] < K ? i0[s * K + h[s]] : -1;
+                    hd[s] = h[s] < K ? d0[s * K + h[s]] : INFINITY;
+                }
+            idx[q * k + t] = oi;
+            if (dist) dist[q * k + t] = best >= 0 ? bd : INFINITY;
+        }
+        return;
+    }
     unsigned char head[64];
     for (int s = 0; s < S; ++s) head[s] = 0;
     for (int t = 0; t < k; ++t) {
@@ -637,52 +668,75 @@ __global__ void k_cell_hist(const double *__restrict__ soa, int64_t capacity, in
     }
 }
 
-// exclusive scan of the cell counts (single CTA, coalesced tiles of 4096) -> cell starts,
-// and a second copy used as the scatter cursor
+// exclusive scan of the cell counts -> cell starts (+ a copy used as the scatter cursor),
+// in three small launches: per-tile sums, scan of the <= 1024 tile sums, per-tile scan + offset
+#define SCAN_TILE 4096
 __global__ void __launch_bounds__(1024)
-k_cell_scan(const int32_t *__restrict__ cells, int64_t L, int32_t *__restrict__ start,
-            int32_t *__restrict__ cursor) {
-    __shared__ int32_t wsum[32];
-    __shared__ int32_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (tid == 0) carry_s = 0;
+k_cell_tile_sums(const int32_t *__restrict__ cells, int64_t L, int32_t *__restrict__ tsums) {
+    __shared__ int32_t ws[32];
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
+    int32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v += i0 + j < L ? cells[i0 + j] : 0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (int64_t base = 0; base < L; base += 4096) {
-        const int64_t i0 = base + (int64_t)tid * 4;
-        int32_t v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = i0 + j < L ? cells[i0 + j] : 0;
-        int32_t tsum = v[0] + v[1] + v[2] + v[3];
-        int32_t inc = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        if (lane == 31) wsum[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            int32_t x = wsum[lane], xi = x;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int32_t u = __shfl_up_sync(0xffffffffu, xi, o);
-                if (lane >= o) xi += u;
-            }
-            wsum[lane] = xi - x;                         // exclusive warp offsets
-        }
-        __syncthreads();
-        const int32_t carry = carry_s;
-        int32_t run = carry + wsum[w] + inc - tsum;      // exclusive prefix of my 4 elements
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
-            run += v[j];
-        }
-        __syncthreads();
-        if (tid == 1023) carry_s = run;                  // total so far
-        __syncthreads();
+    if (threadIdx.x < 32) {
+        v = ws[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) tsums[blockIdx.x] = v;
     }
-    if (tid == 0) start[L] = carry_s;
+}
+
+__global__ void __launch_bounds__(1024)
+k_cell_scan_sums(int32_t *__restrict__ tsums, int nt, int32_t *__restrict__ total) {
+    __shared__ int32_t ws[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int32_t x = tid < nt ? tsums[tid] : 0, inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int32_t y = ws[lane], yi = y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
+        ws[lane] = yi - y;
+    }
+    __syncthreads();
+    const int32_t excl = ws[w] + inc - x;
+    if (tid < nt) tsums[tid] = excl;
+    if (tid == nt - 1) *total = excl + x;
+}
+
+__global__ void __launch_bounds__(1024)
+k_cell_scan_apply(const int32_t *__restrict__ cells, int64_t L, const int32_t *__restrict__ tsums,
+                  int32_t *__restrict__ start, int32_t *__restrict__ cursor) {
+    __shared__ int32_t ws[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = i0 + j < L ? cells[i0 + j] : 0;
+    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int32_t y = ws[lane], yi = y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
+        ws[lane] = yi - y;
+    }
+    __syncthreads();
+    int32_t run = tsums[blockIdx.x] + ws[w] + inc - tsum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
+        run += v[j];
+    }
 }
 
 __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity, int64_t n,
@@ -695,11 +749,11 @@ __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity,
     }
 }
 
-// seed2[q] = K-th smallest exact fp64 d^2 among (up to 64) nodes of the block of cells around
+// seed2[q] = K-th smallest exact fp64 d^2 among (up to 32) nodes of the block of cells around
 // the query -- a subset of the nodes, so an upper bound of the true K-th smallest -- inflated
-// by 1e-9.  One warp per query: the lanes gather the candidates in parallel and select the
-// K-th smallest by rank counting over shuffles.  The order of nodes inside a cell is
-// arbitrary and irrelevant: only the K-th smallest value is used.
+// by 1e-9.  One warp per query: lane f takes the f-th node of the block (row-major over its
+// cells), and the K-th smallest is selected by rank counting over shuffles.  Which nodes of a
+// dense block make it into the 32 is arbitrary and irrelevant for correctness.
 __global__ void __launch_bounds__(256)
 k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
            const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
@@ -731,42 +785,27 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
             const int32_t cnt = __shfl_sync(FULL, inc, 31);
             const bool all = x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1;
             if (cnt >= K) {
-                // flat candidate f (< min(cnt, 64)) lives in the row whose inclusive prefix first exceeds f
-                double v[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int f = lane + 32 * j;
-                    int32_t e = -1;
-                    for (int row = 0; row <= y1 - y0; ++row) {
-                        const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
-                        const int32_t re0 = __shfl_sync(FULL, e0, row);
-                        if (e < 0 && f < rinc && f < cnt) e = re0 + (f - (rinc - rlen));
-                    }
-                    v[j] = INFINITY;
-                    if (e >= 0) {
-                        const int32_t t = ids[e];
-                        const double pv[2] = {soa[t], soa[capacity + t]};
-                        v[j] = dist2_full<2>(pv, qv);
-                    }
+                // flat candidate `lane` lives in the first row whose inclusive prefix exceeds it
+                int32_t e = -1;
+                for (int row = 0; row <= y1 - y0; ++row) {
+                    const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
+                    const int32_t re0 = __shfl_sync(FULL, e0, row);
+                    if (e < 0 && lane < rinc) e = re0 + (lane - (rinc - rlen));
                 }
-                // rank of each held value among the 64 (ties by position); the K-th smallest
-                // is the one with rank K-1
-                int rank[2] = {0, 0};
-#pragma unroll
-                for (int jj = 0; jj < 2; ++jj) {
-                    for (int src = 0; src < 32; ++src) {
-                        const double w = __shfl_sync(FULL, v[jj], src);
-                        const int wpos = src + 32 * jj;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const int mypos = lane + 32 * j;
-                            rank[j] += (w < v[j] || (w == v[j] && wpos < mypos)) ? 1 : 0;
-                        }
-                    }
+                double v = INFINITY;
+                if (e >= 0) {
+                    const int32_t t = ids[e];
+                    const double pv[2] = {soa[t], soa[capacity + t]};
+                    v = dist2_full<2>(pv, qv);
                 }
-                double kth = -1.0;
-                if (rank[0] == K - 1) kth = v[0];
-                if (rank[1] == K - 1) kth = v[1];
+                // rank among the 32 held values (ties by lane); rank K-1 is the K-th smallest
+                int rank = 0;
+#pragma unroll 8
+                for (int src = 0; src < 32; ++src) {
+                    const double w = __shfl_sync(FULL, v, src);
+                    rank += (w < v || (w == v && src < lane)) ? 1 : 0;
+                }
+                double kth = rank == K - 1 ? v : -1.0;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(FULL, kth, o));
                 out = kth * (1.0 + 1e-9) + 1e-300;
@@ -801,7 +840,11 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         int64_t w32 = ((m + 31) / 32 + sm - 1) / sm * 32;
         tpb = (w32 * 100 < w128 * 95) ? 32 : 128;
         int64_t tiles = (m + tpb - 1) / tpb;
-        int64_t want = (2 * sm + tiles - 1) / tiles;
+        // node chunks: with seeded bounds a chunk restart is cheap, so fill the SMs with
+        // ~28 warps each (measured: 1.23 -> 1.04 ms on 50k x 50k); without seeds every chunk
+        // re-learns its bound (K ln(N/K) insertions), so only enough CTAs to cover the SMs
+        const bool seeded = D == 2 && g_knn_seed && n >= 2048;
+        int64_t want = seeded ? (28 * sm * 32 / tpb + tiles - 1) / tiles : (2 * sm + tiles - 1) / tiles;
         int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
     }
@@ -833,15 +876,15 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         if (G > 2048) G = 2048;
         const int64_t L = (int64_t)G * G;
         void *cellbuf = nullptr, *seedbuf = nullptr;
-        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][cells L][start L+1][cursor L][ids n]
+        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][cells L][start L+1][cursor L][ids n][tile sums 1024]
         const size_t hdr = (4 + 4 * BOUNDS_BLOCKS) * sizeof(double);
-        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(3 * L + 1 + n) * sizeof(int32_t), &cellbuf);
+        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
         if (rc) return rc;
         rc = sbp_ctx_scratch(ctx, 6, (size_t)m * sizeof(double), &seedbuf);
         if (rc) return rc;
         double *b4 = (double *)cellbuf;
         int32_t *cells = (int32_t *)((char *)cellbuf + hdr), *start = cells + L, *cursor = start + L + 1,
-                *ids = cursor + L;
+                *ids = cursor + L, *tsums = ids + n;
         SBP_CUDA(cudaMemsetAsync(cells, 0, (size_t)L * sizeof(int32_t), ctx->stream));
         double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
         k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
@@ -849,11 +892,14 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         if (hb > ctx->sm_count * 8) hb = ctx->sm_count * 8;
         k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,
                                                  cells);
-        k_cell_scan<<<1, 1024, 0, ctx->stream>>>(cells, L, start, cursor);
+        const int nt = (int)((L + SCAN_TILE - 1) / SCAN_TILE);            // <= 1024 tiles (G <= 2048)
+        k_cell_tile_sums<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums);
+        k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
+        k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
         k_knn_seed<<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
             s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
-        ctx->launches += 5;
+        ctx->launches += 7;
         SBP_CUDA(cudaGetLastError());
         seed = (const double *)seedbuf;
     }
