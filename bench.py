@@ -284,9 +284,9 @@ def run_ours(args):
     # workload, from the ncu --set full capture summarised in profiles/r1_knn_batched_full.txt
     roof = {"kernel": "k_knn_batched<2,11,32> (+ seed pipeline, k_knn_merge): the 'knn' phase, 95% of the step",
             "bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": 1626880, "peak_source": peak_src,
+            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": 8691712, "peak_source": peak_src,
             "note": "brute-force kNN with 32 queries sharing each streamed node is instruction-issue "
-                    "bound, not HBM bound (1.6 MB of DRAM traffic per launch): see alu"}
+                    "bound, not HBM bound (8.7 MB of DRAM traffic per launch): see alu"}
 
     import ctypes as C
 
