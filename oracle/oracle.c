@@ -367,23 +367,27 @@ void orc_nearest(const double *poses, int64_t N, int d, const double *X,
 }
 
 /* k nearest by (distance, index) -- the stable order np.argsort(kind="stable")
- * gives, and what argmin gives for k=1.  idx/dist are [m][k]; rows are padded
- * with -1 / +inf when N < k. */
+ * gives, and what argmin gives for k=1 on NaN-free rows.  numpy sorts NaN distances
+ * last (after +inf), in index order.  idx/dist are [m][k]; rows are padded with
+ * -1 / +inf when N < k. */
 void orc_knn(const double *poses, int64_t N, int d, const double *X, int64_t m,
              int k, int64_t *idx, double *dist) {
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t q = 0; q < m; ++q) {
         int64_t *bi = idx + q * k; double *bd = dist + q * k;
+        int64_t nan_i[64]; int nn = 0;
         int cnt = 0;
         for (int j = 0; j < k; ++j) { bi[j] = -1; bd[j] = INFINITY; }
         for (int64_t i = 0; i < N; ++i) {
             double v = norm_full(poses + i * d, X + q * d, d);
+            if (v != v) { if (nn < k && nn < 64) nan_i[nn++] = i; continue; }
             if (cnt == k && !(v < bd[k - 1])) continue;
             int pos = cnt < k ? cnt : k - 1;
             while (pos > 0 && v < bd[pos - 1]) { bd[pos] = bd[pos - 1]; bi[pos] = bi[pos - 1]; --pos; }
             bd[pos] = v; bi[pos] = i;
             if (cnt < k) ++cnt;
         }
+        for (int j = 0; cnt < k && j < nn; ++j, ++cnt) { bi[cnt] = nan_i[j]; bd[cnt] = NAN; }
     }
 }
 

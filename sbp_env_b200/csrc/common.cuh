@@ -36,6 +36,10 @@ void sbp_set_error(const char *fmt, ...);
     } while (0)
 
 // ------------------------------------------------------------- handles -----
+// scratch slots: 0,1 kNN partial lists / near work-space; 2-4 staging of the *_host entry points
+// and the fused query; 5,6 cell grid and seeds; 7 append / read staging; 8,9 kNN filter lists;
+// 10,11 spare
+#define SBP_SCRATCH_SLOTS 12
 struct sbp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -44,8 +48,8 @@ struct sbp_ctx {
     int max_smem_optin = 0;
     int64_t launches = 0;
     // growable scratch for the *_host entry points and internal work-spaces
-    void *d_scratch[8] = {};
-    size_t d_scratch_bytes[8] = {};
+    void *d_scratch[SBP_SCRATCH_SLOTS] = {};
+    size_t d_scratch_bytes[SBP_SCRATCH_SLOTS] = {};
     int32_t *d_flags = nullptr;      // 16 x int32
     int32_t *h_flags = nullptr;      // pinned mirror
 };

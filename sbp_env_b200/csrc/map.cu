@@ -60,7 +60,7 @@ extern "C" int32_t sbp_ctx_destroy(sbp_ctx *ctx) {
     if (!ctx) return SBP_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < SBP_SCRATCH_SLOTS; ++i)
         if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);

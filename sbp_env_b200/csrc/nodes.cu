@@ -34,9 +34,14 @@ extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, s
     sbp_nodes *s = new sbp_nodes();
     s->ctx = ctx;
     s->d = d;
-    s->capacity = capacity < 1024 ? 1024 : capacity;
+    // a multiple of 1024 nodes: every per-dimension array stays 16-byte aligned and a tile
+    // tail rounded up to 4 floats stays inside the allocation (bulk copies of k_knn_filter)
+    s->capacity = capacity < 1024 ? 1024 : (capacity + 1023) / 1024 * 1024;
     cudaError_t e = cudaMalloc(&s->d_soa, (size_t)s->capacity * d * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&s->d_soa32, (size_t)s->capacity * d * sizeof(float));
+    // unused fp32 slots read as 3.4e38 (never inside a threshold)
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(s->d_soa32, 0x7f, (size_t)s->capacity * d * sizeof(float), ctx->stream);
     if (e == cudaSuccess) e = cudaMalloc(&s->d_maxabs, sizeof(double));
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_maxabs, 0, sizeof(double), ctx->stream);
     if (e != cudaSuccess) {
@@ -103,6 +108,7 @@ static int32_t nodes_grow(sbp_nodes *s, int64_t need) {
     float *nw32 = nullptr;
     SBP_CUDA(cudaMalloc(&nw, (size_t)cap * s->d * sizeof(double)));
     SBP_CUDA(cudaMalloc(&nw32, (size_t)cap * s->d * sizeof(float)));
+    SBP_CUDA(cudaMemsetAsync(nw32, 0x7f, (size_t)cap * s->d * sizeof(float), s->ctx->stream));
     for (int j = 0; j < s->d; ++j) {
         SBP_CUDA(cudaMemcpyAsync(nw + (int64_t)j * cap, s->d_soa + (int64_t)j * s->capacity,
                                  (size_t)s->n * sizeof(double), cudaMemcpyDeviceToDevice,
@@ -255,6 +261,30 @@ struct TopK {
     }
 };
 
+// numpy sorts NaN distances last, in index order (np.argsort, stable): a row the scan could
+// not fill -- fewer than k nodes at a non-NaN distance, e.g. a NaN query -- is completed
+// with the lowest-index nodes whose distance to the query is NaN (distance reported as NaN).
+// A difference is NaN iff one side is NaN or both are the same infinity; squares and sums of
+// non-NaN terms never produce NaN.  Called by the thread that wrote the row; rare path.
+__device__ __noinline__ void pad_nan_row(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                                         int d, const double *__restrict__ xq, int k,
+                                         int64_t *irow, double *drow) {
+    int cnt = 0;
+    while (cnt < k && irow[cnt] >= 0) ++cnt;
+    for (int64_t i = 0; i < n && cnt < k; ++i) {
+        bool isnan_d = false;
+        for (int j = 0; j < d; ++j) {
+            const double df = soa[(int64_t)j * capacity + i] - xq[j];
+            isnan_d |= df != df;
+        }
+        if (isnan_d) {
+            irow[cnt] = i;
+            if (drow) drow[cnt] = __longlong_as_double(0x7ff8000000000000LL);
+            ++cnt;
+        }
+    }
+}
+
 // ---------------------------------------------- K4a: batched, thread/query ---
 // grid = (ceil(m / TPB), S).  CTA (bx, s) scans node chunk s for its TPB queries; node
 // tiles are staged in shared memory (SoA) and read by broadcast.
@@ -286,7 +316,10 @@ __global__ void __launch_bounds__(TPB)
 k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
               const double *__restrict__ maxabs, int prefilter, int64_t capacity, int64_t n, int S,
               const double *__restrict__ X, int64_t m, const double *__restrict__ seed2,
-              double *__restrict__ pd, int32_t *__restrict__ pi) {
+              double *__restrict__ pd, int32_t *__restrict__ pi,
+              const uint8_t *__restrict__ redo) {
+    // as the fallback of the filter path: only the flagged blocks of 32 queries (TPB == 32)
+    if (redo && !redo[blockIdx.x]) return;
     constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
     __shared__ double tile[D][TILE];  // fp64 tile, or the fp32 tile in the same storage
     float(*tile32)[TILE] = reinterpret_cast<float(*)[TILE]>(&tile[0][0]);
@@ -400,6 +433,204 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
     }
 }
 
+// --------------------------------------- K4a': seeded filter + exact refine ---
+// When every query already has an a-priori bound (seed2, the grid seeds below), the top-K
+// state is not needed during the scan at all: the scan only has to FIND the few nodes inside
+// the bound.  k_knn_filter streams the fp32 shadow through shared memory (TMA bulk copies,
+// double buffered, one mbarrier per stage) and evaluates 8 nodes per step with the packed
+// fp32x2 pipe (FADD2 / FMUL2 / FFMA2) and three-input minima (FMNMX3): 3.25 issued
+// instructions per (query, node) pair for d = 2 instead of ~10.  A group of 8 nodes whose
+// minimum fp32 d2 passes the query's CONSERVATIVE threshold (same bound as above: it can
+// only add false positives) is appended to that query's candidate list; k_knn_refine then
+// decides the candidates exactly in fp64 with the same TopK::offer as the one-kernel scan,
+// visiting them in node-index order.  Queries without a usable bound, or whose list
+// overflows, are flagged per block of 32 queries and recomputed by k_knn_batched.
+// nodes per stage: 2 stages x D x tile x 4 B of static shared memory (<= 32 KB)
+__host__ __device__ constexpr int filter_tile(int D) { return D <= 4 ? 1024 : 512; }
+#define FILTER_STAGES 2
+
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float f_min3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    return ok != 0;
+}
+
+template <int D, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_knn_filter(const float *__restrict__ soa32, const double *__restrict__ maxabs, int64_t capacity,
+             int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
+             const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
+             int32_t *__restrict__ ccount) {
+    constexpr int TILE = filter_tile(D), STAGES = FILTER_STAGES;
+    __shared__ __align__(128) float tile[STAGES][D][TILE];
+    __shared__ __align__(8) uint64_t full[STAGES];
+    const int64_t q = (int64_t)blockIdx.x * (NW * 32) + threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t c0 = (int64_t)s * chunk;                       // multiple of TILE
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    const int T = c1 > c0 ? (int)((c1 - c0 + TILE - 1) / TILE) : 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // one thread feeds the stages: D bulk copies of <= 4 KB per tile (sizes are multiples of
+    // 16 B; the capacity is a multiple of 1024 nodes, so a rounded-up tail stays in bounds)
+    auto issue = [&](int it) {
+        const int st = it % STAGES;
+        const int64_t t0 = c0 + (int64_t)it * TILE;
+        const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
+        const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;
+        mbar_expect_tx(&full[st], bytes * D);
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            bulk_g2s(&tile[st][j][0], soa32 + (int64_t)j * capacity + t0, bytes, &full[st]);
+    };
+    if (threadIdx.x == 0)
+        for (int it = 0; it < T && it < STAGES; ++it) issue(it);
+
+    // per-query threshold (see knn_thr32): conservative for every pair within seed2
+    float nq[D];
+    double qmax = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double v = q < m ? X[q * D + j] : 0.0;
+        nq[j] = -(float)v;
+        const double av = v != v ? INFINITY : fabs(v);
+        qmax = av > qmax ? av : qmax;
+    }
+    const double M = *maxabs;
+    const double mm = M > qmax ? M : qmax;
+    const double sd = q < m ? seed2[q] : -1.0;
+    const double a_err = 4.0 * mm * 5.9604644775390625e-8 * sqrt((double)D) * (1.0 + 1e-6);
+    const bool usable = q < m && mm < 1e15 && sd < INFINITY;       // false for NaN seeds too
+    const float thr_f = usable ? knn_thr32(sd, a_err) : -1.0f;     // d2f >= 0 (or NaN) never passes -1
+    const int64_t cbase = (q * S + s) * (int64_t)C;
+    int cc = (q < m && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
+
+    for (int it = 0; it < T; ++it) {
+        const int st = it % STAGES;
+        const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
+        while (!mbar_try_wait(&full[st], phase)) {}
+        const int64_t t0 = c0 + (int64_t)it * TILE;
+        const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
+        const int groups = (cnt + 7) >> 3;
+        const int32_t g0 = (int32_t)(t0 >> 3);
+#pragma unroll 4
+        for (int g = 0; g < groups; ++g) {
+            uint64_t acc[4];
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
+                const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
+                const uint64_t nq2 = f2_pack(nq[j], nq[j]);
+                const uint64_t d0 = f2_add(f2_pack(a.x, a.y), nq2), d1 = f2_add(f2_pack(a.z, a.w), nq2);
+                const uint64_t d2 = f2_add(f2_pack(b.x, b.y), nq2), d3 = f2_add(f2_pack(b.z, b.w), nq2);
+                acc[0] = j == 0 ? f2_mul(d0, d0) : f2_fma(d0, d0, acc[0]);
+                acc[1] = j == 0 ? f2_mul(d1, d1) : f2_fma(d1, d1, acc[1]);
+                acc[2] = j == 0 ? f2_mul(d2, d2) : f2_fma(d2, d2, acc[2]);
+                acc[3] = j == 0 ? f2_mul(d3, d3) : f2_fma(d3, d3, acc[3]);
+            }
+            float v[8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) f2_unpack(acc[t], v[2 * t], v[2 * t + 1]);
+            float mn = f_min3(v[0], v[1], v[2]);
+            mn = f_min3(mn, v[3], v[4]);
+            mn = f_min3(mn, v[5], v[6]);
+            mn = fminf(mn, v[7]);
+            if (mn <= thr_f) {
+                if (cc < C) cand[cbase + cc] = g0 + g;
+                ++cc;
+            }
+        }
+        __syncthreads();                                         // every warp is done with stage st
+        if (threadIdx.x == 0 && it + STAGES < T) issue(it + STAGES);
+    }
+    if (q < m) ccount[q * S + s] = cc;
+}
+
+// One thread per query: exact fp64 decision of the candidate groups, chunks and groups in
+// ascending node order (ties keep the lower index).  A query that cannot be answered from
+// its lists flags its block of 32 queries for the one-kernel scan.
+template <int D, int K>
+__global__ void __launch_bounds__(128)
+k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
+             const double *__restrict__ X, int64_t m, const double *__restrict__ seed2, int S,
+             int C, const int32_t *__restrict__ cand, const int32_t *__restrict__ ccount, int k,
+             int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    bool over = false;
+    for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
+    if (over) { redo[q >> 5] = 1; return; }
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
+    TopK<K> top;
+    top.init(seed2[q]);
+    for (int s = 0; s < S; ++s) {
+        const int c = ccount[q * S + s];
+        const int32_t *cl = cand + (q * S + s) * (int64_t)C;
+        for (int t = 0; t < c; ++t) {
+            const int64_t b = (int64_t)cl[t] * 8;
+#pragma unroll 1
+            for (int u = 0; u < 8; ++u) {
+                const int64_t id = b + u;
+                if (id >= n) break;
+                double pv[D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + id];
+                top.offer(dist2_full<D>(pv, qv), (int32_t)id);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < K; ++t)
+        if (t < k) {
+            idx[q * k + t] = top.i[t];
+            if (dist) dist[q * k + t] = top.i[t] >= 0 ? top.d[t] : INFINITY;
+        }
+    if (top.i[k - 1 < K ? k - 1 : K - 1] < 0)
+        pad_nan_row(soa, capacity, n, D, X + q * D, k, idx + q * k, dist ? dist + q * k : nullptr);
+}
+
 // ------------------------------------------------- K4b: wide, CTA/(q,chunk) ---
 // For few queries over many nodes (RRT nearest / argsort[:20]): threads stride
 // the chunk with coalesced SoA loads, then the CTA merges its per-thread lists by
@@ -493,8 +724,14 @@ k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
                 if (mask & (1u << u)) top.offer(d2[u], (int32_t)(t0 + (int64_t)u * WIDE_TPB));
         }
     }
-    if (S == 1) block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
-    else block_merge_topk<K>(top, pd + (q * S + s) * K, pi + (q * S + s) * K, nullptr, nullptr, 0);
+    if (S == 1) {
+        block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
+        if (threadIdx.x == 0 && idx[q * k_out + k_out - 1] < 0)
+            pad_nan_row(soa, capacity, n, D, X + q * D, k_out, idx + q * k_out,
+                        dist ? dist + q * k_out : nullptr);
+    } else {
+        block_merge_topk<K>(top, pd + (q * S + s) * K, pi + (q * S + s) * K, nullptr, nullptr, 0);
+    }
 }
 
 // Second level of the wide path: one CTA per query merges its S partial lists
@@ -503,7 +740,9 @@ k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
 template <int K>
 __global__ void __launch_bounds__(WIDE_TPB)
 k_knn_merge_wide(const double *__restrict__ pd, const int32_t *__restrict__ pi, int S, int k_out,
-                 int64_t *__restrict__ idx, double *__restrict__ dist) {
+                 int64_t *__restrict__ idx, double *__restrict__ dist,
+                 const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
+                 const double *__restrict__ X) {
     const int64_t q = blockIdx.x;
     TopK<K> top;
     top.init();
@@ -515,16 +754,17 @@ k_knn_merge_wide(const double *__restrict__ pd, const int32_t *__restrict__ pi, 
             if (i0[t] >= 0) top.offer_sorted(d0[t], i0[t]);
     }
     block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
+    if (threadIdx.x == 0 && idx[q * k_out + k_out - 1] < 0)
+        pad_nan_row(soa, capacity, n, d, X + q * d, k_out, idx + q * k_out,
+                    dist ? dist + q * k_out : nullptr);
 }
 
 // ----------------------------------------------------- K4c: chunk merge ------
 // One thread per query merges S sorted partial lists (chunk s holds indices below
 // chunk s+1, so on equal d the lower chunk wins) into the final [m][k] rows.
-__global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__restrict__ pi, int64_t m,
-                            int S, int K, int k, int64_t *__restrict__ idx,
-                            double *__restrict__ dist) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
+__device__ __forceinline__ void knn_merge_row(const double *__restrict__ pd, const int32_t *__restrict__ pi,
+                                              int64_t q, int S, int K, int k, int64_t *__restrict__ idx,
+                                              double *__restrict__ dist) {
     const double *d0 = pd + q * S * K;
     const int32_t *i0 = pi + q * S * K;
     if (S == 1) {
@@ -587,6 +827,19 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
             head[best]++;
         }
     }
+}
+
+__global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__restrict__ pi, int64_t m,
+                            int S, int K, int k, int64_t *__restrict__ idx,
+                            double *__restrict__ dist, const uint8_t *__restrict__ redo,
+                            const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
+                            const double *__restrict__ X) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    if (redo && !redo[q >> 5]) return;
+    knn_merge_row(pd, pi, q, S, K, k, idx, dist);
+    if (idx[q * k + k - 1] < 0)
+        pad_nan_row(soa, capacity, n, d, X + q * d, k, idx + q * k, dist ? dist + q * k : nullptr);
 }
 
 // ---------------------------------------------------- kNN seeding (d = 2) ----
@@ -652,7 +905,8 @@ __device__ __forceinline__ int cell_of(double v, double mn, double mx, int G) {
     double w = mx - mn;
     if (!(w > 0.0)) return 0;
     double c = floor((v - mn) * ((double)G / w));
-    return c < 0.0 ? 0 : c > (double)(G - 1) ? G - 1 : (int)c;      // NaN -> 0
+    if (!(c >= 0.0)) return 0;                                      // negative or NaN
+    return c > (double)(G - 1) ? G - 1 : (int)c;
 }
 
 __global__ void k_cell_hist(const double *__restrict__ soa, int64_t capacity, int64_t n,
@@ -797,6 +1051,7 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
                     const int32_t t = ids[e];
                     const double pv[2] = {soa[t], soa[capacity + t]};
                     v = dist2_full<2>(pv, qv);
+                    v = v != v ? INFINITY : v;          // a NaN node is never a neighbour
                 }
                 // rank among the 32 held values (ties by lane); rank K-1 is the K-th smallest
                 int rank = 0;
@@ -820,6 +1075,8 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
 int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
 int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
 int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
+int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
+int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -864,7 +1121,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         SBP_CUDA(cudaGetLastError());
         if (S > 1) {
             k_knn_merge_wide<K><<<(unsigned)m, WIDE_TPB, 0, ctx->stream>>>(
-                (const double *)pd, (const int32_t *)pi, S, k, idx, dist);
+                (const double *)pd, (const int32_t *)pi, S, k, idx, dist, s->d_soa, s->capacity, n, D, X);
             ctx->launches++;
             SBP_CUDA(cudaGetLastError());
         }
@@ -903,21 +1160,60 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         SBP_CUDA(cudaGetLastError());
         seed = (const double *)seedbuf;
     }
+    const uint8_t *redo = nullptr;
+    if (seed && g_knn_filter) {
+        // seeded filter + exact refine; the one-kernel scan below then only redoes the
+        // blocks of 32 queries the refine step flagged (normally none)
+        constexpr int NW = 4;
+        const int64_t qblocks = (m + NW * 32 - 1) / (NW * 32);
+        constexpr int FT = filter_tile(D);
+        const int64_t tiles = (n + FT - 1) / FT;
+        int64_t FS = g_knn_filter_chunks > 0 ? g_knn_filter_chunks
+                                             : (16 * (int64_t)ctx->sm_count + qblocks - 1) / qblocks;
+        if (FS > tiles) FS = tiles;
+        if (FS > 64) FS = 64;
+        if (FS < 1) FS = 1;
+        const int64_t chunk = (tiles + FS - 1) / FS * FT;
+        FS = (n + chunk - 1) / chunk;
+        int C = 4 * K / (int)FS + 12;
+        void *cbuf = nullptr, *nbuf = nullptr;
+        rc = sbp_ctx_scratch(ctx, 8, (size_t)m * FS * C * sizeof(int32_t), &cbuf);
+        if (rc) return rc;
+        const size_t nflags = (size_t)((m + 31) / 32);
+        rc = sbp_ctx_scratch(ctx, 9, (size_t)m * FS * sizeof(int32_t) + nflags, &nbuf);
+        if (rc) return rc;
+        int32_t *ccount = (int32_t *)nbuf;
+        uint8_t *flags = (uint8_t *)nbuf + (size_t)m * FS * sizeof(int32_t);
+        SBP_CUDA(cudaMemsetAsync(flags, 0, nflags, ctx->stream));
+        dim3 fgrid((unsigned)qblocks, (unsigned)FS);
+        k_knn_filter<D, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
+            s->d_soa32, s->d_maxabs, s->capacity, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf,
+            ccount);
+        k_knn_refine<D, K><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
+            s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
+            dist, flags);
+        ctx->launches += 2;
+        SBP_CUDA(cudaGetLastError());
+        redo = flags;
+        tpb = 32;
+    }
     if (tpb == 32) {
         dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
         k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
                                                               g_knn_prefilter, s->capacity, n, S, X,
-                                                              m, seed, (double *)pd, (int32_t *)pi);
+                                                              m, seed, (double *)pd, (int32_t *)pi,
+                                                              redo);
     } else {
         dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
         k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
                                                                 g_knn_prefilter, s->capacity, n, S,
-                                                                X, m, seed, (double *)pd, (int32_t *)pi);
+                                                                X, m, seed, (double *)pd, (int32_t *)pi,
+                                                                nullptr);
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     k_knn_merge<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
-        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist);
+        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist, redo, s->d_soa, s->capacity, n, D, X);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;

@@ -283,3 +283,48 @@ def test_knn_grid_seed_never_changes_results(sg, layout):
                     assert np.array_equal(idx, ei) and np.array_equal(dist, ed), (layout, seed, kk)
     finally:
         lib.sbp_tune(b"knn_seed", 1)
+
+
+@pytest.mark.parametrize("layout", ["uniform", "duplicates", "clustered", "nan_inf"])
+@pytest.mark.parametrize("n", [2048, 2055, 20001, 66000])
+def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
+    """Seeded filter (packed fp32 scan of 8-node groups, candidate lists) + exact fp64 refine:
+    identical to the oracle and to the one-kernel scan for every chunking, for node counts
+    that are not multiples of the group / tile size, for layouts whose candidate lists
+    overflow (duplicates: the flagged blocks are redone by the one-kernel scan) and for
+    queries / nodes with non-finite coordinates."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(n + len(layout))
+    m, k = 1300, 11
+    if layout == "duplicates":
+        poses = np.floor(rng.random((n, 2)) * 9) * 64.0              # 81 distinct positions
+    elif layout == "clustered":
+        c = rng.random((30, 2)) * 600
+        poses = c[rng.integers(0, 30, n)] + rng.standard_normal((n, 2)) * 0.25
+    else:
+        poses = rng.random((n, 2)) * 600
+    X = np.concatenate([poses[rng.integers(0, n, m // 2)] + rng.standard_normal((m // 2, 2)) * 0.3,
+                        rng.random((m - m // 2, 2)) * 900 - 150])
+    if layout == "nan_inf":
+        poses[5] = [np.nan, 3.0]
+        poses[77] = [np.inf, 10.0]
+        poses[n - 1] = [250.0, -np.inf]
+        X[3] = [np.nan, np.nan]
+        X[40] = [np.inf, 0.0]
+        X[41] = [100.0, np.nan]
+    t = sg.NodeStore(2)
+    t.extend(poses)
+    lib = _lib.load()
+    try:
+        for kk in (k, 1, 20, 32):
+            ei, ed = orc.knn(poses, X, kk)
+            for filt, chunks in ((1, 0), (1, 1), (1, 7), (0, 0)):
+                lib.sbp_tune(b"knn_filter", filt)
+                lib.sbp_tune(b"knn_filter_chunks", chunks)
+                idx, dist = t.knn(X, kk)
+                assert np.array_equal(idx, ei), (layout, n, kk, filt, chunks)
+                assert np.array_equal(dist, ed, equal_nan=True), (layout, n, kk, filt, chunks)
+    finally:
+        lib.sbp_tune(b"knn_filter", 1)
+        lib.sbp_tune(b"knn_filter_chunks", 0)

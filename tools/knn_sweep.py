@@ -1,19 +1,40 @@
-import sys; sys.path.insert(0,"."); sys.path.insert(0,"tests")
-import torch, numpy as np, sbp_env_b200 as sg
-from sbp_env_b200 import _lib
-lib=_lib.load()
-g=torch.Generator(device="cuda"); g.manual_seed(0)
-n=50000
-tree=sg.NodeStore(2,capacity=n); tree.extend(torch.rand((n,2),generator=g,device="cuda",dtype=torch.float64)*580)
-X=tree.rows_device(0,n)
-def t(reps=10):
-    tree.knn(X,11,return_dist=False); torch.cuda.synchronize()
-    a,b=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+"""Sweep of the kNN tuning knobs on cfg2 (50k x 50k, k=11) -- run under gpurun."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import sbp_env_b200 as sg  # noqa: E402
+from sbp_env_b200 import _lib  # noqa: E402
+
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev)
+g.manual_seed(0)
+lib = _lib.load()
+
+
+def timeit(fn, reps=10):
+    fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for _ in range(reps): tree.knn(X,11,return_dist=False)
-    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b)/reps
-for S in (0,1,2,3,4):
-    lib.sbp_tune(b"knn_chunks",S); print("chunks",S,"ms",t())
-lib.sbp_tune(b"knn_chunks",0)
-for seed,pf in ((1,1),(0,1),(1,0),(0,0)):
-    lib.sbp_tune(b"knn_seed",seed); lib.sbp_tune(b"knn_prefilter",pf); print("seed",seed,"prefilter",pf,"ms",t())
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+for n, m in ((50_000, 50_000), (1_000_000, 100_000), (5000, 5000)):
+    scale = torch.tensor([579.0, 581.0], device=dev, dtype=torch.float64)
+    tree = sg.NodeStore(2, capacity=n)
+    tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * scale)
+    X = tree.rows_device(0, m)
+    for filt, chunks in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 6), (1, 8), (1, 12), (1, 16), (1, 24)):
+        lib.sbp_tune(b"knn_filter", filt)
+        lib.sbp_tune(b"knn_filter_chunks", chunks)
+        ms = timeit(lambda: tree.knn(X, 11, return_dist=False))
+        print(f"n={n} m={m} filter={filt} chunks={chunks}: {ms:.4f} ms  {n * m / ms * 1e3:.3e} evals/s", flush=True)
