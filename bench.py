@@ -38,6 +38,9 @@ K_NN = 10
 MAP = "intel_lab"
 METRIC = "edge collision checks/sec (PRM candidate edges: brute-force kNN connect + visible_batch)"
 UNIT = "edges/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_filter launch on this workload
+# (ncu --set full, profiles/r1_knn_filter_full.txt)
+FILTER_DRAM_TRAFFIC = 18246400
 WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
             "candidate edges per step (kNN 2.5e9 fp64 distance evals + Bresenham visible_batch)")
 
@@ -162,15 +165,7 @@ def run_ours(args):
 
     names = ("knn", "edges", "visible", "gather")
 
-    def step(ev=None):
-        idx = [0]
-
-        def mark(_name):
-            if ev is not None:
-                ev[idx[0]].record()
-                idx[0] += 1
-
-        nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
+    def gather(nbr, vis):
         if world > 1:
             nb_all = torch.empty((world * m, k), dtype=torch.int64, device=dev)
             vs_all = torch.empty((world * m, k), dtype=torch.uint8, device=dev)
@@ -179,7 +174,28 @@ def run_ours(args):
             gathered["nbr"], gathered["vis"] = nb_all, vs_all
         else:
             gathered["nbr"], gathered["vis"] = nbr, vis
+
+    def eager_step(ev=None):
+        idx = [0]
+
+        def mark(_name):
+            if ev is not None:
+                ev[idx[0]].record()
+                idx[0] += 1
+
+        nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
+        gather(nbr, vis)
         mark("gather")
+        return nbr, vis
+
+    # The step is ~20 short kernels; issued one by one from Python the host cannot keep up
+    # with the GPU, so the timed loop replays the step from a CUDA graph (the library's
+    # PRMConnectGraph); the all-gather (N > 1) follows the replay on the same stream.
+    gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
+
+    def step():
+        nbr, vis = gstep.replay()
+        gather(nbr, vis)
         return nbr, vis
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -187,7 +203,6 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
-    launches0 = ctx.launches
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -199,17 +214,15 @@ def run_ours(args):
     t_wall0 = time.time()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in names] for _ in range(args.steps)]
     for s in range(args.steps):
         flush.zero_()                      # evict L2 between timed iterations (not timed)
         starts[s].record()
-        step(phase_ev[s])
+        step()
         ends[s].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    launches = ctx.launches - launches0
     step_ms = np.array([starts[s].elapsed_time(ends[s]) for s in range(args.steps)])
     total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
     if world > 1:
@@ -217,15 +230,44 @@ def run_ours(args):
     total_ms = float(total_ms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
+    # ---- phase breakdown and the dominant kernel's duration: the same step launched eagerly.
+    # A spin kernel ahead of each step lets the host run ahead, so that the events measure
+    # the GPU and not the Python launch path; sbp_tune("time_kernels") brackets k_knn_filter
+    # with its own CUDA events on the launching stream.
+    import ctypes as C
+
+    lib = _lib.load()
+    psteps = min(args.steps, 10)
+    for _ in range(2):
+        eager_step()
+    torch.cuda.synchronize()
+    launches0 = ctx.launches
+    lib.sbp_tune(b"time_kernels", 1)
+    p_start = [torch.cuda.Event(enable_timing=True) for _ in range(psteps)]
+    phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in names] for _ in range(psteps)]
+    for s in range(psteps):
+        flush.zero_()
+        torch.cuda._sleep(4_000_000)       # ~2 ms head start for the host
+        p_start[s].record()
+        eager_step(phase_ev[s])
+    torch.cuda.synchronize()
+    lib.sbp_tune(b"time_kernels", 0)
+    kt_ms, kt_n = C.c_double(), C.c_int64()
+    _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
+    filter_ms = kt_ms.value / max(1, kt_n.value)
+    launches_per_step = (ctx.launches - launches0) // psteps
+    launches = launches_per_step * args.steps
     ph = {}
     for i, nme in enumerate(names):
-        prev = [starts[s] if i == 0 else phase_ev[s][i - 1] for s in range(args.steps)]
-        ph[nme] = float(np.mean([prev[s].elapsed_time(phase_ev[s][i]) for s in range(args.steps)]))
+        prev = [p_start[s] if i == 0 else phase_ev[s][i - 1] for s in range(psteps)]
+        ph[nme] = float(np.mean([prev[s].elapsed_time(phase_ev[s][i]) for s in range(psteps)]))
 
     # parity spot check of the timed configuration (outside the timed region)
     nbr, vis = step()
     torch.cuda.synchronize()
     n_vis = int(vis.sum().item())
+    nbr_e, vis_e = eager_step()
+    assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e), "graph replay differs from the eager step"
 
     # ---- end to end through the public API with host buffers -------------------
     pinned = torch.from_numpy(batch_host).pin_memory()
@@ -233,16 +275,25 @@ def run_ours(args):
     vis_h = torch.empty((m, k), dtype=torch.bool).pin_memory()
     tree2 = sg.NodeStore(2, capacity=N_NODES, device=local) if rank == 0 else None
 
-    def e2e_step():
-        x = pinned.to(dev, non_blocking=True)              # H2D of this step's samples
+    x_dev = torch.empty((m, 2), dtype=torch.float64, device=dev)
+
+    def e2e_body():
+        x_dev.copy_(pinned, non_blocking=True)             # H2D of this step's samples
         if rank == 0:
             tree2.truncate(0)
-            tree2.extend(x)                                # roadmap rebuilt from the samples
+            tree2.extend(x_dev)                            # roadmap rebuilt from the samples
             nb, vs = sg.prm_connect_knn(cc, tree2, k)
         else:
-            nb, vs = sg.prm_connect_knn(cc, tree, k, queries=x)
+            nb, vs = sg.prm_connect_knn(cc, tree, k, queries=x_dev)
         nbr_h.copy_(nb, non_blocking=True)                 # D2H of the adjacency block
         vis_h.copy_(vs, non_blocking=True)
+
+    # the user-facing call: the whole host-to-host step captured once (CapturedStep) and
+    # replayed; H2D, store rebuild, connection and D2H all run inside every replay
+    e2e_graph = sg.CapturedStep(e2e_body, device=local)
+
+    def e2e_step():
+        e2e_graph.replay()
 
     for _ in range(max(3, args.warmup)):
         e2e_step()
@@ -278,19 +329,22 @@ def run_ours(args):
 
     evals = float(m) * float(len(tree))
     knn_s = ph["knn"] / 1e3
-    q_tile = 32                                       # queries sharing one streamed node tile (one warp)
-    alg_bytes = evals * 8 * 2 / q_tile + m * 16 + m * (k + 1) * 8     # node stream + queries + idx out
+    filt_s = filter_ms / 1e3
+    # Dominant kernel: k_knn_filter (the brute-force scan of all m x n pairs).  ALGORITHMIC
+    # bytes per launch (8 d / Q_tile per distance evaluation when Q_tile
+    # queries share a streamed node; the scan streams the fp32 shadow, 4 (d + 1) bytes per
+    # node, to CTAs of Q_tile = 256 queries) + the query rows + the candidate lists.
+    q_tile = 256
+    alg_bytes = evals * 4 * 3 / q_tile + m * 16 + m * 8 + m * 24 * 4
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
-    # workload, from the ncu --set full capture summarised in profiles/r1_knn_batched_full.txt
-    roof = {"kernel": "k_knn_batched<2,11,32> (+ seed pipeline, k_knn_merge): the 'knn' phase, 95% of the step",
-            "bound": "hbm", "achieved": alg_bytes / knn_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / knn_s / 1e9 / hbm_peak, "traffic": 8691712, "peak_source": peak_src,
-            "note": "brute-force kNN with 32 queries sharing each streamed node is instruction-issue "
-                    "bound, not HBM bound (8.7 MB of DRAM traffic per launch): see alu"}
-
-    import ctypes as C
-
-    lib = _lib.load()
+    # workload, from the ncu --set full capture summarised in profiles/r1_knn_filter_full.txt
+    roof = {"kernel": "k_knn_filter<2> (brute-force scan of the kNN phase: all 2.5e9 pairs; "
+                      f"{100 * filter_ms / sum(ph.values()):.0f}% of the step)",
+            "bound": "hbm", "achieved": alg_bytes / filt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / filt_s / 1e9 / hbm_peak, "traffic": FILTER_DRAM_TRAFFIC,
+            "peak_source": peak_src, "kernel_ms": filter_ms, "kernel_launches_timed": int(kt_n.value),
+            "note": "the scan shares every streamed node among 256 queries, so it is bound by the "
+                    "FMA pipe, not by HBM: see fma_pipe"}
 
     def mb(which, nbytes, iters):
         ms, units = C.c_double(), C.c_double()
@@ -298,20 +352,20 @@ def run_ours(args):
         return units.value / (ms.value / 1e3)
 
     fp64_peak = mb(2, 0, 4096)
-    # The scan runs the conservative fp32 prefilter: 7 issued instructions per (query, node)
-    # pair and warp (2 FADD, FMUL, FFMA, FSETP, SEL, 1/2 IADD3, 1/2 LDS.128; SASS of
-    # k_knn_batched) against 4 schedulers x 1 instruction/clk per SM; only flagged pairs reach
-    # the exact fp64 path.  The pure-fp64 scan it replaced needs 6 unfused fp64 ops per pair
-    # (kept for comparison against the measured fp64 rate).
+    # FMA-pipe model of the scan: d packed FFMA2 per 2 pairs (norm expansion), each occupying
+    # the fp32 pipe of its SM sub-partition for 2 cycles (64 lanes-FMAs on a 32-lane pipe), i.e.
+    # d pipe-cycles per warp-pair; peak = 4 sub-partitions x SM count x clock.
     sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-    issue_peak = ctx.info()["sm_count"] * 4 * sm_hz * 1e6
-    roof["alu"] = {"model": "fp32 prefilter scan, 7 issued warp-instructions per 32 pairs",
-                   "achieved_warp_instr_per_s": evals / 32 * 7 / knn_s,
-                   "peak_issue_warp_instr_per_s": issue_peak,
-                   "frac": evals / 32 * 7 / knn_s / issue_peak,
-                   "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / knn_s,
-                                       "measured_peak_unfused_fp64_ops_per_s": fp64_peak,
-                                       "ratio": evals * 6 / knn_s / fp64_peak}}
+    pipe_peak = ctx.info()["sm_count"] * 4 * sm_hz * 1e6
+    roof["fma_pipe"] = {"model": "d = 2 FMA-pipe cycles per warp of 32 (query, node) pairs "
+                                 "(1 packed FFMA2 per pair, 2 cycles each)",
+                        "achieved_pipe_cycles_per_s": evals / 32 * 2 / filt_s,
+                        "peak_pipe_cycles_per_s": pipe_peak,
+                        "frac": evals / 32 * 2 / filt_s / pipe_peak,
+                        "dist_evals_per_s_kernel": evals / filt_s,
+                        "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / knn_s,
+                                            "measured_peak_unfused_fp64_ops_per_s": fp64_peak,
+                                            "ratio": evals * 6 / knn_s / fp64_peak}}
 
     # ---- micro: uniform random edge batches on the same map ------
     micro = None
@@ -392,6 +446,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "map": "intel_lab 579x581 (occupancy fixture tests/golden/maps.npz)",
                    "nodes": N_NODES, "k": K_NN, "edges_per_step_per_gpu": edges_per_rank,
                    "dist_evals_per_step_per_gpu": evals, "l2": "flushed (256 MiB write) between timed steps",
+                   "launch": "the step (and the e2e step) is replayed from a CUDA graph captured by the "
+                             "library (PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms "
+                             "come from the same step launched eagerly",
                    "multi_gpu": "rank r connects batch r of 50000 samples to the replicated roadmap; "
                                 "NCCL all-gather of the neighbour/visibility blocks inside the step"},
         "clocks": clocks,
@@ -400,6 +457,7 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
                 "d2h_bytes_per_step": int(nbr_h.numel() * 8 + vis_h.numel())},
         "gpu_launches": int(launches),
+        "gpu_launches_per_step": int(launches_per_step),
         "roofline": roof,
         "cpu_baseline": cpu,
         "phases_ms": ph,

@@ -9,8 +9,8 @@ from .collision_checker import (CollisionChecker, ImgCollisionChecker,  # noqa: 
                                 RobotArm4dCollisionChecker, bresenham_pixels)
 from .engine import Engine, ImageEngine, RobotArmEngine, euclidean_dist  # noqa: F401
 from .node_store import NodeStore  # noqa: F401
-from .planning import (feasible_batch, knn, near, prm_connect_knn,  # noqa: F401
-                       prm_connect_radius, roadmap_edges_to_host, visible_batch)
+from .planning import (CapturedStep, PRMConnectGraph, feasible_batch, knn, near,  # noqa: F401
+                       prm_connect_knn, prm_connect_radius, roadmap_edges_to_host, visible_batch)
 from . import distributed, planner_ops  # noqa: F401
 from .stats import Stats  # noqa: F401
 

@@ -71,12 +71,14 @@ _SIGNATURES = {
                                     _i32, C.POINTER(_i32), C.POINTER(_i32)],
     "sbp_tune": [C.c_char_p, _i64],
     "sbp_microbench": [_vp, _i32, _i64, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
+    "sbp_ctx_kernel_time": [_vp, C.POINTER(_dbl), C.POINTER(_i64)],
 }
 _RESTYPE = {"sbp_last_error": C.c_char_p}
 
-#: entry points declared in include/sbp_gpu.h (sbp_tune / sbp_microbench are undeclared
-#: tuning / measurement hooks)
-ABI_SYMBOLS = tuple(k for k in _SIGNATURES if k not in ("sbp_tune", "sbp_microbench"))
+#: entry points declared in include/sbp_gpu.h (sbp_tune / sbp_microbench / sbp_ctx_kernel_time
+#: are undeclared tuning / measurement hooks)
+ABI_SYMBOLS = tuple(k for k in _SIGNATURES
+                    if k not in ("sbp_tune", "sbp_microbench", "sbp_ctx_kernel_time"))
 
 
 def load():

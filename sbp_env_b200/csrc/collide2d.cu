@@ -382,7 +382,28 @@ extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint
 int g_visible_group = 0;   // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
 int g_coop_below = 12;     // adaptive kernel: cap of the hand-over threshold (walkers)
 int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
-extern int g_knn_chunks, g_knn_prefilter, g_knn_seed, g_knn_filter, g_knn_filter_chunks;
+extern int g_knn_chunks, g_knn_prefilter, g_knn_seed, g_knn_filter, g_knn_filter_chunks, g_knn_filter_variant;
+
+int g_time_kernels = 0;    // bench instrumentation: event pairs around the dominant kNN kernel
+
+// Sum and count of the event pairs recorded since the last call (synchronises the stream).
+extern "C" int32_t sbp_ctx_kernel_time(sbp_ctx *ctx, double *total_ms, int64_t *launches) {
+    SBP_REQUIRE(ctx && total_ms && launches, "sbp_ctx_kernel_time: NULL argument");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+    double tot = 0.0;
+    for (auto &pr : ctx->timed) {
+        float ms = 0.f;
+        SBP_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        tot += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *total_ms = tot;
+    *launches = (int64_t)ctx->timed.size();
+    ctx->timed.clear();
+    return SBP_OK;
+}
 
 extern "C" int32_t sbp_tune(const char *key, int64_t value) {
     if (!strcmp(key, "visible_group")) { g_visible_group = (int)value; return SBP_OK; }
@@ -392,6 +413,8 @@ extern "C" int32_t sbp_tune(const char *key, int64_t value) {
     if (!strcmp(key, "knn_seed")) { g_knn_seed = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_filter")) { g_knn_filter = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_filter_chunks")) { g_knn_filter_chunks = (int)value; return SBP_OK; }
+    if (!strcmp(key, "knn_filter_variant")) { g_knn_filter_variant = (int)value; return SBP_OK; }
+    if (!strcmp(key, "time_kernels")) { g_time_kernels = (int)value; return SBP_OK; }
     if (!strcmp(key, "force_global")) { g_force_global = (int)value; return SBP_OK; }
     sbp_set_error("sbp_tune: unknown key %s", key);
     return SBP_ERR_ARG;

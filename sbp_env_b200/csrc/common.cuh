@@ -52,6 +52,26 @@ struct sbp_ctx {
     size_t d_scratch_bytes[SBP_SCRATCH_SLOTS] = {};
     int32_t *d_flags = nullptr;      // 16 x int32
     int32_t *h_flags = nullptr;      // pinned mirror
+    // bench instrumentation (sbp_tune("time_kernels", 1)): CUDA events around the dominant
+    // kernel of the kNN path, read back with sbp_ctx_kernel_time
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+};
+
+extern int g_time_kernels;
+struct KernelTimer {          // RAII: records an event pair on the launching stream
+    sbp_ctx *ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit KernelTimer(sbp_ctx *c) : ctx(g_time_kernels ? c : nullptr) {
+        if (!ctx) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (!ctx) return;
+        cudaEventRecord(b, ctx->stream);
+        ctx->timed.emplace_back(a, b);
+    }
 };
 
 int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out);

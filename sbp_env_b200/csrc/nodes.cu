@@ -436,18 +436,34 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
 // --------------------------------------- K4a': seeded filter + exact refine ---
 // When every query already has an a-priori bound (seed2, the grid seeds below), the top-K
 // state is not needed during the scan at all: the scan only has to FIND the few nodes inside
-// the bound.  k_knn_filter streams the fp32 shadow through shared memory (TMA bulk copies,
-// double buffered, one mbarrier per stage) and evaluates 8 nodes per step with the packed
-// fp32x2 pipe (FADD2 / FMUL2 / FFMA2) and three-input minima (FMNMX3): 3.25 issued
-// instructions per (query, node) pair for d = 2 instead of ~10.  A group of 8 nodes whose
-// minimum fp32 d2 passes the query's CONSERVATIVE threshold (same bound as above: it can
-// only add false positives) is appended to that query's candidate list; k_knn_refine then
-// decides the candidates exactly in fp64 with the same TopK::offer as the one-kernel scan,
-// visiting them in node-index order.  Queries without a usable bound, or whose list
-// overflows, are flagged per block of 32 queries and recomputed by k_knn_batched.
-// nodes per stage: 2 stages x D x tile x 4 B of static shared memory (<= 32 KB)
-__host__ __device__ constexpr int filter_tile(int D) { return D <= 4 ? 1024 : 512; }
+// the bound.  The filter runs on a per-call fp32 shadow of the nodes, centred on the middle c
+// of their bounding box, with the squared norm precomputed (k_shadow_centered):
+//     |n - q|^2 = |n^|^2 - 2 n^.q^ + |q^|^2,      n^ = fl32(n - c), q^ = fl32(q - c)
+// so a pair costs D fused multiply-adds instead of D subtractions + D multiply-adds:
+//     t = fma(n^_D, -2q^_D, ... fma(n^_1, -2q^_1, fl32(|n^|^2)))   vs   thr' = bound - |q^|^2.
+// k_knn_filter streams the shadow through shared memory (TMA bulk copies, double buffered,
+// one mbarrier per stage).  A thread owns FQ = 4 queries and evaluates 8 nodes per step for
+// each of them with the packed fp32x2 pipe (FFMA2) and three-input minima (FMNMX3): every
+// broadcast LDS.128 feeds 16 (query, node) pairs -- the shared-memory pipe moves only 8 bytes
+// per wavefront on a broadcast, which bounded the one-query-per-thread version -- and the
+// kernel is bound by the FMA pipe (1 packed FFMA2 = 2 pipe cycles per pair for d = 2).
+//
+// CONSERVATIVE threshold.  With u = 2^-24, M >= |n_j - c_j|, Mq >= |q_j - c_j|:
+//   * |n^ - q^| <= |n - q| + a,  a = 4 u sqrt(D) max(M, Mq)   (roundings of n^ and q^);
+//   * the D+1 roundings of the fma chain change t by at most
+//     E = u D (D+1) M (M + Mq) (1 + 1e-5) + 1e-15 Mq^2    (partial sums are <= D M^2 + 2 j M Mq);
+// so every pair with exact fp64 d^2 <= bound has t <= thr' := round_up((sqrt(bound) + a)^2 + E
+// - |q^|^2).  The filter can only add false positives, never lose a neighbour.  A query
+// whose band E exceeds (sqrt(bound) + a)^2 (huge extent / tiny neighbour distance, outliers),
+// or that has no finite bound, is not filtered: it is flagged and recomputed by k_knn_batched.
+//
+// A group of 8 nodes whose minimum t passes is appended to the (query, chunk) candidate list;
+// k_knn_refine then decides the candidates exactly in fp64 with the same TopK::offer as the
+// one-kernel scan, visiting them in node-index order.
 #define FILTER_STAGES 2
+#define FILTER_Q 4          // queries per thread
+// nodes per stage: 2 stages x (D + 1) x tile x 4 B of static shared memory (<= 40 KB)
+__host__ __device__ constexpr int filter_tile(int D) { return D <= 4 ? 1024 : 512; }
 
 __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
     uint64_t r;
@@ -456,16 +472,6 @@ __device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
 }
 __device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
-    uint64_t r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
 }
 __device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
     uint64_t r;
@@ -491,16 +497,58 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
     return ok != 0;
 }
 
-template <int D, int NW>
+// Centred fp32 shadow [D + 1][cap32]: coordinates relative to the bounding-box centre and
+// the squared norm of the ROUNDED coordinates (exact products, one rounding).  Slots in
+// [n, cap32) hold the origin with norm 3e38 so that a tile tail never passes a threshold.
+// info[0] = M (max |centred coordinate|, +inf when a bound is not finite), info[1+j] = c_j.
+template <int D>
+__global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                                  const double *__restrict__ bounds /*[D][2] = min, max*/,
+                                  int64_t cap32, float *__restrict__ sh, double *__restrict__ info) {
+    double c[D], M = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double mn = bounds[2 * j], mx = bounds[2 * j + 1];
+        c[j] = 0.5 * mn + 0.5 * mx;
+        const double h = fmax(mx - c[j], c[j] - mn);
+        M = (h != h) ? INFINITY : fmax(M, h);
+        if (!(mn <= mx)) M = INFINITY;                  // empty / NaN bounds
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        info[0] = M * (1.0 + 1e-9);
+#pragma unroll
+        for (int j = 0; j < D; ++j) info[1 + j] = c[j];
+    }
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cap32;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        if (t < n) {
+            double nn = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const float xc = (float)(soa[(int64_t)j * capacity + t] - c[j]);
+                sh[(int64_t)j * cap32 + t] = xc;
+                nn += (double)xc * (double)xc;
+            }
+            sh[(int64_t)D * cap32 + t] = (float)nn;
+        } else {
+            // padding: t = fma(0, ., 3e38) = 3e38 never passes a (finite) threshold
+#pragma unroll
+            for (int j = 0; j < D; ++j) sh[(int64_t)j * cap32 + t] = 0.0f;
+            sh[(int64_t)D * cap32 + t] = 3.0e38f;
+        }
+    }
+}
+
+template <int D, int NW, int UNR>
 __global__ void __launch_bounds__(NW * 32)
-k_knn_filter(const float *__restrict__ soa32, const double *__restrict__ maxabs, int64_t capacity,
+k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
              int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
              const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
              int32_t *__restrict__ ccount) {
-    constexpr int TILE = filter_tile(D), STAGES = FILTER_STAGES;
-    __shared__ __align__(128) float tile[STAGES][D][TILE];
+    constexpr int TILE = filter_tile(D), STAGES = FILTER_STAGES, FQ = FILTER_Q, TPB = NW * 32;
+    __shared__ __align__(128) float tile[STAGES][D + 1][TILE];
     __shared__ __align__(8) uint64_t full[STAGES];
-    const int64_t q = (int64_t)blockIdx.x * (NW * 32) + threadIdx.x;
+    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
     const int s = blockIdx.y;
     const int64_t c0 = (int64_t)s * chunk;                       // multiple of TILE
     const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
@@ -511,39 +559,51 @@ k_knn_filter(const float *__restrict__ soa32, const double *__restrict__ maxabs,
         fence_barrier_init();
     }
     __syncthreads();
-    // one thread feeds the stages: D bulk copies of <= 4 KB per tile (sizes are multiples of
-    // 16 B; the capacity is a multiple of 1024 nodes, so a rounded-up tail stays in bounds)
+    // one thread feeds the stages: D + 1 bulk copies of <= 4 KB per tile (cap32 is a multiple
+    // of the tile, so every copy is a whole number of 16-byte units inside the allocation)
     auto issue = [&](int it) {
         const int st = it % STAGES;
         const int64_t t0 = c0 + (int64_t)it * TILE;
         const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
-        const uint32_t bytes = (uint32_t)((cnt + 3) & ~3) * 4u;
-        mbar_expect_tx(&full[st], bytes * D);
+        const uint32_t bytes = (uint32_t)((cnt + 7) & ~7) * 4u;
+        mbar_expect_tx(&full[st], bytes * (D + 1));
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            bulk_g2s(&tile[st][j][0], soa32 + (int64_t)j * capacity + t0, bytes, &full[st]);
+        for (int j = 0; j <= D; ++j)
+            bulk_g2s(&tile[st][j][0], sh + (int64_t)j * cap32 + t0, bytes, &full[st]);
     };
     if (threadIdx.x == 0)
         for (int it = 0; it < T && it < STAGES; ++it) issue(it);
 
-    // per-query threshold (see knn_thr32): conservative for every pair within seed2
-    float nq[D];
-    double qmax = 0.0;
+    const double M = info[0];
+    float nq2[FQ][D];        // -2 q^_j
+    float thr[FQ];
+    int cc[FQ];
+    int32_t *cl[FQ];         // this (query, chunk)'s candidate list
 #pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const double v = q < m ? X[q * D + j] : 0.0;
-        nq[j] = -(float)v;
-        const double av = v != v ? INFINITY : fabs(v);
-        qmax = av > qmax ? av : qmax;
+    for (int r = 0; r < FQ; ++r) {
+        const int64_t q = qb + (int64_t)r * TPB;
+        double Mq = 0.0, qq = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double v = q < m ? X[q * D + j] - info[1 + j] : 0.0;
+            const float qf = (float)v;
+            nq2[r][j] = -2.0f * qf;
+            qq += (double)qf * (double)qf;
+            const double av = v != v ? INFINITY : fabs(v);
+            Mq = av > Mq ? av : Mq;
+        }
+        const double sd = q < m ? seed2[q] : -1.0;
+        const double mm = M > Mq ? M : Mq;
+        const double a = 4.0 * 5.9604644775390625e-8 * sqrt((double)D) * mm * (1.0 + 1e-6);
+        const double E = 5.9604644775390625e-8 * (double)(D * (D + 1)) * M * (M + Mq) * (1.0 + 1e-5) +
+                         1e-15 * Mq * Mq;
+        const double ra = sqrt(sd) + a;                              // NaN for sd < 0 or NaN
+        const double pos = (ra * ra + E) * (1.0 + 1e-9);
+        const bool usable = q < m && mm < 1e15 && sd < INFINITY && E <= ra * ra;
+        thr[r] = usable ? __double2float_ru(pos - qq) : -INFINITY;   // t (or NaN) never passes -inf
+        cc[r] = (q < m && !usable) ? C + 1 : 0;                      // C + 1 = "not filterable"
+        cl[r] = cand + ((q < m ? q : 0) * S + s) * (int64_t)C;
     }
-    const double M = *maxabs;
-    const double mm = M > qmax ? M : qmax;
-    const double sd = q < m ? seed2[q] : -1.0;
-    const double a_err = 4.0 * mm * 5.9604644775390625e-8 * sqrt((double)D) * (1.0 + 1e-6);
-    const bool usable = q < m && mm < 1e15 && sd < INFINITY;       // false for NaN seeds too
-    const float thr_f = usable ? knn_thr32(sd, a_err) : -1.0f;     // d2f >= 0 (or NaN) never passes -1
-    const int64_t cbase = (q * S + s) * (int64_t)C;
-    int cc = (q < m && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
 
     for (int it = 0; it < T; ++it) {
         const int st = it % STAGES;
@@ -553,81 +613,123 @@ k_knn_filter(const float *__restrict__ soa32, const double *__restrict__ maxabs,
         const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         const int groups = (cnt + 7) >> 3;
         const int32_t g0 = (int32_t)(t0 >> 3);
-#pragma unroll 4
+#pragma unroll UNR
         for (int g = 0; g < groups; ++g) {
-            uint64_t acc[4];
+            uint64_t nd[D + 1][4];           // 8 nodes: packed pairs of every component and the norm
 #pragma unroll
-            for (int j = 0; j < D; ++j) {
+            for (int j = 0; j <= D; ++j) {
                 const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
                 const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
-                const uint64_t nq2 = f2_pack(nq[j], nq[j]);
-                const uint64_t d0 = f2_add(f2_pack(a.x, a.y), nq2), d1 = f2_add(f2_pack(a.z, a.w), nq2);
-                const uint64_t d2 = f2_add(f2_pack(b.x, b.y), nq2), d3 = f2_add(f2_pack(b.z, b.w), nq2);
-                acc[0] = j == 0 ? f2_mul(d0, d0) : f2_fma(d0, d0, acc[0]);
-                acc[1] = j == 0 ? f2_mul(d1, d1) : f2_fma(d1, d1, acc[1]);
-                acc[2] = j == 0 ? f2_mul(d2, d2) : f2_fma(d2, d2, acc[2]);
-                acc[3] = j == 0 ? f2_mul(d3, d3) : f2_fma(d3, d3, acc[3]);
+                nd[j][0] = f2_pack(a.x, a.y); nd[j][1] = f2_pack(a.z, a.w);
+                nd[j][2] = f2_pack(b.x, b.y); nd[j][3] = f2_pack(b.z, b.w);
             }
-            float v[8];
+            float mn[FQ];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) f2_unpack(acc[t], v[2 * t], v[2 * t + 1]);
-            float mn = f_min3(v[0], v[1], v[2]);
-            mn = f_min3(mn, v[3], v[4]);
-            mn = f_min3(mn, v[5], v[6]);
-            mn = fminf(mn, v[7]);
-            if (mn <= thr_f) {
-                if (cc < C) cand[cbase + cc] = g0 + g;
-                ++cc;
+            for (int r = 0; r < FQ; ++r) {
+                uint64_t acc[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[p] = nd[D][p];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const uint64_t qj = f2_pack(nq2[r][j], nq2[r][j]);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[p] = f2_fma(nd[j][p], qj, acc[p]);
+                }
+                float v[8];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) f2_unpack(acc[p], v[2 * p], v[2 * p + 1]);
+                float w = f_min3(v[0], v[1], v[2]);
+                w = f_min3(w, v[3], v[4]);
+                w = f_min3(w, v[5], v[6]);
+                mn[r] = fminf(w, v[7]);
+            }
+            // one (rarely taken) branch per group for the four queries
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < FQ; ++r) any |= mn[r] <= thr[r];
+            if (any) {
+#pragma unroll
+                for (int r = 0; r < FQ; ++r)
+                    if (mn[r] <= thr[r]) {
+                        cl[r][cc[r] < C ? cc[r] : C - 1] = g0 + g;   // an overflowing list is never read
+                        ++cc[r];
+                    }
             }
         }
         __syncthreads();                                         // every warp is done with stage st
         if (threadIdx.x == 0 && it + STAGES < T) issue(it + STAGES);
     }
-    if (q < m) ccount[q * S + s] = cc;
+#pragma unroll
+    for (int r = 0; r < FQ; ++r) {
+        const int64_t q = qb + (int64_t)r * TPB;
+        if (q < m) ccount[q * S + s] = cc[r];
+    }
 }
 
 // One thread per query: exact fp64 decision of the candidate groups, chunks and groups in
 // ascending node order (ties keep the lower index).  A query that cannot be answered from
 // its lists flags its block of 32 queries for the one-kernel scan.
 template <int D, int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
              const double *__restrict__ X, int64_t m, const double *__restrict__ seed2, int S,
              int C, const int32_t *__restrict__ cand, const int32_t *__restrict__ ccount, int k,
              int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo) {
+    const unsigned FULL = 0xffffffffu;
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
-    bool over = false;
-    for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
-    if (over) { redo[q >> 5] = 1; return; }
+    bool live = q < m;
+    if (live) {
+        bool over = false;
+        for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
+        if (over) { redo[q >> 5] = 1; live = false; }
+    }
     double qv[D];
 #pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
+    for (int j = 0; j < D; ++j) qv[j] = live ? X[q * D + j] : 0.0;
     TopK<K> top;
-    top.init(seed2[q]);
+    top.init(live ? seed2[q] : -1.0);
+    // The warp walks its 32 candidate lists in lock-step: every lane evaluates the 8 nodes of
+    // its t-th group, then the lanes insert their passing nodes round by round, so that the
+    // ~100-instruction sorted insertion always runs with many lanes active.
     for (int s = 0; s < S; ++s) {
-        const int c = ccount[q * S + s];
-        const int32_t *cl = cand + (q * S + s) * (int64_t)C;
-        for (int t = 0; t < c; ++t) {
-            const int64_t b = (int64_t)cl[t] * 8;
-#pragma unroll 1
+        const int c = live ? ccount[q * S + s] : 0;
+        const int32_t *cl = cand + ((live ? q : 0) * S + s) * (int64_t)C;
+        const int cmax = __reduce_max_sync(FULL, c);
+        for (int t = 0; t < cmax; ++t) {
+            const int64_t b = t < c ? (int64_t)cl[t] * 8 : n;
+            double d2[8];
+            uint32_t mask = 0;
+#pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const int64_t id = b + u;
-                if (id >= n) break;
+                const bool ok = b + u < n;
+                const int64_t id = ok ? b + u : 0;
                 double pv[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + id];
-                top.offer(dist2_full<D>(pv, qv), (int32_t)id);
+                d2[u] = dist2_full<D>(pv, qv);
+                mask |= (ok && d2[u] <= top.bound2) ? (1u << u) : 0u;
+            }
+            while (__any_sync(FULL, mask != 0u)) {
+                const int u = mask ? __ffs(mask) - 1 : 8;
+                mask &= mask - 1;
+                double dd = INFINITY;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) dd = u == v ? d2[v] : dd;
+                top.offer(dd, u < 8 ? (int32_t)(b + u) : -1);
             }
         }
     }
+    if (!live) return;
 #pragma unroll
     for (int t = 0; t < K; ++t)
         if (t < k) {
             idx[q * k + t] = top.i[t];
             if (dist) dist[q * k + t] = top.i[t] >= 0 ? top.d[t] : INFINITY;
         }
-    if (top.i[k - 1 < K ? k - 1 : K - 1] < 0)
+    int have = 0;                             // (static indexing keeps the list in registers)
+#pragma unroll
+    for (int t = 0; t < K; ++t) have += (t < k && top.i[t] >= 0) ? 1 : 0;
+    if (have < k)
         pad_nan_row(soa, capacity, n, D, X + q * D, k, idx + q * k, dist ? dist + q * k : nullptr);
 }
 
@@ -1003,70 +1105,106 @@ __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity,
     }
 }
 
-// seed2[q] = K-th smallest exact fp64 d^2 among (up to 32) nodes of the block of cells around
-// the query -- a subset of the nodes, so an upper bound of the true K-th smallest -- inflated
-// by 1e-9.  One warp per query: lane f takes the f-th node of the block (row-major over its
-// cells), and the K-th smallest is selected by rank counting over shuffles.  Which nodes of a
-// dense block make it into the 32 is arbitrary and irrelevant for correctness.
+// seed2[q] = K-th smallest exact fp64 d^2 among ALL nodes of a block of cells around the
+// query's cell that holds at least K nodes -- a subset of the nodes, so an upper bound of the
+// true K-th smallest -- inflated by 1e-9.  One warp per query.  The block grows ring by ring
+// (then geometrically, until it covers the whole grid: sparse pockets, queries far outside the
+// cloud); lanes own its rows (a row of cells is one contiguous range of `ids`).  The nodes
+// are enumerated 32 at a time, flat over the rows, and merged into the running K smallest by
+// rank counting over shuffles (the K smallest live in lanes 0..K-1, sorted, via a per-warp
+// shared-memory scatter).  inf = fewer than K nodes at a non-NaN distance.
+template <int D>
 __global__ void __launch_bounds__(256)
 k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
            const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
            const int32_t *__restrict__ ids, int K, double *__restrict__ seed2) {
+    __shared__ double sbest[8][32];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= m) return;
-    const double qv[2] = {X[2 * q], X[2 * q + 1]};
+    if (q >= m) return;                                       // warp-uniform
+    double qv[D];
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { qv[j] = X[q * D + j]; finite &= qv[j] == qv[j]; }
     const double mnx = b4[0], mxx = b4[1], mny = b4[2], mxy = b4[3];
     double out = INFINITY;
-    if (qv[0] == qv[0] && qv[1] == qv[1] && mnx <= mxx && mny <= mxy) {
+    if (finite && mnx <= mxx && mny <= mxy) {
         const int cx = cell_of(qv[0], mnx, mxx, G), cy = cell_of(qv[1], mny, mxy, G);
-        for (int r = 1; r <= 8; ++r) {
-            const int x0 = cx - r < 0 ? 0 : cx - r, x1 = cx + r > G - 1 ? G - 1 : cx + r;
-            const int y0 = cy - r < 0 ? 0 : cy - r, y1 = cy + r > G - 1 ? G - 1 : cy + r;
-            // lane t owns row y0 + t of the block (<= 17 rows)
-            int32_t e0 = 0, len = 0;
-            if (y0 + lane <= y1) {
-                e0 = start[(int64_t)(y0 + lane) * G + x0];
-                len = start[(int64_t)(y0 + lane) * G + x1 + 1] - e0;
-            }
-            int32_t inc = len;
+        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        int32_t cnt = 0;
+        for (int r = 1;; r = r < 8 ? r + 1 : 2 * r) {
+            x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
+            y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
+            int32_t c = 0;
+            for (int row = y0 + lane; row <= y1; row += 32)
+                c += start[(int64_t)row * G + x1 + 1] - start[(int64_t)row * G + x0];
+            cnt = __reduce_add_sync(FULL, c);
+            if (cnt >= K || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
+        }
+        if (cnt >= K) {
+            double best = INFINITY;                           // lanes 0..K-1: the K smallest so far
+            int nb = 0;                                       // valid entries of `best`
+            // rows in passes of 32 (one pass unless the block is taller than 32 cells)
+            for (int rb = y0; rb <= y1; rb += 32) {
+                int32_t e0 = 0, len = 0;
+                if (rb + lane <= y1) {
+                    e0 = start[(int64_t)(rb + lane) * G + x0];
+                    len = start[(int64_t)(rb + lane) * G + x1 + 1] - e0;
+                }
+                int32_t inc = len;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int32_t u = __shfl_up_sync(FULL, inc, o);
-                if (lane >= o) inc += u;
-            }
-            const int32_t cnt = __shfl_sync(FULL, inc, 31);
-            const bool all = x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1;
-            if (cnt >= K) {
-                // flat candidate `lane` lives in the first row whose inclusive prefix exceeds it
-                int32_t e = -1;
-                for (int row = 0; row <= y1 - y0; ++row) {
-                    const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
-                    const int32_t re0 = __shfl_sync(FULL, e0, row);
-                    if (e < 0 && lane < rinc) e = re0 + (lane - (rinc - rlen));
+                for (int o = 1; o < 32; o <<= 1) {
+                    int32_t u = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= o) inc += u;
                 }
-                double v = INFINITY;
-                if (e >= 0) {
-                    const int32_t t = ids[e];
-                    const double pv[2] = {soa[t], soa[capacity + t]};
-                    v = dist2_full<2>(pv, qv);
-                    v = v != v ? INFINITY : v;          // a NaN node is never a neighbour
-                }
-                // rank among the 32 held values (ties by lane); rank K-1 is the K-th smallest
-                int rank = 0;
-#pragma unroll 8
-                for (int src = 0; src < 32; ++src) {
-                    const double w = __shfl_sync(FULL, v, src);
-                    rank += (w < v || (w == v && src < lane)) ? 1 : 0;
-                }
-                double kth = rank == K - 1 ? v : -1.0;
+                const int32_t pc = __shfl_sync(FULL, inc, 31);   // nodes in this pass
+                const int nrows = y1 - rb + 1 < 32 ? y1 - rb + 1 : 32;
+                for (int32_t f0 = 0; f0 < pc; f0 += 32) {
+                    // flat candidate f0 + lane lives in the first row whose inclusive prefix exceeds it
+                    const int32_t f = f0 + lane;
+                    int32_t e = -1;
+                    for (int row = 0; row < nrows; ++row) {
+                        const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
+                        const int32_t re0 = __shfl_sync(FULL, e0, row);
+                        if (e < 0 && f < rinc) e = re0 + (f - (rinc - rlen));
+                    }
+                    double v = INFINITY;
+                    if (f < pc && e >= 0) {
+                        const int32_t t = ids[e];
+                        double pv[D];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) kth = fmax(kth, __shfl_xor_sync(FULL, kth, o));
-                out = kth * (1.0 + 1e-9) + 1e-300;
-                break;
+                        for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
+                        v = dist2_full<D>(pv, qv);
+                        v = v != v ? INFINITY : v;          // a NaN node is never a neighbour
+                    }
+                    // ranks in the union of `best` (first on ties) and this chunk; only the
+                    // nb valid entries of `best` and the nv valid entries of the chunk are
+                    // compared against (the rest are +inf and rank behind every finite value)
+                    const int nv = pc - f0 < 32 ? pc - f0 : 32;
+                    int rank_b = 0, rank_v = 0;
+                    for (int src = 0; src < nb; ++src) {
+                        const double a = __shfl_sync(FULL, best, src);
+                        rank_b += (a < best || (a == best && src < lane)) ? 1 : 0;
+                        rank_v += a <= v ? 1 : 0;
+                    }
+                    for (int src = 0; src < nv; ++src) {
+                        const double c = __shfl_sync(FULL, v, src);
+                        rank_b += c < best ? 1 : 0;
+                        rank_v += (c < v || (c == v && src < lane)) ? 1 : 0;
+                    }
+                    sbest[w][lane] = INFINITY;
+                    __syncwarp();
+                    if (lane < nb && rank_b < 32) sbest[w][rank_b] = best;
+                    if (lane < nv && rank_v < 32) sbest[w][rank_v] = v;
+                    __syncwarp();
+                    best = lane < K ? sbest[w][lane] : INFINITY;
+                    __syncwarp();
+                    nb = nb + nv < K ? nb + nv : K;
+                }
             }
-            if (all) break;                            // fewer than K nodes in total
+            const double kth = __shfl_sync(FULL, best, K - 1);
+            out = kth * (1.0 + 1e-9) + 1e-300;
         }
     }
     if (lane == 0) seed2[q] = out;
@@ -1077,6 +1215,7 @@ int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0
 int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
 int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
 int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
+int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filter kernel
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -1127,7 +1266,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         }
         return SBP_OK;
     }
-    const double *seed = nullptr;
+    const double *seed = nullptr, *seed_bounds = nullptr;
     if (D == 2 && g_knn_seed && n >= 2048) {
         int G = (int)ceil(sqrt(2.0 * (double)n));
         if (G > 2048) G = 2048;
@@ -1154,18 +1293,20 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
         k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
-        k_knn_seed<<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        k_knn_seed<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
             s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
         ctx->launches += 7;
         SBP_CUDA(cudaGetLastError());
         seed = (const double *)seedbuf;
+        seed_bounds = b4;
     }
     const uint8_t *redo = nullptr;
     if (seed && g_knn_filter) {
         // seeded filter + exact refine; the one-kernel scan below then only redoes the
         // blocks of 32 queries the refine step flagged (normally none)
-        constexpr int NW = 4;
-        const int64_t qblocks = (m + NW * 32 - 1) / (NW * 32);
+        const int NW = g_knn_filter_variant >= 2 ? 4 : 2;          // warps per CTA
+        const int QPB = NW * 32 * FILTER_Q;                        // queries per CTA
+        const int64_t qblocks = (m + QPB - 1) / QPB;
         constexpr int FT = filter_tile(D);
         const int64_t tiles = (n + FT - 1) / FT;
         int64_t FS = g_knn_filter_chunks > 0 ? g_knn_filter_chunks
@@ -1176,20 +1317,40 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         const int64_t chunk = (tiles + FS - 1) / FS * FT;
         FS = (n + chunk - 1) / chunk;
         int C = 4 * K / (int)FS + 12;
-        void *cbuf = nullptr, *nbuf = nullptr;
+        const int64_t cap32 = tiles * FT;
+        void *cbuf = nullptr, *nbuf = nullptr, *shbuf = nullptr;
         rc = sbp_ctx_scratch(ctx, 8, (size_t)m * FS * C * sizeof(int32_t), &cbuf);
         if (rc) return rc;
         const size_t nflags = (size_t)((m + 31) / 32);
         rc = sbp_ctx_scratch(ctx, 9, (size_t)m * FS * sizeof(int32_t) + nflags, &nbuf);
         if (rc) return rc;
+        rc = sbp_ctx_scratch(ctx, 10, 64 + (size_t)(D + 1) * cap32 * sizeof(float), &shbuf);
+        if (rc) return rc;
+        double *info = (double *)shbuf;                            // [1 + D] <= 64 bytes
+        float *shadow = (float *)((char *)shbuf + 64);
         int32_t *ccount = (int32_t *)nbuf;
         uint8_t *flags = (uint8_t *)nbuf + (size_t)m * FS * sizeof(int32_t);
         SBP_CUDA(cudaMemsetAsync(flags, 0, nflags, ctx->stream));
+        int sb = (int)((cap32 + 255) / 256);
+        if (sb > ctx->sm_count * 8) sb = ctx->sm_count * 8;
+        k_shadow_centered<D><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, seed_bounds, cap32,
+                                                          shadow, info);
         dim3 fgrid((unsigned)qblocks, (unsigned)FS);
-        k_knn_filter<D, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
-            s->d_soa32, s->d_maxabs, s->capacity, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf,
-            ccount);
-        k_knn_refine<D, K><<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
+#define SBP_FILTER_LAUNCH(NW_, UNR_)                                                        \
+    k_knn_filter<D, NW_, UNR_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                         \
+        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf, ccount)
+        {
+        KernelTimer timer(ctx);
+        switch (g_knn_filter_variant) {
+            case 1: SBP_FILTER_LAUNCH(2, 1); break;
+            case 2: SBP_FILTER_LAUNCH(4, 2); break;
+            case 3: SBP_FILTER_LAUNCH(4, 1); break;
+            default: SBP_FILTER_LAUNCH(2, 2); break;
+        }
+        }
+#undef SBP_FILTER_LAUNCH
+        ctx->launches++;
+        k_knn_refine<D, K><<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(
             s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
             dist, flags);
         ctx->launches += 2;

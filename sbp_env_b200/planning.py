@@ -111,3 +111,70 @@ def prm_connect_radius(cc, tree, radius: float):
     src, dst = idx[keep], dst[keep]
     vis = cc.visible_batch(X[src].contiguous(), X[dst].contiguous())
     return src, dst, vis
+
+
+class CapturedStep:
+    """A fixed sequence of launches of this library (and torch copies), captured once into a
+    CUDA graph and replayed with a single ``cudaGraphLaunch``.
+
+    ``fn()`` is called ``warmup`` times eagerly on a side stream (so that every work-space
+    reaches its final size and nothing allocates or synchronises during capture), then once
+    under capture; whatever it returns is kept in ``out`` and overwritten by each replay.
+    Shapes, sizes and addresses are frozen; the *contents* of the input tensors, of the node
+    stores and of the maps may change between replays.
+    """
+
+    def __init__(self, fn, device: int = 0, warmup: int = 2):
+        import torch
+
+        dev = torch.device("cuda", device)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.out = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+
+class PRMConnectGraph(CapturedStep):
+    """:func:`prm_connect_knn` for a fixed problem shape as a :class:`CapturedStep`.
+
+    One connection step is ~20 short kernels (cell grid, seeds, filter, refine, edge gather,
+    visibility); issued one by one from Python their launch cost exceeds the ~0.5 ms the GPU
+    needs for a 50 000-node roadmap, so the inner loop is captured and a step becomes a single
+    graph launch.  Results are identical to the eager call.  ``tree`` must not change size
+    and ``queries`` (when given) must be updated in place.
+
+    >>> g = PRMConnectGraph(cc, tree, k=10)
+    >>> nbr, vis = g.replay()          # tensors owned by the graph, overwritten by each replay
+    """
+
+    def __init__(self, cc, tree, k: int, rows=None, queries=None, warmup: int = 2):
+        if "visible" in getattr(cc, "__dict__", {}):
+            raise ValueError("a mocked checker cannot be captured into a CUDA graph")
+        self.cc, self.tree, self.k = cc, tree, int(k)
+        self._n = len(tree)
+        before = [0]
+
+        def fn():
+            before[0] = int(cc.stats.visible_cnt)
+            return prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries)
+
+        super().__init__(fn, device=tree.ctx.device, warmup=warmup)
+        self._edges = int(cc.stats.visible_cnt) - before[0]     # edges checked by one step
+        self.nbr, self.vis = self.out
+
+    def replay(self):
+        if len(self.tree) != self._n:
+            raise RuntimeError("the node store changed size since the graph was captured")
+        self.graph.replay()
+        self.cc.stats.visible_cnt += self._edges        # Stats accounting of visible_batch
+        return self.nbr, self.vis

@@ -33,8 +33,9 @@ for n, m in ((50_000, 50_000), (1_000_000, 100_000), (5000, 5000)):
     tree = sg.NodeStore(2, capacity=n)
     tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * scale)
     X = tree.rows_device(0, m)
-    for filt, chunks in ((0, 0), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (1, 6), (1, 8), (1, 12), (1, 16), (1, 24)):
+    for filt, var, chunks in [(0, 0, 0)] + [(1, v, c) for v in (0, 1, 2, 3) for c in (0, 4, 8, 16, 32)]:
         lib.sbp_tune(b"knn_filter", filt)
+        lib.sbp_tune(b"knn_filter_variant", var)
         lib.sbp_tune(b"knn_filter_chunks", chunks)
         ms = timeit(lambda: tree.knn(X, 11, return_dist=False))
-        print(f"n={n} m={m} filter={filt} chunks={chunks}: {ms:.4f} ms  {n * m / ms * 1e3:.3e} evals/s", flush=True)
+        print(f"n={n} m={m} filter={filt} variant={var} chunks={chunks}: {ms:.4f} ms  {n * m / ms * 1e3:.3e} evals/s", flush=True)
