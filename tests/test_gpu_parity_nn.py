@@ -328,3 +328,59 @@ def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
     finally:
         lib.sbp_tune(b"knn_filter", 1)
         lib.sbp_tune(b"knn_filter_chunks", 0)
+
+
+def test_prm_connect_graph_replay_equals_eager(sg):
+    """PRMConnectGraph / CapturedStep: the captured step replays to the same neighbour and
+    visibility blocks as the eager call, follows in-place changes of the query tensor, keeps
+    the Stats accounting of visible_batch and refuses a store that changed size."""
+    import torch
+
+    free = load_map("intel_lab")
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
+    rng = np.random.default_rng(5)
+    pts = rng.random((9000, 2)) * free.shape
+    pts = pts[cc.feasible_batch(pts)][:4000]
+    tree = sg.NodeStore(2, capacity=8192)
+    tree.extend(pts)
+    nbr_e, vis_e = sg.prm_connect_knn(cc, tree, 10)
+    g = sg.PRMConnectGraph(cc, tree, 10)
+    before = cc.stats.visible_cnt
+    for _ in range(2):
+        nbr, vis = g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e)
+    assert cc.stats.visible_cnt - before == 2 * 4000 * 10
+    # same edges as the oracle
+    oi, _ = orc.knn(pts, pts, 11)
+    assert np.array_equal(np.sort(nbr.cpu().numpy(), 1), np.sort(oi[:, 1:], 1))
+    # external queries, updated in place between replays
+    Xq = torch.from_numpy(rng.random((1500, 2)) * free.shape).cuda()
+    gq = sg.PRMConnectGraph(cc, tree, 7, queries=Xq)
+    for _ in range(2):
+        Xq.copy_(torch.from_numpy(rng.random((1500, 2)) * free.shape))
+        nbr, vis = gq.replay()
+        ne, ve = sg.prm_connect_knn(cc, tree, 7, queries=Xq)
+        assert torch.equal(nbr, ne) and torch.equal(vis, ve)
+    tree.append(np.array([1.0, 2.0]))
+    with pytest.raises(RuntimeError):
+        g.replay()
+
+
+def test_knn_seeds_in_sparse_pockets_and_far_queries(sg):
+    """Grid seeds: isolated pockets with fewer than k nodes nearby, queries far outside the
+    cloud, and very dense clumps -- the block of cells grows until it holds k nodes and the
+    bound uses all of its nodes; results equal the oracle's."""
+    rng = np.random.default_rng(99)
+    clumps = np.concatenate([c + rng.standard_normal((3000, 2)) * 0.02 for c in ([10.0, 10.0], [500.0, 20.0])])
+    lonely = np.array([[250.0, 250.0], [251.0, 250.0], [900.0, 900.0], [-300.0, 40.0]])
+    sparse = rng.random((3000, 2)) * 1000
+    poses = np.concatenate([clumps, lonely, sparse])
+    X = np.concatenate([lonely + 0.25, [[5000.0, 5000.0], [-1e6, 0.0], [10.0, 10.0], [500.0, 20.0]],
+                        rng.random((600, 2)) * 1200 - 100, clumps[::50] + 1e-3])
+    t = sg.NodeStore(2)
+    t.extend(poses)
+    for k in (11, 1, 32):
+        idx, dist = t.knn(X, k)
+        oi, od = orc.knn(poses, X, k)
+        assert np.array_equal(idx, oi) and np.array_equal(dist, od), k
