@@ -384,6 +384,8 @@ class RobotArm4dCollisionChecker(_GridChecker):
             return np.array([bool(self.feasible(c)) for c in np.asarray(Cfg)], dtype=bool)
         if save_stats:
             self.stats.feasible_cnt += len(Cfg)
+        if _is_torch_tensor(Cfg):
+            return self._feasible_device(Cfg)
         return self._feasible_host(as_host_f64(Cfg, 4))
 
     def visible_batch(self, C1, C2):
@@ -423,6 +425,33 @@ class RobotArm4dCollisionChecker(_GridChecker):
         raise_for_flags(flags.value, "visible")          # the arm checker has no guard (:385-391)
         self.last_ambiguous = int(amb.value)
         return out.astype(bool)
+
+    def _feasible_device(self, Cfg, resolve=True):
+        """Device tensor in, CUDA bool tensor out (guard-band entries settled like
+        :meth:`_visible_device`)."""
+        import torch
+
+        m = self.device_map
+        m.ctx.use_torch_stream()
+        Cfg = as_device_f64(Cfg, 4)
+        n = Cfg.shape[0]
+        L0, L1 = self._lengths()
+        out = torch.empty(n, dtype=torch.uint8, device=Cfg.device)
+        flags = torch.zeros(1, dtype=torch.int32, device=Cfg.device)
+        check(_lib.load().sbp_arm_feasible(m.handle, L0, L1, ptr(Cfg), n, ptr(out), ptr(flags)),
+              "sbp_arm_feasible")
+        self._last_flags = flags
+        if not resolve:
+            return out
+        amb = torch.nonzero(out == _lib.AMBIGUOUS).flatten()
+        self.last_ambiguous = int(amb.numel())
+        if amb.numel():
+            a = Cfg[amb].cpu().numpy()
+            o = np.full(len(a), _lib.AMBIGUOUS, np.uint8)
+            check(_lib.load().sbp_arm_resolve_host(m.handle, L0, L1, ptr(a), None, len(a), ptr(o), None),
+                  "sbp_arm_resolve_host")
+            out[amb] = torch.from_numpy(o).to(out.device)
+        return out.bool()
 
     def _visible_device(self, C1, C2, cfg_tested=None, resolve=True):
         """Device tensors in, CUDA bool tensor out.  Guard-band entries (rare) are

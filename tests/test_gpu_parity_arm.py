@@ -84,9 +84,22 @@ def test_random_vs_oracle(sg, name, L):
     C2 = C1 + rng.standard_normal((n, 4)) * [7, 7, 0.4, 0.4]
     C2[-3000:] = rng.random((3000, 4)) * (hi - lo) + lo                 # long edges
     assert np.array_equal(cc.feasible_batch(C1), om.arm_feasible(C1, *L))
-    assert np.array_equal(cc.visible_batch(C1, C2), om.arm_visible(C1, C2, *L))
-    # H8: argument order matters for the arm; check the reverse direction too
-    assert np.array_equal(cc.visible_batch(C2, C1), om.arm_visible(C2, C1, *L))
+    from sbp_env_b200 import _lib
+
+    lib = _lib.load()
+    want_fwd, want_rev = om.arm_visible(C1, C2, *L), om.arm_visible(C2, C1, *L)
+    try:
+        # lanes per edge of the lane-group kernel (0 = default, 8)
+        for group in (0, 4, 32):
+            lib.sbp_tune(b"arm_group", group)
+            assert np.array_equal(cc.visible_batch(C1, C2), want_fwd), group
+            # H8: argument order matters for the arm; check the reverse direction too
+            assert np.array_equal(cc.visible_batch(C2, C1), want_rev), group
+            # tiny batches (fewer edges than one warp) and a single edge
+            assert np.array_equal(cc.visible_batch(C1[:37], C2[:37]), want_fwd[:37]), group
+            assert np.array_equal(cc.visible_batch(C1[-1:], C2[-1:]), want_fwd[-1:]), group
+    finally:
+        lib.sbp_tune(b"arm_group", 0)
 
 
 def test_guard_band_is_resolved_exactly(sg):
@@ -112,6 +125,8 @@ def test_guard_band_is_resolved_exactly(sg):
     assert cc.last_ambiguous > 0
     got = cc.visible_batch(torch.from_numpy(C1).cuda(), torch.from_numpy(C2).cuda()).cpu().numpy()
     assert np.array_equal(got, om.arm_visible(C1, C2, 30.0, 30.0))
+    got = cc.feasible_batch(torch.from_numpy(C1).cuda()).cpu().numpy()       # device-tensor path
+    assert np.array_equal(got, om.arm_feasible(C1, 30.0, 30.0))
     # uniform random configs almost never land in the band
     U = rng.random((200000, 4)) * [W, H, 6, 6] - [0, 0, 3, 3]
     cc.feasible_batch(U)
