@@ -40,7 +40,7 @@ METRIC = "edge collision checks/sec (PRM candidate edges: brute-force kNN connec
 UNIT = "edges/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_filter launch on this workload
 # (ncu --set full, profiles/r1_knn_filter_full.txt)
-FILTER_DRAM_TRAFFIC = 18246400
+FILTER_DRAM_TRAFFIC = 18273024
 WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
             "candidate edges per step (kNN 2.5e9 fp64 distance evals + Bresenham visible_batch)")
 

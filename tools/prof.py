@@ -5,6 +5,7 @@
     python tools/prof.py visible_l2 # 2^22 edges on a 16384^2 blocky-noise grid (L2 path)
     python tools/prof.py arm        # 2^18 arm edges on the 1024^2 map
     python tools/prof.py nearest    # 1 query over 2^20 nodes
+    python tools/prof.py step       # the bench step (cfg2 PRM connect: kNN + edges + visible), eager launches
 """
 import os
 import sys
@@ -37,7 +38,17 @@ def timeit(fn):
     return a.elapsed_time(b) / reps
 
 
-if what in ("knn", "nearest"):
+if what == "step":
+    import bench
+
+    free = bench.load_free()
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
+    nodes = bench.draw_free_samples(free, bench.N_NODES, 0, cc.feasible_batch)
+    tree = sg.NodeStore(2, capacity=bench.N_NODES)
+    tree.extend(nodes)
+    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, bench.K_NN))
+    print(what, "ms (eager, host-bound)", ms)
+elif what in ("knn", "nearest"):
     free = load_map("intel_lab")
     W, H = free.shape
     scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
