@@ -382,7 +382,7 @@ extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint
 int g_visible_group = 0;   // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
 int g_coop_below = 12;     // adaptive kernel: cap of the hand-over threshold (walkers)
 int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
-extern int g_arm_group;
+extern int g_arm_group, g_near_filter;
 extern int g_knn_chunks, g_knn_prefilter, g_knn_seed, g_knn_filter, g_knn_filter_chunks, g_knn_filter_variant;
 
 int g_time_kernels = 0;    // bench instrumentation: event pairs around the dominant kNN kernel
@@ -417,6 +417,7 @@ extern "C" int32_t sbp_tune(const char *key, int64_t value) {
     if (!strcmp(key, "knn_filter_variant")) { g_knn_filter_variant = (int)value; return SBP_OK; }
     if (!strcmp(key, "time_kernels")) { g_time_kernels = (int)value; return SBP_OK; }
     if (!strcmp(key, "arm_group")) { g_arm_group = (int)value; return SBP_OK; }
+    if (!strcmp(key, "near_filter")) { g_near_filter = (int)value; return SBP_OK; }
     if (!strcmp(key, "force_global")) { g_force_global = (int)value; return SBP_OK; }
     sbp_set_error("sbp_tune: unknown key %s", key);
     return SBP_ERR_ARG;

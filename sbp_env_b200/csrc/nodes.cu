@@ -539,19 +539,46 @@ __global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capaci
     }
 }
 
-template <int D, int NW, int UNR>
-__global__ void __launch_bounds__(NW * 32)
-k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
-             int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
-             const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
-             int32_t *__restrict__ ccount) {
-    constexpr int TILE = filter_tile(D), STAGES = FILTER_STAGES, FQ = FILTER_Q, TPB = NW * 32;
-    __shared__ __align__(128) float tile[STAGES][D + 1][TILE];
+// Threshold of one query for the filter (see the derivation above).  `bound2` is the exact
+// fp64 d^2 bound of the query (seed, or the radius threshold); xq its coordinates (stride of
+// the caller), DD the number of leading coordinates the distance uses.  Returns false -- and
+// thr = -inf, so that nothing passes -- when the query cannot be filtered conservatively.
+template <int DD>
+__device__ __forceinline__ bool filter_query_setup(const double *__restrict__ info, const double *xq,
+                                                   bool live, double bound2, float (&nq2)[DD],
+                                                   float &thr) {
+    const double M = info[0];
+    double Mq = 0.0, qq = 0.0;
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {
+        const double v = live ? xq[j] - info[1 + j] : 0.0;
+        const float qf = (float)v;
+        nq2[j] = -2.0f * qf;
+        qq += (double)qf * (double)qf;
+        const double av = v != v ? INFINITY : fabs(v);
+        Mq = av > Mq ? av : Mq;
+    }
+    const double mm = M > Mq ? M : Mq;
+    const double a = 4.0 * 5.9604644775390625e-8 * sqrt((double)DD) * mm * (1.0 + 1e-6);
+    const double E = 5.9604644775390625e-8 * (double)(DD * (DD + 1)) * M * (M + Mq) * (1.0 + 1e-5) +
+                     1e-15 * Mq * Mq;
+    const double ra = sqrt(bound2) + a;                              // NaN for bound2 < 0 or NaN
+    const double pos = (ra * ra + E) * (1.0 + 1e-9);
+    const bool usable = live && mm < 1e15 && bound2 < INFINITY && E <= ra * ra;
+    thr = usable ? __double2float_ru(pos - qq) : -INFINITY;          // t (or NaN) never passes -inf
+    return usable;
+}
+
+// The scan itself: streams node chunk [c0, c1) of the centred shadow through shared memory
+// and calls on_group(r, g) for every (query slot r, group of 8 nodes g = node index / 8) whose
+// minimum t passes thr[r].  All threads of the CTA must call it (barriers inside).
+template <int DD, int NW, int UNR, class OnGroup>
+__device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_t cap32, int64_t c0,
+                                            int64_t c1, const float (&nq2)[FILTER_Q][DD],
+                                            const float (&thr)[FILTER_Q], OnGroup on_group) {
+    constexpr int TILE = filter_tile(DD), STAGES = FILTER_STAGES, FQ = FILTER_Q;
+    __shared__ __align__(128) float tile[STAGES][DD + 1][TILE];
     __shared__ __align__(8) uint64_t full[STAGES];
-    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
-    const int s = blockIdx.y;
-    const int64_t c0 = (int64_t)s * chunk;                       // multiple of TILE
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
     const int T = c1 > c0 ? (int)((c1 - c0 + TILE - 1) / TILE) : 0;
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -559,52 +586,20 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
         fence_barrier_init();
     }
     __syncthreads();
-    // one thread feeds the stages: D + 1 bulk copies of <= 4 KB per tile (cap32 is a multiple
+    // one thread feeds the stages: DD + 1 bulk copies of <= 4 KB per tile (cap32 is a multiple
     // of the tile, so every copy is a whole number of 16-byte units inside the allocation)
     auto issue = [&](int it) {
         const int st = it % STAGES;
         const int64_t t0 = c0 + (int64_t)it * TILE;
         const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         const uint32_t bytes = (uint32_t)((cnt + 7) & ~7) * 4u;
-        mbar_expect_tx(&full[st], bytes * (D + 1));
+        mbar_expect_tx(&full[st], bytes * (DD + 1));
 #pragma unroll
-        for (int j = 0; j <= D; ++j)
+        for (int j = 0; j <= DD; ++j)
             bulk_g2s(&tile[st][j][0], sh + (int64_t)j * cap32 + t0, bytes, &full[st]);
     };
     if (threadIdx.x == 0)
         for (int it = 0; it < T && it < STAGES; ++it) issue(it);
-
-    const double M = info[0];
-    float nq2[FQ][D];        // -2 q^_j
-    float thr[FQ];
-    int cc[FQ];
-    int32_t *cl[FQ];         // this (query, chunk)'s candidate list
-#pragma unroll
-    for (int r = 0; r < FQ; ++r) {
-        const int64_t q = qb + (int64_t)r * TPB;
-        double Mq = 0.0, qq = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const double v = q < m ? X[q * D + j] - info[1 + j] : 0.0;
-            const float qf = (float)v;
-            nq2[r][j] = -2.0f * qf;
-            qq += (double)qf * (double)qf;
-            const double av = v != v ? INFINITY : fabs(v);
-            Mq = av > Mq ? av : Mq;
-        }
-        const double sd = q < m ? seed2[q] : -1.0;
-        const double mm = M > Mq ? M : Mq;
-        const double a = 4.0 * 5.9604644775390625e-8 * sqrt((double)D) * mm * (1.0 + 1e-6);
-        const double E = 5.9604644775390625e-8 * (double)(D * (D + 1)) * M * (M + Mq) * (1.0 + 1e-5) +
-                         1e-15 * Mq * Mq;
-        const double ra = sqrt(sd) + a;                              // NaN for sd < 0 or NaN
-        const double pos = (ra * ra + E) * (1.0 + 1e-9);
-        const bool usable = q < m && mm < 1e15 && sd < INFINITY && E <= ra * ra;
-        thr[r] = usable ? __double2float_ru(pos - qq) : -INFINITY;   // t (or NaN) never passes -inf
-        cc[r] = (q < m && !usable) ? C + 1 : 0;                      // C + 1 = "not filterable"
-        cl[r] = cand + ((q < m ? q : 0) * S + s) * (int64_t)C;
-    }
-
     for (int it = 0; it < T; ++it) {
         const int st = it % STAGES;
         const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
@@ -615,9 +610,9 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
         const int32_t g0 = (int32_t)(t0 >> 3);
 #pragma unroll UNR
         for (int g = 0; g < groups; ++g) {
-            uint64_t nd[D + 1][4];           // 8 nodes: packed pairs of every component and the norm
+            uint64_t nd[DD + 1][4];          // 8 nodes: packed pairs of every component and the norm
 #pragma unroll
-            for (int j = 0; j <= D; ++j) {
+            for (int j = 0; j <= DD; ++j) {
                 const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
                 const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
                 nd[j][0] = f2_pack(a.x, a.y); nd[j][1] = f2_pack(a.z, a.w);
@@ -628,9 +623,9 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
             for (int r = 0; r < FQ; ++r) {
                 uint64_t acc[4];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) acc[p] = nd[D][p];
+                for (int p = 0; p < 4; ++p) acc[p] = nd[DD][p];
 #pragma unroll
-                for (int j = 0; j < D; ++j) {
+                for (int j = 0; j < DD; ++j) {
                     const uint64_t qj = f2_pack(nq2[r][j], nq2[r][j]);
 #pragma unroll
                     for (int p = 0; p < 4; ++p) acc[p] = f2_fma(nd[j][p], qj, acc[p]);
@@ -650,19 +645,108 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
             if (any) {
 #pragma unroll
                 for (int r = 0; r < FQ; ++r)
-                    if (mn[r] <= thr[r]) {
-                        cl[r][cc[r] < C ? cc[r] : C - 1] = g0 + g;   // an overflowing list is never read
-                        ++cc[r];
-                    }
+                    if (mn[r] <= thr[r]) on_group(r, g0 + g);
             }
         }
         __syncthreads();                                         // every warp is done with stage st
         if (threadIdx.x == 0 && it + STAGES < T) issue(it + STAGES);
     }
+}
+
+template <int D, int NW, int UNR>
+__global__ void __launch_bounds__(NW * 32)
+k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
+             int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
+             const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
+             int32_t *__restrict__ ccount) {
+    constexpr int FQ = FILTER_Q, TPB = NW * 32;
+    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
+    const int s = blockIdx.y;
+    const int64_t c0 = (int64_t)s * chunk;                       // multiple of the tile
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    float nq2[FQ][D];        // -2 q^_j
+    float thr[FQ];
+    int cc[FQ];
+    int32_t *cl[FQ];         // this (query, chunk)'s candidate list
+#pragma unroll
+    for (int r = 0; r < FQ; ++r) {
+        const int64_t q = qb + (int64_t)r * TPB;
+        const bool live = q < m;
+        const bool usable = filter_query_setup<D>(info, X + (live ? q : 0) * D, live,
+                                                  live ? seed2[q] : -1.0, nq2[r], thr[r]);
+        cc[r] = (live && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
+        cl[r] = cand + ((live ? q : 0) * S + s) * (int64_t)C;
+    }
+    filter_scan<D, NW, UNR>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+        cl[r][cc[r] < C ? cc[r] : C - 1] = g;                        // an overflowing list is never read
+        ++cc[r];
+    });
 #pragma unroll
     for (int r = 0; r < FQ; ++r) {
         const int64_t q = qb + (int64_t)r * TPB;
         if (q < m) ccount[q * S + s] = cc[r];
+    }
+}
+
+// Radius query on the same scan (K5'): a group that passes the conservative fp32 test has
+// its 8 nodes decided exactly in fp64 (near_d2 / near_in, the comparison of the unfiltered
+// kernels); PASS 0 counts the matches of (query, chunk), PASS 1 writes them at the scanned
+// offsets, ascending.  A query that cannot be filtered gets thr = +inf, i.e. every group is
+// decided exactly: slower, same result.  DD = coordinates the metric uses (2 for XY).
+template <int D, bool XY, int PASS, int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_near_filtered(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
+                const double *__restrict__ soa, int64_t capacity, int64_t n, int S, int64_t chunk,
+                const double *__restrict__ X, int64_t m, double thr2, int closed,
+                int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
+                int64_t *__restrict__ idx, int64_t idx_capacity, const int64_t *__restrict__ needed) {
+    constexpr int DD = XY ? 2 : D;
+    constexpr int FQ = FILTER_Q, TPB = NW * 32;
+    if (PASS == 1 && *needed > idx_capacity) return;
+    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;
+    const int s = blockIdx.y;
+    const int64_t c0 = (int64_t)s * chunk;
+    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
+    float nq2[FQ][DD];
+    float thr[FQ];
+    int64_t pos[FQ];         // PASS 0: matches so far; PASS 1: next output slot
+#pragma unroll
+    for (int r = 0; r < FQ; ++r) {
+        const int64_t q = qb + (int64_t)r * TPB;
+        const bool live = q < m;
+        const bool usable = filter_query_setup<DD>(info, X + (live ? q : 0) * D, live, thr2, nq2[r], thr[r]);
+        if (live && !usable) {                                       // decide every node exactly:
+            thr[r] = INFINITY;                                       // t = |n^|^2 <= inf always passes
+#pragma unroll
+            for (int j = 0; j < DD; ++j) nq2[r][j] = 0.0f;
+        }
+        pos[r] = (PASS == 1 && live) ? offsets[q * S + s] : 0;
+    }
+    filter_scan<DD, NW, 1>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+        const int64_t q = qb + (int64_t)r * TPB;
+        double qv[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) qv[j] = j < DD ? X[q * D + j] : 0.0;
+        const int64_t b = (int64_t)g * 8;
+#pragma unroll 1
+        for (int u = 0; u < 8; ++u) {
+            const int64_t id = b + u;
+            if (id >= c1) break;
+            double pv[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) pv[j] = j < DD ? soa[(int64_t)j * capacity + id] : 0.0;
+            if (near_in(near_d2<D, XY>(pv, qv), thr2, closed)) {
+                if (PASS == 1) idx[pos[r]] = id;
+                ++pos[r];
+            }
+        }
+    });
+    if (PASS == 0) {
+#pragma unroll
+        for (int r = 0; r < FQ; ++r) {
+            const int64_t q = qb + (int64_t)r * TPB;
+            if (q < m) counts[q * S + s] = pos[r];
+        }
     }
 }
 
@@ -1593,12 +1677,102 @@ k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
     }
 }
 
+// Bounding box of the first DD coordinates: per-block partials [blocks][DD][2] = (min, max),
+// then a one-warp fold (NaN coordinates are ignored by fmin / fmax).
+template <int DD>
+__global__ void __launch_bounds__(256)
+k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial) {
+    __shared__ double sh[2 * DD][8];
+    double mn[DD], mx[DD];
+#pragma unroll
+    for (int j = 0; j < DD; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
+#pragma unroll
+        for (int j = 0; j < DD; ++j) {
+            const double v = soa[(int64_t)j * capacity + t];
+            mn[j] = fmin(mn[j], v); mx[j] = fmax(mx[j], v);
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[j] = fmin(mn[j], __shfl_down_sync(0xffffffffu, mn[j], o));
+            mx[j] = fmax(mx[j], __shfl_down_sync(0xffffffffu, mx[j], o));
+        }
+        if (lane == 0) { sh[2 * j][w] = mn[j]; sh[2 * j + 1][w] = mx[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * DD) {
+        double v = sh[threadIdx.x][0];
+        for (int i = 1; i < 8; ++i) v = (threadIdx.x & 1) ? fmax(v, sh[threadIdx.x][i]) : fmin(v, sh[threadIdx.x][i]);
+        partial[(int64_t)blockIdx.x * 2 * DD + threadIdx.x] = v;
+    }
+}
+
+template <int DD>
+__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+    const int c = threadIdx.x;                     // one thread per (coordinate, min | max)
+    if (c >= 2 * DD) return;
+    double v = partial[c];
+    for (int i = 1; i < nb; ++i) v = (c & 1) ? fmax(v, partial[(int64_t)i * 2 * DD + c]) : fmin(v, partial[(int64_t)i * 2 * DD + c]);
+    out[c] = v;
+}
+
+int g_near_filter = 1;    // tuning knob: filtered radius query (results unchanged)
+
 template <int D, bool XY>
 static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr, int closed,
                            int64_t *row_ptr, int64_t *idx, int64_t idx_capacity, int64_t *needed) {
     sbp_ctx *ctx = s->ctx;
     const int64_t n = s->n;
     bool wide = m < 256;
+    if (!wide && n >= 4096 && g_near_filter) {
+        // filtered path: centred fp32 shadow + packed scan, exact fp64 decision of the groups
+        // that pass (k_near_filtered); same counts -> scan -> fill structure as below
+        constexpr int DD = XY ? 2 : D;
+        constexpr int NW = 2, FT = filter_tile(DD);
+        const int QPB = NW * 32 * FILTER_Q;
+        const int64_t qblocks = (m + QPB - 1) / QPB;
+        const int64_t tiles = (n + FT - 1) / FT;
+        int64_t FS = (16 * (int64_t)ctx->sm_count + qblocks - 1) / qblocks;
+        if (FS > tiles) FS = tiles;
+        if (FS > 256) FS = 256;
+        if (FS < 1) FS = 1;
+        const int64_t chunk = (tiles + FS - 1) / FS * FT;
+        FS = (n + chunk - 1) / chunk;
+        const int64_t cap32 = tiles * FT, L = m * FS;
+        void *ws = nullptr, *shbuf = nullptr;
+        int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
+        if (rc) return rc;
+        const size_t hdr = 64 + 128 + (size_t)BOUNDS_BLOCKS * 2 * DD * sizeof(double);
+        rc = sbp_ctx_scratch(ctx, 10, hdr + (size_t)(DD + 1) * cap32 * sizeof(float), &shbuf);
+        if (rc) return rc;
+        double *info = (double *)shbuf, *bnd = (double *)((char *)shbuf + 64),
+               *partial = (double *)((char *)shbuf + 64 + 128);
+        float *shadow = (float *)((char *)shbuf + hdr);
+        int64_t *counts = (int64_t *)ws, *offsets = counts + L;
+        k_bounds_partial<DD><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
+        k_bounds_fold<DD><<<1, 32, 0, ctx->stream>>>(partial, BOUNDS_BLOCKS, bnd);
+        int sb = (int)((cap32 + 255) / 256);
+        if (sb > ctx->sm_count * 8) sb = ctx->sm_count * 8;
+        k_shadow_centered<DD><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, bnd, cap32, shadow, info);
+        dim3 fgrid((unsigned)qblocks, (unsigned)FS);
+        k_near_filtered<D, XY, 0, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
+            shadow, info, cap32, s->d_soa, s->capacity, n, (int)FS, chunk, X, m, thr, closed, counts,
+            offsets, idx, idx_capacity, needed);
+        k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, L, (int)FS, m, offsets, row_ptr, needed);
+        ctx->launches += 5;
+        SBP_CUDA(cudaGetLastError());
+        if (idx && idx_capacity > 0) {
+            k_near_filtered<D, XY, 1, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
+                shadow, info, cap32, s->d_soa, s->capacity, n, (int)FS, chunk, X, m, thr, closed, counts,
+                offsets, idx, idx_capacity, needed);
+            ctx->launches++;
+            SBP_CUDA(cudaGetLastError());
+        }
+        return SBP_OK;
+    }
     int S, tpb = 128;
     if (wide) {
         int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;

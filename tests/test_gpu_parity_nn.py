@@ -384,3 +384,41 @@ def test_knn_seeds_in_sparse_pockets_and_far_queries(sg):
         idx, dist = t.knn(X, k)
         oi, od = orc.knn(poses, X, k)
         assert np.array_equal(idx, oi) and np.array_equal(dist, od), k
+
+
+@pytest.mark.parametrize("d", [2, 3, 4, 6])
+def test_near_filtered_scan_never_changes_results(sg, d):
+    """Filtered radius query (centred fp32 shadow + packed scan, exact fp64 decision of the
+    groups that pass): row pointers and index lists equal the oracle's and the unfiltered
+    kernels' for both metrics and comparisons, for radii from 0 to larger than the cloud, on
+    lattice data where d == r happens, with an unfilterable outlier node and with queries
+    that are NaN, far away or beyond fp32 range."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(40 + d)
+    n, m = 23_456, 700
+    poses = np.floor(rng.random((n, d)) * 250)
+    X = np.floor(rng.random((m, d)) * 250)
+    X[5] = np.nan
+    X[6, 0] = 1e300
+    X[7] = -4000.0
+    X[8, 1] = np.inf
+    lib = _lib.load()
+    for variant in ("plain", "outlier"):
+        if variant == "outlier":
+            poses = poses.copy()
+            poses[123] = 1e14            # the band E exceeds r^2: every query becomes unfilterable
+        t = sg.NodeStore(d)
+        t.extend(poses)
+        try:
+            for metric in ("full", "xy"):
+                for closed in (False, True):
+                    for r in (0.0, 5.0, 13.0, 1000.0) if variant == "plain" else (13.0,):
+                        orp, oix = orc.near(poses, X, r, metric, closed)
+                        for filt in (1, 0):
+                            lib.sbp_tune(b"near_filter", filt)
+                            rp, ix = t.near(X, r, metric, closed)
+                            assert np.array_equal(rp, orp), (variant, metric, closed, r, filt)
+                            assert np.array_equal(ix, oix), (variant, metric, closed, r, filt)
+        finally:
+            lib.sbp_tune(b"near_filter", 1)
