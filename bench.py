@@ -166,12 +166,8 @@ def run_ours(args):
     names = ("knn", "edges", "visible", "gather")
 
     def gather(nbr, vis):
-        if world > 1:
-            nb_all = torch.empty((world * m, k), dtype=torch.int64, device=dev)
-            vs_all = torch.empty((world * m, k), dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(nb_all, nbr)
-            dist.all_gather_into_tensor(vs_all, vis.to(torch.uint8))
-            gathered["nbr"], gathered["vis"] = nb_all, vs_all
+        if world > 1:        # one packed int32 all-gather assembles the adjacency on every rank
+            gathered["packed"] = sg.distributed.all_gather_adjacency(nbr, vis, unpack=False)
         else:
             gathered["nbr"], gathered["vis"] = nbr, vis
 
@@ -450,7 +446,7 @@ def run_ours(args):
                              "library (PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms "
                              "come from the same step launched eagerly",
                    "multi_gpu": "rank r connects batch r of 50000 samples to the replicated roadmap; "
-                                "NCCL all-gather of the neighbour/visibility blocks inside the step"},
+                                "one NCCL all-gather of the packed neighbour/visibility blocks inside the step"},
         "clocks": clocks,
         "e2e": {"value": world * edges_per_rank * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,

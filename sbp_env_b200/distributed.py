@@ -47,6 +47,41 @@ def all_gather_rows(local, counts, group=None):
     return torch.cat(parts, 0)
 
 
+def pack_adjacency(nbr, vis):
+    """One int32 per candidate edge: ``(nbr + 1) * 2 + vis`` (nbr in [-1, 2^30)), so that the
+    neighbour block and its visibility mask travel in ONE collective of 4 bytes per edge
+    instead of two of 8 + 1."""
+    import torch
+
+    return (((nbr + 1) << 1) | vis.to(nbr.dtype)).to(torch.int32)
+
+
+def unpack_adjacency(code):
+    """Inverse of :func:`pack_adjacency`: ``(nbr int64, vis bool)``."""
+    import torch
+
+    return (code >> 1).to(torch.int64) - 1, (code & 1).bool()
+
+
+def all_gather_adjacency(nbr, vis, counts=None, group=None, unpack=True):
+    """All-gather of the per-rank (nbr, vis) row blocks as one packed int32 collective.
+    ``counts`` (rows per rank) is only needed when the blocks differ in length.  With
+    ``unpack=False`` the packed int32 adjacency is returned as is (decode it where it is
+    consumed with :func:`unpack_adjacency`)."""
+    import torch
+    import torch.distributed as dist
+
+    code = pack_adjacency(nbr, vis)
+    if counts is None or len(set(int(c) for c in counts)) == 1:
+        world = dist.get_world_size(group)
+        out = torch.empty((world * code.shape[0],) + tuple(code.shape[1:]), dtype=code.dtype,
+                          device=code.device)
+        dist.all_gather_into_tensor(out, code, group=group)
+    else:
+        out = all_gather_rows(code, counts, group=group)
+    return unpack_adjacency(out) if unpack else out
+
+
 def sharded_visible_batch(visible_fn, P, Q, group=None, costs=None):
     """Every rank holds the full edge list (P, Q); each checks its chunk with
     ``visible_fn`` and the masks are all-gathered, so every rank returns the full mask.
@@ -82,6 +117,4 @@ def sharded_prm_connect(connect_fn, n_nodes: int, group=None):
     first, count = shard_range(n_nodes, rank, world)
     nbr, vis = connect_fn(first, count)
     counts = [shard_range(n_nodes, r, world)[1] for r in range(world)]
-    nbr_all = all_gather_rows(nbr.to(torch.int64), counts, group=group)
-    vis_all = all_gather_rows(vis.to(torch.uint8), counts, group=group).bool()
-    return nbr_all, vis_all
+    return all_gather_adjacency(nbr.to(torch.int64), vis, counts, group=group)
