@@ -11,7 +11,7 @@ from .engine import Engine, ImageEngine, RobotArmEngine, euclidean_dist  # noqa:
 from .node_store import NodeStore  # noqa: F401
 from .planning import (CapturedStep, PRMConnectGraph, feasible_batch, knn, near,  # noqa: F401
                        prm_connect_knn, prm_connect_radius, roadmap_edges_to_host, visible_batch)
-from . import distributed, planner_ops  # noqa: F401
+from . import distributed, planner_ops, samplers  # noqa: F401
 from .stats import Stats  # noqa: F401
 
 __version__ = "0.1.0"

@@ -107,6 +107,34 @@ class _GridChecker(CollisionChecker):
         # (tests/test_rrtPlanner.py:31-33); batched calls must honour them
         return name in self.__dict__
 
+    # ---- sampler pre-screening ------------------------------
+    _dim = 2
+
+    def prescreen(self, P) -> np.ndarray:
+        """Decide a whole bucket of candidate states with ONE ``feasible_batch`` launch and
+        remember the answers: a later ``feasible(p)`` whose ``p`` is bit-identical to a row
+        of ``P`` returns the remembered value without touching the device.
+
+        The reference's samplers draw 10 000 states at a time (``RandomnessManager``,
+        randomness.py:150-190) and then test them one by one
+        (``Sampler.get_valid_next_pos``, samplers/baseSampler.py:58-66): pre-screening the
+        bucket when it is drawn (:func:`sbp_env_b200.samplers.attach_prescreen`) turns
+        ~2 launches per accepted node into one per 10 000 draws, with the same draws in the
+        same order and the same ``Stats`` counts.  Returns the bool array; a bucket with
+        non-finite rows is not remembered (``feasible`` must raise for those rows)."""
+        P = as_host_f64(P, self._dim)
+        try:
+            ok = self._feasible_host(P)
+        except (ValueError, OverflowError):
+            self.__dict__.pop("_prescreened", None)
+            raise
+        self._prescreened = {row.tobytes(): bool(v) for row, v in zip(P, ok)}
+        return ok
+
+    def _remembered(self, pt: np.ndarray):
+        cache = self.__dict__.get("_prescreened")
+        return None if cache is None else cache.get(pt.tobytes())
+
 
 class ImgCollisionChecker(_GridChecker):
     """2-D image-space checker (collisionChecker.py:83-215) on the GPU."""
@@ -144,6 +172,9 @@ class ImgCollisionChecker(_GridChecker):
         if save_stats:
             self.stats.feasible_cnt += 1
         pt = np.array([float(p[0]), float(p[1])], dtype=np.float64).reshape(1, 2)
+        hit = self._remembered(pt)
+        if hit is not None:
+            return np.bool_(hit)
         return np.bool_(self._feasible_host(pt)[0])
 
     def visible(self, pos1, pos2):
@@ -303,6 +334,8 @@ class RobotArm4dCollisionChecker(_GridChecker):
     """4-D (x, y, r0, r1) two-link stick arm in image space (collisionChecker.py:299-503)
     on the GPU."""
 
+    _dim = 4
+
     def __init__(self, img, map_mat: typing.Optional[np.ndarray] = None,
                  stick_robot_length_config: typing.Optional[typing.Sequence[float]] = None,
                  device: int = 0):
@@ -366,6 +399,9 @@ class RobotArm4dCollisionChecker(_GridChecker):
         if save_stats:
             self.stats.feasible_cnt += 1
         c = np.array([float(v) for v in p[:4]], dtype=np.float64).reshape(1, 4)
+        hit = self._remembered(c)
+        if hit is not None:
+            return hit
         return bool(self._feasible_host(c)[0])
 
     @staticmethod

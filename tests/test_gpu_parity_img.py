@@ -217,3 +217,55 @@ def test_stats_mock_deepcopy_pickle(sg):
 def test_empty_batches(kat):
     assert kat.visible_batch(np.zeros((0, 2)), np.zeros((0, 2))).shape == (0,)
     assert kat.feasible_batch(np.zeros((0, 2))).shape == (0,)
+
+
+def test_prescreen_bucket_answers_feasible_without_launch(sg):
+    """cc.prescreen(bucket) is one feasible_batch launch; feasible(p) of a
+    row is then answered from the remembered booleans (same value, same Stats count), other
+    points still go to the device, and a bucket with a NaN row is refused like feasible(NaN)."""
+    from sbp_env_b200 import samplers
+
+    name = "room1"
+    eng = sg.ImageEngine(None, map_png(name))
+    cc = eng.cc
+    om = orc.Map(load_map(name))
+    rng = np.random.default_rng(11)
+    W, H = load_map(name).shape
+    bucket = rng.random((10000, 2)) * [W, H]
+    want = om.feasible2d(bucket)
+    launches = []
+    inner = cc._feasible_host
+    cc._feasible_host = lambda P: (launches.append(len(P)), inner(P))[1]
+    try:
+        got = cc.prescreen(bucket)
+        assert np.array_equal(got, want) and launches == [10000]
+        before = cc.stats.feasible_cnt
+        for i in (0, 17, 9999, 4242):
+            assert bool(cc.feasible(bucket[i])) == bool(want[i])
+        assert launches == [10000] and cc.stats.feasible_cnt == before + 4
+        assert bool(cc.feasible((100.5, 100.25))) == bool(om.feasible2d(np.array([[100.5, 100.25]]))[0])
+        assert launches == [10000, 1]
+        bad = bucket.copy()
+        bad[3, 0] = np.nan
+        with pytest.raises(ValueError):
+            cc.prescreen(bad)
+        with pytest.raises(ValueError):
+            cc.feasible(bad[3])
+
+        # the hook on a RandomnessManager look-alike: every redraw pre-screens the new bucket
+        class RM:
+            def __init__(self):
+                self.random_draws = {}
+
+            def redraw(self, method):
+                self.random_draws[method] = rng.random((500, 2))
+
+        assert eng.upper.tolist() == [W, H]
+        rm = samplers.attach_prescreen(RM(), eng)
+        rm.redraw("pseudo_random")
+        assert launches[-1] == 500
+        n0 = len(launches)
+        p = eng.transform(rm.random_draws["pseudo_random"][-1])
+        assert bool(cc.feasible(p)) == bool(om.feasible2d(p.reshape(1, 2))[0]) and len(launches) == n0
+    finally:
+        del cc._feasible_host

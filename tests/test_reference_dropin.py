@@ -103,7 +103,7 @@ def make_args(planner_id, engine_factory, start, goal, max_nodes, **kw):
     return args
 
 
-def run(planner_id, engine_factory, swap_cc, start, goal, max_nodes, **kw):
+def run(planner_id, engine_factory, swap_cc, start, goal, max_nodes, before_run=None, **kw):
     from sbp_env.env import Env
     from sbp_env.utils.common import Stats
 
@@ -112,6 +112,8 @@ def run(planner_id, engine_factory, swap_cc, start, goal, max_nodes, **kw):
     if swap_cc is not None:
         args.engine.cc = swap_cc(args.engine.cc)
     env = Env(args, fixed_seed=0)
+    if before_run is not None:
+        before_run(env)
     stats = env.run()
     pl = env.planner
     n = len(pl.nodes)
@@ -139,6 +141,38 @@ def test_seeded_2d_runs_identical(ref, planner_id):
     b = run(planner_id, fac, lambda cc: ImgCollisionChecker(cc.image_fname), "100,100", "350,350", 250)
     _same(a, b)
     assert a["counters"][2] >= 250            # valid samples (Bi-RRT splits them over two trees)
+
+
+def test_sampler_prescreen_keeps_the_seeded_run_and_saves_launches(ref, monkeypatch):
+    """pre-screening each 10 000-draw bucket of the reference's
+    RandomnessManager (one feasible_batch launch) leaves the seeded run -- draws, accepted
+    nodes, c_max, Stats counters -- identical, while the per-state feasible() launches of the
+    sampling loop disappear."""
+    from sbp_env import engine
+    import sbp_env_b200 as sg
+    import sbp_env_b200.collision_checker as gcc
+
+    img = ref_shims.reference_map_path("room1.png")
+    fac = lambda args: engine.ImageEngine(args, img)
+    swap = lambda cc: sg.ImgCollisionChecker(cc.image_fname)
+    launches = []
+    inner = gcc.ImgCollisionChecker._feasible_host
+
+    def counting(self, P):
+        launches.append(len(P))
+        return inner(self, P)
+
+    monkeypatch.setattr(gcc.ImgCollisionChecker, "_feasible_host", counting)
+    a = run("rrt", fac, swap, "100,100", "350,350", 250)
+    plain = list(launches)
+    del launches[:]
+    b = run("rrt", fac, swap, "100,100", "350,350", 250,
+            before_run=lambda env: sg.samplers.attach_prescreen_to_sampler(env.args.sampler))
+    _same(a, b)
+    assert max(plain) == 1 and len(plain) > 250               # one launch per tested state
+    assert launches.count(10000) >= 1                          # the bucket, in one launch
+    # what is left are the goal-biased draws (goal_pos is not a bucket row) and env checks
+    assert len(launches) < len(plain) // 5
 
 
 def test_seeded_arm_run_identical(ref):
