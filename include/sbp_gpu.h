@@ -56,6 +56,7 @@ extern "C" {
 typedef struct sbp_ctx sbp_ctx;
 typedef struct sbp_map sbp_map;
 typedef struct sbp_nodes sbp_nodes;
+typedef struct sbp_graph sbp_graph;
 
 int32_t sbp_abi_version(void);
 const char *sbp_last_error(void);
@@ -228,6 +229,36 @@ int32_t sbp_nodes_near_visible_host(sbp_nodes *nodes, sbp_map *map, int32_t arm,
                                     int32_t closed, int32_t direction, int64_t *out_idx,
                                     uint8_t *out_vis, int32_t cap, int32_t *n_hits,
                                     int32_t *flags);
+
+/* ---- roadmap graph ------------------------------- */
+/* The PRM roadmap as a device-resident CSR graph.
+ * replaces: the networkx DiGraph PRMPlanner.build_graph fills edge by edge
+ * (prmPlanner.py:91-101, `graph.add_weighted_edges_from([(m_g, v, dist)])`) and the
+ * nx.has_path / nx.shortest_path query of PRMPlanner.get_solution (prmPlanner.py:128-154;
+ * unweighted: fewest hops).  Edge weights are engine.dist of the end poses and are
+ * recomputed from the node store where a cost is needed. */
+int32_t sbp_graph_create(sbp_ctx *ctx, int64_t n_nodes, sbp_graph **out);
+int32_t sbp_graph_destroy(sbp_graph *g);
+/* (Re)build from a candidate-edge block of sbp_nodes_knn_edges + the visibility bytes of
+ * sbp_visible2d / sbp_arm_visible (device pointers, [m][k]): for row i and column j with
+ * vis != 0 and nbr >= 0 the directed edge nbr[i][j] -> first_row + i (m_g -> v). */
+int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis, int64_t m,
+                            int32_t k, int64_t first_row);
+/* (Re)build from explicit edge lists src[e] -> dst[e] (device), `keep` an optional mask. */
+int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,
+                              const uint8_t *keep, int64_t e);
+int32_t sbp_graph_info(sbp_graph *g, int64_t *n_nodes, int64_t *n_edges);   /* synchronises */
+/* Copy the CSR arrays to device buffers row_ptr [n_nodes + 1], col [col_capacity >= n_edges]
+ * (col may be NULL); the order of a row's entries is unspecified. */
+int32_t sbp_graph_csr(sbp_graph *g, int64_t *row_ptr, int32_t *col, int64_t col_capacity);
+/* Batched fewest-hop paths start[q] -> goal[q] (device int64 [nq]), one CTA per query.
+ * hops [nq]: number of edges, 0 when start == goal, -1 when unreachable (nx.has_path False)
+ * or an index is out of range.  paths (optional) [nq][max_len]: node indices start..goal,
+ * -1 padded; all -1 when there is no path or it has more than max_len nodes.  Among the
+ * fewest-hop paths the one whose every node has the lowest-index predecessor on the previous
+ * BFS level is returned (deterministic; networkx returns an adjacency-order dependent one). */
+int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64_t *goal, int64_t nq,
+                      int32_t *hops, int64_t *paths, int32_t max_len);
 
 #ifdef __cplusplus
 }

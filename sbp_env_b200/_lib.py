@@ -69,6 +69,13 @@ _SIGNATURES = {
                                _i32, _vp, _vp],
     "sbp_nodes_near_visible_host": [_vp, _vp, _i32, _dbl, _dbl, _vp, _dbl, _i32, _i32, _i32, _vp, _vp,
                                     _i32, C.POINTER(_i32), C.POINTER(_i32)],
+    "sbp_graph_create": [_vp, _i64, C.POINTER(_vp)],
+    "sbp_graph_destroy": [_vp],
+    "sbp_graph_build_knn": [_vp, _vp, _vp, _i64, _i32, _i64],
+    "sbp_graph_build_edges": [_vp, _vp, _vp, _vp, _i64],
+    "sbp_graph_info": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
+    "sbp_graph_csr": [_vp, _vp, _vp, _i64],
+    "sbp_graph_bfs": [_vp, _vp, _vp, _i64, _vp, _vp, _i32],
     "sbp_tune": [C.c_char_p, _i64],
     "sbp_microbench": [_vp, _i32, _i64, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
     "sbp_ctx_kernel_time": [_vp, C.POINTER(_dbl), C.POINTER(_i64)],

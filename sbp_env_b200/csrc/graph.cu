@@ -1,0 +1,332 @@
+// graph.cu -- K7: the PRM roadmap as a device-resident CSR graph and batched hop-count
+// shortest paths on it.
+//
+// Reference behaviour restated (file:line under /root/reference/sbp_env/planners/):
+//   PRMPlanner.build_graph    prmPlanner.py:91-101   directed edges m_g -> v into a networkx
+//                                                    DiGraph for every visible candidate pair
+//   PRMPlanner.get_solution   prmPlanner.py:128-154  nx.has_path / nx.shortest_path(graph,
+//                                                    start, goal): UNWEIGHTED, fewest hops
+//                                                    (no weight= argument, :143)
+//
+// Layout: row_ptr int64 [n + 1], col int32 [E]; row u lists the heads v of the edges u -> v
+// (order inside a row is arbitrary: the search below does not depend on it).
+//
+// Search: one CTA per (start, goal) query, level-synchronous BFS over a CTA-private work-space
+// (level and parent arrays, FIFO of touched nodes; only touched entries are reset between
+// queries).  Among the fewest-hop paths networkx returns whichever its bidirectional search
+// meets first (adjacency-order dependent); here the path is made deterministic instead: the
+// parent of v is the LOWEST-INDEX node of the previous level with an edge to v (atomicMin), so
+// the result does not depend on thread timing or on the order of `col`.  Hop counts and
+// reachability are exactly networkx's; the path is one of the shortest ones.
+#include "common.cuh"
+
+struct sbp_graph {
+    sbp_ctx *ctx = nullptr;
+    int64_t n = 0, e = 0, e_capacity = 0;
+    int64_t *d_row_ptr = nullptr;    // [n + 1]
+    int32_t *d_col = nullptr;        // [e_capacity]
+    int32_t *d_deg = nullptr;        // [n + 1] degree counts, then scatter cursors
+    int64_t *d_total = nullptr;      // device scalar: number of edges of the last build
+    // BFS work-space, grown on demand: per CTA slot level [n], parent [n], queue [n]
+    int32_t *d_work = nullptr;
+    int64_t work_slots = 0;
+};
+
+extern "C" int32_t sbp_graph_create(sbp_ctx *ctx, int64_t n_nodes, sbp_graph **out) {
+    SBP_REQUIRE(ctx && out, "sbp_graph_create: NULL argument");
+    SBP_REQUIRE(n_nodes >= 0 && n_nodes < ((int64_t)1 << 31), "sbp_graph_create: bad node count");
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    sbp_graph *g = new sbp_graph();
+    g->ctx = ctx;
+    g->n = n_nodes;
+    cudaError_t e = cudaMalloc(&g->d_row_ptr, (size_t)(n_nodes + 1) * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_deg, (size_t)(n_nodes + 1) * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_total, sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_row_ptr, 0, (size_t)(n_nodes + 1) * sizeof(int64_t), ctx->stream);
+    if (e != cudaSuccess) {
+        sbp_set_error("sbp_graph_create: %s", cudaGetErrorString(e));
+        delete g;
+        return SBP_ERR_CUDA;
+    }
+    *out = g;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_graph_destroy(sbp_graph *g) {
+    if (!g) return SBP_OK;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    if (g->d_row_ptr) cudaFree(g->d_row_ptr);
+    if (g->d_col) cudaFree(g->d_col);
+    if (g->d_deg) cudaFree(g->d_deg);
+    if (g->d_total) cudaFree(g->d_total);
+    if (g->d_work) cudaFree(g->d_work);
+    delete g;
+    return SBP_OK;
+}
+
+// ----------------------------------------------------------------- build ----
+// Edge t of a kNN block: row = first_row + t / k (the node v whose neighbours were searched),
+// neighbour m_g = nbr[t]; the reference adds m_g -> v (prmPlanner.py:99-101).
+// Edge t of an explicit list: src[t] -> dst[t].  `keep` (optional) masks candidates out.
+struct EdgeSource {
+    const int64_t *nbr;      // kNN block, or src list
+    const int64_t *dst;      // NULL for a kNN block
+    const uint8_t *keep;     // optional
+    int64_t total;
+    int32_t k;
+    int64_t first_row, n;
+    __device__ __forceinline__ bool edge(int64_t t, int64_t &u, int64_t &v) const {
+        if (keep && !keep[t]) return false;
+        u = nbr[t];
+        v = dst ? dst[t] : first_row + t / k;
+        return u >= 0 && u < n && v >= 0 && v < n;
+    }
+};
+
+__global__ void k_graph_degree(EdgeSource es, int32_t *__restrict__ deg) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < es.total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t u, v;
+        if (es.edge(t, u, v)) atomicAdd(deg + u, 1);
+    }
+}
+
+// Exclusive scan of deg[n] -> row_ptr[n + 1] (single CTA, serial segments; the build is a
+// one-off per roadmap); deg is turned into the scatter cursor (all zeros again).
+__global__ void __launch_bounds__(1024)
+k_graph_scan(int32_t *__restrict__ deg, int64_t n, int64_t *__restrict__ row_ptr,
+             int64_t *__restrict__ total) {
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x;
+    const int64_t seg = (n + 1023) / 1024;
+    const int64_t a = (int64_t)tid * seg, b = a + seg < n ? a + seg : n;
+    int64_t sum = 0;
+    for (int64_t t = a; t < b; ++t) sum += deg[t];
+    part[tid] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int64_t v = tid >= o ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int64_t run = part[tid] - sum;
+    for (int64_t t = a; t < b; ++t) {
+        row_ptr[t] = run;
+        run += deg[t];
+        deg[t] = 0;
+    }
+    if (tid == 1023) { row_ptr[n] = part[1023]; *total = part[1023]; }
+}
+
+__global__ void k_graph_scatter(EdgeSource es, const int64_t *__restrict__ row_ptr,
+                                int32_t *__restrict__ cursor, int32_t *__restrict__ col) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < es.total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t u, v;
+        if (es.edge(t, u, v)) col[row_ptr[u] + atomicAdd(cursor + u, 1)] = (int32_t)v;
+    }
+}
+
+static int32_t graph_build(sbp_graph *g, EdgeSource es) {
+    sbp_ctx *ctx = g->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    es.n = g->n;
+    // every candidate may become an edge: size `col` for all of them (no host round trip)
+    if (es.total > g->e_capacity) {
+        SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (g->d_col) SBP_CUDA(cudaFree(g->d_col));
+        g->d_col = nullptr;
+        g->e_capacity = 0;
+        SBP_CUDA(cudaMalloc(&g->d_col, (size_t)(es.total > 0 ? es.total : 1) * sizeof(int32_t)));
+        g->e_capacity = es.total;
+    }
+    SBP_CUDA(cudaMemsetAsync(g->d_deg, 0, (size_t)(g->n + 1) * sizeof(int32_t), ctx->stream));
+    int blocks = (int)((es.total + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_graph_degree<<<blocks, 256, 0, ctx->stream>>>(es, g->d_deg);
+    k_graph_scan<<<1, 1024, 0, ctx->stream>>>(g->d_deg, g->n, g->d_row_ptr, g->d_total);
+    k_graph_scatter<<<blocks, 256, 0, ctx->stream>>>(es, g->d_row_ptr, g->d_deg, g->d_col);
+    ctx->launches += 3;
+    SBP_CUDA(cudaGetLastError());
+    g->e = -1;                       // known on the device; fetched lazily by sbp_graph_info
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis, int64_t m,
+                                       int32_t k, int64_t first_row) {
+    SBP_REQUIRE(g && (m == 0 || nbr), "sbp_graph_build_knn: NULL argument");
+    SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_graph_build_knn: bad sizes");
+    EdgeSource es{nbr, nullptr, vis, m * k, k, first_row, g->n};
+    return graph_build(g, es);
+}
+
+extern "C" int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,
+                                         const uint8_t *keep, int64_t e) {
+    SBP_REQUIRE(g && (e == 0 || (src && dst)), "sbp_graph_build_edges: NULL argument");
+    SBP_REQUIRE(e >= 0, "sbp_graph_build_edges: e < 0");
+    EdgeSource es{src, dst, keep, e, 1, 0, g->n};
+    return graph_build(g, es);
+}
+
+extern "C" int32_t sbp_graph_info(sbp_graph *g, int64_t *n_nodes, int64_t *n_edges) {
+    SBP_REQUIRE(g, "sbp_graph_info: NULL argument");
+    if (g->e < 0) {
+        SBP_CUDA(cudaSetDevice(g->ctx->device));
+        SBP_CUDA(cudaMemcpyAsync(&g->e, g->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                 g->ctx->stream));
+        SBP_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    }
+    if (n_nodes) *n_nodes = g->n;
+    if (n_edges) *n_edges = g->e;
+    return SBP_OK;
+}
+
+// Copy the CSR arrays out (device buffers: row_ptr [n + 1], col [>= n_edges]).
+extern "C" int32_t sbp_graph_csr(sbp_graph *g, int64_t *row_ptr, int32_t *col, int64_t col_capacity) {
+    SBP_REQUIRE(g && row_ptr, "sbp_graph_csr: NULL argument");
+    int64_t e = 0;
+    int32_t rc = sbp_graph_info(g, nullptr, &e);
+    if (rc) return rc;
+    SBP_REQUIRE(!col || col_capacity >= e, "sbp_graph_csr: col buffer too small");
+    SBP_CUDA(cudaMemcpyAsync(row_ptr, g->d_row_ptr, (size_t)(g->n + 1) * sizeof(int64_t),
+                             cudaMemcpyDeviceToDevice, g->ctx->stream));
+    if (col && e > 0)
+        SBP_CUDA(cudaMemcpyAsync(col, g->d_col, (size_t)e * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                 g->ctx->stream));
+    return SBP_OK;
+}
+
+// ------------------------------------------------------------------- BFS ----
+#define BFS_TPB 512
+#define BFS_UNSET 0x7fffffff
+
+// Queries q = blockIdx.x, blockIdx.x + gridDim.x, ... ; work-space slot = blockIdx.x.
+//   level[v]  = -1 untouched, else BFS level of v (start = 0)
+//   parent[v] = lowest-index predecessor on the previous level (BFS_UNSET until touched)
+//   queue     = touched nodes in level order
+__global__ void __launch_bounds__(BFS_TPB)
+k_graph_bfs(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int64_t n,
+            const int64_t *__restrict__ start, const int64_t *__restrict__ goal, int64_t nq,
+            int32_t *__restrict__ work, int32_t *__restrict__ hops, int64_t *__restrict__ paths,
+            int32_t max_len) {
+    int32_t *level = work + (int64_t)blockIdx.x * 3 * n, *parent = level + n, *queue = parent + n;
+    __shared__ int s_tail, s_found;
+    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+        const int64_t s = start[q], t = goal[q];
+        const bool ok = s >= 0 && s < n && t >= 0 && t < n;
+        int head = 0, tail = 0, lvl = 0;
+        if (threadIdx.x == 0) {
+            s_found = 0;
+            s_tail = 0;
+            if (ok) {
+                level[s] = 0;
+                queue[0] = (int32_t)s;
+                s_tail = 1;
+                if (s == t) s_found = 1;
+            }
+        }
+        __syncthreads();
+        tail = s_tail;
+        bool found = s_found != 0;
+        __syncthreads();
+        // expand level by level; the level in which the goal is touched is completed, so that
+        // its parent is the minimum over the whole previous level.  s_tail / s_found are read
+        // into registers between two barriers: every thread takes the same decision.
+        while (head < tail && !found) {
+            for (int i = head + threadIdx.x; i < tail; i += BFS_TPB) {
+                const int32_t u = queue[i];
+                const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
+                for (int64_t e = e0; e < e1; ++e) {
+                    const int32_t v = col[e];
+                    int32_t lv = __ldcg(level + v);
+                    if (lv < 0) {
+                        lv = atomicCAS(level + v, -1, lvl + 1);
+                        if (lv < 0) {                            // first touch: enqueue
+                            queue[atomicAdd(&s_tail, 1)] = v;
+                            lv = lvl + 1;
+                            if (v == t) s_found = 1;
+                        }
+                    }
+                    if (lv == lvl + 1) atomicMin(parent + v, u);
+                }
+            }
+            __syncthreads();
+            head = tail;
+            tail = s_tail;
+            found = s_found != 0;
+            ++lvl;
+            __syncthreads();
+        }
+        found = ok && found;
+        if (threadIdx.x == 0) {
+            const int32_t h = found ? __ldcg(level + t) : -1;
+            hops[q] = h;
+            if (paths && h >= 0 && h + 1 <= max_len) {
+                int64_t *p = paths + q * (int64_t)max_len;
+                int32_t v = (int32_t)t;
+                for (int i = h; i >= 0; --i) {
+                    p[i] = v;
+                    v = __ldcg(parent + v);
+                }
+                for (int i = h + 1; i < max_len; ++i) p[i] = -1;
+            } else if (paths) {
+                for (int i = 0; i < max_len; ++i) paths[q * (int64_t)max_len + i] = -1;
+            }
+        }
+        __syncthreads();
+        // reset only what this query touched
+        for (int i = threadIdx.x; i < tail; i += BFS_TPB) {
+            const int32_t v = queue[i];
+            level[v] = -1;
+            parent[v] = BFS_UNSET;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void k_graph_work_init(int32_t *__restrict__ work, int64_t n, int64_t slots) {
+    const int64_t total = slots * 3 * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = t % (3 * n);
+        work[t] = r < n ? -1 : BFS_UNSET;        // level | parent, queue (queue content is irrelevant)
+    }
+}
+
+// For every query q: fewest-hop path start[q] -> goal[q] along the directed edges.
+//   hops[q]  = number of edges, 0 when start == goal, -1 when unreachable / out of range
+//   paths    = optional [nq][max_len] node indices start..goal, -1 padded; all -1 when the path
+//              does not fit (hops[q] + 1 > max_len) or does not exist
+// start / goal / hops / paths are device pointers.
+extern "C" int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64_t *goal, int64_t nq,
+                                 int32_t *hops, int64_t *paths, int32_t max_len) {
+    SBP_REQUIRE(g && (nq == 0 || (start && goal && hops)), "sbp_graph_bfs: NULL argument");
+    SBP_REQUIRE(nq >= 0 && (!paths || max_len >= 1), "sbp_graph_bfs: bad sizes");
+    if (nq == 0) return SBP_OK;
+    sbp_ctx *ctx = g->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_REQUIRE(g->n > 0, "sbp_graph_bfs: empty graph");
+    // two CTAs per SM hide the latency of the dependent loads; bounded by 8 GiB of work-space
+    int64_t slots = 2 * (int64_t)ctx->sm_count;
+    if (slots > nq) slots = nq;
+    const int64_t per_slot = 3 * g->n * (int64_t)sizeof(int32_t);
+    while (slots > 1 && slots * per_slot > ((int64_t)8 << 30)) slots /= 2;
+    if (slots > g->work_slots) {
+        SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (g->d_work) SBP_CUDA(cudaFree(g->d_work));
+        g->d_work = nullptr;
+        g->work_slots = 0;
+        SBP_CUDA(cudaMalloc(&g->d_work, (size_t)(slots * per_slot)));
+        g->work_slots = slots;
+        k_graph_work_init<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_work, g->n, slots);
+        ctx->launches++;
+    }
+    k_graph_bfs<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, start, goal,
+                                                             nq, g->d_work, hops, paths, max_len);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}

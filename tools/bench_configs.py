@@ -355,6 +355,39 @@ def cfg5():
     tq = timeit(lambda: sg.prm_connect_knn(cc, tree, k, queries=SG))
     out["connect_4096_start_goal_pairs"] = {"ms": tq * 1e3, "queries": 8192,
                                             "dist_evals_per_s": 8192 * 1e6 / tq}
+    # roadmap graph on the device: CSR assembly of the 10M candidate edges and
+    # the 4096 start/goal queries as fewest-hop searches (one CTA per query)
+    gm = sg.Roadmap(len(tree))
+    t_build = timeit(lambda: gm.build_from_knn(nbr, vis))
+    nq, kq = 4096, 1
+    nb_q, vis_q = sg.prm_connect_knn(cc, tree, kq, queries=SG)        # nearest roadmap node of each endpoint
+    ends = torch.where(vis_q[:, 0], nb_q[:, 0], torch.full_like(nb_q[:, 0], -1))
+    S, T = ends[:nq].contiguous(), ends[nq:].contiguous()
+    t_bfs = timeit(lambda: gm.shortest_paths(S, T, max_len=2048), reps=2)
+    hops, paths = gm.shortest_paths(S, T, max_len=2048)
+    hh = hops.cpu().numpy()
+    # spot check against networkx on the same edge list (a few queries: nx BFS on 8.7M edges is slow)
+    import networkx as nx
+
+    rp, col = gm.csr()
+    rp, col = rp.cpu().numpy(), col.cpu().numpy()
+    G = nx.DiGraph()
+    G.add_nodes_from(range(len(tree)))
+    G.add_edges_from(zip(np.repeat(np.arange(len(tree)), np.diff(rp)).tolist(), col.tolist()))
+    ok = True
+    Sh, Th = S.cpu().numpy(), T.cpu().numpy()
+    for q in range(8):
+        if Sh[q] < 0 or Th[q] < 0:
+            ok &= hh[q] == -1
+        elif nx.has_path(G, int(Sh[q]), int(Th[q])):
+            ok &= hh[q] == nx.shortest_path_length(G, int(Sh[q]), int(Th[q]))
+        else:
+            ok &= hh[q] == -1
+    out["roadmap_graph"] = {"nodes": len(tree), "edges": gm.n_edges, "csr_build_ms": t_build * 1e3,
+                            "bfs_4096_queries_ms": t_bfs * 1e3, "queries_per_s": nq / t_bfs,
+                            "reachable_fraction": float((hh >= 0).mean()),
+                            "mean_hops_reachable": float(hh[hh >= 0].mean()) if (hh >= 0).any() else None,
+                            "max_hops": int(hh.max()), "hops_parity_vs_networkx_8_queries": bool(ok)}
     return out
 
 
