@@ -348,16 +348,24 @@ def run_ours(args):
         return units.value / (ms.value / 1e3)
 
     fp64_peak = mb(2, 0, 4096)
-    # FMA-pipe model of the scan: d packed FFMA2 per 2 pairs (norm expansion), each occupying
-    # the fp32 pipe of its SM sub-partition for 2 cycles (64 lanes-FMAs on a 32-lane pipe), i.e.
-    # d pipe-cycles per warp-pair; peak = 4 sub-partitions x SM count x clock.
+    # FMA-pipe roofline of the scan: d fp32 FMAs per (query, node) pair (norm expansion, issued as
+    # packed FFMA2) against the MEASURED packed-FMA rate of this GPU (sbp_microbench 3: independent
+    # fma.rn.f32x2 chains; 127 FMA/clk/SM = the scalar FFMA rate as well).  The scan also needs
+    # ~1.1 min/compare lane-operations per pair (FMNMX3 runs at half the FMNMX rate, microbench 5/6)
+    # which share issue and, partly, datapath with the FMAs (microbench 7: 8 FFMA2 + 8 FMNMX take
+    # 20.7 cycles, not 16): `mixed_bound_frac` relates the kernel to that instruction mix.
+    fma_peak = mb(3, 0, 4096)
+    mix_rate = mb(7, 0, 4096)            # lane-instructions/s of the 1:1 FFMA2 : FMNMX mix
     sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-    pipe_peak = ctx.info()["sm_count"] * 4 * sm_hz * 1e6
-    roof["fma_pipe"] = {"model": "d = 2 FMA-pipe cycles per warp of 32 (query, node) pairs "
-                                 "(1 packed FFMA2 per pair, 2 cycles each)",
-                        "achieved_pipe_cycles_per_s": evals / 32 * 2 / filt_s,
-                        "peak_pipe_cycles_per_s": pipe_peak,
-                        "frac": evals / 32 * 2 / filt_s / pipe_peak,
+    # per warp and group of 8 nodes x 4 queries: 32 FFMA2 + 12 FMNMX3 (= 24 FMNMX slots) + 4 FMNMX
+    # + 7 FSETP ~ 32 packed + 35 ALU operations ~ 67 mixed instructions at the measured mix rate
+    mix_bound_s = evals / 32.0 * 67.0 / mix_rate
+    roof["fma_pipe"] = {"model": "d = 2 fp32 FMAs per (query, node) pair, packed FFMA2",
+                        "achieved_fma_per_s": evals * 2 / filt_s,
+                        "peak_fma_per_s_measured": fma_peak,
+                        "frac": evals * 2 / filt_s / fma_peak,
+                        "mixed_bound_ms": mix_bound_s * 1e3,
+                        "mixed_bound_frac": mix_bound_s / filt_s,
                         "dist_evals_per_s_kernel": evals / filt_s,
                         "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / knn_s,
                                             "measured_peak_unfused_fp64_ops_per_s": fp64_peak,

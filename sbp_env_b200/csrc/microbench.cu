@@ -49,8 +49,115 @@ __global__ void __launch_bounds__(256) k_mb_fp64(int iters, double *out) {
     if (a0 + a1 + a2 + a3 == 12345.678) out[0] = a0;
 }
 
+// which = 3 / 4: independent fp32 FMA chains, packed (fma.rn.f32x2 -> FFMA2, two FMAs per
+// lane and instruction, the filter scan's instruction) or scalar (FFMA): the measured
+// denominator of the kNN filter's FMA-pipe roofline.  8 independent accumulators per thread,
+// the multiplier a scalar broadcast as in the scan.
+__global__ void __launch_bounds__(256) k_mb_ffma2(int iters, float *out) {
+    uint64_t acc[8];
+    float q = 1.0000001f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = threadIdx.x * 1e-3f + i;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(v), "f"(v + 0.5f));
+    }
+    uint64_t q2, c2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(q2) : "f"(q));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(1e-9f));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(q2), "l"(c2));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi;
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) k_mb_ffma(int iters, float *out) {
+    float acc[16];
+    const float q = 1.0000001f, c = 1e-9f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(q), "f"(c));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+// which = 5 / 6: three-input (FMNMX3) and two-input (FMNMX) fp32 minima on independent
+// chains: the ALU-pipe denominator of the filter scan's min reduction.
+template <bool THREE>
+__global__ void __launch_bounds__(256) k_mb_fmin(int iters, float *out) {
+    float acc[16];
+    const float b = threadIdx.x * 0.5f + 3.f, c = threadIdx.x * 0.25f + 5.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = threadIdx.x * 1e-3f + i + 100.f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (THREE) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(b), "f"(c));
+                else asm volatile("min.f32 %0, %0, %1;" : "+f"(acc[i]) : "f"(b));
+            }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == 12345.678f) out[0] = s;
+}
+
+// which = 7: FFMA2 and FMNMX interleaved 1:1 on independent chains -- do the packed FMAs and
+// the minima share a datapath (times add) or overlap (the slower one hides the other)?
+__global__ void __launch_bounds__(256) k_mb_mix(int iters, float *out) {
+    uint64_t acc[8];
+    float mn[8];
+    const float b = threadIdx.x * 0.5f + 3.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float v = threadIdx.x * 1e-3f + i;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(v), "f"(v + 0.5f));
+        mn[i] = v + 100.f;
+    }
+    uint64_t q2, c2;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(q2) : "f"(1.0000001f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(1e-9f));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(q2), "l"(c2));
+                asm volatile("min.f32 %0, %0, %1;" : "+f"(mn[i]) : "f"(b));
+            }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+        s += lo + hi + mn[i];
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
 // Returns in *ms the average duration of one launch and in *units the number of
-// gathers (which 0/1) or fp64 operations (which 2) per launch.
+// gathers (which 0/1), fp64 operations (which 2) or fp32 FMAs (which 3/4) per launch.
 extern "C" int32_t sbp_microbench(sbp_ctx *ctx, int32_t which, int64_t bytes, int32_t iters,
                                   double *ms, double *units) {
     SBP_REQUIRE(ctx && ms && units, "sbp_microbench: NULL argument");
@@ -81,6 +188,22 @@ extern "C" int32_t sbp_microbench(sbp_ctx *ctx, int32_t which, int64_t bytes, in
             k_mb_gather<<<grid, 256, 0, ctx->stream>>>(buf, (uint64_t)bytes / 32, iters, d_out);
         SBP_CUDA(cudaEventRecord(e1, ctx->stream));
         *units = (double)grid * 256.0 * iters * 8.0;
+    } else if (which >= 3 && which <= 7) {
+        int grid = ctx->sm_count * 8;
+        auto launch = [&]() {
+            if (which == 3) k_mb_ffma2<<<grid, 256, 0, ctx->stream>>>(iters, (float *)d_out);
+            else if (which == 4) k_mb_ffma<<<grid, 256, 0, ctx->stream>>>(iters, (float *)d_out);
+            else if (which == 5) k_mb_fmin<true><<<grid, 256, 0, ctx->stream>>>(iters, (float *)d_out);
+            else if (which == 6) k_mb_fmin<false><<<grid, 256, 0, ctx->stream>>>(iters, (float *)d_out);
+            else k_mb_mix<<<grid, 256, 0, ctx->stream>>>(iters, (float *)d_out);   // 8 FFMA2 + 8 FMNMX per 16 "units"
+        };
+        launch();
+        SBP_CUDA(cudaEventRecord(e0, ctx->stream));
+        for (int r = 0; r < reps; ++r) launch();
+        SBP_CUDA(cudaEventRecord(e1, ctx->stream));
+        // units = fp32 FMAs (3/4) or min instructions x 32 lanes (5/6) per launch:
+        // 4 unrolled x (8 packed x 2 | 16 scalar) per thread and iteration
+        *units = (double)grid * 256.0 * iters * 4.0 * 16.0;
     } else {
         int grid = ctx->sm_count * 8;
         k_mb_fp64<<<grid, 256, 0, ctx->stream>>>(iters, (double *)d_out);

@@ -572,11 +572,11 @@ __device__ __forceinline__ bool filter_query_setup(const double *__restrict__ in
 // The scan itself: streams node chunk [c0, c1) of the centred shadow through shared memory
 // and calls on_group(r, g) for every (query slot r, group of 8 nodes g = node index / 8) whose
 // minimum t passes thr[r].  All threads of the CTA must call it (barriers inside).
-template <int DD, int NW, int UNR, class OnGroup>
+template <int DD, int NW, int UNR, int FQ, class OnGroup>
 __device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_t cap32, int64_t c0,
-                                            int64_t c1, const float (&nq2)[FILTER_Q][DD],
-                                            const float (&thr)[FILTER_Q], OnGroup on_group) {
-    constexpr int TILE = filter_tile(DD), STAGES = FILTER_STAGES, FQ = FILTER_Q;
+                                            int64_t c1, const float (&nq2)[FQ][DD],
+                                            const float (&thr)[FQ], OnGroup on_group) {
+    constexpr int TILE = filter_tile(DD), STAGES = FILTER_STAGES;
     __shared__ __align__(128) float tile[STAGES][DD + 1][TILE];
     __shared__ __align__(8) uint64_t full[STAGES];
     const int T = c1 > c0 ? (int)((c1 - c0 + TILE - 1) / TILE) : 0;
@@ -653,13 +653,13 @@ __device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_
     }
 }
 
-template <int D, int NW, int UNR>
+template <int D, int NW, int UNR, int FQ>
 __global__ void __launch_bounds__(NW * 32)
 k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
              int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
              const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
              int32_t *__restrict__ ccount) {
-    constexpr int FQ = FILTER_Q, TPB = NW * 32;
+    constexpr int TPB = NW * 32;
     const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
     const int s = blockIdx.y;
     const int64_t c0 = (int64_t)s * chunk;                       // multiple of the tile
@@ -677,7 +677,7 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
         cc[r] = (live && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
         cl[r] = cand + ((live ? q : 0) * S + s) * (int64_t)C;
     }
-    filter_scan<D, NW, UNR>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+    filter_scan<D, NW, UNR, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
         cl[r][cc[r] < C ? cc[r] : C - 1] = g;                        // an overflowing list is never read
         ++cc[r];
     });
@@ -722,7 +722,7 @@ k_near_filtered(const float *__restrict__ sh, const double *__restrict__ info, i
         }
         pos[r] = (PASS == 1 && live) ? offsets[q * S + s] : 0;
     }
-    filter_scan<DD, NW, 1>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+    filter_scan<DD, NW, 1, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
         const int64_t q = qb + (int64_t)r * TPB;
         double qv[D];
 #pragma unroll
@@ -1388,8 +1388,9 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     if (seed && g_knn_filter) {
         // seeded filter + exact refine; the one-kernel scan below then only redoes the
         // blocks of 32 queries the refine step flagged (normally none)
-        const int NW = g_knn_filter_variant >= 2 ? 4 : 2;          // warps per CTA
-        const int QPB = NW * 32 * FILTER_Q;                        // queries per CTA
+        const int NW = (g_knn_filter_variant & 3) >= 2 ? 4 : 2;    // warps per CTA
+        const int FQv = g_knn_filter_variant >= 8 ? 8 : g_knn_filter_variant >= 4 ? 2 : FILTER_Q;
+        const int QPB = NW * 32 * FQv;                             // queries per CTA
         const int64_t qblocks = (m + QPB - 1) / QPB;
         constexpr int FT = filter_tile(D);
         const int64_t tiles = (n + FT - 1) / FT;
@@ -1420,16 +1421,20 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_shadow_centered<D><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, seed_bounds, cap32,
                                                           shadow, info);
         dim3 fgrid((unsigned)qblocks, (unsigned)FS);
-#define SBP_FILTER_LAUNCH(NW_, UNR_)                                                        \
-    k_knn_filter<D, NW_, UNR_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                         \
+#define SBP_FILTER_LAUNCH(NW_, UNR_, FQ_)                                                   \
+    k_knn_filter<D, NW_, UNR_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                    \
         shadow, info, cap32, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf, ccount)
         {
         KernelTimer timer(ctx);
         switch (g_knn_filter_variant) {
-            case 1: SBP_FILTER_LAUNCH(2, 1); break;
-            case 2: SBP_FILTER_LAUNCH(4, 2); break;
-            case 3: SBP_FILTER_LAUNCH(4, 1); break;
-            default: SBP_FILTER_LAUNCH(2, 2); break;
+            case 1: SBP_FILTER_LAUNCH(2, 1, FILTER_Q); break;
+            case 2: SBP_FILTER_LAUNCH(4, 2, FILTER_Q); break;
+            case 3: SBP_FILTER_LAUNCH(4, 1, FILTER_Q); break;
+            case 4: SBP_FILTER_LAUNCH(2, 2, 2); break;
+            case 6: SBP_FILTER_LAUNCH(4, 2, 2); break;
+            case 8: SBP_FILTER_LAUNCH(2, 1, 8); break;
+            case 10: SBP_FILTER_LAUNCH(4, 1, 8); break;
+            default: SBP_FILTER_LAUNCH(2, 2, FILTER_Q); break;
         }
         }
 #undef SBP_FILTER_LAUNCH
