@@ -20,6 +20,7 @@
 
 #include "common.cuh"
 #include "device_fns.cuh"
+#include "filter.cuh"
 
 #define KNN_TPB 128        // queries per CTA in the batched radius kernel
 #define KNN_TILE 1024      // nodes staged in shared memory per step
@@ -434,225 +435,7 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
 }
 
 // --------------------------------------- K4a': seeded filter + exact refine ---
-// When every query already has an a-priori bound (seed2, the grid seeds below), the top-K
-// state is not needed during the scan at all: the scan only has to FIND the few nodes inside
-// the bound.  The filter runs on a per-call fp32 shadow of the nodes, centred on the middle c
-// of their bounding box, with the squared norm precomputed (k_shadow_centered):
-//     |n - q|^2 = |n^|^2 - 2 n^.q^ + |q^|^2,      n^ = fl32(n - c), q^ = fl32(q - c)
-// so a pair costs D fused multiply-adds instead of D subtractions + D multiply-adds:
-//     t = fma(n^_D, -2q^_D, ... fma(n^_1, -2q^_1, fl32(|n^|^2)))   vs   thr' = bound - |q^|^2.
-// k_knn_filter streams the shadow through shared memory (TMA bulk copies, double buffered,
-// one mbarrier per stage).  A thread owns FQ = 4 queries and evaluates 8 nodes per step for
-// each of them with the packed fp32x2 pipe (FFMA2) and three-input minima (FMNMX3): every
-// broadcast LDS.128 feeds 16 (query, node) pairs -- the shared-memory pipe moves only 8 bytes
-// per wavefront on a broadcast, which bounded the one-query-per-thread version -- and the
-// kernel is bound by the FMA pipe (1 packed FFMA2 = 2 pipe cycles per pair for d = 2).
-//
-// CONSERVATIVE threshold.  With u = 2^-24, M >= |n_j - c_j|, Mq >= |q_j - c_j|:
-//   * |n^ - q^| <= |n - q| + a,  a = 4 u sqrt(D) max(M, Mq)   (roundings of n^ and q^);
-//   * the D+1 roundings of the fma chain change t by at most
-//     E = u D (D+1) M (M + Mq) (1 + 1e-5) + 1e-15 Mq^2    (partial sums are <= D M^2 + 2 j M Mq);
-// so every pair with exact fp64 d^2 <= bound has t <= thr' := round_up((sqrt(bound) + a)^2 + E
-// - |q^|^2).  The filter can only add false positives, never lose a neighbour.  A query
-// whose band E exceeds (sqrt(bound) + a)^2 (huge extent / tiny neighbour distance, outliers),
-// or that has no finite bound, is not filtered: it is flagged and recomputed by k_knn_batched.
-//
-// A group of 8 nodes whose minimum t passes is appended to the (query, chunk) candidate list;
-// k_knn_refine then decides the candidates exactly in fp64 with the same TopK::offer as the
-// one-kernel scan, visiting them in node-index order.
-#define FILTER_STAGES 2
-#define FILTER_Q 4          // queries per thread
-// nodes per stage: 2 stages x (D + 1) x tile x 4 B of static shared memory (<= 40 KB)
-__host__ __device__ constexpr int filter_tile(int D) { return D <= 4 ? 1024 : 512; }
-
-__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(uint64_t v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ float f_min3(float a, float b, float c) {
-    float r;
-    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    return ok != 0;
-}
-
-// Centred fp32 shadow [D + 1][cap32]: coordinates relative to the bounding-box centre and
-// the squared norm of the ROUNDED coordinates (exact products, one rounding).  Slots in
-// [n, cap32) hold the origin with norm 3e38 so that a tile tail never passes a threshold.
-// info[0] = M (max |centred coordinate|, +inf when a bound is not finite), info[1+j] = c_j.
-template <int D>
-__global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                                  const double *__restrict__ bounds /*[D][2] = min, max*/,
-                                  int64_t cap32, float *__restrict__ sh, double *__restrict__ info) {
-    double c[D], M = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const double mn = bounds[2 * j], mx = bounds[2 * j + 1];
-        c[j] = 0.5 * mn + 0.5 * mx;
-        const double h = fmax(mx - c[j], c[j] - mn);
-        M = (h != h) ? INFINITY : fmax(M, h);
-        if (!(mn <= mx)) M = INFINITY;                  // empty / NaN bounds
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        info[0] = M * (1.0 + 1e-9);
-#pragma unroll
-        for (int j = 0; j < D; ++j) info[1 + j] = c[j];
-    }
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cap32;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        if (t < n) {
-            double nn = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-                const float xc = (float)(soa[(int64_t)j * capacity + t] - c[j]);
-                sh[(int64_t)j * cap32 + t] = xc;
-                nn += (double)xc * (double)xc;
-            }
-            sh[(int64_t)D * cap32 + t] = (float)nn;
-        } else {
-            // padding: t = fma(0, ., 3e38) = 3e38 never passes a (finite) threshold
-#pragma unroll
-            for (int j = 0; j < D; ++j) sh[(int64_t)j * cap32 + t] = 0.0f;
-            sh[(int64_t)D * cap32 + t] = 3.0e38f;
-        }
-    }
-}
-
-// Threshold of one query for the filter (see the derivation above).  `bound2` is the exact
-// fp64 d^2 bound of the query (seed, or the radius threshold); xq its coordinates (stride of
-// the caller), DD the number of leading coordinates the distance uses.  Returns false -- and
-// thr = -inf, so that nothing passes -- when the query cannot be filtered conservatively.
-template <int DD>
-__device__ __forceinline__ bool filter_query_setup(const double *__restrict__ info, const double *xq,
-                                                   bool live, double bound2, float (&nq2)[DD],
-                                                   float &thr) {
-    const double M = info[0];
-    double Mq = 0.0, qq = 0.0;
-#pragma unroll
-    for (int j = 0; j < DD; ++j) {
-        const double v = live ? xq[j] - info[1 + j] : 0.0;
-        const float qf = (float)v;
-        nq2[j] = -2.0f * qf;
-        qq += (double)qf * (double)qf;
-        const double av = v != v ? INFINITY : fabs(v);
-        Mq = av > Mq ? av : Mq;
-    }
-    const double mm = M > Mq ? M : Mq;
-    const double a = 4.0 * 5.9604644775390625e-8 * sqrt((double)DD) * mm * (1.0 + 1e-6);
-    const double E = 5.9604644775390625e-8 * (double)(DD * (DD + 1)) * M * (M + Mq) * (1.0 + 1e-5) +
-                     1e-15 * Mq * Mq;
-    const double ra = sqrt(bound2) + a;                              // NaN for bound2 < 0 or NaN
-    const double pos = (ra * ra + E) * (1.0 + 1e-9);
-    const bool usable = live && mm < 1e15 && bound2 < INFINITY && E <= ra * ra;
-    thr = usable ? __double2float_ru(pos - qq) : -INFINITY;          // t (or NaN) never passes -inf
-    return usable;
-}
-
-// The scan itself: streams node chunk [c0, c1) of the centred shadow through shared memory
-// and calls on_group(r, g) for every (query slot r, group of 8 nodes g = node index / 8) whose
-// minimum t passes thr[r].  All threads of the CTA must call it (barriers inside).
-template <int DD, int NW, int UNR, int FQ, class OnGroup>
-__device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_t cap32, int64_t c0,
-                                            int64_t c1, const float (&nq2)[FQ][DD],
-                                            const float (&thr)[FQ], OnGroup on_group) {
-    constexpr int TILE = filter_tile(DD), STAGES = FILTER_STAGES;
-    __shared__ __align__(128) float tile[STAGES][DD + 1][TILE];
-    __shared__ __align__(8) uint64_t full[STAGES];
-    const int T = c1 > c0 ? (int)((c1 - c0 + TILE - 1) / TILE) : 0;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
-        fence_barrier_init();
-    }
-    __syncthreads();
-    // one thread feeds the stages: DD + 1 bulk copies of <= 4 KB per tile (cap32 is a multiple
-    // of the tile, so every copy is a whole number of 16-byte units inside the allocation)
-    auto issue = [&](int it) {
-        const int st = it % STAGES;
-        const int64_t t0 = c0 + (int64_t)it * TILE;
-        const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
-        const uint32_t bytes = (uint32_t)((cnt + 7) & ~7) * 4u;
-        mbar_expect_tx(&full[st], bytes * (DD + 1));
-#pragma unroll
-        for (int j = 0; j <= DD; ++j)
-            bulk_g2s(&tile[st][j][0], sh + (int64_t)j * cap32 + t0, bytes, &full[st]);
-    };
-    if (threadIdx.x == 0)
-        for (int it = 0; it < T && it < STAGES; ++it) issue(it);
-    for (int it = 0; it < T; ++it) {
-        const int st = it % STAGES;
-        const uint32_t phase = (uint32_t)(it / STAGES) & 1u;
-        while (!mbar_try_wait(&full[st], phase)) {}
-        const int64_t t0 = c0 + (int64_t)it * TILE;
-        const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
-        const int groups = (cnt + 7) >> 3;
-        const int32_t g0 = (int32_t)(t0 >> 3);
-#pragma unroll UNR
-        for (int g = 0; g < groups; ++g) {
-            uint64_t nd[DD + 1][4];          // 8 nodes: packed pairs of every component and the norm
-#pragma unroll
-            for (int j = 0; j <= DD; ++j) {
-                const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
-                const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
-                nd[j][0] = f2_pack(a.x, a.y); nd[j][1] = f2_pack(a.z, a.w);
-                nd[j][2] = f2_pack(b.x, b.y); nd[j][3] = f2_pack(b.z, b.w);
-            }
-            float mn[FQ];
-#pragma unroll
-            for (int r = 0; r < FQ; ++r) {
-                uint64_t acc[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) acc[p] = nd[DD][p];
-#pragma unroll
-                for (int j = 0; j < DD; ++j) {
-                    const uint64_t qj = f2_pack(nq2[r][j], nq2[r][j]);
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) acc[p] = f2_fma(nd[j][p], qj, acc[p]);
-                }
-                float v[8];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) f2_unpack(acc[p], v[2 * p], v[2 * p + 1]);
-                float w = f_min3(v[0], v[1], v[2]);
-                w = f_min3(w, v[3], v[4]);
-                w = f_min3(w, v[5], v[6]);
-                mn[r] = fminf(w, v[7]);
-            }
-            // one (rarely taken) branch per group for the four queries
-            bool any = false;
-#pragma unroll
-            for (int r = 0; r < FQ; ++r) any |= mn[r] <= thr[r];
-            if (any) {
-#pragma unroll
-                for (int r = 0; r < FQ; ++r)
-                    if (mn[r] <= thr[r]) on_group(r, g0 + g);
-            }
-        }
-        __syncthreads();                                         // every warp is done with stage st
-        if (threadIdx.x == 0 && it + STAGES < T) issue(it + STAGES);
-    }
-}
-
+// (scan, thresholds and the centred shadow: filter.cuh)
 template <int D, int NW, int UNR, int FQ>
 __global__ void __launch_bounds__(NW * 32)
 k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
@@ -1191,22 +974,23 @@ __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity,
 
 // seed2[q] = K-th smallest exact fp64 d^2 among ALL nodes of a block of cells around the
 // query's cell that holds at least K nodes -- a subset of the nodes, so an upper bound of the
-// true K-th smallest -- inflated by 1e-9.  One warp per query.  The block grows ring by ring
+// true K-th smallest -- inflated by 1e-9.  GS = 16 or 32 lanes per query.  The block grows ring by ring
 // (then geometrically, until it covers the whole grid: sparse pockets, queries far outside the
 // cloud); lanes own its rows (a row of cells is one contiguous range of `ids`).  The nodes
 // are enumerated 32 at a time, flat over the rows, and merged into the running K smallest by
 // rank counting over shuffles (the K smallest live in lanes 0..K-1, sorted, via a per-warp
 // shared-memory scatter).  inf = fewer than K nodes at a non-NaN distance.
-template <int D>
+template <int D, int GS>      // GS = lanes per query: 16 (K <= 16) or 32
 __global__ void __launch_bounds__(256)
 k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
            const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
            const int32_t *__restrict__ ids, int K, double *__restrict__ seed2) {
-    __shared__ double sbest[8][32];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= m) return;                                       // warp-uniform
+    __shared__ double sbest[256 / GS][GS];
+    const int lane = threadIdx.x & (GS - 1), grp = threadIdx.x / GS;
+    // every warp-level primitive below is restricted to this query's lanes
+    const unsigned SEG = GS == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    if (q >= m) return;                                       // uniform over the GS lanes
     double qv[D];
     bool finite = true;
 #pragma unroll
@@ -1221,16 +1005,16 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
             x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
             y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
             int32_t c = 0;
-            for (int row = y0 + lane; row <= y1; row += 32)
+            for (int row = y0 + lane; row <= y1; row += GS)
                 c += start[(int64_t)row * G + x1 + 1] - start[(int64_t)row * G + x0];
-            cnt = __reduce_add_sync(FULL, c);
+            cnt = __reduce_add_sync(SEG, c);
             if (cnt >= K || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
         }
         if (cnt >= K) {
             double best = INFINITY;                           // lanes 0..K-1: the K smallest so far
             int nb = 0;                                       // valid entries of `best`
-            // rows in passes of 32 (one pass unless the block is taller than 32 cells)
-            for (int rb = y0; rb <= y1; rb += 32) {
+            // rows in passes of GS (one pass unless the block is taller than GS cells)
+            for (int rb = y0; rb <= y1; rb += GS) {
                 int32_t e0 = 0, len = 0;
                 if (rb + lane <= y1) {
                     e0 = start[(int64_t)(rb + lane) * G + x0];
@@ -1238,19 +1022,19 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
                 }
                 int32_t inc = len;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int32_t u = __shfl_up_sync(FULL, inc, o);
+                for (int o = 1; o < GS; o <<= 1) {
+                    int32_t u = __shfl_up_sync(SEG, inc, o, GS);
                     if (lane >= o) inc += u;
                 }
-                const int32_t pc = __shfl_sync(FULL, inc, 31);   // nodes in this pass
-                const int nrows = y1 - rb + 1 < 32 ? y1 - rb + 1 : 32;
-                for (int32_t f0 = 0; f0 < pc; f0 += 32) {
+                const int32_t pc = __shfl_sync(SEG, inc, GS - 1, GS);   // nodes in this pass
+                const int nrows = y1 - rb + 1 < GS ? y1 - rb + 1 : GS;
+                for (int32_t f0 = 0; f0 < pc; f0 += GS) {
                     // flat candidate f0 + lane lives in the first row whose inclusive prefix exceeds it
                     const int32_t f = f0 + lane;
                     int32_t e = -1;
                     for (int row = 0; row < nrows; ++row) {
-                        const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
-                        const int32_t re0 = __shfl_sync(FULL, e0, row);
+                        const int32_t rinc = __shfl_sync(SEG, inc, row, GS), rlen = __shfl_sync(SEG, len, row, GS);
+                        const int32_t re0 = __shfl_sync(SEG, e0, row, GS);
                         if (e < 0 && f < rinc) e = re0 + (f - (rinc - rlen));
                     }
                     double v = INFINITY;
@@ -1265,29 +1049,29 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
                     // ranks in the union of `best` (first on ties) and this chunk; only the
                     // nb valid entries of `best` and the nv valid entries of the chunk are
                     // compared against (the rest are +inf and rank behind every finite value)
-                    const int nv = pc - f0 < 32 ? pc - f0 : 32;
+                    const int nv = pc - f0 < GS ? pc - f0 : GS;
                     int rank_b = 0, rank_v = 0;
                     for (int src = 0; src < nb; ++src) {
-                        const double a = __shfl_sync(FULL, best, src);
+                        const double a = __shfl_sync(SEG, best, src, GS);
                         rank_b += (a < best || (a == best && src < lane)) ? 1 : 0;
                         rank_v += a <= v ? 1 : 0;
                     }
                     for (int src = 0; src < nv; ++src) {
-                        const double c = __shfl_sync(FULL, v, src);
+                        const double c = __shfl_sync(SEG, v, src, GS);
                         rank_b += c < best ? 1 : 0;
                         rank_v += (c < v || (c == v && src < lane)) ? 1 : 0;
                     }
-                    sbest[w][lane] = INFINITY;
-                    __syncwarp();
-                    if (lane < nb && rank_b < 32) sbest[w][rank_b] = best;
-                    if (lane < nv && rank_v < 32) sbest[w][rank_v] = v;
-                    __syncwarp();
-                    best = lane < K ? sbest[w][lane] : INFINITY;
-                    __syncwarp();
+                    sbest[grp][lane] = INFINITY;
+                    __syncwarp(SEG);
+                    if (lane < nb && rank_b < GS) sbest[grp][rank_b] = best;
+                    if (lane < nv && rank_v < GS) sbest[grp][rank_v] = v;
+                    __syncwarp(SEG);
+                    best = lane < K ? sbest[grp][lane] : INFINITY;
+                    __syncwarp(SEG);
                     nb = nb + nv < K ? nb + nv : K;
                 }
             }
-            const double kth = __shfl_sync(FULL, best, K - 1);
+            const double kth = __shfl_sync(SEG, best, K - 1, GS);
             out = kth * (1.0 + 1e-9) + 1e-300;
         }
     }
@@ -1377,7 +1161,9 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
         k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
-        k_knn_seed<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
+        // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
+        k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
             s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
         ctx->launches += 7;
         SBP_CUDA(cudaGetLastError());
