@@ -562,8 +562,12 @@ k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
         const int c = live ? ccount[q * S + s] : 0;
         const int32_t *cl = cand + ((live ? q : 0) * S + s) * (int64_t)C;
         const int cmax = __reduce_max_sync(FULL, c);
+        // the candidate id of the next iteration is fetched one iteration ahead (the loop is
+        // bound by the latency of its dependent loads: list entry -> node coordinates)
+        int32_t g_next = 0 < c ? cl[0] : -1;
         for (int t = 0; t < cmax; ++t) {
-            const int64_t b = t < c ? (int64_t)cl[t] * 8 : n;
+            const int64_t b = g_next >= 0 ? (int64_t)g_next * 8 : n;
+            g_next = t + 1 < c ? cl[t + 1] : -1;
             double d2[8];
             uint32_t mask = 0;
 #pragma unroll
