@@ -36,7 +36,7 @@ k_arm_feasible(MapView mv, double L0, double L1, const double4 *__restrict__ C, 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         double4 c = C[i];
-        out[i] = (uint8_t)arm_config<SMEM>(words, mv, L0, L1, c.x, c.y, c.z, c.w, myflag);
+        out[i] = (uint8_t)arm_config<SMEM, true>(words, mv, L0, L1, c.x, c.y, c.z, c.w, myflag);
     }
     if (myflag && flags) atomicOr(flags, myflag);
 }
@@ -111,7 +111,7 @@ k_arm_visible(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
                 double bx = (double)(steep ? bb : aa), by = (double)(steep ? aa : bb);
                 double r0 = __dadd_rn(__dmul_rn(st0, (double)o), a.z);
                 double r1 = __dadd_rn(__dmul_rn(st1, (double)o), a.w);
-                r = arm_config<SMEM>(words, mv, L0, L1, bx, by, r0, r1, myflag);
+                r = arm_config<SMEM, true>(words, mv, L0, L1, bx, by, r0, r1, myflag);
                 if (COUNT) tested += 1ull;
             }
             unsigned blocked = (__ballot_sync(FULL, act && r == 0) >> gshift) & gmask_bits;
@@ -135,10 +135,11 @@ k_arm_visible(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
 extern int g_force_global;
 int g_arm_group = 0;   // 0 = auto
 
+// The arm kernels read the ROW-MAJOR copy of the map (sbp_map::rows, common.cuh).
 static void arm_cfg(const sbp_map *m, bool smem, int &grid, int &threads, size_t &bytes) {
     const sbp_ctx *ctx = m->ctx;
     if (smem) {
-        bytes = (size_t)m->packed_bytes;
+        bytes = (size_t)m->rows.n_words * 4;
         int per_sm = (int)((size_t)(228 * 1024) / (bytes + 2048));
         per_sm = per_sm < 1 ? 1 : per_sm > 4 ? 4 : per_sm;
         threads = per_sm <= 2 ? 1024 : 512;
@@ -156,8 +157,10 @@ extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const do
     SBP_REQUIRE(n >= 0, "sbp_arm_feasible: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    bool smem = !g_force_global && map->smem_resident &&
-                n * 64 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
+    int32_t rc_rows = sbp_map_ensure_rows(map);
+    if (rc_rows) return rc_rows;
+    bool smem = !g_force_global && map->rows_smem_resident &&
+                n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 4;
     int grid, threads; size_t bytes;
     arm_cfg(map, smem, grid, threads, bytes);
     int64_t need = (n + threads - 1) / threads;
@@ -165,9 +168,9 @@ extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const do
     if (smem) {
         if (bytes > 48 * 1024)
             SBP_CUDA(cudaFuncSetAttribute(k_arm_feasible<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        k_arm_feasible<true><<<grid, threads, bytes, ctx->stream>>>(map->view, L0, L1, (const double4 *)C, n, out, flags);
+        k_arm_feasible<true><<<grid, threads, bytes, ctx->stream>>>(map->rows, L0, L1, (const double4 *)C, n, out, flags);
     } else {
-        k_arm_feasible<false><<<grid, threads, 0, ctx->stream>>>(map->view, L0, L1, (const double4 *)C, n, out, flags);
+        k_arm_feasible<false><<<grid, threads, 0, ctx->stream>>>(map->rows, L0, L1, (const double4 *)C, n, out, flags);
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
@@ -189,7 +192,7 @@ static int32_t launch_arm_visible(sbp_map *map, double L0, double L1, const doub
         if (bytes > 48 * 1024)                                                                     \
             SBP_CUDA(cudaFuncSetAttribute(k_arm_visible<G, SM, CT>,                                \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
-        k_arm_visible<G, SM, CT><<<grid, threads, bytes, ctx->stream>>>(map->view, L0, L1, c1, c2, \
+        k_arm_visible<G, SM, CT><<<grid, threads, bytes, ctx->stream>>>(map->rows, L0, L1, c1, c2, \
                                                                         n, out, flags, cnt);       \
     } while (0)
     if (smem) { if (cnt) SBP_LAUNCH_ARM(true, true); else SBP_LAUNCH_ARM(true, false); }
@@ -207,8 +210,10 @@ extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const dou
     SBP_REQUIRE(n >= 0, "sbp_arm_visible: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    bool smem = !g_force_global && map->smem_resident &&
-                n * 64 >= map->packed_bytes * (int64_t)ctx->sm_count / 16;
+    int32_t rc_rows = sbp_map_ensure_rows(map);
+    if (rc_rows) return rc_rows;
+    bool smem = !g_force_global && map->rows_smem_resident &&
+                n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 16;
     unsigned long long *cnt = (unsigned long long *)cfg_tested;
     int G = g_arm_group ? g_arm_group : 8;
     switch (G) {

@@ -96,7 +96,16 @@ struct sbp_map {
     std::vector<uint32_t> h_words;   // host mirror (arm guard-band resolution)
     int64_t packed_bytes = 0;
     bool smem_resident = false;      // whole map fits one CTA's shared memory
+    // Second, row-major copy for the arm link sweeps (built on first use, sbp_map_ensure_rows):
+    // word = y * WR + (x >> 5), bit = x & 31 -- two shifts and one multiply-add per pixel where
+    // the tiled layout above needs ~12 integer operations (the arm sweep is bound by exactly
+    // that arithmetic); `rows.SX` holds WR, the words per row.
+    uint32_t *d_rows = nullptr;
+    MapView rows{};
+    bool rows_smem_resident = false;
 };
+
+int32_t sbp_map_ensure_rows(sbp_map *map);
 
 struct sbp_nodes {
     sbp_ctx *ctx = nullptr;
@@ -126,6 +135,13 @@ __device__ __forceinline__ bool map_free(const uint32_t *words, int SX, int x, i
     uint32_t wi = map_word_index(SX, x, y);
     uint32_t w = GLOBAL_LDG ? __ldg(words + wi) : words[wi];
     return (w >> map_bit_index(x, y)) & 1u;
+}
+
+template <bool GLOBAL_LDG>
+__device__ __forceinline__ bool map_free_rows(const uint32_t *words, int WR, int x, int y) {
+    uint32_t wi = (uint32_t)y * (uint32_t)WR + ((uint32_t)x >> 5);
+    uint32_t w = GLOBAL_LDG ? __ldg(words + wi) : words[wi];
+    return (w >> ((uint32_t)x & 31u)) & 1u;
 }
 
 // numpy index semantics of `_img[x, y]`: valid iff -W <= i < W,

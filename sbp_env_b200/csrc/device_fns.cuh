@@ -64,7 +64,8 @@ __device__ __forceinline__ bool edge_visible_seq(const uint32_t *words, const Ma
 // ======================= 4-DoF arm (collisionChecker.py:346-503) ================
 // Sequential Bresenham walk of one link; all pixels free?  Order is irrelevant
 // for the boolean, so the canonical traversal is walked directly.
-template <bool SMEM>
+// ROWS selects the row-major map copy (mv = sbp_map::rows, mv.SX = words per row).
+template <bool SMEM, bool ROWS = false>
 __device__ __forceinline__ bool link_free(const uint32_t *words, const MapView &mv, int x1, int y1,
                                           int x2, int y2) {
     int dx = x2 - x1, dy = y2 - y1;
@@ -76,9 +77,13 @@ __device__ __forceinline__ bool link_free(const uint32_t *words, const MapView &
     int err = da >> 1;                                  // int(dx / 2.0), :486
     int ystep = b1 < b2 ? 1 : -1;                       // :487
     int b = b1;
+    // one loop for both major axes (selects, not branches): lanes of a warp walk links of
+    // different orientation, and per-axis loops would serialise them
     for (int a = a1; a <= a2; ++a) {                    // :492-498
         int x = steep ? b : a, y = steep ? a : b;
-        if (!map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H))) return false;
+        const int xw = wrap_index(x, mv.W), yw = wrap_index(y, mv.H);
+        if (!(ROWS ? map_free_rows<!SMEM>(words, mv.SX, xw, yw) : map_free<!SMEM>(words, mv.SX, xw, yw)))
+            return false;
         err -= adb;
         if (err < 0) { b += ystep; err += da; }
     }
@@ -93,7 +98,7 @@ __device__ __forceinline__ bool near_pixel_boundary(double v, double L) {
 }
 
 // One configuration: 1 free, 0 blocked, 2 ambiguous.  flag receives SBP_FLAG_*.
-template <bool SMEM>
+template <bool SMEM, bool ROWS = false>
 __device__ __forceinline__ int arm_config(const uint32_t *words, const MapView &mv, double L0,
                                           double L1, double bx, double by, double r0, double r1,
                                           int &flag) {
@@ -117,13 +122,13 @@ __device__ __forceinline__ int arm_config(const uint32_t *words, const MapView &
     if (t2x.flag || t2y.flag) { flag |= t2x.flag ? t2x.flag : t2y.flag; return 0; }
     if (amb1) return 2;
     if (!t2x.in_range || !t2y.in_range) return 0;       // end pixel of link 1 is out of range
-    if (!link_free<SMEM>(words, mv, tbx.i, tby.i, t2x.i, t2y.i)) return 0;   // :413-415
+    if (!link_free<SMEM, ROWS>(words, mv, tbx.i, tby.i, t2x.i, t2y.i)) return 0;   // :413-415
     bool amb2 = near_pixel_boundary(p3x, L1) || near_pixel_boundary(p3y, L1);
     TruncResult t3x = trunc_index(p3x, mv.W), t3y = trunc_index(p3y, mv.H);
     if (t3x.flag || t3y.flag) { flag |= t3x.flag ? t3x.flag : t3y.flag; return 0; }
     if (amb2) return 2;
     if (!t3x.in_range || !t3y.in_range) return 0;
-    return link_free<SMEM>(words, mv, t2x.i, t2y.i, t3x.i, t3y.i) ? 1 : 0;   // :422-424
+    return link_free<SMEM, ROWS>(words, mv, t2x.i, t2y.i, t3x.i, t3y.i) ? 1 : 0;   // :422-424
 }
 
 

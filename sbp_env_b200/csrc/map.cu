@@ -201,11 +201,45 @@ extern "C" int32_t sbp_map_create_device(sbp_ctx *ctx, const uint8_t *free_xy_de
     return rc;
 }
 
+// Row-major twin of the tiled map (arm link sweeps): one thread per 32-pixel word.
+__global__ void k_rows_from_tiles(MapView mv, int WR, uint32_t n_row_words, uint32_t *__restrict__ rows) {
+    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_row_words;
+         wi += gridDim.x * blockDim.x) {
+        const int y = (int)(wi / (uint32_t)WR), x0 = (int)(wi % (uint32_t)WR) * 32;
+        uint32_t w = 0;
+        for (int b = 0; b < 32 && y < mv.H; ++b)            // y >= H: padding words
+            if (x0 + b < mv.W && map_free<true>(mv.words, mv.SX, x0 + b, y)) w |= 1u << b;
+        rows[wi] = w;
+    }
+}
+
+int32_t sbp_map_ensure_rows(sbp_map *m) {
+    if (m->d_rows) return SBP_OK;
+    sbp_ctx *ctx = m->ctx;
+    const int WR = (m->view.W + 31) / 32;
+    // padded to whole 16-byte units: the bulk copy that stages it moves multiples of 16 bytes
+    const uint64_t nw = ((uint64_t)WR * (uint64_t)m->view.H + 3ull) & ~3ull;
+    SBP_REQUIRE(nw <= 0xffffffffull / 4ull, "row-major map copy too large for 32-bit word indexing");
+    SBP_CUDA(cudaMalloc(&m->d_rows, (size_t)nw * 4));
+    m->rows = m->view;
+    m->rows.words = m->d_rows;
+    m->rows.SX = WR;
+    m->rows.n_words = (uint32_t)nw;
+    m->rows_smem_resident = (size_t)nw * 4 + 1024 <= (size_t)ctx->max_smem_optin;
+    int blocks = (int)((nw + 255) / 256);
+    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
+    k_rows_from_tiles<<<blocks, 256, 0, ctx->stream>>>(m->view, WR, (uint32_t)nw, m->d_rows);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
 extern "C" int32_t sbp_map_destroy(sbp_map *map) {
     if (!map) return SBP_OK;
     cudaSetDevice(map->ctx->device);
     cudaStreamSynchronize(map->ctx->stream);
     if (map->d_words) cudaFree(map->d_words);
+    if (map->d_rows) cudaFree(map->d_rows);
     delete map;
     return SBP_OK;
 }
