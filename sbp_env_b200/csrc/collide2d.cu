@@ -135,7 +135,15 @@ k_visible2d(MapView mv, const double2 *__restrict__ P, const double2 *__restrict
 // Batches of equal-length edges (PRM k-NN candidates) therefore run entirely in the
 // divergence-free phase A; heavy-tailed batches (uniform random edges) hand their few
 // long edges to phase B instead of idling 31 lanes behind them.
-template <bool SMEM, bool COUNT>
+template <bool SMEM, bool ROWS>
+__device__ __forceinline__ bool px_free(const uint32_t *words, const MapView &mv, int x, int y) {
+    return ROWS ? map_free_rows<!SMEM>(words, mv.SX, x, y) : map_free<!SMEM>(words, mv.SX, x, y);
+}
+
+// ROWS: `mv` is the row-major copy of the map (sbp_map::rows; shared-memory resident maps:
+// 3 integer operations per pixel index instead of ~12 for the tiled layout, which only pays off
+// through its sector locality when the map lives in L2 / HBM).
+template <bool SMEM, bool COUNT, bool ROWS>
 __global__ void __launch_bounds__(1024)
 k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *__restrict__ Q,
                      int64_t n, uint8_t *__restrict__ out, int32_t *__restrict__ flags,
@@ -166,7 +174,7 @@ k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *_
         bool result = valid && ed.walk;
         // end pixel first (:204-206: it is a member of the list)
         if (result) {
-            result = map_free<!SMEM>(words, mv.SX, wrap_index(ed.x2, mv.W), wrap_index(ed.y2, mv.H));
+            result = px_free<SMEM, ROWS>(words, mv, wrap_index(ed.x2, mv.W), wrap_index(ed.y2, mv.H));
             if (COUNT) tested += 1ull;
         }
         int a = ed.a1, b = ed.b1;
@@ -193,7 +201,7 @@ k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *_
             for (int st = 0; st < 4; ++st) {
                 if (active) {
                     int x = ed.steep ? b : a, y = ed.steep ? a : b;          // :205
-                    bool fr = map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H));
+                    bool fr = px_free<SMEM, ROWS>(words, mv, wrap_index(x, mv.W), wrap_index(y, mv.H));
                     if (COUNT) tested += 1ull;
                     err -= (int)ed.adb;                                      // :207-210
                     if (err < 0) { b += ed.ystep; err += (int)ed.da; }
@@ -234,7 +242,7 @@ k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *_
                 if (j < left) {
                     int aa = s_a + (int)j, bb = s_b + ystep * (int)m;
                     int x = steep ? bb : aa, y = steep ? aa : bb;
-                    blk = !map_free<!SMEM>(words, mv.SX, wrap_index(x, mv.W), wrap_index(y, mv.H));
+                    blk = !px_free<SMEM, ROWS>(words, mv, wrap_index(x, mv.W), wrap_index(y, mv.H));
                     if (COUNT) tested += 1ull;
                 }
                 if (__any_sync(FULL, blk)) { hit = true; break; }
@@ -457,23 +465,29 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
     unsigned long long *px = (unsigned long long *)px_tested;
     if (g_visible_group == 0) {
         LaunchCfg c;
-        c.smem = smem ? (size_t)map->packed_bytes : 0;
+        if (smem) {                 // shared-memory resident: the row-major copy (cheaper index)
+            int32_t rc = sbp_map_ensure_rows(map);
+            if (rc) return rc;
+            smem = map->rows_smem_resident;
+        }
+        const MapView mview = smem ? map->rows : map->view;
+        c.smem = smem ? (size_t)map->rows.n_words * 4 : 0;
         c.threads = (smem && c.smem > 110 * 1024) ? 1024 : 512;
         c.grid = 0;
         int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
         const double2 *p2 = (const double2 *)P, *q2 = (const double2 *)Q;
 #define SBP_LAUNCH_ADP(SM, CT)                                                                    \
     do {                                                                                           \
-        int32_t rc = set_smem(k_visible2d_adaptive<SM, CT>, c.smem);                               \
+        int32_t rc = set_smem(k_visible2d_adaptive<SM, CT, SM>, c.smem);                           \
         if (rc) return rc;                                                                         \
         int per_sm = 0;                                                                            \
         SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
-            &per_sm, k_visible2d_adaptive<SM, CT>, c.threads, c.smem));                            \
+            &per_sm, k_visible2d_adaptive<SM, CT, SM>, c.threads, c.smem));                        \
         c.grid = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);                                        \
         int64_t need = (n + c.threads - 1) / c.threads;                                            \
         if (need < c.grid) c.grid = (int)need;                                                     \
-        k_visible2d_adaptive<SM, CT><<<c.grid, c.threads, c.smem, ctx->stream>>>(                  \
-            map->view, p2, q2, n, out, flags, px, coop);                                           \
+        k_visible2d_adaptive<SM, CT, SM><<<c.grid, c.threads, c.smem, ctx->stream>>>(              \
+            mview, p2, q2, n, out, flags, px, coop);                                               \
     } while (0)
         if (smem) { if (px) SBP_LAUNCH_ADP(true, true); else SBP_LAUNCH_ADP(true, false); }
         else      { if (px) SBP_LAUNCH_ADP(false, true); else SBP_LAUNCH_ADP(false, false); }
