@@ -206,10 +206,8 @@ __device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_
                 float v[8];
 #pragma unroll
                 for (int p = 0; p < 4; ++p) f2_unpack(acc[p], v[2 * p], v[2 * p + 1]);
-                float w = f_min3(v[0], v[1], v[2]);
-                w = f_min3(w, v[3], v[4]);
-                w = f_min3(w, v[5], v[6]);
-                mn[r] = fminf(w, v[7]);
+                // depth-2 tree (same four instructions as a chain, half the dependent latency)
+                mn[r] = f_min3(f_min3(v[0], v[1], v[2]), f_min3(v[3], v[4], v[5]), fminf(v[6], v[7]));
             }
             // one (rarely taken) branch per group for the four queries
             bool any = false;
