@@ -165,11 +165,25 @@ def run_ours(args):
 
     names = ("knn", "edges", "visible", "gather")
 
+    # N > 1: the packed adjacency is assembled on every rank by ONE kernel that packs the block
+    # and stores it over NVLink into every rank's symmetric buffer, plus a signal-pad barrier
+    # (PeerAdjacencyGather); NCCL all-gather of the packed block when peer memory is unavailable
+    peer = None
+    gather_kind = "none (N = 1)"
+    if world > 1:
+        try:
+            peer = sg.distributed.PeerAdjacencyGather(m, k, device=local)
+            gather_kind = "peer-memory scatter kernel + symmetric-memory barrier"
+        except Exception as e:      # noqa: BLE001
+            gather_kind = f"NCCL all-gather of the packed block (peer memory unavailable: {type(e).__name__})"
+
     def gather(nbr, vis):
-        if world > 1:        # one packed int32 all-gather assembles the adjacency on every rank
-            gathered["packed"] = sg.distributed.all_gather_adjacency(nbr, vis, unpack=False)
-        else:
+        if world == 1:
             gathered["nbr"], gathered["vis"] = nbr, vis
+        elif peer is not None:
+            gathered["packed"] = peer.gather(nbr, vis)
+        else:
+            gathered["packed"] = sg.distributed.all_gather_adjacency(nbr, vis, unpack=False)
 
     def eager_step(ev=None):
         idx = [0]
@@ -454,7 +468,7 @@ def run_ours(args):
                              "library (PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms "
                              "come from the same step launched eagerly",
                    "multi_gpu": "rank r connects batch r of 50000 samples to the replicated roadmap; "
-                                "one NCCL all-gather of the packed neighbour/visibility blocks inside the step"},
+                                "the packed neighbour/visibility blocks are assembled on every rank inside the step"},
         "clocks": clocks,
         "e2e": {"value": world * edges_per_rank * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
@@ -462,6 +476,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(nbr_h.numel() * 8 + vis_h.numel())},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": int(launches_per_step),
+        "adjacency_gather": gather_kind,
         "roofline": roof,
         "cpu_baseline": cpu,
         "phases_ms": ph,

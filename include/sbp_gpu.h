@@ -260,6 +260,15 @@ int32_t sbp_graph_csr(sbp_graph *g, int64_t *row_ptr, int32_t *col, int64_t col_
 int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64_t *goal, int64_t nq,
                       int32_t *hops, int64_t *paths, int32_t max_len);
 
+/* Multi-GPU assembly of the roadmap adjacency over peer memory: packs
+ * this rank's candidate block -- (nbr + 1) * 2 + vis, one int32 per candidate -- and stores it
+ * into the peer-mapped int32 buffer of every rank (peer_bufs: HOST array of `world` device
+ * pointers, e.g. torch symmetric memory) at element `offset` (a multiple of 4).  One kernel:
+ * packing + NVLink stores; the caller runs the cross-rank barrier. */
+int32_t sbp_adjacency_peer_scatter(sbp_ctx *ctx, const int64_t *nbr, const uint8_t *vis,
+                                   int64_t total, void *const *peer_bufs, int32_t world,
+                                   int64_t offset);
+
 #ifdef __cplusplus
 }
 #endif

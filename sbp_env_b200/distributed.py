@@ -82,6 +82,62 @@ def all_gather_adjacency(nbr, vis, counts=None, group=None, unpack=True):
     return unpack_adjacency(out) if unpack else out
 
 
+class PeerAdjacencyGather:
+    """All-gather of equally sized (nbr, vis) blocks WITHOUT a collective library call on the
+    data path: one kernel packs this rank's block and stores it over NVLink into every
+    rank's symmetric buffer (``sbp_adjacency_peer_scatter``), then the ranks meet at a
+    signal-pad barrier of torch's symmetric memory.  Two buffers alternate, so a rank may
+    still be reading step s while step s + 1 is being written.
+
+    >>> ag = PeerAdjacencyGather(rows_per_rank=m, k=k, device=local_rank)
+    >>> packed = ag.gather(nbr, vis)          # int32 [world * m][k], decode with unpack_adjacency
+    """
+
+    def __init__(self, rows_per_rank: int, k: int, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .runtime import get_context
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.m, self.k = int(rows_per_rank), int(k)
+        self.block = self.m * self.k
+        self.stride = (self.block + 3) // 4 * 4                    # 16-byte aligned row offsets
+        self.ctx = get_context(device)
+        dev = torch.device("cuda", device)
+        self.buf = symm_mem.empty((2, self.world * self.stride), dtype=torch.int32, device=dev)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        base = [int(p) for p in self.hdl.buffer_ptrs]
+        import ctypes as C
+
+        half = self.world * self.stride * 4
+        self._ptrs = [(C.c_void_p * self.world)(*[b + h * half for b in base]) for h in (0, 1)]
+        self._step = 0
+
+    def gather(self, nbr, vis):
+        import torch
+
+        from . import _lib
+        from .runtime import ptr
+
+        if nbr.shape != (self.m, self.k) or vis.shape != (self.m, self.k):
+            raise ValueError("block shape differs from the one the buffers were sized for")
+        self.ctx.use_torch_stream()
+        h = self._step & 1
+        self._step += 1
+        nbr = nbr.contiguous()
+        vis8 = vis.contiguous().view(torch.uint8) if vis.dtype == torch.bool else vis.contiguous()
+        _lib.check(_lib.load().sbp_adjacency_peer_scatter(self.ctx.handle, ptr(nbr), ptr(vis8), self.block,
+                                                          self._ptrs[h], self.world, self.rank * self.stride),
+                   "sbp_adjacency_peer_scatter")
+        self.hdl.barrier(channel=h)
+        out = self.buf[h].view(self.world, self.stride)[:, : self.block]
+        return out.reshape(self.world * self.m, self.k) if self.stride == self.block else \
+            out.reshape(self.world, self.m, self.k).reshape(self.world * self.m, self.k)
+
+
 def sharded_visible_batch(visible_fn, P, Q, group=None, costs=None):
     """Every rank holds the full edge list (P, Q); each checks its chunk with
     ``visible_fn`` and the masks are all-gathered, so every rank returns the full mask.

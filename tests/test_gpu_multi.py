@@ -1,0 +1,69 @@
+"""-m gpu, needs >= 2 GPUs (skipped otherwise): the peer-memory adjacency all-gather
+(sbp_adjacency_peer_scatter + symmetric-memory barrier) against the NCCL all-gather of the
+same blocks, one process per GPU."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    try:
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        from sbp_env_b200 import distributed as D
+
+        for m, k in ((5000, 10), (777, 3)):                    # 777 * 3 is not a multiple of 4
+            ag = D.PeerAdjacencyGather(m, k, device=rank)
+            for step in range(5):                               # both buffers, reuse
+                g = torch.Generator(device=dev)
+                g.manual_seed(1000 * step + rank)
+                nbr = torch.randint(-1, 1 << 20, (m, k), generator=g, device=dev, dtype=torch.int64)
+                vis = torch.rand((m, k), generator=g, device=dev) < 0.7
+                packed = ag.gather(nbr, vis)
+                want_n, want_v = D.all_gather_adjacency(nbr, vis)
+                got_n, got_v = D.unpack_adjacency(packed)
+                assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), (m, k, step)
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as e:          # noqa: BLE001 - reported to the parent
+        import traceback
+
+        q.put((rank, "".join(traceback.format_exception(e))))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_peer_adjacency_gather_equals_nccl_all_gather():
+    import torch.multiprocessing as mp
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=240) for _ in ps]
+    for p in ps:
+        p.join(30)
+    assert all(r[1] == "ok" for r in res), res
