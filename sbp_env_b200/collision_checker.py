@@ -281,7 +281,7 @@ class ImgCollisionChecker(_GridChecker):
         flags = torch.zeros(1, dtype=torch.int32, device=P.device)
         check(_lib.load().sbp_feasible2d(m.handle, ptr(P), n, ptr(out), ptr(flags)), "sbp_feasible2d")
         self._last_flags = flags     # inspected lazily: no synchronisation on this path
-        return out.bool()
+        return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy
 
     def _visible_device(self, P, Q, px_tested=None):
         import torch
@@ -297,7 +297,7 @@ class ImgCollisionChecker(_GridChecker):
         check(_lib.load().sbp_visible2d(m.handle, ptr(P), ptr(Q), n, ptr(out), ptr(flags),
                                         ptr(px_tested)), "sbp_visible2d")
         self._last_flags = flags
-        return out.bool()
+        return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy
 
     def check_device_flags(self, what="batch"):
         """Synchronise and raise what CPython would have raised for the last device-side
@@ -487,7 +487,7 @@ class RobotArm4dCollisionChecker(_GridChecker):
             check(_lib.load().sbp_arm_resolve_host(m.handle, L0, L1, ptr(a), None, len(a), ptr(o), None),
                   "sbp_arm_resolve_host")
             out[amb] = torch.from_numpy(o).to(out.device)
-        return out.bool()
+        return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy
 
     def _visible_device(self, C1, C2, cfg_tested=None, resolve=True):
         """Device tensors in, CUDA bool tensor out.  Guard-band entries (rare) are
@@ -516,4 +516,4 @@ class RobotArm4dCollisionChecker(_GridChecker):
             check(_lib.load().sbp_arm_resolve_host(m.handle, L0, L1, ptr(a), ptr(b), len(a), ptr(o),
                                                    None), "sbp_arm_resolve_host")
             out[amb] = torch.from_numpy(o).to(out.device)
-        return out.bool()
+        return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy

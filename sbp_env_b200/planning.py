@@ -72,7 +72,12 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
         dist = None
     if mark:
         mark("edges")
-    vis = cc.visible_batch(P, Q).reshape(count, k) & valid.bool().reshape(count, k)
+    vis = cc.visible_batch(P, Q).reshape(count, k)
+    if _is_torch_tensor(valid):
+        import torch
+
+        valid = valid.view(torch.bool)           # 0 / 1 bytes written by k_knn_edges
+    vis = vis & valid.reshape(count, k)
     if mark:
         mark("visible")
     if return_dist:
