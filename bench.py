@@ -281,8 +281,9 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers -------------------
     pinned = torch.from_numpy(batch_host).pin_memory()
-    nbr_h = torch.empty((m, k), dtype=torch.int64).pin_memory()
-    vis_h = torch.empty((m, k), dtype=torch.bool).pin_memory()
+    # the step's result travels to the host as the packed adjacency, 4 bytes per candidate edge:
+    # (neighbour + 1) * 2 + visible (distributed.pack_adjacency / unpack_adjacency)
+    code_h = torch.empty((m, k), dtype=torch.int32).pin_memory()
     tree2 = sg.NodeStore(2, capacity=N_NODES, device=local) if rank == 0 else None
 
     x_dev = torch.empty((m, 2), dtype=torch.float64, device=dev)
@@ -295,8 +296,7 @@ def run_ours(args):
             nb, vs = sg.prm_connect_knn(cc, tree2, k)
         else:
             nb, vs = sg.prm_connect_knn(cc, tree, k, queries=x_dev)
-        nbr_h.copy_(nb, non_blocking=True)                 # D2H of the adjacency block
-        vis_h.copy_(vs, non_blocking=True)
+        code_h.copy_(sg.distributed.pack_adjacency(nb, vs), non_blocking=True)   # D2H of the adjacency block
 
     # the user-facing call: the whole host-to-host step captured once (CapturedStep) and
     # replayed; H2D, store rebuild, connection and D2H all run inside every replay
@@ -324,7 +324,9 @@ def run_ours(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
         dist.barrier()
     e2e_ms = float(e2e_ms.item())
-    assert int(vis_h.sum()) == n_vis, "e2e result differs from the device-resident run"
+    nb_e2e, vs_e2e = sg.distributed.unpack_adjacency(code_h)
+    assert int(vs_e2e.sum()) == n_vis and torch.equal(nb_e2e, nbr.cpu()), \
+        "e2e result differs from the device-resident run"
 
     if rank != 0:
         if world > 1:
@@ -473,7 +475,8 @@ def run_ours(args):
         "e2e": {"value": world * edges_per_rank * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
-                "d2h_bytes_per_step": int(nbr_h.numel() * 8 + vis_h.numel())},
+                "d2h_bytes_per_step": int(code_h.numel() * 4),
+                "result": "packed adjacency int32 [m][k] = (neighbour + 1) * 2 + visible"},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": int(launches_per_step),
         "adjacency_gather": gather_kind,

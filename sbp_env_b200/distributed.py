@@ -49,10 +49,26 @@ def all_gather_rows(local, counts, group=None):
 
 def pack_adjacency(nbr, vis):
     """One int32 per candidate edge: ``(nbr + 1) * 2 + vis`` (nbr in [-1, 2^30)), so that the
-    neighbour block and its visibility mask travel in ONE collective of 4 bytes per edge
-    instead of two of 8 + 1."""
+    neighbour block and its visibility mask travel as 4 bytes per edge -- in ONE collective,
+    or in one device-to-host copy -- instead of 8 + 1.  CUDA tensors are packed by one launch
+    of the library's pack kernel (``sbp_adjacency_peer_scatter`` with itself as the only peer)."""
     import torch
 
+    if nbr.is_cuda and nbr.dtype == torch.int64 and vis.dtype in (torch.bool, torch.uint8):
+        import ctypes as C
+
+        from . import _lib
+        from .runtime import get_context, ptr
+
+        ctx = get_context(nbr.device.index)
+        ctx.use_torch_stream()
+        nbr = nbr.contiguous()
+        vis8 = vis.contiguous().view(torch.uint8)
+        out = torch.empty(nbr.shape, dtype=torch.int32, device=nbr.device)
+        dst = (C.c_void_p * 1)(out.data_ptr())
+        _lib.check(_lib.load().sbp_adjacency_peer_scatter(ctx.handle, ptr(nbr), ptr(vis8), nbr.numel(),
+                                                          dst, 1, 0), "sbp_adjacency_peer_scatter")
+        return out
     return (((nbr + 1) << 1) | vis.to(nbr.dtype)).to(torch.int32)
 
 

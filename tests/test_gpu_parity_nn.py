@@ -422,3 +422,22 @@ def test_near_filtered_scan_never_changes_results(sg, d):
                             assert np.array_equal(ix, oix), (variant, metric, closed, r, filt)
         finally:
             lib.sbp_tune(b"near_filter", 1)
+
+
+def test_pack_adjacency_device_kernel_roundtrip(sg):
+    """distributed.pack_adjacency on CUDA tensors (one launch of the pack kernel) equals the
+    torch expression and unpacks to the inputs, for sizes that are not multiples of 4 and for
+    empty neighbour slots (-1)."""
+    import torch
+
+    D = sg.distributed
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    for m, k in ((1, 1), (3, 7), (1001, 10), (4096, 4)):
+        nbr = torch.randint(-1, 1 << 29, (m, k), generator=g, device="cuda", dtype=torch.int64)
+        vis = torch.rand((m, k), generator=g, device="cuda") < 0.5
+        code = D.pack_adjacency(nbr, vis)
+        assert code.dtype == torch.int32 and code.shape == (m, k)
+        assert torch.equal(code, D.pack_adjacency(nbr.cpu(), vis.cpu()).cuda())
+        n2, v2 = D.unpack_adjacency(code)
+        assert torch.equal(n2, nbr) and torch.equal(v2, vis)
