@@ -523,10 +523,19 @@ def cpu_prm_sample(free, nodes, target_s):
     t0 = time.perf_counter()
     cpu_prm_rows(om, nodes, 0, rows, K_NN)
     dt = time.perf_counter() - t0
+    # the reference itself is single-threaded: one core on a smaller sample too
+    orc.set_threads(1)
+    rows1 = max(256, rows // (2 * cores))
+    t0 = time.perf_counter()
+    cpu_prm_rows(om, nodes, 0, rows1, K_NN)
+    dt1 = time.perf_counter() - t0
+    orc.set_threads(cores)
     return {"value": rows * K_NN / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"first {rows} of {len(nodes)} rows of the same workload (kNN k+1 against all "
                       f"{len(nodes)} nodes + visible of their {rows * K_NN} edges), oracle/oracle.c with "
-                      f"OpenMP on {cores} threads, {dt:.2f} s"}
+                      f"OpenMP on {cores} threads, {dt:.2f} s",
+            "value_1core": rows1 * K_NN / dt1,
+            "sample_1core": f"first {rows1} rows on one thread, {dt1:.2f} s"}
 
 
 def run_reference(args):
