@@ -11,7 +11,7 @@ from .engine import Engine, ImageEngine, RobotArmEngine, euclidean_dist  # noqa:
 from .node_store import NodeStore  # noqa: F401
 from .planning import (CapturedStep, PRMConnectGraph, feasible_batch, knn, near,  # noqa: F401
                        prm_connect_knn, prm_connect_radius, roadmap_edges_to_host, visible_batch)
-from . import distributed, planner_ops, samplers  # noqa: F401
+from . import distributed, planner_hooks, planner_ops, samplers  # noqa: F401
 from .roadmap import Roadmap, prm_get_solution  # noqa: F401
 from .stats import Stats  # noqa: F401
 

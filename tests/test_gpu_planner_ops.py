@@ -188,3 +188,71 @@ def test_birrt_join_and_prm_nearest_free(sg):
         if ref_dist(x, sub[i]) < 6.0:
             exp.append((k, i))
     assert got == exp
+
+
+def test_accelerate_rrt_hooks_on_a_planner_look_alike(sg):
+    """planner_hooks.accelerate_rrt with the REAL device node store and checker, on a planner
+    object that restates the reference's RRTPlanner members the hook touches (poses, nodes,
+    add_newnode :106-113, find_nearest_neighbour_idx :268-279, the linear
+    choose_least_cost_parent :173-196).  The hooked and the plain object grow identical trees
+    from the same seeded samples.  (The unmodified reference classes are hooked in
+    tests/test_reference_dropin.py, where the device is replaced by the oracle.)"""
+    import types
+
+    free = load_map("room1")
+    W, H = free.shape
+
+    class Node:
+        def __init__(self, pos):
+            self.pos, self.cost, self.parent = np.array(pos, dtype=np.float64), 0.0, None
+
+    class Planner:
+        def __init__(self, cc):
+            eng = types.SimpleNamespace(cc=cc, dist=ref_dist, get_dimension=lambda: 2)
+            self.args = types.SimpleNamespace(engine=eng, radius=11.0)
+            self.poses, self.nodes = np.empty((3000, 2)), []
+
+        def add_newnode(self, node):
+            self.poses[len(self.nodes)] = node.pos
+            self.nodes.append(node)
+
+        def find_nearest_neighbour_idx(self, pos, poses):
+            return int(np.argmin(np.linalg.norm(poses - pos, axis=1)))
+
+        def choose_least_cost_parent(self, newnode, nn=None, nodes=None, skip_optimality=False,
+                                     use_rtree=False, poses=None):
+            cc = self.args.engine.cc
+            idx, cost = ref_choose_parent(lambda a, b: cc.visible(a, b), self.poses[: len(nodes)],
+                                          [n.cost for n in nodes], newnode.pos,
+                                          None if nn is None else nodes.index(nn), self.args.radius)
+            newnode.cost, newnode.parent = cost, nodes[idx]
+            return newnode, nodes[idx]
+
+    def grow(hooked):
+        cc = sg.ImgCollisionChecker(map_png("room1"))
+        vis0 = cc.stats.visible_cnt                 # process-global Stats: count the delta
+        pl = Planner(cc)
+        pl.add_newnode(Node((100.0, 100.0)))
+        store = sg.planner_hooks.accelerate_rrt(pl) if hooked else None
+        rng = np.random.default_rng(5)
+        while len(pl.nodes) < 700:
+            r = rng.random(2) * [W, H]
+            if not cc.feasible(r):
+                continue
+            nn = pl.nodes[pl.find_nearest_neighbour_idx(r, pl.poses[: len(pl.nodes)])]
+            v = r - nn.pos
+            newpos = nn.pos + min(ref_dist(nn.pos, r), 10.0) * v / np.linalg.norm(v)
+            if not cc.visible(nn.pos, newpos):
+                continue
+            newnode, _ = pl.choose_least_cost_parent(Node(newpos), nn, nodes=pl.nodes)
+            pl.add_newnode(newnode)
+        return pl, store, cc.stats.visible_cnt - vis0
+
+    a, _, vis_a = grow(False)
+    b, store, vis_b = grow(True)
+    assert np.array_equal(a.poses[:700], b.poses[:700])
+    assert [n.cost for n in a.nodes] == [n.cost for n in b.nodes]
+    assert [None if n.parent is None else a.nodes.index(n.parent) for n in a.nodes] == \
+           [None if n.parent is None else b.nodes.index(n.parent) for n in b.nodes]
+    assert len(store) == 700 and np.array_equal(store.poses, b.poses[:700])
+    assert vis_a == vis_b                          # same Stats accounting of the edge checks

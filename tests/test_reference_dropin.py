@@ -175,6 +175,82 @@ def test_sampler_prescreen_keeps_the_seeded_run_and_saves_launches(ref, monkeypa
     assert len(launches) < len(plain) // 5
 
 
+class FakeNodeStore:
+    """Stands in for NodeStore (no CUDA device in the build container): same methods, answers
+    from numpy / the oracle.  The real store is checked against the same oracle by -m gpu."""
+
+    def __init__(self, dim, om):
+        self.dim, self.om, self.rows = dim, om, []
+        self.nearest_calls = self.near_visible_calls = 0
+
+    def __len__(self):
+        return len(self.rows)
+
+    def extend(self, X):
+        self.rows.extend(np.asarray(X, dtype=np.float64).reshape(-1, self.dim).copy())
+
+    def append(self, x):
+        self.extend(np.asarray(x).reshape(1, self.dim))
+        return len(self.rows) - 1
+
+    def poses_rows(self, idx):
+        return np.array([self.rows[int(i)] for i in idx]).reshape(-1, self.dim)
+
+    def nearest(self, x):
+        self.nearest_calls += 1
+        return int(orc.knn(np.array(self.rows), np.asarray(x, dtype=np.float64).reshape(1, self.dim), 1)[0][0, 0])
+
+    def near_visible(self, cc, x, r, metric="xy", closed=True, direction=0, cap=256):
+        self.near_visible_calls += 1
+        P = np.array(self.rows)
+        x = np.asarray(x, dtype=np.float64).reshape(1, self.dim)
+        rp, idx = orc.near(P, x, r, metric, closed)
+        X = np.repeat(x[:, :2], len(idx), 0)
+        vis = self.om.visible2d(X, P[idx][:, :2]) if direction == 0 else self.om.visible2d(P[idx][:, :2], X)
+        cc.stats.visible_cnt += len(idx)
+        return idx, vis
+
+
+@pytest.mark.parametrize("planner_id", ["rrt", "informedrrt"])
+def test_accelerate_rrt_hooks_keep_the_seeded_run(ref, planner_id):
+    """planner_hooks.accelerate_rrt on an unmodified reference planner object
+    -- nearest through the node store, choose_least_cost_parent through one fused
+    near + visible query -- gives the identical seeded run (nodes, c_max, Stats), and the
+    planner's own O(N) loop over engine.dist no longer runs."""
+    from sbp_env import engine
+    import sbp_env_b200 as sg
+
+    img = ref_shims.reference_map_path("room1.png")
+    fac = lambda args: engine.ImageEngine(args, img)
+    swap = lambda cc: sg.ImgCollisionChecker(cc.image_fname)
+    dist_calls = []
+
+    def counting_engine(args):
+        e = engine.ImageEngine(args, img)
+        inner = e.dist
+        e.dist = lambda *a: (dist_calls.append(1), inner(*a))[1]
+        return e
+
+    a = run(planner_id, counting_engine, swap, "100,100", "350,350", 300)
+    plain_calls = len(dist_calls)
+    del dist_calls[:]
+    stores = []
+
+    def hook(env):
+        om = orc.Map(np.asarray(env.args.engine.cc._img) == 1)
+        stores.append(sg.planner_hooks.accelerate_rrt(env.planner, store=FakeNodeStore(2, om)))
+
+    b = run(planner_id, counting_engine, swap, "100,100", "350,350", 300, before_run=hook)
+    _same(a, b)
+    pa, pb = a["env"].planner, b["env"].planner
+    assert [n.cost for n in pa.nodes] == [n.cost for n in pb.nodes]
+    assert [None if n.parent is None else tuple(n.parent.pos) for n in pa.nodes] == \
+           [None if n.parent is None else tuple(n.parent.pos) for n in pb.nodes]
+    st = stores[0]
+    assert len(st) == len(pb.nodes) and st.near_visible_calls >= 300 and st.nearest_calls >= 300
+    assert len(dist_calls) < plain_calls // 4          # the O(N) engine.dist loop is gone
+
+
 def test_seeded_arm_run_identical(ref):
     from sbp_env import engine
     from sbp_env_b200 import RobotArm4dCollisionChecker
