@@ -216,7 +216,10 @@ __global__ void k_rows_from_tiles(MapView mv, int WR, uint32_t n_row_words, uint
 int32_t sbp_map_ensure_rows(sbp_map *m) {
     if (m->d_rows) return SBP_OK;
     sbp_ctx *ctx = m->ctx;
-    const int WR = (m->view.W + 31) / 32;
+    // an ODD number of words per row: lanes that walk different rows at similar x then fall
+    // into different shared-memory banks (bank = (y * WR + (x >> 5)) mod 32; with WR = 32, the
+    // 1024-pixel arm map, 78 % of the wavefronts were bank conflicts)
+    const int WR = ((m->view.W + 31) / 32) | 1;
     // padded to whole 16-byte units: the bulk copy that stages it moves multiples of 16 bytes
     const uint64_t nw = ((uint64_t)WR * (uint64_t)m->view.H + 3ull) & ~3ull;
     SBP_REQUIRE(nw <= 0xffffffffull / 4ull, "row-major map copy too large for 32-bit word indexing");
