@@ -22,6 +22,8 @@ passed through to the original method.
 """
 from __future__ import annotations
 
+import numpy as np
+
 from . import planner_ops
 from .node_store import NodeStore
 
@@ -101,5 +103,48 @@ def accelerate_rrt(planner, store=None):
     planner.find_nearest_neighbour_idx = find_nearest_neighbour_idx
     planner.choose_least_cost_parent = choose_least_cost_parent
     planner._sbp_accelerated = True
+    planner._sbp_store = store
+    return store
+
+
+def accelerate_prm(planner, store=None, chunk_rows: int = 4096):
+    """Hook a reference ``PRMPlanner`` object (planners/prmPlanner.py): ``build_graph``
+    (:80-101) -- for every node a Python scan of ALL nodes (``nearest_neighbours``, :28-44) and
+    one ``cc.visible`` call per neighbour -- becomes, per block of ``chunk_rows`` nodes, one
+    batched radius query (``NodeStore.near``: all dims, strict ``<``, index-ascending, exactly
+    the order of the reference's double loop) and one ``visible_batch`` launch over the
+    candidate pairs ``visible(m_g.pos, v.pos)``.  The edges are then inserted into the planner's
+    own networkx ``DiGraph`` in the reference's order with ``engine.dist`` weights, so that
+    ``get_solution`` (and anything else that reads ``planner.graph``) sees the identical graph.
+
+    The radius is the reference's PRM* radius ``gamma * (log(n+1)/(n+1))^(1/d)`` (:87-89), which
+    for the shipped maps exceeds the map: the candidate set is then all n^2 pairs,
+    which is why the rows are processed in blocks.  Returns the node store."""
+    args = planner.args
+    cc = args.engine.cc
+    d = args.engine.get_dimension()
+    if store is None:
+        store = NodeStore(d, capacity=len(planner.poses), device=getattr(cc, "_device", 0))
+
+    def build_graph():
+        n = len(planner.nodes)
+        radius = planner.gamma * np.power(np.log(n + 1) / (n + 1), 1 / d)       # :87-89
+        poses = np.ascontiguousarray(planner.poses[:n], dtype=np.float64)
+        if len(store) != n:                          # (re)fill: PRM only appends between builds
+            if len(store) > n:
+                store.truncate(0)
+            store.extend(poses[len(store):])
+        nodes, dist, graph = planner.nodes, args.engine.dist, planner.graph
+        for first in range(0, n, chunk_rows):
+            rows = poses[first:first + chunk_rows]
+            row_ptr, idx = store.near(rows, float(radius), metric="full", closed=False)
+            dst = np.repeat(np.arange(first, first + len(rows), dtype=np.int64), np.diff(row_ptr))
+            keep = idx != dst                        # `if m_g is v: continue` (:94-95)
+            src, dst = idx[keep], dst[keep]
+            vis = np.asarray(cc.visible_batch(poses[src], poses[dst]), dtype=bool)   # visible(m_g, v), :97
+            for a, b in zip(src[vis].tolist(), dst[vis].tolist()):
+                graph.add_weighted_edges_from([(nodes[a], nodes[b], dist(nodes[a].pos, nodes[b].pos))])
+
+    planner.build_graph = build_graph
     planner._sbp_store = store
     return store

@@ -251,6 +251,54 @@ def test_accelerate_rrt_hooks_keep_the_seeded_run(ref, planner_id):
     assert len(dist_calls) < plain_calls // 4          # the O(N) engine.dist loop is gone
 
 
+def test_accelerate_prm_builds_the_identical_graph(ref, monkeypatch):
+    """planner_hooks.accelerate_prm: build_graph through the batched radius query and one
+    visible_batch launch per block gives the reference's DiGraph -- same edges in the same
+    insertion order, same weights -- and therefore the same get_solution; the per-pair
+    cc.visible calls of the reference's double loop are gone."""
+    from sbp_env import engine
+    import sbp_env_b200 as sg
+    import sbp_env_b200.collision_checker as gcc
+
+    img = ref_shims.reference_map_path("maze1.png")
+    fac = lambda args: sg.ImageEngine(args, img)
+    single, batched = [], []
+    inner = gcc.ImgCollisionChecker._visible_host
+
+    def counting(self, P, Q):
+        (single if len(P) == 1 else batched).append(len(P))
+        return inner(self, P, Q)
+
+    monkeypatch.setattr(gcc.ImgCollisionChecker, "_visible_host", counting)
+
+    class FakeNear(FakeNodeStore):
+        def truncate(self, n):
+            del self.rows[n:]
+
+        def near(self, X, r, metric="full", closed=False):
+            return orc.near(np.array(self.rows), np.asarray(X, dtype=np.float64), r, metric, closed)
+
+    outs = []
+    for hooked in (False, True):
+        del single[:], batched[:]
+        r = run("prm", fac, None, "25,25", "290,290", 70)
+        pl = r["env"].planner
+        if hooked:
+            om = orc.Map(np.asarray(pl.args.engine.cc._img) == 1)
+            sg.planner_hooks.accelerate_prm(pl, store=FakeNear(2, om), chunk_rows=16)
+        before = len(single)
+        pl.build_graph()
+        in_build = len(single) - before
+        outs.append(dict(run=r, edges=[(tuple(u.pos), tuple(v.pos), w["weight"]) for u, v, w in pl.graph.edges(data=True)],
+                         sol=pl.get_solution(), singles=in_build, batches=list(batched),
+                         vis_cnt=r["env"].args.engine.cc.stats.visible_cnt))
+    _same(outs[0]["run"], outs[1]["run"])
+    assert outs[0]["edges"] == outs[1]["edges"] and len(outs[0]["edges"]) > 50
+    assert outs[0]["sol"] == outs[1]["sol"]
+    assert outs[0]["singles"] > 1000 and outs[1]["singles"] == 0 and len(outs[1]["batches"]) == 5
+    assert outs[0]["vis_cnt"] == outs[1]["vis_cnt"]
+
+
 def test_seeded_arm_run_identical(ref):
     from sbp_env import engine
     from sbp_env_b200 import RobotArm4dCollisionChecker
