@@ -1,5 +1,5 @@
-// nodes.cu -- device-resident append-only node store; K4 brute-force kNN with
-// per-thread top-k and shuffle merge; K5 radius query with ordered compaction.
+// nodes.cu -- device-resident append-only node store and the batched planner primitives
+// that gather candidate edges from it.  The queries live in knn.cu (K4) and near.cu (K5).
 //
 // Reference behaviour restated (file:line under /root/reference/sbp_env/):
 //   planners' `poses` arrays and appends      planners/rrtPlanner.py:24-26, :106-113
@@ -20,7 +20,6 @@
 
 #include "common.cuh"
 #include "device_fns.cuh"
-#include "filter.cuh"
 
 #define KNN_TPB 128        // queries per CTA in the batched radius kernel
 #define KNN_TILE 1024      // nodes staged in shared memory per step
@@ -207,1466 +206,6 @@ extern "C" int32_t sbp_nodes_rows_device(sbp_nodes *s, int64_t first, int64_t co
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
-}
-
-// --------------------------------------------------------- distance core ----
-// Per-thread sorted list of the K best (d, idx), d ascending, ties keep arrival
-// order (callers feed indices in ascending order, so ties keep the lower index).
-template <int K>
-struct TopK {
-    double d[K];
-    int32_t i[K];
-    double bound2;   // round-up(d[K-1]^2): candidates with d^2 > bound2 are rejected
-    double seed2;    // a-priori bound used while the list is not full (inf = none)
-    __device__ __forceinline__ void init(double seed = INFINITY) {
-#pragma unroll
-        for (int t = 0; t < K; ++t) { d[t] = INFINITY; i[t] = -1; }
-        bound2 = seed2 = seed;
-    }
-    // Empty slots are (inf, -1) and rank after every real entry, including real entries
-    // whose distance is +inf (fp64 overflow of d^2): those fill the list in index order,
-    // as a stable argsort of an all-inf row does.
-    //
-    // Branch-free sorted insertion: r_t = "entry t ranks before the new one" (real and
-    // d[t] <= dd; ties keep the earlier arrival = lower index) is a prefix of trues, and
-    //     new[t] = r_t ? old[t] : (r_{t-1} ? (dd, idx) : old[t-1]).
-    // Pure predicate/select code, ~8 instructions per slot (the earlier `if (!placed)`
-    // formulation made ptxas copy the whole list per step: ~30 instructions per slot).
-    __device__ __forceinline__ void insert_sorted(double dd, int32_t idx) {
-        bool r_cur = i[K - 1] >= 0 && d[K - 1] <= dd;        // r_{K-1}: true => list full, no room
-#pragma unroll
-        for (int t = K - 1; t >= 1; --t) {
-            const bool r_prev = i[t - 1] >= 0 && d[t - 1] <= dd;
-            const double nd = r_prev ? dd : d[t - 1];
-            const int32_t ni = r_prev ? idx : i[t - 1];
-            d[t] = r_cur ? d[t] : nd;
-            i[t] = r_cur ? i[t] : ni;
-            r_cur = r_prev;
-        }
-        d[0] = r_cur ? d[0] : dd;
-        i[0] = r_cur ? i[0] : idx;
-    }
-    __device__ __forceinline__ void offer(double d2, int32_t idx) {
-        if (d2 <= bound2 && idx >= 0) {
-            insert_sorted(__dsqrt_rn(d2), idx);
-            bound2 = i[K - 1] < 0 ? seed2 : __dmul_ru(d[K - 1], d[K - 1]);
-        }
-    }
-    // insert an already square-rooted distance (merging partial lists)
-    __device__ __forceinline__ void offer_sorted(double dd, int32_t idx) { insert_sorted(dd, idx); }
-    // remove the head (used by the block merge)
-    __device__ __forceinline__ void pop() {
-#pragma unroll
-        for (int t = 0; t + 1 < K; ++t) { d[t] = d[t + 1]; i[t] = i[t + 1]; }
-        d[K - 1] = INFINITY; i[K - 1] = -1;
-    }
-};
-
-// numpy sorts NaN distances last, in index order (np.argsort, stable): a row the scan could
-// not fill -- fewer than k nodes at a non-NaN distance, e.g. a NaN query -- is completed
-// with the lowest-index nodes whose distance to the query is NaN (distance reported as NaN).
-// A difference is NaN iff one side is NaN or both are the same infinity; squares and sums of
-// non-NaN terms never produce NaN.  Called by the thread that wrote the row; rare path.
-__device__ __noinline__ void pad_nan_row(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                                         int d, const double *__restrict__ xq, int k,
-                                         int64_t *irow, double *drow) {
-    int cnt = 0;
-    while (cnt < k && irow[cnt] >= 0) ++cnt;
-    for (int64_t i = 0; i < n && cnt < k; ++i) {
-        bool isnan_d = false;
-        for (int j = 0; j < d; ++j) {
-            const double df = soa[(int64_t)j * capacity + i] - xq[j];
-            isnan_d |= df != df;
-        }
-        if (isnan_d) {
-            irow[cnt] = i;
-            if (drow) drow[cnt] = __longlong_as_double(0x7ff8000000000000LL);
-            ++cnt;
-        }
-    }
-}
-
-// ---------------------------------------------- K4a: batched, thread/query ---
-// grid = (ceil(m / TPB), S).  CTA (bx, s) scans node chunk s for its TPB queries; node
-// tiles are staged in shared memory (SoA) and read by broadcast.
-//
-// Two-phase scan per block of 32 nodes.  Phase 1 is branch-free with the top-k state
-// read-only (a fused scan+insert loop made ptxas copy the whole list between unrolled
-// iterations: ~45 instructions per pair) and only FLAGS candidates in a 32-bit mask.
-// Phase 2 revisits the flagged nodes in lock-step over the warp and decides them exactly
-// in fp64 (offer()); stale or spurious flags are harmless because offer() re-checks.
-//
-// fp32 prefilter (default).  Phase 1 runs on an fp32 shadow of the nodes: d2f =
-// fma(dy,dy,dx*dx) is compared with a per-query threshold thr_f that is CONSERVATIVE:
-// with u = 2^-24, M = max |coordinate| and a = 4*M*u*sqrt(D) (conversion + subtraction
-// error of every component), the fp32 value of a pair whose exact distance is r satisfies
-// d2f <= (r + a)^2 (1+u)^D, so every pair with fp64 d^2 < bound2 has
-// d2f <= thr_f := round_up((sqrt(bound2) + a)^2 (1 + 1e-6)).  The prefilter can therefore
-// only add false positives (a relative band of ~1e-6), never lose a neighbour; results
-// stay bit-exact while the scan moves from the fp64 pipe (64 lanes/SM) to the fp32 pipe
-// (128 lanes/SM).  It is bypassed (pure fp64 scan) when coordinates are too large for
-// fp32 squares (M >= 1e15) or when sbp_tune("knn_prefilter", 0) is set.
-__device__ __forceinline__ float knn_thr32(double bound2, double a) {
-    if (!(bound2 < INFINITY)) return INFINITY;
-    double r = sqrt(bound2) + a;
-    return __double2float_ru(r * r * (1.0 + 1e-6));
-}
-
-template <int D, int K, int TPB>
-__global__ void __launch_bounds__(TPB)
-k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
-              const double *__restrict__ maxabs, int prefilter, int64_t capacity, int64_t n, int S,
-              const double *__restrict__ X, int64_t m, const double *__restrict__ seed2,
-              double *__restrict__ pd, int32_t *__restrict__ pi,
-              const uint8_t *__restrict__ redo) {
-    // as the fallback of the filter path: only the flagged blocks of 32 queries (TPB == 32)
-    if (redo && !redo[blockIdx.x]) return;
-    constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
-    __shared__ double tile[D][TILE];  // fp64 tile, or the fp32 tile in the same storage
-    float(*tile32)[TILE] = reinterpret_cast<float(*)[TILE]>(&tile[0][0]);
-    const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    const int s = blockIdx.y;
-    const int64_t chunk = (n + S - 1) / S;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    double qv[D];
-    float qf[D];
-    double qmax = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        qv[j] = q < m ? X[q * D + j] : 0.0;
-        qf[j] = (float)qv[j];
-        double av = qv[j] != qv[j] ? INFINITY : fabs(qv[j]);
-        qmax = av > qmax ? av : qmax;
-    }
-    const double M = *maxabs;
-    const bool use32 = prefilter && M < 1e15;              // block-uniform
-    const double mm = M > qmax ? M : qmax;
-    const bool lane32 = mm < 1e15;                         // this lane's fp32 squares are safe
-    const double a_err = 4.0 * mm * 5.9604644775390625e-8 * sqrt((double)D) * (1.0 + 1e-6);
-    TopK<K> top;
-    top.init((seed2 && q < m) ? seed2[q] : INFINITY);
-    float thr_f = (use32 && lane32) ? knn_thr32(top.bound2, a_err) : INFINITY;
-    for (int64_t t0 = c0; t0 < c1; t0 += TILE) {
-        int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
-        __syncthreads();
-        if (use32) {
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                for (int t = threadIdx.x; t < cnt; t += TPB)
-                    tile32[j][t] = soa32[(int64_t)j * capacity + t0 + t];
-        } else {
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                for (int t = threadIdx.x; t < cnt; t += TPB)
-                    tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
-        }
-        __syncthreads();
-        for (int b0 = 0; b0 < cnt; b0 += 32) {
-            const int bn = cnt - b0 < 32 ? cnt - b0 : 32;
-            const double bound2 = top.bound2;
-            uint32_t mask = 0;
-            if (use32) {
-                if (bn == 32) {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        float sf = 0.f;
-#pragma unroll
-                        for (int j = 0; j < D; ++j) {
-                            float df = tile32[j][b0 + t] - qf[j];
-                            sf = j == 0 ? df * df : fmaf(df, df, sf);
-                        }
-                        mask |= (sf <= thr_f) ? (1u << t) : 0u;
-                    }
-                } else {
-                    for (int t = 0; t < bn; ++t) {
-                        float sf = 0.f;
-#pragma unroll
-                        for (int j = 0; j < D; ++j) {
-                            float df = tile32[j][b0 + t] - qf[j];
-                            sf = j == 0 ? df * df : fmaf(df, df, sf);
-                        }
-                        mask |= (sf <= thr_f) ? (1u << t) : 0u;
-                    }
-                }
-            } else {
-                if (bn == 32) {
-#pragma unroll
-                    for (int t = 0; t < 32; ++t) {
-                        double pv[D];
-#pragma unroll
-                        for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
-                        mask |= (dist2_full<D>(pv, qv) <= bound2) ? (1u << t) : 0u;
-                    }
-                } else {
-                    for (int t = 0; t < bn; ++t) {
-                        double pv[D];
-#pragma unroll
-                        for (int j = 0; j < D; ++j) pv[j] = tile[j][b0 + t];
-                        mask |= (dist2_full<D>(pv, qv) <= bound2) ? (1u << t) : 0u;
-                    }
-                }
-            }
-            // lock-step over the warp: round r decides every lane's r-th flagged node, so
-            // insertions of different queries share one pass through offer()
-            while (__any_sync(0xffffffffu, mask != 0u)) {
-                double d2 = INFINITY;
-                int32_t id = -1;
-                if (mask) {
-                    const int t = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    double pv[D];
-#pragma unroll
-                    for (int j = 0; j < D; ++j)
-                        pv[j] = use32 ? soa[(int64_t)j * capacity + t0 + b0 + t] : tile[j][b0 + t];
-                    d2 = dist2_full<D>(pv, qv);
-                    id = (int32_t)(t0 + b0 + t);
-                }
-                top.offer(d2, id);
-            }
-            if (use32 && top.bound2 != bound2) thr_f = lane32 ? knn_thr32(top.bound2, a_err) : INFINITY;
-        }
-    }
-    if (q < m) {
-        int64_t base = (q * S + s) * K;
-#pragma unroll
-        for (int t = 0; t < K; ++t) { pd[base + t] = top.d[t]; pi[base + t] = top.i[t]; }
-    }
-}
-
-// --------------------------------------- K4a': seeded filter + exact refine ---
-// (scan, thresholds and the centred shadow: filter.cuh)
-template <int D, int NW, int UNR, int FQ>
-__global__ void __launch_bounds__(NW * 32)
-k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
-             int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
-             const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
-             int32_t *__restrict__ ccount) {
-    constexpr int TPB = NW * 32;
-    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
-    const int s = blockIdx.y;
-    const int64_t c0 = (int64_t)s * chunk;                       // multiple of the tile
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    float nq2[FQ][D];        // -2 q^_j
-    float thr[FQ];
-    int cc[FQ];
-    int32_t *cl[FQ];         // this (query, chunk)'s candidate list
-#pragma unroll
-    for (int r = 0; r < FQ; ++r) {
-        const int64_t q = qb + (int64_t)r * TPB;
-        const bool live = q < m;
-        const bool usable = filter_query_setup<D>(info, X + (live ? q : 0) * D, live,
-                                                  live ? seed2[q] : -1.0, nq2[r], thr[r]);
-        cc[r] = (live && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
-        cl[r] = cand + ((live ? q : 0) * S + s) * (int64_t)C;
-    }
-    filter_scan<D, NW, UNR, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
-        cl[r][cc[r] < C ? cc[r] : C - 1] = g;                        // an overflowing list is never read
-        ++cc[r];
-    });
-#pragma unroll
-    for (int r = 0; r < FQ; ++r) {
-        const int64_t q = qb + (int64_t)r * TPB;
-        if (q < m) ccount[q * S + s] = cc[r];
-    }
-}
-
-// Radius query on the same scan (K5'): a group that passes the conservative fp32 test has
-// its 8 nodes decided exactly in fp64 (near_d2 / near_in, the comparison of the unfiltered
-// kernels); PASS 0 counts the matches of (query, chunk), PASS 1 writes them at the scanned
-// offsets, ascending.  A query that cannot be filtered gets thr = +inf, i.e. every group is
-// decided exactly: slower, same result.  DD = coordinates the metric uses (2 for XY).
-template <int D, bool XY, int PASS, int NW>
-__global__ void __launch_bounds__(NW * 32)
-k_near_filtered(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
-                const double *__restrict__ soa, int64_t capacity, int64_t n, int S, int64_t chunk,
-                const double *__restrict__ X, int64_t m, double thr2, int closed,
-                int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-                int64_t *__restrict__ idx, int64_t idx_capacity, const int64_t *__restrict__ needed) {
-    constexpr int DD = XY ? 2 : D;
-    constexpr int FQ = FILTER_Q, TPB = NW * 32;
-    if (PASS == 1 && *needed > idx_capacity) return;
-    const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;
-    const int s = blockIdx.y;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    float nq2[FQ][DD];
-    float thr[FQ];
-    int64_t pos[FQ];         // PASS 0: matches so far; PASS 1: next output slot
-#pragma unroll
-    for (int r = 0; r < FQ; ++r) {
-        const int64_t q = qb + (int64_t)r * TPB;
-        const bool live = q < m;
-        const bool usable = filter_query_setup<DD>(info, X + (live ? q : 0) * D, live, thr2, nq2[r], thr[r]);
-        if (live && !usable) {                                       // decide every node exactly:
-            thr[r] = INFINITY;                                       // t = |n^|^2 <= inf always passes
-#pragma unroll
-            for (int j = 0; j < DD; ++j) nq2[r][j] = 0.0f;
-        }
-        pos[r] = (PASS == 1 && live) ? offsets[q * S + s] : 0;
-    }
-    filter_scan<DD, NW, 1, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
-        const int64_t q = qb + (int64_t)r * TPB;
-        double qv[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) qv[j] = j < DD ? X[q * D + j] : 0.0;
-        const int64_t b = (int64_t)g * 8;
-#pragma unroll 1
-        for (int u = 0; u < 8; ++u) {
-            const int64_t id = b + u;
-            if (id >= c1) break;
-            double pv[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) pv[j] = j < DD ? soa[(int64_t)j * capacity + id] : 0.0;
-            if (near_in(near_d2<D, XY>(pv, qv), thr2, closed)) {
-                if (PASS == 1) idx[pos[r]] = id;
-                ++pos[r];
-            }
-        }
-    });
-    if (PASS == 0) {
-#pragma unroll
-        for (int r = 0; r < FQ; ++r) {
-            const int64_t q = qb + (int64_t)r * TPB;
-            if (q < m) counts[q * S + s] = pos[r];
-        }
-    }
-}
-
-// One thread per query: exact fp64 decision of the candidate groups, chunks and groups in
-// ascending node order (ties keep the lower index).  A query that cannot be answered from
-// its lists flags its block of 32 queries for the one-kernel scan.
-template <int D, int K>
-__global__ void __launch_bounds__(64)
-k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
-             const double *__restrict__ X, int64_t m, const double *__restrict__ seed2, int S,
-             int C, const int32_t *__restrict__ cand, const int32_t *__restrict__ ccount, int k,
-             int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo) {
-    const unsigned FULL = 0xffffffffu;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = q < m;
-    if (live) {
-        bool over = false;
-        for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
-        if (over) { redo[q >> 5] = 1; live = false; }
-    }
-    double qv[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = live ? X[q * D + j] : 0.0;
-    TopK<K> top;
-    top.init(live ? seed2[q] : -1.0);
-    // The warp walks its 32 candidate lists in lock-step: every lane evaluates the 8 nodes of
-    // its t-th group, then the lanes insert their passing nodes round by round, so that the
-    // ~100-instruction sorted insertion always runs with many lanes active.
-    for (int s = 0; s < S; ++s) {
-        const int c = live ? ccount[q * S + s] : 0;
-        const int32_t *cl = cand + ((live ? q : 0) * S + s) * (int64_t)C;
-        const int cmax = __reduce_max_sync(FULL, c);
-        // the candidate id of the next iteration is fetched one iteration ahead (the loop is
-        // bound by the latency of its dependent loads: list entry -> node coordinates)
-        int32_t g_next = 0 < c ? cl[0] : -1;
-        for (int t = 0; t < cmax; ++t) {
-            const int64_t b = g_next >= 0 ? (int64_t)g_next * 8 : n;
-            g_next = t + 1 < c ? cl[t + 1] : -1;
-            double d2[8];
-            uint32_t mask = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const bool ok = b + u < n;
-                const int64_t id = ok ? b + u : 0;
-                double pv[D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + id];
-                d2[u] = dist2_full<D>(pv, qv);
-                mask |= (ok && d2[u] <= top.bound2) ? (1u << u) : 0u;
-            }
-            while (__any_sync(FULL, mask != 0u)) {
-                const int u = mask ? __ffs(mask) - 1 : 8;
-                mask &= mask - 1;
-                double dd = INFINITY;
-#pragma unroll
-                for (int v = 0; v < 8; ++v) dd = u == v ? d2[v] : dd;
-                top.offer(dd, u < 8 ? (int32_t)(b + u) : -1);
-            }
-        }
-    }
-    if (!live) return;
-#pragma unroll
-    for (int t = 0; t < K; ++t)
-        if (t < k) {
-            idx[q * k + t] = top.i[t];
-            if (dist) dist[q * k + t] = top.i[t] >= 0 ? top.d[t] : INFINITY;
-        }
-    int have = 0;                             // (static indexing keeps the list in registers)
-#pragma unroll
-    for (int t = 0; t < K; ++t) have += (t < k && top.i[t] >= 0) ? 1 : 0;
-    if (have < k)
-        pad_nan_row(soa, capacity, n, D, X + q * D, k, idx + q * k, dist ? dist + q * k : nullptr);
-}
-
-// ------------------------------------------------- K4b: wide, CTA/(q,chunk) ---
-// For few queries over many nodes (RRT nearest / argsort[:20]): threads stride
-// the chunk with coalesced SoA loads, then the CTA merges its per-thread lists by
-// repeatedly extracting the (d, idx)-smallest head with warp shuffles.
-
-// K rounds of block-wide argmin over the list heads, key (d, idx).  Round r's winner
-// goes to the partial buffers (pd/pi) or, when idx64 is given, to the final row.
-template <int K>
-__device__ __forceinline__ void block_merge_topk(TopK<K> &top, double *pd, int32_t *pi,
-                                                 int64_t *idx64, double *dist, int k_out) {
-    __shared__ double wd[WIDE_TPB / 32];
-    __shared__ int32_t wi[WIDE_TPB / 32];
-    __shared__ int wl[WIDE_TPB / 32];
-    __shared__ int win_thread;
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rounds = idx64 ? k_out : K;
-    for (int r = 0; r < rounds; ++r) {
-        double bd = top.d[0];
-        int32_t bi = top.i[0];
-        int bl = threadIdx.x;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            double od = __shfl_xor_sync(FULL, bd, o);
-            int32_t oi = __shfl_xor_sync(FULL, bi, o);
-            int ol = __shfl_xor_sync(FULL, bl, o);
-            // empty heads (idx -1, d inf) lose against anything real
-            bool take = (oi >= 0) && (bi < 0 || od < bd || (od == bd && oi < bi));
-            if (take) { bd = od; bi = oi; bl = ol; }
-        }
-        if (lane == 0) { wd[warp] = bd; wi[warp] = bi; wl[warp] = bl; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double fd = wd[0]; int32_t fi = wi[0]; int fl = wl[0];
-            for (int w = 1; w < WIDE_TPB / 32; ++w) {
-                bool take = (wi[w] >= 0) && (fi < 0 || wd[w] < fd || (wd[w] == fd && wi[w] < fi));
-                if (take) { fd = wd[w]; fi = wi[w]; fl = wl[w]; }
-            }
-            if (idx64) {
-                idx64[r] = fi;
-                if (dist) dist[r] = fi >= 0 ? fd : INFINITY;
-            } else {
-                pd[r] = fi >= 0 ? fd : INFINITY;
-                pi[r] = fi;
-            }
-            win_thread = fi >= 0 ? fl : -1;
-        }
-        __syncthreads();
-        if ((int)threadIdx.x == win_thread) top.pop();
-        __syncthreads();
-    }
-}
-
-template <int D, int K>
-__global__ void __launch_bounds__(WIDE_TPB)
-k_knn_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
-           const double *__restrict__ X, int64_t m, double *__restrict__ pd,
-           int32_t *__restrict__ pi, int64_t *__restrict__ idx, double *__restrict__ dist,
-           int k_out) {
-    const int64_t q = blockIdx.x;
-    const int s = blockIdx.y;
-    const int64_t chunk = (n + S - 1) / S;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    double qv[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = X[q * D + j];
-    TopK<K> top;
-    top.init();
-    // blocks of UNR nodes per thread: all loads issued first (memory-level
-    // parallelism), flags gathered branch-free, flagged nodes inserted afterwards
-    constexpr int UNR = 8;
-    for (int64_t t0 = c0 + threadIdx.x; t0 < c1; t0 += (int64_t)WIDE_TPB * UNR) {
-        double pv[UNR][D];
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            int64_t t = t0 + (int64_t)u * WIDE_TPB;
-#pragma unroll
-            for (int j = 0; j < D; ++j) pv[u][j] = t < c1 ? soa[(int64_t)j * capacity + t] : INFINITY;
-        }
-        double d2[UNR];
-        uint32_t mask = 0;
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-            d2[u] = dist2_full<D>(pv[u], qv);
-            mask |= (t0 + (int64_t)u * WIDE_TPB < c1 && d2[u] <= top.bound2) ? (1u << u) : 0u;
-        }
-        if (mask) {
-#pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (mask & (1u << u)) top.offer(d2[u], (int32_t)(t0 + (int64_t)u * WIDE_TPB));
-        }
-    }
-    if (S == 1) {
-        block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
-        if (threadIdx.x == 0 && idx[q * k_out + k_out - 1] < 0)
-            pad_nan_row(soa, capacity, n, D, X + q * D, k_out, idx + q * k_out,
-                        dist ? dist + q * k_out : nullptr);
-    } else {
-        block_merge_topk<K>(top, pd + (q * S + s) * K, pi + (q * S + s) * K, nullptr, nullptr, 0);
-    }
-}
-
-// Second level of the wide path: one CTA per query merges its S partial lists
-// (S up to 1024; thread t takes lists t, t+256, ...; ascending chunk order keeps
-// the lower index first among equal distances).
-template <int K>
-__global__ void __launch_bounds__(WIDE_TPB)
-k_knn_merge_wide(const double *__restrict__ pd, const int32_t *__restrict__ pi, int S, int k_out,
-                 int64_t *__restrict__ idx, double *__restrict__ dist,
-                 const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
-                 const double *__restrict__ X) {
-    const int64_t q = blockIdx.x;
-    TopK<K> top;
-    top.init();
-    for (int s = threadIdx.x; s < S; s += WIDE_TPB) {
-        const double *d0 = pd + (q * S + s) * K;
-        const int32_t *i0 = pi + (q * S + s) * K;
-#pragma unroll
-        for (int t = 0; t < K; ++t)
-            if (i0[t] >= 0) top.offer_sorted(d0[t], i0[t]);
-    }
-    block_merge_topk<K>(top, nullptr, nullptr, idx + q * k_out, dist ? dist + q * k_out : nullptr, k_out);
-    if (threadIdx.x == 0 && idx[q * k_out + k_out - 1] < 0)
-        pad_nan_row(soa, capacity, n, d, X + q * d, k_out, idx + q * k_out,
-                    dist ? dist + q * k_out : nullptr);
-}
-
-// ----------------------------------------------------- K4c: chunk merge ------
-// One thread per query merges S sorted partial lists (chunk s holds indices below
-// chunk s+1, so on equal d the lower chunk wins) into the final [m][k] rows.
-__device__ __forceinline__ void knn_merge_row(const double *__restrict__ pd, const int32_t *__restrict__ pi,
-                                              int64_t q, int S, int K, int k, int64_t *__restrict__ idx,
-                                              double *__restrict__ dist) {
-    const double *d0 = pd + q * S * K;
-    const int32_t *i0 = pi + q * S * K;
-    if (S == 1) {
-        for (int t = 0; t < k; ++t) {
-            idx[q * k + t] = i0[t];
-            if (dist) dist[q * k + t] = i0[t] >= 0 ? d0[t] : INFINITY;
-        }
-        return;
-    }
-    if (S <= 4) {
-        // few chunks (the seeded batched path uses 1-4): head pointers stay in registers and
-        // each list's current head is cached, so a round is S compares and one reload
-        int h[4] = {0, 0, 0, 0};
-        double hd[4];
-        int32_t hi[4];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) {
-            hi[s] = s < S ? i0[s * K] : -1;
-            hd[s] = s < S ? d0[s * K] : INFINITY;
-        }
-        for (int t = 0; t < k; ++t) {
-            int best = -1;
-            double bd = INFINITY;
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (hi[s] >= 0 && (best < 0 || hd[s] < bd)) { best = s; bd = hd[s]; }
-            int64_t oi = -1;
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-                if (s == best) {
-                    oi = hi[s];
-                    ++h[s];
-                    hi[s] = h[s] < K ? i0[s * K + h[s]] : -1;
-                    hd[s] = h[s] < K ? d0[s * K + h[s]] : INFINITY;
-                }
-            idx[q * k + t] = oi;
-            if (dist) dist[q * k + t] = best >= 0 ? bd : INFINITY;
-        }
-        return;
-    }
-    unsigned char head[64];
-    for (int s = 0; s < S; ++s) head[s] = 0;
-    for (int t = 0; t < k; ++t) {
-        int best = -1;
-        double bd = INFINITY;
-        for (int s = 0; s < S; ++s) {
-            int h = head[s];
-            if (h >= K) continue;
-            int32_t ci = i0[s * K + h];
-            if (ci < 0) continue;
-            double cd = d0[s * K + h];
-            if (best < 0 || cd < bd) { best = s; bd = cd; }
-        }
-        if (best < 0) {
-            idx[q * k + t] = -1;
-            if (dist) dist[q * k + t] = INFINITY;
-        } else {
-            idx[q * k + t] = i0[best * K + head[best]];
-            if (dist) dist[q * k + t] = bd;
-            head[best]++;
-        }
-    }
-}
-
-__global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__restrict__ pi, int64_t m,
-                            int S, int K, int k, int64_t *__restrict__ idx,
-                            double *__restrict__ dist, const uint8_t *__restrict__ redo,
-                            const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
-                            const double *__restrict__ X) {
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
-    if (redo && !redo[q >> 5]) return;
-    knn_merge_row(pd, pi, q, S, K, k, idx, dist);
-    if (idx[q * k + k - 1] < 0)
-        pad_nan_row(soa, capacity, n, d, X + q * d, k, idx + q * k, dist ? dist + q * k : nullptr);
-}
-
-// ---------------------------------------------------- kNN seeding (d = 2) ----
-// An a-priori upper bound of each query's K-th neighbour distance, so that the brute
-// force scan does not spend K*ln(N/K) list insertions per query discovering it.  Nodes
-// are counted into a uniform G x G grid over their bounding box; a query grows a square
-// block of cells around its own cell until the block holds >= K nodes; every node of the
-// block lies within B = distance from the query to the farthest corner of the block, so
-// the K-th nearest distance is <= B and no node farther than B can be among the K nearest.
-// B^2 is inflated by 1e-9 (cell-assignment rounding, and distinct d^2 that collapse to one
-// rounded square root).  The scan still evaluates every (query, node) pair; only the
-// number of candidates that reach the exact fp64 insertion path shrinks (~9.4K -> ~2K).
-#define BOUNDS_BLOCKS 128
-// per-block partial bounding boxes [BOUNDS_BLOCKS][4] = (min x, max x, min y, max y)
-__global__ void __launch_bounds__(256)
-k_bounds2d_partial(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                   double *__restrict__ partial) {
-    __shared__ double sh[4][8];
-    double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
-        double x = soa[t], y = soa[capacity + t];
-        mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        mnx = fmin(mnx, __shfl_down_sync(0xffffffffu, mnx, o));
-        mxx = fmax(mxx, __shfl_down_sync(0xffffffffu, mxx, o));
-        mny = fmin(mny, __shfl_down_sync(0xffffffffu, mny, o));
-        mxy = fmax(mxy, __shfl_down_sync(0xffffffffu, mxy, o));
-    }
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { sh[0][w] = mnx; sh[1][w] = mxx; sh[2][w] = mny; sh[3][w] = mxy; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 1; i < 8; ++i) {
-            mnx = fmin(mnx, sh[0][i]); mxx = fmax(mxx, sh[1][i]);
-            mny = fmin(mny, sh[2][i]); mxy = fmax(mxy, sh[3][i]);
-        }
-        double *o = partial + 4 * blockIdx.x;
-        o[0] = mnx; o[1] = mxx; o[2] = mny; o[3] = mxy;
-    }
-}
-
-// every block of the histogram kernel folds the partials itself (block 0 publishes b4)
-__device__ __forceinline__ void fold_bounds(const double *__restrict__ partial, int nb, double *sh4) {
-    if (threadIdx.x < 32) {
-        double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
-        for (int i = threadIdx.x; i < nb; i += 32) {
-            mnx = fmin(mnx, partial[4 * i]); mxx = fmax(mxx, partial[4 * i + 1]);
-            mny = fmin(mny, partial[4 * i + 2]); mxy = fmax(mxy, partial[4 * i + 3]);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = fmin(mnx, __shfl_down_sync(0xffffffffu, mnx, o));
-            mxx = fmax(mxx, __shfl_down_sync(0xffffffffu, mxx, o));
-            mny = fmin(mny, __shfl_down_sync(0xffffffffu, mny, o));
-            mxy = fmax(mxy, __shfl_down_sync(0xffffffffu, mxy, o));
-        }
-        if (threadIdx.x == 0) { sh4[0] = mnx; sh4[1] = mxx; sh4[2] = mny; sh4[3] = mxy; }
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ int cell_of(double v, double mn, double mx, int G) {
-    double w = mx - mn;
-    if (!(w > 0.0)) return 0;
-    double c = floor((v - mn) * ((double)G / w));
-    if (!(c >= 0.0)) return 0;                                      // negative or NaN
-    return c > (double)(G - 1) ? G - 1 : (int)c;
-}
-
-__global__ void k_cell_hist(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                            const double *__restrict__ partial, int nb, double *__restrict__ b4,
-                            int G, int32_t *__restrict__ cells) {
-    __shared__ double sb[4];
-    fold_bounds(partial, nb, sb);
-    if (blockIdx.x == 0 && threadIdx.x < 4) b4[threadIdx.x] = sb[threadIdx.x];
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        int cx = cell_of(soa[t], sb[0], sb[1], G), cy = cell_of(soa[capacity + t], sb[2], sb[3], G);
-        atomicAdd(cells + (int64_t)cy * G + cx, 1);
-    }
-}
-
-// exclusive scan of the cell counts -> cell starts (+ a copy used as the scatter cursor),
-// in three small launches: per-tile sums, scan of the <= 1024 tile sums, per-tile scan + offset
-#define SCAN_TILE 4096
-__global__ void __launch_bounds__(1024)
-k_cell_tile_sums(const int32_t *__restrict__ cells, int64_t L, int32_t *__restrict__ tsums) {
-    __shared__ int32_t ws[32];
-    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * 4;
-    int32_t v = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v += i0 + j < L ? cells[i0 + j] : 0;
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        v = ws[threadIdx.x];
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) tsums[blockIdx.x] = v;
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_cell_scan_sums(int32_t *__restrict__ tsums, int nt, int32_t *__restrict__ total) {
-    __shared__ int32_t ws[32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int32_t x = tid < nt ? tsums[tid] : 0, inc = x;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    if (lane == 31) ws[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int32_t y = ws[lane], yi = y;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
-        ws[lane] = yi - y;
-    }
-    __syncthreads();
-    const int32_t excl = ws[w] + inc - x;
-    if (tid < nt) tsums[tid] = excl;
-    if (tid == nt - 1) *total = excl + x;
-}
-
-__global__ void __launch_bounds__(1024)
-k_cell_scan_apply(const int32_t *__restrict__ cells, int64_t L, const int32_t *__restrict__ tsums,
-                  int32_t *__restrict__ start, int32_t *__restrict__ cursor) {
-    __shared__ int32_t ws[32];
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int64_t i0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)tid * 4;
-    int32_t v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = i0 + j < L ? cells[i0 + j] : 0;
-    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
-    int32_t inc = tsum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    if (lane == 31) ws[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        int32_t y = ws[lane], yi = y;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
-        ws[lane] = yi - y;
-    }
-    __syncthreads();
-    int32_t run = tsums[blockIdx.x] + ws[w] + inc - tsum;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
-        run += v[j];
-    }
-}
-
-__global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                               const double *__restrict__ b4, int G, int32_t *__restrict__ cursor,
-                               int32_t *__restrict__ ids) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        int cx = cell_of(soa[t], b4[0], b4[1], G), cy = cell_of(soa[capacity + t], b4[2], b4[3], G);
-        ids[atomicAdd(cursor + (int64_t)cy * G + cx, 1)] = (int32_t)t;
-    }
-}
-
-// seed2[q] = K-th smallest exact fp64 d^2 among ALL nodes of a block of cells around the
-// query's cell that holds at least K nodes -- a subset of the nodes, so an upper bound of the
-// true K-th smallest -- inflated by 1e-9.  GS = 16 or 32 lanes per query.  The block grows ring by ring
-// (then geometrically, until it covers the whole grid: sparse pockets, queries far outside the
-// cloud); lanes own its rows (a row of cells is one contiguous range of `ids`).  The nodes
-// are enumerated 32 at a time, flat over the rows, and merged into the running K smallest by
-// rank counting over shuffles (the K smallest live in lanes 0..K-1, sorted, via a per-warp
-// shared-memory scatter).  inf = fewer than K nodes at a non-NaN distance.
-template <int D, int GS>      // GS = lanes per query: 16 (K <= 16) or 32
-__global__ void __launch_bounds__(256)
-k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
-           const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
-           const int32_t *__restrict__ ids, int K, double *__restrict__ seed2) {
-    __shared__ double sbest[256 / GS][GS];
-    const int lane = threadIdx.x & (GS - 1), grp = threadIdx.x / GS;
-    // every warp-level primitive below is restricted to this query's lanes
-    const unsigned SEG = GS == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
-    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / GS;
-    if (q >= m) return;                                       // uniform over the GS lanes
-    double qv[D];
-    bool finite = true;
-#pragma unroll
-    for (int j = 0; j < D; ++j) { qv[j] = X[q * D + j]; finite &= qv[j] == qv[j]; }
-    const double mnx = b4[0], mxx = b4[1], mny = b4[2], mxy = b4[3];
-    double out = INFINITY;
-    if (finite && mnx <= mxx && mny <= mxy) {
-        const int cx = cell_of(qv[0], mnx, mxx, G), cy = cell_of(qv[1], mny, mxy, G);
-        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
-        int32_t cnt = 0;
-        for (int r = 1;; r = r < 8 ? r + 1 : 2 * r) {
-            x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
-            y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
-            int32_t c = 0;
-            for (int row = y0 + lane; row <= y1; row += GS)
-                c += start[(int64_t)row * G + x1 + 1] - start[(int64_t)row * G + x0];
-            cnt = __reduce_add_sync(SEG, c);
-            if (cnt >= K || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
-        }
-        if (cnt >= K) {
-            double best = INFINITY;                           // lanes 0..K-1: the K smallest so far
-            int nb = 0;                                       // valid entries of `best`
-            // rows in passes of GS (one pass unless the block is taller than GS cells)
-            for (int rb = y0; rb <= y1; rb += GS) {
-                int32_t e0 = 0, len = 0;
-                if (rb + lane <= y1) {
-                    e0 = start[(int64_t)(rb + lane) * G + x0];
-                    len = start[(int64_t)(rb + lane) * G + x1 + 1] - e0;
-                }
-                int32_t inc = len;
-#pragma unroll
-                for (int o = 1; o < GS; o <<= 1) {
-                    int32_t u = __shfl_up_sync(SEG, inc, o, GS);
-                    if (lane >= o) inc += u;
-                }
-                const int32_t pc = __shfl_sync(SEG, inc, GS - 1, GS);   // nodes in this pass
-                const int nrows = y1 - rb + 1 < GS ? y1 - rb + 1 : GS;
-                for (int32_t f0 = 0; f0 < pc; f0 += GS) {
-                    // flat candidate f0 + lane lives in the first row whose inclusive prefix exceeds it
-                    const int32_t f = f0 + lane;
-                    int32_t e = -1;
-                    for (int row = 0; row < nrows; ++row) {
-                        const int32_t rinc = __shfl_sync(SEG, inc, row, GS), rlen = __shfl_sync(SEG, len, row, GS);
-                        const int32_t re0 = __shfl_sync(SEG, e0, row, GS);
-                        if (e < 0 && f < rinc) e = re0 + (f - (rinc - rlen));
-                    }
-                    double v = INFINITY;
-                    if (f < pc && e >= 0) {
-                        const int32_t t = ids[e];
-                        double pv[D];
-#pragma unroll
-                        for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
-                        v = dist2_full<D>(pv, qv);
-                        v = v != v ? INFINITY : v;          // a NaN node is never a neighbour
-                    }
-                    // ranks in the union of `best` (first on ties) and this chunk; only the
-                    // nb valid entries of `best` and the nv valid entries of the chunk are
-                    // compared against (the rest are +inf and rank behind every finite value)
-                    const int nv = pc - f0 < GS ? pc - f0 : GS;
-                    int rank_b = 0, rank_v = 0;
-                    for (int src = 0; src < nb; ++src) {
-                        const double a = __shfl_sync(SEG, best, src, GS);
-                        rank_b += (a < best || (a == best && src < lane)) ? 1 : 0;
-                        rank_v += a <= v ? 1 : 0;
-                    }
-                    for (int src = 0; src < nv; ++src) {
-                        const double c = __shfl_sync(SEG, v, src, GS);
-                        rank_b += c < best ? 1 : 0;
-                        rank_v += (c < v || (c == v && src < lane)) ? 1 : 0;
-                    }
-                    sbest[grp][lane] = INFINITY;
-                    __syncwarp(SEG);
-                    if (lane < nb && rank_b < GS) sbest[grp][rank_b] = best;
-                    if (lane < nv && rank_v < GS) sbest[grp][rank_v] = v;
-                    __syncwarp(SEG);
-                    best = lane < K ? sbest[grp][lane] : INFINITY;
-                    __syncwarp(SEG);
-                    nb = nb + nv < K ? nb + nv : K;
-                }
-            }
-            const double kth = __shfl_sync(SEG, best, K - 1, GS);
-            out = kth * (1.0 + 1e-9) + 1e-300;
-        }
-    }
-    if (lane == 0) seed2[q] = out;
-}
-
-int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
-int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
-int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
-int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
-int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
-int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filter kernel
-
-template <int D, int K>
-static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
-                          double *dist) {
-    sbp_ctx *ctx = s->ctx;
-    const int64_t n = s->n;
-    bool wide = m < 256;
-    int S, tpb = 128;
-    if (wide) {
-        int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
-        int64_t maxs = (n + 2047) / 2048;
-        S = (int)(want < maxs ? want : maxs);
-    } else {
-        // queries per CTA: 128, or 32 when single-warp CTAs balance the SMs better
-        // (work per SM is ceil(tiles / SMs) * tpb query rows)
-        int64_t sm = ctx->sm_count;
-        int64_t w128 = ((m + 127) / 128 + sm - 1) / sm * 128;
-        int64_t w32 = ((m + 31) / 32 + sm - 1) / sm * 32;
-        tpb = (w32 * 100 < w128 * 95) ? 32 : 128;
-        int64_t tiles = (m + tpb - 1) / tpb;
-        // node chunks: with seeded bounds a chunk restart is cheap, so fill the SMs with
-        // ~28 warps each (measured: 1.23 -> 1.04 ms on 50k x 50k); without seeds every chunk
-        // re-learns its bound (K ln(N/K) insertions), so only enough CTAs to cover the SMs
-        const bool seeded = D == 2 && g_knn_seed && n >= 2048;
-        int64_t want = seeded ? (28 * sm * 32 / tpb + tiles - 1) / tiles : (2 * sm + tiles - 1) / tiles;
-        int64_t maxs = (n + 4095) / 4096;
-        S = (int)(want < maxs ? want : maxs);
-    }
-    if (!wide && g_knn_chunks > 0) S = g_knn_chunks;
-    if (S < 1) S = 1;
-    if (S > (wide ? 1024 : 64)) S = wide ? 1024 : 64;
-    void *pd = nullptr, *pi = nullptr;
-    int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)m * S * K * sizeof(double), &pd);
-    if (rc) return rc;
-    rc = sbp_ctx_scratch(ctx, 1, (size_t)m * S * K * sizeof(int32_t), &pi);
-    if (rc) return rc;
-    if (wide) {
-        dim3 grid((unsigned)m, (unsigned)S);
-        k_knn_wide<D, K><<<grid, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
-                                                              (double *)pd, (int32_t *)pi, idx, dist, k);
-        ctx->launches++;
-        SBP_CUDA(cudaGetLastError());
-        if (S > 1) {
-            k_knn_merge_wide<K><<<(unsigned)m, WIDE_TPB, 0, ctx->stream>>>(
-                (const double *)pd, (const int32_t *)pi, S, k, idx, dist, s->d_soa, s->capacity, n, D, X);
-            ctx->launches++;
-            SBP_CUDA(cudaGetLastError());
-        }
-        return SBP_OK;
-    }
-    const double *seed = nullptr, *seed_bounds = nullptr;
-    if (D == 2 && g_knn_seed && n >= 2048) {
-        int G = (int)ceil(sqrt(2.0 * (double)n));
-        if (G > 2048) G = 2048;
-        const int64_t L = (int64_t)G * G;
-        void *cellbuf = nullptr, *seedbuf = nullptr;
-        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][cells L][start L+1][cursor L][ids n][tile sums 1024]
-        const size_t hdr = (4 + 4 * BOUNDS_BLOCKS) * sizeof(double);
-        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
-        if (rc) return rc;
-        rc = sbp_ctx_scratch(ctx, 6, (size_t)m * sizeof(double), &seedbuf);
-        if (rc) return rc;
-        double *b4 = (double *)cellbuf;
-        int32_t *cells = (int32_t *)((char *)cellbuf + hdr), *start = cells + L, *cursor = start + L + 1,
-                *ids = cursor + L, *tsums = ids + n;
-        SBP_CUDA(cudaMemsetAsync(cells, 0, (size_t)L * sizeof(int32_t), ctx->stream));
-        double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
-        k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
-        int hb = (int)((n + 255) / 256);
-        if (hb > ctx->sm_count * 8) hb = ctx->sm_count * 8;
-        k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,
-                                                 cells);
-        const int nt = (int)((L + SCAN_TILE - 1) / SCAN_TILE);            // <= 1024 tiles (G <= 2048)
-        k_cell_tile_sums<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums);
-        k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
-        k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
-        k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
-        // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
-        // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
-        k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
-        ctx->launches += 7;
-        SBP_CUDA(cudaGetLastError());
-        seed = (const double *)seedbuf;
-        seed_bounds = b4;
-    }
-    const uint8_t *redo = nullptr;
-    if (seed && g_knn_filter) {
-        // seeded filter + exact refine; the one-kernel scan below then only redoes the
-        // blocks of 32 queries the refine step flagged (normally none)
-        const int NW = (g_knn_filter_variant & 3) >= 2 ? 4 : 2;    // warps per CTA
-        const int FQv = g_knn_filter_variant >= 8 ? 8 : g_knn_filter_variant >= 4 ? 2 : FILTER_Q;
-        const int QPB = NW * 32 * FQv;                             // queries per CTA
-        const int64_t qblocks = (m + QPB - 1) / QPB;
-        constexpr int FT = filter_tile(D);
-        const int64_t tiles = (n + FT - 1) / FT;
-        int64_t FS = g_knn_filter_chunks > 0 ? g_knn_filter_chunks
-                                             : (16 * (int64_t)ctx->sm_count + qblocks - 1) / qblocks;
-        if (FS > tiles) FS = tiles;
-        if (FS > 64) FS = 64;
-        if (FS < 1) FS = 1;
-        const int64_t chunk = (tiles + FS - 1) / FS * FT;
-        FS = (n + chunk - 1) / chunk;
-        int C = 4 * K / (int)FS + 12;
-        const int64_t cap32 = tiles * FT;
-        void *cbuf = nullptr, *nbuf = nullptr, *shbuf = nullptr;
-        rc = sbp_ctx_scratch(ctx, 8, (size_t)m * FS * C * sizeof(int32_t), &cbuf);
-        if (rc) return rc;
-        const size_t nflags = (size_t)((m + 31) / 32);
-        rc = sbp_ctx_scratch(ctx, 9, (size_t)m * FS * sizeof(int32_t) + nflags, &nbuf);
-        if (rc) return rc;
-        rc = sbp_ctx_scratch(ctx, 10, 64 + (size_t)(D + 1) * cap32 * sizeof(float), &shbuf);
-        if (rc) return rc;
-        double *info = (double *)shbuf;                            // [1 + D] <= 64 bytes
-        float *shadow = (float *)((char *)shbuf + 64);
-        int32_t *ccount = (int32_t *)nbuf;
-        uint8_t *flags = (uint8_t *)nbuf + (size_t)m * FS * sizeof(int32_t);
-        SBP_CUDA(cudaMemsetAsync(flags, 0, nflags, ctx->stream));
-        int sb = (int)((cap32 + 255) / 256);
-        if (sb > ctx->sm_count * 8) sb = ctx->sm_count * 8;
-        k_shadow_centered<D><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, seed_bounds, cap32,
-                                                          shadow, info);
-        dim3 fgrid((unsigned)qblocks, (unsigned)FS);
-#define SBP_FILTER_LAUNCH(NW_, UNR_, FQ_)                                                   \
-    k_knn_filter<D, NW_, UNR_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                    \
-        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf, ccount)
-        {
-        KernelTimer timer(ctx);
-        switch (g_knn_filter_variant) {
-            case 1: SBP_FILTER_LAUNCH(2, 1, FILTER_Q); break;
-            case 2: SBP_FILTER_LAUNCH(4, 2, FILTER_Q); break;
-            case 3: SBP_FILTER_LAUNCH(4, 1, FILTER_Q); break;
-            case 4: SBP_FILTER_LAUNCH(2, 2, 2); break;
-            case 6: SBP_FILTER_LAUNCH(4, 2, 2); break;
-            case 8: SBP_FILTER_LAUNCH(2, 1, 8); break;
-            case 10: SBP_FILTER_LAUNCH(4, 1, 8); break;
-            default: SBP_FILTER_LAUNCH(2, 2, FILTER_Q); break;
-        }
-        }
-#undef SBP_FILTER_LAUNCH
-        ctx->launches++;
-        k_knn_refine<D, K><<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(
-            s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
-            dist, flags);
-        ctx->launches += 2;
-        SBP_CUDA(cudaGetLastError());
-        redo = flags;
-        tpb = 32;
-    }
-    if (tpb == 32) {
-        dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
-        k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
-                                                              g_knn_prefilter, s->capacity, n, S, X,
-                                                              m, seed, (double *)pd, (int32_t *)pi,
-                                                              redo);
-    } else {
-        dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
-        k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
-                                                                g_knn_prefilter, s->capacity, n, S,
-                                                                X, m, seed, (double *)pd, (int32_t *)pi,
-                                                                nullptr);
-    }
-    ctx->launches++;
-    SBP_CUDA(cudaGetLastError());
-    k_knn_merge<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
-        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist, redo, s->d_soa, s->capacity, n, D, X);
-    ctx->launches++;
-    SBP_CUDA(cudaGetLastError());
-    return SBP_OK;
-}
-
-template <int D>
-static int32_t knn_dispatch_k(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
-                              double *dist) {
-    // list length K >= k; 11 and 21 are the PRM / RRT* cases (k = 10 or 20 plus self)
-    if (k <= 1) return knn_launch<D, 1>(s, X, m, k, idx, dist);
-    if (k <= 2) return knn_launch<D, 2>(s, X, m, k, idx, dist);
-    if (k <= 4) return knn_launch<D, 4>(s, X, m, k, idx, dist);
-    if (k <= 8) return knn_launch<D, 8>(s, X, m, k, idx, dist);
-    if (k <= 11) return knn_launch<D, 11>(s, X, m, k, idx, dist);
-    if (k <= 16) return knn_launch<D, 16>(s, X, m, k, idx, dist);
-    if (k <= 21) return knn_launch<D, 21>(s, X, m, k, idx, dist);
-    return knn_launch<D, 32>(s, X, m, k, idx, dist);
-}
-
-__global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        idx[t] = -1;
-        if (dist) dist[t] = INFINITY;
-    }
-}
-
-extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32_t k,
-                                 int32_t precision, int64_t *idx, double *dist) {
-    SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_knn: NULL argument");
-    SBP_REQUIRE(m >= 0, "sbp_nodes_knn: m < 0");
-    SBP_REQUIRE(k >= 1 && k <= 32, "sbp_nodes_knn: 1 <= k <= 32");
-    SBP_REQUIRE(precision == 64, "sbp_nodes_knn: only the bit-exact fp64 path exists (precision=64)");
-    if (m == 0) return SBP_OK;
-    SBP_CUDA(cudaSetDevice(s->ctx->device));
-    if (s->n == 0) {
-        k_fill_empty_knn<<<64, 256, 0, s->ctx->stream>>>(m * k, idx, dist);
-        s->ctx->launches++;
-        SBP_CUDA(cudaGetLastError());
-        return SBP_OK;
-    }
-    switch (s->d) {
-        case 2: return knn_dispatch_k<2>(s, X, m, k, idx, dist);
-        case 3: return knn_dispatch_k<3>(s, X, m, k, idx, dist);
-        case 4: return knn_dispatch_k<4>(s, X, m, k, idx, dist);
-        case 6: return knn_dispatch_k<6>(s, X, m, k, idx, dist);
-        default:
-            sbp_set_error("sbp_nodes_knn: dimension %d not instantiated (2, 3, 4, 6)", s->d);
-            return SBP_ERR_ARG;
-    }
-}
-
-// --------------------------------------------------------- K5: radius -------
-// Membership is decided on d^2 against a host-computed threshold (see
-// near_threshold below), so no square root is evaluated per pair.
-// wide: CTA per (query, chunk).  PASS 0 counts, PASS 1 writes indices in order.
-template <int D, bool XY, int PASS>
-__global__ void __launch_bounds__(WIDE_TPB)
-k_near_wide(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
-            const double *__restrict__ X, int64_t m, double thr, int closed,
-            int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-            int64_t *__restrict__ idx, int64_t idx_capacity, const int64_t *__restrict__ needed) {
-    const int64_t q = blockIdx.x;
-    const int s = blockIdx.y;
-    if (PASS == 1 && *needed > idx_capacity) return;
-    const int64_t chunk = (n + S - 1) / S;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    constexpr int DD = XY ? 2 : D;
-    double qv[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = j < DD ? X[q * D + j] : 0.0;
-    __shared__ int wsum[WIDE_TPB / 32];
-    __shared__ int64_t base_s;
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t mycount = 0;
-    if (PASS == 1 && threadIdx.x == 0) base_s = offsets[q * S + s];
-    if (PASS == 1) __syncthreads();
-    for (int64_t t0 = c0; t0 < c1; t0 += WIDE_TPB) {
-        int64_t t = t0 + threadIdx.x;
-        bool in = false;
-        if (t < c1) {
-            double pv[D];
-#pragma unroll
-            for (int j = 0; j < D; ++j) pv[j] = j < DD ? soa[(int64_t)j * capacity + t] : 0.0;
-            in = near_in(near_d2<D, XY>(pv, qv), thr, closed);
-        }
-        if (PASS == 0) {
-            mycount += in ? 1 : 0;
-        } else {
-            unsigned bal = __ballot_sync(FULL, in);
-            int pre = __popc(bal & ((1u << lane) - 1u));
-            if (lane == 0) wsum[warp] = __popc(bal);
-            __syncthreads();
-            int woff = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < WIDE_TPB / 32; ++w) {
-                int v = wsum[w];
-                if (w < warp) woff += v;
-                tot += v;
-            }
-            int64_t b = base_s;
-            if (in) idx[b + woff + pre] = t;
-            __syncthreads();
-            if (threadIdx.x == 0) base_s = b + tot;
-            __syncthreads();
-        }
-    }
-    if (PASS == 0) {
-        for (int o = 16; o > 0; o >>= 1) mycount += __shfl_down_sync(FULL, mycount, o);
-        __shared__ int64_t wc[WIDE_TPB / 32];
-        if (lane == 0) wc[warp] = mycount;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int64_t tot = 0;
-            for (int w = 0; w < WIDE_TPB / 32; ++w) tot += wc[w];
-            counts[q * S + s] = tot;
-        }
-    }
-}
-
-// batched: thread per query over shared-memory node tiles; same branch-free 32-node
-// blocks as the kNN scan (flags gathered in a mask, then counted or written in order).
-template <int D, bool XY, int PASS, int TPB>
-__global__ void __launch_bounds__(TPB)
-k_near_batched(const double *__restrict__ soa, int64_t capacity, int64_t n, int S,
-               const double *__restrict__ X, int64_t m, double thr, int closed,
-               int64_t *__restrict__ counts, const int64_t *__restrict__ offsets,
-               int64_t *__restrict__ idx, int64_t idx_capacity,
-               const int64_t *__restrict__ needed) {
-    constexpr int DD = XY ? 2 : D;
-    constexpr int TILE = TPB * 8;
-    __shared__ double tile[DD][TILE];
-    if (PASS == 1 && *needed > idx_capacity) return;
-    const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    const int s = blockIdx.y;
-    const int64_t chunk = (n + S - 1) / S;
-    const int64_t c0 = (int64_t)s * chunk;
-    const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
-    double qv[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) qv[j] = (q < m && j < DD) ? X[q * D + j] : 0.0;
-    int64_t cnt_or_pos = 0;
-    if (PASS == 1 && q < m) cnt_or_pos = offsets[q * S + s];
-    for (int64_t t0 = c0; t0 < c1; t0 += TILE) {
-        int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
-        __syncthreads();
-#pragma unroll
-        for (int j = 0; j < DD; ++j)
-            for (int t = threadIdx.x; t < cnt; t += TPB)
-                tile[j][t] = soa[(int64_t)j * capacity + t0 + t];
-        __syncthreads();
-        for (int b0 = 0; b0 < cnt; b0 += 32) {
-            const int bn = cnt - b0 < 32 ? cnt - b0 : 32;
-            uint32_t mask = 0;
-            if (bn == 32) {
-#pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                    double pv[D];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][b0 + t] : 0.0;
-                    mask |= near_in(near_d2<D, XY>(pv, qv), thr, closed) ? (1u << t) : 0u;
-                }
-            } else {
-                for (int t = 0; t < bn; ++t) {
-                    double pv[D];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) pv[j] = j < DD ? tile[j < DD ? j : 0][b0 + t] : 0.0;
-                    mask |= near_in(near_d2<D, XY>(pv, qv), thr, closed) ? (1u << t) : 0u;
-                }
-            }
-            if (PASS == 0) {
-                cnt_or_pos += __popc(mask);
-            } else if (q < m) {
-                while (mask) {                                   // ascending node index
-                    const int t = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    idx[cnt_or_pos++] = t0 + b0 + t;
-                }
-            }
-        }
-    }
-    if (PASS == 0 && q < m) counts[q * S + s] = cnt_or_pos;
-}
-
-// Exclusive scan of counts[L] (single CTA; L = m*S) -> offsets[L]; row_ptr[q] =
-// offsets[q*S], row_ptr[m] = total, *needed = total.
-__global__ void __launch_bounds__(1024)
-k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
-              int64_t *__restrict__ offsets, int64_t *__restrict__ row_ptr,
-              int64_t *__restrict__ needed) {
-    __shared__ int64_t part[1024];
-    const int tid = threadIdx.x;
-    const int64_t seg = (L + 1023) / 1024;
-    const int64_t a = (int64_t)tid * seg, b = a + seg < L ? a + seg : L;
-    int64_t sum = 0;
-    for (int64_t t = a; t < b; ++t) sum += counts[t];
-    part[tid] = sum;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int64_t v = tid >= o ? part[tid - o] : 0;
-        __syncthreads();
-        part[tid] += v;
-        __syncthreads();
-    }
-    int64_t run = part[tid] - sum;   // exclusive prefix of my segment
-    for (int64_t t = a; t < b; ++t) {
-        offsets[t] = run;
-        if (t % S == 0) row_ptr[t / S] = run;
-        run += counts[t];
-    }
-    if (tid == 1023) {
-        row_ptr[m] = part[1023];
-        *needed = part[1023];
-    }
-}
-
-// Bounding box of the first DD coordinates: per-block partials [blocks][DD][2] = (min, max),
-// then a one-warp fold (NaN coordinates are ignored by fmin / fmax).
-template <int DD>
-__global__ void __launch_bounds__(256)
-k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial) {
-    __shared__ double sh[2 * DD][8];
-    double mn[DD], mx[DD];
-#pragma unroll
-    for (int j = 0; j < DD; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
-#pragma unroll
-        for (int j = 0; j < DD; ++j) {
-            const double v = soa[(int64_t)j * capacity + t];
-            mn[j] = fmin(mn[j], v); mx[j] = fmax(mx[j], v);
-        }
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < DD; ++j) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[j] = fmin(mn[j], __shfl_down_sync(0xffffffffu, mn[j], o));
-            mx[j] = fmax(mx[j], __shfl_down_sync(0xffffffffu, mx[j], o));
-        }
-        if (lane == 0) { sh[2 * j][w] = mn[j]; sh[2 * j + 1][w] = mx[j]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * DD) {
-        double v = sh[threadIdx.x][0];
-        for (int i = 1; i < 8; ++i) v = (threadIdx.x & 1) ? fmax(v, sh[threadIdx.x][i]) : fmin(v, sh[threadIdx.x][i]);
-        partial[(int64_t)blockIdx.x * 2 * DD + threadIdx.x] = v;
-    }
-}
-
-template <int DD>
-__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out) {
-    const int c = threadIdx.x;                     // one thread per (coordinate, min | max)
-    if (c >= 2 * DD) return;
-    double v = partial[c];
-    for (int i = 1; i < nb; ++i) v = (c & 1) ? fmax(v, partial[(int64_t)i * 2 * DD + c]) : fmin(v, partial[(int64_t)i * 2 * DD + c]);
-    out[c] = v;
-}
-
-int g_near_filter = 1;    // tuning knob: filtered radius query (results unchanged)
-
-template <int D, bool XY>
-static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr, int closed,
-                           int64_t *row_ptr, int64_t *idx, int64_t idx_capacity, int64_t *needed) {
-    sbp_ctx *ctx = s->ctx;
-    const int64_t n = s->n;
-    bool wide = m < 256;
-    if (!wide && n >= 4096 && g_near_filter) {
-        // filtered path: centred fp32 shadow + packed scan, exact fp64 decision of the groups
-        // that pass (k_near_filtered); same counts -> scan -> fill structure as below
-        constexpr int DD = XY ? 2 : D;
-        constexpr int NW = 2, FT = filter_tile(DD);
-        const int QPB = NW * 32 * FILTER_Q;
-        const int64_t qblocks = (m + QPB - 1) / QPB;
-        const int64_t tiles = (n + FT - 1) / FT;
-        int64_t FS = (16 * (int64_t)ctx->sm_count + qblocks - 1) / qblocks;
-        if (FS > tiles) FS = tiles;
-        if (FS > 256) FS = 256;
-        if (FS < 1) FS = 1;
-        const int64_t chunk = (tiles + FS - 1) / FS * FT;
-        FS = (n + chunk - 1) / chunk;
-        const int64_t cap32 = tiles * FT, L = m * FS;
-        void *ws = nullptr, *shbuf = nullptr;
-        int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
-        if (rc) return rc;
-        const size_t hdr = 64 + 128 + (size_t)BOUNDS_BLOCKS * 2 * DD * sizeof(double);
-        rc = sbp_ctx_scratch(ctx, 10, hdr + (size_t)(DD + 1) * cap32 * sizeof(float), &shbuf);
-        if (rc) return rc;
-        double *info = (double *)shbuf, *bnd = (double *)((char *)shbuf + 64),
-               *partial = (double *)((char *)shbuf + 64 + 128);
-        float *shadow = (float *)((char *)shbuf + hdr);
-        int64_t *counts = (int64_t *)ws, *offsets = counts + L;
-        k_bounds_partial<DD><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
-        k_bounds_fold<DD><<<1, 32, 0, ctx->stream>>>(partial, BOUNDS_BLOCKS, bnd);
-        int sb = (int)((cap32 + 255) / 256);
-        if (sb > ctx->sm_count * 8) sb = ctx->sm_count * 8;
-        k_shadow_centered<DD><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, bnd, cap32, shadow, info);
-        dim3 fgrid((unsigned)qblocks, (unsigned)FS);
-        k_near_filtered<D, XY, 0, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
-            shadow, info, cap32, s->d_soa, s->capacity, n, (int)FS, chunk, X, m, thr, closed, counts,
-            offsets, idx, idx_capacity, needed);
-        k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, L, (int)FS, m, offsets, row_ptr, needed);
-        ctx->launches += 5;
-        SBP_CUDA(cudaGetLastError());
-        if (idx && idx_capacity > 0) {
-            k_near_filtered<D, XY, 1, NW><<<fgrid, NW * 32, 0, ctx->stream>>>(
-                shadow, info, cap32, s->d_soa, s->capacity, n, (int)FS, chunk, X, m, thr, closed, counts,
-                offsets, idx, idx_capacity, needed);
-            ctx->launches++;
-            SBP_CUDA(cudaGetLastError());
-        }
-        return SBP_OK;
-    }
-    int S, tpb = 128;
-    if (wide) {
-        int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
-        int64_t maxs = (n + 2047) / 2048;
-        S = (int)(want < maxs ? want : maxs);
-    } else {
-        int64_t sm = ctx->sm_count;
-        int64_t w128 = ((m + 127) / 128 + sm - 1) / sm * 128;
-        int64_t w32 = ((m + 31) / 32 + sm - 1) / sm * 32;
-        tpb = (w32 * 100 < w128 * 95) ? 32 : 128;
-        int64_t tiles = (m + tpb - 1) / tpb;
-        // no per-chunk restart cost here (unlike the kNN lists): aim for >= 24 warps per SM
-        int64_t want = (24 * sm * 32 / tpb + tiles - 1) / tiles;
-        int64_t maxs = (n + 4095) / 4096;
-        S = (int)(want < maxs ? want : maxs);
-    }
-    if (S < 1) S = 1;
-    if (S > 1024) S = 1024;
-    const int64_t L = m * S;
-    void *ws = nullptr;
-    int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
-    if (rc) return rc;
-    int64_t *counts = (int64_t *)ws, *offsets = counts + L;
-    dim3 gw((unsigned)m, (unsigned)S), gb((unsigned)((m + tpb - 1) / tpb), (unsigned)S);
-#define NEAR_BATCHED(PASSV)                                                                        \
-    do {                                                                                            \
-        if (tpb == 32)                                                                              \
-            k_near_batched<D, XY, PASSV, 32><<<gb, 32, 0, ctx->stream>>>(                           \
-                s->d_soa, s->capacity, n, S, X, m, thr, closed, counts, offsets, idx, idx_capacity, \
-                needed);                                                                            \
-        else                                                                                        \
-            k_near_batched<D, XY, PASSV, 128><<<gb, 128, 0, ctx->stream>>>(                         \
-                s->d_soa, s->capacity, n, S, X, m, thr, closed, counts, offsets, idx, idx_capacity, \
-                needed);                                                                            \
-    } while (0)
-    if (wide)
-        k_near_wide<D, XY, 0><<<gw, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m, thr,
-                                                                closed, counts, offsets, idx,
-                                                                idx_capacity, needed);
-    else
-        NEAR_BATCHED(0);
-    ctx->launches++;
-    SBP_CUDA(cudaGetLastError());
-    k_scan_counts<<<1, 1024, 0, ctx->stream>>>(counts, L, S, m, offsets, row_ptr, needed);
-    ctx->launches++;
-    SBP_CUDA(cudaGetLastError());
-    if (idx && idx_capacity > 0) {
-        if (wide)
-            k_near_wide<D, XY, 1><<<gw, WIDE_TPB, 0, ctx->stream>>>(s->d_soa, s->capacity, n, S, X, m,
-                                                                    thr, closed, counts, offsets, idx,
-                                                                    idx_capacity, needed);
-        else
-            NEAR_BATCHED(1);
-        ctx->launches++;
-        SBP_CUDA(cudaGetLastError());
-    }
-#undef NEAR_BATCHED
-    return SBP_OK;
-}
-
-__global__ void k_zero_rowptr(int64_t m, int64_t *row_ptr, int64_t *needed) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= m;
-         t += (int64_t)gridDim.x * blockDim.x)
-        row_ptr[t] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *needed = 0;
-}
-
-extern "C" int32_t sbp_nodes_near(sbp_nodes *s, const double *X, int64_t m, double r,
-                                  int32_t metric, int32_t closed, int64_t *row_ptr, int64_t *idx,
-                                  int64_t idx_capacity, int64_t *needed) {
-    SBP_REQUIRE(s && row_ptr && needed && (m == 0 || X), "sbp_nodes_near: NULL argument");
-    SBP_REQUIRE(m >= 0 && idx_capacity >= 0, "sbp_nodes_near: negative size");
-    SBP_REQUIRE(metric == SBP_METRIC_FULL || metric == SBP_METRIC_XY, "sbp_nodes_near: bad metric");
-    SBP_REQUIRE(metric == SBP_METRIC_FULL || s->d >= 2, "sbp_nodes_near: XY metric needs d >= 2");
-    SBP_CUDA(cudaSetDevice(s->ctx->device));
-    double thr;
-    int cl;
-    near_threshold(r, closed ? 1 : 0, &thr, &cl);
-    if (m == 0 || s->n == 0) {
-        k_zero_rowptr<<<64, 256, 0, s->ctx->stream>>>(m, row_ptr, needed);
-        s->ctx->launches++;
-        SBP_CUDA(cudaGetLastError());
-        return SBP_OK;
-    }
-#define SBP_NEAR_CASE(DV)                                                                        \
-    case DV:                                                                                      \
-        return metric == SBP_METRIC_XY                                                            \
-                   ? near_launch<DV, true>(s, X, m, thr, cl, row_ptr, idx, idx_capacity, needed)  \
-                   : near_launch<DV, false>(s, X, m, thr, cl, row_ptr, idx, idx_capacity, needed);
-    switch (s->d) {
-        SBP_NEAR_CASE(2)
-        SBP_NEAR_CASE(3)
-        SBP_NEAR_CASE(4)
-        SBP_NEAR_CASE(6)
-        default:
-            sbp_set_error("sbp_nodes_near: dimension %d not instantiated (2, 3, 4, 6)", s->d);
-            return SBP_ERR_ARG;
-    }
-#undef SBP_NEAR_CASE
 }
 
 // -------------------------------------------- batched planner primitives -----
