@@ -173,7 +173,7 @@ def run_ours(args):
     if world > 1:
         try:
             peer = sg.distributed.PeerAdjacencyGather(m, k, device=local)
-            gather_kind = "peer-memory scatter kernel + symmetric-memory barrier"
+            gather_kind = f"one pack + {peer.kind} kernel, symmetric-memory barrier"
         except Exception as e:      # noqa: BLE001
             gather_kind = f"NCCL all-gather of the packed block (peer memory unavailable: {type(e).__name__})"
 

@@ -269,6 +269,11 @@ int32_t sbp_adjacency_peer_scatter(sbp_ctx *ctx, const int64_t *nbr, const uint8
                                    int64_t total, void *const *peer_bufs, int32_t world,
                                    int64_t offset);
 
+/* The same exchange through the NVSwitch multicast (NVLS) mapping of the symmetric buffer:
+ * `multimem.st` stores, replicated by the switch into every rank's buffer. */
+int32_t sbp_adjacency_multicast(sbp_ctx *ctx, const int64_t *nbr, const uint8_t *vis,
+                                int64_t total, void *mc_buf, int64_t offset);
+
 #ifdef __cplusplus
 }
 #endif

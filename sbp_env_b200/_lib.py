@@ -77,6 +77,7 @@ _SIGNATURES = {
     "sbp_graph_csr": [_vp, _vp, _vp, _i64],
     "sbp_graph_bfs": [_vp, _vp, _vp, _i64, _vp, _vp, _i32],
     "sbp_adjacency_peer_scatter": [_vp, _vp, _vp, _i64, _vp, _i32, _i64],
+    "sbp_adjacency_multicast": [_vp, _vp, _vp, _i64, _vp, _i64],
     "sbp_tune": [C.c_char_p, _i64],
     "sbp_microbench": [_vp, _i32, _i64, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
     "sbp_ctx_kernel_time": [_vp, C.POINTER(_dbl), C.POINTER(_i64)],

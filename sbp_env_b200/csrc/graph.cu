@@ -387,3 +387,45 @@ extern "C" int32_t sbp_adjacency_peer_scatter(sbp_ctx *ctx, const int64_t *nbr, 
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
 }
+
+// Same exchange through the NVSwitch MULTICAST mapping of the symmetric buffer (NVLS): one
+// `multimem.st` per 16 bytes is replicated by the switch into every rank's buffer, so a rank
+// sends its block once instead of once per peer.
+__global__ void __launch_bounds__(256)
+k_adjacency_multicast(const int64_t *__restrict__ nbr, const uint8_t *__restrict__ vis, int64_t total,
+                      int32_t *__restrict__ mc, int64_t offset) {
+    const int64_t quads = total >> 2;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quads;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t << 2;
+        const float c0 = __int_as_float((int32_t)((nbr[i] + 1) << 1) | (vis[i] ? 1 : 0));
+        const float c1 = __int_as_float((int32_t)((nbr[i + 1] + 1) << 1) | (vis[i + 1] ? 1 : 0));
+        const float c2 = __int_as_float((int32_t)((nbr[i + 2] + 1) << 1) | (vis[i + 2] ? 1 : 0));
+        const float c3 = __int_as_float((int32_t)((nbr[i + 3] + 1) << 1) | (vis[i + 3] ? 1 : 0));
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + offset + i),
+                     "f"(c0), "f"(c1), "f"(c2), "f"(c3)
+                     : "memory");
+    }
+    for (int64_t i = (quads << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const float c = __int_as_float((int32_t)((nbr[i] + 1) << 1) | (vis[i] ? 1 : 0));
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + offset + i), "f"(c) : "memory");
+    }
+}
+
+// mc_buf: the multicast (NVLS) address of the ranks' symmetric int32 buffer; see
+// sbp_adjacency_peer_scatter for the rest.
+extern "C" int32_t sbp_adjacency_multicast(sbp_ctx *ctx, const int64_t *nbr, const uint8_t *vis,
+                                           int64_t total, void *mc_buf, int64_t offset) {
+    SBP_REQUIRE(ctx && (total == 0 || (nbr && vis)) && mc_buf, "sbp_adjacency_multicast: NULL argument");
+    SBP_REQUIRE(total >= 0 && offset >= 0 && (offset & 3) == 0, "sbp_adjacency_multicast: bad offset / size");
+    if (total == 0) return SBP_OK;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    int blocks = (int)(((total >> 2) + 255) / 256);
+    if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
+    if (blocks < 1) blocks = 1;
+    k_adjacency_multicast<<<blocks, 256, 0, ctx->stream>>>(nbr, vis, total, (int32_t *)mc_buf, offset);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}

@@ -109,7 +109,7 @@ class PeerAdjacencyGather:
     >>> packed = ag.gather(nbr, vis)          # int32 [world * m][k], decode with unpack_adjacency
     """
 
-    def __init__(self, rows_per_rank: int, k: int, device: int, group=None):
+    def __init__(self, rows_per_rank: int, k: int, device: int, group=None, multicast: bool = True):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -130,6 +130,11 @@ class PeerAdjacencyGather:
 
         half = self.world * self.stride * 4
         self._ptrs = [(C.c_void_p * self.world)(*[b + h * half for b in base]) for h in (0, 1)]
+        # NVSwitch multicast (NVLS) mapping of the same buffer, when the fabric offers it: the
+        # block is then sent once and replicated by the switch
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0) if multicast else 0
+        self._mc = [C.c_void_p(mc + h * half) for h in (0, 1)] if mc else None
+        self.kind = "NVSwitch multicast stores" if mc else "NVLink peer stores"
         self._step = 0
 
     def gather(self, nbr, vis):
@@ -145,9 +150,14 @@ class PeerAdjacencyGather:
         self._step += 1
         nbr = nbr.contiguous()
         vis8 = vis.contiguous().view(torch.uint8) if vis.dtype == torch.bool else vis.contiguous()
-        _lib.check(_lib.load().sbp_adjacency_peer_scatter(self.ctx.handle, ptr(nbr), ptr(vis8), self.block,
-                                                          self._ptrs[h], self.world, self.rank * self.stride),
-                   "sbp_adjacency_peer_scatter")
+        if self._mc is not None:
+            _lib.check(_lib.load().sbp_adjacency_multicast(self.ctx.handle, ptr(nbr), ptr(vis8), self.block,
+                                                           self._mc[h], self.rank * self.stride),
+                       "sbp_adjacency_multicast")
+        else:
+            _lib.check(_lib.load().sbp_adjacency_peer_scatter(self.ctx.handle, ptr(nbr), ptr(vis8), self.block,
+                                                              self._ptrs[h], self.world, self.rank * self.stride),
+                       "sbp_adjacency_peer_scatter")
         self.hdl.barrier(channel=h)
         out = self.buf[h].view(self.world, self.stride)[:, : self.block]
         return out.reshape(self.world * self.m, self.k) if self.stride == self.block else \

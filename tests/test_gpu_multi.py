@@ -32,8 +32,10 @@ def _worker(rank, world, port, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         from sbp_env_b200 import distributed as D
 
-        for m, k in ((5000, 10), (777, 3)):                    # 777 * 3 is not a multiple of 4
-            ag = D.PeerAdjacencyGather(m, k, device=rank)
+        kinds = set()
+        for m, k, mc in ((5000, 10, True), (777, 3, True), (5000, 10, False)):   # 777 * 3 is not a multiple of 4
+            ag = D.PeerAdjacencyGather(m, k, device=rank, multicast=mc)
+            kinds.add(ag.kind)
             for step in range(5):                               # both buffers, reuse
                 g = torch.Generator(device=dev)
                 g.manual_seed(1000 * step + rank)
@@ -45,6 +47,7 @@ def _worker(rank, world, port, q):
                 assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), (m, k, step)
         dist.barrier()
         dist.destroy_process_group()
+        print("exchange kinds exercised:", sorted(kinds), flush=True)
         q.put((rank, "ok"))
     except Exception as e:          # noqa: BLE001 - reported to the parent
         import traceback
