@@ -145,7 +145,7 @@ __device__ __forceinline__ bool filter_query_setup(const double *__restrict__ in
 // The scan itself: streams node chunk [c0, c1) of the centred shadow through shared memory
 // and calls on_group(r, g) for every (query slot r, group of 8 nodes g = node index / 8) whose
 // minimum t passes thr[r].  All threads of the CTA must call it (barriers inside).
-template <int DD, int NW, int UNR, int FQ, class OnGroup>
+template <int DD, int NW, int FQ, class OnGroup>
 __device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_t cap32, int64_t c0,
                                             int64_t c1, const float (&nq2)[FQ][DD],
                                             const float (&thr)[FQ], OnGroup on_group) {
@@ -181,42 +181,52 @@ __device__ __forceinline__ void filter_scan(const float *__restrict__ sh, int64_
         const int cnt = (int)(c1 - t0 < TILE ? c1 - t0 : TILE);
         const int groups = (cnt + 7) >> 3;
         const int32_t g0 = (int32_t)(t0 >> 3);
-#pragma unroll UNR
-        for (int g = 0; g < groups; ++g) {
-            uint64_t nd[DD + 1][4];          // 8 nodes: packed pairs of every component and the norm
+        // Two groups of 8 nodes per step: the minima of both groups are combined before the
+        // compare, so the hot path pays one compare per query and one branch per 16 nodes; the
+        // (rare) candidate path tells the two groups apart again (and ignores the stale second
+        // half of an odd tail).
+        const int pairs = (groups + 1) >> 1;
+#pragma unroll 1
+        for (int gp = 0; gp < pairs; ++gp) {
+            float mn[2][FQ];
 #pragma unroll
-            for (int j = 0; j <= DD; ++j) {
-                const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
-                const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
-                nd[j][0] = f2_pack(a.x, a.y); nd[j][1] = f2_pack(a.z, a.w);
-                nd[j][2] = f2_pack(b.x, b.y); nd[j][3] = f2_pack(b.z, b.w);
-            }
-            float mn[FQ];
+            for (int h = 0; h < 2; ++h) {
+                const int g = 2 * gp + h;
+                uint64_t nd[DD + 1][4];      // 8 nodes: packed pairs of every component and the norm
 #pragma unroll
-            for (int r = 0; r < FQ; ++r) {
-                uint64_t acc[4];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) acc[p] = nd[DD][p];
-#pragma unroll
-                for (int j = 0; j < DD; ++j) {
-                    const uint64_t qj = f2_pack(nq2[r][j], nq2[r][j]);
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) acc[p] = f2_fma(nd[j][p], qj, acc[p]);
+                for (int j = 0; j <= DD; ++j) {
+                    const float4 a = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8]);
+                    const float4 b = *reinterpret_cast<const float4 *>(&tile[st][j][g * 8 + 4]);
+                    nd[j][0] = f2_pack(a.x, a.y); nd[j][1] = f2_pack(a.z, a.w);
+                    nd[j][2] = f2_pack(b.x, b.y); nd[j][3] = f2_pack(b.z, b.w);
                 }
-                float v[8];
 #pragma unroll
-                for (int p = 0; p < 4; ++p) f2_unpack(acc[p], v[2 * p], v[2 * p + 1]);
-                // depth-2 tree (same four instructions as a chain, half the dependent latency)
-                mn[r] = f_min3(f_min3(v[0], v[1], v[2]), f_min3(v[3], v[4], v[5]), fminf(v[6], v[7]));
+                for (int r = 0; r < FQ; ++r) {
+                    uint64_t acc[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[p] = nd[DD][p];
+#pragma unroll
+                    for (int j = 0; j < DD; ++j) {
+                        const uint64_t qj = f2_pack(nq2[r][j], nq2[r][j]);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) acc[p] = f2_fma(nd[j][p], qj, acc[p]);
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) f2_unpack(acc[p], v[2 * p], v[2 * p + 1]);
+                    // depth-2 tree (same four instructions as a chain, half the dependent latency)
+                    mn[h][r] = f_min3(f_min3(v[0], v[1], v[2]), f_min3(v[3], v[4], v[5]), fminf(v[6], v[7]));
+                }
             }
-            // one (rarely taken) branch per group for the four queries
             bool any = false;
 #pragma unroll
-            for (int r = 0; r < FQ; ++r) any |= mn[r] <= thr[r];
+            for (int r = 0; r < FQ; ++r) any |= fminf(mn[0][r], mn[1][r]) <= thr[r];
             if (any) {
 #pragma unroll
-                for (int r = 0; r < FQ; ++r)
-                    if (mn[r] <= thr[r]) on_group(r, g0 + g);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int r = 0; r < FQ; ++r)
+                        if (mn[h][r] <= thr[r] && 2 * gp + h < groups) on_group(r, g0 + 2 * gp + h);
             }
         }
         __syncthreads();                                         // every warp is done with stage st

@@ -249,7 +249,7 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
 
 // --------------------------------------- K4a': seeded filter + exact refine ---
 // (scan, thresholds and the centred shadow: filter.cuh)
-template <int D, int NW, int UNR, int FQ>
+template <int D, int NW, int FQ>
 __global__ void __launch_bounds__(NW * 32)
 k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
              int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
@@ -273,7 +273,7 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
         cc[r] = (live && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
         cl[r] = cand + ((live ? q : 0) * S + s) * (int64_t)C;
     }
-    filter_scan<D, NW, UNR, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+    filter_scan<D, NW, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
         cl[r][cc[r] < C ? cc[r] : C - 1] = g;                        // an overflowing list is never read
         ++cc[r];
     });
@@ -962,20 +962,18 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_shadow_centered<D><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, seed_bounds, cap32,
                                                           shadow, info);
         dim3 fgrid((unsigned)qblocks, (unsigned)FS);
-#define SBP_FILTER_LAUNCH(NW_, UNR_, FQ_)                                                   \
-    k_knn_filter<D, NW_, UNR_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                    \
+#define SBP_FILTER_LAUNCH(NW_, FQ_)                                                         \
+    k_knn_filter<D, NW_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                          \
         shadow, info, cap32, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf, ccount)
         {
         KernelTimer timer(ctx);
         switch (g_knn_filter_variant) {
-            case 1: SBP_FILTER_LAUNCH(2, 1, FILTER_Q); break;
-            case 2: SBP_FILTER_LAUNCH(4, 2, FILTER_Q); break;
-            case 3: SBP_FILTER_LAUNCH(4, 1, FILTER_Q); break;
-            case 4: SBP_FILTER_LAUNCH(2, 2, 2); break;
-            case 6: SBP_FILTER_LAUNCH(4, 2, 2); break;
-            case 8: SBP_FILTER_LAUNCH(2, 1, 8); break;
-            case 10: SBP_FILTER_LAUNCH(4, 1, 8); break;
-            default: SBP_FILTER_LAUNCH(2, 2, FILTER_Q); break;
+            case 2: SBP_FILTER_LAUNCH(4, FILTER_Q); break;
+            case 4: SBP_FILTER_LAUNCH(2, 2); break;
+            case 6: SBP_FILTER_LAUNCH(4, 2); break;
+            case 8: SBP_FILTER_LAUNCH(2, 8); break;
+            case 10: SBP_FILTER_LAUNCH(4, 8); break;
+            default: SBP_FILTER_LAUNCH(2, FILTER_Q); break;
         }
         }
 #undef SBP_FILTER_LAUNCH

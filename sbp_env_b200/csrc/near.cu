@@ -52,7 +52,7 @@ k_near_filtered(const float *__restrict__ sh, const double *__restrict__ info, i
         }
         pos[r] = (PASS == 1 && live) ? offsets[q * S + s] : 0;
     }
-    filter_scan<DD, NW, 1, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
+    filter_scan<DD, NW, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
         const int64_t q = qb + (int64_t)r * TPB;
         double qv[D];
 #pragma unroll
