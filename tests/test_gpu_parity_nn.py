@@ -441,3 +441,45 @@ def test_pack_adjacency_device_kernel_roundtrip(sg):
         assert torch.equal(code, D.pack_adjacency(nbr.cpu(), vis.cpu()).cuda())
         n2, v2 = D.unpack_adjacency(code)
         assert torch.equal(n2, nbr) and torch.equal(v2, vis)
+
+
+def test_captured_step_host_to_host_follows_its_inputs(sg):
+    """CapturedStep around a whole host-to-host step (H2D of a sample batch from pinned memory,
+    node store rebuilt, connection, packed adjacency back to pinned memory): every replay works
+    on the CURRENT contents of the pinned input and equals the eager computation."""
+    import torch
+
+    free = load_map("room1")
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
+    rng = np.random.default_rng(21)
+    m, k = 3000, 6
+
+    def batch():
+        pts = rng.random((3 * m, 2)) * free.shape
+        return pts[cc.feasible_batch(pts)][:m]
+
+    pinned = torch.from_numpy(batch()).pin_memory()
+    x_dev = torch.empty((m, 2), dtype=torch.float64, device="cuda")
+    code_h = torch.empty((m, k), dtype=torch.int32).pin_memory()
+    tree = sg.NodeStore(2, capacity=4096)
+
+    def body():
+        x_dev.copy_(pinned, non_blocking=True)
+        tree.truncate(0)
+        tree.extend(x_dev)
+        nb, vs = sg.prm_connect_knn(cc, tree, k)
+        code_h.copy_(sg.distributed.pack_adjacency(nb, vs), non_blocking=True)
+
+    step = sg.CapturedStep(body)
+    for _ in range(3):
+        pinned.copy_(torch.from_numpy(batch()))           # new samples in the same pinned buffer
+        step.replay()
+        torch.cuda.synchronize()
+        nbr, vis = sg.distributed.unpack_adjacency(code_h)
+        pts = pinned.numpy()
+        oi, _ = orc.knn(pts, pts, k + 1)
+        want = np.array([[j for j in r if j != i][:k] for i, r in enumerate(oi)])
+        assert np.array_equal(nbr.numpy(), want)
+        om = orc.Map(free)
+        assert np.array_equal(vis.numpy(), om.visible2d(pts[want.reshape(-1)], np.repeat(pts, k, 0)).reshape(m, k))
+        assert len(tree) == m and np.array_equal(tree.poses, pts)
