@@ -70,10 +70,54 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
     return ok != 0;
 }
 
+#define BOUNDS_BLOCKS 128
+// Bounding box of the first DD coordinates: per-block partials [blocks][DD][2] = (min, max),
+// then a one-warp fold (NaN coordinates are ignored by fmin / fmax).
+template <int DD>
+__global__ void __launch_bounds__(256)
+k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial) {
+    __shared__ double sh[2 * DD][8];
+    double mn[DD], mx[DD];
+#pragma unroll
+    for (int j = 0; j < DD; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
+#pragma unroll
+        for (int j = 0; j < DD; ++j) {
+            const double v = soa[(int64_t)j * capacity + t];
+            mn[j] = fmin(mn[j], v); mx[j] = fmax(mx[j], v);
+        }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < DD; ++j) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[j] = fmin(mn[j], __shfl_down_sync(0xffffffffu, mn[j], o));
+            mx[j] = fmax(mx[j], __shfl_down_sync(0xffffffffu, mx[j], o));
+        }
+        if (lane == 0) { sh[2 * j][w] = mn[j]; sh[2 * j + 1][w] = mx[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * DD) {
+        double v = sh[threadIdx.x][0];
+        for (int i = 1; i < 8; ++i) v = (threadIdx.x & 1) ? fmax(v, sh[threadIdx.x][i]) : fmin(v, sh[threadIdx.x][i]);
+        partial[(int64_t)blockIdx.x * 2 * DD + threadIdx.x] = v;
+    }
+}
+
+template <int DD>
+__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+    const int c = threadIdx.x;                     // one thread per (coordinate, min | max)
+    if (c >= 2 * DD) return;
+    double v = partial[c];
+    for (int i = 1; i < nb; ++i) v = (c & 1) ? fmax(v, partial[(int64_t)i * 2 * DD + c]) : fmin(v, partial[(int64_t)i * 2 * DD + c]);
+    out[c] = v;
+}
+
 // Centred fp32 shadow [D + 1][cap32]: coordinates relative to the bounding-box centre and
 // the squared norm of the ROUNDED coordinates (exact products, one rounding).  Slots in
 // [n, cap32) hold the origin with norm 3e38 so that a tile tail never passes a threshold.
-// info[0] = M (max |centred coordinate|, +inf when a bound is not finite), info[1+j] = c_j.
+// info[0] = M (max |centred coordinate|, +inf when a bound is not finite), info[1+j] = c_j,
+// info[1+D+j] = extent of coordinate j (max - min).
 template <int D>
 __global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capacity, int64_t n,
                                   const double *__restrict__ bounds /*[D][2] = min, max*/,
@@ -90,7 +134,10 @@ __global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capaci
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         info[0] = M * (1.0 + 1e-9);
 #pragma unroll
-        for (int j = 0; j < D; ++j) info[1 + j] = c[j];
+        for (int j = 0; j < D; ++j) {
+            info[1 + j] = c[j];
+            info[1 + D + j] = bounds[2 * j + 1] - bounds[2 * j];
+        }
     }
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < cap32;
          t += (int64_t)gridDim.x * blockDim.x) {
@@ -116,10 +163,15 @@ __global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capaci
 // fp64 d^2 bound of the query (seed, or the radius threshold); xq its coordinates (stride of
 // the caller), DD the number of leading coordinates the distance uses.  Returns false -- and
 // thr = -inf, so that nothing passes -- when the query cannot be filtered conservatively.
+// `max_expected` > 0 additionally refuses a query whose bound is too loose to be worth filtering:
+// the expected number of nodes inside the bounding cube of its ball, n * prod_j min(1, 2 r /
+// extent_j), exceeds it (seeds from an x-y grid say little about the other coordinates of
+// isotropic clouds; such queries go to the one-kernel scan instead of overflowing their lists).
 template <int DD>
 __device__ __forceinline__ bool filter_query_setup(const double *__restrict__ info, const double *xq,
                                                    bool live, double bound2, float (&nq2)[DD],
-                                                   float &thr) {
+                                                   float &thr, double n_nodes = 0.0,
+                                                   double max_expected = 0.0) {
     const double M = info[0];
     double Mq = 0.0, qq = 0.0;
 #pragma unroll
@@ -137,7 +189,16 @@ __device__ __forceinline__ bool filter_query_setup(const double *__restrict__ in
                      1e-15 * Mq * Mq;
     const double ra = sqrt(bound2) + a;                              // NaN for bound2 < 0 or NaN
     const double pos = (ra * ra + E) * (1.0 + 1e-9);
-    const bool usable = live && mm < 1e15 && bound2 < INFINITY && E <= ra * ra;
+    bool usable = live && mm < 1e15 && bound2 < INFINITY && E <= ra * ra;
+    if (usable && max_expected > 0.0) {
+        double expect = n_nodes;
+#pragma unroll
+        for (int j = 0; j < DD; ++j) {
+            const double ext = info[1 + DD + j];
+            expect *= (ext > 2.0 * ra) ? 2.0 * ra / ext : 1.0;
+        }
+        usable = expect <= max_expected;
+    }
     thr = usable ? __double2float_ru(pos - qq) : -INFINITY;          // t (or NaN) never passes -inf
     return usable;
 }

@@ -264,14 +264,28 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
     float thr[FQ];
     int cc[FQ];
     int32_t *cl[FQ];         // this (query, chunk)'s candidate list
+    bool any_usable = false;
 #pragma unroll
     for (int r = 0; r < FQ; ++r) {
         const int64_t q = qb + (int64_t)r * TPB;
         const bool live = q < m;
+        // a bound so loose that more nodes are expected inside it than the lists hold (C S groups)
         const bool usable = filter_query_setup<D>(info, X + (live ? q : 0) * D, live,
-                                                  live ? seed2[q] : -1.0, nq2[r], thr[r]);
+                                                  live ? seed2[q] : -1.0, nq2[r], thr[r], (double)n,
+                                                  2.0 * (double)C * (double)S);
         cc[r] = (live && !usable) ? C + 1 : 0;                       // C + 1 = "not filterable"
         cl[r] = cand + ((live ? q : 0) * S + s) * (int64_t)C;
+        any_usable |= usable;
+    }
+    // nothing to filter for this CTA's queries (loose seeds of an isotropic cloud in d > 2,
+    // outliers, ...): they are all flagged; skip the scan
+    if (!__syncthreads_or(any_usable ? 1 : 0)) {
+#pragma unroll
+        for (int r = 0; r < FQ; ++r) {
+            const int64_t q = qb + (int64_t)r * TPB;
+            if (q < m) ccount[q * S + s] = cc[r];
+        }
+        return;
     }
     filter_scan<D, NW, FQ>(sh, cap32, c0, c1, nq2, thr, [&](int r, int32_t g) {
         cl[r][cc[r] < C ? cc[r] : C - 1] = g;                        // an overflowing list is never read
@@ -576,7 +590,6 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
 // B^2 is inflated by 1e-9 (cell-assignment rounding, and distinct d^2 that collapse to one
 // rounded square root).  The scan still evaluates every (query, node) pair; only the
 // number of candidates that reach the exact fp64 insertion path shrinks (~9.4K -> ~2K).
-#define BOUNDS_BLOCKS 128
 // per-block partial bounding boxes [BOUNDS_BLOCKS][4] = (min x, max x, min y, max y)
 __global__ void __launch_bounds__(256)
 k_bounds2d_partial(const double *__restrict__ soa, int64_t capacity, int64_t n,
@@ -862,7 +875,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         // node chunks: with seeded bounds a chunk restart is cheap, so fill the SMs with
         // ~28 warps each (measured: 1.23 -> 1.04 ms on 50k x 50k); without seeds every chunk
         // re-learns its bound (K ln(N/K) insertions), so only enough CTAs to cover the SMs
-        const bool seeded = D == 2 && g_knn_seed && n >= 2048;
+        const bool seeded = D >= 2 && g_knn_seed && n >= 2048;
         int64_t want = seeded ? (28 * sm * 32 / tpb + tiles - 1) / tiles : (2 * sm + tiles - 1) / tiles;
         int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
@@ -890,7 +903,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         return SBP_OK;
     }
     const double *seed = nullptr, *seed_bounds = nullptr;
-    if (D == 2 && g_knn_seed && n >= 2048) {
+    if (D >= 2 && g_knn_seed && n >= 2048) {
         int G = (int)ceil(sqrt(2.0 * (double)n));
         if (G > 2048) G = 2048;
         const int64_t L = (int64_t)G * G;
@@ -950,10 +963,18 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         const size_t nflags = (size_t)((m + 31) / 32);
         rc = sbp_ctx_scratch(ctx, 9, (size_t)m * FS * sizeof(int32_t) + nflags, &nbuf);
         if (rc) return rc;
-        rc = sbp_ctx_scratch(ctx, 10, 64 + (size_t)(D + 1) * cap32 * sizeof(float), &shbuf);
+        const size_t shdr = 128 + 128 + (size_t)BOUNDS_BLOCKS * 2 * D * sizeof(double);   // info | bounds | partials
+        rc = sbp_ctx_scratch(ctx, 10, shdr + (size_t)(D + 1) * cap32 * sizeof(float), &shbuf);
         if (rc) return rc;
-        double *info = (double *)shbuf;                            // [1 + D] <= 64 bytes
-        float *shadow = (float *)((char *)shbuf + 64);
+        double *info = (double *)shbuf;                            // [1 + 2 D] doubles
+        float *shadow = (float *)((char *)shbuf + shdr);
+        if (D > 2) {               // the cell grid only bounds x and y: all D coordinates here
+            double *bnd = (double *)((char *)shbuf + 128), *partial = (double *)((char *)shbuf + 256);
+            k_bounds_partial<D><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
+            k_bounds_fold<D><<<1, 32, 0, ctx->stream>>>(partial, BOUNDS_BLOCKS, bnd);
+            ctx->launches += 2;
+            seed_bounds = bnd;
+        }
         int32_t *ccount = (int32_t *)nbuf;
         uint8_t *flags = (uint8_t *)nbuf + (size_t)m * FS * sizeof(int32_t);
         SBP_CUDA(cudaMemsetAsync(flags, 0, nflags, ctx->stream));

@@ -15,7 +15,6 @@
 #define KNN_TPB 128        // queries per CTA in the batched radius kernel
 #define KNN_TILE 1024      // nodes staged in shared memory per step
 #define WIDE_TPB 256
-#define BOUNDS_BLOCKS 128
 
 // --------------------------------------------------------- K5: radius -------
 // Radius query on the same scan (K5'): a group that passes the conservative fp32 test has
@@ -245,48 +244,6 @@ k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
     }
 }
 
-// Bounding box of the first DD coordinates: per-block partials [blocks][DD][2] = (min, max),
-// then a one-warp fold (NaN coordinates are ignored by fmin / fmax).
-template <int DD>
-__global__ void __launch_bounds__(256)
-k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial) {
-    __shared__ double sh[2 * DD][8];
-    double mn[DD], mx[DD];
-#pragma unroll
-    for (int j = 0; j < DD; ++j) { mn[j] = INFINITY; mx[j] = -INFINITY; }
-    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < n; t += (int64_t)gridDim.x * 256) {
-#pragma unroll
-        for (int j = 0; j < DD; ++j) {
-            const double v = soa[(int64_t)j * capacity + t];
-            mn[j] = fmin(mn[j], v); mx[j] = fmax(mx[j], v);
-        }
-    }
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int j = 0; j < DD; ++j) {
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[j] = fmin(mn[j], __shfl_down_sync(0xffffffffu, mn[j], o));
-            mx[j] = fmax(mx[j], __shfl_down_sync(0xffffffffu, mx[j], o));
-        }
-        if (lane == 0) { sh[2 * j][w] = mn[j]; sh[2 * j + 1][w] = mx[j]; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * DD) {
-        double v = sh[threadIdx.x][0];
-        for (int i = 1; i < 8; ++i) v = (threadIdx.x & 1) ? fmax(v, sh[threadIdx.x][i]) : fmin(v, sh[threadIdx.x][i]);
-        partial[(int64_t)blockIdx.x * 2 * DD + threadIdx.x] = v;
-    }
-}
-
-template <int DD>
-__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out) {
-    const int c = threadIdx.x;                     // one thread per (coordinate, min | max)
-    if (c >= 2 * DD) return;
-    double v = partial[c];
-    for (int i = 1; i < nb; ++i) v = (c & 1) ? fmax(v, partial[(int64_t)i * 2 * DD + c]) : fmin(v, partial[(int64_t)i * 2 * DD + c]);
-    out[c] = v;
-}
-
 int g_near_filter = 1;    // tuning knob: filtered radius query (results unchanged)
 
 template <int D, bool XY>
@@ -313,11 +270,11 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
         void *ws = nullptr, *shbuf = nullptr;
         int32_t rc = sbp_ctx_scratch(ctx, 0, (size_t)L * 2 * sizeof(int64_t), &ws);
         if (rc) return rc;
-        const size_t hdr = 64 + 128 + (size_t)BOUNDS_BLOCKS * 2 * DD * sizeof(double);
+        const size_t hdr = 128 + 128 + (size_t)BOUNDS_BLOCKS * 2 * DD * sizeof(double);   // info | bounds | partials
         rc = sbp_ctx_scratch(ctx, 10, hdr + (size_t)(DD + 1) * cap32 * sizeof(float), &shbuf);
         if (rc) return rc;
-        double *info = (double *)shbuf, *bnd = (double *)((char *)shbuf + 64),
-               *partial = (double *)((char *)shbuf + 64 + 128);
+        double *info = (double *)shbuf, *bnd = (double *)((char *)shbuf + 128),
+               *partial = (double *)((char *)shbuf + 128 + 128);
         float *shadow = (float *)((char *)shbuf + hdr);
         int64_t *counts = (int64_t *)ws, *offsets = counts + L;
         k_bounds_partial<DD><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);

@@ -483,3 +483,42 @@ def test_captured_step_host_to_host_follows_its_inputs(sg):
         om = orc.Map(free)
         assert np.array_equal(vis.numpy(), om.visible2d(pts[want.reshape(-1)], np.repeat(pts, k, 0)).reshape(m, k))
         assert len(tree) == m and np.array_equal(tree.poses, pts)
+
+
+@pytest.mark.parametrize("d,layout", [(4, "arm"), (3, "cube"), (6, "cube"), (4, "planar"), (3, "nan_inf")])
+def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
+    """d > 2: the seeds come from the x-y cell grid, the bound is the exact d-dimensional K-th
+    distance among the nodes found there.  Arm-like clouds (x, y in pixels, angles in radians)
+    and clouds that are flat in the extra coordinates filter well; isotropic cubes give loose
+    bounds, are recognised (expected count inside the bound) and go to the one-kernel scan.
+    Either way the result equals the oracle's and the unfiltered kernels'."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(10 * d + len(layout))
+    n, m = 30_011, 2100
+    if layout == "arm":
+        poses = rng.random((n, 4)) * [1024, 1024, 2 * np.pi, 2 * np.pi] - [0, 0, np.pi, np.pi]
+    elif layout == "planar":
+        poses = np.concatenate([rng.random((n, 2)) * 500, rng.standard_normal((n, 2)) * 1e-3], 1)
+    else:
+        poses = rng.random((n, d)) * 300
+    X = poses[rng.integers(0, n, m)] + rng.standard_normal((m, d)) * 0.2
+    X[: m // 4] = rng.random((m // 4, d)) * (poses.max(0) - poses.min(0)) * 1.2 + poses.min(0)
+    if layout == "nan_inf":
+        poses[3] = np.nan
+        poses[9, 2] = np.inf
+        X[5, 1] = np.nan
+        X[6] = 1e300
+    t = sg.NodeStore(d)
+    t.extend(poses)
+    lib = _lib.load()
+    try:
+        for k in (11, 1, 32):
+            ei, ed = orc.knn(poses, X, k)
+            for filt in (1, 0):
+                lib.sbp_tune(b"knn_filter", filt)
+                idx, dist = t.knn(X, k)
+                assert np.array_equal(idx, ei), (d, layout, k, filt)
+                assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt)
+    finally:
+        lib.sbp_tune(b"knn_filter", 1)
