@@ -33,7 +33,7 @@ for n, m in ((50_000, 50_000), (1_000_000, 100_000)):
     tree = sg.NodeStore(2, capacity=n)
     tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * scale)
     X = tree.rows_device(0, m)
-    for filt, var, chunks in [(0, 0, 0)] + [(1, v, c) for v in (0, 2, 8, 10) for c in (0, 8, 16)]:
+    for filt, var, chunks in [(0, 0, 0)] + [(1, v, c) for v in (0, 2) for c in (0, 4, 6, 8, 10, 12, 16)]:
         lib.sbp_tune(b"knn_filter", filt)
         lib.sbp_tune(b"knn_filter_variant", var)
         lib.sbp_tune(b"knn_filter_chunks", chunks)
