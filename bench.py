@@ -430,6 +430,21 @@ def run_ours(args):
         P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
         Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
         micro["uniform_2^24_edges"] = time_visible(P, Q)
+        # point feasibility: a pure stream of 16 B in + 1 B out per point
+        cc.feasible_batch(P)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            cc.feasible_batch(P)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        tf = float(np.median(ts)) / 1e3
+        micro["feasible_2^24_points"] = {"points": n_u, "ms": tf * 1e3, "points_per_s": n_u / tf,
+                                         "algorithmic_GBps": 17.0 * n_u / tf / 1e9,
+                                         "hbm_frac": 17.0 * n_u / tf / 1e9 / hbm_peak}
         fr = torch.from_numpy(nodes).to(dev)
         for L in (8, 32, 128):
             n_b = 1 << 22
