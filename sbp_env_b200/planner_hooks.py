@@ -5,7 +5,7 @@ planner object.
 inherits its ``run_once``; /root/reference/sbp_env/planners/rrtPlanner.py) after ``Env`` has
 initialised it and replaces, on that INSTANCE only:
 
-  add_newnode                   :106-113   also appends the pose to a device ``NodeStore``
+  (the node arrays)             :106-113   mirrored lazily into a device ``NodeStore``
   find_nearest_neighbour_idx    :268-279   ``NodeStore.nearest`` (one wide-kNN launch) when the
                                            array passed in is the planner's own node prefix
   choose_least_cost_parent      :173-196   linear path: the O(N) Python loop over all nodes
@@ -52,59 +52,103 @@ class _LazyDistances(dict):
         return v
 
 
-def accelerate_rrt(planner, store=None):
-    """Hook ``planner`` (see module docstring).  ``store`` may be passed in (tests); by default
-    a ``NodeStore`` of the engine's dimension on the checker's device is created and filled
-    with the nodes the planner already holds.  Returns the store."""
-    if getattr(planner, "_sbp_accelerated", False):
-        return planner._sbp_store
+class _Tree:
+    """One tree of a planner (its Node list and pose array) and the device store that mirrors
+    it.  The planners append to their arrays directly (``poses[len(nodes)] = pos;
+    nodes.append(node)``: rrtPlanner.py:106-113, birrtPlanner.py:67-69, :113-114), so the mirror
+    is brought up to date lazily, at the start of every hooked query."""
+
+    def __init__(self, nodes, poses, store):
+        self.nodes, self.poses, self.store = nodes, poses, store
+        self.index_of = {}
+        self.costs = _NodeCosts(nodes)
+
+    def sync(self):
+        have, n = len(self.store), len(self.nodes)
+        if have < n:
+            self.store.extend(self.poses[have:n])
+            for i in range(have, n):
+                self.index_of[id(self.nodes[i])] = i
+        return self.store
+
+
+def _accelerate(planner, trees):
     args = planner.args
     cc = args.engine.cc
-    if store is None:
-        store = NodeStore(args.engine.get_dimension(), capacity=len(planner.poses),
-                          device=getattr(cc, "_device", 0))
-    n0 = len(planner.nodes)
-    if n0:
-        store.extend(planner.poses[:n0])
-    index_of = {id(n): i for i, n in enumerate(planner.nodes)}
-    orig_add = planner.add_newnode
     orig_nearest = planner.find_nearest_neighbour_idx
     orig_choose = planner.choose_least_cost_parent
-    costs = _NodeCosts(planner.nodes)
 
-    def add_newnode(node):
-        index_of[id(node)] = len(planner.nodes)
-        orig_add(node)
-        store.append(node.pos)
+    def tree_of_poses(poses):
+        base = getattr(poses, "base", None)
+        for t in trees:
+            if base is t.poses and len(poses) == len(t.nodes):
+                return t
+        return None
 
     def find_nearest_neighbour_idx(pos, poses):
-        # the planner passes its own prefix `self.poses[:len(self.nodes)]` (rrtPlanner.py:77)
-        if getattr(poses, "base", None) is planner.poses and len(poses) == len(store):
-            return store.nearest(pos)
-        return orig_nearest(pos, poses)
+        # the planners pass a prefix of their own pose array (rrtPlanner.py:77, birrtPlanner.py:54)
+        t = tree_of_poses(poses)
+        if t is None:
+            return orig_nearest(pos, poses)
+        return t.sync().nearest(pos)
 
     def choose_least_cost_parent(newnode, nn=None, nodes=None, skip_optimality=False, use_rtree=False,
                                  poses=None):
-        if skip_optimality or use_rtree or poses is not None or nodes is not planner.nodes \
-                or len(nodes) != len(store):
+        t = next((t for t in trees if nodes is t.nodes), None)
+        if skip_optimality or use_rtree or poses is not None or t is None:
             return orig_choose(newnode, nn, nodes, skip_optimality=skip_optimality, use_rtree=use_rtree,
                                poses=poses)
+        store = t.sync()
         planner._new_node_dist_to_all_others = _LazyDistances(args.engine.dist)
-        nn_idx = None if nn is None else index_of[id(nn)]
+        nn_idx = None if nn is None else t.index_of[id(nn)]
         parent, cost, _ = planner_ops.choose_least_cost_parent(
-            cc, store, costs, newnode.pos, nn_idx, args.radius, dist=args.engine.dist, poses=planner.poses)
+            cc, store, t.costs, newnode.pos, nn_idx, args.radius, dist=args.engine.dist, poses=t.poses)
         nn = nodes[parent]
         newnode.cost = cost
         assert newnode is not nn
         newnode.parent = nn
         return newnode, nn
 
-    planner.add_newnode = add_newnode
     planner.find_nearest_neighbour_idx = find_nearest_neighbour_idx
     planner.choose_least_cost_parent = choose_least_cost_parent
     planner._sbp_accelerated = True
-    planner._sbp_store = store
-    return store
+    planner._sbp_trees = trees
+
+
+def _new_store(planner, poses):
+    cc = planner.args.engine.cc
+    return NodeStore(planner.args.engine.get_dimension(), capacity=len(poses), device=getattr(cc, "_device", 0))
+
+
+def accelerate_rrt(planner, store=None):
+    """Hook ``planner`` (see module docstring).  ``store`` may be passed in (tests); by default
+    a ``NodeStore`` of the engine's dimension on the checker's device is created; it mirrors
+    ``planner.poses[:len(planner.nodes)]``.  Returns the store."""
+    if getattr(planner, "_sbp_accelerated", False):
+        return planner._sbp_trees[0].store
+    tree = _Tree(planner.nodes, planner.poses, store if store is not None else _new_store(planner, planner.poses))
+    tree.sync()
+    _accelerate(planner, [tree])
+    return tree.store
+
+
+def accelerate_birrt(planner, stores=None):
+    """The same hooks for ``BiRRTPlanner`` (planners/birrtPlanner.py:36-124), whose ``run_once``
+    alternates between the start tree (``nodes`` / ``poses``) and the goal tree
+    (``goal_tree_nodes`` / ``goal_tree_poses``): each tree gets its own device store, picked by
+    the identity of the array / list the planner passes in.  The join test (:80-87) and the
+    re-parenting walk after the join (:101-118, which calls ``choose_least_cost_parent`` on the
+    start tree) run unchanged on top.  Returns the two stores."""
+    if getattr(planner, "_sbp_accelerated", False):
+        return tuple(t.store for t in planner._sbp_trees)
+    s0, s1 = stores if stores is not None else (_new_store(planner, planner.poses),
+                                                _new_store(planner, planner.goal_tree_poses))
+    trees = [_Tree(planner.nodes, planner.poses, s0),
+             _Tree(planner.goal_tree_nodes, planner.goal_tree_poses, s1)]
+    for t in trees:
+        t.sync()
+    _accelerate(planner, trees)
+    return s0, s1
 
 
 def accelerate_prm(planner, store=None, chunk_rows: int = 4096):

@@ -254,5 +254,6 @@ def test_accelerate_rrt_hooks_on_a_planner_look_alike(sg):
     assert [n.cost for n in a.nodes] == [n.cost for n in b.nodes]
     assert [None if n.parent is None else a.nodes.index(n.parent) for n in a.nodes] == \
            [None if n.parent is None else b.nodes.index(n.parent) for n in b.nodes]
+    b._sbp_trees[0].sync()                         # the mirror is brought up to date lazily
     assert len(store) == 700 and np.array_equal(store.poses, b.poses[:700])
     assert vis_a == vis_b                          # same Stats accounting of the edge checks
