@@ -131,3 +131,29 @@ def test_guard_band_is_resolved_exactly(sg):
     U = rng.random((200000, 4)) * [W, H, 6, 6] - [0, 0, 3, 3]
     cc.feasible_batch(U)
     assert cc.last_ambiguous <= 5
+
+
+def test_arm_prescreen_bucket(sg):
+    """cc.prescreen for the 4-D arm checker: one launch decides a whole bucket of configurations,
+    feasible(c) of a row is answered from the remembered booleans (guard-band rows included)."""
+    free = load_map("4d")
+    W, H = free.shape
+    cc = sg.RobotArm4dCollisionChecker(map_png("4d"), stick_robot_length_config=[30.0, 30.0])
+    om = orc.Map(free)
+    rng = np.random.default_rng(17)
+    bucket = rng.random((10000, 4)) * [W, H, 2 * np.pi, 2 * np.pi] - [0, 0, np.pi, np.pi]
+    bucket[:50, :2] = np.floor(bucket[:50, :2])
+    bucket[:50, 2:] = rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi], (50, 2))     # on pixel boundaries
+    want = om.arm_feasible(bucket, 30.0, 30.0)
+    launches = []
+    inner = cc._feasible_host
+    cc._feasible_host = lambda C: (launches.append(len(C)), inner(C))[1]
+    try:
+        assert np.array_equal(cc.prescreen(bucket), want) and launches == [10000]
+        for i in (0, 7, 49, 5000, 9999):
+            assert bool(cc.feasible(bucket[i])) == bool(want[i])
+        assert launches == [10000]
+        assert bool(cc.feasible([100.5, 200.25, 0.3, -1.2])) == bool(om.arm_feasible(np.array([[100.5, 200.25, 0.3, -1.2]]), 30.0, 30.0)[0])
+        assert launches == [10000, 1]
+    finally:
+        del cc._feasible_host
