@@ -198,8 +198,8 @@ def run_ours(args):
         mark("gather")
         return nbr, vis
 
-    # The step is ~20 short kernels; issued one by one from Python the host cannot keep up
-    # with the GPU, so the timed loop replays the step from a CUDA graph (the library's
+    # The step is ~20 short kernels; issued one by one from Python the launch gaps cost ~15 %,
+    # so the timed loop replays the step from a CUDA graph (the library's
     # PRMConnectGraph); the all-gather (N > 1) follows the replay on the same stream.
     gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
 

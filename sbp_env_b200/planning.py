@@ -153,7 +153,7 @@ class PRMConnectGraph(CapturedStep):
     """:func:`prm_connect_knn` for a fixed problem shape as a :class:`CapturedStep`.
 
     One connection step is ~20 short kernels (cell grid, seeds, filter, refine, edge gather,
-    visibility); issued one by one from Python their launch cost exceeds the ~0.5 ms the GPU
+    visibility); issued one by one from Python the launch gaps add ~15 % to the ~0.5 ms the GPU
     needs for a 50 000-node roadmap, so the inner loop is captured and a step becomes a single
     graph launch.  Results are identical to the eager call.  ``tree`` must not change size
     and ``queries`` (when given) must be updated in place.
