@@ -153,6 +153,7 @@ static void arm_cfg(const sbp_map *m, bool smem, int &grid, int &threads, size_t
 
 extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const double *C,
                                     int64_t n, uint8_t *out, int32_t *flags) {
+    SBP_NVTX("sbp_arm_feasible");
     SBP_REQUIRE(map && (n == 0 || (C && out)), "sbp_arm_feasible: NULL argument");
     SBP_REQUIRE(n >= 0, "sbp_arm_feasible: n < 0");
     if (n == 0) return SBP_OK;
@@ -206,6 +207,7 @@ static int32_t launch_arm_visible(sbp_map *map, double L0, double L1, const doub
 extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const double *C1,
                                    const double *C2, int64_t n, uint8_t *out, int32_t *flags,
                                    uint64_t *cfg_tested) {
+    SBP_NVTX("sbp_arm_visible");
     SBP_REQUIRE(map && (n == 0 || (C1 && C2 && out)), "sbp_arm_visible: NULL argument");
     SBP_REQUIRE(n >= 0, "sbp_arm_visible: n < 0");
     if (n == 0) return SBP_OK;

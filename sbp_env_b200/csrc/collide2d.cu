@@ -377,6 +377,7 @@ static int32_t set_smem(K kernel, size_t smem) {
 
 extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint8_t *out,
                                   int32_t *flags) {
+    SBP_NVTX("sbp_feasible2d");
     SBP_REQUIRE(map && (n == 0 || (P && out)), "sbp_feasible2d: NULL argument");
     SBP_REQUIRE(n >= 0, "sbp_feasible2d: n < 0");
     if (n == 0) return SBP_OK;
@@ -467,6 +468,7 @@ static int32_t launch_visible(sbp_map *map, const double *P, const double *Q, in
 
 extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q, int64_t n,
                                  uint8_t *out, int32_t *flags, uint64_t *px_tested) {
+    SBP_NVTX("sbp_visible2d");
     SBP_REQUIRE(map && (n == 0 || (P && Q && out)), "sbp_visible2d: NULL argument");
     SBP_REQUIRE(n >= 0, "sbp_visible2d: n < 0");
     if (n == 0) return SBP_OK;
@@ -518,6 +520,7 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
 
 extern "C" int32_t sbp_first_blocked2d(sbp_map *map, const double *P, const double *Q, int64_t n,
                                        int32_t *out_xy, int32_t *flags) {
+    SBP_NVTX("sbp_first_blocked2d");
     SBP_REQUIRE(map && (n == 0 || (P && Q && out_xy)), "sbp_first_blocked2d: NULL argument");
     SBP_REQUIRE(n >= 0, "sbp_first_blocked2d: n < 0");
     if (n == 0) return SBP_OK;

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/sbp_gpu.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -34,6 +36,14 @@ void sbp_set_error(const char *fmt, ...);
             return SBP_ERR_ARG;                                                     \
         }                                                                           \
     } while (0)
+
+// NVTX range around a C-ABI entry point (header-only NVTX v3: a no-op unless a profiler is
+// attached), so that timelines show the library calls by name.
+struct SbpNvtxRange {
+    explicit SbpNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~SbpNvtxRange() { nvtxRangePop(); }
+};
+#define SBP_NVTX(name) SbpNvtxRange sbp_nvtx_range__(name)
 
 // ------------------------------------------------------------- handles -----
 // scratch slots: 0,1 kNN partial lists / near work-space; 2-4 staging of the *_host entry points

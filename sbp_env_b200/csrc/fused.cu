@@ -87,6 +87,7 @@ extern "C" int32_t sbp_nodes_near_visible(sbp_nodes *s, sbp_map *map, int32_t ar
                                           int32_t metric, int32_t closed, int32_t direction,
                                           int64_t *out_idx, uint8_t *out_vis, int32_t cap,
                                           int32_t *count, int32_t *flags) {
+    SBP_NVTX("sbp_nodes_near_visible");
     SBP_REQUIRE(s && map && X && out_idx && out_vis && count, "sbp_nodes_near_visible: NULL argument");
     SBP_REQUIRE(m >= 1 && m <= 65535 && cap >= 1, "sbp_nodes_near_visible: 1 <= m <= 65535, cap >= 1");
     SBP_REQUIRE(s->d >= 2 && (!arm || s->d == 4), "sbp_nodes_near_visible: d >= 2 (arm: d == 4)");

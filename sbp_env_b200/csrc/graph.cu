@@ -157,6 +157,7 @@ static int32_t graph_build(sbp_graph *g, EdgeSource es) {
 
 extern "C" int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis, int64_t m,
                                        int32_t k, int64_t first_row) {
+    SBP_NVTX("sbp_graph_build_knn");
     SBP_REQUIRE(g && (m == 0 || nbr), "sbp_graph_build_knn: NULL argument");
     SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_graph_build_knn: bad sizes");
     EdgeSource es{nbr, nullptr, vis, m * k, k, first_row, g->n};
@@ -165,6 +166,7 @@ extern "C" int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const u
 
 extern "C" int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,
                                          const uint8_t *keep, int64_t e) {
+    SBP_NVTX("sbp_graph_build_edges");
     SBP_REQUIRE(g && (e == 0 || (src && dst)), "sbp_graph_build_edges: NULL argument");
     SBP_REQUIRE(e >= 0, "sbp_graph_build_edges: e < 0");
     EdgeSource es{src, dst, keep, e, 1, 0, g->n};
@@ -303,6 +305,7 @@ __global__ void k_graph_work_init(int32_t *__restrict__ work, int64_t n, int64_t
 // start / goal / hops / paths are device pointers.
 extern "C" int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64_t *goal, int64_t nq,
                                  int32_t *hops, int64_t *paths, int32_t max_len) {
+    SBP_NVTX("sbp_graph_bfs");
     SBP_REQUIRE(g && (nq == 0 || (start && goal && hops)), "sbp_graph_bfs: NULL argument");
     SBP_REQUIRE(nq >= 0 && (!paths || max_len >= 1), "sbp_graph_bfs: bad sizes");
     if (nq == 0) return SBP_OK;
@@ -369,6 +372,7 @@ k_adjacency_peer_scatter(const int64_t *__restrict__ nbr, const uint8_t *__restr
 extern "C" int32_t sbp_adjacency_peer_scatter(sbp_ctx *ctx, const int64_t *nbr, const uint8_t *vis,
                                               int64_t total, void *const *peer_bufs, int32_t world,
                                               int64_t offset) {
+    SBP_NVTX("sbp_adjacency_peer_scatter");
     SBP_REQUIRE(ctx && (total == 0 || (nbr && vis)) && peer_bufs, "sbp_adjacency_peer_scatter: NULL argument");
     SBP_REQUIRE(world >= 1 && world <= 16, "sbp_adjacency_peer_scatter: 1 <= world <= 16");
     SBP_REQUIRE(total >= 0 && offset >= 0 && (offset & 3) == 0, "sbp_adjacency_peer_scatter: bad offset / size");
@@ -417,6 +421,7 @@ k_adjacency_multicast(const int64_t *__restrict__ nbr, const uint8_t *__restrict
 // sbp_adjacency_peer_scatter for the rest.
 extern "C" int32_t sbp_adjacency_multicast(sbp_ctx *ctx, const int64_t *nbr, const uint8_t *vis,
                                            int64_t total, void *mc_buf, int64_t offset) {
+    SBP_NVTX("sbp_adjacency_multicast");
     SBP_REQUIRE(ctx && (total == 0 || (nbr && vis)) && mc_buf, "sbp_adjacency_multicast: NULL argument");
     SBP_REQUIRE(total >= 0 && offset >= 0 && (offset & 3) == 0, "sbp_adjacency_multicast: bad offset / size");
     if (total == 0) return SBP_OK;

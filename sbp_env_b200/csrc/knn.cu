@@ -1053,6 +1053,7 @@ __global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {
 
 extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32_t k,
                                  int32_t precision, int64_t *idx, double *dist) {
+    SBP_NVTX("sbp_nodes_knn");
     SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_knn: NULL argument");
     SBP_REQUIRE(m >= 0, "sbp_nodes_knn: m < 0");
     SBP_REQUIRE(k >= 1 && k <= 32, "sbp_nodes_knn: 1 <= k <= 32");

@@ -171,6 +171,7 @@ static int32_t map_create_common(sbp_ctx *ctx, const uint8_t *d_free_xy, int32_t
 
 extern "C" int32_t sbp_map_create(sbp_ctx *ctx, const uint8_t *free_xy, int32_t W, int32_t H,
                                   sbp_map **out) {
+    SBP_NVTX("sbp_map_create");
     SBP_REQUIRE(ctx && free_xy && out, "sbp_map_create: NULL argument");
     SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "sbp_map_create: 1 <= W,H <= 65536");
     SBP_CUDA(cudaSetDevice(ctx->device));
@@ -192,6 +193,7 @@ extern "C" int32_t sbp_map_create(sbp_ctx *ctx, const uint8_t *free_xy, int32_t 
 
 extern "C" int32_t sbp_map_create_device(sbp_ctx *ctx, const uint8_t *free_xy_device, int32_t W,
                                          int32_t H, sbp_map **out) {
+    SBP_NVTX("sbp_map_create_device");
     SBP_REQUIRE(ctx && free_xy_device && out, "sbp_map_create_device: NULL argument");
     SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536,
                 "sbp_map_create_device: 1 <= W,H <= 65536");

@@ -368,6 +368,7 @@ __global__ void k_zero_rowptr(int64_t m, int64_t *row_ptr, int64_t *needed) {
 extern "C" int32_t sbp_nodes_near(sbp_nodes *s, const double *X, int64_t m, double r,
                                   int32_t metric, int32_t closed, int64_t *row_ptr, int64_t *idx,
                                   int64_t idx_capacity, int64_t *needed) {
+    SBP_NVTX("sbp_nodes_near");
     SBP_REQUIRE(s && row_ptr && needed && (m == 0 || X), "sbp_nodes_near: NULL argument");
     SBP_REQUIRE(m >= 0 && idx_capacity >= 0, "sbp_nodes_near: negative size");
     SBP_REQUIRE(metric == SBP_METRIC_FULL || metric == SBP_METRIC_XY, "sbp_nodes_near: bad metric");

@@ -127,6 +127,7 @@ static int32_t nodes_grow(sbp_nodes *s, int64_t need) {
 }
 
 extern "C" int32_t sbp_nodes_append(sbp_nodes *s, const double *X, int64_t m, int32_t on_device) {
+    SBP_NVTX("sbp_nodes_append");
     SBP_REQUIRE(s && (m == 0 || X), "sbp_nodes_append: NULL argument");
     SBP_REQUIRE(m >= 0, "sbp_nodes_append: m < 0");
     if (m == 0) return SBP_OK;
@@ -235,6 +236,7 @@ __global__ void k_gather_edges(const double *__restrict__ soa, int64_t capacity,
 extern "C" int32_t sbp_nodes_gather_edges(sbp_nodes *s, const int64_t *nbr, int64_t m, int32_t k,
                                           int64_t first_row, double *P, double *Q,
                                           uint8_t *valid) {
+    SBP_NVTX("sbp_nodes_gather_edges");
     SBP_REQUIRE(s && (m == 0 || (nbr && P && Q)), "sbp_nodes_gather_edges: NULL argument");
     SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_nodes_gather_edges: bad sizes");
     if (m == 0) return SBP_OK;
@@ -288,6 +290,7 @@ __global__ void k_knn_edges(const double *__restrict__ soa, int64_t capacity, in
 extern "C" int32_t sbp_nodes_knn_edges(sbp_nodes *s, const int64_t *nbr_in, int64_t m,
                                        int32_t k_in, int64_t first_row, const double *X,
                                        int64_t *nbr_out, double *P, double *Q, uint8_t *valid) {
+    SBP_NVTX("sbp_nodes_knn_edges");
     SBP_REQUIRE(s && (m == 0 || (nbr_in && nbr_out && P && Q && valid)),
                 "sbp_nodes_knn_edges: NULL argument");
     int k_out = X ? k_in : k_in - 1;
