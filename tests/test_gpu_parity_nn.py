@@ -522,3 +522,63 @@ def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
                 assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt)
     finally:
         lib.sbp_tune(b"knn_filter", 1)
+
+
+def test_cfg2_full_size_connection_equals_oracle(sg):
+    """BASELINE.json configs[1] at FULL size -- intel_lab, 50 000 free samples, k = 10, i.e. the
+    bench workload itself: every neighbour row and every visibility bit of the 500 000
+    candidate edges equals the oracle's (the oracle needs ~0.5 s on 16 cores for this)."""
+    import bench
+
+    free = bench.load_free()
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
+    nodes = bench.draw_free_samples(free, bench.N_NODES, 0, cc.feasible_batch)
+    tree = sg.NodeStore(2, capacity=bench.N_NODES)
+    tree.extend(nodes)
+    k = bench.K_NN
+    nbr, vis = sg.prm_connect_knn(cc, tree, k)
+    oi, _ = orc.knn(nodes, nodes, k + 1)
+    rows = np.arange(len(nodes))[:, None]
+    self_col = (oi == rows)
+    # drop the self entry (or the last column when a duplicate precedes it)
+    drop = np.where(self_col.any(1), self_col.argmax(1), k)
+    keep = np.ones_like(oi, bool)
+    keep[np.arange(len(nodes)), drop] = False
+    want = oi[keep].reshape(len(nodes), k)
+    assert np.array_equal(nbr.cpu().numpy(), want)
+    om = orc.Map(free)
+    want_vis = om.visible2d(nodes[want.reshape(-1)], np.repeat(nodes, k, 0)).reshape(-1, k)
+    assert np.array_equal(vis.cpu().numpy(), want_vis)
+
+
+def test_million_node_knn_properties(sg):
+    """cfg5-scale store (1M nodes): size-independent properties of the kNN answer for 20 000
+    queries -- rows ordered by (distance, index), distances equal to the fp64 recomputation, no
+    stored node closer than the k-th neighbour among 64 random probes per query -- plus exact
+    equality with the oracle on 200 sampled rows."""
+    import torch
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(12)
+    n, m, k = 1_000_000, 20_000, 10
+    P = torch.rand((n, 2), generator=g, device="cuda", dtype=torch.float64) * 32768
+    P[:1000] = torch.floor(P[:1000])                                   # exact ties on a lattice
+    X = torch.rand((m, 2), generator=g, device="cuda", dtype=torch.float64) * 32768
+    X[:500] = torch.floor(X[:500]) + 0.5
+    tree = sg.NodeStore(2, capacity=n)
+    tree.extend(P)
+    idx, dist = tree.knn(X, k)
+    assert int(idx.min()) >= 0 and int(idx.max()) < n
+    d = (P[idx] - X[:, None, :])
+    re = torch.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])     # same operation order as the kernel
+    assert torch.equal(re, dist)
+    ordered = (dist[:, 1:] > dist[:, :-1]) | ((dist[:, 1:] == dist[:, :-1]) & (idx[:, 1:] > idx[:, :-1]))
+    assert bool(ordered.all())
+    probe = torch.randint(0, n, (m, 64), generator=g, device="cuda")
+    dp = P[probe] - X[:, None, :]
+    dpr = torch.sqrt(dp[..., 0] * dp[..., 0] + dp[..., 1] * dp[..., 1])
+    in_row = (probe[:, :, None] == idx[:, None, :]).any(-1)
+    assert bool(((dpr >= dist[:, -1:]) | in_row).all())
+    rows = torch.randperm(m, generator=g, device="cuda")[:200].cpu().numpy()
+    oi, od = orc.knn(P.cpu().numpy(), X.cpu().numpy()[rows], k)
+    assert np.array_equal(idx.cpu().numpy()[rows], oi) and np.array_equal(dist.cpu().numpy()[rows], od)
