@@ -151,6 +151,60 @@ def accelerate_birrt(planner, stores=None):
     return s0, s1
 
 
+class _ArrayMirror:
+    """Device mirror of one append-only pose array, keyed by the identity of the array (RRdT*
+    owns one array per tree: rrdtPlanner.py:858-887).  The planner's prefix is brought up to
+    date lazily; the last mirrored row is compared first, so that an array that was rewritten
+    rather than appended to is mirrored again from scratch."""
+
+    def __init__(self, base, store):
+        self.base, self.store, self.last = base, store, None
+
+    def sync(self, n):
+        have = len(self.store)
+        if have > n or (have and not np.array_equal(self.base[have - 1], self.last)):
+            self.store.truncate(0)
+            have = 0
+        if have < n:
+            self.store.extend(self.base[have:n])
+        if n:
+            self.last = np.array(self.base[n - 1], copy=True)
+        return self.store
+
+
+def accelerate_rrdt(planner, min_nodes: int = 1024, store_factory=None):
+    """Hook for ``RRdTPlanner`` (planners/rrdtPlanner.py): its many trees each own a pose array
+    and are searched one by one with ``find_nearest_neighbour_idx(pos, tree.poses[:len(tree.nodes)])``
+    (:571, :709-711).  Arrays whose prefix has at least ``min_nodes`` rows -- in practice the
+    root tree, which absorbs the others -- get a device mirror (created on first sight, keyed by
+    array identity, synced lazily); small trees stay on numpy, where a launch would cost more
+    than the scan.  Everything else runs unchanged; results are those of ``np.argmin`` over
+    ``np.linalg.norm`` (first minimum).  Returns the dict of mirrors."""
+    if getattr(planner, "_sbp_accelerated", False):
+        return planner._sbp_mirrors
+    cc = planner.args.engine.cc
+    d = planner.args.engine.get_dimension()
+    orig_nearest = planner.find_nearest_neighbour_idx
+    mirrors = {}
+    if store_factory is None:
+        store_factory = lambda base: NodeStore(d, capacity=len(base), device=getattr(cc, "_device", 0))
+
+    def find_nearest_neighbour_idx(pos, poses):
+        base = getattr(poses, "base", None)
+        n = len(poses)
+        if base is None or n < min_nodes or base.ndim != 2 or base.shape[1] != d:
+            return orig_nearest(pos, poses)
+        m = mirrors.get(id(base))
+        if m is None or m.base is not base:
+            m = mirrors[id(base)] = _ArrayMirror(base, store_factory(base))
+        return m.sync(n).nearest(pos)
+
+    planner.find_nearest_neighbour_idx = find_nearest_neighbour_idx
+    planner._sbp_accelerated = True
+    planner._sbp_mirrors = mirrors
+    return mirrors
+
+
 def accelerate_prm(planner, store=None, chunk_rows: int = 4096):
     """Hook a reference ``PRMPlanner`` object (planners/prmPlanner.py): ``build_graph``
     (:80-101) -- for every node a Python scan of ALL nodes (``nearest_neighbours``, :28-44) and

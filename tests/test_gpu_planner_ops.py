@@ -257,3 +257,40 @@ def test_accelerate_rrt_hooks_on_a_planner_look_alike(sg):
     b._sbp_trees[0].sync()                         # the mirror is brought up to date lazily
     assert len(store) == 700 and np.array_equal(store.poses, b.poses[:700])
     assert vis_a == vis_b                          # same Stats accounting of the edge checks
+
+
+def test_rrdt_array_mirrors_follow_their_arrays(sg):
+    """planner_hooks.accelerate_rrdt with real device stores: arrays are mirrored on first
+    sight above the size threshold, grow with the planner's prefix, are mirrored again when
+    rewritten in place, and answer like np.argmin(np.linalg.norm(...)) (first minimum)."""
+    import types
+
+    rng = np.random.default_rng(8)
+    cc = sg.ImgCollisionChecker(map_png("room1"))
+    eng = types.SimpleNamespace(cc=cc, get_dimension=lambda: 2)
+
+    class P:
+        args = types.SimpleNamespace(engine=eng)
+
+        @staticmethod
+        def find_nearest_neighbour_idx(pos, poses):
+            return int(np.argmin(np.linalg.norm(poses - pos, axis=1)))
+
+    pl = P()
+    ref = P.find_nearest_neighbour_idx
+    mirrors = sg.planner_hooks.accelerate_rrdt(pl, min_nodes=64)
+    big, small = rng.random((5000, 2)) * 500, rng.random((40, 2)) * 500
+    big[10] = big[3]                                             # duplicate: first minimum wins
+    for n in (64, 700, 701, 5000):
+        for _ in range(20):
+            x = rng.random(2) * 500
+            assert pl.find_nearest_neighbour_idx(x, big[:n]) == ref(x, big[:n])
+        assert pl.find_nearest_neighbour_idx(big[10], big[:n]) == 3
+    assert len(mirrors) == 1 and len(next(iter(mirrors.values())).store) == 5000
+    assert pl.find_nearest_neighbour_idx(small[5], small[:40]) == ref(small[5], small[:40])
+    assert len(mirrors) == 1                                     # below the threshold: numpy
+    big[:2000] = rng.random((2000, 2)) * 500                     # rewritten in place
+    big[1999] += 1.0
+    for n in (2000, 1500):
+        x = rng.random(2) * 500
+        assert pl.find_nearest_neighbour_idx(x, big[:n]) == ref(x, big[:n])

@@ -277,6 +277,37 @@ def test_accelerate_birrt_hooks_keep_the_seeded_run(ref):
     assert all(s.near_visible_calls > 50 and s.nearest_calls > 50 for s in stores)
 
 
+def test_accelerate_rrdt_hook_keeps_the_seeded_run(ref):
+    """RRdT*: every tree's pose array that is searched gets a mirror on first sight (the
+    threshold is lowered to 8 rows here so that the disjoint trees are covered too); the
+    seeded run is identical."""
+    from sbp_env import engine
+    import sbp_env_b200 as sg
+
+    img = ref_shims.reference_map_path("room1.png")
+    fac = lambda args: engine.ImageEngine(args, img)
+    swap = lambda cc: sg.ImgCollisionChecker(cc.image_fname)
+    a = run("rrdt", fac, swap, "100,100", "350,350", 350)
+    made = []
+
+    class FakeTruncatable(FakeNodeStore):
+        def truncate(self, n):
+            del self.rows[n:]
+
+    def hook(env):
+        om = orc.Map(np.asarray(env.args.engine.cc._img) == 1)
+
+        def factory(base):
+            made.append(FakeTruncatable(2, om))
+            return made[-1]
+
+        sg.planner_hooks.accelerate_rrdt(env.planner, min_nodes=8, store_factory=factory)
+
+    b = run("rrdt", fac, swap, "100,100", "350,350", 350, before_run=hook)
+    _same(a, b)
+    assert len(made) >= 1 and sum(s.nearest_calls for s in made) > 100
+
+
 def test_accelerate_prm_builds_the_identical_graph(ref, monkeypatch):
     """planner_hooks.accelerate_prm: build_graph through the batched radius query and one
     visible_batch launch per block gives the reference's DiGraph -- same edges in the same
