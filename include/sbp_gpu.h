@@ -205,6 +205,17 @@ int32_t sbp_nodes_knn_edges(sbp_nodes *nodes, const int64_t *nbr_in, int64_t m, 
                             int64_t first_row, const double *X, int64_t *nbr_out, double *P,
                             double *Q, uint8_t *valid);
 
+/* sbp_nodes_knn_edges + sbp_visible2d in ONE launch for the 2-D image checker: the candidate
+ * edges of a kNN answer are resolved against the node store inside the visibility kernel, no
+ * endpoint arrays are written.
+ * replaces: the body of PRMPlanner.build_graph's double loop (prmPlanner.py:91-101) --
+ * `if m_g is v: continue` and `cc.visible(m_g.pos, v.pos)` -- for a whole block of rows.
+ * Row / column / X meaning as in sbp_nodes_knn_edges.  Writes nbr_out [m][k_out] and
+ * vis [m][k_out]: 1 = the neighbour slot is filled and ImgCollisionChecker.visible is True. */
+int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in, int64_t m,
+                                int32_t k_in, int64_t first_row, const double *X,
+                                int64_t *nbr_out, uint8_t *vis, int32_t *flags);
+
 /* Fused radius query + edge visibility in ONE launch, for the sequential planners.
  * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:
  * engine.dist(new,p) <= radius and cc.visible(new.pos, p.pos)), rewire

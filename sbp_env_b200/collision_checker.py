@@ -299,6 +299,30 @@ class ImgCollisionChecker(_GridChecker):
         self._last_flags = flags
         return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy
 
+    def knn_edges_visible(self, tree, nbr_in, first_row: int = 0, queries=None):
+        """``tree.knn_edges`` + :meth:`visible_batch` in ONE launch (prmPlanner.py:91-101):
+        the candidate edges of the kNN answer ``nbr_in`` are resolved against the node store
+        inside the visibility kernel.  Returns ``(nbr, vis)`` as CUDA tensors [m][k_out];
+        ``vis`` already excludes empty neighbour slots.  Counts m * k_out visible calls."""
+        import torch
+
+        m = self.device_map
+        m.ctx.use_torch_stream()
+        nbr_in = nbr_in.contiguous()
+        rows, k_in = nbr_in.shape
+        k_out = k_in if queries is not None else k_in - 1
+        dev = nbr_in.device
+        nbr = torch.empty((rows, k_out), dtype=torch.int64, device=dev)
+        vis = torch.empty((rows, k_out), dtype=torch.uint8, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        X = as_device_f64(queries, 2) if queries is not None else None
+        self.stats.visible_cnt += rows * k_out
+        check(_lib.load().sbp_knn_edges_visible2d(m.handle, tree._h, ptr(nbr_in), rows, k_in,
+                                                  int(first_row), ptr(X), ptr(nbr), ptr(vis),
+                                                  ptr(flags)), "sbp_knn_edges_visible2d")
+        self._last_flags = flags
+        return nbr, vis.view(torch.bool)
+
     def check_device_flags(self, what="batch"):
         """Synchronise and raise what CPython would have raised for the last device-side
         batch (NaN in ``feasible`` -> ValueError, inf -> OverflowError)."""

@@ -154,9 +154,54 @@ __device__ __forceinline__ bool px_free(const uint32_t *words, const MapView &mv
 // ROWS: `mv` is the row-major copy of the map (sbp_map::rows; shared-memory resident maps:
 // 3 integer operations per pixel index instead of ~12 for the tiled layout, which only pays off
 // through its sector locality when the map lives in L2 / HBM).
-template <bool SMEM, bool COUNT, bool ROWS>
+// Where the edges come from: two endpoint arrays, or the rows of a kNN answer resolved against
+// the node store on the fly (fused edge gather: no P / Q arrays are materialised).
+struct EdgeArrays {
+    const double2 *P, *Q;
+    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q) const {
+        p = P[e]; q = Q[e];
+        return true;
+    }
+};
+
+// Candidate edge e = (row i, column j) of a kNN answer nbr_in [m][k_in] (prmPlanner.py:91-101):
+// the row's own entry is dropped -- the column equal to the row index if present, else the last
+// column -- and the edge is visible(m_g.pos, v.pos) = (neighbour pose -> row pose).  X != NULL:
+// row i is the external query X[i] and no column is dropped.  Writes the neighbour index.
+struct EdgeKnnRows {
+    const double *soa;
+    int64_t capacity, n_nodes;
+    const int64_t *nbr_in;
+    int k_in, k_out;
+    int64_t first_row;
+    const double2 *X;
+    int64_t *nbr_out;
+    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q) const {
+        const int64_t i = e / k_out;
+        const int j = (int)(e - i * k_out);
+        const int64_t *row = nbr_in + i * k_in;
+        int col = j;
+        if (X) {
+            q = X[i];
+        } else {
+            const int64_t self = first_row + i;
+            int drop = k_in - 1;
+            for (int c = 0; c < k_in; ++c)
+                if (row[c] == self) { drop = c; break; }
+            col = j < drop ? j : j + 1;
+            q = make_double2(soa[self], soa[capacity + self]);
+        }
+        const int64_t nb = row[col];
+        nbr_out[e] = nb;
+        const bool ok = nb >= 0 && nb < n_nodes;
+        p = ok ? make_double2(soa[nb], soa[capacity + nb]) : q;
+        return ok;
+    }
+};
+
+template <bool SMEM, bool COUNT, bool ROWS, class Edges = EdgeArrays>
 __global__ void __launch_bounds__(1024)
-k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *__restrict__ Q,
+k_visible2d_adaptive(MapView mv, Edges edges,
                      int64_t n, uint8_t *__restrict__ out, int32_t *__restrict__ flags,
                      unsigned long long *__restrict__ px_tested, int COOP_BELOW) {
     extern __shared__ __align__(16) uint32_t smap[];
@@ -173,12 +218,14 @@ k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *_
 
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
-    if (e < n) { p = P[e]; q = Q[e]; }
+    bool have = false;                                      // the edge exists (neighbour slot filled)
+    if (e < n) have = edges.load(e, p, q);
     for (; e < n_round; e += stride) {
         const bool valid = e < n;
+        const bool exists = have;
         const double2 cp = p, cq = q;
         const int64_t en = e + stride;                      // prefetch the next batch
-        if (en < n) { p = P[en]; q = Q[en]; }
+        if (en < n) have = edges.load(en, p, q);
 
         Edge2D ed = make_edge(cp.x, cp.y, cq.x, cq.y, mv.W, mv.H);
         if (valid) myflag |= ed.flag;
@@ -262,7 +309,7 @@ k_visible2d_adaptive(MapView mv, const double2 *__restrict__ P, const double2 *_
             }
             if (lane == src) result = !hit;
         }
-        if (valid) out[e] = result ? 1 : 0;
+        if (valid) out[e] = (result && exists) ? 1 : 0;
     }
     if (myflag && flags) atomicOr(flags, myflag);
     if (COUNT) {
@@ -500,7 +547,7 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         int64_t need = (n + c.threads - 1) / c.threads;                                            \
         if (need < c.grid) c.grid = (int)need;                                                     \
         k_visible2d_adaptive<SM, CT, SM><<<c.grid, c.threads, c.smem, ctx->stream>>>(              \
-            mview, p2, q2, n, out, flags, px, coop);                                               \
+            mview, EdgeArrays{p2, q2}, n, out, flags, px, coop);                                   \
     } while (0)
         if (smem) { if (px) SBP_LAUNCH_ADP(true, true); else SBP_LAUNCH_ADP(true, false); }
         else      { if (px) SBP_LAUNCH_ADP(false, true); else SBP_LAUNCH_ADP(false, false); }
@@ -516,6 +563,56 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         case 32: return launch_visible<32>(map, P, Q, n, out, flags, px, smem);
         default: sbp_set_error("visible_group must be 0, 4, 8, 16 or 32"); return SBP_ERR_ARG;
     }
+}
+
+// Fused form of sbp_nodes_knn_edges + sbp_visible2d for the 2-D checker: the candidate edges of
+// a kNN answer are resolved against the node store inside the visibility kernel.
+// nbr_out [m][k_out] and vis [m][k_out] (1 = the neighbour slot is filled and the edge is free).
+extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in,
+                                           int64_t m, int32_t k_in, int64_t first_row, const double *X,
+                                           int64_t *nbr_out, uint8_t *vis, int32_t *flags) {
+    SBP_NVTX("sbp_knn_edges_visible2d");
+    SBP_REQUIRE(map && nodes && (m == 0 || (nbr_in && nbr_out && vis)), "sbp_knn_edges_visible2d: NULL argument");
+    SBP_REQUIRE(nodes->d == 2, "sbp_knn_edges_visible2d: the 2-D checker needs a 2-D node store");
+    SBP_REQUIRE(map->ctx == nodes->ctx, "sbp_knn_edges_visible2d: map and node store live in different contexts");
+    const int k_out = X ? k_in : k_in - 1;
+    SBP_REQUIRE(m >= 0 && k_out >= 1, "sbp_knn_edges_visible2d: bad sizes");
+    SBP_REQUIRE(X || (first_row >= 0 && first_row + m <= nodes->n), "sbp_knn_edges_visible2d: row range");
+    if (m == 0) return SBP_OK;
+    sbp_ctx *ctx = map->ctx;
+    SBP_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = m * k_out;
+    bool smem = !g_force_global && map->smem_resident &&
+                n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
+    if (smem) {
+        int32_t rc = sbp_map_ensure_rows(map);
+        if (rc) return rc;
+        smem = map->rows_smem_resident;
+    }
+    const MapView mview = smem ? map->rows : map->view;
+    const size_t sbytes = smem ? (size_t)map->rows.n_words * 4 : 0;
+    const int threads = (smem && sbytes > 110 * 1024) ? 1024 : 512;
+    const int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
+    EdgeKnnRows src{nodes->d_soa, nodes->capacity, nodes->n, nbr_in, k_in, k_out, first_row,
+                    (const double2 *)X, nbr_out};
+#define SBP_LAUNCH_FUSED(SM)                                                                       \
+    do {                                                                                           \
+        int32_t rc = set_smem(k_visible2d_adaptive<SM, false, SM, EdgeKnnRows>, sbytes);           \
+        if (rc) return rc;                                                                         \
+        int per_sm = 0;                                                                            \
+        SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                    \
+            &per_sm, k_visible2d_adaptive<SM, false, SM, EdgeKnnRows>, threads, sbytes));          \
+        int grid = ctx->sm_count * (per_sm < 1 ? 1 : per_sm);                                      \
+        int64_t need = (n + threads - 1) / threads;                                                \
+        if (need < grid) grid = (int)need;                                                         \
+        k_visible2d_adaptive<SM, false, SM, EdgeKnnRows><<<grid, threads, sbytes, ctx->stream>>>(  \
+            mview, src, n, vis, flags, nullptr, coop);                                             \
+    } while (0)
+    if (smem) SBP_LAUNCH_FUSED(true); else SBP_LAUNCH_FUSED(false);
+#undef SBP_LAUNCH_FUSED
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
 }
 
 extern "C" int32_t sbp_first_blocked2d(sbp_map *map, const double *P, const double *Q, int64_t n,

@@ -54,30 +54,36 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
         ``dist`` fp64 [m][k] (only for ``queries``; stored rows include the self column).
     """
     tree.ctx.use_torch_stream()
+    # the 2-D image checker resolves the kNN rows inside its visibility kernel (one launch)
+    fused = (hasattr(cc, "knn_edges_visible") and hasattr(tree, "_h") and tree.dim == 2
+             and not cc._mocked("visible"))
     if queries is not None:
         X = queries
         count = X.shape[0]
         idx, dist = tree.knn(X, k, return_dist=return_dist)
-        if mark:
-            mark("knn")
-        nbr, P, Q, valid = tree.knn_edges(idx, queries=X)
+        first = 0
     else:
         n = len(tree)
         first, count = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
         X = tree.rows_device(first, count)
         idx, dist = tree.knn(X, k + 1, return_dist=False)
-        if mark:
-            mark("knn")
-        nbr, P, Q, valid = tree.knn_edges(idx, first_row=first)
         dist = None
     if mark:
-        mark("edges")
-    vis = cc.visible_batch(P, Q).reshape(count, k)
-    if _is_torch_tensor(valid):
-        import torch
+        mark("knn")
+    if fused:
+        if mark:
+            mark("edges")                            # no separate edge-gather launch
+        nbr, vis = cc.knn_edges_visible(tree, idx, first_row=first, queries=queries)
+    else:
+        nbr, P, Q, valid = tree.knn_edges(idx, first_row=first, queries=queries)
+        if mark:
+            mark("edges")
+        vis = cc.visible_batch(P, Q).reshape(count, k)
+        if _is_torch_tensor(valid):
+            import torch
 
-        valid = valid.view(torch.bool)           # 0 / 1 bytes written by k_knn_edges
-    vis = vis & valid.reshape(count, k)
+            valid = valid.view(torch.bool)           # 0 / 1 bytes written by k_knn_edges
+        vis = vis & valid.reshape(count, k)
     if mark:
         mark("visible")
     if return_dist:

@@ -136,6 +136,48 @@ def test_device_tensors_and_prm_connect(sg):
     assert len(src) == int(vis.sum())
 
 
+@pytest.mark.parametrize("map_name,n_nodes,k", [("intel_lab", 6000, 10), ("maze1", 5, 9), ("4d", 3000, 4)])
+def test_fused_knn_edges_visible_equals_the_two_launch_form(sg, map_name, n_nodes, k):
+    """sbp_knn_edges_visible2d == sbp_nodes_knn_edges + sbp_visible2d (+ `& valid`): stored rows,
+    a row slice, external queries, empty neighbour slots (k > n) and the visible counter."""
+    import torch
+
+    free = load_map(map_name)
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png(map_name))
+    rng = np.random.default_rng(3)
+    pts = rng.random((n_nodes, 2)) * [W, H]
+    if n_nodes > 100:
+        pts[77] = pts[76] = pts[75]                              # duplicates ahead of the row node
+    t = sg.NodeStore(2)
+    t.extend(pts)
+    Xq = torch.from_numpy(rng.random((257, 2)) * [W, H]).cuda()
+    for first, count, queries in [(0, n_nodes, None), (n_nodes // 3, n_nodes // 2, None), (0, 257, Xq)]:
+        X = queries if queries is not None else t.rows_device(first, count)
+        idx, _ = t.knn(X, k if queries is not None else k + 1)
+        nbr_a, P, Q, valid = t.knn_edges(idx, first_row=first, queries=queries)
+        vis_a = cc.visible_batch(P, Q).reshape(count, k) & valid.view(torch.bool).reshape(count, k)
+        before = cc.stats.visible_cnt
+        nbr_b, vis_b = cc.knn_edges_visible(t, idx, first_row=first, queries=queries)
+        assert cc.stats.visible_cnt - before == count * k
+        assert torch.equal(nbr_a, nbr_b)
+        assert torch.equal(vis_a, vis_b)
+        if n_nodes <= k:
+            assert int((nbr_b < 0).sum()) > 0 and not bool(vis_b[nbr_b < 0].any())
+    # forced global-memory map path gives the same answer
+    from sbp_env_b200 import _lib
+
+    lib = _lib.load()
+    lib.sbp_tune(b"force_global", 1)
+    try:
+        idx, _ = t.knn(t.rows_device(0, n_nodes), k + 1)
+        nbr_c, vis_c = cc.knn_edges_visible(t, idx)
+    finally:
+        lib.sbp_tune(b"force_global", 0)
+    nbr_d, vis_d = cc.knn_edges_visible(t, idx)
+    assert torch.equal(nbr_c, nbr_d) and torch.equal(vis_c, vis_d)
+
+
 def test_empty_store_and_truncate(sg):
     t = sg.NodeStore(2)
     idx, dist = t.knn(np.zeros((3, 2)), 2)
