@@ -253,8 +253,8 @@ template <int D, int NW, int FQ>
 __global__ void __launch_bounds__(NW * 32)
 k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
              int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
-             const double *__restrict__ seed2, int C, int32_t *__restrict__ cand,
-             int32_t *__restrict__ ccount) {
+             const double *__restrict__ seed2, const uint8_t *__restrict__ done, int C,
+             int32_t *__restrict__ cand, int32_t *__restrict__ ccount) {
     constexpr int TPB = NW * 32;
     const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
     const int s = blockIdx.y;
@@ -268,7 +268,7 @@ k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int6
 #pragma unroll
     for (int r = 0; r < FQ; ++r) {
         const int64_t q = qb + (int64_t)r * TPB;
-        const bool live = q < m;
+        const bool live = q < m && !(done && done[q]);               // done: answered by k_knn_cells
         // a bound so loose that more nodes are expected inside it than the lists hold (C S groups)
         const bool usable = filter_query_setup<D>(info, X + (live ? q : 0) * D, live,
                                                   live ? seed2[q] : -1.0, nq2[r], thr[r], (double)n,
@@ -306,10 +306,12 @@ __global__ void __launch_bounds__(64)
 k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
              const double *__restrict__ X, int64_t m, const double *__restrict__ seed2, int S,
              int C, const int32_t *__restrict__ cand, const int32_t *__restrict__ ccount, int k,
-             int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo) {
+             int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo,
+             const uint8_t *__restrict__ done) {
     const unsigned FULL = 0xffffffffu;
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = q < m;
+    bool live = q < m && !(done && done[q]);                     // done: row already written
+    if (!__any_sync(FULL, live)) return;
     if (live) {
         bool over = false;
         for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
@@ -846,12 +848,199 @@ k_knn_seed(const double *__restrict__ soa, int64_t capacity, const double *__res
     if (lane == 0) seed2[q] = out;
 }
 
+// ------------------------------------------- K4c: exact kNN on the cell grid ---
+// One warp per query.  Phase 1 is the seed above with (d, index) pairs: the K best nodes of a
+// block of cells holding >= K nodes, d_K = their K-th distance.  Every node that can enter the
+// answer has sqrt_rn(d^2) <= d_K, hence |x - q_x|, |y - q_y| <= d_K (1 + 2^-52): it lies in
+// the rectangle R of cells [cell_of(q - r), cell_of(q + r)] with r = d_K (1 + 1e-9) (cell_of
+// is monotone, so the argument survives its rounding and the clamping at the grid border; for
+// D > 2 the grid bounds x and y only, which keeps R a superset).  Phase 2 merges the nodes of R
+// (skipped when R lies inside the block) -- if R holds at most `limit` nodes the row is
+// written here and done[q] = 1, otherwise done[q] = 0 and the query keeps its seed for the
+// brute-force filter.  The order is (sqrt_rn(d^2), index) decided explicitly, so the cells may
+// be visited in any order; bound2 = ru(d_K^2) (1 + 1e-9) also admits the d^2 just above
+// d_K^2 whose root still rounds to d_K (an index tie the lower index must win).
+
+// rows [ya, yb] x cells [xa, xb] of the grid, 32 nodes at a time: f(e, nv) with e the position
+// in `ids` of this lane's node (-1: none) and nv the nodes in the chunk; warp-uniform calls
+template <class F>
+__device__ __forceinline__ void cells_rect_chunks(const int32_t *__restrict__ start, int G, int xa,
+                                                  int xb, int ya, int yb, int lane, F f) {
+    const unsigned FULL = 0xffffffffu;
+    for (int rb = ya; rb <= yb; rb += 32) {
+        int32_t e0 = 0, len = 0;
+        if (rb + lane <= yb) {
+            e0 = start[(int64_t)(rb + lane) * G + xa];
+            len = start[(int64_t)(rb + lane) * G + xb + 1] - e0;
+        }
+        int32_t inc = len;                                        // inclusive prefix over the rows
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += u;
+        }
+        const int32_t pc = __shfl_sync(FULL, inc, 31);            // nodes in this pass
+        for (int32_t f0 = 0; f0 < pc; f0 += 32) {
+            // flat node f0 + lane lives in the first row whose inclusive prefix exceeds it
+            const int32_t fl = f0 + lane;
+            int row = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const int32_t v = __shfl_sync(FULL, inc, row + step - 1);
+                if (v <= fl) row += step;
+            }
+            const int32_t rinc = __shfl_sync(FULL, inc, row), rlen = __shfl_sync(FULL, len, row);
+            const int32_t re0 = __shfl_sync(FULL, e0, row);
+            f(fl < pc ? re0 + (fl - (rinc - rlen)) : -1, pc - f0 < 32 ? pc - f0 : 32);
+        }
+    }
+}
+
+// the K best (d, index) of a warp: lanes 0..nb-1 hold them in ascending order, the other lanes
+// (inf, INT_MAX).  merge() inserts the lanes' candidates flagged `ok` (finite d, distinct
+// indices not yet in the list) by rank counting: survivors are compared over shuffles, the
+// sorted list is binary-searched.
+struct WarpBest {
+    double d;
+    int32_t i;
+    int nb;
+    __device__ __forceinline__ void init() { d = INFINITY; i = 0x7fffffff; nb = 0; }
+    __device__ __forceinline__ void merge(bool ok, double vd, int32_t vi, int K, int lane,
+                                          double *sd, int32_t *si) {
+        const unsigned FULL = 0xffffffffu;
+        const unsigned mask = __ballot_sync(FULL, ok);
+        if (!mask) return;
+        int before_b = 0, before_v = 0;                           // survivors ranking before me
+        for (unsigned mm = mask; mm; mm &= mm - 1) {
+            const int src = __ffs(mm) - 1;
+            const double cd = __shfl_sync(FULL, vd, src);
+            const int32_t ci = __shfl_sync(FULL, vi, src);
+            before_b += (cd < d || (cd == d && ci < i)) ? 1 : 0;
+            before_v += (cd < vd || (cd == vd && ci < vi)) ? 1 : 0;
+        }
+        int pos = 0;                                              // list entries ranking before me
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const double bd = __shfl_sync(FULL, d, pos + step - 1);
+            const int32_t bi = __shfl_sync(FULL, i, pos + step - 1);
+            if (bd < vd || (bd == vd && bi < vi)) pos += step;
+        }
+        {   // the five steps count up to 31 entries: a full list of 32 needs its last one tested too
+            const double bd = __shfl_sync(FULL, d, 31);
+            const int32_t bi = __shfl_sync(FULL, i, 31);
+            if (pos == 31 && (bd < vd || (bd == vd && bi < vi))) pos = 32;
+        }
+        const int rank_b = lane + before_b, rank_v = pos + before_v;
+        sd[lane] = INFINITY;
+        si[lane] = 0x7fffffff;
+        __syncwarp(FULL);
+        if (lane < nb && rank_b < 32) { sd[rank_b] = d; si[rank_b] = i; }
+        if (ok && rank_v < 32) { sd[rank_v] = vd; si[rank_v] = vi; }
+        __syncwarp(FULL);
+        d = lane < K ? sd[lane] : INFINITY;
+        i = lane < K ? si[lane] : 0x7fffffff;
+        __syncwarp(FULL);
+        nb += __popc(mask);
+        nb = nb < K ? nb : K;
+    }
+};
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_knn_cells(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
+            const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
+            const int32_t *__restrict__ ids, int K, int limit, double *__restrict__ seed2,
+            uint8_t *__restrict__ done, int64_t *__restrict__ idx, double *__restrict__ dist) {
+    __shared__ double sd[8][32];
+    __shared__ int32_t si[8][32];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= m) return;                                           // uniform over the warp
+    double qv[D];
+    bool finite = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { qv[j] = X[q * D + j]; finite &= qv[j] == qv[j]; }
+    const double mnx = b4[0], mxx = b4[1], mny = b4[2], mxy = b4[3];
+    double out = INFINITY;
+    bool handled = false;
+    WarpBest best;
+    best.init();
+    if (finite && mnx <= mxx && mny <= mxy) {
+        const int cx = cell_of(qv[0], mnx, mxx, G), cy = cell_of(qv[1], mny, mxy, G);
+        int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        int32_t cnt = 0;
+        for (int r = 1;; r = r < 8 ? r + 1 : 2 * r) {
+            x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
+            y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
+            int32_t c = 0;
+            for (int row = y0 + lane; row <= y1; row += 32)
+                c += start[(int64_t)row * G + x1 + 1] - start[(int64_t)row * G + x0];
+            cnt = __reduce_add_sync(FULL, c);
+            if (cnt >= K || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
+        }
+        if (cnt >= K) {
+            double bound2 = INFINITY;
+            auto visit = [&](int32_t e, int) {
+                bool ok = false;
+                double vd = INFINITY;
+                int32_t t = 0x7fffffff;
+                if (e >= 0) {
+                    t = ids[e];
+                    double pv[D];
+#pragma unroll
+                    for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
+                    const double d2 = dist2_full<D>(pv, qv);
+                    ok = d2 <= bound2 && d2 < INFINITY;           // NaN / overflow: not a candidate here
+                    if (ok) vd = __dsqrt_rn(d2);
+                }
+                best.merge(ok, vd, t, K, lane, sd[w], si[w]);
+                if (best.nb == K) {
+                    const double kth = __shfl_sync(FULL, best.d, K - 1);
+                    const double b2 = __dmul_ru(kth, kth) * (1.0 + 1e-9) + 1e-300;
+                    bound2 = b2 < bound2 ? b2 : bound2;
+                }
+            };
+            cells_rect_chunks(start, G, x0, x1, y0, y1, lane, visit);
+            if (best.nb == K && bound2 < INFINITY) {
+                out = bound2;
+                const double r = sqrt(bound2) * (1.0 + 1e-9) + 1e-300;
+                const int xa = cell_of(__dsub_rd(qv[0], r), mnx, mxx, G), xb = cell_of(__dadd_ru(qv[0], r), mnx, mxx, G);
+                const int ya = cell_of(__dsub_rd(qv[1], r), mny, mxy, G), yb = cell_of(__dadd_ru(qv[1], r), mny, mxy, G);
+                if (xa >= x0 && xb <= x1 && ya >= y0 && yb <= y1) {
+                    handled = true;                               // the block already covers R
+                } else {
+                    int32_t c = 0;
+                    for (int row = ya + lane; row <= yb; row += 32)
+                        c += start[(int64_t)row * G + xb + 1] - start[(int64_t)row * G + xa];
+                    c = __reduce_add_sync(FULL, c);
+                    if (c <= limit) {
+                        best.init();
+                        cells_rect_chunks(start, G, xa, xb, ya, yb, lane, visit);
+                        handled = best.nb == K;
+                    }
+                }
+            }
+        }
+    }
+    if (handled && lane < K) {
+        idx[q * K + lane] = best.i;
+        if (dist) dist[q * K + lane] = best.d;
+    }
+    if (lane == 0) {
+        seed2[q] = out;
+        done[q] = handled ? 1 : 0;
+    }
+}
+
 int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
 int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
 int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
 int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
 int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
 int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filter kernel
+int g_knn_cells = 1;          // tuning knob: exact answers from the cell grid where its rectangle is small
+int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -903,6 +1092,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         return SBP_OK;
     }
     const double *seed = nullptr, *seed_bounds = nullptr;
+    void *donebuf = nullptr;                 // per query: 1 = row already written by k_knn_cells
     if (D >= 2 && g_knn_seed && n >= 2048) {
         int G = (int)ceil(sqrt(2.0 * (double)n));
         if (G > 2048) G = 2048;
@@ -931,8 +1121,16 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
         // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
-        k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
+        if (g_knn_filter && g_knn_cells) {
+            rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
+            if (rc) return rc;
+            k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                s->d_soa, s->capacity, X, m, b4, G, start, ids, k, g_knn_cells_limit, (double *)seedbuf,
+                (uint8_t *)donebuf, idx, dist);
+        } else {
+            k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
+        }
         ctx->launches += 7;
         SBP_CUDA(cudaGetLastError());
         seed = (const double *)seedbuf;
@@ -985,7 +1183,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         dim3 fgrid((unsigned)qblocks, (unsigned)FS);
 #define SBP_FILTER_LAUNCH(NW_, FQ_)                                                         \
     k_knn_filter<D, NW_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                          \
-        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, C, (int32_t *)cbuf, ccount)
+        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, (const uint8_t *)donebuf, C,      \
+        (int32_t *)cbuf, ccount)
         {
         KernelTimer timer(ctx);
         switch (g_knn_filter_variant) {
@@ -1001,7 +1200,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         ctx->launches++;
         k_knn_refine<D, K><<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(
             s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
-            dist, flags);
+            dist, flags, (const uint8_t *)donebuf);
         ctx->launches += 2;
         SBP_CUDA(cudaGetLastError());
         redo = flags;

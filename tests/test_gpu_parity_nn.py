@@ -361,15 +361,71 @@ def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
     try:
         for kk in (k, 1, 20, 32):
             ei, ed = orc.knn(poses, X, kk)
-            for filt, chunks in ((1, 0), (1, 1), (1, 7), (0, 0)):
+            for filt, chunks, cells in ((1, 0, 1), (1, 0, 0), (1, 1, 0), (1, 7, 0), (0, 0, 0)):
                 lib.sbp_tune(b"knn_filter", filt)
                 lib.sbp_tune(b"knn_filter_chunks", chunks)
+                lib.sbp_tune(b"knn_cells", cells)
                 idx, dist = t.knn(X, kk)
-                assert np.array_equal(idx, ei), (layout, n, kk, filt, chunks)
-                assert np.array_equal(dist, ed, equal_nan=True), (layout, n, kk, filt, chunks)
+                assert np.array_equal(idx, ei), (layout, n, kk, filt, chunks, cells)
+                assert np.array_equal(dist, ed, equal_nan=True), (layout, n, kk, filt, chunks, cells)
     finally:
         lib.sbp_tune(b"knn_filter", 1)
         lib.sbp_tune(b"knn_filter_chunks", 0)
+        lib.sbp_tune(b"knn_cells", 1)
+
+
+@pytest.mark.parametrize("layout", ["uniform", "clustered", "duplicates", "line", "outliers", "lattice", "nan_inf"])
+@pytest.mark.parametrize("d", [2, 3])
+def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
+    """k_knn_cells answers a query exactly from the rectangle of grid cells that covers its
+    K-th seed distance; queries whose rectangle holds more than the limit stay with the
+    brute-force filter.  Every limit (0: only rectangles inside the seed block, small: a mix of
+    both paths in one batch, huge: everything from the grid) gives the oracle's rows -- also
+    with exact distance ties (lattice: many equidistant nodes, the lower index must win)."""
+    from sbp_env_b200 import _lib
+
+    rng = np.random.default_rng(len(layout) + d)
+    n, m = 30000, 2100
+    if layout == "uniform":
+        poses = rng.random((n, d)) * 600
+    elif layout == "clustered":
+        c = rng.random((20, d)) * 600
+        poses = c[rng.integers(0, 20, n)] + rng.standard_normal((n, d)) * 0.5
+    elif layout == "duplicates":
+        poses = np.floor(rng.random((n, d)) * 12) * 50.0
+    elif layout == "line":
+        poses = rng.random((n, d)) * 600
+        poses[:, 1] = 123.25                                       # zero extent in y
+    elif layout == "lattice":
+        poses = np.floor(rng.random((n, d)) * 200) * 3.0          # integer lattice with repeats
+    elif layout == "outliers":
+        poses = rng.random((n, d)) * 10
+        poses[:3, :2] = [[1e9, 1e9], [-1e9, 3.0], [5.0, 1e12]]
+    else:
+        poses = rng.random((n, d)) * 600
+        poses[5, 0] = np.nan
+        poses[77, 0] = np.inf
+        poses[n - 1, 1] = -np.inf
+    X = np.concatenate([poses[rng.integers(0, n, m // 3)],
+                        poses[rng.integers(0, n, m // 3)] + rng.standard_normal((m // 3, d)) * 0.3,
+                        rng.random((m - 2 * (m // 3), d)) * 900 - 150])
+    if layout == "nan_inf":
+        X[3] = np.nan
+        X[40, 0] = np.inf
+        X[41, 1] = np.nan
+    t = sg.NodeStore(d)
+    t.extend(poses)
+    lib = _lib.load()
+    try:
+        for kk in (11, 1, 4, 21, 32):
+            ei, ed = orc.knn(poses, X, kk)
+            for limit in (0, 48, 1024, 1 << 30):
+                lib.sbp_tune(b"knn_cells_limit", limit)
+                idx, dist = t.knn(X, kk)
+                assert np.array_equal(idx, ei), (layout, d, kk, limit)
+                assert np.array_equal(dist, ed, equal_nan=True), (layout, d, kk, limit)
+    finally:
+        lib.sbp_tune(b"knn_cells_limit", 1024)
 
 
 def test_prm_connect_graph_replay_equals_eager(sg):
@@ -557,13 +613,15 @@ def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
     try:
         for k in (11, 1, 32):
             ei, ed = orc.knn(poses, X, k)
-            for filt in (1, 0):
+            for filt, cells in ((1, 1), (1, 0), (0, 0)):
                 lib.sbp_tune(b"knn_filter", filt)
+                lib.sbp_tune(b"knn_cells", cells)
                 idx, dist = t.knn(X, k)
-                assert np.array_equal(idx, ei), (d, layout, k, filt)
-                assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt)
+                assert np.array_equal(idx, ei), (d, layout, k, filt, cells)
+                assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt, cells)
     finally:
         lib.sbp_tune(b"knn_filter", 1)
+        lib.sbp_tune(b"knn_cells", 1)
 
 
 def test_cfg2_full_size_connection_equals_oracle(sg):
