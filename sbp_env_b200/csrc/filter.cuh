@@ -75,7 +75,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t phase) {
 // then a one-warp fold (NaN coordinates are ignored by fmin / fmax).
 template <int DD>
 __global__ void __launch_bounds__(256)
-k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial) {
+k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, double *__restrict__ partial,
+                 const int32_t *__restrict__ pending = nullptr) {
+    if (pending && *pending == 0) return;          // every query already answered (k_knn_cells)
     __shared__ double sh[2 * DD][8];
     double mn[DD], mx[DD];
 #pragma unroll
@@ -105,7 +107,9 @@ k_bounds_partial(const double *__restrict__ soa, int64_t capacity, int64_t n, do
 }
 
 template <int DD>
-__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out) {
+__global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double *__restrict__ out,
+                              const int32_t *__restrict__ pending = nullptr) {
+    if (pending && *pending == 0) return;
     const int c = threadIdx.x;                     // one thread per (coordinate, min | max)
     if (c >= 2 * DD) return;
     double v = partial[c];
@@ -121,7 +125,9 @@ __global__ void k_bounds_fold(const double *__restrict__ partial, int nb, double
 template <int D>
 __global__ void k_shadow_centered(const double *__restrict__ soa, int64_t capacity, int64_t n,
                                   const double *__restrict__ bounds /*[D][2] = min, max*/,
-                                  int64_t cap32, float *__restrict__ sh, double *__restrict__ info) {
+                                  int64_t cap32, float *__restrict__ sh, double *__restrict__ info,
+                                  const int32_t *__restrict__ pending = nullptr) {
+    if (pending && *pending == 0) return;          // every query already answered (k_knn_cells)
     double c[D], M = 0.0;
 #pragma unroll
     for (int j = 0; j < D; ++j) {

@@ -65,6 +65,29 @@ struct TopK {
             bound2 = i[K - 1] < 0 ? seed2 : __dmul_ru(d[K - 1], d[K - 1]);
         }
     }
+    // The same insertion with the order (d, index) decided explicitly, for callers that do not
+    // feed indices in ascending order (k_knn_cells_t walks the nodes cell by cell).  bound2 is
+    // inflated so that it also admits a d^2 just above d_K^2 whose root still rounds to d_K.
+    __device__ __forceinline__ void insert_pair(double dd, int32_t idx) {
+        bool r_cur = i[K - 1] >= 0 && (d[K - 1] < dd || (d[K - 1] == dd && i[K - 1] < idx));
+#pragma unroll
+        for (int t = K - 1; t >= 1; --t) {
+            const bool r_prev = i[t - 1] >= 0 && (d[t - 1] < dd || (d[t - 1] == dd && i[t - 1] < idx));
+            const double nd = r_prev ? dd : d[t - 1];
+            const int32_t ni = r_prev ? idx : i[t - 1];
+            d[t] = r_cur ? d[t] : nd;
+            i[t] = r_cur ? i[t] : ni;
+            r_cur = r_prev;
+        }
+        d[0] = r_cur ? d[0] : dd;
+        i[0] = r_cur ? i[0] : idx;
+    }
+    __device__ __forceinline__ void offer_pair(double d2, int32_t idx) {
+        if (d2 <= bound2 && idx >= 0) {
+            insert_pair(__dsqrt_rn(d2), idx);
+            bound2 = i[K - 1] < 0 ? seed2 : __dmul_ru(d[K - 1], d[K - 1]) * (1.0 + 1e-9) + 1e-300;
+        }
+    }
     // insert an already square-rooted distance (merging partial lists)
     __device__ __forceinline__ void offer_sorted(double dd, int32_t idx) { insert_sorted(dd, idx); }
     // remove the head (used by the block merge)
@@ -131,8 +154,10 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
               const double *__restrict__ maxabs, int prefilter, int64_t capacity, int64_t n, int S,
               const double *__restrict__ X, int64_t m, const double *__restrict__ seed2,
               double *__restrict__ pd, int32_t *__restrict__ pi,
-              const uint8_t *__restrict__ redo) {
-    // as the fallback of the filter path: only the flagged blocks of 32 queries (TPB == 32)
+              const uint8_t *__restrict__ redo, const int32_t *__restrict__ pending = nullptr) {
+    // as the fallback of the filter path: only the flagged blocks of 32 queries (TPB == 32);
+    // pending == 0: the cell-grid kernel answered every query, nothing can be flagged
+    if (pending && *pending == 0) return;
     if (redo && !redo[blockIdx.x]) return;
     constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
     __shared__ double tile[D][TILE];  // fp64 tile, or the fp32 tile in the same storage
@@ -253,8 +278,10 @@ template <int D, int NW, int FQ>
 __global__ void __launch_bounds__(NW * 32)
 k_knn_filter(const float *__restrict__ sh, const double *__restrict__ info, int64_t cap32,
              int64_t n, int S, int64_t chunk, const double *__restrict__ X, int64_t m,
-             const double *__restrict__ seed2, const uint8_t *__restrict__ done, int C,
+             const double *__restrict__ seed2, const uint8_t *__restrict__ done,
+             const int32_t *__restrict__ pending, int C,
              int32_t *__restrict__ cand, int32_t *__restrict__ ccount) {
+    if (pending && *pending == 0) return;          // every query already answered (k_knn_cells)
     constexpr int TPB = NW * 32;
     const int64_t qb = (int64_t)blockIdx.x * (TPB * FQ) + threadIdx.x;   // query r: qb + r * TPB
     const int s = blockIdx.y;
@@ -307,7 +334,8 @@ k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
              const double *__restrict__ X, int64_t m, const double *__restrict__ seed2, int S,
              int C, const int32_t *__restrict__ cand, const int32_t *__restrict__ ccount, int k,
              int64_t *__restrict__ idx, double *__restrict__ dist, uint8_t *__restrict__ redo,
-             const uint8_t *__restrict__ done) {
+             const uint8_t *__restrict__ done, const int32_t *__restrict__ pending) {
+    if (pending && *pending == 0) return;
     const unsigned FULL = 0xffffffffu;
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = q < m && !(done && done[q]);                     // done: row already written
@@ -573,7 +601,8 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
                             int S, int K, int k, int64_t *__restrict__ idx,
                             double *__restrict__ dist, const uint8_t *__restrict__ redo,
                             const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
-                            const double *__restrict__ X) {
+                            const double *__restrict__ X, const int32_t *__restrict__ pending = nullptr) {
+    if (pending && *pending == 0) return;
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= m) return;
     if (redo && !redo[q >> 5]) return;
@@ -730,6 +759,59 @@ k_cell_scan_apply(const int32_t *__restrict__ cells, int64_t L, const int32_t *_
         if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
         run += v[j];
     }
+}
+
+// The whole scan in one launch for grids of up to SCAN_FUSED_TILES tiles: every tile sums the
+// cells of the tiles before it itself (a few hundred KB of L2 reads) instead of waiting for two
+// more launches.
+#define SCAN_FUSED_TILES 48
+__global__ void __launch_bounds__(1024)
+k_cell_scan_fused(const int32_t *__restrict__ cells, int64_t L, int32_t *__restrict__ start,
+                  int32_t *__restrict__ cursor) {
+    __shared__ int32_t ws[32];
+    __shared__ int32_t s_before;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE;
+    int32_t acc = 0;
+    for (int64_t i = (int64_t)tid * 4; i < t0; i += 4096) {      // t0 is a multiple of 4096
+        const int4 v = *reinterpret_cast<const int4 *>(cells + i);
+        acc += v.x + v.y + v.z + v.w;
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if (lane == 0) ws[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        acc = ws[lane];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_before = acc;
+    }
+    __syncthreads();
+    const int32_t before = s_before;
+    __syncthreads();
+    const int64_t i0 = t0 + (int64_t)tid * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = i0 + j < L ? cells[i0 + j] : 0;
+    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int32_t y = ws[lane], yi = y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
+        ws[lane] = yi - y;
+    }
+    __syncthreads();
+    int32_t run = before + ws[w] + inc - tsum;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < L) { start[i0 + j] = run; cursor[i0 + j] = run; }
+        run += v[j];
+    }
+    if (i0 <= L - 1 && L - 1 < i0 + 4) start[L] = run;            // total = start[L]
 }
 
 __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity, int64_t n,
@@ -950,7 +1032,8 @@ __global__ void __launch_bounds__(256)
 k_knn_cells(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
             const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
             const int32_t *__restrict__ ids, int K, int limit, double *__restrict__ seed2,
-            uint8_t *__restrict__ done, int64_t *__restrict__ idx, double *__restrict__ dist) {
+            uint8_t *__restrict__ done, int32_t *__restrict__ pending, int64_t *__restrict__ idx,
+            double *__restrict__ dist) {
     __shared__ double sd[8][32];
     __shared__ int32_t si[8][32];
     const unsigned FULL = 0xffffffffu;
@@ -1030,7 +1113,147 @@ k_knn_cells(const double *__restrict__ soa, int64_t capacity, const double *__re
     if (lane == 0) {
         seed2[q] = out;
         done[q] = handled ? 1 : 0;
+        if (!handled) atomicAdd(pending, 1);                      // the brute-force kernels have work
     }
+}
+
+// ---------------------------- K4c': the same search with one THREAD per query ---
+// Same algorithm and guarantees as k_knn_cells with a per-thread sorted list (TopK<K>,
+// explicit (d, index) order): ~10x fewer warp instructions per query, which is what bounds
+// the warp-per-query form once there are enough queries to fill the SMs with one-warp CTAs.
+// The 32 queries of a warp walk their rectangles row by row in lock-step: per row one
+// contiguous range of `ids` (two when the seed block, already merged, is cut out of R), four
+// nodes per lane and step, then the lanes insert their passing nodes round by round.
+template <int D, int K>
+__device__ __forceinline__ void cells_scan_rows(const double *__restrict__ soa, int64_t capacity,
+                                                const int32_t *__restrict__ start,
+                                                const int32_t *__restrict__ ids, int G,
+                                                const double (&qv)[D], TopK<K> &top, bool active,
+                                                int xa, int xb, int ya, int yb, int sx0, int sx1,
+                                                int sy0, int sy1, int mid, bool centre_out) {
+    const unsigned FULL = 0xffffffffu;
+    const int nrows = active ? yb - ya + 1 : 0;
+    const int maxrows = __reduce_max_sync(FULL, nrows);
+    const bool cut = sx1 >= sx0;
+    const int nseg = __any_sync(FULL, active && cut) ? 2 : 1;
+    for (int j = 0; j < maxrows; ++j) {
+        // rows nearest to the query's own row first: the list fills with near nodes, its bound
+        // tightens early and fewer of the later nodes reach the insertion (results unchanged)
+        int row = ya + j;
+        if (centre_out) {
+            const int up = mid + ((j + 1) >> 1), dn = mid - ((j + 1) >> 1);
+            const int lo_left = mid - ya, hi_left = yb - mid;      // rows below / above mid
+            const int paired = 2 * (lo_left < hi_left ? lo_left : hi_left);
+            if (j <= paired) row = (j & 1) ? up : dn;
+            else row = lo_left < hi_left ? mid + (j - lo_left) : mid - (j - hi_left);
+        }
+        const bool rowok = j < nrows;
+        const bool in_cut = cut && row >= sy0 && row <= sy1;
+        for (int seg = 0; seg < nseg; ++seg) {
+            // outside the cut rows: [xa, xb]; inside: [xa, sx0 - 1] and [sx1 + 1, xb]
+            const int c0 = seg == 0 ? xa : (sx1 + 1 > xa ? sx1 + 1 : xa);
+            const int c1 = seg == 0 ? (in_cut ? (sx0 - 1 < xb ? sx0 - 1 : xb) : xb) : xb;
+            int32_t e = 0, e1 = 0;
+            if (rowok && c1 >= c0 && (seg == 0 || in_cut)) {
+                e = start[(int64_t)row * G + c0];
+                e1 = start[(int64_t)row * G + c1 + 1];
+            }
+            while (__any_sync(FULL, e < e1)) {
+                double d2[4];
+                int32_t id[4];
+                unsigned mask = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const bool ok = e + u < e1;
+                    id[u] = ok ? ids[e + u] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double pv[D];
+#pragma unroll
+                    for (int c = 0; c < D; ++c) pv[c] = soa[(int64_t)c * capacity + id[u]];
+                    d2[u] = dist2_full<D>(pv, qv);
+                    mask |= (e + u < e1 && d2[u] <= top.bound2) ? (1u << u) : 0u;
+                }
+                e += 4;
+                while (__any_sync(FULL, mask != 0u)) {
+                    const int u = mask ? __ffs(mask) - 1 : 4;
+                    mask &= mask - 1;
+                    double dd = INFINITY;
+                    int32_t ii = -1;
+#pragma unroll
+                    for (int v = 0; v < 4; ++v) { dd = u == v ? d2[v] : dd; ii = u == v ? id[v] : ii; }
+                    top.offer_pair(dd, ii);
+                }
+            }
+        }
+    }
+}
+
+template <int D, int K>
+__global__ void __launch_bounds__(32)
+k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
+              const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
+              const int32_t *__restrict__ ids, int k, int r_init, int limit,
+              double *__restrict__ seed2, uint8_t *__restrict__ done, int32_t *__restrict__ pending,
+              int64_t *__restrict__ idx, double *__restrict__ dist) {
+    const int64_t q = (int64_t)blockIdx.x * 32 + threadIdx.x;
+    const bool live = q < m;
+    double qv[D];
+    bool finite = live;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { qv[j] = live ? X[q * D + j] : 0.0; finite &= qv[j] == qv[j]; }
+    const double mnx = b4[0], mxx = b4[1], mny = b4[2], mxy = b4[3];
+    TopK<K> top;
+    top.init(INFINITY);
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cy_q = 0;
+    bool have_block = false;
+    if (finite && mnx <= mxx && mny <= mxy) {
+        const int cx = cell_of(qv[0], mnx, mxx, G), cy = cell_of(qv[1], mny, mxy, G);
+        cy_q = cy;
+        for (int r = r_init;; r = r < 8 ? r + 1 : 2 * r) {
+            x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
+            y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
+            int32_t c = 0;
+            for (int row = y0; row <= y1; ++row)
+                c += start[(int64_t)row * G + x1 + 1] - start[(int64_t)row * G + x0];
+            have_block = c >= K;
+            if (have_block || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
+        }
+    }
+    cells_scan_rows<D, K>(soa, capacity, start, ids, G, qv, top, have_block, x0, x1, y0, y1, 0, -1, 0, -1,
+                          cy_q, true);
+    const bool full = have_block && top.i[K - 1] >= 0 && top.bound2 < INFINITY;
+    bool handled = false, pass2 = false;
+    int xa = 0, xb = -1, ya = 0, yb = -1;
+    if (full) {
+        const double r = sqrt(top.bound2) * (1.0 + 1e-9) + 1e-300;
+        xa = cell_of(__dsub_rd(qv[0], r), mnx, mxx, G); xb = cell_of(__dadd_ru(qv[0], r), mnx, mxx, G);
+        ya = cell_of(__dsub_rd(qv[1], r), mny, mxy, G); yb = cell_of(__dadd_ru(qv[1], r), mny, mxy, G);
+        if (xa >= x0 && xb <= x1 && ya >= y0 && yb <= y1) {
+            handled = true;                                       // the block already covers R
+        } else if (yb - ya < 64) {
+            int32_t c = 0;
+            for (int row = ya; row <= yb; ++row)
+                c += start[(int64_t)row * G + xb + 1] - start[(int64_t)row * G + xa];
+            pass2 = c <= limit;
+            handled = pass2;
+        }
+    }
+    // pass 2: the cells of R outside the block (the block's nodes are in the list already)
+    cells_scan_rows<D, K>(soa, capacity, start, ids, G, qv, top, pass2, xa, xb, ya, yb, x0, x1, y0, y1, 0, false);
+    if (!live) return;
+    if (handled) {
+#pragma unroll
+        for (int t = 0; t < K; ++t)
+            if (t < k) {
+                idx[q * k + t] = top.i[t];
+                if (dist) dist[q * k + t] = top.d[t];
+            }
+    }
+    seed2[q] = full ? top.bound2 : INFINITY;
+    done[q] = handled ? 1 : 0;
+    if (!handled) atomicAdd(pending, 1);                          // the brute-force kernels have work
 }
 
 int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
@@ -1039,8 +1262,10 @@ int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan
 int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
 int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
 int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filter kernel
-int g_knn_cells = 1;          // tuning knob: exact answers from the cell grid where its rectangle is small
-int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes
+int g_knn_cells = 2;          // tuning knob: exact answers from the cell grid where its rectangle is small
+                              // (0 = off, 1 = warp per query, 2 = thread per query when >= 4096 queries, 3 = always)
+int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes (thread per query: a quarter)
+int g_knn_cell_density = 100; // tuning knob: nodes per grid cell x 100
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -1093,21 +1318,25 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     }
     const double *seed = nullptr, *seed_bounds = nullptr;
     void *donebuf = nullptr;                 // per query: 1 = row already written by k_knn_cells
+    int32_t *pending_all = nullptr;          // [0]: queries k_knn_cells left to the brute-force kernels
+    const int32_t *pending = nullptr;        // ... handed to those kernels when k_knn_cells ran
     if (D >= 2 && g_knn_seed && n >= 2048) {
-        int G = (int)ceil(sqrt(2.0 * (double)n));
+        int G = (int)ceil(sqrt(100.0 / (double)(g_knn_cell_density < 1 ? 1 : g_knn_cell_density) * (double)n));
         if (G > 2048) G = 2048;
+        if (G < 1) G = 1;
         const int64_t L = (int64_t)G * G;
         void *cellbuf = nullptr, *seedbuf = nullptr;
-        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][cells L][start L+1][cursor L][ids n][tile sums 1024]
+        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][pending: 4 ints][cells L][start L+1][cursor L][ids n][tile sums 1024]
         const size_t hdr = (4 + 4 * BOUNDS_BLOCKS) * sizeof(double);
-        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
+        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(4 + 3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
         if (rc) return rc;
         rc = sbp_ctx_scratch(ctx, 6, (size_t)m * sizeof(double), &seedbuf);
         if (rc) return rc;
         double *b4 = (double *)cellbuf;
-        int32_t *cells = (int32_t *)((char *)cellbuf + hdr), *start = cells + L, *cursor = start + L + 1,
+        pending_all = (int32_t *)((char *)cellbuf + hdr);        // zeroed with the cell counts
+        int32_t *cells = pending_all + 4, *start = cells + L, *cursor = start + L + 1,
                 *ids = cursor + L, *tsums = ids + n;
-        SBP_CUDA(cudaMemsetAsync(cells, 0, (size_t)L * sizeof(int32_t), ctx->stream));
+        SBP_CUDA(cudaMemsetAsync(pending_all, 0, (size_t)(L + 4) * sizeof(int32_t), ctx->stream));
         double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
         k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
         int hb = (int)((n + 255) / 256);
@@ -1115,18 +1344,34 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,
                                                  cells);
         const int nt = (int)((L + SCAN_TILE - 1) / SCAN_TILE);            // <= 1024 tiles (G <= 2048)
-        k_cell_tile_sums<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums);
-        k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
-        k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
+        if (nt <= SCAN_FUSED_TILES) {
+            k_cell_scan_fused<<<nt, 1024, 0, ctx->stream>>>(cells, L, start, cursor);
+            ctx->launches -= 2;
+        } else {
+            k_cell_tile_sums<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums);
+            k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
+            k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
+        }
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
         // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
         if (g_knn_filter && g_knn_cells) {
             rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
             if (rc) return rc;
-            k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-                s->d_soa, s->capacity, X, m, b4, G, start, ids, k, g_knn_cells_limit, (double *)seedbuf,
-                (uint8_t *)donebuf, idx, dist);
+            if (g_knn_cells >= 3 || (g_knn_cells == 2 && m >= 4096)) {
+                // first ring radius whose block is expected to hold K nodes
+                const double per_cell = (double)n / ((double)G * (double)G);
+                int r_init = (int)ceil((sqrt((double)K / per_cell) - 1.0) / 2.0);
+                r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
+                k_knn_cells_t<D, K><<<(unsigned)((m + 31) / 32), 32, 0, ctx->stream>>>(
+                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, g_knn_cells_limit / 4,
+                    (double *)seedbuf, (uint8_t *)donebuf, pending_all, idx, dist);
+            } else {
+                k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, g_knn_cells_limit, (double *)seedbuf,
+                    (uint8_t *)donebuf, pending_all, idx, dist);
+            }
+            pending = pending_all;
         } else {
             k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
                 s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
@@ -1168,8 +1413,9 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         float *shadow = (float *)((char *)shbuf + shdr);
         if (D > 2) {               // the cell grid only bounds x and y: all D coordinates here
             double *bnd = (double *)((char *)shbuf + 128), *partial = (double *)((char *)shbuf + 256);
-            k_bounds_partial<D><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
-            k_bounds_fold<D><<<1, 32, 0, ctx->stream>>>(partial, BOUNDS_BLOCKS, bnd);
+            k_bounds_partial<D><<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial,
+                                                                        pending);
+            k_bounds_fold<D><<<1, 32, 0, ctx->stream>>>(partial, BOUNDS_BLOCKS, bnd, pending);
             ctx->launches += 2;
             seed_bounds = bnd;
         }
@@ -1179,12 +1425,12 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         int sb = (int)((cap32 + 255) / 256);
         if (sb > ctx->sm_count * 8) sb = ctx->sm_count * 8;
         k_shadow_centered<D><<<sb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, seed_bounds, cap32,
-                                                          shadow, info);
+                                                          shadow, info, pending);
         dim3 fgrid((unsigned)qblocks, (unsigned)FS);
 #define SBP_FILTER_LAUNCH(NW_, FQ_)                                                         \
     k_knn_filter<D, NW_, FQ_><<<fgrid, NW_ * 32, 0, ctx->stream>>>(                          \
-        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, (const uint8_t *)donebuf, C,      \
-        (int32_t *)cbuf, ccount)
+        shadow, info, cap32, n, (int)FS, chunk, X, m, seed, (const uint8_t *)donebuf, pending, \
+        C, (int32_t *)cbuf, ccount)
         {
         KernelTimer timer(ctx);
         switch (g_knn_filter_variant) {
@@ -1200,7 +1446,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         ctx->launches++;
         k_knn_refine<D, K><<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(
             s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
-            dist, flags, (const uint8_t *)donebuf);
+            dist, flags, (const uint8_t *)donebuf, pending);
         ctx->launches += 2;
         SBP_CUDA(cudaGetLastError());
         redo = flags;
@@ -1211,7 +1457,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
                                                               g_knn_prefilter, s->capacity, n, S, X,
                                                               m, seed, (double *)pd, (int32_t *)pi,
-                                                              redo);
+                                                              redo, redo ? pending : nullptr);
     } else {
         dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
         k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
@@ -1222,7 +1468,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     k_knn_merge<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
-        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist, redo, s->d_soa, s->capacity, n, D, X);
+        (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist, redo, s->d_soa, s->capacity, n, D, X,
+        redo ? pending : nullptr);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;

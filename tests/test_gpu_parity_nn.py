@@ -361,7 +361,7 @@ def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
     try:
         for kk in (k, 1, 20, 32):
             ei, ed = orc.knn(poses, X, kk)
-            for filt, chunks, cells in ((1, 0, 1), (1, 0, 0), (1, 1, 0), (1, 7, 0), (0, 0, 0)):
+            for filt, chunks, cells in ((1, 0, 1), (1, 0, 3), (1, 0, 0), (1, 1, 0), (1, 7, 0), (0, 0, 0)):
                 lib.sbp_tune(b"knn_filter", filt)
                 lib.sbp_tune(b"knn_filter_chunks", chunks)
                 lib.sbp_tune(b"knn_cells", cells)
@@ -371,7 +371,7 @@ def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
     finally:
         lib.sbp_tune(b"knn_filter", 1)
         lib.sbp_tune(b"knn_filter_chunks", 0)
-        lib.sbp_tune(b"knn_cells", 1)
+        lib.sbp_tune(b"knn_cells", 2)
 
 
 @pytest.mark.parametrize("layout", ["uniform", "clustered", "duplicates", "line", "outliers", "lattice", "nan_inf"])
@@ -419,13 +419,19 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
     try:
         for kk in (11, 1, 4, 21, 32):
             ei, ed = orc.knn(poses, X, kk)
-            for limit in (0, 48, 1024, 1 << 30):
+            for mode, limit, density in ((1, 0, 50), (1, 48, 50), (1, 1024, 50), (1, 1 << 30, 50),
+                                         (3, 0, 50), (3, 200, 50), (3, 1024, 300), (3, 1 << 30, 50),
+                                         (3, 1024, 5)):
+                lib.sbp_tune(b"knn_cells", mode)                  # 1 = warp, 3 = thread per query
                 lib.sbp_tune(b"knn_cells_limit", limit)
+                lib.sbp_tune(b"knn_cell_density", density)
                 idx, dist = t.knn(X, kk)
-                assert np.array_equal(idx, ei), (layout, d, kk, limit)
-                assert np.array_equal(dist, ed, equal_nan=True), (layout, d, kk, limit)
+                assert np.array_equal(idx, ei), (layout, d, kk, mode, limit, density)
+                assert np.array_equal(dist, ed, equal_nan=True), (layout, d, kk, mode, limit, density)
     finally:
+        lib.sbp_tune(b"knn_cells", 2)
         lib.sbp_tune(b"knn_cells_limit", 1024)
+        lib.sbp_tune(b"knn_cell_density", 100)
 
 
 def test_prm_connect_graph_replay_equals_eager(sg):
@@ -613,7 +619,7 @@ def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
     try:
         for k in (11, 1, 32):
             ei, ed = orc.knn(poses, X, k)
-            for filt, cells in ((1, 1), (1, 0), (0, 0)):
+            for filt, cells in ((1, 1), (1, 3), (1, 0), (0, 0)):
                 lib.sbp_tune(b"knn_filter", filt)
                 lib.sbp_tune(b"knn_cells", cells)
                 idx, dist = t.knn(X, k)
@@ -621,7 +627,7 @@ def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
                 assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt, cells)
     finally:
         lib.sbp_tune(b"knn_filter", 1)
-        lib.sbp_tune(b"knn_cells", 1)
+        lib.sbp_tune(b"knn_cells", 2)
 
 
 def test_cfg2_full_size_connection_equals_oracle(sg):

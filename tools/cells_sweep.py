@@ -1,0 +1,30 @@
+"""cfg2 kNN (50k x 50k, k = 11) and 1M x 1M under the cell-grid knobs."""
+import sys, numpy as np, torch
+sys.path.insert(0, "/root/repo")
+import sbp_env_b200 as sg
+from sbp_env_b200 import _lib
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev); g.manual_seed(0)
+def timeit(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+for n in (50_000, 1_000_000):
+    tree = sg.NodeStore(2, capacity=n)
+    tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * torch.tensor([579., 581.], device=dev, dtype=torch.float64))
+    X = tree.rows_device(0, n)
+    ref = None
+    for mode, dens in ((1, 50), (3, 50), (3, 100), (3, 150), (3, 200), (3, 300), (3, 25), (1, 100), (1, 200)):
+        lib.sbp_tune(b"knn_cells", mode); lib.sbp_tune(b"knn_cell_density", dens)
+        gr = torch.cuda.CUDAGraph()
+        tree.knn(X, 11, return_dist=False); torch.cuda.synchronize()
+        with torch.cuda.graph(gr):
+            out = tree.knn(X, 11, return_dist=False)
+        ms = timeit(gr.replay)
+        idx = out[0] if isinstance(out, tuple) else out
+        if ref is None: ref = idx.clone()
+        print(n, "mode", mode, "density", dens, "ms %.4f" % ms, "same", bool(torch.equal(ref, idx)), flush=True)
