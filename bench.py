@@ -3,9 +3,10 @@
 maps/intel_lab (579x581), 50 000 free samples, k = 10 nearest neighbours, the
 500 000 candidate edges checked through visible_batch.
 
-One step = one pass of the hot path over one batch: brute-force fp64 kNN of 50 000
-rows against the 50 000-node roadmap (2.5e9 distance evaluations), edge gather, and
-integer-Bresenham visibility of the 500 000 candidate edges.  At N GPUs (weak
+One step = one pass of the hot path over one batch: exact fp64 kNN of 50 000 rows
+against the 50 000-node roadmap (2.5e9 pairs; answered from a cell grid rebuilt inside
+every step, the brute-force scan behind it is timed separately as roofline_bruteforce),
+and integer-Bresenham visibility of the 500 000 candidate edges.  At N GPUs (weak
 scaling) rank 0's batch is the roadmap's own nodes (= PRM build, self excluded) and
 rank r > 0 connects a further batch of 50 000 free samples to the replicated
 roadmap; the per-rank neighbour/visibility blocks are all-gathered (NCCL) inside the
@@ -36,13 +37,19 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 N_NODES = 50_000
 K_NN = 10
 MAP = "intel_lab"
-METRIC = "edge collision checks/sec (PRM candidate edges: brute-force kNN connect + visible_batch)"
+METRIC = "edge collision checks/sec (PRM candidate edges: exact kNN connect + visible_batch)"
 UNIT = "edges/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_filter launch on this workload
 # (ncu --set full, profiles/r1_knn_filter_full.txt)
 FILTER_DRAM_TRAFFIC = 18273024
+# the same for one k_knn_cells_t launch (profiles/r1_knn_cells_full.txt), and that capture's
+# instruction / L1 sector counts (static facts about the kernel on this workload)
+CELLS_DRAM_TRAFFIC = 2196736
+CELLS_NCU = {"warp_instructions": 25814577, "l1_global_load_sectors": 5197265,
+             "issue_active_pct": 33.7, "threads_per_instruction": 16.6, "warps_per_sm": 9.1,
+             "source": "profiles/r1_knn_cells_full.txt"}
 WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
-            "candidate edges per step (kNN 2.5e9 fp64 distance evals + Bresenham visible_batch)")
+            "candidate edges per step (exact kNN of 50000 rows among 50000 nodes = 2.5e9 pairs + Bresenham visible_batch)")
 
 
 def load_free():
@@ -252,7 +259,7 @@ def run_ours(args):
         eager_step()
     torch.cuda.synchronize()
     launches0 = ctx.launches
-    lib.sbp_tune(b"time_kernels", 1)
+    lib.sbp_tune(b"time_kernels", 2)       # event pair around the cell-grid kNN kernel
     p_start = [torch.cuda.Event(enable_timing=True) for _ in range(psteps)]
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in names] for _ in range(psteps)]
     for s in range(psteps):
@@ -264,7 +271,7 @@ def run_ours(args):
     lib.sbp_tune(b"time_kernels", 0)
     kt_ms, kt_n = C.c_double(), C.c_int64()
     _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
-    filter_ms = kt_ms.value / max(1, kt_n.value)
+    cells_ms, cells_n = kt_ms.value / max(1, kt_n.value), int(kt_n.value)
     launches_per_step = (ctx.launches - launches0) // psteps
     launches = launches_per_step * args.steps
     ph = {}
@@ -278,6 +285,35 @@ def run_ours(args):
     n_vis = int(vis.sum().item())
     nbr_e, vis_e = eager_step()
     assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e), "graph replay differs from the eager step"
+
+    # ---- the brute-force scan (the path of queries the cell grid cannot answer), same rows:
+    # kNN alone with sbp_tune("knn_cells", 0), k_knn_filter bracketed by its own events
+    Xq = queries if queries is not None else tree.rows_device(0, m)
+    kq = k if queries is not None else k + 1
+    lib.sbp_tune(b"knn_cells", 0)
+    lib.sbp_tune(b"time_kernels", 1)
+    try:
+        idx_bf, _ = tree.knn(Xq, kq, return_dist=False)
+        torch.cuda.synchronize()
+        _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
+        bf_a, bf_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        bf_ms = []
+        for _ in range(psteps):
+            flush.zero_()
+            torch.cuda._sleep(2_000_000)
+            bf_a.record()
+            tree.knn(Xq, kq, return_dist=False)
+            bf_b.record()
+            torch.cuda.synchronize()
+            bf_ms.append(bf_a.elapsed_time(bf_b))
+        _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
+        filter_ms, filter_n = kt_ms.value / max(1, kt_n.value), int(kt_n.value)
+        bf_call_ms = float(np.median(bf_ms))
+    finally:
+        lib.sbp_tune(b"time_kernels", 0)
+        lib.sbp_tune(b"knn_cells", 2)
+    idx_grid, _ = tree.knn(Xq, kq, return_dist=False)
+    assert torch.equal(idx_bf, idx_grid), "cell-grid kNN differs from the brute-force scan"
 
     # ---- end to end through the public API with host buffers -------------------
     pinned = torch.from_numpy(batch_host).pin_memory()
@@ -342,21 +378,40 @@ def run_ours(args):
     evals = float(m) * float(len(tree))
     knn_s = ph["knn"] / 1e3
     filt_s = filter_ms / 1e3
-    # Dominant kernel: k_knn_filter (the brute-force scan of all m x n pairs).  ALGORITHMIC
-    # bytes per launch (8 d / Q_tile per distance evaluation when Q_tile
-    # queries share a streamed node; the scan streams the fp32 shadow, 4 (d + 1) bytes per
-    # node, to CTAs of Q_tile = 256 queries) + the query rows + the candidate lists.
+    cells_s = cells_ms / 1e3
+    n_nodes = float(len(tree))
+    # Dominant kernel: k_knn_cells_t (exact kNN from the cell grid, one thread per query).
+    # ALGORITHMIC bytes per launch = every byte it has to touch once: node coordinates (16 B) and
+    # cell-sorted ids (4 B) per node, the cell starts (one int per node at density 1), the
+    # query rows (16 B) and per query the index row ((k + 1) x 8 B), its seed (8 B) and flag (1 B).
+    alg_cells = n_nodes * (16 + 4 + 4) + m * (16 + kq * 8 + 9)
+    roof = {"kernel": f"k_knn_cells_t<2,{kq}> (exact kNN from the cell grid, one thread per query; "
+                      f"{100 * cells_ms / sum(ph.values()):.0f}% of the step)",
+            "bound": "hbm", "achieved": alg_cells / cells_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_cells / cells_s / 1e9 / hbm_peak, "traffic": CELLS_DRAM_TRAFFIC,
+            "peak_source": peak_src, "kernel_ms": cells_ms, "kernel_launches_timed": cells_n,
+            "algorithmic_bytes_per_launch": alg_cells,
+            "note": "a gather over L1 / L2-resident arrays (1.6 MB), not an HBM stream: the kernel is "
+                    "bound by its warps' serial chains (dependent loads cell start -> id -> node, "
+                    "lock-step sorted insertions) at ~9 warps per SM; see issue and l2_gather",
+            "issue": dict(CELLS_NCU, warp_instructions_per_query=CELLS_NCU["warp_instructions"] / float(m)),
+            "l2_gather": {"l1_sector_GBps": CELLS_NCU["l1_global_load_sectors"] * 32 / cells_s / 1e9},
+            "queries_per_s_kernel": m / cells_s,
+            "effective_pair_rate_per_s": evals / cells_s}
+    # The brute-force scan k_knn_filter (all m x n pairs), which the step used before the cell grid
+    # and which still serves the queries the grid cannot answer.  ALGORITHMIC bytes per launch
+    # (8 d / Q_tile per distance evaluation when Q_tile queries share a streamed
+    # node; the scan streams the fp32 shadow, 4 (d + 1) bytes per node, to CTAs of Q_tile = 256
+    # queries) + the query rows + the candidate lists.
     q_tile = 256
     alg_bytes = evals * 4 * 3 / q_tile + m * 16 + m * 8 + m * 24 * 4
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on this
-    # workload, from the ncu --set full capture summarised in profiles/r1_knn_filter_full.txt
-    roof = {"kernel": "k_knn_filter<2> (brute-force scan of the kNN phase: all 2.5e9 pairs; "
-                      f"{100 * filter_ms / sum(ph.values()):.0f}% of the step)",
-            "bound": "hbm", "achieved": alg_bytes / filt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / filt_s / 1e9 / hbm_peak, "traffic": FILTER_DRAM_TRAFFIC,
-            "peak_source": peak_src, "kernel_ms": filter_ms, "kernel_launches_timed": int(kt_n.value),
-            "note": "the scan shares every streamed node among 256 queries, so it is bound by the "
-                    "FMA pipe, not by HBM: see fma_pipe"}
+    brute = {"kernel": "k_knn_filter<2> (brute-force scan: all 2.5e9 pairs), kNN call with "
+                       "sbp_tune('knn_cells', 0)",
+             "bound": "hbm", "achieved": alg_bytes / filt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": alg_bytes / filt_s / 1e9 / hbm_peak, "traffic": FILTER_DRAM_TRAFFIC,
+             "kernel_ms": filter_ms, "knn_call_ms": bf_call_ms, "kernel_launches_timed": filter_n,
+             "note": "the scan shares every streamed node among 256 queries, so it is bound by the "
+                     "FMA pipe, not by HBM: see fma_pipe"}
 
     def mb(which, nbytes, iters):
         ms, units = C.c_double(), C.c_double()
@@ -376,16 +431,16 @@ def run_ours(args):
     # per warp and group of 8 nodes x 4 queries: 32 FFMA2 + 12 FMNMX3 (= 24 FMNMX slots) + 4 FMNMX
     # + 7 FSETP ~ 32 packed + 35 ALU operations ~ 67 mixed instructions at the measured mix rate
     mix_bound_s = evals / 32.0 * 67.0 / mix_rate
-    roof["fma_pipe"] = {"model": "d = 2 fp32 FMAs per (query, node) pair, packed FFMA2",
+    brute["fma_pipe"] = {"model": "d = 2 fp32 FMAs per (query, node) pair, packed FFMA2",
                         "achieved_fma_per_s": evals * 2 / filt_s,
                         "peak_fma_per_s_measured": fma_peak,
                         "frac": evals * 2 / filt_s / fma_peak,
                         "mixed_bound_ms": mix_bound_s * 1e3,
                         "mixed_bound_frac": mix_bound_s / filt_s,
                         "dist_evals_per_s_kernel": evals / filt_s,
-                        "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / knn_s,
+                        "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / (bf_call_ms / 1e3),
                                             "measured_peak_unfused_fp64_ops_per_s": fp64_peak,
-                                            "ratio": evals * 6 / knn_s / fp64_peak}}
+                                            "ratio": evals * 6 / (bf_call_ms / 1e3) / fp64_peak}}
 
     # ---- micro: uniform random edge batches on the same map ------
     micro = None
@@ -496,9 +551,12 @@ def run_ours(args):
         "gpu_launches_per_step": int(launches_per_step),
         "adjacency_gather": gather_kind,
         "roofline": roof,
+        "roofline_bruteforce": brute,
         "cpu_baseline": cpu,
         "phases_ms": ph,
-        "submetrics": {"knn_dist_evals_per_s_per_gpu": evals / knn_s,
+        "submetrics": {"knn_queries_per_s_per_gpu": m / knn_s,
+                       "knn_effective_pairs_per_s_per_gpu": evals / knn_s,
+                       "knn_bruteforce_dist_evals_per_s_per_gpu": evals / (bf_call_ms / 1e3),
                        "visible_batch_edges_per_s_per_gpu": edges_per_rank / (ph["visible"] / 1e3),
                        "prm_build_ms": total_ms / args.steps,
                        "roadmap_edges_visible": n_vis},

@@ -71,7 +71,8 @@ extern int g_time_kernels;
 struct KernelTimer {          // RAII: records an event pair on the launching stream
     sbp_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
-    explicit KernelTimer(sbp_ctx *c) : ctx(g_time_kernels ? c : nullptr) {
+    // which: 1 = k_knn_filter, 2 = k_knn_cells / k_knn_cells_t (sbp_tune("time_kernels", which))
+    explicit KernelTimer(sbp_ctx *c, int which = 1) : ctx(g_time_kernels == which ? c : nullptr) {
         if (!ctx) return;
         cudaEventCreate(&a);
         cudaEventCreate(&b);

@@ -1358,6 +1358,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         if (g_knn_filter && g_knn_cells) {
             rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
             if (rc) return rc;
+            KernelTimer timer(ctx, 2);
             if (g_knn_cells >= 3 || (g_knn_cells == 2 && m >= 4096)) {
                 // first ring radius whose block is expected to hold K nodes
                 const double per_cell = (double)n / ((double)G * (double)G);
