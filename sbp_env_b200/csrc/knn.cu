@@ -68,11 +68,18 @@ struct TopK {
     // The same insertion with the order (d, index) decided explicitly, for callers that do not
     // feed indices in ascending order (k_knn_cells_t walks the nodes cell by cell).  bound2 is
     // inflated so that it also admits a d^2 just above d_K^2 whose root still rounds to d_K.
+    // (Bitwise predicate logic on purpose: with && / || ptxas emitted two divergent branches
+    // per slot, ~265 instructions per insertion instead of ~150.  An empty slot is (inf, -1):
+    // as an unsigned index it never ranks before a real one, also when dd itself is +inf.)
+    __device__ __forceinline__ bool before(int t, double dd, int32_t idx) const {
+        const bool lt = d[t] < dd, eq = d[t] == dd, il = (uint32_t)i[t] < (uint32_t)idx;
+        return lt | (eq & il);
+    }
     __device__ __forceinline__ void insert_pair(double dd, int32_t idx) {
-        bool r_cur = i[K - 1] >= 0 && (d[K - 1] < dd || (d[K - 1] == dd && i[K - 1] < idx));
+        bool r_cur = before(K - 1, dd, idx);
 #pragma unroll
         for (int t = K - 1; t >= 1; --t) {
-            const bool r_prev = i[t - 1] >= 0 && (d[t - 1] < dd || (d[t - 1] == dd && i[t - 1] < idx));
+            const bool r_prev = before(t - 1, dd, idx);
             const double nd = r_prev ? dd : d[t - 1];
             const int32_t ni = r_prev ? idx : i[t - 1];
             d[t] = r_cur ? d[t] : nd;
@@ -84,7 +91,11 @@ struct TopK {
     }
     __device__ __forceinline__ void offer_pair(double d2, int32_t idx) {
         if (d2 <= bound2 && idx >= 0) {
-            insert_pair(__dsqrt_rn(d2), idx);
+            // (a query that is itself a node: d^2 = 0 would send the whole warp through the
+            // slow path of the square root; the root is taken of 1 instead and discarded)
+            const bool pos = d2 > 0.0;
+            const double root = __dsqrt_rn(pos ? d2 : 1.0);
+            insert_pair(pos ? root : d2, idx);
             bound2 = i[K - 1] < 0 ? seed2 : __dmul_ru(d[K - 1], d[K - 1]) * (1.0 + 1e-9) + 1e-300;
         }
     }
