@@ -46,10 +46,10 @@ struct TopK {
     // Pure predicate/select code, ~8 instructions per slot (the earlier `if (!placed)`
     // formulation made ptxas copy the whole list per step: ~30 instructions per slot).
     __device__ __forceinline__ void insert_sorted(double dd, int32_t idx) {
-        bool r_cur = i[K - 1] >= 0 && d[K - 1] <= dd;        // r_{K-1}: true => list full, no room
+        bool r_cur = (i[K - 1] >= 0) & (d[K - 1] <= dd);     // r_{K-1}: true => list full, no room
 #pragma unroll
         for (int t = K - 1; t >= 1; --t) {
-            const bool r_prev = i[t - 1] >= 0 && d[t - 1] <= dd;
+            const bool r_prev = (i[t - 1] >= 0) & (d[t - 1] <= dd);
             const double nd = r_prev ? dd : d[t - 1];
             const int32_t ni = r_prev ? idx : i[t - 1];
             d[t] = r_cur ? d[t] : nd;
@@ -1135,7 +1135,7 @@ k_knn_cells(const double *__restrict__ soa, int64_t capacity, const double *__re
 // The 32 queries of a warp walk their rectangles row by row in lock-step: per row one
 // contiguous range of `ids` (two when the seed block, already merged, is cut out of R), four
 // nodes per lane and step, then the lanes insert their passing nodes round by round.
-template <int D, int K>
+template <int D, int K, int U>
 __device__ __forceinline__ void cells_scan_rows(const double *__restrict__ soa, int64_t capacity,
                                                 const int32_t *__restrict__ start,
                                                 const int32_t *__restrict__ ids, int G,
@@ -1147,6 +1147,9 @@ __device__ __forceinline__ void cells_scan_rows(const double *__restrict__ soa, 
     const int maxrows = __reduce_max_sync(FULL, nrows);
     const bool cut = sx1 >= sx0;
     const int nseg = __any_sync(FULL, active && cut) ? 2 : 1;
+    // (a software pipeline that requests the ids of the next segment and the range of the one
+    // after it ahead of time was measured: no gain -- the kernel is bound by the instructions
+    // it issues, not by the latency of its dependent loads)
     for (int j = 0; j < maxrows; ++j) {
         // rows nearest to the query's own row first: the list fills with near nodes, its bound
         // tightens early and fewer of the later nodes reach the insertion (results unchanged)
@@ -1170,30 +1173,30 @@ __device__ __forceinline__ void cells_scan_rows(const double *__restrict__ soa, 
                 e1 = start[(int64_t)row * G + c1 + 1];
             }
             while (__any_sync(FULL, e < e1)) {
-                double d2[4];
-                int32_t id[4];
+                double d2[U];
+                int32_t id[U];
                 unsigned mask = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const bool ok = e + u < e1;
                     id[u] = ok ? ids[e + u] : 0;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < U; ++u) {
                     double pv[D];
 #pragma unroll
                     for (int c = 0; c < D; ++c) pv[c] = soa[(int64_t)c * capacity + id[u]];
                     d2[u] = dist2_full<D>(pv, qv);
                     mask |= (e + u < e1 && d2[u] <= top.bound2) ? (1u << u) : 0u;
                 }
-                e += 4;
+                e += U;
                 while (__any_sync(FULL, mask != 0u)) {
-                    const int u = mask ? __ffs(mask) - 1 : 4;
+                    const int u = mask ? __ffs(mask) - 1 : U;
                     mask &= mask - 1;
                     double dd = INFINITY;
                     int32_t ii = -1;
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) { dd = u == v ? d2[v] : dd; ii = u == v ? id[v] : ii; }
+                    for (int v = 0; v < U; ++v) { dd = u == v ? d2[v] : dd; ii = u == v ? id[v] : ii; }
                     top.offer_pair(dd, ii);
                 }
             }
@@ -1201,15 +1204,16 @@ __device__ __forceinline__ void cells_scan_rows(const double *__restrict__ soa, 
     }
 }
 
-template <int D, int K>
+template <int D, int K, int U>
 __global__ void __launch_bounds__(32)
 k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
               const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
-              const int32_t *__restrict__ ids, int k, int r_init, int limit,
+              const int32_t *__restrict__ ids, int k, int r_init, int limit, int qpw,
               double *__restrict__ seed2, uint8_t *__restrict__ done, int32_t *__restrict__ pending,
               int64_t *__restrict__ idx, double *__restrict__ dist) {
-    const int64_t q = (int64_t)blockIdx.x * 32 + threadIdx.x;
-    const bool live = q < m;
+    // qpw queries per warp (the other lanes idle; experiment knob, 32 is fastest)
+    const int64_t q = (int64_t)blockIdx.x * qpw + threadIdx.x;
+    const bool live = q < m && (int)threadIdx.x < qpw;
     double qv[D];
     bool finite = live;
 #pragma unroll
@@ -1232,7 +1236,7 @@ k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__
             if (have_block || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
         }
     }
-    cells_scan_rows<D, K>(soa, capacity, start, ids, G, qv, top, have_block, x0, x1, y0, y1, 0, -1, 0, -1,
+    cells_scan_rows<D, K, U>(soa, capacity, start, ids, G, qv, top, have_block, x0, x1, y0, y1, 0, -1, 0, -1,
                           cy_q, true);
     const bool full = have_block && top.i[K - 1] >= 0 && top.bound2 < INFINITY;
     bool handled = false, pass2 = false;
@@ -1252,7 +1256,7 @@ k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__
         }
     }
     // pass 2: the cells of R outside the block (the block's nodes are in the list already)
-    cells_scan_rows<D, K>(soa, capacity, start, ids, G, qv, top, pass2, xa, xb, ya, yb, x0, x1, y0, y1, 0, false);
+    cells_scan_rows<D, K, U>(soa, capacity, start, ids, G, qv, top, pass2, xa, xb, ya, yb, x0, x1, y0, y1, 0, false);
     if (!live) return;
     if (handled) {
 #pragma unroll
@@ -1276,6 +1280,7 @@ int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filte
 int g_knn_cells = 2;          // tuning knob: exact answers from the cell grid where its rectangle is small
                               // (0 = off, 1 = warp per query, 2 = thread per query when >= 4096 queries, 3 = always)
 int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes (thread per query: a quarter)
+int g_knn_cells_qpw = 0;      // tuning knob: queries per warp of k_knn_cells_t (0 = 32)
 int g_knn_cell_density = 100; // tuning knob: nodes per grid cell x 100
 
 template <int D, int K>
@@ -1375,8 +1380,13 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                 const double per_cell = (double)n / ((double)G * (double)G);
                 int r_init = (int)ceil((sqrt((double)K / per_cell) - 1.0) / 2.0);
                 r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
-                k_knn_cells_t<D, K><<<(unsigned)((m + 31) / 32), 32, 0, ctx->stream>>>(
-                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, g_knn_cells_limit / 4,
+                int qpw = g_knn_cells_qpw;
+                // (measured on cfg2: 16 / 8 queries per warp take 0.094 / 0.113 ms instead of 0.075:
+                // the kernel is bound by the instructions it issues, not by the length of a warp's chain)
+                if (qpw <= 0 || qpw > 32) qpw = 32;
+                // (8 nodes per lane and step were measured too: 0.077 instead of 0.076 ms on cfg2)
+                k_knn_cells_t<D, K, 4><<<(unsigned)((m + qpw - 1) / qpw), 32, 0, ctx->stream>>>(
+                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, g_knn_cells_limit / 4, qpw,
                     (double *)seedbuf, (uint8_t *)donebuf, pending_all, idx, dist);
             } else {
                 k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
