@@ -382,9 +382,9 @@ def run_ours(args):
     n_nodes = float(len(tree))
     # Dominant kernel: k_knn_cells_t (exact kNN from the cell grid, one thread per query).
     # ALGORITHMIC bytes per launch = every byte it has to touch once: node coordinates (16 B) and
-    # cell-sorted ids (4 B) per node, the cell starts (one int per node at density 1), the
+    # cell-sorted ids (4 B) per node, the cell starts (one int per cell, 3 nodes per cell), the
     # query rows (16 B) and per query the index row ((k + 1) x 8 B), its seed (8 B) and flag (1 B).
-    alg_cells = n_nodes * (16 + 4 + 4) + m * (16 + kq * 8 + 9)
+    alg_cells = n_nodes * (16 + 4 + 4.0 / 3.0) + m * (16 + kq * 8 + 9)
     roof = {"kernel": f"k_knn_cells_t<2,{kq}> (exact kNN from the cell grid, one thread per query; "
                       f"{100 * cells_ms / sum(ph.values()):.0f}% of the step)",
             "bound": "hbm", "achieved": alg_cells / cells_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -394,7 +394,9 @@ def run_ours(args):
             "note": "a gather over L1 / L2-resident arrays (1.6 MB), not an HBM stream: the kernel is "
                     "bound by its warps' serial chains (dependent loads cell start -> id -> node, "
                     "lock-step sorted insertions) at ~9 warps per SM; see issue and l2_gather",
-            "issue": dict(CELLS_NCU, warp_instructions_per_query=CELLS_NCU["warp_instructions"] / float(m)),
+            "issue": dict(CELLS_NCU, warp_instructions_per_query=CELLS_NCU["warp_instructions"] / float(m),
+                          issue_slot_frac=CELLS_NCU["warp_instructions"]
+                          / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) / cells_s),
             "l2_gather": {"l1_sector_GBps": CELLS_NCU["l1_global_load_sectors"] * 32 / cells_s / 1e9},
             "queries_per_s_kernel": m / cells_s,
             "effective_pair_rate_per_s": evals / cells_s}

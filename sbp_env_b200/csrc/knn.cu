@@ -1209,11 +1209,16 @@ __global__ void __launch_bounds__(32)
 k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__restrict__ X, int64_t m,
               const double *__restrict__ b4, int G, const int32_t *__restrict__ start,
               const int32_t *__restrict__ ids, int k, int r_init, int limit, int qpw,
-              double *__restrict__ seed2, uint8_t *__restrict__ done, int32_t *__restrict__ pending,
+              const int32_t *__restrict__ order, double *__restrict__ seed2,
+              uint8_t *__restrict__ done, int32_t *__restrict__ pending,
               int64_t *__restrict__ idx, double *__restrict__ dist) {
-    // qpw queries per warp (the other lanes idle; experiment knob, 32 is fastest)
-    const int64_t q = (int64_t)blockIdx.x * qpw + threadIdx.x;
-    const bool live = q < m && (int)threadIdx.x < qpw;
+    // qpw queries per warp (the other lanes idle; experiment knob, 32 is fastest).  `order`: a
+    // permutation of the queries; the launcher passes the cell-sorted node ids when there are as
+    // many queries as nodes, so that -- when the queries are the stored nodes themselves (PRM
+    // build) -- the 32 queries of a warp are neighbours: same cells, same loads, similar lists.
+    const int64_t slot = (int64_t)blockIdx.x * qpw + threadIdx.x;
+    const bool live = slot < m && (int)threadIdx.x < qpw;
+    const int64_t q = live ? (order ? (int64_t)order[slot] : slot) : m;
     double qv[D];
     bool finite = live;
 #pragma unroll
@@ -1281,7 +1286,8 @@ int g_knn_cells = 2;          // tuning knob: exact answers from the cell grid w
                               // (0 = off, 1 = warp per query, 2 = thread per query when >= 4096 queries, 3 = always)
 int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes (thread per query: a quarter)
 int g_knn_cells_qpw = 0;      // tuning knob: queries per warp of k_knn_cells_t (0 = 32)
-int g_knn_cell_density = 100; // tuning knob: nodes per grid cell x 100
+int g_knn_cells_order = 1;    // tuning knob: cell-sorted query order when m == n (results unchanged)
+int g_knn_cell_density = 300; // tuning knob: nodes per grid cell x 100
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -1387,7 +1393,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                 // (8 nodes per lane and step were measured too: 0.077 instead of 0.076 ms on cfg2)
                 k_knn_cells_t<D, K, 4><<<(unsigned)((m + qpw - 1) / qpw), 32, 0, ctx->stream>>>(
                     s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, g_knn_cells_limit / 4, qpw,
-                    (double *)seedbuf, (uint8_t *)donebuf, pending_all, idx, dist);
+                    (g_knn_cells_order && m == n) ? ids : nullptr, (double *)seedbuf, (uint8_t *)donebuf,
+                    pending_all, idx, dist);
             } else {
                 k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
                     s->d_soa, s->capacity, X, m, b4, G, start, ids, k, g_knn_cells_limit, (double *)seedbuf,

@@ -428,10 +428,23 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
                 idx, dist = t.knn(X, kk)
                 assert np.array_equal(idx, ei), (layout, d, kk, mode, limit, density)
                 assert np.array_equal(dist, ed, equal_nan=True), (layout, d, kk, mode, limit, density)
+        # as many queries as nodes (the PRM build: the stored rows themselves, and an unrelated
+        # batch of the same size): the queries are then walked in cell-sorted order
+        for Xs in (poses, np.roll(X, 7, axis=0)[np.arange(n) % len(X)]):
+            ei, ed = orc.knn(poses, Xs, 11)
+            for mode, order in ((3, 1), (3, 0), (2, 1)):
+                lib.sbp_tune(b"knn_cells", mode)
+                lib.sbp_tune(b"knn_cells_limit", 1024)
+                lib.sbp_tune(b"knn_cell_density", 300)
+                lib.sbp_tune(b"knn_cells_order", order)
+                idx, dist = t.knn(Xs, 11)
+                assert np.array_equal(idx, ei), (layout, d, mode, order)
+                assert np.array_equal(dist, ed, equal_nan=True), (layout, d, mode, order)
     finally:
         lib.sbp_tune(b"knn_cells", 2)
         lib.sbp_tune(b"knn_cells_limit", 1024)
-        lib.sbp_tune(b"knn_cell_density", 100)
+        lib.sbp_tune(b"knn_cell_density", 300)
+        lib.sbp_tune(b"knn_cells_order", 1)
 
 
 def test_prm_connect_graph_replay_equals_eager(sg):
