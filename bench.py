@@ -184,6 +184,13 @@ def run_ours(args):
         except Exception as e:      # noqa: BLE001
             gather_kind = f"NCCL all-gather of the packed block (peer memory unavailable: {type(e).__name__})"
 
+    # where the fabric has the multicast mapping, the visibility kernel itself sends the packed
+    # adjacency through the switch (one captured graph per buffer half) and only the barrier follows
+    fused_exchange = peer is not None and peer.fused
+    if fused_exchange:
+        gather_kind = "fused: the visibility kernel stores the packed adjacency through the NVSwitch " \
+                      "multicast mapping as edges are decided; symmetric-memory barrier"
+
     def gather(nbr, vis):
         if world == 1:
             gathered["nbr"], gathered["vis"] = nbr, vis
@@ -200,19 +207,52 @@ def run_ours(args):
                 ev[idx[0]].record()
                 idx[0] += 1
 
-        nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
-        gather(nbr, vis)
+        if fused_exchange:
+            h = peer_step[0] & 1
+            peer_step[0] += 1
+            nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark, packed_out=peer.target(h))
+            gathered["packed"] = peer.complete(h)
+        else:
+            nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
+            gather(nbr, vis)
         mark("gather")
         return nbr, vis
+
+    peer_step = [0]
 
     # The step is ~20 short kernels; issued one by one from Python the launch gaps cost ~15 %,
     # so the timed loop replays the step from a CUDA graph (the library's
     # PRMConnectGraph); the all-gather (N > 1) follows the replay on the same stream.
-    gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
+    barrier_in_graph = False
+    if fused_exchange:
+        # the barrier is captured into the step's graph when torch's symmetric-memory barrier
+        # allows it (BENCH_EAGER_BARRIER=1 keeps it as a separate launch after the replay)
+        if os.environ.get("BENCH_EAGER_BARRIER", "0") != "1":
+            try:
+                gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h),
+                                             after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
+                barrier_in_graph = True
+            except Exception as e:      # noqa: BLE001
+                print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
+        ok = torch.tensor([1 if barrier_in_graph else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        barrier_in_graph = bool(ok.item())
+        if not barrier_in_graph:
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h)) for h in (0, 1)]
+        gather_kind += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
+        dist.barrier()
+    else:
+        gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
 
     def step():
-        nbr, vis = gstep.replay()
-        gather(nbr, vis)
+        if fused_exchange:
+            h = peer_step[0] & 1
+            peer_step[0] += 1
+            nbr, vis = gsteps[h].replay()
+            gathered["packed"] = peer.view(h) if barrier_in_graph else peer.complete(h)
+        else:
+            nbr, vis = gstep.replay()
+            gather(nbr, vis)
         return nbr, vis
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -285,6 +325,10 @@ def run_ours(args):
     n_vis = int(vis.sum().item())
     nbr_e, vis_e = eager_step()
     assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e), "graph replay differs from the eager step"
+    if world > 1:      # the assembled adjacency holds this rank's block at its place
+        torch.cuda.synchronize()
+        gn, gv = sg.distributed.unpack_adjacency(gathered["packed"][rank * m:(rank + 1) * m])
+        assert torch.equal(gn, nbr_e) and torch.equal(gv, vis_e), "assembled adjacency differs from the local block"
 
     # ---- the brute-force scan (the path of queries the cell grid cannot answer), same rows:
     # kNN alone with sbp_tune("knn_cells", 0), k_knn_filter bracketed by its own events
@@ -323,16 +367,17 @@ def run_ours(args):
     tree2 = sg.NodeStore(2, capacity=N_NODES, device=local) if rank == 0 else None
 
     x_dev = torch.empty((m, 2), dtype=torch.float64, device=dev)
+    code_dev = torch.empty((m, k), dtype=torch.int32, device=dev)
 
     def e2e_body():
         x_dev.copy_(pinned, non_blocking=True)             # H2D of this step's samples
         if rank == 0:
             tree2.truncate(0)
             tree2.extend(x_dev)                            # roadmap rebuilt from the samples
-            nb, vs = sg.prm_connect_knn(cc, tree2, k)
+            sg.prm_connect_knn(cc, tree2, k, packed_out=code_dev)
         else:
-            nb, vs = sg.prm_connect_knn(cc, tree, k, queries=x_dev)
-        code_h.copy_(sg.distributed.pack_adjacency(nb, vs), non_blocking=True)   # D2H of the adjacency block
+            sg.prm_connect_knn(cc, tree, k, queries=x_dev, packed_out=code_dev)
+        code_h.copy_(code_dev, non_blocking=True)          # D2H of the adjacency block (packed by the kernel)
 
     # the user-facing call: the whole host-to-host step captured once (CapturedStep) and
     # replayed; H2D, store rebuild, connection and D2H all run inside every replay

@@ -211,10 +211,16 @@ int32_t sbp_nodes_knn_edges(sbp_nodes *nodes, const int64_t *nbr_in, int64_t m, 
  * replaces: the body of PRMPlanner.build_graph's double loop (prmPlanner.py:91-101) --
  * `if m_g is v: continue` and `cc.visible(m_g.pos, v.pos)` -- for a whole block of rows.
  * Row / column / X meaning as in sbp_nodes_knn_edges.  Writes nbr_out [m][k_out] and
- * vis [m][k_out]: 1 = the neighbour slot is filled and ImgCollisionChecker.visible is True. */
+ * vis [m][k_out]: 1 = the neighbour slot is filled and ImgCollisionChecker.visible is True.
+ * packed (optional, [m][k_out] int32): the adjacency code (neighbour + 1) * 2 + visible of every
+ * edge, written as the edge is decided -- to a local buffer, or with packed_multicast != 0 through
+ * the NVSwitch multicast address of the ranks' symmetric buffer (multimem.st): the multi-GPU
+ * assembly of the PRM adjacency (BASELINE.json north_star) then overlaps the visibility walk and
+ * only a barrier follows (distributed.PeerAdjacencyGather.target / complete). */
 int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in, int64_t m,
                                 int32_t k_in, int64_t first_row, const double *X,
-                                int64_t *nbr_out, uint8_t *vis, int32_t *flags);
+                                int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                                int32_t packed_multicast, int32_t *flags);
 
 /* Fused radius query + edge visibility in ONE launch, for the sequential planners.
  * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:

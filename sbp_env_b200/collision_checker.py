@@ -299,7 +299,7 @@ class ImgCollisionChecker(_GridChecker):
         self._last_flags = flags
         return out.view(torch.bool)          # the kernels write 0 / 1: reinterpret, no copy
 
-    def knn_edges_visible(self, tree, nbr_in, first_row: int = 0, queries=None):
+    def knn_edges_visible(self, tree, nbr_in, first_row: int = 0, queries=None, packed_out=None):
         """``tree.knn_edges`` + :meth:`visible_batch` in ONE launch (prmPlanner.py:91-101):
         the candidate edges of the kNN answer ``nbr_in`` are resolved against the node store
         inside the visibility kernel.  Returns ``(nbr, vis)`` as CUDA tensors [m][k_out];
@@ -317,9 +317,20 @@ class ImgCollisionChecker(_GridChecker):
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         X = as_device_f64(queries, 2) if queries is not None else None
         self.stats.visible_cnt += rows * k_out
+        # packed adjacency written by the kernel itself: a local int32 tensor, or (address, True)
+        # = the multicast address of a symmetric buffer (PeerAdjacencyGather.target)
+        p_ptr, p_mc = None, 0
+        if packed_out is not None:
+            if isinstance(packed_out, tuple):
+                p_ptr, p_mc = C.c_void_p(int(packed_out[0])), int(bool(packed_out[1]))
+            else:
+                if packed_out.dtype != torch.int32 or packed_out.numel() != rows * k_out \
+                        or not packed_out.is_contiguous() or packed_out.device != dev:
+                    raise ValueError("packed_out must be a contiguous CUDA int32 tensor [m][k]")
+                p_ptr = ptr(packed_out)
         check(_lib.load().sbp_knn_edges_visible2d(m.handle, tree._h, ptr(nbr_in), rows, k_in,
                                                   int(first_row), ptr(X), ptr(nbr), ptr(vis),
-                                                  ptr(flags)), "sbp_knn_edges_visible2d")
+                                                  p_ptr, p_mc, ptr(flags)), "sbp_knn_edges_visible2d")
         self._last_flags = flags
         return nbr, vis.view(torch.bool)
 

@@ -158,10 +158,11 @@ __device__ __forceinline__ bool px_free(const uint32_t *words, const MapView &mv
 // the node store on the fly (fused edge gather: no P / Q arrays are materialised).
 struct EdgeArrays {
     const double2 *P, *Q;
-    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q) const {
-        p = P[e]; q = Q[e];
+    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q, int32_t &tag) const {
+        p = P[e]; q = Q[e]; tag = 0;
         return true;
     }
+    __device__ __forceinline__ void store(int64_t, int32_t, bool) const {}
 };
 
 // Candidate edge e = (row i, column j) of a kNN answer nbr_in [m][k_in] (prmPlanner.py:91-101):
@@ -176,7 +177,22 @@ struct EdgeKnnRows {
     int64_t first_row;
     const double2 *X;
     int64_t *nbr_out;
-    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q) const {
+    // optional packed adjacency (neighbour + 1) * 2 + visible, one int32 per edge: a local buffer,
+    // or (packed_mc) the NVSwitch multicast address of the ranks' symmetric buffer -- the result
+    // is then replicated into every rank's copy by the switch as the edges are decided, so the
+    // multi-GPU exchange of the adjacency overlaps the visibility walk (distributed.py)
+    int32_t *packed;
+    int packed_mc;
+    __device__ __forceinline__ void store(int64_t e, int32_t tag, bool vis) const {
+        if (!packed) return;
+        const int32_t code = ((tag + 1) << 1) | (vis ? 1 : 0);
+        if (packed_mc)
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(packed + e),
+                         "f"(__int_as_float(code)) : "memory");
+        else
+            packed[e] = code;
+    }
+    __device__ __forceinline__ bool load(int64_t e, double2 &p, double2 &q, int32_t &tag) const {
         const int64_t i = e / k_out;
         const int j = (int)(e - i * k_out);
         const int64_t *row = nbr_in + i * k_in;
@@ -193,6 +209,7 @@ struct EdgeKnnRows {
         }
         const int64_t nb = row[col];
         nbr_out[e] = nb;
+        tag = (int32_t)nb;
         const bool ok = nb >= 0 && nb < n_nodes;
         p = ok ? make_double2(soa[nb], soa[capacity + nb]) : q;
         return ok;
@@ -219,13 +236,15 @@ k_visible2d_adaptive(MapView mv, Edges edges,
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double2 p = make_double2(0.0, 0.0), q = make_double2(0.0, 0.0);
     bool have = false;                                      // the edge exists (neighbour slot filled)
-    if (e < n) have = edges.load(e, p, q);
+    int32_t tag = 0;                                        // what store() needs besides the result
+    if (e < n) have = edges.load(e, p, q, tag);
     for (; e < n_round; e += stride) {
         const bool valid = e < n;
         const bool exists = have;
+        const int32_t ctag = tag;
         const double2 cp = p, cq = q;
         const int64_t en = e + stride;                      // prefetch the next batch
-        if (en < n) have = edges.load(en, p, q);
+        if (en < n) have = edges.load(en, p, q, tag);
 
         Edge2D ed = make_edge(cp.x, cp.y, cq.x, cq.y, mv.W, mv.H);
         if (valid) myflag |= ed.flag;
@@ -309,7 +328,10 @@ k_visible2d_adaptive(MapView mv, Edges edges,
             }
             if (lane == src) result = !hit;
         }
-        if (valid) out[e] = (result && exists) ? 1 : 0;
+        if (valid) {
+            out[e] = (result && exists) ? 1 : 0;
+            edges.store(e, ctag, result && exists);
+        }
     }
     if (myflag && flags) atomicOr(flags, myflag);
     if (COUNT) {
@@ -576,7 +598,8 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
 // nbr_out [m][k_out] and vis [m][k_out] (1 = the neighbour slot is filled and the edge is free).
 extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in,
                                            int64_t m, int32_t k_in, int64_t first_row, const double *X,
-                                           int64_t *nbr_out, uint8_t *vis, int32_t *flags) {
+                                           int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                                           int32_t packed_multicast, int32_t *flags) {
     SBP_NVTX("sbp_knn_edges_visible2d");
     SBP_REQUIRE(map && nodes && (m == 0 || (nbr_in && nbr_out && vis)), "sbp_knn_edges_visible2d: NULL argument");
     SBP_REQUIRE(nodes->d == 2, "sbp_knn_edges_visible2d: the 2-D checker needs a 2-D node store");
@@ -600,7 +623,7 @@ extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const
     const int threads = (smem && sbytes > 110 * 1024) ? 1024 : 512;
     const int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
     EdgeKnnRows src{nodes->d_soa, nodes->capacity, nodes->n, nbr_in, k_in, k_out, first_row,
-                    (const double2 *)X, nbr_out};
+                    (const double2 *)X, nbr_out, packed, packed_multicast};
 #define SBP_LAUNCH_FUSED(SM)                                                                       \
     do {                                                                                           \
         int32_t rc = set_smem(k_visible2d_adaptive<SM, false, SM, EdgeKnnRows>, sbytes);           \

@@ -137,6 +137,33 @@ class PeerAdjacencyGather:
         self.kind = "NVSwitch multicast stores" if mc else "NVLink peer stores"
         self._step = 0
 
+    # ---- fused form: the producing kernel stores straight into the multicast mapping -----
+    @property
+    def fused(self) -> bool:
+        """True when the fabric offers the multicast mapping the fused form needs."""
+        return self._mc is not None
+
+    def target(self, h: int):
+        """``packed_out`` for :func:`planning.prm_connect_knn` / ``PRMConnectGraph``: the multicast
+        address of this rank's block in buffer ``h`` (0 / 1).  The visibility kernel then sends
+        every adjacency code through the switch as the edge is decided, so the exchange overlaps
+        the computation and :meth:`complete` is only the barrier."""
+        if self._mc is None:
+            raise RuntimeError("no multicast mapping: use gather()")
+        return (int(self._mc[h].value) + self.rank * self.stride * 4, True)
+
+    def complete(self, h: int):
+        """Barrier after a step that wrote through :meth:`target` (h); returns the assembled
+        int32 [world * m][k] block like :meth:`gather`."""
+        self.ctx.use_torch_stream()
+        self.hdl.barrier(channel=h)
+        return self.view(h)
+
+    def view(self, h: int):
+        """The assembled int32 [world * m][k] block of buffer half ``h`` (no synchronisation)."""
+        out = self.buf[h].view(self.world, self.stride)[:, : self.block]
+        return out.reshape(self.world, self.m, self.k).reshape(self.world * self.m, self.k)
+
     def gather(self, nbr, vis):
         import torch
 

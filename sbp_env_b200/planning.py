@@ -33,7 +33,7 @@ def near(tree, X, r, metric="full", closed=False):
 
 
 def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, queries=None,
-                    mark=None):
+                    mark=None, packed_out=None):
     """Candidate roadmap edges of every stored node to its k nearest other nodes and
     their visibility, entirely on the device.
 
@@ -47,6 +47,11 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
         multi-GPU shard of this rank); neighbours are still searched among all nodes.
     :param queries: optional CUDA tensor [m][d] of external samples to connect to the
         stored roadmap instead of the stored rows (no self entry to drop).
+    :param packed_out: optional destination of the packed adjacency ``(nbr + 1) * 2 + vis``
+        (int32 per candidate edge), written by the visibility kernel itself as the edges are
+        decided: a CUDA int32 tensor [m][k], or ``(address, True)`` for the NVSwitch multicast
+        address of a symmetric buffer (``distributed.PeerAdjacencyGather.target``).  2-D image
+        checker only.
     :param mark: optional callable ``mark(name)`` invoked between the phases
         ("knn", "edges", "visible") on the launching stream (bench.py records CUDA
         events there).
@@ -70,10 +75,13 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
         dist = None
     if mark:
         mark("knn")
+    if packed_out is not None and not fused:
+        raise ValueError("packed_out needs the 2-D image checker on a device node store")
     if fused:
         if mark:
             mark("edges")                            # no separate edge-gather launch
-        nbr, vis = cc.knn_edges_visible(tree, idx, first_row=first, queries=queries)
+        nbr, vis = cc.knn_edges_visible(tree, idx, first_row=first, queries=queries,
+                                        packed_out=packed_out)
     else:
         nbr, P, Q, valid = tree.knn_edges(idx, first_row=first, queries=queries)
         if mark:
@@ -158,9 +166,9 @@ class CapturedStep:
 class PRMConnectGraph(CapturedStep):
     """:func:`prm_connect_knn` for a fixed problem shape as a :class:`CapturedStep`.
 
-    One connection step is ~20 short kernels (cell grid, seeds, filter, refine, edge gather,
-    visibility); issued one by one from Python the launch gaps add ~15 % to the ~0.5 ms the GPU
-    needs for a 50 000-node roadmap, so the inner loop is captured and a step becomes a single
+    One connection step is a dozen short kernels (cell grid, cell-grid kNN, the brute-force
+    kernels behind it, visibility); issued one by one from Python it takes twice the ~0.1 ms the
+    GPU needs for a 50 000-node roadmap, so the inner loop is captured and a step becomes a single
     graph launch.  Results are identical to the eager call.  ``tree`` must not change size
     and ``queries`` (when given) must be updated in place.
 
@@ -168,7 +176,10 @@ class PRMConnectGraph(CapturedStep):
     >>> nbr, vis = g.replay()          # tensors owned by the graph, overwritten by each replay
     """
 
-    def __init__(self, cc, tree, k: int, rows=None, queries=None, warmup: int = 2):
+    def __init__(self, cc, tree, k: int, rows=None, queries=None, warmup: int = 2, packed_out=None,
+                 after=None):
+        """``after``: optional callable run (and captured) right after the connection step, on
+        the same stream -- e.g. the barrier of ``PeerAdjacencyGather.complete``."""
         if "visible" in getattr(cc, "__dict__", {}):
             raise ValueError("a mocked checker cannot be captured into a CUDA graph")
         self.cc, self.tree, self.k = cc, tree, int(k)
@@ -177,7 +188,10 @@ class PRMConnectGraph(CapturedStep):
 
         def fn():
             before[0] = int(cc.stats.visible_cnt)
-            return prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries)
+            out = prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries, packed_out=packed_out)
+            if after is not None:
+                after()
+            return out
 
         super().__init__(fn, device=tree.ctx.device, warmup=warmup)
         self._edges = int(cc.stats.visible_cnt) - before[0]     # edges checked by one step

@@ -45,6 +45,31 @@ def _worker(rank, world, port, q):
                 want_n, want_v = D.all_gather_adjacency(nbr, vis)
                 got_n, got_v = D.unpack_adjacency(packed)
                 assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), (m, k, step)
+        # fused form: the visibility kernel of the connection step stores the packed adjacency
+        # straight through the multicast mapping; only a barrier follows
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import sbp_env_b200 as sg
+        from _util import load_map, map_png
+
+        free = load_map("maze1")
+        W, H = free.shape
+        cc = sg.ImgCollisionChecker(map_png("maze1"), device=rank)
+        rng = np.random.default_rng(5)
+        pts = rng.random((6000, 2)) * [W, H]
+        tree = sg.NodeStore(2, device=rank)
+        tree.extend(pts)
+        m, k = 1500, 7
+        ag = D.PeerAdjacencyGather(m, k, device=rank)
+        if ag.fused:
+            kinds.add("fused into the visibility kernel")
+            for step in range(4):
+                Xq = torch.from_numpy(np.random.default_rng(100 * step + rank).random((m, 2)) * [W, H]).to(dev)
+                h = step & 1
+                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=Xq, packed_out=ag.target(h))
+                packed = ag.complete(h)
+                want_n, want_v = D.all_gather_adjacency(nbr, vis)
+                got_n, got_v = D.unpack_adjacency(packed)
+                assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), ("fused", step)
         dist.barrier()
         dist.destroy_process_group()
         print("exchange kinds exercised:", sorted(kinds), flush=True)

@@ -164,6 +164,11 @@ def test_fused_knn_edges_visible_equals_the_two_launch_form(sg, map_name, n_node
         assert torch.equal(vis_a, vis_b)
         if n_nodes <= k:
             assert int((nbr_b < 0).sum()) > 0 and not bool(vis_b[nbr_b < 0].any())
+        # the packed adjacency written by the kernel itself == pack_adjacency of its results
+        code = torch.full((count, k), -7, dtype=torch.int32, device=nbr_b.device)
+        nbr_p, vis_p = cc.knn_edges_visible(t, idx, first_row=first, queries=queries, packed_out=code)
+        assert torch.equal(nbr_p, nbr_b) and torch.equal(vis_p, vis_b)
+        assert torch.equal(code, sg.distributed.pack_adjacency(nbr_b, vis_b))
     # forced global-memory map path gives the same answer
     from sbp_env_b200 import _lib
 
