@@ -210,8 +210,13 @@ def run_ours(args):
         if fused_exchange:
             h = peer_step[0] & 1
             peer_step[0] += 1
-            nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark, packed_out=peer.target(h))
-            gathered["packed"] = peer.complete(h)
+            if rendezvous_eager[0]:
+                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark,
+                                              packed_out=peer.target_with_rendezvous(h))
+                gathered["packed"] = peer.view(h)
+            else:
+                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark, packed_out=peer.target(h))
+                gathered["packed"] = peer.complete(h)
         else:
             nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
             gather(nbr, vis)
@@ -219,27 +224,39 @@ def run_ours(args):
         return nbr, vis
 
     peer_step = [0]
+    rendezvous_eager = [fused_exchange and os.environ.get("BENCH_EXCHANGE", "barrier") == "rendezvous"]
 
     # The step is ~20 short kernels; issued one by one from Python the launch gaps cost ~15 %,
     # so the timed loop replays the step from a CUDA graph (the library's
     # PRMConnectGraph); the all-gather (N > 1) follows the replay on the same stream.
     barrier_in_graph = False
+    rendezvous = False
     if fused_exchange:
-        # the barrier is captured into the step's graph when torch's symmetric-memory barrier
-        # allows it (BENCH_EAGER_BARRIER=1 keeps it as a separate launch after the replay)
-        if os.environ.get("BENCH_EAGER_BARRIER", "0") != "1":
-            try:
-                gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h),
-                                             after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
-                barrier_in_graph = True
-            except Exception as e:      # noqa: BLE001
-                print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
-        ok = torch.tensor([1 if barrier_in_graph else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        barrier_in_graph = bool(ok.item())
-        if not barrier_in_graph:
-            gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h)) for h in (0, 1)]
-        gather_kind += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
+        mode = os.environ.get("BENCH_EXCHANGE", "barrier")
+        if mode == "rendezvous":
+            # the kernel itself meets the other ranks: its last CTA publishes an epoch through the
+            # switch and waits for every rank's (no barrier launch).  Measured at N = 2: 0.126 ms per
+            # step against 0.120 ms with the captured symmetric-memory barrier, hence not the default.
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries,
+                                         packed_out=peer.target_with_rendezvous(h)) for h in (0, 1)]
+            rendezvous = True
+            gather_kind += " -- replaced by a rendezvous inside the kernel (last CTA: multicast epoch + wait)"
+        else:
+            # the barrier is captured into the step's graph when torch's symmetric-memory barrier
+            # allows it (BENCH_EXCHANGE=eager_barrier keeps it as a separate launch after the replay)
+            if mode != "eager_barrier":
+                try:
+                    gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h),
+                                                 after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
+                    barrier_in_graph = True
+                except Exception as e:      # noqa: BLE001
+                    print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
+            ok = torch.tensor([1 if barrier_in_graph else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            barrier_in_graph = bool(ok.item())
+            if not barrier_in_graph:
+                gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h)) for h in (0, 1)]
+            gather_kind += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
         dist.barrier()
     else:
         gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
@@ -249,7 +266,7 @@ def run_ours(args):
             h = peer_step[0] & 1
             peer_step[0] += 1
             nbr, vis = gsteps[h].replay()
-            gathered["packed"] = peer.view(h) if barrier_in_graph else peer.complete(h)
+            gathered["packed"] = peer.view(h) if (barrier_in_graph or rendezvous) else peer.complete(h)
         else:
             nbr, vis = gstep.replay()
             gather(nbr, vis)
@@ -271,8 +288,18 @@ def run_ours(args):
     t_wall0 = time.time()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    def align_ranks():
+        # N > 1: the untimed L2 flush does not take the same time on every rank; without this the
+        # timed step of an early rank would include waiting for a rank that is still flushing
+        if world > 1:
+            if peer is not None:
+                peer.hdl.barrier(channel=2)
+            else:
+                dist.barrier()
+
     for s in range(args.steps):
         flush.zero_()                      # evict L2 between timed iterations (not timed)
+        align_ranks()                      # (not timed) all ranks start the step together
         starts[s].record()
         step()
         ends[s].record()
@@ -305,6 +332,7 @@ def run_ours(args):
     for s in range(psteps):
         flush.zero_()
         torch.cuda._sleep(4_000_000)       # ~2 ms head start for the host
+        align_ranks()
         p_start[s].record()
         eager_step(phase_ev[s])
     torch.cuda.synchronize()
@@ -395,6 +423,7 @@ def run_ours(args):
     e_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for s in range(args.steps):
         flush.zero_()
+        align_ranks()
         e_s[s].record()
         e2e_step()
         e_e[s].record()
@@ -582,7 +611,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "map": "intel_lab 579x581 (occupancy fixture tests/golden/maps.npz)",
                    "nodes": N_NODES, "k": K_NN, "edges_per_step_per_gpu": edges_per_rank,
-                   "dist_evals_per_step_per_gpu": evals, "l2": "flushed (256 MiB write) between timed steps",
+                   "dist_evals_per_step_per_gpu": evals, "l2": "flushed (256 MiB write) between timed steps; N > 1: ranks aligned by an untimed barrier after the flush",
                    "launch": "the step (and the e2e step) is replayed from a CUDA graph captured by the "
                              "library (PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms "
                              "come from the same step launched eagerly",

@@ -40,6 +40,7 @@ extern "C" {
  * raise for that batch (collisionChecker.py:151, :173-174, :400) */
 #define SBP_FLAG_NAN 1       /* int(nan)           -> ValueError   */
 #define SBP_FLAG_OVERFLOW 2  /* int(+-inf), or an index in [2^63,2^64) -> OverflowError */
+#define SBP_FLAG_PEER_TIMEOUT 1024 /* sbp_knn_edges_visible2d rendezvous: a peer never signalled */
 
 /* values written to the `out` bytes of the arm entry points */
 #define SBP_FREE 1
@@ -216,11 +217,16 @@ int32_t sbp_nodes_knn_edges(sbp_nodes *nodes, const int64_t *nbr_in, int64_t m, 
  * edge, written as the edge is decided -- to a local buffer, or with packed_multicast != 0 through
  * the NVSwitch multicast address of the ranks' symmetric buffer (multimem.st): the multi-GPU
  * assembly of the PRM adjacency (BASELINE.json north_star) then overlaps the visibility walk and
- * only a barrier follows (distributed.PeerAdjacencyGather.target / complete). */
+ * only a barrier follows (distributed.PeerAdjacencyGather.target / complete) -- or not even that:
+ * rendezvous (optional HOST array of 6 int64: multicast and local address of a symmetric int32
+ * [world] signal array, addresses of two local int32 counters (CTA ticket, epoch), rank, world)
+ * makes the last CTA publish this rank's epoch through the switch and wait for every rank's, so
+ * the kernel returns when the adjacency is complete on this rank (bounded spin: a missing peer
+ * sets SBP_FLAG_PEER_TIMEOUT in *flags instead of hanging). */
 int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in, int64_t m,
                                 int32_t k_in, int64_t first_row, const double *X,
                                 int64_t *nbr_out, uint8_t *vis, int32_t *packed,
-                                int32_t packed_multicast, int32_t *flags);
+                                int32_t packed_multicast, const int64_t *rendezvous, int32_t *flags);
 
 /* Fused radius query + edge visibility in ONE launch, for the sequential planners.
  * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsbpgpu.so")
 SBP_OK = 0
 FLAG_NAN = 1
 FLAG_OVERFLOW = 2
+FLAG_PEER_TIMEOUT = 1024
 FREE, BLOCKED, AMBIGUOUS = 1, 0, 2
 METRIC = {"full": 0, "xy": 1}
 
@@ -65,7 +66,7 @@ _SIGNATURES = {
     "sbp_nodes_near_host": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, C.POINTER(_i64)],
     "sbp_nodes_gather_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp],
     "sbp_nodes_knn_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
-    "sbp_knn_edges_visible2d": [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp],
+    "sbp_knn_edges_visible2d": [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "sbp_nodes_near_visible": [_vp, _vp, _i32, _dbl, _dbl, _vp, _i64, _dbl, _i32, _i32, _i32, _vp, _vp,
                                _i32, _vp, _vp],
     "sbp_nodes_near_visible_host": [_vp, _vp, _i32, _dbl, _dbl, _vp, _dbl, _i32, _i32, _i32, _vp, _vp,

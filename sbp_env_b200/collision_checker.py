@@ -319,10 +319,12 @@ class ImgCollisionChecker(_GridChecker):
         self.stats.visible_cnt += rows * k_out
         # packed adjacency written by the kernel itself: a local int32 tensor, or (address, True)
         # = the multicast address of a symmetric buffer (PeerAdjacencyGather.target)
-        p_ptr, p_mc = None, 0
+        p_ptr, p_mc, p_sync = None, 0, None
         if packed_out is not None:
             if isinstance(packed_out, tuple):
                 p_ptr, p_mc = C.c_void_p(int(packed_out[0])), int(bool(packed_out[1]))
+                if len(packed_out) > 2 and packed_out[2] is not None:   # in-kernel rendezvous block
+                    p_sync = (C.c_int64 * 6)(*[int(v) for v in packed_out[2]])
             else:
                 if packed_out.dtype != torch.int32 or packed_out.numel() != rows * k_out \
                         or not packed_out.is_contiguous() or packed_out.device != dev:
@@ -330,7 +332,7 @@ class ImgCollisionChecker(_GridChecker):
                 p_ptr = ptr(packed_out)
         check(_lib.load().sbp_knn_edges_visible2d(m.handle, tree._h, ptr(nbr_in), rows, k_in,
                                                   int(first_row), ptr(X), ptr(nbr), ptr(vis),
-                                                  p_ptr, p_mc, ptr(flags)), "sbp_knn_edges_visible2d")
+                                                  p_ptr, p_mc, p_sync, ptr(flags)), "sbp_knn_edges_visible2d")
         self._last_flags = flags
         return nbr, vis.view(torch.bool)
 

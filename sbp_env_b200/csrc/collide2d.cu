@@ -163,6 +163,7 @@ struct EdgeArrays {
         return true;
     }
     __device__ __forceinline__ void store(int64_t, int32_t, bool) const {}
+    __device__ __forceinline__ void finish(int32_t *) const {}
 };
 
 // Candidate edge e = (row i, column j) of a kNN answer nbr_in [m][k_in] (prmPlanner.py:91-101):
@@ -183,6 +184,43 @@ struct EdgeKnnRows {
     // multi-GPU exchange of the adjacency overlaps the visibility walk (distributed.py)
     int32_t *packed;
     int packed_mc;
+    // optional rendezvous of the ranks inside this kernel (instead of a barrier launch after it):
+    // sig_mc / sig_local = multicast and local address of a symmetric int32 [world] signal array,
+    // ticket / epoch = two local counters.  The last CTA of every rank publishes its epoch through
+    // the multicast mapping and waits until every rank's entry has reached it.
+    int32_t *sig_mc;
+    const int32_t *sig_local;
+    int32_t *ticket, *epoch;
+    int rank, world;
+    __device__ __forceinline__ void finish(int32_t *flags) const {
+        if (!sig_mc) return;
+        __shared__ int s_last, s_epoch;
+        __threadfence_system();                               // this thread's multicast stores
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == (int)gridDim.x - 1 ? 1 : 0;
+        __syncthreads();
+        if (!s_last) return;
+        if (threadIdx.x == 0) {
+            *ticket = 0;
+            const int32_t ep = *epoch + 1;
+            *epoch = ep;
+            s_epoch = ep;
+            __threadfence_system();
+            asm volatile("multimem.st.release.sys.global.f32 [%0], %1;" ::"l"(sig_mc + rank),
+                         "f"(__int_as_float(ep)) : "memory");
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < world) {
+            const int32_t ep = s_epoch;
+            int32_t seen;
+            long long spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(sig_local + threadIdx.x) : "memory");
+            } while (seen - ep < 0 && ++spins < 4000000ll);
+            if (seen - ep < 0 && flags) atomicOr(flags, SBP_FLAG_PEER_TIMEOUT);   // never hang the GPU
+        }
+        __syncthreads();
+    }
     __device__ __forceinline__ void store(int64_t e, int32_t tag, bool vis) const {
         if (!packed) return;
         const int32_t code = ((tag + 1) << 1) | (vis ? 1 : 0);
@@ -338,6 +376,7 @@ k_visible2d_adaptive(MapView mv, Edges edges,
         for (int o = 16; o > 0; o >>= 1) tested += __shfl_down_sync(FULL, tested, o);
         if (lane == 0 && tested && px_tested) atomicAdd(px_tested, tested);
     }
+    edges.finish(flags);
 }
 
 // --------------------------------------------------------------- K2b -------
@@ -599,7 +638,8 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
 extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *nbr_in,
                                            int64_t m, int32_t k_in, int64_t first_row, const double *X,
                                            int64_t *nbr_out, uint8_t *vis, int32_t *packed,
-                                           int32_t packed_multicast, int32_t *flags) {
+                                           int32_t packed_multicast, const int64_t *rendezvous,
+                                           int32_t *flags) {
     SBP_NVTX("sbp_knn_edges_visible2d");
     SBP_REQUIRE(map && nodes && (m == 0 || (nbr_in && nbr_out && vis)), "sbp_knn_edges_visible2d: NULL argument");
     SBP_REQUIRE(nodes->d == 2, "sbp_knn_edges_visible2d: the 2-D checker needs a 2-D node store");
@@ -623,7 +663,20 @@ extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const
     const int threads = (smem && sbytes > 110 * 1024) ? 1024 : 512;
     const int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
     EdgeKnnRows src{nodes->d_soa, nodes->capacity, nodes->n, nbr_in, k_in, k_out, first_row,
-                    (const double2 *)X, nbr_out, packed, packed_multicast};
+                    (const double2 *)X, nbr_out, packed, packed_multicast,
+                    nullptr, nullptr, nullptr, nullptr, 0, 0};
+    if (rendezvous) {       // host array: sig_mc, sig_local, ticket, epoch (addresses), rank, world
+        SBP_REQUIRE(packed && packed_multicast, "sbp_knn_edges_visible2d: rendezvous needs the multicast output");
+        SBP_REQUIRE(rendezvous[0] && rendezvous[1] && rendezvous[2] && rendezvous[3] && rendezvous[5] >= 1 &&
+                        rendezvous[5] <= 64 && rendezvous[4] >= 0 && rendezvous[4] < rendezvous[5],
+                    "sbp_knn_edges_visible2d: bad rendezvous block");
+        src.sig_mc = (int32_t *)(uintptr_t)rendezvous[0];
+        src.sig_local = (const int32_t *)(uintptr_t)rendezvous[1];
+        src.ticket = (int32_t *)(uintptr_t)rendezvous[2];
+        src.epoch = (int32_t *)(uintptr_t)rendezvous[3];
+        src.rank = (int)rendezvous[4];
+        src.world = (int)rendezvous[5];
+    }
 #define SBP_LAUNCH_FUSED(SM)                                                                       \
     do {                                                                                           \
         int32_t rc = set_smem(k_visible2d_adaptive<SM, false, SM, EdgeKnnRows>, sbytes);           \

@@ -123,12 +123,18 @@ class PeerAdjacencyGather:
         self.stride = (self.block + 3) // 4 * 4                    # 16-byte aligned row offsets
         self.ctx = get_context(device)
         dev = torch.device("cuda", device)
-        self.buf = symm_mem.empty((2, self.world * self.stride), dtype=torch.int32, device=dev)
+        # per half: the world blocks + 64 ints of rendezvous signals (one per rank)
+        self._half_ints = self.world * self.stride + 64
+        self.buf = symm_mem.empty((2, self._half_ints), dtype=torch.int32, device=dev)
+        self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)                                   # every rank's signals are zero
+        self._state = torch.zeros(4, dtype=torch.int32, device=dev)   # CTA ticket, epoch of half 0 / 1
         base = [int(p) for p in self.hdl.buffer_ptrs]
         import ctypes as C
 
-        half = self.world * self.stride * 4
+        half = self._half_ints * 4
         self._ptrs = [(C.c_void_p * self.world)(*[b + h * half for b in base]) for h in (0, 1)]
         # NVSwitch multicast (NVLS) mapping of the same buffer, when the fabric offers it: the
         # block is then sent once and replicated by the switch
@@ -152,6 +158,19 @@ class PeerAdjacencyGather:
             raise RuntimeError("no multicast mapping: use gather()")
         return (int(self._mc[h].value) + self.rank * self.stride * 4, True)
 
+    def target_with_rendezvous(self, h: int):
+        """Like :meth:`target`, plus the block that makes the kernel itself meet the other ranks
+        (its last CTA publishes an epoch through the switch and waits for everyone's): after the
+        step the adjacency is complete on this rank, :meth:`view` needs no barrier."""
+        addr, mc = self.target(h)
+        sig_off = self.world * self.stride * 4
+        sync = (int(self._mc[h].value) + sig_off,                      # signals, multicast address
+                int(self.buf[h].data_ptr()) + sig_off,                 # signals, local address
+                int(self._state.data_ptr()),                           # CTA ticket
+                int(self._state.data_ptr()) + 4 * (1 + h),             # epoch of this half
+                self.rank, self.world)
+        return (addr, mc, sync)
+
     def complete(self, h: int):
         """Barrier after a step that wrote through :meth:`target` (h); returns the assembled
         int32 [world * m][k] block like :meth:`gather`."""
@@ -161,7 +180,7 @@ class PeerAdjacencyGather:
 
     def view(self, h: int):
         """The assembled int32 [world * m][k] block of buffer half ``h`` (no synchronisation)."""
-        out = self.buf[h].view(self.world, self.stride)[:, : self.block]
+        out = self.buf[h][: self.world * self.stride].view(self.world, self.stride)[:, : self.block]
         return out.reshape(self.world, self.m, self.k).reshape(self.world * self.m, self.k)
 
     def gather(self, nbr, vis):
@@ -186,9 +205,7 @@ class PeerAdjacencyGather:
                                                               self._ptrs[h], self.world, self.rank * self.stride),
                        "sbp_adjacency_peer_scatter")
         self.hdl.barrier(channel=h)
-        out = self.buf[h].view(self.world, self.stride)[:, : self.block]
-        return out.reshape(self.world * self.m, self.k) if self.stride == self.block else \
-            out.reshape(self.world, self.m, self.k).reshape(self.world * self.m, self.k)
+        return self.view(h)
 
 
 def sharded_visible_batch(visible_fn, P, Q, group=None, costs=None):

@@ -159,6 +159,8 @@ def ptr(a):
 
 def raise_for_flags(flags: int, what: str, nan_is_error: bool = True) -> None:
     """Surface what CPython would have raised for the batch."""
+    if flags & _lib.FLAG_PEER_TIMEOUT:
+        raise RuntimeError(f"{what}: a peer rank never signalled the in-kernel rendezvous")
     if flags & _lib.FLAG_OVERFLOW:
         raise OverflowError(f"{what}: cannot convert float infinity to integer")
     if nan_is_error and flags & _lib.FLAG_NAN:

@@ -70,6 +70,20 @@ def _worker(rank, world, port, q):
                 want_n, want_v = D.all_gather_adjacency(nbr, vis)
                 got_n, got_v = D.unpack_adjacency(packed)
                 assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), ("fused", step)
+            # ... and with the rendezvous inside the kernel: no barrier launch at all
+            kinds.add("fused + in-kernel rendezvous")
+            ag2 = D.PeerAdjacencyGather(m, k, device=rank)
+            for step in range(6):
+                Xq = torch.from_numpy(np.random.default_rng(200 * step + rank).random((m, 2)) * [W, H]).to(dev)
+                h = step & 1
+                if rank == step % world:
+                    torch.cuda._sleep(20_000_000)               # a late rank: the others must wait for it
+                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=Xq, packed_out=ag2.target_with_rendezvous(h))
+                packed = ag2.view(h).clone()                    # same stream: after the kernel returned
+                cc.check_device_flags("rendezvous")
+                want_n, want_v = D.all_gather_adjacency(nbr, vis)
+                got_n, got_v = D.unpack_adjacency(packed)
+                assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), ("rendezvous", step)
         dist.barrier()
         dist.destroy_process_group()
         print("exchange kinds exercised:", sorted(kinds), flush=True)
