@@ -161,10 +161,14 @@ int32_t sbp_nodes_rows_device(sbp_nodes *nodes, int64_t first, int64_t count, do
 
 /* replaces: RRTPlanner.find_nearest_neighbour_idx (rrtPlanner.py:268-279) for
  * k = 1 and the np.argsort(distances)[:k] candidate lists (rrtPlanner.py:151-152,
- * :226-227) for k > 1: brute force over all nodes, d = sqrt_rn of the
+ * :226-227) for k > 1: the k nearest of ALL nodes, d = sqrt_rn of the
  * left-to-right unfused sum of squares over all dims, ordered by (d, index).
+ * (How: batches of >= 256 queries over >= 2048 nodes are answered exactly from a cell
+ * grid built inside the call, with the brute-force scan behind it for the queries the
+ * grid cannot settle; fewer queries / nodes are scanned by brute force.  Same rows
+ * either way -- DESIGN.md 3a.)
  * X: device [m][dim].  idx: device [m][k] int64, dist: device [m][k] fp64
- * (nullable); rows are padded with -1 / +inf when size < k.  1 <= k <= 64.
+ * (nullable); rows are padded with -1 / +inf when size < k.  1 <= k <= 32.
  * precision: 64 only (bit-exact); 32 is reserved. */
 int32_t sbp_nodes_knn(sbp_nodes *nodes, const double *X, int64_t m, int32_t k,
                       int32_t precision, int64_t *idx, double *dist);

@@ -1,6 +1,8 @@
-// knn.cu -- K4: brute-force k-nearest-neighbour queries on the node store: seeded filter +
-// exact refine for batches (filter.cuh), thread-per-query scan with per-thread top-k as the
-// general / fallback kernel, CTA-per-query scan with shuffle merge for few queries.
+// knn.cu -- K4: k-nearest-neighbour queries on the node store.  Batches are answered exactly
+// from a uniform cell grid built inside the call (k_knn_cells_t: thread per query, k_knn_cells:
+// warp per query); behind it, for the queries the grid cannot settle, the brute-force path:
+// seeded filter + exact refine (filter.cuh), thread-per-query scan with per-thread top-k as the
+// general / fallback kernel; CTA-per-query scan with shuffle merge for few queries.
 //
 // Reference behaviour restated (file:line under /root/reference/sbp_env/):
 //   RRTPlanner.find_nearest_neighbour_idx     planners/rrtPlanner.py:268-279
