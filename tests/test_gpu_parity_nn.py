@@ -169,6 +169,11 @@ def test_fused_knn_edges_visible_equals_the_two_launch_form(sg, map_name, n_node
         nbr_p, vis_p = cc.knn_edges_visible(t, idx, first_row=first, queries=queries, packed_out=code)
         assert torch.equal(nbr_p, nbr_b) and torch.equal(vis_p, vis_b)
         assert torch.equal(code, sg.distributed.pack_adjacency(nbr_b, vis_b))
+        # ... also when the destination is pinned host memory (zero-copy stores, bench.py e2e)
+        code_h = torch.full((count, k), -7, dtype=torch.int32).pin_memory()
+        cc.knn_edges_visible(t, idx, first_row=first, queries=queries, packed_out=(code_h.data_ptr(), False))
+        torch.cuda.synchronize()
+        assert torch.equal(code_h, code.cpu())
     # forced global-memory map path gives the same answer
     from sbp_env_b200 import _lib
 
