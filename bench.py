@@ -462,9 +462,9 @@ def run_ours(args):
     n_nodes = float(len(tree))
     # Dominant kernel: k_knn_cells_t (exact kNN from the cell grid, one thread per query).
     # ALGORITHMIC bytes per launch = every byte it has to touch once: node coordinates (16 B) and
-    # cell-sorted ids (4 B) per node, the cell starts (one int per cell, 3 nodes per cell), the
+    # cell-sorted ids (4 B) per node, the cell starts (one int per cell, 1.5 nodes per cell), the
     # query rows (16 B) and per query the index row ((k + 1) x 8 B), its seed (8 B) and flag (1 B).
-    alg_cells = n_nodes * (16 + 4 + 4.0 / 3.0) + m * (16 + kq * 8 + 9)
+    alg_cells = n_nodes * (16 + 4 + 4.0 / 1.5) + m * (16 + kq * 8 + 9)
     roof = {"kernel": f"k_knn_cells_t<2,{kq}> (exact kNN from the cell grid, one thread per query; "
                       f"{100 * cells_ms / sum(ph.values()):.0f}% of the step)",
             "bound": "hbm", "achieved": alg_cells / cells_s / 1e9, "peak": hbm_peak, "unit": "GB/s",

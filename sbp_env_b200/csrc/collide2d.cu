@@ -512,7 +512,7 @@ int g_coop_below = 12;     // adaptive kernel: cap of the hand-over threshold (w
 int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
 extern int g_arm_group, g_near_filter;
 extern int g_knn_chunks, g_knn_prefilter, g_knn_seed, g_knn_filter, g_knn_filter_chunks, g_knn_filter_variant;
-extern int g_knn_cells, g_knn_cells_limit, g_knn_cell_density, g_knn_cells_qpw, g_knn_cells_order;
+extern int g_knn_cells, g_knn_cells_limit, g_knn_cell_density, g_knn_cells_qpw, g_knn_cells_order, g_knn_cells_rinit;
 
 int g_time_kernels = 0;    // bench instrumentation: event pairs around the dominant kNN kernel
 
@@ -545,6 +545,7 @@ extern "C" int32_t sbp_tune(const char *key, int64_t value) {
     if (!strcmp(key, "knn_filter_chunks")) { g_knn_filter_chunks = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_filter_variant")) { g_knn_filter_variant = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_cells")) { g_knn_cells = (int)value; return SBP_OK; }
+    if (!strcmp(key, "knn_cells_rinit")) { g_knn_cells_rinit = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_cells_order")) { g_knn_cells_order = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_cells_qpw")) { g_knn_cells_qpw = (int)value; return SBP_OK; }
     if (!strcmp(key, "knn_cell_density")) { g_knn_cell_density = (int)value; return SBP_OK; }

@@ -1288,8 +1288,9 @@ int g_knn_cells = 2;          // tuning knob: exact answers from the cell grid w
                               // (0 = off, 1 = warp per query, 2 = thread per query when >= 20000 queries, 3 = always)
 int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes (thread per query: a quarter)
 int g_knn_cells_qpw = 0;      // tuning knob: queries per warp of k_knn_cells_t (0 = 32)
+int g_knn_cells_rinit = 0;    // tuning knob: first ring radius of k_knn_cells_t (0 = from the density)
 int g_knn_cells_order = 1;    // tuning knob: cell-sorted query order when m == n (results unchanged)
-int g_knn_cell_density = 300; // tuning knob: nodes per grid cell x 100
+int g_knn_cell_density = 150; // tuning knob: nodes per grid cell x 100
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
@@ -1387,10 +1388,12 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             // form, 16 384 queries 73 / 74 us, 50 000 queries 137 / 71 us: a one-warp CTA's chain of
             // 32 queries takes ~50 us however few CTAs there are)
             if (g_knn_cells >= 3 || (g_knn_cells == 2 && m >= 20000)) {
-                // first ring radius whose block is expected to hold K nodes
+                // first ring radius whose block is expected to hold 2 K nodes (then the rectangle of
+                // the K-th distance usually lies inside the block and there is no second pass)
                 const double per_cell = (double)n / ((double)G * (double)G);
-                int r_init = (int)ceil((sqrt((double)K / per_cell) - 1.0) / 2.0);
+                int r_init = (int)ceil((sqrt(2.0 * (double)K / per_cell) - 1.0) / 2.0);
                 r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
+                if (g_knn_cells_rinit > 0) r_init = g_knn_cells_rinit;
                 int qpw = g_knn_cells_qpw;
                 // (measured on cfg2: 16 / 8 queries per warp take 0.094 / 0.113 ms instead of 0.075:
                 // the kernel is bound by the instructions it issues, not by the length of a warp's chain)

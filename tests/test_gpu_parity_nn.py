@@ -445,7 +445,7 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
             for mode, order in ((3, 1), (3, 0), (2, 1)):
                 lib.sbp_tune(b"knn_cells", mode)
                 lib.sbp_tune(b"knn_cells_limit", 1024)
-                lib.sbp_tune(b"knn_cell_density", 300)
+                lib.sbp_tune(b"knn_cell_density", 150)
                 lib.sbp_tune(b"knn_cells_order", order)
                 idx, dist = t.knn(Xs, 11)
                 assert np.array_equal(idx, ei), (layout, d, mode, order)
@@ -453,7 +453,7 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
     finally:
         lib.sbp_tune(b"knn_cells", 2)
         lib.sbp_tune(b"knn_cells_limit", 1024)
-        lib.sbp_tune(b"knn_cell_density", 300)
+        lib.sbp_tune(b"knn_cell_density", 150)
         lib.sbp_tune(b"knn_cells_order", 1)
 
 
