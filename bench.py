@@ -44,9 +44,9 @@ UNIT = "edges/s"
 FILTER_DRAM_TRAFFIC = 18273024
 # the same for one k_knn_cells_t launch (profiles/r1_knn_cells_full.txt), and that capture's
 # instruction / L1 sector counts (static facts about the kernel on this workload)
-CELLS_DRAM_TRAFFIC = 1895680
-CELLS_NCU = {"warp_instructions": 15051976, "l1_global_load_sectors": 1680584,
-             "issue_active_pct": 39.5, "threads_per_instruction": 20.7, "warps_per_sm": 8.4,
+CELLS_DRAM_TRAFFIC = 1956864
+CELLS_NCU = {"warp_instructions": 15318739, "l1_global_load_sectors": 2879287,
+             "issue_active_pct": 39.4, "threads_per_instruction": 21.8, "warps_per_sm": 9.0,
              "source": "profiles/r1_knn_cells_full.txt"}
 WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
             "candidate edges per step (exact kNN of 50000 rows among 50000 nodes = 2.5e9 pairs + Bresenham visible_batch)")
