@@ -18,8 +18,8 @@ for n in (50_000, 1_000_000):
     tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * torch.tensor([579., 581.], device=dev, dtype=torch.float64))
     X = tree.rows_device(0, n)
     ref = None
-    for mode, dens, qpw in ((3, 300, 0), (3, 300, 2), (3, 100, 2), (3, 100, 3), (3, 200, 2), (3, 150, 2), (3, 600, 1), (3, 1000, 1)):
-        lib.sbp_tune(b"knn_cells", mode); lib.sbp_tune(b"knn_cell_density", dens); lib.sbp_tune(b"knn_cells_rinit", qpw)
+    for mode, dens, qpw in ((3, 150, 32), (3, 150, 28), (3, 150, 24), (3, 150, 20), (3, 150, 18), (3, 150, 16)):
+        lib.sbp_tune(b"knn_cells", mode); lib.sbp_tune(b"knn_cell_density", dens); lib.sbp_tune(b"knn_cells_qpw", qpw)
         gr = torch.cuda.CUDAGraph()
         tree.knn(X, 11, return_dist=False); torch.cuda.synchronize()
         with torch.cuda.graph(gr):
@@ -27,4 +27,4 @@ for n in (50_000, 1_000_000):
         ms = timeit(gr.replay)
         idx = out[0] if isinstance(out, tuple) else out
         if ref is None: ref = idx.clone()
-        print(n, "mode", mode, "density", dens, "rinit", qpw, "ms %.4f" % ms, "same", bool(torch.equal(ref, idx)), flush=True)
+        print(n, "mode", mode, "density", dens, "qpw", qpw, "ms %.4f" % ms, "same", bool(torch.equal(ref, idx)), flush=True)
