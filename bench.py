@@ -399,14 +399,18 @@ def run_ours(args):
     e2e_copy = os.environ.get("BENCH_E2E_COPY", "0") == "1"
 
     def e2e_body():
-        x_dev.copy_(pinned, non_blocking=True)             # H2D of this step's samples
+        # H2D of this step's samples: rank 0 rebuilds its roadmap from them, and the append kernel
+        # reads the pinned host rows itself (zero-copy: transfer and AoS -> SoA conversion in one
+        # launch; BENCH_E2E_COPY=1: explicit copy first); ranks > 0 query with them, so they are copied
+        if rank != 0 or e2e_copy:
+            x_dev.copy_(pinned, non_blocking=True)
         # D2H of the adjacency block: the visibility kernel packs it and (default) stores it straight
         # into the pinned host buffer -- mapped into the device's address space (UVA) -- as the edges
         # are decided, so the transfer overlaps the kernel; BENCH_E2E_COPY=1: device buffer + copy
         dst = code_dev if e2e_copy else (code_h.data_ptr(), False)
         if rank == 0:
             tree2.truncate(0)
-            tree2.extend(x_dev)                            # roadmap rebuilt from the samples
+            tree2.extend(x_dev if e2e_copy else pinned)    # roadmap rebuilt from the samples
             sg.prm_connect_knn(cc, tree2, k, packed_out=dst)
         else:
             sg.prm_connect_knn(cc, tree, k, queries=x_dev, packed_out=dst)
@@ -630,7 +634,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(code_h.numel() * 4),
                 "result": "packed adjacency int32 [m][k] = (neighbour + 1) * 2 + visible",
                 "d2h": "copy from a device buffer" if e2e_copy else
-                       "stored by the visibility kernel straight into the pinned host buffer (zero-copy)"},
+                       "stored by the visibility kernel straight into the pinned host buffer (zero-copy)",
+                "h2d": "copy into a device buffer" if (e2e_copy or rank != 0) else
+                       "read from the pinned host buffer by the node-store append kernel (zero-copy)"},
         "gpu_launches": int(launches),
         "gpu_launches_per_step": int(launches_per_step),
         "adjacency_gather": gather_kind,

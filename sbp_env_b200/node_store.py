@@ -49,7 +49,13 @@ class NodeStore:
 
     def extend(self, X) -> None:
         """Bulk append of rows (RRdT* ``extend_tree``, rrdtPlanner.py:878-887)."""
+        if _is_torch_tensor(X) and not X.is_cuda and not X.is_pinned():
+            X = X.detach().numpy()                        # pageable host tensor: the host path below
         if _is_torch_tensor(X):
+            # CUDA tensor, or PINNED host tensor: pinned memory is mapped into the device's address
+            # space (UVA), so the append kernel reads it over PCIe itself -- the host-to-device
+            # transfer and the AoS -> SoA conversion are one asynchronous, graph-capturable launch
+            # (the caller must keep the tensor unchanged until the stream has passed the launch)
             self.ctx.use_torch_stream()
             X = as_device_f64(X, self.dim)
             check(_lib.load().sbp_nodes_append(self._h, ptr(X), X.shape[0], 1), "sbp_nodes_append")

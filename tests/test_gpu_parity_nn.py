@@ -188,6 +188,23 @@ def test_fused_knn_edges_visible_equals_the_two_launch_form(sg, map_name, n_node
     assert torch.equal(nbr_c, nbr_d) and torch.equal(vis_c, vis_d)
 
 
+def test_store_extend_from_pinned_and_pageable_host_tensors(sg):
+    """A pinned host tensor is read by the append kernel itself (zero-copy), a pageable one goes
+    through the host path: same store either way."""
+    import torch
+
+    rng = np.random.default_rng(12)
+    pts = rng.random((5000, 2)) * 300
+    stores = []
+    for src in (torch.from_numpy(pts).pin_memory(), torch.from_numpy(pts.copy()), torch.from_numpy(pts).cuda(), pts):
+        t = sg.NodeStore(2)
+        t.extend(src)
+        torch.cuda.synchronize()
+        stores.append(t.rows_device(0, len(t)).cpu().numpy())
+    for a in stores:
+        assert np.array_equal(a, pts)
+
+
 def test_empty_store_and_truncate(sg):
     t = sg.NodeStore(2)
     idx, dist = t.knn(np.zeros((3, 2)), 2)
