@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SBP_ABI_VERSION 1
+#define SBP_ABI_VERSION 2
 
 /* status codes */
 #define SBP_OK 0
@@ -71,6 +71,28 @@ int32_t sbp_ctx_set_stream(sbp_ctx *ctx, void *stream);
 int32_t sbp_ctx_sync(sbp_ctx *ctx);
 /* number of SMs of the context's device and kernels launched so far */
 int32_t sbp_ctx_info(sbp_ctx *ctx, int32_t *sm_count, int64_t *launches);
+/* Counter that changes whenever one of the context's internal work buffers is reallocated
+ * (a later call needed more room).  A CUDA graph captured from calls of this library froze the
+ * old addresses: compare the value taken at capture time before every replay and recapture
+ * when it moved (planning.CapturedStep does). */
+int32_t sbp_ctx_scratch_generation(sbp_ctx *ctx, int64_t *generation);
+
+/* ---- instrumentation (never changes a result) ----------------------------------
+ * Tuning knobs, PER CONTEXT: key is one of visible_group, coop_below, force_global, arm_group,
+ * near_filter, knn_seed, knn_chunks, knn_prefilter, knn_filter, knn_filter_chunks,
+ * knn_filter_variant, knn_cells, knn_cells_limit, knn_cells_qpw, knn_cells_rinit,
+ * knn_cells_order, knn_cell_density, time_kernels (csrc/common.cuh: sbp_tuning). */
+int32_t sbp_ctx_tune(sbp_ctx *ctx, const char *key, int64_t value);
+/* With time_kernels = 1 (k_knn_filter), 2 (k_knn_cells*) or 3 (2-D visibility kernel) every
+ * launch of that kernel is bracketed by a CUDA event pair on the launching stream; this returns
+ * the summed milliseconds and the number of pairs since the last call (synchronises). */
+int32_t sbp_ctx_kernel_time(sbp_ctx *ctx, double *total_ms, int64_t *launches);
+/* Measured denominators for the rooflines (csrc/microbench.cu): which = 0 shared-memory word
+ * gathers, 1 random 32-byte sector gathers over `bytes` of global memory, 2 unfused fp64
+ * mul/add, 3 packed fp32 FMA, 5-7 min/compare mixes.  *ms = time of `iters` iterations,
+ * *units = operations performed. */
+int32_t sbp_microbench(sbp_ctx *ctx, int32_t which, int64_t bytes, int32_t iters, double *ms,
+                       double *units);
 
 /* ---- occupancy map -------------------------------------------------------
  * replaces: ImgCollisionChecker.__init__ / RobotArm4dCollisionChecker.__init__
@@ -268,17 +290,33 @@ int32_t sbp_graph_create(sbp_ctx *ctx, int64_t n_nodes, sbp_graph **out);
 int32_t sbp_graph_destroy(sbp_graph *g);
 /* (Re)build from a candidate-edge block of sbp_nodes_knn_edges + the visibility bytes of
  * sbp_visible2d / sbp_arm_visible (device pointers, [m][k]): for row i and column j with
- * vis != 0 and nbr >= 0 the directed edge nbr[i][j] -> first_row + i (m_g -> v). */
+ * vis != 0 and nbr >= 0 the arc nbr[i][j] -> first_row + i (m_g -> v).
+ * undirected != 0 also adds first_row + i -> nbr[i][j]: the reference's radius rule is symmetric
+ * (v in near(u) <=> u in near(v)), so its DiGraph holds both (m_g -> v) and (v -> m_g)
+ * (prmPlanner.py:91-101), which a k-NN candidate set does not give by itself.  A mirrored arc
+ * that the block already holds in its own right is not stored twice. */
 int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis, int64_t m,
-                            int32_t k, int64_t first_row);
-/* (Re)build from explicit edge lists src[e] -> dst[e] (device), `keep` an optional mask. */
+                            int32_t k, int64_t first_row, int32_t undirected);
+/* The same from the packed adjacency (nbr + 1) * 2 + vis, one int32 per candidate [m][k]: what
+ * sbp_knn_edges_visible2d / sbp_prm_connect2d write and what the multi-GPU exchange assembles
+ * on every rank. */
+int32_t sbp_graph_build_packed(sbp_graph *g, const int32_t *packed, int64_t m, int32_t k,
+                               int64_t first_row, int32_t undirected);
+/* (Re)build from explicit arc lists src[e] -> dst[e] (device), `keep` an optional mask;
+ * undirected != 0 adds dst[e] -> src[e] too (duplicates in the list are kept). */
 int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,
-                              const uint8_t *keep, int64_t e);
+                              const uint8_t *keep, int64_t e, int32_t undirected);
 int32_t sbp_graph_info(sbp_graph *g, int64_t *n_nodes, int64_t *n_edges);   /* synchronises */
 /* Copy the CSR arrays to device buffers row_ptr [n_nodes + 1], col [col_capacity >= n_edges]
  * (col may be NULL); the order of a row's entries is unspecified. */
 int32_t sbp_graph_csr(sbp_graph *g, int64_t *row_ptr, int32_t *col, int64_t col_capacity);
-/* Batched fewest-hop paths start[q] -> goal[q] (device int64 [nq]), one CTA per query.
+/* Weakly connected components (union-find over the arcs): labels (device int32 [n], nullable) =
+ * smallest node index of each node's component; *n_components (HOST, nullable; synchronises).
+ * nx.has_path(u, v) (prmPlanner.py:141) needs label[u] == label[v] -- and that suffices when the
+ * graph was built undirected -- so sbp_graph_bfs settles every query with different labels
+ * without a search. */
+int32_t sbp_graph_components(sbp_graph *g, int32_t *labels, int64_t *n_components);
+/* Batched fewest-hop paths start[q] -> goal[q] (device int64 [nq]), one CTA per searched query.
  * hops [nq]: number of edges, 0 when start == goal, -1 when unreachable (nx.has_path False)
  * or an index is out of range.  paths (optional) [nq][max_len]: node indices start..goal,
  * -1 padded; all -1 when there is no path or it has more than max_len nodes.  Among the

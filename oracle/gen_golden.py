@@ -17,7 +17,15 @@ functions (imported through oracle/ref_shims.py, nothing copied):
                 prmPlanner.nearest_neighbours (prmPlanner.py:28-44),
                 engine.euclidean_dist (engine.py:13-24), np.linalg.norm rows
 
-The GPU box has no /root/reference; tests there read only these fixtures.
+  planner.npz   whole seeded planner runs of the UNMODIFIED planners (rows a13-a17): RRT* on
+                room1 -- the sample stream, per step nearest index / accepted flag, and the final
+                parent / cost arrays (rrtPlanner.py:68-104, :173-196); the same run with the
+                LINEAR rewire variant switched on (rrtPlanner.py:250-266, `use_rtree=False`);
+                the Bi-RRT join test per accepted node (birrtPlanner.py:82-87); RRdT*'s
+                find_nearest_node_from_neighbour on a snapshot of its trees (rrdtPlanner.py:
+                685-721); PRMPlanner.build_graph edge list + get_solution (prmPlanner.py:80-154)
+
+The GPU box has no /root/reference; the fixture tests there read only these files.
 """
 from __future__ import annotations
 
@@ -270,6 +278,195 @@ def gen_nn(ref):
     np.savez_compressed(os.path.join(GOLDEN, "nn.npz"), **out)
 
 
+def _quiet_tqdm():
+    from functools import partialmethod
+
+    from tqdm import tqdm
+
+    tqdm.__init__ = partialmethod(tqdm.__init__, disable=True)
+
+
+def gen_planner(ref):
+    """Trajectory fixtures: everything below is produced by the reference's own planner code."""
+    sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tests"))
+    import _refrun
+    from sbp_env import engine
+    from sbp_env.planners.rrtPlanner import RRTPlanner
+    from sbp_env.utils.common import Node
+
+    _quiet_tqdm()
+    out = {}
+    room1 = ref_shims.reference_map_path("room1.png")
+    fac = lambda args: engine.ImageEngine(args, room1)
+
+    def index_map(nodes):
+        return {id(n): i for i, n in enumerate(nodes)}
+
+    def parents_of(nodes, extra=()):
+        ix = index_map(nodes)
+        for i, n in enumerate(extra):
+            ix.setdefault(id(n), -2 - i)
+        return np.array([-1 if n.parent is None else ix.get(id(n.parent), -9) for n in nodes], np.int64)
+
+    # ---- (A) RRT*, shipped behaviour (rewire is a no-op, SURVEY.md D2); (B) linear rewire on
+    for tag, linear_rewire in (("rrt", False), ("rrtrw", True)):
+        rec = dict(rand=[], nn=[], accept=[])
+
+        def hook(env, rec=rec, linear_rewire=linear_rewire):
+            pl = env.planner
+            smp = env.args.sampler
+            inner_next = smp.get_valid_next_pos
+            inner_nn = pl.find_nearest_neighbour_idx
+
+            def get_valid_next_pos():
+                r = inner_next()
+                rec["rand"].append(np.array(r[0], dtype=np.float64))
+                rec["accept"].append(False)
+                return r
+
+            def find_nn(pos, poses):
+                i = inner_nn(pos, poses)
+                rec["nn"].append(int(i))
+                return i
+
+            inner_add = pl.add_newnode
+
+            def add_newnode(node):
+                if rec["accept"]:
+                    rec["accept"][-1] = True
+                return inner_add(node)
+
+            smp.get_valid_next_pos = get_valid_next_pos
+            pl.find_nearest_neighbour_idx = find_nn
+            pl.add_newnode = add_newnode
+            if linear_rewire:
+                pl.rewire = lambda newnode, nodes, **kw: RRTPlanner.rewire(pl, newnode, nodes, use_rtree=False)
+
+        r = _refrun.run("rrt", fac, None, "100,100", "350,350", 500, before_run=hook)
+        pl = r["env"].planner
+        T = len(rec["rand"])
+        assert len(rec["nn"]) == T
+        out[f"{tag}_rand"] = np.array(rec["rand"])
+        out[f"{tag}_nn"] = np.array(rec["nn"], np.int64)
+        out[f"{tag}_accept"] = np.packbits(np.array(rec["accept"], bool))
+        out[f"{tag}_steps"] = np.array(T)
+        out[f"{tag}_poses"] = r["poses"]
+        out[f"{tag}_parent"] = parents_of(pl.nodes)
+        out[f"{tag}_cost"] = np.array([float(n.cost) for n in pl.nodes])
+        out[f"{tag}_c_max"] = np.array(float(pl.c_max))
+        out[f"{tag}_counters"] = np.array(r["counters"], np.int64)
+        out[f"{tag}_params"] = np.array([pl.args.epsilon, pl.args.radius, pl.args.goal_radius], np.float64)
+        out[f"{tag}_goal"] = np.array(pl.goal_pt.pos, np.float64)
+        print(tag, "steps", T, "nodes", r["n"], "c_max", pl.c_max, "counters", r["counters"])
+
+    # ---- (C) Bi-RRT join test per accepted node, up to and including the join
+    rec = dict(tree=[], newpos=[], join=[])
+
+    def hook_bi(env):
+        pl = env.planner
+        cc = pl.args.engine.cc
+        inner_vis = cc.visible
+        state = dict(last_two=[])
+
+        inner_run = pl.run_once
+
+        def run_once():
+            was_found = pl.found_solution
+            n0, n1 = len(pl.nodes), len(pl.goal_tree_nodes)
+            turn_goal = pl.goal_tree_turn and not pl.found_solution
+            inner_run()
+            if was_found:
+                return
+            grew = len(pl.goal_tree_nodes) > n1 if turn_goal else len(pl.nodes) > n0
+            if not grew:
+                return
+            own_nodes = pl.goal_tree_nodes if turn_goal else pl.nodes
+            own_n0 = n1 if turn_goal else n0
+            newpos = np.array(own_nodes[own_n0].pos, dtype=np.float64)
+            other_poses = pl.poses[:n0] if turn_goal else pl.goal_tree_poses[:n1]
+            d = np.linalg.norm(other_poses - newpos, axis=1)            # birrtPlanner.py:82-84
+            j = -1
+            if min(d) < pl.args.epsilon:
+                i = int(np.argmin(d))
+                if pl.found_solution:                                    # the planner joined here
+                    j = i
+            rec["tree"].append(1 if turn_goal else 0)
+            rec["newpos"].append(newpos)
+            rec["join"].append(j)
+
+        pl.run_once = run_once
+
+    r = _refrun.run("birrt", fac, None, "100,100", "350,350", 500, before_run=hook_bi)
+    pl = r["env"].planner
+    out["bi_tree"] = np.array(rec["tree"], np.int64)
+    out["bi_newpos"] = np.array(rec["newpos"])
+    out["bi_join"] = np.array(rec["join"], np.int64)
+    out["bi_start"], out["bi_goal"] = np.array(pl.start_pt.pos, np.float64), np.array(pl.goal_pt.pos, np.float64)
+    out["bi_eps"] = np.array(float(pl.args.epsilon))
+    out["bi_found"] = np.array(bool(pl.found_solution))
+    print("birrt accepted before/at join", len(rec["tree"]), "joined at", int(np.flatnonzero(np.array(rec["join"]) >= 0)[0])
+          if (np.array(rec["join"]) >= 0).any() else None, "found", pl.found_solution)
+
+    # ---- (D) RRdT*: neighbour search over a snapshot of the disjoint trees
+    r = _refrun.run("rrdt", fac, None, "100,100", "350,350", 400)
+    pl = r["env"].planner
+    trees = [*pl._disjointed_trees, pl.root]
+    sizes = [len(t.nodes) for t in trees]
+    out["rrdt_tree_off"] = np.cumsum([0] + sizes).astype(np.int64)
+    out["rrdt_tree_poses"] = np.concatenate([np.array(t.poses[: len(t.nodes)]) for t in trees])
+    rng = np.random.default_rng(5)
+    W, H = pl.args.engine.cc._img.shape
+    Q = rng.random((300, 2)) * [W, H]
+    Q[:100] = out["rrdt_tree_poses"][rng.integers(0, len(out["rrdt_tree_poses"]), 100)] + rng.standard_normal((100, 2)) * 4
+    own = rng.integers(-1, len(trees), len(Q))
+    res_off, res = [0], []
+    for q, o in zip(Q, own):
+        lst = pl.find_nearest_node_from_neighbour(Node(q), None if o < 0 else trees[o], pl.args.epsilon)
+        for nd, tr in lst:
+            ti = next(i for i, t in enumerate(trees) if t is tr)
+            res.append((ti, next(i for i, n in enumerate(tr.nodes) if n is nd)))
+        res_off.append(len(res))
+    out["rrdt_Q"], out["rrdt_own"] = Q, own.astype(np.int64)
+    out["rrdt_res_off"] = np.array(res_off, np.int64)
+    out["rrdt_res"] = np.array(res, np.int64).reshape(-1, 2)
+    out["rrdt_eps"] = np.array(float(pl.args.epsilon))
+    print("rrdt trees", sizes, "hits", len(res))
+
+    # ---- (E) PRM: build_graph edge list (insertion order) + get_solution
+    r = _refrun.run("prm", fac, None, "100,100", "350,350", 700)
+    pl = r["env"].planner
+    pl.build_graph()
+    ix = index_map(pl.nodes)
+    e = [(ix[id(u)], ix[id(v)], w["weight"]) for u, v, w in pl.graph.edges(data=True) if id(u) in ix and id(v) in ix]
+    n = len(pl.nodes)
+    out["prm_poses"] = r["poses"]
+    out["prm_radius"] = np.array(float(pl.gamma * np.power(np.log(n + 1) / (n + 1), 1 / 2)))
+    out["prm_edges"] = np.array([(a, b) for a, b, _ in e], np.int64)
+    out["prm_weights"] = np.array([w for _, _, w in e])
+    sol = pl.get_solution()
+    import networkx as nx
+
+    goal = pl.args.env.goal_pt.parent
+    start = next((nd for nd in pl.nodes if nd.parent is pl.args.env.start_pt), None)
+    out["prm_c_max"] = np.array(float(sol))
+    out["prm_start_goal"] = np.array([-1 if start is None else ix[id(start)], -1 if goal is None else ix[id(goal)]], np.int64)
+    out["prm_hops"] = np.array(-1 if start is None or goal is None else nx.shortest_path_length(pl.graph, start, goal))
+    out["prm_query"] = np.array([pl.args.sampler.start_pos, pl.args.sampler.goal_pos], np.float64)
+    out["prm_eps"] = np.array(float(pl.args.epsilon))
+    # hop counts of a batch of node pairs (nx.shortest_path_length, -1 = no path)
+    rng = np.random.default_rng(6)
+    pairs = rng.integers(0, n, (200, 2))
+    hops = []
+    for a, b in pairs:
+        try:
+            hops.append(nx.shortest_path_length(pl.graph, pl.nodes[a], pl.nodes[b]))
+        except (nx.NetworkXNoPath, nx.NodeNotFound):      # an isolated node was never added
+            hops.append(-1)
+    out["prm_pairs"], out["prm_pair_hops"] = pairs.astype(np.int64), np.array(hops, np.int64)
+    print("prm nodes", n, "edges", len(e), "c_max", sol, "hops", int(out["prm_hops"]))
+    np.savez_compressed(os.path.join(GOLDEN, "planner.npz"), **out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = ref_shims.import_reference()
@@ -278,6 +475,7 @@ def main():
     gen_img_cc(ref)
     gen_arm_cc(ref)
     gen_nn(ref)
+    gen_planner(ref)
     for f in sorted(os.listdir(GOLDEN)):
         print(f, os.path.getsize(os.path.join(GOLDEN, f)))
 

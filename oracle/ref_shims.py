@@ -6,9 +6,11 @@ docopt, SALib).  None of them takes part in the collision / nearest-neighbour
 arithmetic, so they are replaced by inert stand-ins in ``sys.modules`` and the
 reference is then imported from where it lies (nothing is copied).
 
-Used by ``oracle/gen_golden.py`` (fixture generation) and by the container-only
-cross-checks in ``tests/`` (skipped when ``/root/reference`` is absent, as it
-is on the GPU box).  Never imported by the product package.
+Used by ``oracle/gen_golden.py`` (fixture generation), by the cross-checks in
+``tests/`` and by the reference arm of ``bench.py``.  On the GPU box ``/root/reference``
+does not exist: there the untouched copy staged by ``oracle/stage_ref.py`` under
+``oracle/_ref/`` (git-ignored, shipped by gpurun) is imported instead; tests that need
+the reference are skipped when neither is present.  Never imported by the product package.
 """
 from __future__ import annotations
 
@@ -17,7 +19,20 @@ import sys
 import types
 from unittest import mock
 
-REFERENCE_ROOT = os.environ.get("SBP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+STAGED_ROOT = os.path.join(_HERE, "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("SBP_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isdir("/root/reference/sbp_env"):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

@@ -73,23 +73,25 @@ _SIGNATURES = {
                                     _i32, C.POINTER(_i32), C.POINTER(_i32)],
     "sbp_graph_create": [_vp, _i64, C.POINTER(_vp)],
     "sbp_graph_destroy": [_vp],
-    "sbp_graph_build_knn": [_vp, _vp, _vp, _i64, _i32, _i64],
-    "sbp_graph_build_edges": [_vp, _vp, _vp, _vp, _i64],
+    "sbp_graph_build_knn": [_vp, _vp, _vp, _i64, _i32, _i64, _i32],
+    "sbp_graph_build_packed": [_vp, _vp, _i64, _i32, _i64, _i32],
+    "sbp_graph_build_edges": [_vp, _vp, _vp, _vp, _i64, _i32],
+    "sbp_graph_components": [_vp, _vp, C.POINTER(_i64)],
     "sbp_graph_info": [_vp, C.POINTER(_i64), C.POINTER(_i64)],
     "sbp_graph_csr": [_vp, _vp, _vp, _i64],
     "sbp_graph_bfs": [_vp, _vp, _vp, _i64, _vp, _vp, _i32],
     "sbp_adjacency_peer_scatter": [_vp, _vp, _vp, _i64, _vp, _i32, _i64],
     "sbp_adjacency_multicast": [_vp, _vp, _vp, _i64, _vp, _i64],
-    "sbp_tune": [C.c_char_p, _i64],
+    "sbp_ctx_tune": [_vp, C.c_char_p, _i64],
+    "sbp_ctx_scratch_generation": [_vp, C.POINTER(_i64)],
     "sbp_microbench": [_vp, _i32, _i64, _i32, C.POINTER(_dbl), C.POINTER(_dbl)],
     "sbp_ctx_kernel_time": [_vp, C.POINTER(_dbl), C.POINTER(_i64)],
 }
 _RESTYPE = {"sbp_last_error": C.c_char_p}
 
-#: entry points declared in include/sbp_gpu.h (sbp_tune / sbp_microbench / sbp_ctx_kernel_time
-#: are undeclared tuning / measurement hooks)
-ABI_SYMBOLS = tuple(k for k in _SIGNATURES
-                    if k not in ("sbp_tune", "sbp_microbench", "sbp_ctx_kernel_time"))
+#: every entry point the library exports is declared in include/sbp_gpu.h (the tuning /
+#: measurement hooks under "instrumentation")
+ABI_SYMBOLS = tuple(_SIGNATURES)
 
 
 def load():

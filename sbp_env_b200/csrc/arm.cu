@@ -132,8 +132,6 @@ k_arm_visible(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
 }
 
 // ------------------------------------------------------------ launchers -----
-extern int g_force_global;
-int g_arm_group = 0;   // 0 = auto
 
 // The arm kernels read the ROW-MAJOR copy of the map (sbp_map::rows, common.cuh).
 static void arm_cfg(const sbp_map *m, bool smem, int &grid, int &threads, size_t &bytes) {
@@ -158,9 +156,10 @@ extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const do
     SBP_REQUIRE(n >= 0, "sbp_arm_feasible: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
+    SBP_DEVICE(ctx);
     int32_t rc_rows = sbp_map_ensure_rows(map);
     if (rc_rows) return rc_rows;
-    bool smem = !g_force_global && map->rows_smem_resident &&
+    bool smem = !ctx->tune.force_global && map->rows_smem_resident &&
                 n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 4;
     int grid, threads; size_t bytes;
     arm_cfg(map, smem, grid, threads, bytes);
@@ -212,12 +211,13 @@ extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const dou
     SBP_REQUIRE(n >= 0, "sbp_arm_visible: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
+    SBP_DEVICE(ctx);
     int32_t rc_rows = sbp_map_ensure_rows(map);
     if (rc_rows) return rc_rows;
-    bool smem = !g_force_global && map->rows_smem_resident &&
+    bool smem = !ctx->tune.force_global && map->rows_smem_resident &&
                 n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 16;
     unsigned long long *cnt = (unsigned long long *)cfg_tested;
-    int G = g_arm_group ? g_arm_group : 8;
+    int G = ctx->tune.arm_group ? ctx->tune.arm_group : 8;
     switch (G) {
         case 4: return launch_arm_visible<4>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
         case 8: return launch_arm_visible<8>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);

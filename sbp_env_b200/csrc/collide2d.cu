@@ -490,6 +490,7 @@ extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint
     SBP_REQUIRE(n >= 0, "sbp_feasible2d: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
+    SBP_DEVICE(ctx);
     // staging the map pays off only when the batch is large compared to the map
     bool smem = map->smem_resident && n * 16 >= map->packed_bytes * (int64_t)ctx->sm_count;
     LaunchCfg c = cfg_for(map, smem);
@@ -507,19 +508,10 @@ extern "C" int32_t sbp_feasible2d(sbp_map *map, const double *P, int64_t n, uint
     return SBP_OK;
 }
 
-int g_visible_group = 0;   // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
-int g_coop_below = 12;     // adaptive kernel: cap of the hand-over threshold (walkers)
-int g_force_global = 0;    // 1 = never stage the map in shared memory (tuning knob)
-extern int g_arm_group, g_near_filter;
-extern int g_knn_chunks, g_knn_prefilter, g_knn_seed, g_knn_filter, g_knn_filter_chunks, g_knn_filter_variant;
-extern int g_knn_cells, g_knn_cells_limit, g_knn_cell_density, g_knn_cells_qpw, g_knn_cells_order, g_knn_cells_rinit;
-
-int g_time_kernels = 0;    // bench instrumentation: event pairs around the dominant kNN kernel
-
 // Sum and count of the event pairs recorded since the last call (synchronises the stream).
 extern "C" int32_t sbp_ctx_kernel_time(sbp_ctx *ctx, double *total_ms, int64_t *launches) {
     SBP_REQUIRE(ctx && total_ms && launches, "sbp_ctx_kernel_time: NULL argument");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     SBP_CUDA(cudaStreamSynchronize(ctx->stream));
     double tot = 0.0;
     for (auto &pr : ctx->timed) {
@@ -535,26 +527,22 @@ extern "C" int32_t sbp_ctx_kernel_time(sbp_ctx *ctx, double *total_ms, int64_t *
     return SBP_OK;
 }
 
-extern "C" int32_t sbp_tune(const char *key, int64_t value) {
-    if (!strcmp(key, "visible_group")) { g_visible_group = (int)value; return SBP_OK; }
-    if (!strcmp(key, "coop_below")) { g_coop_below = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_chunks")) { g_knn_chunks = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_prefilter")) { g_knn_prefilter = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_seed")) { g_knn_seed = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_filter")) { g_knn_filter = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_filter_chunks")) { g_knn_filter_chunks = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_filter_variant")) { g_knn_filter_variant = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cells")) { g_knn_cells = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cells_rinit")) { g_knn_cells_rinit = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cells_order")) { g_knn_cells_order = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cells_qpw")) { g_knn_cells_qpw = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cell_density")) { g_knn_cell_density = (int)value; return SBP_OK; }
-    if (!strcmp(key, "knn_cells_limit")) { g_knn_cells_limit = (int)value; return SBP_OK; }
-    if (!strcmp(key, "time_kernels")) { g_time_kernels = (int)value; return SBP_OK; }
-    if (!strcmp(key, "arm_group")) { g_arm_group = (int)value; return SBP_OK; }
-    if (!strcmp(key, "near_filter")) { g_near_filter = (int)value; return SBP_OK; }
-    if (!strcmp(key, "force_global")) { g_force_global = (int)value; return SBP_OK; }
-    sbp_set_error("sbp_tune: unknown key %s", key);
+extern "C" int32_t sbp_ctx_tune(sbp_ctx *ctx, const char *key, int64_t value) {
+    SBP_REQUIRE(ctx && key, "sbp_ctx_tune: NULL argument");
+    sbp_tuning &t = ctx->tune;
+    struct { const char *name; int *slot; } table[] = {
+        {"visible_group", &t.visible_group}, {"coop_below", &t.coop_below},
+        {"force_global", &t.force_global}, {"arm_group", &t.arm_group},
+        {"near_filter", &t.near_filter}, {"knn_seed", &t.knn_seed}, {"knn_chunks", &t.knn_chunks},
+        {"knn_prefilter", &t.knn_prefilter}, {"knn_filter", &t.knn_filter},
+        {"knn_filter_chunks", &t.knn_filter_chunks}, {"knn_filter_variant", &t.knn_filter_variant},
+        {"knn_cells", &t.knn_cells}, {"knn_cells_limit", &t.knn_cells_limit},
+        {"knn_cells_qpw", &t.knn_cells_qpw}, {"knn_cells_rinit", &t.knn_cells_rinit},
+        {"knn_cells_order", &t.knn_cells_order}, {"knn_cell_density", &t.knn_cell_density},
+        {"time_kernels", &t.time_kernels}};
+    for (auto &e : table)
+        if (!strcmp(key, e.name)) { *e.slot = (int)value; return SBP_OK; }
+    sbp_set_error("sbp_ctx_tune: unknown key %s", key);
     return SBP_ERR_ARG;
 }
 
@@ -588,10 +576,11 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
     SBP_REQUIRE(n >= 0, "sbp_visible2d: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    bool smem = !g_force_global && map->smem_resident &&
+    SBP_DEVICE(ctx);
+    bool smem = !ctx->tune.force_global && map->smem_resident &&
                 n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
     unsigned long long *px = (unsigned long long *)px_tested;
-    if (g_visible_group == 0) {
+    if (ctx->tune.visible_group == 0) {
         LaunchCfg c;
         if (smem) {                 // shared-memory resident: the row-major copy (cheaper index)
             int32_t rc = sbp_map_ensure_rows(map);
@@ -602,7 +591,7 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         c.smem = smem ? (size_t)map->rows.n_words * 4 : 0;
         c.threads = (smem && c.smem > 110 * 1024) ? 1024 : 512;
         c.grid = 0;
-        int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
+        int coop = ctx->tune.coop_below < 1 ? 1 : ctx->tune.coop_below > 33 ? 33 : ctx->tune.coop_below;
         const double2 *p2 = (const double2 *)P, *q2 = (const double2 *)Q;
 #define SBP_LAUNCH_ADP(SM, CT)                                                                    \
     do {                                                                                           \
@@ -624,7 +613,7 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         SBP_CUDA(cudaGetLastError());
         return SBP_OK;
     }
-    switch (g_visible_group) {
+    switch (ctx->tune.visible_group) {
         case 4: return launch_visible<4>(map, P, Q, n, out, flags, px, smem);
         case 8: return launch_visible<8>(map, P, Q, n, out, flags, px, smem);
         case 16: return launch_visible<16>(map, P, Q, n, out, flags, px, smem);
@@ -650,9 +639,9 @@ extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const
     SBP_REQUIRE(X || (first_row >= 0 && first_row + m <= nodes->n), "sbp_knn_edges_visible2d: row range");
     if (m == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     const int64_t n = m * k_out;
-    bool smem = !g_force_global && map->smem_resident &&
+    bool smem = !ctx->tune.force_global && map->smem_resident &&
                 n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
     if (smem) {
         int32_t rc = sbp_map_ensure_rows(map);
@@ -662,7 +651,7 @@ extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const
     const MapView mview = smem ? map->rows : map->view;
     const size_t sbytes = smem ? (size_t)map->rows.n_words * 4 : 0;
     const int threads = (smem && sbytes > 110 * 1024) ? 1024 : 512;
-    const int coop = g_coop_below < 1 ? 1 : g_coop_below > 33 ? 33 : g_coop_below;
+    const int coop = ctx->tune.coop_below < 1 ? 1 : ctx->tune.coop_below > 33 ? 33 : ctx->tune.coop_below;
     EdgeKnnRows src{nodes->d_soa, nodes->capacity, nodes->n, nbr_in, k_in, k_out, first_row,
                     (const double2 *)X, nbr_out, packed, packed_multicast,
                     nullptr, nullptr, nullptr, nullptr, 0, 0};
@@ -705,7 +694,8 @@ extern "C" int32_t sbp_first_blocked2d(sbp_map *map, const double *P, const doub
     SBP_REQUIRE(n >= 0, "sbp_first_blocked2d: n < 0");
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    bool smem = !g_force_global && map->smem_resident &&
+    SBP_DEVICE(ctx);
+    bool smem = !ctx->tune.force_global && map->smem_resident &&
                 n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
     LaunchCfg c = cfg_for(map, smem);
     int64_t need = (n * 32 + c.threads - 1) / c.threads;

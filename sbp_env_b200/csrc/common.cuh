@@ -37,6 +37,31 @@ void sbp_set_error(const char *fmt, ...);
         }                                                                           \
     } while (0)
 
+// Every entry point runs on its context's device and leaves the caller's current device as it
+// found it (torch keeps its own notion of the current device).
+struct SbpDeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t err;
+    explicit SbpDeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) {
+            err = cudaSetDevice(dev);
+            changed = err == cudaSuccess;
+        }
+    }
+    ~SbpDeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+#define SBP_DEVICE(ctxp)                                                             \
+    SbpDeviceGuard sbp_dev_guard__((ctxp)->device);                                  \
+    do {                                                                             \
+        if (sbp_dev_guard__.err != cudaSuccess) {                                    \
+            sbp_set_error("%s:%d cudaSetDevice(%d) -> %s", __FILE__, __LINE__,       \
+                          (ctxp)->device, cudaGetErrorString(sbp_dev_guard__.err));  \
+            return SBP_ERR_CUDA;                                                     \
+        }                                                                            \
+    } while (0)
+
 // NVTX range around a C-ABI entry point (header-only NVTX v3: a no-op unless a profiler is
 // attached), so that timelines show the library calls by name.
 struct SbpNvtxRange {
@@ -50,6 +75,32 @@ struct SbpNvtxRange {
 // and the fused query; 5,6 cell grid and seeds; 7 append / read staging; 8,9 kNN filter lists;
 // 10,11 spare
 #define SBP_SCRATCH_SLOTS 12
+// Tuning / instrumentation knobs (sbp_ctx_tune): per context, so that two contexts -- or two
+// threads driving different contexts -- never see each other's settings.  None of them changes
+// a result; the defaults are the measured optima.
+struct sbp_tuning {
+    int visible_group = 0;        // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
+    int coop_below = 12;          // adaptive kernel: cap of the hand-over threshold (walkers)
+    int force_global = 0;         // 1 = never stage the map in shared memory
+    int arm_group = 0;            // lanes per arm edge (0 = default 8)
+    int near_filter = 1;          // filtered scan of the batched radius query
+    int knn_seed = 1;             // grid-seeded a-priori bounds
+    int knn_chunks = 0;           // node chunks of the batched kNN kernel (0 = auto)
+    int knn_prefilter = 1;        // fp32 prefilter of the batched kNN scan
+    int knn_filter = 1;           // seeded filter + refine pipeline
+    int knn_filter_chunks = 0;    // node chunks of the filter kernel (0 = auto)
+    int knn_filter_variant = 0;   // CTA shape / unrolling of the filter kernel
+    int knn_cells = 2;            // exact answers from the cell grid (0 = off, 1 = warp per query,
+                                  // 2 = thread per query when >= 20000 queries, 3 = always)
+    int knn_cells_limit = 1024;   // ... where the rectangle holds at most this many nodes
+    int knn_cells_qpw = 0;        // queries per warp of k_knn_cells_t (0 = 32)
+    int knn_cells_rinit = 0;      // first ring radius of k_knn_cells_t (0 = from the density)
+    int knn_cells_order = 1;      // cell-sorted query order when m == n
+    int knn_cell_density = 150;   // nodes per grid cell x 100
+    int time_kernels = 0;         // event pairs around one kernel family (sbp_ctx_kernel_time):
+                                  // 1 = k_knn_filter, 2 = k_knn_cells*, 3 = 2-D visibility
+};
+
 struct sbp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -57,22 +108,25 @@ struct sbp_ctx {
     int sm_count = 0;
     int max_smem_optin = 0;
     int64_t launches = 0;
+    sbp_tuning tune;
     // growable scratch for the *_host entry points and internal work-spaces
     void *d_scratch[SBP_SCRATCH_SLOTS] = {};
     size_t d_scratch_bytes[SBP_SCRATCH_SLOTS] = {};
     int32_t *d_flags = nullptr;      // 16 x int32
     int32_t *h_flags = nullptr;      // pinned mirror
+    cudaEvent_t switch_event = nullptr;   // orders a new stream after the previous one
+    int64_t scratch_generation = 0;  // bumped whenever a scratch slot is reallocated
     // bench instrumentation (sbp_tune("time_kernels", 1)): CUDA events around the dominant
     // kernel of the kNN path, read back with sbp_ctx_kernel_time
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
 };
 
-extern int g_time_kernels;
 struct KernelTimer {          // RAII: records an event pair on the launching stream
     sbp_ctx *ctx;
     cudaEvent_t a = nullptr, b = nullptr;
-    // which: 1 = k_knn_filter, 2 = k_knn_cells / k_knn_cells_t (sbp_tune("time_kernels", which))
-    explicit KernelTimer(sbp_ctx *c, int which = 1) : ctx(g_time_kernels == which ? c : nullptr) {
+    // which: 1 = k_knn_filter, 2 = k_knn_cells / k_knn_cells_t, 3 = the 2-D visibility kernel
+    // (sbp_ctx_tune(ctx, "time_kernels", which))
+    explicit KernelTimer(sbp_ctx *c, int which = 1) : ctx(c->tune.time_kernels == which ? c : nullptr) {
         if (!ctx) return;
         cudaEventCreate(&a);
         cudaEventCreate(&b);

@@ -93,7 +93,7 @@ extern "C" int32_t sbp_nodes_near_visible(sbp_nodes *s, sbp_map *map, int32_t ar
     SBP_REQUIRE(s->d >= 2 && (!arm || s->d == 4), "sbp_nodes_near_visible: d >= 2 (arm: d == 4)");
     SBP_REQUIRE(s->ctx == map->ctx, "sbp_nodes_near_visible: store and map live in different contexts");
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     SBP_CUDA(cudaMemsetAsync(count, 0, (size_t)m * sizeof(int32_t), ctx->stream));
     if (s->n == 0) return SBP_OK;
     double thr;
@@ -122,7 +122,7 @@ extern "C" int32_t sbp_nodes_near_visible_host(sbp_nodes *s, sbp_map *map, int32
     SBP_REQUIRE(s && map && x && out_idx && out_vis && n_hits, "sbp_nodes_near_visible_host: NULL argument");
     SBP_REQUIRE(cap >= 1, "sbp_nodes_near_visible_host: cap >= 1");
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     void *dX, *dI, *dV;
     int32_t rc;
     if ((rc = sbp_ctx_scratch(ctx, 2, (size_t)s->d * 8, &dX))) return rc;

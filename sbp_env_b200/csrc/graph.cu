@@ -26,23 +26,36 @@ struct sbp_graph {
     int64_t *d_row_ptr = nullptr;    // [n + 1]
     int32_t *d_col = nullptr;        // [e_capacity]
     int32_t *d_deg = nullptr;        // [n + 1] degree counts, then scatter cursors
-    int64_t *d_total = nullptr;      // device scalar: number of edges of the last build
+    int64_t *d_total = nullptr;      // device scalar: number of arcs of the last build
+    int64_t *d_tsums = nullptr;      // per-tile degree sums of the row_ptr scan
+    int64_t tiles = 0;
+    // weakly connected components of the last build (union-find over the arcs), computed on
+    // the first query after a build: comp[u] != comp[v]  =>  no path either way
+    int32_t *d_comp = nullptr;       // [n]
+    bool comp_valid = false;
     // BFS work-space, grown on demand: per CTA slot level [n], parent [n], queue [n]
     int32_t *d_work = nullptr;
     int64_t work_slots = 0;
 };
 
+#define GSCAN_TILE 4096
+
 extern "C" int32_t sbp_graph_create(sbp_ctx *ctx, int64_t n_nodes, sbp_graph **out) {
     SBP_REQUIRE(ctx && out, "sbp_graph_create: NULL argument");
     SBP_REQUIRE(n_nodes >= 0 && n_nodes < ((int64_t)1 << 31), "sbp_graph_create: bad node count");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     sbp_graph *g = new sbp_graph();
     g->ctx = ctx;
     g->n = n_nodes;
+    g->tiles = (n_nodes + GSCAN_TILE - 1) / GSCAN_TILE;
+    if (g->tiles < 1) g->tiles = 1;
     cudaError_t e = cudaMalloc(&g->d_row_ptr, (size_t)(n_nodes + 1) * sizeof(int64_t));
     if (e == cudaSuccess) e = cudaMalloc(&g->d_deg, (size_t)(n_nodes + 1) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMalloc(&g->d_total, sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_tsums, (size_t)g->tiles * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_comp, (size_t)(n_nodes + 1) * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemsetAsync(g->d_row_ptr, 0, (size_t)(n_nodes + 1) * sizeof(int64_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->d_total, 0, sizeof(int64_t), ctx->stream);
     if (e != cudaSuccess) {
         sbp_set_error("sbp_graph_create: %s", cudaGetErrorString(e));
         delete g;
@@ -54,33 +67,65 @@ extern "C" int32_t sbp_graph_create(sbp_ctx *ctx, int64_t n_nodes, sbp_graph **o
 
 extern "C" int32_t sbp_graph_destroy(sbp_graph *g) {
     if (!g) return SBP_OK;
-    cudaSetDevice(g->ctx->device);
+    SbpDeviceGuard guard(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
     if (g->d_row_ptr) cudaFree(g->d_row_ptr);
     if (g->d_col) cudaFree(g->d_col);
     if (g->d_deg) cudaFree(g->d_deg);
     if (g->d_total) cudaFree(g->d_total);
+    if (g->d_tsums) cudaFree(g->d_tsums);
+    if (g->d_comp) cudaFree(g->d_comp);
     if (g->d_work) cudaFree(g->d_work);
     delete g;
     return SBP_OK;
 }
 
 // ----------------------------------------------------------------- build ----
-// Edge t of a kNN block: row = first_row + t / k (the node v whose neighbours were searched),
-// neighbour m_g = nbr[t]; the reference adds m_g -> v (prmPlanner.py:99-101).
-// Edge t of an explicit list: src[t] -> dst[t].  `keep` (optional) masks candidates out.
+// Candidate t of a kNN block: row v = first_row + t / k (the node whose neighbours were
+// searched), neighbour m_g = nbr[t]; the reference adds the arc m_g -> v (prmPlanner.py:99-101).
+// The block comes as (nbr int64, vis uint8) or as the packed adjacency code
+// (nbr + 1) * 2 + vis (int32, what the visibility kernel / the multi-GPU exchange produce).
+// Candidate t of an explicit list: src[t] -> dst[t].  `keep` (optional) masks candidates out.
+//
+// undirected: every kept arc u -> v also yields v -> u -- the graph the reference's radius rule
+// builds, where v in near(u) <=> u in near(v) puts both (m_g -> v) and (v -> m_g) into the DiGraph
+// (prmPlanner.py:91-101); a k-NN candidate set is not symmetric by itself.  For kNN / packed
+// blocks the mirrored arc is skipped when row u of the same block already lists v as a kept
+// candidate (the arc v -> u then exists in its own right), so that no arc is stored twice.
 struct EdgeSource {
     const int64_t *nbr;      // kNN block, or src list
+    const int32_t *packed;   // packed kNN block (then nbr == NULL)
     const int64_t *dst;      // NULL for a kNN block
     const uint8_t *keep;     // optional
     int64_t total;
     int32_t k;
-    int64_t first_row, n;
-    __device__ __forceinline__ bool edge(int64_t t, int64_t &u, int64_t &v) const {
-        if (keep && !keep[t]) return false;
+    int64_t first_row, n, m;
+    int32_t undirected;
+    __device__ __forceinline__ bool cand(int64_t t, int64_t &u) const {
+        if (packed) {
+            const int32_t c = packed[t];
+            u = (int64_t)(c >> 1) - 1;
+            return (c & 1) != 0;
+        }
         u = nbr[t];
+        return !keep || keep[t] != 0;
+    }
+    __device__ __forceinline__ bool edge(int64_t t, int64_t &u, int64_t &v) const {
+        if (!cand(t, u)) return false;
         v = dst ? dst[t] : first_row + t / k;
         return u >= 0 && u < n && v >= 0 && v < n;
+    }
+    // the mirrored arc v -> u of kept candidate (row v, neighbour u) duplicates an arc the block
+    // already holds iff row u lists v as a kept candidate
+    __device__ __forceinline__ bool mirror_is_duplicate(int64_t u, int64_t v) const {
+        if (dst) return false;
+        const int64_t r = u - first_row;
+        if (r < 0 || r >= m) return false;
+        for (int c = 0; c < k; ++c) {
+            int64_t w;
+            if (cand(r * k + c, w) && w == v) return true;
+        }
+        return false;
     }
 };
 
@@ -88,36 +133,91 @@ __global__ void k_graph_degree(EdgeSource es, int32_t *__restrict__ deg) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < es.total;
          t += (int64_t)gridDim.x * blockDim.x) {
         int64_t u, v;
-        if (es.edge(t, u, v)) atomicAdd(deg + u, 1);
+        if (!es.edge(t, u, v)) continue;
+        atomicAdd(deg + u, 1);
+        if (es.undirected && u != v && !es.mirror_is_duplicate(u, v)) atomicAdd(deg + v, 1);
     }
 }
 
-// Exclusive scan of deg[n] -> row_ptr[n + 1] (single CTA, serial segments; the build is a
-// one-off per roadmap); deg is turned into the scatter cursor (all zeros again).
+// Exclusive scan deg[n] -> row_ptr[n + 1] in three launches (tile sums, scan of the tile sums
+// by one CTA, per-tile scan + offset); deg is turned into the scatter cursor (zeros again).
 __global__ void __launch_bounds__(1024)
-k_graph_scan(int32_t *__restrict__ deg, int64_t n, int64_t *__restrict__ row_ptr,
-             int64_t *__restrict__ total) {
-    __shared__ int64_t part[1024];
-    const int tid = threadIdx.x;
-    const int64_t seg = (n + 1023) / 1024;
-    const int64_t a = (int64_t)tid * seg, b = a + seg < n ? a + seg : n;
-    int64_t sum = 0;
-    for (int64_t t = a; t < b; ++t) sum += deg[t];
-    part[tid] = sum;
+k_graph_tile_sums(const int32_t *__restrict__ deg, int64_t n, int64_t *__restrict__ tsums) {
+    __shared__ int32_t ws[32];
+    const int64_t i0 = (int64_t)blockIdx.x * GSCAN_TILE + (int64_t)threadIdx.x * 4;
+    int32_t v = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v += i0 + j < n ? deg[i0 + j] : 0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        int64_t v = tid >= o ? part[tid - o] : 0;
+    if (threadIdx.x < 32) {
+        v = ws[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) tsums[blockIdx.x] = v;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_graph_scan_tiles(int64_t *__restrict__ tsums, int64_t nt, int64_t *__restrict__ total,
+                   int64_t *__restrict__ row_ptr_n) {
+    __shared__ int64_t ws[32];
+    __shared__ int64_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nt; base += 1024) {
+        const int64_t i = base + tid;
+        const int64_t x = i < nt ? tsums[i] : 0;
+        int64_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int64_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) ws[w] = inc;
         __syncthreads();
-        part[tid] += v;
+        if (w == 0) {
+            int64_t y = ws[lane], yi = y;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int64_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
+            ws[lane] = yi - y;
+        }
+        __syncthreads();
+        const int64_t excl = s_carry + ws[w] + inc - x;
+        if (i < nt) tsums[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + x;
         __syncthreads();
     }
-    int64_t run = part[tid] - sum;
-    for (int64_t t = a; t < b; ++t) {
-        row_ptr[t] = run;
-        run += deg[t];
-        deg[t] = 0;
+    if (tid == 0) { *total = s_carry; *row_ptr_n = s_carry; }
+}
+
+__global__ void __launch_bounds__(1024)
+k_graph_scan_apply(int32_t *__restrict__ deg, int64_t n, const int64_t *__restrict__ tsums,
+                   int64_t *__restrict__ row_ptr) {
+    __shared__ int32_t ws[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t i0 = (int64_t)blockIdx.x * GSCAN_TILE + (int64_t)tid * 4;
+    int32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = i0 + j < n ? deg[i0 + j] : 0;
+    const int32_t tsum = v[0] + v[1] + v[2] + v[3];
+    int32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) ws[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int32_t y = ws[lane], yi = y;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int32_t u = __shfl_up_sync(0xffffffffu, yi, o); if (lane >= o) yi += u; }
+        ws[lane] = yi - y;
     }
-    if (tid == 1023) { row_ptr[n] = part[1023]; *total = part[1023]; }
+    __syncthreads();
+    int64_t run = tsums[blockIdx.x] + (int64_t)(ws[w] + inc - tsum);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i0 + j < n) { row_ptr[i0 + j] = run; deg[i0 + j] = 0; }
+        run += v[j];
+    }
 }
 
 __global__ void k_graph_scatter(EdgeSource es, const int64_t *__restrict__ row_ptr,
@@ -125,58 +225,75 @@ __global__ void k_graph_scatter(EdgeSource es, const int64_t *__restrict__ row_p
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < es.total;
          t += (int64_t)gridDim.x * blockDim.x) {
         int64_t u, v;
-        if (es.edge(t, u, v)) col[row_ptr[u] + atomicAdd(cursor + u, 1)] = (int32_t)v;
+        if (!es.edge(t, u, v)) continue;
+        col[row_ptr[u] + atomicAdd(cursor + u, 1)] = (int32_t)v;
+        if (es.undirected && u != v && !es.mirror_is_duplicate(u, v))
+            col[row_ptr[v] + atomicAdd(cursor + v, 1)] = (int32_t)u;
     }
 }
 
 static int32_t graph_build(sbp_graph *g, EdgeSource es) {
     sbp_ctx *ctx = g->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     es.n = g->n;
-    // every candidate may become an edge: size `col` for all of them (no host round trip)
-    if (es.total > g->e_capacity) {
+    g->comp_valid = false;
+    // every candidate may become an arc (two when undirected): size `col` for all of them (no
+    // host round trip)
+    const int64_t need = es.total * (es.undirected ? 2 : 1);
+    if (need > g->e_capacity) {
         SBP_CUDA(cudaStreamSynchronize(ctx->stream));
         if (g->d_col) SBP_CUDA(cudaFree(g->d_col));
         g->d_col = nullptr;
         g->e_capacity = 0;
-        SBP_CUDA(cudaMalloc(&g->d_col, (size_t)(es.total > 0 ? es.total : 1) * sizeof(int32_t)));
-        g->e_capacity = es.total;
+        SBP_CUDA(cudaMalloc(&g->d_col, (size_t)(need > 0 ? need : 1) * sizeof(int32_t)));
+        g->e_capacity = need;
     }
     SBP_CUDA(cudaMemsetAsync(g->d_deg, 0, (size_t)(g->n + 1) * sizeof(int32_t), ctx->stream));
     int blocks = (int)((es.total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     if (blocks < 1) blocks = 1;
     k_graph_degree<<<blocks, 256, 0, ctx->stream>>>(es, g->d_deg);
-    k_graph_scan<<<1, 1024, 0, ctx->stream>>>(g->d_deg, g->n, g->d_row_ptr, g->d_total);
+    k_graph_tile_sums<<<(unsigned)g->tiles, 1024, 0, ctx->stream>>>(g->d_deg, g->n, g->d_tsums);
+    k_graph_scan_tiles<<<1, 1024, 0, ctx->stream>>>(g->d_tsums, g->tiles, g->d_total, g->d_row_ptr + g->n);
+    k_graph_scan_apply<<<(unsigned)g->tiles, 1024, 0, ctx->stream>>>(g->d_deg, g->n, g->d_tsums, g->d_row_ptr);
     k_graph_scatter<<<blocks, 256, 0, ctx->stream>>>(es, g->d_row_ptr, g->d_deg, g->d_col);
-    ctx->launches += 3;
+    ctx->launches += 5;
     SBP_CUDA(cudaGetLastError());
     g->e = -1;                       // known on the device; fetched lazily by sbp_graph_info
     return SBP_OK;
 }
 
 extern "C" int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis, int64_t m,
-                                       int32_t k, int64_t first_row) {
+                                       int32_t k, int64_t first_row, int32_t undirected) {
     SBP_NVTX("sbp_graph_build_knn");
     SBP_REQUIRE(g && (m == 0 || nbr), "sbp_graph_build_knn: NULL argument");
     SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_graph_build_knn: bad sizes");
-    EdgeSource es{nbr, nullptr, vis, m * k, k, first_row, g->n};
+    EdgeSource es{nbr, nullptr, nullptr, vis, m * k, k, first_row, g->n, m, undirected ? 1 : 0};
+    return graph_build(g, es);
+}
+
+extern "C" int32_t sbp_graph_build_packed(sbp_graph *g, const int32_t *packed, int64_t m, int32_t k,
+                                          int64_t first_row, int32_t undirected) {
+    SBP_NVTX("sbp_graph_build_packed");
+    SBP_REQUIRE(g && (m == 0 || packed), "sbp_graph_build_packed: NULL argument");
+    SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_graph_build_packed: bad sizes");
+    EdgeSource es{nullptr, packed, nullptr, nullptr, m * k, k, first_row, g->n, m, undirected ? 1 : 0};
     return graph_build(g, es);
 }
 
 extern "C" int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,
-                                         const uint8_t *keep, int64_t e) {
+                                         const uint8_t *keep, int64_t e, int32_t undirected) {
     SBP_NVTX("sbp_graph_build_edges");
     SBP_REQUIRE(g && (e == 0 || (src && dst)), "sbp_graph_build_edges: NULL argument");
     SBP_REQUIRE(e >= 0, "sbp_graph_build_edges: e < 0");
-    EdgeSource es{src, dst, keep, e, 1, 0, g->n};
+    EdgeSource es{src, nullptr, dst, keep, e, 1, 0, g->n, 0, undirected ? 1 : 0};
     return graph_build(g, es);
 }
 
 extern "C" int32_t sbp_graph_info(sbp_graph *g, int64_t *n_nodes, int64_t *n_edges) {
     SBP_REQUIRE(g, "sbp_graph_info: NULL argument");
     if (g->e < 0) {
-        SBP_CUDA(cudaSetDevice(g->ctx->device));
+        SBP_DEVICE(g->ctx);
         SBP_CUDA(cudaMemcpyAsync(&g->e, g->d_total, sizeof(int64_t), cudaMemcpyDeviceToHost,
                                  g->ctx->stream));
         SBP_CUDA(cudaStreamSynchronize(g->ctx->stream));
@@ -201,38 +318,165 @@ extern "C" int32_t sbp_graph_csr(sbp_graph *g, int64_t *row_ptr, int32_t *col, i
     return SBP_OK;
 }
 
+// ------------------------------------------------- connected components ----
+// Weakly connected components by lock-free union-find over the arcs (hook the larger root
+// under the smaller with atomicCAS, path halving on the way), then one flattening pass:
+// comp[v] = smallest node index of v's component.  nx.has_path(u, v) needs comp[u] == comp[v]
+// (sufficient too when the graph was built undirected), so the search kernel answers every
+// query with different labels at once: on a fragmented roadmap (cfg5: ~2 % of the random
+// start / goal pairs are connected) almost all of them.
+__device__ __forceinline__ int32_t uf_find(int32_t *__restrict__ parent, int32_t v) {
+    int32_t p = __ldcg(parent + v);
+    while (p != v) {
+        const int32_t gp = __ldcg(parent + p);
+        if (gp != p) parent[v] = gp;                          // path halving (benign race)
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__global__ void k_graph_cc_init(int32_t *__restrict__ parent, int64_t n) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n;
+         v += (int64_t)gridDim.x * blockDim.x)
+        parent[v] = (int32_t)v;
+}
+
+__global__ void k_graph_cc_hook(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                int64_t n, int32_t *__restrict__ parent) {
+    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < n;
+         u += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
+        for (int64_t e = e0; e < e1; ++e) {
+            int32_t a = uf_find(parent, (int32_t)u), b = uf_find(parent, col[e]);
+            while (a != b) {
+                if (a < b) { const int32_t t = a; a = b; b = t; }      // a > b: hook a under b
+                const int32_t old = atomicCAS(parent + a, a, b);
+                if (old == a) break;
+                a = uf_find(parent, old);
+                b = uf_find(parent, b);
+            }
+        }
+    }
+}
+
+__global__ void k_graph_cc_flatten(int32_t *__restrict__ parent, int64_t n) {
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        int32_t r = (int32_t)v;
+        while (true) {
+            const int32_t p = __ldcg(parent + r);
+            if (p == r) break;
+            r = p;
+        }
+        parent[v] = r;                   // roots keep themselves; only non-roots are rewritten
+    }
+}
+
+static int32_t graph_ensure_components(sbp_graph *g) {
+    if (g->comp_valid) return SBP_OK;
+    sbp_ctx *ctx = g->ctx;
+    int blocks = (int)((g->n + 255) / 256);
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    k_graph_cc_init<<<blocks, 256, 0, ctx->stream>>>(g->d_comp, g->n);
+    k_graph_cc_hook<<<blocks, 256, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, g->d_comp);
+    k_graph_cc_flatten<<<blocks, 256, 0, ctx->stream>>>(g->d_comp, g->n);
+    ctx->launches += 3;
+    SBP_CUDA(cudaGetLastError());
+    g->comp_valid = true;
+    return SBP_OK;
+}
+
+// labels: device int32 [n] (nullable): smallest node index of each node's weakly connected
+// component.  n_components (nullable, HOST): number of components (synchronises).
+__global__ void k_graph_cc_count(const int32_t *__restrict__ comp, int64_t n, unsigned long long *cnt) {
+    unsigned long long c = 0;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n;
+         v += (int64_t)gridDim.x * blockDim.x)
+        c += comp[v] == (int32_t)v ? 1ull : 0ull;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, c);
+}
+
+extern "C" int32_t sbp_graph_components(sbp_graph *g, int32_t *labels, int64_t *n_components) {
+    SBP_NVTX("sbp_graph_components");
+    SBP_REQUIRE(g, "sbp_graph_components: NULL argument");
+    sbp_ctx *ctx = g->ctx;
+    SBP_DEVICE(ctx);
+    if (g->n == 0) { if (n_components) *n_components = 0; return SBP_OK; }
+    int32_t rc = graph_ensure_components(g);
+    if (rc) return rc;
+    if (labels)
+        SBP_CUDA(cudaMemcpyAsync(labels, g->d_comp, (size_t)g->n * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+    if (n_components) {
+        unsigned long long *cnt = (unsigned long long *)(ctx->d_flags + 12);     // 8-byte aligned slot
+        SBP_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), ctx->stream));
+        int blocks = (int)((g->n + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        k_graph_cc_count<<<blocks, 256, 0, ctx->stream>>>(g->d_comp, g->n, cnt);
+        ctx->launches++;
+        SBP_CUDA(cudaMemcpyAsync(ctx->h_flags + 12, cnt, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
+        SBP_CUDA(cudaStreamSynchronize(ctx->stream));
+        *n_components = (int64_t) * (unsigned long long *)(ctx->h_flags + 12);
+    }
+    return SBP_OK;
+}
+
 // ------------------------------------------------------------------- BFS ----
 #define BFS_TPB 512
 #define BFS_UNSET 0x7fffffff
 
-// Queries q = blockIdx.x, blockIdx.x + gridDim.x, ... ; work-space slot = blockIdx.x.
+// Queries are taken from a device-side ticket counter (the ones the component labels settle
+// cost nothing, so a static split would leave most CTAs idle); work-space slot = blockIdx.x.
 //   level[v]  = -1 untouched, else BFS level of v (start = 0)
 //   parent[v] = lowest-index predecessor on the previous level (BFS_UNSET until touched)
 //   queue     = touched nodes in level order
 __global__ void __launch_bounds__(BFS_TPB)
 k_graph_bfs(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int64_t n,
-            const int64_t *__restrict__ start, const int64_t *__restrict__ goal, int64_t nq,
-            int32_t *__restrict__ work, int32_t *__restrict__ hops, int64_t *__restrict__ paths,
-            int32_t max_len) {
+            const int32_t *__restrict__ comp, const int64_t *__restrict__ start,
+            const int64_t *__restrict__ goal, int64_t nq, int32_t *__restrict__ work,
+            int32_t *__restrict__ hops, int64_t *__restrict__ paths, int32_t max_len,
+            unsigned long long *__restrict__ ticket) {
     int32_t *level = work + (int64_t)blockIdx.x * 3 * n, *parent = level + n, *queue = parent + n;
     __shared__ int s_tail, s_found;
-    for (int64_t q = blockIdx.x; q < nq; q += gridDim.x) {
+    __shared__ long long s_q;
+    while (true) {
+        // next query that needs a search (a whole warp scans 32 tickets at a time would be
+        // overkill: the test is two loads per query)
+        if (threadIdx.x == 0) {
+            long long q;
+            while (true) {
+                q = (long long)atomicAdd(ticket, 1ull);
+                if (q >= nq) break;
+                const int64_t s = start[q], t = goal[q];
+                const bool ok = s >= 0 && s < n && t >= 0 && t < n;
+                if (ok && s != t && comp[s] == comp[t]) break;          // needs the search
+                hops[q] = ok && s == t ? 0 : -1;
+                if (paths) {
+                    int64_t *p = paths + q * (int64_t)max_len;
+                    for (int i = 0; i < max_len; ++i) p[i] = -1;
+                    if (ok && s == t) p[0] = s;
+                }
+            }
+            s_q = q;
+        }
+        __syncthreads();
+        const int64_t q = s_q;
+        if (q >= nq) return;
         const int64_t s = start[q], t = goal[q];
-        const bool ok = s >= 0 && s < n && t >= 0 && t < n;
         int head = 0, tail = 0, lvl = 0;
         if (threadIdx.x == 0) {
             s_found = 0;
-            s_tail = 0;
-            if (ok) {
-                level[s] = 0;
-                queue[0] = (int32_t)s;
-                s_tail = 1;
-                if (s == t) s_found = 1;
-            }
+            level[s] = 0;
+            queue[0] = (int32_t)s;
+            s_tail = 1;
         }
         __syncthreads();
         tail = s_tail;
-        bool found = s_found != 0;
+        bool found = false;
         __syncthreads();
         // expand level by level; the level in which the goal is touched is completed, so that
         // its parent is the minimum over the whole previous level.  s_tail / s_found are read
@@ -262,7 +506,6 @@ k_graph_bfs(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col
             ++lvl;
             __syncthreads();
         }
-        found = ok && found;
         if (threadIdx.x == 0) {
             const int32_t h = found ? __ldcg(level + t) : -1;
             hops[q] = h;
@@ -298,8 +541,8 @@ __global__ void k_graph_work_init(int32_t *__restrict__ work, int64_t n, int64_t
     }
 }
 
-// For every query q: fewest-hop path start[q] -> goal[q] along the directed edges.
-//   hops[q]  = number of edges, 0 when start == goal, -1 when unreachable / out of range
+// For every query q: fewest-hop path start[q] -> goal[q] along the arcs.
+//   hops[q]  = number of arcs, 0 when start == goal, -1 when unreachable / out of range
 //   paths    = optional [nq][max_len] node indices start..goal, -1 padded; all -1 when the path
 //              does not fit (hops[q] + 1 > max_len) or does not exist
 // start / goal / hops / paths are device pointers.
@@ -310,8 +553,10 @@ extern "C" int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64
     SBP_REQUIRE(nq >= 0 && (!paths || max_len >= 1), "sbp_graph_bfs: bad sizes");
     if (nq == 0) return SBP_OK;
     sbp_ctx *ctx = g->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     SBP_REQUIRE(g->n > 0, "sbp_graph_bfs: empty graph");
+    int32_t rc = graph_ensure_components(g);
+    if (rc) return rc;
     // two CTAs per SM hide the latency of the dependent loads; bounded by 8 GiB of work-space
     int64_t slots = 2 * (int64_t)ctx->sm_count;
     if (slots > nq) slots = nq;
@@ -327,8 +572,10 @@ extern "C" int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64
         k_graph_work_init<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(g->d_work, g->n, slots);
         ctx->launches++;
     }
-    k_graph_bfs<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, start, goal,
-                                                             nq, g->d_work, hops, paths, max_len);
+    unsigned long long *ticket = (unsigned long long *)(ctx->d_flags + 14);      // 8-byte aligned slot
+    SBP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx->stream));
+    k_graph_bfs<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, g->d_comp, start,
+                                                             goal, nq, g->d_work, hops, paths, max_len, ticket);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
@@ -377,7 +624,7 @@ extern "C" int32_t sbp_adjacency_peer_scatter(sbp_ctx *ctx, const int64_t *nbr, 
     SBP_REQUIRE(world >= 1 && world <= 16, "sbp_adjacency_peer_scatter: 1 <= world <= 16");
     SBP_REQUIRE(total >= 0 && offset >= 0 && (offset & 3) == 0, "sbp_adjacency_peer_scatter: bad offset / size");
     if (total == 0) return SBP_OK;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     PeerBuffers pb{};
     for (int r = 0; r < world; ++r) {
         SBP_REQUIRE(peer_bufs[r] != nullptr, "sbp_adjacency_peer_scatter: NULL peer buffer");
@@ -425,7 +672,7 @@ extern "C" int32_t sbp_adjacency_multicast(sbp_ctx *ctx, const int64_t *nbr, con
     SBP_REQUIRE(ctx && (total == 0 || (nbr && vis)) && mc_buf, "sbp_adjacency_multicast: NULL argument");
     SBP_REQUIRE(total >= 0 && offset >= 0 && (offset & 3) == 0, "sbp_adjacency_multicast: bad offset / size");
     if (total == 0) return SBP_OK;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int blocks = (int)(((total >> 2) + 255) / 256);
     if (blocks > ctx->sm_count * 4) blocks = ctx->sm_count * 4;
     if (blocks < 1) blocks = 1;

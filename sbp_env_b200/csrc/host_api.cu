@@ -47,7 +47,7 @@ extern "C" int32_t sbp_feasible2d_host(sbp_map *map, const double *P, int64_t n,
     if (flags) *flags = 0;
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dP = (double *)st.dev(2, (size_t)n * 16);
     uint8_t *dO = (uint8_t *)st.dev(3, (size_t)n);
@@ -68,7 +68,7 @@ extern "C" int32_t sbp_visible2d_host(sbp_map *map, const double *P, const doubl
     if (flags) *flags = 0;
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dP = (double *)st.dev(2, (size_t)n * 16);
     double *dQ = (double *)st.dev(3, (size_t)n * 16);
@@ -91,7 +91,7 @@ extern "C" int32_t sbp_first_blocked2d_host(sbp_map *map, const double *P, const
     if (flags) *flags = 0;
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dP = (double *)st.dev(2, (size_t)n * 16);
     double *dQ = (double *)st.dev(3, (size_t)n * 16);
@@ -122,7 +122,7 @@ extern "C" int32_t sbp_arm_feasible_host(sbp_map *map, double L0, double L1, con
     if (n_ambiguous) *n_ambiguous = 0;
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dC = (double *)st.dev(2, (size_t)n * 32);
     uint8_t *dO = (uint8_t *)st.dev(4, (size_t)n);
@@ -149,7 +149,7 @@ extern "C" int32_t sbp_arm_visible_host(sbp_map *map, double L0, double L1, cons
     if (n_ambiguous) *n_ambiguous = 0;
     if (n == 0) return SBP_OK;
     sbp_ctx *ctx = map->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *d1 = (double *)st.dev(2, (size_t)n * 32);
     double *d2 = (double *)st.dev(3, (size_t)n * 32);
@@ -175,7 +175,7 @@ extern "C" int32_t sbp_nodes_knn_host(sbp_nodes *s, const double *X, int64_t m, 
     SBP_REQUIRE(m >= 0 && k >= 1, "sbp_nodes_knn_host: bad sizes");
     if (m == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dX = (double *)st.dev(2, (size_t)m * s->d * 8);
     int64_t *dI = (int64_t *)st.dev(3, (size_t)m * k * 8);
@@ -194,7 +194,7 @@ extern "C" int32_t sbp_nodes_near_host(sbp_nodes *s, const double *X, int64_t m,
     SBP_REQUIRE(s && row_ptr && needed && (m == 0 || X), "sbp_nodes_near_host: NULL argument");
     SBP_REQUIRE(m >= 0 && idx_capacity >= 0, "sbp_nodes_near_host: bad sizes");
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     Staging st(ctx);
     double *dX = (double *)st.dev(2, (size_t)(m ? m : 1) * s->d * 8);
     int64_t *dR = (int64_t *)st.dev(3, (size_t)(m + 1) * 8);

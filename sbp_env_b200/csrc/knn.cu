@@ -1278,20 +1278,6 @@ k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__
     if (!handled) atomicAdd(pending, 1);                          // the brute-force kernels have work
 }
 
-int g_knn_seed = 1;     // tuning knob: grid-seeded a-priori bounds for d = 2 (results unchanged)
-int g_knn_chunks = 0;   // tuning knob: node chunks of the batched kNN kernel (0 = auto)
-int g_knn_prefilter = 1;  // tuning knob: fp32 prefilter of the batched kNN scan (results unchanged)
-int g_knn_filter = 1;     // tuning knob: seeded filter + refine pipeline (results unchanged)
-int g_knn_filter_chunks = 0;  // tuning knob: node chunks of the filter kernel (0 = auto)
-int g_knn_filter_variant = 0; // tuning knob: CTA shape / unrolling of the filter kernel
-int g_knn_cells = 2;          // tuning knob: exact answers from the cell grid where its rectangle is small
-                              // (0 = off, 1 = warp per query, 2 = thread per query when >= 20000 queries, 3 = always)
-int g_knn_cells_limit = 1024; // ... i.e. holds at most this many nodes (thread per query: a quarter)
-int g_knn_cells_qpw = 0;      // tuning knob: queries per warp of k_knn_cells_t (0 = 32)
-int g_knn_cells_rinit = 0;    // tuning knob: first ring radius of k_knn_cells_t (0 = from the density)
-int g_knn_cells_order = 1;    // tuning knob: cell-sorted query order when m == n (results unchanged)
-int g_knn_cell_density = 150; // tuning knob: nodes per grid cell x 100
-
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
                           double *dist) {
@@ -1314,12 +1300,12 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         // node chunks: with seeded bounds a chunk restart is cheap, so fill the SMs with
         // ~28 warps each (measured: 1.23 -> 1.04 ms on 50k x 50k); without seeds every chunk
         // re-learns its bound (K ln(N/K) insertions), so only enough CTAs to cover the SMs
-        const bool seeded = D >= 2 && g_knn_seed && n >= 2048;
+        const bool seeded = D >= 2 && ctx->tune.knn_seed && n >= 2048;
         int64_t want = seeded ? (28 * sm * 32 / tpb + tiles - 1) / tiles : (2 * sm + tiles - 1) / tiles;
         int64_t maxs = (n + 4095) / 4096;
         S = (int)(want < maxs ? want : maxs);
     }
-    if (!wide && g_knn_chunks > 0) S = g_knn_chunks;
+    if (!wide && ctx->tune.knn_chunks > 0) S = ctx->tune.knn_chunks;
     if (S < 1) S = 1;
     if (S > (wide ? 1024 : 64)) S = wide ? 1024 : 64;
     void *pd = nullptr, *pi = nullptr;
@@ -1345,8 +1331,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     void *donebuf = nullptr;                 // per query: 1 = row already written by k_knn_cells
     int32_t *pending_all = nullptr;          // [0]: queries k_knn_cells left to the brute-force kernels
     const int32_t *pending = nullptr;        // ... handed to those kernels when k_knn_cells ran
-    if (D >= 2 && g_knn_seed && n >= 2048) {
-        int G = (int)ceil(sqrt(100.0 / (double)(g_knn_cell_density < 1 ? 1 : g_knn_cell_density) * (double)n));
+    if (D >= 2 && ctx->tune.knn_seed && n >= 2048) {
+        int G = (int)ceil(sqrt(100.0 / (double)(ctx->tune.knn_cell_density < 1 ? 1 : ctx->tune.knn_cell_density) * (double)n));
         if (G > 2048) G = 2048;
         if (G < 1) G = 1;
         const int64_t L = (int64_t)G * G;
@@ -1380,32 +1366,32 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
         // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
-        if (g_knn_filter && g_knn_cells) {
+        if (ctx->tune.knn_filter && ctx->tune.knn_cells) {
             rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
             if (rc) return rc;
             KernelTimer timer(ctx, 2);
             // (measured on 50 000 nodes, k = 11, whole call: 4096 queries 44 us warp form / 66 us thread
             // form, 16 384 queries 73 / 74 us, 50 000 queries 137 / 71 us: a one-warp CTA's chain of
             // 32 queries takes ~50 us however few CTAs there are)
-            if (g_knn_cells >= 3 || (g_knn_cells == 2 && m >= 20000)) {
+            if (ctx->tune.knn_cells >= 3 || (ctx->tune.knn_cells == 2 && m >= 20000)) {
                 // first ring radius whose block is expected to hold 2 K nodes (then the rectangle of
                 // the K-th distance usually lies inside the block and there is no second pass)
                 const double per_cell = (double)n / ((double)G * (double)G);
                 int r_init = (int)ceil((sqrt(2.0 * (double)K / per_cell) - 1.0) / 2.0);
                 r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
-                if (g_knn_cells_rinit > 0) r_init = g_knn_cells_rinit;
-                int qpw = g_knn_cells_qpw;
+                if (ctx->tune.knn_cells_rinit > 0) r_init = ctx->tune.knn_cells_rinit;
+                int qpw = ctx->tune.knn_cells_qpw;
                 // (measured on cfg2: 16 / 8 queries per warp take 0.094 / 0.113 ms instead of 0.075:
                 // the kernel is bound by the instructions it issues, not by the length of a warp's chain)
                 if (qpw <= 0 || qpw > 32) qpw = 32;
                 // (8 nodes per lane and step were measured too: 0.077 instead of 0.076 ms on cfg2)
                 k_knn_cells_t<D, K, 4><<<(unsigned)((m + qpw - 1) / qpw), 32, 0, ctx->stream>>>(
-                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, g_knn_cells_limit / 4, qpw,
-                    (g_knn_cells_order && m == n) ? ids : nullptr, (double *)seedbuf, (uint8_t *)donebuf,
+                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, ctx->tune.knn_cells_limit / 4, qpw,
+                    (ctx->tune.knn_cells_order && m == n) ? ids : nullptr, (double *)seedbuf, (uint8_t *)donebuf,
                     pending_all, idx, dist);
             } else {
                 k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, g_knn_cells_limit, (double *)seedbuf,
+                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, ctx->tune.knn_cells_limit, (double *)seedbuf,
                     (uint8_t *)donebuf, pending_all, idx, dist);
             }
             pending = pending_all;
@@ -1419,16 +1405,16 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         seed_bounds = b4;
     }
     const uint8_t *redo = nullptr;
-    if (seed && g_knn_filter) {
+    if (seed && ctx->tune.knn_filter) {
         // seeded filter + exact refine; the one-kernel scan below then only redoes the
         // blocks of 32 queries the refine step flagged (normally none)
-        const int NW = (g_knn_filter_variant & 3) >= 2 ? 4 : 2;    // warps per CTA
-        const int FQv = g_knn_filter_variant >= 8 ? 8 : g_knn_filter_variant >= 4 ? 2 : FILTER_Q;
+        const int NW = (ctx->tune.knn_filter_variant & 3) >= 2 ? 4 : 2;    // warps per CTA
+        const int FQv = ctx->tune.knn_filter_variant >= 8 ? 8 : ctx->tune.knn_filter_variant >= 4 ? 2 : FILTER_Q;
         const int QPB = NW * 32 * FQv;                             // queries per CTA
         const int64_t qblocks = (m + QPB - 1) / QPB;
         constexpr int FT = filter_tile(D);
         const int64_t tiles = (n + FT - 1) / FT;
-        int64_t FS = g_knn_filter_chunks > 0 ? g_knn_filter_chunks
+        int64_t FS = ctx->tune.knn_filter_chunks > 0 ? ctx->tune.knn_filter_chunks
                                              : (16 * (int64_t)ctx->sm_count + qblocks - 1) / qblocks;
         if (FS > tiles) FS = tiles;
         if (FS > 64) FS = 64;
@@ -1470,7 +1456,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         C, (int32_t *)cbuf, ccount)
         {
         KernelTimer timer(ctx);
-        switch (g_knn_filter_variant) {
+        switch (ctx->tune.knn_filter_variant) {
             case 2: SBP_FILTER_LAUNCH(4, FILTER_Q); break;
             case 4: SBP_FILTER_LAUNCH(2, 2); break;
             case 6: SBP_FILTER_LAUNCH(4, 2); break;
@@ -1492,13 +1478,13 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     if (tpb == 32) {
         dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
         k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
-                                                              g_knn_prefilter, s->capacity, n, S, X,
+                                                              ctx->tune.knn_prefilter, s->capacity, n, S, X,
                                                               m, seed, (double *)pd, (int32_t *)pi,
                                                               redo, redo ? pending : nullptr);
     } else {
         dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
         k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
-                                                                g_knn_prefilter, s->capacity, n, S,
+                                                                ctx->tune.knn_prefilter, s->capacity, n, S,
                                                                 X, m, seed, (double *)pd, (int32_t *)pi,
                                                                 nullptr);
     }
@@ -1542,7 +1528,7 @@ extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32
     SBP_REQUIRE(k >= 1 && k <= 32, "sbp_nodes_knn: 1 <= k <= 32");
     SBP_REQUIRE(precision == 64, "sbp_nodes_knn: only the bit-exact fp64 path exists (precision=64)");
     if (m == 0) return SBP_OK;
-    SBP_CUDA(cudaSetDevice(s->ctx->device));
+    SBP_DEVICE(s->ctx);
     if (s->n == 0) {
         k_fill_empty_knn<<<64, 256, 0, s->ctx->stream>>>(m * k, idx, dist);
         s->ctx->launches++;

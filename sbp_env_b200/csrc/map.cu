@@ -31,7 +31,8 @@ extern "C" int32_t sbp_ctx_create(int32_t device, void *stream_or_null, sbp_ctx 
         return SBP_ERR_NODEV;
     }
     SBP_REQUIRE(device >= 0 && device < count, "sbp_ctx_create: bad device ordinal");
-    SBP_CUDA(cudaSetDevice(device));
+    SbpDeviceGuard guard(device);
+    SBP_CUDA(guard.err);
     cudaDeviceProp prop;
     SBP_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
@@ -58,12 +59,13 @@ extern "C" int32_t sbp_ctx_create(int32_t device, void *stream_or_null, sbp_ctx 
 
 extern "C" int32_t sbp_ctx_destroy(sbp_ctx *ctx) {
     if (!ctx) return SBP_OK;
-    cudaSetDevice(ctx->device);
+    SbpDeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < SBP_SCRATCH_SLOTS; ++i)
         if (ctx->d_scratch[i]) cudaFree(ctx->d_scratch[i]);
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+    if (ctx->switch_event) cudaEventDestroy(ctx->switch_event);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SBP_OK;
@@ -71,10 +73,28 @@ extern "C" int32_t sbp_ctx_destroy(sbp_ctx *ctx) {
 
 extern "C" int32_t sbp_ctx_set_stream(sbp_ctx *ctx, void *stream) {
     SBP_REQUIRE(ctx != nullptr, "sbp_ctx_set_stream: ctx is NULL");
+    if ((cudaStream_t)stream == ctx->stream) return SBP_OK;
+    SBP_DEVICE(ctx);
     if (ctx->own_stream) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
         ctx->own_stream = false;
+    } else {
+        // the context's scratch buffers and flag words are shared by everything launched through
+        // it: work already queued on the old stream must be ordered before work on the new one.
+        // (Not possible while either stream is being captured into a CUDA graph: a capture runs
+        // on one stream from its first to its last launch and the library never switches inside.)
+        cudaStreamCaptureStatus st_old = cudaStreamCaptureStatusNone, st_new = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(ctx->stream, &st_old);
+        cudaStreamIsCapturing((cudaStream_t)stream, &st_new);
+        if (st_old == cudaStreamCaptureStatusNone && st_new == cudaStreamCaptureStatusNone) {
+            if (!ctx->switch_event)
+                SBP_CUDA(cudaEventCreateWithFlags(&ctx->switch_event, cudaEventDisableTiming));
+            SBP_CUDA(cudaEventRecord(ctx->switch_event, ctx->stream));
+            SBP_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, ctx->switch_event, 0));
+        } else {
+            cudaGetLastError();
+        }
     }
     ctx->stream = (cudaStream_t)stream;
     return SBP_OK;
@@ -82,6 +102,7 @@ extern "C" int32_t sbp_ctx_set_stream(sbp_ctx *ctx, void *stream) {
 
 extern "C" int32_t sbp_ctx_sync(sbp_ctx *ctx) {
     SBP_REQUIRE(ctx != nullptr, "sbp_ctx_sync: ctx is NULL");
+    SBP_DEVICE(ctx);
     SBP_CUDA(cudaStreamSynchronize(ctx->stream));
     return SBP_OK;
 }
@@ -90,6 +111,12 @@ extern "C" int32_t sbp_ctx_info(sbp_ctx *ctx, int32_t *sm_count, int64_t *launch
     SBP_REQUIRE(ctx != nullptr, "sbp_ctx_info: ctx is NULL");
     if (sm_count) *sm_count = ctx->sm_count;
     if (launches) *launches = ctx->launches;
+    return SBP_OK;
+}
+
+extern "C" int32_t sbp_ctx_scratch_generation(sbp_ctx *ctx, int64_t *generation) {
+    SBP_REQUIRE(ctx && generation, "sbp_ctx_scratch_generation: NULL argument");
+    *generation = ctx->scratch_generation;
     return SBP_OK;
 }
 
@@ -105,6 +132,7 @@ int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out) {
         want = (want + 255) & ~(size_t)255;
         SBP_CUDA(cudaMalloc(&ctx->d_scratch[slot], want));
         ctx->d_scratch_bytes[slot] = want;
+        ctx->scratch_generation++;       // addresses frozen into captured graphs are now stale
     }
     *out = ctx->d_scratch[slot];
     return SBP_OK;
@@ -174,7 +202,7 @@ extern "C" int32_t sbp_map_create(sbp_ctx *ctx, const uint8_t *free_xy, int32_t 
     SBP_NVTX("sbp_map_create");
     SBP_REQUIRE(ctx && free_xy && out, "sbp_map_create: NULL argument");
     SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536, "sbp_map_create: 1 <= W,H <= 65536");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     uint8_t *d_in = nullptr;
     size_t bytes = (size_t)W * (size_t)H;
     SBP_CUDA(cudaMalloc(&d_in, bytes));
@@ -197,7 +225,7 @@ extern "C" int32_t sbp_map_create_device(sbp_ctx *ctx, const uint8_t *free_xy_de
     SBP_REQUIRE(ctx && free_xy_device && out, "sbp_map_create_device: NULL argument");
     SBP_REQUIRE(W > 0 && H > 0 && W <= 65536 && H <= 65536,
                 "sbp_map_create_device: 1 <= W,H <= 65536");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int32_t rc = map_create_common(ctx, free_xy_device, W, H, out);
     if (rc == SBP_OK) SBP_CUDA(cudaStreamSynchronize(ctx->stream));
     return rc;
@@ -241,7 +269,7 @@ int32_t sbp_map_ensure_rows(sbp_map *m) {
 
 extern "C" int32_t sbp_map_destroy(sbp_map *map) {
     if (!map) return SBP_OK;
-    cudaSetDevice(map->ctx->device);
+    SbpDeviceGuard guard(map->ctx->device);
     cudaStreamSynchronize(map->ctx->stream);
     if (map->d_words) cudaFree(map->d_words);
     if (map->d_rows) cudaFree(map->d_rows);

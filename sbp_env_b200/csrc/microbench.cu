@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) k_mb_mix(int iters, float *out) {
 extern "C" int32_t sbp_microbench(sbp_ctx *ctx, int32_t which, int64_t bytes, int32_t iters,
                                   double *ms, double *units) {
     SBP_REQUIRE(ctx && ms && units, "sbp_microbench: NULL argument");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     cudaEvent_t e0, e1;
     SBP_CUDA(cudaEventCreate(&e0));
     SBP_CUDA(cudaEventCreate(&e1));

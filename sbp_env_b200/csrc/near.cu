@@ -244,7 +244,6 @@ k_scan_counts(const int64_t *__restrict__ counts, int64_t L, int S, int64_t m,
     }
 }
 
-int g_near_filter = 1;    // tuning knob: filtered radius query (results unchanged)
 
 template <int D, bool XY>
 static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr, int closed,
@@ -252,7 +251,7 @@ static int32_t near_launch(sbp_nodes *s, const double *X, int64_t m, double thr,
     sbp_ctx *ctx = s->ctx;
     const int64_t n = s->n;
     bool wide = m < 256;
-    if (!wide && n >= 4096 && g_near_filter) {
+    if (!wide && n >= 4096 && ctx->tune.near_filter) {
         // filtered path: centred fp32 shadow + packed scan, exact fp64 decision of the groups
         // that pass (k_near_filtered); same counts -> scan -> fill structure as below
         constexpr int DD = XY ? 2 : D;
@@ -373,7 +372,7 @@ extern "C" int32_t sbp_nodes_near(sbp_nodes *s, const double *X, int64_t m, doub
     SBP_REQUIRE(m >= 0 && idx_capacity >= 0, "sbp_nodes_near: negative size");
     SBP_REQUIRE(metric == SBP_METRIC_FULL || metric == SBP_METRIC_XY, "sbp_nodes_near: bad metric");
     SBP_REQUIRE(metric == SBP_METRIC_FULL || s->d >= 2, "sbp_nodes_near: XY metric needs d >= 2");
-    SBP_CUDA(cudaSetDevice(s->ctx->device));
+    SBP_DEVICE(s->ctx);
     double thr;
     int cl;
     near_threshold(r, closed ? 1 : 0, &thr, &cl);

@@ -30,7 +30,7 @@ extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, s
     SBP_REQUIRE(ctx && out, "sbp_nodes_create: NULL argument");
     SBP_REQUIRE(d >= 1 && d <= 8, "sbp_nodes_create: 1 <= d <= 8");
     SBP_REQUIRE(capacity >= 0 && capacity < ((int64_t)1 << 31), "sbp_nodes_create: bad capacity");
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     sbp_nodes *s = new sbp_nodes();
     s->ctx = ctx;
     s->d = d;
@@ -55,7 +55,7 @@ extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, s
 
 extern "C" int32_t sbp_nodes_destroy(sbp_nodes *s) {
     if (!s) return SBP_OK;
-    cudaSetDevice(s->ctx->device);
+    SbpDeviceGuard guard(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     if (s->d_soa) cudaFree(s->d_soa);
     if (s->d_soa32) cudaFree(s->d_soa32);
@@ -132,7 +132,7 @@ extern "C" int32_t sbp_nodes_append(sbp_nodes *s, const double *X, int64_t m, in
     SBP_REQUIRE(m >= 0, "sbp_nodes_append: m < 0");
     if (m == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int32_t rc = nodes_grow(s, s->n + m);
     if (rc) return rc;
     const double *src = X;
@@ -175,7 +175,7 @@ extern "C" int32_t sbp_nodes_read(sbp_nodes *s, int64_t first, int64_t count, do
     SBP_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "sbp_nodes_read: range");
     if (count == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     void *stage = nullptr;
     int32_t rc = sbp_ctx_scratch(ctx, 7, (size_t)count * s->d * sizeof(double), &stage);
     if (rc) return rc;
@@ -198,7 +198,7 @@ extern "C" int32_t sbp_nodes_rows_device(sbp_nodes *s, int64_t first, int64_t co
     SBP_REQUIRE(first >= 0 && count >= 0 && first + count <= s->n, "sbp_nodes_rows_device: range");
     if (count == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int64_t total = count * s->d;
     int blocks = (int)((total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
@@ -241,7 +241,7 @@ extern "C" int32_t sbp_nodes_gather_edges(sbp_nodes *s, const int64_t *nbr, int6
     SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_nodes_gather_edges: bad sizes");
     if (m == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int64_t total = m * k;
     int blocks = (int)((total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
@@ -298,7 +298,7 @@ extern "C" int32_t sbp_nodes_knn_edges(sbp_nodes *s, const int64_t *nbr_in, int6
     SBP_REQUIRE(X || (first_row >= 0 && first_row + m <= s->n), "sbp_nodes_knn_edges: row range");
     if (m == 0) return SBP_OK;
     sbp_ctx *ctx = s->ctx;
-    SBP_CUDA(cudaSetDevice(ctx->device));
+    SBP_DEVICE(ctx);
     int64_t total = m * k_out;
     int blocks = (int)((total + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;

@@ -154,13 +154,38 @@ class CapturedStep:
                 fn()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        from .runtime import get_context
+
+        self._fn, self._dev, self._side = fn, dev, side
+        self._ctx = get_context(device)
+        self._capture()
+
+    def _capture(self):
+        import torch
+
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph, stream=side):
-            self.out = fn()
+        with torch.cuda.graph(self.graph, stream=self._side):
+            self.out = self._fn()
+        # the library's internal work buffers are frozen into the graph by address: if a later
+        # eager call makes one of them grow, the context's scratch generation moves and the
+        # graph is captured again before its next replay (never replayed on freed memory)
+        self._generation = self._ctx.scratch_generation
 
     def replay(self):
+        if self._ctx.scratch_generation != self._generation:
+            import torch
+
+            torch.cuda.synchronize(self._dev)
+            with torch.cuda.stream(self._side):
+                self._fn()                       # eager: work buffers settle at their new size
+            torch.cuda.synchronize(self._dev)
+            self._capture()
+            self._recaptured()
         self.graph.replay()
         return self.out
+
+    def _recaptured(self):
+        pass
 
 
 class PRMConnectGraph(CapturedStep):
@@ -197,9 +222,12 @@ class PRMConnectGraph(CapturedStep):
         self._edges = int(cc.stats.visible_cnt) - before[0]     # edges checked by one step
         self.nbr, self.vis = self.out
 
+    def _recaptured(self):
+        self.nbr, self.vis = self.out
+
     def replay(self):
         if len(self.tree) != self._n:
             raise RuntimeError("the node store changed size since the graph was captured")
-        self.graph.replay()
+        super().replay()
         self.cc.stats.visible_cnt += self._edges        # Stats accounting of visible_batch
         return self.nbr, self.vis

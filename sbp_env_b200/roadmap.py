@@ -44,14 +44,31 @@ class Roadmap:
 
     # ---- construction --------------------------------------------------------------
     @classmethod
-    def from_knn(cls, nbr, vis, n_nodes: int = None, first_row: int = 0, device: int = None):
-        """Roadmap of the candidate blocks ``nbr`` / ``vis`` ([m][k], CUDA or numpy): edge
-        ``nbr[i][j] -> first_row + i`` wherever ``vis[i][j]`` (prmPlanner.py:91-101)."""
+    def from_knn(cls, nbr, vis, n_nodes: int = None, first_row: int = 0, device: int = None,
+                 undirected: bool = False):
+        """Roadmap of the candidate blocks ``nbr`` / ``vis`` ([m][k], CUDA or numpy): arc
+        ``nbr[i][j] -> first_row + i`` wherever ``vis[i][j]`` (prmPlanner.py:91-101).
+
+        ``undirected=True`` adds the mirrored arcs as well: the reference connects by radius,
+        which is symmetric, so its DiGraph holds both ``m_g -> v`` and ``v -> m_g``; a k-NN
+        candidate set is not symmetric by itself."""
         if device is None:
             device = nbr.device.index if _is_torch_tensor(nbr) else 0
         n = int(n_nodes) if n_nodes is not None else int(first_row + nbr.shape[0])
         g = cls(n, device)
-        g.build_from_knn(nbr, vis, first_row)
+        g.build_from_knn(nbr, vis, first_row, undirected=undirected)
+        return g
+
+    @classmethod
+    def from_packed(cls, packed, n_nodes: int = None, first_row: int = 0, device: int = None,
+                    undirected: bool = False):
+        """The same from the packed adjacency ``(nbr + 1) * 2 + vis`` (CUDA int32 [m][k]): the
+        form the connection step writes and the multi-GPU exchange assembles on every rank."""
+        if device is None:
+            device = packed.device.index if _is_torch_tensor(packed) else 0
+        n = int(n_nodes) if n_nodes is not None else int(first_row + packed.shape[0])
+        g = cls(n, device)
+        g.build_from_packed(packed, first_row, undirected=undirected)
         return g
 
     def _dev(self, a, dtype):
@@ -61,7 +78,7 @@ class Roadmap:
             a = torch.from_numpy(np.ascontiguousarray(a))
         return a.to(device=torch.device("cuda", self.ctx.device), dtype=dtype).contiguous()
 
-    def build_from_knn(self, nbr, vis, first_row: int = 0):
+    def build_from_knn(self, nbr, vis, first_row: int = 0, undirected: bool = False):
         import torch
 
         self.ctx.use_torch_stream()
@@ -70,12 +87,24 @@ class Roadmap:
         m, k = nbr.shape
         if tuple(vis.shape) != (m, k):
             raise ValueError("nbr and vis must have the same [m][k] shape")
-        check(_lib.load().sbp_graph_build_knn(self._h, ptr(nbr), ptr(vis), m, k, int(first_row)),
-              "sbp_graph_build_knn")
+        check(_lib.load().sbp_graph_build_knn(self._h, ptr(nbr), ptr(vis), m, k, int(first_row),
+                                              int(bool(undirected))), "sbp_graph_build_knn")
         return self
 
-    def build_from_edges(self, src, dst, keep=None):
-        """Directed edges ``src[e] -> dst[e]`` (e.g. the output of
+    def build_from_packed(self, packed, first_row: int = 0, undirected: bool = False):
+        import torch
+
+        self.ctx.use_torch_stream()
+        packed = self._dev(packed, torch.int32)
+        if packed.dim() != 2:
+            raise ValueError("packed adjacency must be [m][k]")
+        m, k = packed.shape
+        check(_lib.load().sbp_graph_build_packed(self._h, ptr(packed), m, k, int(first_row),
+                                                 int(bool(undirected))), "sbp_graph_build_packed")
+        return self
+
+    def build_from_edges(self, src, dst, keep=None, undirected: bool = False):
+        """Arcs ``src[e] -> dst[e]`` (e.g. the output of
         :func:`sbp_env_b200.planning.prm_connect_radius`), ``keep`` an optional mask."""
         import torch
 
@@ -84,9 +113,20 @@ class Roadmap:
         if src.shape != dst.shape:
             raise ValueError("src and dst must have the same length")
         keep = None if keep is None else self._dev(keep, torch.uint8)
-        check(_lib.load().sbp_graph_build_edges(self._h, ptr(src), ptr(dst), ptr(keep), src.numel()),
-              "sbp_graph_build_edges")
+        check(_lib.load().sbp_graph_build_edges(self._h, ptr(src), ptr(dst), ptr(keep), src.numel(),
+                                                int(bool(undirected))), "sbp_graph_build_edges")
         return self
+
+    def components(self):
+        """``(labels int32 [n] CUDA, n_components)``: weakly connected components, label =
+        smallest node index of the component (``nx.has_path`` needs equal labels)."""
+        import torch
+
+        self.ctx.use_torch_stream()
+        labels = torch.empty(self.n_nodes, dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
+        nc = C.c_int64()
+        check(_lib.load().sbp_graph_components(self._h, ptr(labels), C.byref(nc)), "sbp_graph_components")
+        return labels, int(nc.value)
 
     # ---- inspection ----------------------------------------------------------------
     @property

@@ -59,6 +59,31 @@ class Context:
     def launches(self) -> int:
         return self.info()["launches"]
 
+    def tune(self, key, value: int) -> None:
+        """Set a tuning / instrumentation knob of THIS context (csrc/common.cuh: sbp_tuning);
+        none of them changes a result."""
+        if isinstance(key, str):
+            key = key.encode()
+        check(_lib.load().sbp_ctx_tune(self._h, key, int(value)), "sbp_ctx_tune")
+
+    def kernel_time(self):
+        """``(total_ms, launches)`` of the kernels bracketed since the last call
+        (``tune("time_kernels", which)``); synchronises the stream."""
+        ms, n = C.c_double(), C.c_int64()
+        check(_lib.load().sbp_ctx_kernel_time(self._h, C.byref(ms), C.byref(n)), "sbp_ctx_kernel_time")
+        return float(ms.value), int(n.value)
+
+    @property
+    def scratch_generation(self) -> int:
+        g = C.c_int64()
+        check(_lib.load().sbp_ctx_scratch_generation(self._h, C.byref(g)), "sbp_ctx_scratch_generation")
+        return int(g.value)
+
+
+def tune(key, value: int, device: int = 0) -> None:
+    """``get_context(device).tune(key, value)``."""
+    get_context(device).tune(key, value)
+
 
 def get_context(device: int = 0) -> Context:
     """Process-wide context of a device (created on first use; raises without a B200)."""

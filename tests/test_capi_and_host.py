@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in sbp_gpu.h but not exported"
     # and the Python binding table covers exactly the declared ABI
     assert sorted(_lib.ABI_SYMBOLS) == declared
-    assert _lib.load().sbp_abi_version() == 1
+    assert _lib.load().sbp_abi_version() == 2
 
 
 def test_no_cuda_means_loud_failure():

@@ -4,6 +4,7 @@ import pytest
 
 import c_oracle as orc
 from _util import golden, kat_png, load_map, map_png, unpack
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -91,7 +92,7 @@ def test_random_vs_oracle(sg, name, L):
     try:
         # lanes per edge of the lane-group kernel (0 = default, 8)
         for group in (0, 4, 32):
-            lib.sbp_tune(b"arm_group", group)
+            tune("arm_group", group)
             assert np.array_equal(cc.visible_batch(C1, C2), want_fwd), group
             # H8: argument order matters for the arm; check the reverse direction too
             assert np.array_equal(cc.visible_batch(C2, C1), want_rev), group
@@ -99,7 +100,7 @@ def test_random_vs_oracle(sg, name, L):
             assert np.array_equal(cc.visible_batch(C1[:37], C2[:37]), want_fwd[:37]), group
             assert np.array_equal(cc.visible_batch(C1[-1:], C2[-1:]), want_fwd[-1:]), group
     finally:
-        lib.sbp_tune(b"arm_group", 0)
+        tune("arm_group", 0)
 
 
 def test_guard_band_is_resolved_exactly(sg):

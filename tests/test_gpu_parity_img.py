@@ -9,6 +9,7 @@ import pytest
 
 import c_oracle as orc
 from _util import golden, kat_png, load_map, map_png, unpack
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 EPS = 1e-5
@@ -96,14 +97,14 @@ def test_all_kernel_variants_agree(sg, group, coop, force_global):
     P, Q = np.tile(P, (8, 1)), np.tile(Q, (8, 1))
     lib = _lib.load()
     try:
-        lib.sbp_tune(b"visible_group", group)
-        lib.sbp_tune(b"coop_below", coop)
-        lib.sbp_tune(b"force_global", force_global)
+        tune("visible_group", group)
+        tune("coop_below", coop)
+        tune("force_global", force_global)
         got = cc.visible_batch(P, Q)
     finally:
-        lib.sbp_tune(b"visible_group", 0)
-        lib.sbp_tune(b"coop_below", 12)
-        lib.sbp_tune(b"force_global", 0)
+        tune("visible_group", 0)
+        tune("coop_below", 12)
+        tune("force_global", 0)
     assert np.array_equal(got, np.tile(unpack(g["room1_visible"], len(g["room1_P"])), 8))
 
 

@@ -5,6 +5,7 @@ import pytest
 
 import c_oracle as orc
 from _util import golden, load_map, map_png
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
@@ -178,12 +179,12 @@ def test_fused_knn_edges_visible_equals_the_two_launch_form(sg, map_name, n_node
     from sbp_env_b200 import _lib
 
     lib = _lib.load()
-    lib.sbp_tune(b"force_global", 1)
+    tune("force_global", 1)
     try:
         idx, _ = t.knn(t.rows_device(0, n_nodes), k + 1)
         nbr_c, vis_c = cc.knn_edges_visible(t, idx)
     finally:
-        lib.sbp_tune(b"force_global", 0)
+        tune("force_global", 0)
     nbr_d, vis_d = cc.knn_edges_visible(t, idx)
     assert torch.equal(nbr_c, nbr_d) and torch.equal(vis_c, vis_d)
 
@@ -294,12 +295,12 @@ def test_knn_fp32_prefilter_never_changes_results(sg, scale, offset):
     lib = _lib.load()
     try:
         for pf in (1, 0):
-            lib.sbp_tune(b"knn_prefilter", pf)
+            tune("knn_prefilter", pf)
             idx, dist = t.knn(X, k)
             assert np.array_equal(idx, oi), (scale, offset, pf)
             assert np.array_equal(dist, od), (scale, offset, pf)
     finally:
-        lib.sbp_tune(b"knn_prefilter", 1)
+        tune("knn_prefilter", 1)
 
 
 def test_knn_prefilter_with_queries_far_outside_the_cloud(sg):
@@ -342,7 +343,7 @@ def test_knn_grid_seed_never_changes_results(sg, layout):
     lib = _lib.load()
     try:
         for seed in (1, 0):
-            lib.sbp_tune(b"knn_seed", seed)
+            tune("knn_seed", seed)
             for kk in (k, 10, 1, 20):
                 idx, dist = t.knn(X, kk)
                 if kk == k:
@@ -351,7 +352,7 @@ def test_knn_grid_seed_never_changes_results(sg, layout):
                     ei, ed = orc.knn(poses, X, kk)
                     assert np.array_equal(idx, ei) and np.array_equal(dist, ed), (layout, seed, kk)
     finally:
-        lib.sbp_tune(b"knn_seed", 1)
+        tune("knn_seed", 1)
 
 
 @pytest.mark.parametrize("layout", ["uniform", "duplicates", "clustered", "nan_inf"])
@@ -389,16 +390,16 @@ def test_knn_filter_pipeline_never_changes_results(sg, layout, n):
         for kk in (k, 1, 20, 32):
             ei, ed = orc.knn(poses, X, kk)
             for filt, chunks, cells in ((1, 0, 1), (1, 0, 3), (1, 0, 0), (1, 1, 0), (1, 7, 0), (0, 0, 0)):
-                lib.sbp_tune(b"knn_filter", filt)
-                lib.sbp_tune(b"knn_filter_chunks", chunks)
-                lib.sbp_tune(b"knn_cells", cells)
+                tune("knn_filter", filt)
+                tune("knn_filter_chunks", chunks)
+                tune("knn_cells", cells)
                 idx, dist = t.knn(X, kk)
                 assert np.array_equal(idx, ei), (layout, n, kk, filt, chunks, cells)
                 assert np.array_equal(dist, ed, equal_nan=True), (layout, n, kk, filt, chunks, cells)
     finally:
-        lib.sbp_tune(b"knn_filter", 1)
-        lib.sbp_tune(b"knn_filter_chunks", 0)
-        lib.sbp_tune(b"knn_cells", 2)
+        tune("knn_filter", 1)
+        tune("knn_filter_chunks", 0)
+        tune("knn_cells", 2)
 
 
 @pytest.mark.parametrize("layout", ["uniform", "clustered", "duplicates", "line", "outliers", "lattice", "nan_inf"])
@@ -449,9 +450,9 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
             for mode, limit, density in ((1, 0, 50), (1, 48, 50), (1, 1024, 50), (1, 1 << 30, 50),
                                          (3, 0, 50), (3, 200, 50), (3, 1024, 300), (3, 1 << 30, 50),
                                          (3, 1024, 5)):
-                lib.sbp_tune(b"knn_cells", mode)                  # 1 = warp, 3 = thread per query
-                lib.sbp_tune(b"knn_cells_limit", limit)
-                lib.sbp_tune(b"knn_cell_density", density)
+                tune("knn_cells", mode)                  # 1 = warp, 3 = thread per query
+                tune("knn_cells_limit", limit)
+                tune("knn_cell_density", density)
                 idx, dist = t.knn(X, kk)
                 assert np.array_equal(idx, ei), (layout, d, kk, mode, limit, density)
                 assert np.array_equal(dist, ed, equal_nan=True), (layout, d, kk, mode, limit, density)
@@ -460,18 +461,18 @@ def test_knn_cell_grid_answers_equal_the_oracle(sg, layout, d):
         for Xs in (poses, np.roll(X, 7, axis=0)[np.arange(n) % len(X)]):
             ei, ed = orc.knn(poses, Xs, 11)
             for mode, order in ((3, 1), (3, 0), (2, 1)):
-                lib.sbp_tune(b"knn_cells", mode)
-                lib.sbp_tune(b"knn_cells_limit", 1024)
-                lib.sbp_tune(b"knn_cell_density", 150)
-                lib.sbp_tune(b"knn_cells_order", order)
+                tune("knn_cells", mode)
+                tune("knn_cells_limit", 1024)
+                tune("knn_cell_density", 150)
+                tune("knn_cells_order", order)
                 idx, dist = t.knn(Xs, 11)
                 assert np.array_equal(idx, ei), (layout, d, mode, order)
                 assert np.array_equal(dist, ed, equal_nan=True), (layout, d, mode, order)
     finally:
-        lib.sbp_tune(b"knn_cells", 2)
-        lib.sbp_tune(b"knn_cells_limit", 1024)
-        lib.sbp_tune(b"knn_cell_density", 150)
-        lib.sbp_tune(b"knn_cells_order", 1)
+        tune("knn_cells", 2)
+        tune("knn_cells_limit", 1024)
+        tune("knn_cell_density", 150)
+        tune("knn_cells_order", 1)
 
 
 def test_prm_connect_graph_replay_equals_eager(sg):
@@ -560,12 +561,12 @@ def test_near_filtered_scan_never_changes_results(sg, d):
                     for r in (0.0, 5.0, 13.0, 1000.0) if variant == "plain" else (13.0,):
                         orp, oix = orc.near(poses, X, r, metric, closed)
                         for filt in (1, 0):
-                            lib.sbp_tune(b"near_filter", filt)
+                            tune("near_filter", filt)
                             rp, ix = t.near(X, r, metric, closed)
                             assert np.array_equal(rp, orp), (variant, metric, closed, r, filt)
                             assert np.array_equal(ix, oix), (variant, metric, closed, r, filt)
         finally:
-            lib.sbp_tune(b"near_filter", 1)
+            tune("near_filter", 1)
 
 
 def test_pack_adjacency_device_kernel_roundtrip(sg):
@@ -660,14 +661,14 @@ def test_knn_filter_pipeline_in_more_than_two_dimensions(sg, d, layout):
         for k in (11, 1, 32):
             ei, ed = orc.knn(poses, X, k)
             for filt, cells in ((1, 1), (1, 3), (1, 0), (0, 0)):
-                lib.sbp_tune(b"knn_filter", filt)
-                lib.sbp_tune(b"knn_cells", cells)
+                tune("knn_filter", filt)
+                tune("knn_cells", cells)
                 idx, dist = t.knn(X, k)
                 assert np.array_equal(idx, ei), (d, layout, k, filt, cells)
                 assert np.array_equal(dist, ed, equal_nan=True), (d, layout, k, filt, cells)
     finally:
-        lib.sbp_tune(b"knn_filter", 1)
-        lib.sbp_tune(b"knn_cells", 2)
+        tune("knn_filter", 1)
+        tune("knn_cells", 2)
 
 
 def test_cfg2_full_size_connection_equals_oracle(sg):

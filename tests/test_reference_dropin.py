@@ -85,49 +85,7 @@ def ref(monkeypatch):
     Stats.clear_instance()
 
 
-def make_args(planner_id, engine_factory, start, goal, max_nodes, **kw):
-    from sbp_env.utils import planner_registry
-    from sbp_env.utils.common import PlanningOptions
-    import sbp_env.planners  # noqa: F401 - fills the registries
-    import sbp_env.samplers  # noqa: F401
-
-    pdp = planner_registry.PLANNERS[planner_id]
-    opts = dict(always_refresh=False, epsilon=None, goalBias=0.03, start_pt=start, goal_pt=goal,
-                goal_radius=None, ignore_step_size=False, max_number_nodes=max_nodes, no_display=True,
-                planner_data_pack=pdp, sampler_data_pack=planner_registry.SAMPLERS[pdp.sampler_id],
-                radius=None, rrdt_proposal_distribution="dynamic-vonmises", scaling=1.5,
-                showSampledPoint=False, skip_optimality=False)
-    opts.update(kw)
-    args = PlanningOptions(**opts)
-    args.engine = engine_factory(args)
-    return args
-
-
-def run(planner_id, engine_factory, swap_cc, start, goal, max_nodes, before_run=None, **kw):
-    from sbp_env.env import Env
-    from sbp_env.utils.common import Stats
-
-    Stats.clear_instance()
-    args = make_args(planner_id, engine_factory, start, goal, max_nodes, **kw)
-    if swap_cc is not None:
-        args.engine.cc = swap_cc(args.engine.cc)
-    env = Env(args, fixed_seed=0)
-    if before_run is not None:
-        before_run(env)
-    stats = env.run()
-    pl = env.planner
-    n = len(pl.nodes)
-    return dict(poses=np.array(pl.poses[:n]), c_max=pl.c_max, n=n,
-                counters=(stats.visible_cnt, stats.feasible_cnt, stats.valid_sample,
-                          stats.invalid_samples_obstacles, stats.invalid_samples_connections),
-                env=env)
-
-
-def _same(a, b):
-    assert a["n"] == b["n"]
-    assert np.array_equal(a["poses"], b["poses"])
-    assert a["c_max"] == b["c_max"]
-    assert a["counters"] == b["counters"]
+from _refrun import make_args, run, same_run as _same  # noqa: E402,F401
 
 
 @pytest.mark.parametrize("planner_id", ["rrt", "birrt", "informedrrt"])

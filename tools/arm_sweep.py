@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import sbp_env_b200 as sg  # noqa: E402
 from sbp_env_b200 import _lib  # noqa: E402
 from _util import load_map  # noqa: E402
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
@@ -51,6 +52,6 @@ for name, C1 in sets.items():
     vis = cc._visible_device(C1, C2, cfg_tested=cnt, resolve=False)
     print(name, "edges", m, "visible frac", float((vis == 1).double().mean()), "configs tested", int(cnt.item()), flush=True)
     for group in (8, 4, 16):
-        lib.sbp_tune(b"arm_group", group)
+        tune("arm_group", group)
         ms = timeit(lambda: cc._visible_device(C1, C2, resolve=False))
         print(f"  group={group}: {ms:.4f} ms  {m / ms * 1e3:.3e} edges/s", flush=True)

@@ -3,6 +3,7 @@ import sys, torch
 sys.path.insert(0, "/root/repo")
 import sbp_env_b200 as sg
 from sbp_env_b200 import _lib
+from sbp_env_b200.runtime import tune  # noqa: E402
 lib = _lib.load()
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -21,11 +22,11 @@ for m in (256, 512, 1024, 2048, 4096, 8192, 16384):
     X = torch.rand((m, 2), generator=g, device=dev, dtype=torch.float64) * scale
     row = []
     for mode in (1, 3, 0):
-        lib.sbp_tune(b"knn_cells", mode)
+        tune("knn_cells", mode)
         gr = torch.cuda.CUDAGraph()
         tree.knn(X, 11, return_dist=False); torch.cuda.synchronize()
         with torch.cuda.graph(gr):
             tree.knn(X, 11, return_dist=False)
         row.append(timeit(gr.replay))
     print(f"m={m:6d}  warp {row[0]*1e3:7.1f} us   thread {row[1]*1e3:7.1f} us   brute force {row[2]*1e3:7.1f} us", flush=True)
-lib.sbp_tune(b"knn_cells", 2)
+tune("knn_cells", 2)

@@ -3,6 +3,7 @@ import sys, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import sbp_env_b200 as sg
 from sbp_env_b200 import _lib
+from sbp_env_b200.runtime import tune  # noqa: E402
 lib = _lib.load()
 dev = torch.device("cuda", 0)
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -19,7 +20,7 @@ for n in (50_000, 1_000_000):
     X = tree.rows_device(0, n)
     ref = None
     for mode, dens, qpw in ((3, 150, 32), (3, 150, 28), (3, 150, 24), (3, 150, 20), (3, 150, 18), (3, 150, 16)):
-        lib.sbp_tune(b"knn_cells", mode); lib.sbp_tune(b"knn_cell_density", dens); lib.sbp_tune(b"knn_cells_qpw", qpw)
+        tune("knn_cells", mode); tune("knn_cell_density", dens); tune("knn_cells_qpw", qpw)
         gr = torch.cuda.CUDAGraph()
         tree.knn(X, 11, return_dist=False); torch.cuda.synchronize()
         with torch.cuda.graph(gr):

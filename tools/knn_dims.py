@@ -9,6 +9,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import sbp_env_b200 as sg  # noqa: E402
 from sbp_env_b200 import _lib  # noqa: E402
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
@@ -36,7 +37,7 @@ for name, d, scale, off in (("arm d=4", 4, [1024, 1024, 2 * np.pi, 2 * np.pi], [
     tree.extend(P)
     X = tree.rows_device(0, m)
     for filt in (0, 1):
-        lib.sbp_tune(b"knn_filter", filt)
+        tune("knn_filter", filt)
         ms = timeit(lambda: tree.knn(X, 11, return_dist=False))
         print(f"{name}: filter={filt} {ms:.3f} ms  {n * m / ms * 1e3:.3e} evals/s", flush=True)
-lib.sbp_tune(b"knn_filter", 1)
+tune("knn_filter", 1)

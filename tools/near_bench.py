@@ -9,6 +9,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import sbp_env_b200 as sg  # noqa: E402
 from sbp_env_b200 import _lib  # noqa: E402
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
@@ -19,7 +20,7 @@ tree = sg.NodeStore(2, capacity=n)
 tree.extend(torch.rand((n, 2), generator=g, device=dev, dtype=torch.float64) * 16384)
 X = torch.rand((m, 2), generator=g, device=dev, dtype=torch.float64) * 16384
 for filt in (1, 0):
-    lib.sbp_tune(b"near_filter", filt)
+    tune("near_filter", filt)
     for _ in range(2):
         rp, ix = tree.near(X, 64.0)
     torch.cuda.synchronize()

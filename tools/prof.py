@@ -6,6 +6,7 @@
     python tools/prof.py arm        # 2^18 arm edges on the 1024^2 map
     python tools/prof.py nearest    # 1 query over 2^20 nodes
     python tools/prof.py step       # the bench step (cfg2 PRM connect: kNN + edges + visible), eager launches
+    python tools/prof.py cfg5       # cfg5 PRM connect: 1M nodes on the 32k^2 maze, k = 10 (kNN + fused visible)
 """
 import os
 import sys
@@ -48,6 +49,13 @@ if what == "step":
     tree.extend(nodes)
     ms = timeit(lambda: sg.prm_connect_knn(cc, tree, bench.K_NN))
     print(what, "ms (eager, host-bound)", ms)
+elif what == "cfg5":
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import workloads
+
+    mz, cc, tree, nodes, S, T = workloads.cfg5_on_device(dev)
+    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, 10))
+    print(what, "ms (eager)", ms)
 elif what in ("knn", "nearest"):
     free = load_map("intel_lab")
     W, H = free.shape

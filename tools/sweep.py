@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import sbp_env_b200 as sg  # noqa: E402
 from sbp_env_b200 import _lib  # noqa: E402
 from _util import load_map  # noqa: E402
+from sbp_env_b200.runtime import tune  # noqa: E402
 
 lib = _lib.load()
 dev = torch.device("cuda", 0)
@@ -53,17 +54,17 @@ print("workload            " + " ".join(f"{v[0]}{'' if v[1] else ':' + str(v[2])
 for name, (P, Q) in sets.items():
     row = []
     for _, G, c in variants:
-        lib.sbp_tune(b"visible_group", G)
-        lib.sbp_tune(b"coop_below", c)
+        tune("visible_group", G)
+        tune("coop_below", c)
         row.append(timeit(lambda: cc.visible_batch(P, Q)))
     print(f"{name:20s}" + " ".join(f"{t * 1e3:10.1f}us" for t in row), " vis=%.3f" % cc.visible_batch(P, Q).float().mean().item())
-lib.sbp_tune(b"visible_group", 0)
-lib.sbp_tune(b"coop_below", 12)
+tune("visible_group", 0)
+tune("coop_below", 12)
 
 tree = sg.NodeStore(2, capacity=50000)
 tree.extend(torch.rand((50000, 2), generator=g, device=dev, dtype=torch.float64) * scale)
 X = tree.rows_device(0, 50000)
 for S in (0, 1, 2, 3, 4, 6):
-    lib.sbp_tune(b"knn_chunks", S)
+    tune("knn_chunks", S)
     print("knn 50k x 50k k=11 chunks", S, "ms", timeit(lambda: tree.knn(X, 11, return_dist=False)))
-lib.sbp_tune(b"knn_chunks", 0)
+tune("knn_chunks", 0)
