@@ -1,21 +1,26 @@
 #!/usr/bin/env python
-"""bench.py -- the hot path on BASELINE.json configs[1]: PRM roadmap connection on
-maps/intel_lab (579x581), 50 000 free samples, k = 10 nearest neighbours, the
-500 000 candidate edges checked through visible_batch.
+"""bench.py -- the hot path on BASELINE.json configs[4] (cfg5): PRM roadmap construction on the
+32 768^2 synthetic maze, 1 000 000 free nodes, k = 10 nearest neighbours -> 10 000 000 candidate
+edges checked through visible_batch, then 4 096 independent start / goal queries.
 
-One step = one pass of the hot path over one batch: exact fp64 kNN of 50 000 rows
-against the 50 000-node roadmap (2.5e9 pairs; answered from a cell grid rebuilt inside
-every step, the brute-force scan behind it is timed separately as roofline_bruteforce),
-and integer-Bresenham visibility of the 500 000 candidate edges.  At N GPUs (weak
-scaling) rank 0's batch is the roadmap's own nodes (= PRM build, self excluded) and
-rank r > 0 connects a further batch of 50 000 free samples to the replicated
-roadmap; the per-rank neighbour/visibility blocks are all-gathered (NCCL) inside the
-step -- the only collective, used to assemble the adjacency.
+One step = one pass of the hot path over the whole roadmap: exact fp64 kNN of every node among
+all nodes (the cell grid is rebuilt inside every step) + integer-Bresenham visibility of the
+10 M candidate edges (map = 128 MiB bit-packed, L2 / HBM resident), the packed adjacency
+(4 bytes per candidate) complete on every rank at the end of the step.  At N GPUs the rows are
+split N ways (STRONG scaling: the total work is fixed) and every rank's block is written
+through the NVSwitch multicast mapping by the visibility kernel itself as the edges are
+decided; the only other synchronisation is the barrier at the end of the step.
+
+After the timed loop the query stage is timed separately (`query_stage`): CSR assembly of the
+undirected roadmap from the packed adjacency, connection of the 8 192 query endpoints, connected
+components, fewest-hop search; the queries are sharded round-robin over the ranks and the hop
+counts all-gathered.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-`--impl reference` times the CPU restatement of the reference (oracle/, all host
-threads) on the same workload, bounded sample per step.  Prints ONE JSON line.
+`--impl reference` times the UNMODIFIED reference (oracle/_ref: prmPlanner.nearest_neighbours +
+ImgCollisionChecker.visible, all host cores via multiprocessing) on bounded samples of the same
+workload.  Prints ONE JSON line.
 """
 from __future__ import annotations
 
@@ -30,47 +35,37 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-N_NODES = 50_000
-K_NN = 10
-MAP = "intel_lab"
+import workloads  # noqa: E402  (synthetic problem generators; harness code)
+
+SCALE = float(os.environ.get("BENCH_SCALE", "1.0"))       # < 1: a smaller maze (debugging only)
+K_NN = workloads.CFG5["k"]
+K_CONNECT = 8                                              # nearest roadmap nodes tried per query endpoint
 METRIC = "edge collision checks/sec (PRM candidate edges: exact kNN connect + visible_batch)"
 UNIT = "edges/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_knn_filter launch on this workload
-# (ncu --set full, profiles/r1_knn_filter_full.txt)
-FILTER_DRAM_TRAFFIC = 18273024
-# the same for one k_knn_cells_t launch (profiles/r1_knn_cells_full.txt), and that capture's
-# instruction / L1 sector counts (static facts about the kernel on this workload)
-CELLS_DRAM_TRAFFIC = 1956864
-CELLS_NCU = {"warp_instructions": 15318739, "l1_global_load_sectors": 2879287,
-             "issue_active_pct": 39.4, "threads_per_instruction": 21.8, "warps_per_sm": 9.0,
-             "source": "profiles/r1_knn_cells_full.txt"}
-WORKLOAD = ("cfg2: PRM roadmap connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 "
-            "candidate edges per step (exact kNN of 50000 rows among 50000 nodes = 2.5e9 pairs + Bresenham visible_batch)")
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the visibility kernel on this
+# workload (ncu --set full, profiles/r2_visible_cfg5_full.txt)
+VIS_DRAM_TRAFFIC = int(os.environ.get("BENCH_VIS_TRAFFIC", 872389632))
 
 
-def load_free():
-    from _util import load_map
+def problem():
+    mz, nodes, S, T = workloads.cfg5_problem(SCALE)
+    return mz, nodes, S, T
 
-    return load_map(MAP)            # bool [W][H], the reference's `_img == 1`
 
-
-def draw_free_samples(free, n, seed, feasible_fn):
-    """First n accepted of default_rng(seed).random((., 2)) * [W, H] filtered by
-    feasible."""
-    W, H = free.shape
-    rng = np.random.default_rng(seed)
-    out = []
-    have = 0
-    while have < n:
-        c = rng.random((2 * n, 2)) * [W, H]
-        c = c[feasible_fn(c)]
-        out.append(c)
-        have += len(c)
-    return np.ascontiguousarray(np.concatenate(out)[:n])
+def config_dict(mz, n_nodes, n_queries):
+    """The SAME dict from both arms (the driver compares them)."""
+    wl = (f"cfg5: PRM roadmap on a {mz.W}x{mz.H} seeded recursive-backtracker maze "
+          f"({mz.cells}x{mz.cells} cells of {mz.pitch} px, walls {mz.wall} px), {n_nodes} free nodes, k={K_NN} -> "
+          f"{n_nodes * K_NN} candidate edges per step (exact kNN of every node among all nodes + Bresenham "
+          f"visible_batch, adjacency assembled on every rank); {n_queries} start/goal queries timed separately")
+    return {"workload": wl, "map": f"synthetic maze {mz.W}x{mz.H}, seed {mz.seed}, bit-packed {mz.W * mz.H // 8} bytes",
+            "nodes": int(n_nodes), "k": K_NN, "edges_per_step": int(n_nodes * K_NN), "queries": int(n_queries),
+            "l2": "flushed (256 MiB write) between timed steps; the 128 MiB map exceeds what L2 keeps anyway",
+            "scale": SCALE}
 
 
 class ClockSampler:
@@ -145,7 +140,6 @@ def run_ours(args):
     import torch.distributed as dist
 
     import sbp_env_b200 as sg
-    from sbp_env_b200 import _lib
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -154,140 +148,100 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    free = load_free()
-    W, H = free.shape
-    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8), device=local)
+
+    # ---- the problem: identical on every rank (seeded host generators) ----------------
+    mz, nodes_h, S_h, T_h = problem()
+    n, k = len(nodes_h), K_NN
+    nq = len(S_h)
+    free = mz.raster_device(dev)
+    cc = sg.ImgCollisionChecker.from_free_mask(free, device=local)
+    del free
     ctx = cc.device_map.ctx
-    nodes = draw_free_samples(free, N_NODES, 0, cc.feasible_batch)
-    tree = sg.NodeStore(2, capacity=N_NODES, device=local)
-    tree.extend(nodes)
-    if rank == 0:
-        batch_host, queries = nodes, None
-    else:
-        batch_host = draw_free_samples(free, N_NODES, 100 + rank, cc.feasible_batch)
-        queries = torch.from_numpy(batch_host).to(dev)
-    m, k = N_NODES, K_NN
-    edges_per_rank = m * k
-    gathered = {}
+    nodes_d = torch.from_numpy(nodes_h).to(dev)
+    tree = sg.NodeStore(2, capacity=n, device=local)
+    tree.extend(nodes_d)
+    first, count = sg.distributed.shard_range(n, rank, world)
+    edges_total = n * k
 
-    names = ("knn", "edges", "visible", "gather")
-
-    # N > 1: the packed adjacency is assembled on every rank by ONE kernel that packs the block
-    # and stores it over NVLink into every rank's symmetric buffer, plus a signal-pad barrier
-    # (PeerAdjacencyGather); NCCL all-gather of the packed block when peer memory is unavailable
-    peer = None
-    gather_kind = "none (N = 1)"
+    # N > 1: every rank's block of the packed adjacency is stored through the NVSwitch multicast
+    # mapping of a symmetric buffer by the visibility kernel itself; NVLink peer stores from a
+    # separate pack kernel, or an NCCL all-gather, when the fabric / torch lacks the mapping
+    peer, exchange = None, "none (N = 1): packed adjacency written to a local buffer"
     if world > 1:
-        try:
-            peer = sg.distributed.PeerAdjacencyGather(m, k, device=local)
-            gather_kind = f"one pack + {peer.kind} kernel, symmetric-memory barrier"
-        except Exception as e:      # noqa: BLE001
-            gather_kind = f"NCCL all-gather of the packed block (peer memory unavailable: {type(e).__name__})"
-
-    # where the fabric has the multicast mapping, the visibility kernel itself sends the packed
-    # adjacency through the switch (one captured graph per buffer half) and only the barrier follows
-    fused_exchange = peer is not None and peer.fused
-    if fused_exchange:
-        gather_kind = "fused: the visibility kernel stores the packed adjacency through the NVSwitch " \
-                      "multicast mapping as edges are decided; symmetric-memory barrier"
-
-    def gather(nbr, vis):
-        if world == 1:
-            gathered["nbr"], gathered["vis"] = nbr, vis
-        elif peer is not None:
-            gathered["packed"] = peer.gather(nbr, vis)
+        if n % world == 0:
+            try:
+                peer = sg.distributed.PeerAdjacencyGather(count, k, device=local)
+            except Exception as e:      # noqa: BLE001
+                exchange = f"NCCL all-gather of the packed blocks (peer memory unavailable: {type(e).__name__})"
         else:
-            gathered["packed"] = sg.distributed.all_gather_adjacency(nbr, vis, unpack=False)
+            exchange = "NCCL all-gather of the packed blocks (rows not divisible by the ranks)"
+    fused = peer is not None and peer.fused
+    if peer is not None:
+        exchange = ("fused: the visibility kernel stores the packed adjacency through the NVSwitch multicast "
+                    "mapping as edges are decided; symmetric-memory barrier" if fused else
+                    f"one pack + {peer.kind} kernel, symmetric-memory barrier")
+    packed_local = torch.empty((count, k), dtype=torch.int32, device=dev)
+    packed_full = {}                                  # filled by every step: int32 [n][k]
+    peer_step = [0]
 
-    def eager_step(ev=None):
-        idx = [0]
-
-        def mark(_name):
-            if ev is not None:
-                ev[idx[0]].record()
-                idx[0] += 1
-
-        if fused_exchange:
+    def eager_step(mark=None):
+        if fused:
             h = peer_step[0] & 1
             peer_step[0] += 1
-            if rendezvous_eager[0]:
-                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark,
-                                              packed_out=peer.target_with_rendezvous(h))
-                gathered["packed"] = peer.view(h)
-            else:
-                nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark, packed_out=peer.target(h))
-                gathered["packed"] = peer.complete(h)
+            nbr, vis = sg.prm_connect_knn(cc, tree, k, rows=(first, count), mark=mark, packed_out=peer.target(h))
+            packed_full["p"] = peer.complete(h)
         else:
-            nbr, vis = sg.prm_connect_knn(cc, tree, k, queries=queries, mark=mark)
-            gather(nbr, vis)
-        mark("gather")
+            nbr, vis = sg.prm_connect_knn(cc, tree, k, rows=(first, count), mark=mark, packed_out=packed_local)
+            if world == 1:
+                packed_full["p"] = packed_local
+            elif peer is not None:
+                packed_full["p"] = peer.gather(nbr, vis)
+            else:
+                packed_full["p"] = sg.distributed.all_gather_adjacency(
+                    nbr, vis, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
+        if mark:
+            mark("exchange")
         return nbr, vis
 
-    peer_step = [0]
-    rendezvous_eager = [fused_exchange and os.environ.get("BENCH_EXCHANGE", "barrier") == "rendezvous"]
-
-    # The step is ~20 short kernels; issued one by one from Python the launch gaps cost ~15 %,
-    # so the timed loop replays the step from a CUDA graph (the library's
-    # PRMConnectGraph); the all-gather (N > 1) follows the replay on the same stream.
+    # the timed loop replays the step from a CUDA graph captured by the library (one per buffer half
+    # when the exchange is fused; the barrier is captured too where torch allows it)
     barrier_in_graph = False
-    rendezvous = False
-    if fused_exchange:
-        mode = os.environ.get("BENCH_EXCHANGE", "barrier")
-        if mode == "rendezvous":
-            # the kernel itself meets the other ranks: its last CTA publishes an epoch through the
-            # switch and waits for every rank's (no barrier launch).  Measured at N = 2: 0.126 ms per
-            # step against 0.120 ms with the captured symmetric-memory barrier, hence not the default.
-            gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries,
-                                         packed_out=peer.target_with_rendezvous(h)) for h in (0, 1)]
-            rendezvous = True
-            gather_kind += " -- replaced by a rendezvous inside the kernel (last CTA: multicast epoch + wait)"
-        else:
-            # the barrier is captured into the step's graph when torch's symmetric-memory barrier
-            # allows it (BENCH_EXCHANGE=eager_barrier keeps it as a separate launch after the replay)
-            if mode != "eager_barrier":
-                try:
-                    gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h),
-                                                 after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
-                    barrier_in_graph = True
-                except Exception as e:      # noqa: BLE001
-                    print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
-            ok = torch.tensor([1 if barrier_in_graph else 0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            barrier_in_graph = bool(ok.item())
-            if not barrier_in_graph:
-                gsteps = [sg.PRMConnectGraph(cc, tree, k, queries=queries, packed_out=peer.target(h)) for h in (0, 1)]
-            gather_kind += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
+    if fused:
+        try:
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=peer.target(h),
+                                         after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
+            barrier_in_graph = True
+        except Exception as e:      # noqa: BLE001
+            print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
+        ok = torch.tensor([1 if barrier_in_graph else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        barrier_in_graph = bool(ok.item())
+        if not barrier_in_graph:
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=peer.target(h)) for h in (0, 1)]
+        exchange += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
         dist.barrier()
     else:
-        gstep = sg.PRMConnectGraph(cc, tree, k, queries=queries)
+        gstep = sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=packed_local)
 
     def step():
-        if fused_exchange:
+        if fused:
             h = peer_step[0] & 1
             peer_step[0] += 1
             nbr, vis = gsteps[h].replay()
-            gathered["packed"] = peer.view(h) if (barrier_in_graph or rendezvous) else peer.complete(h)
+            packed_full["p"] = peer.view(h) if barrier_in_graph else peer.complete(h)
         else:
             nbr, vis = gstep.replay()
-            gather(nbr, vis)
+            if world == 1:
+                packed_full["p"] = packed_local
+            elif peer is not None:
+                packed_full["p"] = peer.gather(nbr, vis)
+            else:
+                packed_full["p"] = sg.distributed.all_gather_adjacency(
+                    nbr, vis, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
         return nbr, vis
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall0 = time.time()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     def align_ranks():
         # N > 1: the untimed L2 flush does not take the same time on every rank; without this the
         # timed step of an early rank would include waiting for a rank that is still flushing
@@ -297,159 +251,202 @@ def run_ours(args):
             else:
                 dist.barrier()
 
-    for s in range(args.steps):
-        flush.zero_()                      # evict L2 between timed iterations (not timed)
-        align_ranks()                      # (not timed) all ranks start the step together
-        starts[s].record()
+    def timed_loop(fn, steps):
+        a = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        b = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for s in range(steps):
+            flush.zero_()                      # evict L2 between timed iterations (not timed)
+            align_ranks()                      # (not timed) all ranks start the step together
+            a[s].record()
+            fn()
+            b[s].record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([sum(a[s].elapsed_time(b[s]) for s in range(steps))], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
         step()
-        ends[s].record()
     torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    total_ms = timed_loop(step, args.steps)
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    step_ms = np.array([starts[s].elapsed_time(ends[s]) for s in range(args.steps)])
-    total_ms = torch.tensor([float(step_ms.sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
-    # ---- phase breakdown and the dominant kernel's duration: the same step launched eagerly.
-    # A spin kernel ahead of each step lets the host run ahead, so that the events measure
-    # the GPU and not the Python launch path; sbp_tune("time_kernels") brackets k_knn_filter
-    # with its own CUDA events on the launching stream.
-    import ctypes as C
-
-    lib = _lib.load()
+    # ---- phase breakdown and the dominant kernel's own duration: the same step launched eagerly
+    # behind a spin kernel (the host runs ahead, so the events measure the GPU); the visibility
+    # kernel is bracketed by its own CUDA events on the launching stream
+    names = ("knn", "edges", "visible", "exchange")
     psteps = min(args.steps, 10)
     for _ in range(2):
         eager_step()
     torch.cuda.synchronize()
     launches0 = ctx.launches
-    lib.sbp_tune(b"time_kernels", 2)       # event pair around the cell-grid kNN kernel
+    ctx.tune("time_kernels", 3)
     p_start = [torch.cuda.Event(enable_timing=True) for _ in range(psteps)]
     phase_ev = [[torch.cuda.Event(enable_timing=True) for _ in names] for _ in range(psteps)]
     for s in range(psteps):
         flush.zero_()
-        torch.cuda._sleep(4_000_000)       # ~2 ms head start for the host
+        torch.cuda._sleep(6_000_000)       # ~3 ms head start for the host
         align_ranks()
         p_start[s].record()
-        eager_step(phase_ev[s])
+        it = iter(phase_ev[s])
+        eager_step(mark=lambda _name, it=it: next(it).record())
     torch.cuda.synchronize()
-    lib.sbp_tune(b"time_kernels", 0)
-    kt_ms, kt_n = C.c_double(), C.c_int64()
-    _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
-    cells_ms, cells_n = kt_ms.value / max(1, kt_n.value), int(kt_n.value)
+    ctx.tune("time_kernels", 0)
+    vis_ms_total, vis_n = ctx.kernel_time()
+    vis_ms = vis_ms_total / max(1, vis_n)
     launches_per_step = (ctx.launches - launches0) // psteps
-    launches = launches_per_step * args.steps
     ph = {}
     for i, nme in enumerate(names):
         prev = [p_start[s] if i == 0 else phase_ev[s][i - 1] for s in range(psteps)]
         ph[nme] = float(np.mean([prev[s].elapsed_time(phase_ev[s][i]) for s in range(psteps)]))
+    # the cell-grid kNN kernel the same way
+    ctx.tune("time_kernels", 2)
+    for s in range(3):
+        flush.zero_()
+        eager_step()
+    torch.cuda.synchronize()
+    ctx.tune("time_kernels", 0)
+    knn_ms_total, knn_n = ctx.kernel_time()
+    knn_kernel_ms = knn_ms_total / max(1, knn_n)
 
-    # parity spot check of the timed configuration (outside the timed region)
+    # ---- parity of the timed configuration (outside the timed region) ----------------------
     nbr, vis = step()
     torch.cuda.synchronize()
-    n_vis = int(vis.sum().item())
     nbr_e, vis_e = eager_step()
+    torch.cuda.synchronize()
     assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e), "graph replay differs from the eager step"
-    if world > 1:      # the assembled adjacency holds this rank's block at its place
-        torch.cuda.synchronize()
-        gn, gv = sg.distributed.unpack_adjacency(gathered["packed"][rank * m:(rank + 1) * m])
-        assert torch.equal(gn, nbr_e) and torch.equal(gv, vis_e), "assembled adjacency differs from the local block"
+    full = packed_full["p"]
+    assert tuple(full.shape) == (n, k)
+    gn, gv = sg.distributed.unpack_adjacency(full[first:first + count])
+    assert torch.equal(gn, nbr_e) and torch.equal(gv, vis_e), "assembled adjacency differs from the local block"
+    adjacency_check = "single rank"
+    if world > 1:
+        # the WHOLE assembled adjacency against an NCCL all-gather of the same blocks, on every rank
+        want = sg.distributed.all_gather_adjacency(
+            nbr_e, vis_e, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
+        same = torch.tensor([1 if torch.equal(want, full) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        assert bool(same.item()), "adjacency assembled through peer memory differs from the NCCL all-gather"
+        adjacency_check = f"equal to the NCCL all-gather of the {world} blocks on every rank"
+    n_vis = int((full & 1).sum().item())
+    # size-independent properties at full size: the 2-D checker is direction symmetric, and a
+    # visible edge has feasible endpoints
+    rows_idx = torch.arange(first, first + count, device=dev).repeat_interleave(k)
+    P = nodes_d[nbr_e.reshape(-1).clamp(min=0)].contiguous()
+    Q = nodes_d[rows_idx].contiguous()
+    v_rev = cc.visible_batch(Q, P).reshape(count, k) & (nbr_e >= 0)
+    assert torch.equal(v_rev, vis_e), "visible(p, q) != visible(q, p)"
+    assert bool((~vis_e.reshape(-1) | (cc.feasible_batch(P) & cc.feasible_batch(Q))).all().item())
+    px_full = float((torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
+                                   (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item())
+    del P, Q, rows_idx, v_rev
+    px_t = torch.tensor([px_full], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(px_t)
+    px_total = float(px_t.item())
 
-    # ---- the brute-force scan (the path of queries the cell grid cannot answer), same rows:
-    # kNN alone with sbp_tune("knn_cells", 0), k_knn_filter bracketed by its own events
-    Xq = queries if queries is not None else tree.rows_device(0, m)
-    kq = k if queries is not None else k + 1
-    lib.sbp_tune(b"knn_cells", 0)
-    lib.sbp_tune(b"time_kernels", 1)
-    try:
-        idx_bf, _ = tree.knn(Xq, kq, return_dist=False)
-        torch.cuda.synchronize()
-        _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
-        bf_a, bf_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        bf_ms = []
-        for _ in range(psteps):
-            flush.zero_()
-            torch.cuda._sleep(2_000_000)
-            bf_a.record()
-            tree.knn(Xq, kq, return_dist=False)
-            bf_b.record()
-            torch.cuda.synchronize()
-            bf_ms.append(bf_a.elapsed_time(bf_b))
-        _lib.check(lib.sbp_ctx_kernel_time(ctx.handle, C.byref(kt_ms), C.byref(kt_n)))
-        filter_ms, filter_n = kt_ms.value / max(1, kt_n.value), int(kt_n.value)
-        bf_call_ms = float(np.median(bf_ms))
-    finally:
-        lib.sbp_tune(b"time_kernels", 0)
-        lib.sbp_tune(b"knn_cells", 2)
-    idx_grid, _ = tree.knn(Xq, kq, return_dist=False)
-    assert torch.equal(idx_bf, idx_grid), "cell-grid kNN differs from the brute-force scan"
+    # ---- query stage: undirected CSR + endpoint connection + components + fewest-hop search ----
+    road = sg.Roadmap(n, device=local)
+    SG_all = np.concatenate([S_h, T_h])
+    mine = np.arange(rank, nq, world)                                  # round-robin shard of the queries
+    SG_mine = torch.from_numpy(np.concatenate([S_h[mine], T_h[mine]])).to(dev)
+    hops_all = torch.full((nq,), -2, dtype=torch.int32, device=dev)
+    q_ev = {}
 
-    # ---- end to end through the public API with host buffers -------------------
-    pinned = torch.from_numpy(batch_host).pin_memory()
-    # the step's result travels to the host as the packed adjacency, 4 bytes per candidate edge:
-    # (neighbour + 1) * 2 + visible (distributed.pack_adjacency / unpack_adjacency)
-    code_h = torch.empty((m, k), dtype=torch.int32).pin_memory()
-    tree2 = sg.NodeStore(2, capacity=N_NODES, device=local) if rank == 0 else None
+    def query_stage(record=False):
+        def mk(name):
+            if record:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                q_ev[name] = e
+        mk("start")
+        road.build_from_packed(packed_full["p"], undirected=True)
+        mk("csr")
+        ends = sg.connect_to_roadmap(cc, tree, SG_mine, K_CONNECT)
+        mk("connect")
+        m_q = len(mine)
+        hops = road.shortest_paths(ends[:m_q].contiguous(), ends[m_q:].contiguous())
+        mk("search")
+        if world > 1:
+            pad = (nq + world - 1) // world
+            buf = torch.full((pad,), -2, dtype=torch.int32, device=dev)
+            buf[:m_q] = hops
+            allh = torch.empty((world * pad,), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(allh, buf)
+            for r in range(world):
+                cnt = len(range(r, nq, world))
+                hops_all[r::world] = allh[r * pad: r * pad + cnt]
+        else:
+            hops_all.copy_(hops)
+        mk("gather")
+        return ends
 
-    x_dev = torch.empty((m, 2), dtype=torch.float64, device=dev)
-    code_dev = torch.empty((m, k), dtype=torch.int32, device=dev)
+    query_stage()
+    torch.cuda.synchronize()
+    q_reps = 3
+    q_ms = timed_loop(query_stage, q_reps) / q_reps
+    ends = query_stage(record=True)
+    torch.cuda.synchronize()
+    q_ph = {b: q_ev[a].elapsed_time(q_ev[b]) for a, b in zip(("start", "csr", "connect", "search"),
+                                                             ("csr", "connect", "search", "gather"))}
+    hh = hops_all.cpu().numpy()
+    assert (hh >= -1).all()
+    _, n_comp = road.components()
+    # parity spot check of the search at full size (rank 0): scipy's BFS on the same CSR for a
+    # few of this rank's queries, reachable ones first
+    query_check = None
+    if rank == 0:
+        query_check = check_queries(road, ends, hh[mine], len(mine))
+
+    # ---- end to end through the public API with host buffers -------------------------------
+    pinned = torch.from_numpy(nodes_h).pin_memory()
+    code_h = torch.empty((count, k), dtype=torch.int32).pin_memory()
+    code_dev = torch.empty((count, k), dtype=torch.int32, device=dev)
+    x_dev = torch.empty((n, 2), dtype=torch.float64, device=dev)
+    tree2 = sg.NodeStore(2, capacity=n, device=local)
     e2e_copy = os.environ.get("BENCH_E2E_COPY", "0") == "1"
 
     def e2e_body():
-        # H2D of this step's samples: rank 0 rebuilds its roadmap from them, and the append kernel
-        # reads the pinned host rows itself (zero-copy: transfer and AoS -> SoA conversion in one
-        # launch; BENCH_E2E_COPY=1: explicit copy first); ranks > 0 query with them, so they are copied
-        if rank != 0 or e2e_copy:
+        # H2D of the step's samples: the node-store append kernel reads the pinned host rows itself
+        # (zero-copy: transfer and AoS -> SoA conversion in one launch; BENCH_E2E_COPY=1: explicit copy
+        # first).  D2H of this rank's adjacency block: the visibility kernel stores the packed codes
+        # straight into the pinned host buffer (mapped into the device's address space) as the edges
+        # are decided; BENCH_E2E_COPY=1: device buffer + copy.
+        if e2e_copy:
             x_dev.copy_(pinned, non_blocking=True)
-        # D2H of the adjacency block: the visibility kernel packs it and (default) stores it straight
-        # into the pinned host buffer -- mapped into the device's address space (UVA) -- as the edges
-        # are decided, so the transfer overlaps the kernel; BENCH_E2E_COPY=1: device buffer + copy
-        dst = code_dev if e2e_copy else (code_h.data_ptr(), False)
-        if rank == 0:
-            tree2.truncate(0)
-            tree2.extend(x_dev if e2e_copy else pinned)    # roadmap rebuilt from the samples
-            sg.prm_connect_knn(cc, tree2, k, packed_out=dst)
-        else:
-            sg.prm_connect_knn(cc, tree, k, queries=x_dev, packed_out=dst)
+        tree2.truncate(0)
+        tree2.extend(x_dev if e2e_copy else pinned)
+        sg.prm_connect_knn(cc, tree2, k, rows=(first, count),
+                           packed_out=code_dev if e2e_copy else (code_h.data_ptr(), False))
         if e2e_copy:
             code_h.copy_(code_dev, non_blocking=True)
 
-    # the user-facing call: the whole host-to-host step captured once (CapturedStep) and
-    # replayed; H2D, store rebuild, connection and D2H all run inside every replay
     e2e_graph = sg.CapturedStep(e2e_body, device=local)
-
-    def e2e_step():
-        e2e_graph.replay()
-
     for _ in range(max(3, args.warmup)):
-        e2e_step()
+        e2e_graph.replay()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    e_s = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    e_e = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    for s in range(args.steps):
-        flush.zero_()
-        align_ranks()
-        e_s[s].record()
-        e2e_step()
-        e_e[s].record()
-    torch.cuda.synchronize()
-    e2e_ms = torch.tensor([sum(e_s[s].elapsed_time(e_e[s]) for s in range(args.steps))], device=dev,
-                          dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        dist.barrier()
-    e2e_ms = float(e2e_ms.item())
+    e2e_ms = timed_loop(e2e_graph.replay, args.steps)
     nb_e2e, vs_e2e = sg.distributed.unpack_adjacency(code_h)
-    assert int(vs_e2e.sum()) == n_vis and torch.equal(nb_e2e, nbr.cpu()), \
+    assert torch.equal(nb_e2e, nbr_e.cpu()) and torch.equal(vs_e2e, vis_e.cpu()), \
         "e2e result differs from the device-resident run"
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -459,285 +456,394 @@ def run_ours(args):
     else:
         hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    evals = float(m) * float(len(tree))
-    knn_s = ph["knn"] / 1e3
-    filt_s = filter_ms / 1e3
-    cells_s = cells_ms / 1e3
-    n_nodes = float(len(tree))
-    # Dominant kernel: k_knn_cells_t (exact kNN from the cell grid, one thread per query).
-    # ALGORITHMIC bytes per launch = every byte it has to touch once: node coordinates (16 B) and
-    # cell-sorted ids (4 B) per node, the cell starts (one int per cell, 1.5 nodes per cell), the
-    # query rows (16 B) and per query the index row ((k + 1) x 8 B), its seed (8 B) and flag (1 B).
-    alg_cells = n_nodes * (16 + 4 + 4.0 / 1.5) + m * (16 + kq * 8 + 9)
-    roof = {"kernel": f"k_knn_cells_t<2,{kq}> (exact kNN from the cell grid, one thread per query; "
-                      f"{100 * cells_ms / sum(ph.values()):.0f}% of the step)",
-            "bound": "hbm", "achieved": alg_cells / cells_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_cells / cells_s / 1e9 / hbm_peak, "traffic": CELLS_DRAM_TRAFFIC,
-            "peak_source": peak_src, "kernel_ms": cells_ms, "kernel_launches_timed": cells_n,
-            "algorithmic_bytes_per_launch": alg_cells,
-            "note": "a gather over L1 / L2-resident arrays (1.6 MB), not an HBM stream: the kernel is "
-                    "bound by its warps' serial chains (dependent loads cell start -> id -> node, "
-                    "lock-step sorted insertions) at ~9 warps per SM; see issue and l2_gather",
-            "issue": dict(CELLS_NCU, warp_instructions_per_query=CELLS_NCU["warp_instructions"] / float(m),
-                          issue_slot_frac=CELLS_NCU["warp_instructions"]
-                          / (148 * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6) / cells_s),
-            "l2_gather": {"l1_sector_GBps": CELLS_NCU["l1_global_load_sectors"] * 32 / cells_s / 1e9},
-            "queries_per_s_kernel": m / cells_s,
-            "effective_pair_rate_per_s": evals / cells_s}
-    # The brute-force scan k_knn_filter (all m x n pairs), which the step used before the cell grid
-    # and which still serves the queries the grid cannot answer.  ALGORITHMIC bytes per launch
-    # (8 d / Q_tile per distance evaluation when Q_tile queries share a streamed
-    # node; the scan streams the fp32 shadow, 4 (d + 1) bytes per node, to CTAs of Q_tile = 256
-    # queries) + the query rows + the candidate lists.
-    q_tile = 256
-    alg_bytes = evals * 4 * 3 / q_tile + m * 16 + m * 8 + m * 24 * 4
-    brute = {"kernel": "k_knn_filter<2> (brute-force scan: all 2.5e9 pairs), kNN call with "
-                       "sbp_tune('knn_cells', 0)",
-             "bound": "hbm", "achieved": alg_bytes / filt_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-             "frac": alg_bytes / filt_s / 1e9 / hbm_peak, "traffic": FILTER_DRAM_TRAFFIC,
-             "kernel_ms": filter_ms, "knn_call_ms": bf_call_ms, "kernel_launches_timed": filter_n,
-             "note": "the scan shares every streamed node among 256 queries, so it is bound by the "
-                     "FMA pipe, not by HBM: see fma_pipe"}
+    # Dominant kernel: the 2-D visibility kernel on the L2 / HBM resident map.  ALGORITHMIC bytes
+    # per launch: 33 B per edge (two fp64 endpoints in, one byte out) + 0.125 B
+    # (one map bit) per interpolant of the full Bresenham line.
+    edges_rank = count * k
+    alg_bytes = 33.0 * edges_rank + 0.125 * px_total / world
+    vis_s = vis_ms / 1e3
+    l2_gather = microbench(ctx, 1, 64 << 20, 512)
+    hbm_gather = microbench(ctx, 1, 8 << 30, 512)
+    roof = {"kernel": f"2-D visibility kernel, fused with the kNN-row edge gather ({100 * vis_ms / sum(ph.values()):.0f}% of "
+                      f"the step): {edges_rank} edges, {px_total / world:.4g} interpolants per launch on the 128 MiB map",
+            "bound": "hbm", "achieved": alg_bytes / vis_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": alg_bytes / vis_s / 1e9 / hbm_peak, "traffic": VIS_DRAM_TRAFFIC if world == 1 and SCALE == 1.0 else None,
+            "peak_source": peak_src, "kernel_ms": vis_ms, "kernel_launches_timed": vis_n,
+            "algorithmic_bytes_per_launch": alg_bytes,
+            "edges_per_s_kernel": edges_rank / vis_s, "interpolants_per_s_kernel": px_total / world / vis_s,
+            "note": "a gather of map bits and node coordinates, bound by the integer pipe and by L2 sector gathers, "
+                    "not by the HBM stream: see gather (map sectors touched per second against the measured "
+                    "random-sector gather peaks of this GPU)",
+            "gather": {"map_sectors_per_edge_model": 1.0 + 37.0 / 16.0 * 1.27,
+                       "l2_random_sector_gathers_per_s_64MiB": l2_gather,
+                       "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}}
+    roof["gather"]["map_sector_rate_per_s"] = roof["gather"]["map_sectors_per_edge_model"] * edges_rank / vis_s
+    roof["gather"]["frac_of_l2_gather_peak"] = roof["gather"]["map_sector_rate_per_s"] / l2_gather
 
-    def mb(which, nbytes, iters):
-        ms, units = C.c_double(), C.c_double()
-        _lib.check(lib.sbp_microbench(ctx.handle, which, nbytes, iters, C.byref(ms), C.byref(units)))
-        return units.value / (ms.value / 1e3)
+    sub = {"knn_queries_per_s_per_gpu": count / (ph["knn"] / 1e3),
+           "knn_kernel_ms": knn_kernel_ms, "knn_kernel_queries_per_s": count / (knn_kernel_ms / 1e3),
+           "knn_effective_pairs_per_s_per_gpu": float(count) * n / (ph["knn"] / 1e3),
+           "visible_batch_edges_per_s_per_gpu": edges_rank / (ph["visible"] / 1e3),
+           "interpolant_checks_per_s_per_gpu": px_total / world / (ph["visible"] / 1e3),
+           "prm_build_ms": total_ms / args.steps,
+           "roadmap_edges_visible": n_vis,
+           "build_plus_queries_ms": total_ms / args.steps + q_ms}
+    queries = {"ms": q_ms, "queries_per_s": nq / (q_ms / 1e3), "phases_ms": q_ph, "queries": nq,
+               "k_connect": K_CONNECT, "sharding": f"round-robin over {world} rank(s); hop counts all-gathered",
+               "graph": "undirected (both directions of every visible candidate, duplicates removed)",
+               "arcs": road.n_edges, "components": n_comp,
+               "connected_endpoints_fraction": float(((ends >= 0).float().mean()).item()),
+               "reachable_fraction": float((hh >= 0).mean()),
+               "mean_hops_reachable": float(hh[hh >= 0].mean()) if (hh >= 0).any() else None,
+               "max_hops": int(hh.max()), "parity": query_check,
+               "note": "a k = 10 roadmap on 112-px corridors breaks wherever a corridor stretch of ~90 px holds no "
+                       "sample (about 40 places in this maze), so only a few percent of the random start/goal "
+                       "pairs are connected; the component labels settle the others without a search"}
 
-    fp64_peak = mb(2, 0, 4096)
-    # FMA-pipe roofline of the scan: d fp32 FMAs per (query, node) pair (norm expansion, issued as
-    # packed FFMA2) against the MEASURED packed-FMA rate of this GPU (sbp_microbench 3: independent
-    # fma.rn.f32x2 chains; 127 FMA/clk/SM = the scalar FFMA rate as well).  The scan also needs
-    # ~1.1 min/compare lane-operations per pair (FMNMX3 runs at half the FMNMX rate, microbench 5/6)
-    # which share issue and, partly, datapath with the FMAs (microbench 7: 8 FFMA2 + 8 FMNMX take
-    # 20.7 cycles, not 16): `mixed_bound_frac` relates the kernel to that instruction mix.
-    fma_peak = mb(3, 0, 4096)
-    mix_rate = mb(7, 0, 4096)            # lane-instructions/s of the 1:1 FFMA2 : FMNMX mix
-    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
-    # per warp and group of 8 nodes x 4 queries: 32 FFMA2 + 12 FMNMX3 (= 24 FMNMX slots) + 4 FMNMX
-    # + 7 FSETP ~ 32 packed + 35 ALU operations ~ 67 mixed instructions at the measured mix rate
-    mix_bound_s = evals / 32.0 * 67.0 / mix_rate
-    brute["fma_pipe"] = {"model": "d = 2 fp32 FMAs per (query, node) pair, packed FFMA2",
-                        "achieved_fma_per_s": evals * 2 / filt_s,
-                        "peak_fma_per_s_measured": fma_peak,
-                        "frac": evals * 2 / filt_s / fma_peak,
-                        "mixed_bound_ms": mix_bound_s * 1e3,
-                        "mixed_bound_frac": mix_bound_s / filt_s,
-                        "dist_evals_per_s_kernel": evals / filt_s,
-                        "fp64_equivalent": {"fp64_ops_per_eval": 6, "ops_per_s": evals * 6 / (bf_call_ms / 1e3),
-                                            "measured_peak_unfused_fp64_ops_per_s": fp64_peak,
-                                            "ratio": evals * 6 / (bf_call_ms / 1e3) / fp64_peak}}
-
-    # ---- micro: uniform random edge batches on the same map ------
-    micro = None
-    if world == 1:        # N = 1 only: keeps the N > 1 runs short
-        micro = {}
-        smem_gather = mb(0, int(cc.device_map.info()["packed_bytes"]), 2048)
-        l2_gather = mb(1, 64 << 20, 512)
-        hbm_gather = mb(1, 8 << 30, 512)
-        micro["measured_gather_peaks"] = {"smem_random_word_gathers_per_s": smem_gather,
-                                          "l2_random_sector_gathers_per_s_64MiB": l2_gather,
-                                          "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}
-        g = torch.Generator(device=dev)
-        g.manual_seed(4)
-        scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
-
-        def time_visible(P, Q, iters=5):
-            cc.visible_batch(P, Q)
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ts = []
-            for _ in range(iters):
-                flush.zero_()
-                a.record()
-                r = cc.visible_batch(P, Q)
-                b.record()
-                torch.cuda.synchronize()
-                ts.append(a.elapsed_time(b))
-            px = (torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
-                                (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item()
-            cnt = torch.zeros(1, dtype=torch.int64, device=dev)
-            cc._visible_device(P, Q, px_tested=cnt)
-            t = float(np.median(ts)) / 1e3
-            n = P.shape[0]
-            ab = 33.0 * n + 0.125 * px
-            return {"edges": n, "ms": t * 1e3, "interpolants_full_line": px,
-                    "interpolants_per_s": px / t, "pixel_tests_executed": int(cnt.item()),
-                    "pixel_tests_per_s": int(cnt.item()) / t, "edges_per_s": n / t,
-                    "visible_fraction": float(r.float().mean().item()),
-                    "algorithmic_GBps": ab / t / 1e9, "hbm_frac": ab / t / 1e9 / hbm_peak}
-
-        n_u = 1 << 24
-        P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
-        Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
-        micro["uniform_2^24_edges"] = time_visible(P, Q)
-        # point feasibility: a pure stream of 16 B in + 1 B out per point
-        cc.feasible_batch(P)
-        ts = []
-        for _ in range(5):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            cc.feasible_batch(P)
-            b.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b))
-        tf = float(np.median(ts)) / 1e3
-        micro["feasible_2^24_points"] = {"points": n_u, "ms": tf * 1e3, "points_per_s": n_u / tf,
-                                         "algorithmic_GBps": 17.0 * n_u / tf / 1e9,
-                                         "hbm_frac": 17.0 * n_u / tf / 1e9 / hbm_peak}
-        fr = torch.from_numpy(nodes).to(dev)
-        for L in (8, 32, 128):
-            n_b = 1 << 22
-            base = fr[torch.randint(0, len(nodes), (n_b,), generator=g, device=dev)]
-            ang = torch.rand(n_b, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi)
-            Qb = base + torch.stack([ang.cos(), ang.sin()], 1) * L
-            micro[f"free_start_len{L}_2^22_edges"] = time_visible(base, Qb)
-        del P, Q
-
-        # single-query nearest over a 1M-node tree (RRT-style, latency bound)
-        big = sg.NodeStore(2, capacity=1 << 20, device=local)
-        big.extend(torch.rand((1 << 20, 2), generator=g, device=dev, dtype=torch.float64) * scale)
-        q1 = torch.rand((1, 2), generator=g, device=dev, dtype=torch.float64) * scale
-        big.knn(q1, 1)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(50):
-            big.knn(q1, 1)
-        b.record()
-        torch.cuda.synchronize()
-        t1 = a.elapsed_time(b) / 50 / 1e3
-        micro["nearest_1q_over_2^20_nodes"] = {"ms": t1 * 1e3, "dist_evals_per_s": (1 << 20) / t1,
-                                               "node_stream_GBps": (1 << 20) * 16 / t1 / 1e9}
-
-    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
-    cpu = cpu_prm_sample(free, nodes, target_s=12.0) if world == 1 else None
+    # cfg2 (BASELINE configs[1], the round-1 headline) as a second line, N = 1 only
+    cfg2 = cfg2_line(sg, dev, local, flush) if world == 1 and os.environ.get("BENCH_CFG2", "1") == "1" else None
+    # CPU baseline: the unmodified reference on this box's host cores, in a child process (fork
+    # pool; this process holds a CUDA context), bounded sample
+    cpu = None
+    if world == 1 and os.environ.get("BENCH_CPU", "1") == "1":
+        cpu = cpu_baseline_subprocess(budget_s=14.0)
 
     out = {
-        "metric": METRIC, "value": world * edges_per_rank * args.steps / (total_ms / 1e3), "unit": UNIT,
+        "metric": METRIC, "value": edges_total * args.steps / (total_ms / 1e3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "map": "intel_lab 579x581 (occupancy fixture tests/golden/maps.npz)",
-                   "nodes": N_NODES, "k": K_NN, "edges_per_step_per_gpu": edges_per_rank,
-                   "dist_evals_per_step_per_gpu": evals, "l2": "flushed (256 MiB write) between timed steps; N > 1: ranks aligned by an untimed barrier after the flush",
-                   "launch": "the step (and the e2e step) is replayed from a CUDA graph captured by the "
-                             "library (PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms "
-                             "come from the same step launched eagerly",
-                   "multi_gpu": "rank r connects batch r of 50000 samples to the replicated roadmap; "
-                                "the packed neighbour/visibility blocks are assembled on every rank inside the step"},
+        "config": config_dict(mz, n, nq),
         "clocks": clocks,
-        "e2e": {"value": world * edges_per_rank * args.steps / (e2e_ms / 1e3), "unit": UNIT,
+        "e2e": {"value": edges_total * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
                 "d2h_bytes_per_step": int(code_h.numel() * 4),
-                "result": "packed adjacency int32 [m][k] = (neighbour + 1) * 2 + visible",
+                "result": "packed adjacency int32 [rows of this rank][k] = (neighbour + 1) * 2 + visible",
                 "d2h": "copy from a device buffer" if e2e_copy else
                        "stored by the visibility kernel straight into the pinned host buffer (zero-copy)",
-                "h2d": "copy into a device buffer" if (e2e_copy or rank != 0) else
+                "h2d": "copy into a device buffer" if e2e_copy else
                        "read from the pinned host buffer by the node-store append kernel (zero-copy)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),
-        "adjacency_gather": gather_kind,
+        "launch": "the step (and the e2e step) is replayed from a CUDA graph captured by the library "
+                  "(PRMConnectGraph / CapturedStep); phases_ms and roofline.kernel_ms come from the same step "
+                  "launched eagerly",
+        "multi_gpu": {"rows_per_rank": count, "exchange": exchange, "adjacency_check": adjacency_check},
         "roofline": roof,
-        "roofline_bruteforce": brute,
         "cpu_baseline": cpu,
         "phases_ms": ph,
-        "submetrics": {"knn_queries_per_s_per_gpu": m / knn_s,
-                       "knn_effective_pairs_per_s_per_gpu": evals / knn_s,
-                       "knn_bruteforce_dist_evals_per_s_per_gpu": evals / (bf_call_ms / 1e3),
-                       "visible_batch_edges_per_s_per_gpu": edges_per_rank / (ph["visible"] / 1e3),
-                       "prm_build_ms": total_ms / args.steps,
-                       "roadmap_edges_visible": n_vis},
-        "micro": micro,
+        "submetrics": sub,
+        "query_stage": queries,
+        "cfg2": cfg2,
     }
     print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
+def microbench(ctx, which, nbytes, iters):
+    import ctypes as C
+
+    from sbp_env_b200 import _lib
+
+    ms, units = C.c_double(), C.c_double()
+    _lib.check(_lib.load().sbp_microbench(ctx.handle, which, nbytes, iters, C.byref(ms), C.byref(units)))
+    return units.value / (ms.value / 1e3)
+
+
+def check_queries(road, ends, hops_mine, m_q, n_check=24):
+    """scipy's BFS (csgraph, unweighted) on the same CSR for a few queries of rank 0."""
+    try:
+        import scipy.sparse as sp
+        from scipy.sparse.csgraph import breadth_first_order
+    except Exception as e:      # noqa: BLE001
+        return f"scipy unavailable ({type(e).__name__})"
+    rp, col = road.csr()
+    rp, col = rp.cpu().numpy(), col.cpu().numpy()
+    nn = len(rp) - 1
+    A = sp.csr_matrix((np.ones(len(col), np.int8), col, rp), shape=(nn, nn))
+    e = ends.cpu().numpy()
+    s_idx, t_idx = e[:m_q], e[m_q:]
+    order = np.argsort(-(hops_mine >= 0).astype(np.int64), kind="stable")[:n_check]   # reachable ones first
+    ok, n_reach = True, 0
+    for q in order:
+        s, t = int(s_idx[q]), int(t_idx[q])
+        if s < 0 or t < 0:
+            ok &= hops_mine[q] == -1
+            continue
+        _, pred = breadth_first_order(A, s, directed=True, return_predecessors=True)
+        want, v = 0, t
+        while v != s:                       # depth of t in the BFS tree = fewest hops
+            v = int(pred[v])
+            if v < 0:
+                want = -1
+                break
+            want += 1
+        ok &= int(hops_mine[q]) == want
+        n_reach += want >= 0
+    assert ok, "hop counts differ from scipy's BFS on the same graph"
+    return f"hop counts of {len(order)} queries ({n_reach} reachable) equal scipy.sparse.csgraph BFS on the same CSR"
+
+
+# ------------------------------------------------------------ cfg2 line --------
+def cfg2_line(sg, dev, local, flush):
+    """BASELINE.json configs[1] (the round-1 headline): PRM connection on intel_lab, 50 000 free
+    samples, k = 10 -> 500 000 candidate edges, device-resident, CUDA-graph replay."""
+    import torch
+
+    from _util import load_map
+
+    free = load_map("intel_lab")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8), device=local)
+    rng = np.random.default_rng(0)
+    pts, have = [], 0
+    while have < 50_000:
+        c = rng.random((100_000, 2)) * [W, H]
+        c = c[cc.feasible_batch(c)]
+        pts.append(c)
+        have += len(c)
+    nodes = np.ascontiguousarray(np.concatenate(pts)[:50_000])
+    tree = sg.NodeStore(2, capacity=50_000, device=local)
+    tree.extend(nodes)
+    g = sg.PRMConnectGraph(cc, tree, 10)
+    for _ in range(5):
+        g.replay()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = float(np.mean(ts))
+    launches0 = tree.ctx.launches
+    sg.prm_connect_knn(cc, tree, 10)
+    micro = micro_edges(sg, cc, W, H, nodes, dev, flush)
+    return {"micro": micro, "workload": "cfg2: PRM connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 candidate edges",
+            "ms_per_step": ms, "edges_per_s": 500_000 / (ms / 1e3), "gpu_launches_per_step": int(tree.ctx.launches - launches0),
+            "roadmap_edges_visible": int(g.vis.sum().item())}
+
+
+def micro_edges(sg, cc, W, H, nodes, dev, flush):
+    """Uniform / length-bucketed random edge batches and point feasibility on intel_lab (map
+    resident in shared memory), SURVEY.md 8(d) "micro"."""
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    scale = torch.tensor([W, H], device=dev, dtype=torch.float64)
+    hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) \
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+    def time_visible(P, Q, iters=5):
+        cc.visible_batch(P, Q)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = cc.visible_batch(P, Q)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        px = (torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
+                            (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item()
+        t = float(np.median(ts)) / 1e3
+        nn = P.shape[0]
+        ab = 33.0 * nn + 0.125 * px
+        return {"edges": nn, "ms": t * 1e3, "interpolants_full_line": px, "interpolants_per_s": px / t,
+                "edges_per_s": nn / t, "visible_fraction": float(r.float().mean().item()),
+                "algorithmic_GBps": ab / t / 1e9, "hbm_frac": ab / t / 1e9 / hbm}
+
+    out = {}
+    n_u = 1 << 24
+    P = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+    Q = torch.rand((n_u, 2), generator=g, device=dev, dtype=torch.float64) * scale
+    out["uniform_2^24_edges"] = time_visible(P, Q)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        cc.feasible_batch(P)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    tf = float(np.median(ts)) / 1e3
+    out["feasible_2^24_points"] = {"points": n_u, "ms": tf * 1e3, "points_per_s": n_u / tf,
+                                   "algorithmic_GBps": 17.0 * n_u / tf / 1e9, "hbm_frac": 17.0 * n_u / tf / 1e9 / hbm}
+    fr = torch.from_numpy(nodes).to(dev)
+    for L in (8, 32, 128):
+        n_b = 1 << 22
+        base = fr[torch.randint(0, len(nodes), (n_b,), generator=g, device=dev)]
+        ang = torch.rand(n_b, generator=g, device=dev, dtype=torch.float64) * (2 * np.pi)
+        out[f"free_start_len{L}_2^22_edges"] = time_visible(base, base + torch.stack([ang.cos(), ang.sin()], 1) * L)
+    return out
+
+
 # ------------------------------------------------------------ CPU legs --------
-def cpu_prm_rows(om, nodes, first, count, k):
-    """The oracle port of the step for `count` rows: kNN (k+1, self dropped) + visible."""
+_REF = {}
+
+
+def _ref_worker_init(img, poses):
+    """Runs in every pool worker (fork): the unmodified reference, its checker around the
+    pre-binarised uint8 grid (the reference's own __init__ would build an 8 GiB float64 image,
+    collisionChecker.py:101-108), and the node array."""
+    import ref_shims
+
+    ref_shims.import_reference()
+    from sbp_env.collisionChecker import CollisionChecker, ImgCollisionChecker
+    from sbp_env.planners import prmPlanner
+
+    cc = ImgCollisionChecker.__new__(ImgCollisionChecker)
+    CollisionChecker.__init__(cc)
+    cc._img = img
+    _REF.update(cc=cc, nn=prmPlanner.nearest_neighbours, poses=poses, nodes=range(len(poses)))
+
+
+def _ref_rows(job):
+    """The reference's own code on a few rows: prmPlanner.nearest_neighbours (prmPlanner.py:28-44)
+    with the radius that makes it return the row's k nearest, `if m_g is v: continue`, and
+    ImgCollisionChecker.visible(m_g.pos, v.pos) (prmPlanner.py:91-97)."""
+    rows, radii = job
+    cc, nn, poses, nodes = _REF["cc"], _REF["nn"], _REF["poses"], _REF["nodes"]
+    out = []
+    t0 = time.perf_counter()
+    for v, r in zip(rows, radii):
+        m_near = nn(nodes, poses, poses[v], r)
+        cand = [m for m in m_near if m != v]
+        out.append((int(v), cand, [bool(cc.visible(poses[m], poses[v])) for m in cand]))
+    return out, time.perf_counter() - t0
+
+
+def port_rows(om, nodes, rows, k):
+    """The oracle port (C, OpenMP) of the step for the given rows: kNN (k+1, self dropped) + visible."""
     import c_oracle as orc
 
-    idx, _ = orc.knn(nodes, nodes[first:first + count], k + 1)
-    rows = np.arange(first, first + count)[:, None]
-    is_self = idx == rows
+    idx, dist = orc.knn(nodes, nodes[rows], k + 1)
+    is_self = idx == np.asarray(rows)[:, None]
     drop = np.where(is_self.any(1), is_self.argmax(1), k)
     keep = np.ones_like(idx, bool)
-    keep[np.arange(count), drop] = False
-    nbr = idx[keep].reshape(count, k)
-    vis = om.visible2d(nodes[nbr.reshape(-1)], np.repeat(nodes[first:first + count], k, axis=0))
-    return nbr, vis.reshape(count, k)
-
-
-def cpu_prm_sample(free, nodes, target_s):
-    import c_oracle as orc
-
-    cores = os.cpu_count() or 1
-    orc.set_threads(cores)
-    om = orc.Map(free)
-    t0 = time.perf_counter()
-    cpu_prm_rows(om, nodes, 0, 256, K_NN)
-    probe = time.perf_counter() - t0
-    rows = int(min(len(nodes), max(256, 256 * target_s / max(probe, 1e-4))))
-    t0 = time.perf_counter()
-    cpu_prm_rows(om, nodes, 0, rows, K_NN)
-    dt = time.perf_counter() - t0
-    # the reference itself is single-threaded (SURVEY.md 8(d)): one core on a smaller sample too
-    orc.set_threads(1)
-    rows1 = max(256, rows // (2 * cores))
-    t0 = time.perf_counter()
-    cpu_prm_rows(om, nodes, 0, rows1, K_NN)
-    dt1 = time.perf_counter() - t0
-    orc.set_threads(cores)
-    return {"value": rows * K_NN / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"first {rows} of {len(nodes)} rows of the same workload (kNN k+1 against all "
-                      f"{len(nodes)} nodes + visible of their {rows * K_NN} edges), oracle/oracle.c with "
-                      f"OpenMP on {cores} threads, {dt:.2f} s",
-            "value_1core": rows1 * K_NN / dt1,
-            "sample_1core": f"first {rows1} rows on one thread, {dt1:.2f} s"}
+    keep[np.arange(len(rows)), drop] = False
+    nbr = idx[keep].reshape(len(rows), k)
+    vis = om.visible2d(nodes[nbr.reshape(-1)], np.repeat(nodes[rows], k, axis=0))
+    return nbr, vis.reshape(len(rows), k), dist
 
 
 def run_reference(args):
-    """The reference's algorithm on the host cores (oracle C port, all threads)."""
+    """The reference's own CPU implementation of the path on this box's host cores."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    import multiprocessing as mp
+
     import c_oracle as orc
+    import ref_shims
 
     cores = os.cpu_count() or 1
+    mz, nodes, S_h, T_h = problem()
+    n, k = len(nodes), K_NN
+    img = mz.raster_host()                                   # the reference's `_img` ([W][H] uint8)
+    om = orc.Map.__new__(orc.Map)                            # dense grid shared with the port (no copy)
+    om.img, om.W, om.H = img, mz.W, mz.H
     orc.set_threads(cores)
-    free = load_free()
-    om = orc.Map(free)
-    nodes = draw_free_samples(free, N_NODES, 0, om.feasible2d)
-    t0 = time.perf_counter()
-    cpu_prm_rows(om, nodes, 0, 256, K_NN)
-    probe = time.perf_counter() - t0
-    budget = 150.0 / max(1, args.steps + args.warmup)          # whole run within a few minutes
-    rows = int(min(len(nodes), max(256, 256 * min(budget, 6.0) / max(probe, 1e-4))))
-    for _ in range(args.warmup):
-        cpu_prm_rows(om, nodes, 0, rows, K_NN)
-    ts = []
-    for s in range(args.steps):
-        first = (s * rows) % max(1, len(nodes) - rows)
+    have_ref = ref_shims.reference_available()
+    steps, warmup = args.steps, args.warmup
+    budget = args.budget if args.budget > 0 else 150.0
+    per_step_s = max(0.5, budget / max(1, steps + warmup))
+    rng = np.random.default_rng(11)
+
+    def radii_for(rows):
+        # (untimed) the radius that makes the reference's radius query return exactly the row's k
+        # nearest: just above the (k+1)-th smallest distance (the row itself is the first)
+        _, dist = orc.knn(nodes, nodes[rows], k + 1)
+        return np.nextafter(dist[:, k], np.inf)
+
+    result = {}
+    if have_ref:
+        pool = mp.get_context("fork").Pool(cores, initializer=_ref_worker_init, initargs=(img, nodes))
+        probe_rows = rng.integers(0, n, cores)
+        probe_jobs = [([r], [x]) for r, x in zip(probe_rows, radii_for(probe_rows))]
+        pool.map(_ref_rows, probe_jobs)                       # (workers import the reference here)
         t0 = time.perf_counter()
-        cpu_prm_rows(om, nodes, first, rows, K_NN)
-        ts.append(time.perf_counter() - t0)
-    val = rows * K_NN * len(ts) / sum(ts)
-    sample = (f"{rows} of {len(nodes)} rows per step (kNN k+1 against all nodes + visible of "
-              f"{rows * K_NN} edges), oracle/oracle.c OpenMP x{cores}")
+        pool.map(_ref_rows, probe_jobs)
+        row_s = time.perf_counter() - t0                      # one row per core, in parallel
+        rpw = max(1, int(per_step_s / max(row_s, 1e-3)))      # rows per worker and step
+        ts, row_secs, checked = [], [], 0
+        for s in range(warmup + steps):
+            rows = rng.integers(0, n, cores * rpw)
+            radii = radii_for(rows)
+            jobs = [(rows[w::cores], radii[w::cores]) for w in range(cores)]
+            t0 = time.perf_counter()
+            res = pool.map(_ref_rows, jobs)
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                ts.append(dt)
+                row_secs += [sec / max(1, len(j[0])) for (_, sec), j in zip(res, jobs)]
+            # parity of the port against the reference on this sample
+            flat = [r for part, _ in res for r in part]
+            rr = np.array([r[0] for r in flat])
+            pn, pv, _ = port_rows(om, nodes, rr, k)
+            for (v, cand, vis), a, b in zip(flat, pn, pv):
+                if len(cand) == k:                            # (distance ties at the radius add candidates)
+                    assert sorted(cand) == sorted(a.tolist()) and \
+                        dict(zip(cand, vis)) == dict(zip(a.tolist(), b.tolist())), "port differs from the reference"
+                    checked += 1
+        pool.close()
+        edges_step = cores * rpw * k
+        val = edges_step * len(ts) / sum(ts)
+        result = {"value": val, "kind": "reference", "cores": cores,
+                  "sample": f"{cores * rpw} random rows of {n} per step ({edges_step} candidate edges): the reference's "
+                            f"prmPlanner.nearest_neighbours over all {n} nodes + ImgCollisionChecker.visible per candidate, "
+                            f"unmodified (oracle/_ref), multiprocessing over {cores} cores; {checked} rows also equal to the C port",
+                  "value_1core": k / float(np.mean(row_secs)),
+                  "ms_per_step": 1e3 * sum(ts) / len(ts)}
+    # the C / OpenMP port on the same kind of sample (second figure; the only one when the
+    # reference copy is not staged)
+    t0 = time.perf_counter()
+    port_rows(om, nodes, rng.integers(0, n, 64), k)
+    probe = time.perf_counter() - t0
+    prow = int(min(4096, max(64, 64 * min(per_step_s, 3.0) / max(probe, 1e-4))))
+    pts = []
+    for s in range(3):
+        rows = rng.integers(0, n, prow)
+        t0 = time.perf_counter()
+        port_rows(om, nodes, rows, k)
+        pts.append(time.perf_counter() - t0)
+    port = {"value": prow * k / float(np.median(pts)), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{prow} random rows per step, oracle/oracle.c (brute-force kNN over {n} nodes + Bresenham) with OpenMP on {cores} threads"}
+    if not result:
+        result = dict(port, ms_per_step=1e3 * float(np.median(pts)))
+    cfg = config_dict(mz, n, len(S_h))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
-        "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "nodes": N_NODES, "k": K_NN},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": result["value"], "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": steps, "warmup": warmup,
+        "ms_per_step": result["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": cfg,
+        "cpu_baseline": {"value": result["value"], "unit": UNIT, "cores": cores, "kind": result["kind"],
+                         "sample": result["sample"], "value_1core": result.get("value_1core"), "port": port},
+        "e2e": {"value": result["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+def cpu_baseline_subprocess(budget_s):
+    """`bench.py --impl reference` in a child process with a small budget; its cpu_baseline object."""
+    try:
+        o = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2",
+                            "--warmup", "1", "--budget", str(budget_s)], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+        line = [l for l in o.stdout.splitlines() if l.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:      # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def main():
@@ -746,6 +852,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--budget", type=float, default=0.0,
+                    help="reference arm: seconds of CPU sampling for the whole run (0 = 150)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -606,8 +606,11 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         k_visible2d_adaptive<SM, CT, SM><<<c.grid, c.threads, c.smem, ctx->stream>>>(              \
             mview, EdgeArrays{p2, q2}, n, out, flags, px, coop);                                   \
     } while (0)
-        if (smem) { if (px) SBP_LAUNCH_ADP(true, true); else SBP_LAUNCH_ADP(true, false); }
-        else      { if (px) SBP_LAUNCH_ADP(false, true); else SBP_LAUNCH_ADP(false, false); }
+        {
+            KernelTimer timer(ctx, 3);
+            if (smem) { if (px) SBP_LAUNCH_ADP(true, true); else SBP_LAUNCH_ADP(true, false); }
+            else      { if (px) SBP_LAUNCH_ADP(false, true); else SBP_LAUNCH_ADP(false, false); }
+        }
 #undef SBP_LAUNCH_ADP
         ctx->launches++;
         SBP_CUDA(cudaGetLastError());
@@ -680,7 +683,10 @@ extern "C" int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const
         k_visible2d_adaptive<SM, false, SM, EdgeKnnRows><<<grid, threads, sbytes, ctx->stream>>>(  \
             mview, src, n, vis, flags, nullptr, coop);                                             \
     } while (0)
-    if (smem) SBP_LAUNCH_FUSED(true); else SBP_LAUNCH_FUSED(false);
+    {
+        KernelTimer timer(ctx, 3);
+        if (smem) SBP_LAUNCH_FUSED(true); else SBP_LAUNCH_FUSED(false);
+    }
 #undef SBP_LAUNCH_FUSED
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());

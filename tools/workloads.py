@@ -63,13 +63,34 @@ class Maze:
         return self.free_at(np.trunc(P[:, 0]).astype(np.int64), np.trunc(P[:, 1]).astype(np.int64))
 
     def raster_host(self, dtype=np.uint8):
-        """The reference checker's `_img` ([W][H], 1 = free) as a host array (1 GiB at 32k^2)."""
-        out = np.empty((self.W, self.H), dtype)
-        ys = np.arange(self.H)
-        for x0 in range(0, self.W, 512):
-            xs = np.arange(x0, min(x0 + 512, self.W))
-            out[x0:x0 + len(xs)] = self.free_at(xs[:, None], ys[None, :])
-        return out
+        """The reference checker's `_img` ([W][H], 1 = free) as a host array (1 GiB at 32k^2),
+        assembled from the 16 possible cell tiles (which of the four wall strips are open)."""
+        p, n = self.pitch, self.cells
+        lx = np.arange(p)
+        tiles = np.empty((16, p, p), dtype)
+        for code in range(16):
+            # free_at() of a stand-alone cell whose passages are the bits of `code`
+            h = self.wall // 2
+            in_a = (lx >= h) & (lx < p - h)
+            f = in_a[:, None] & in_a[None, :]
+            if code & 1:
+                f = f | ((lx >= p - h)[:, None] & in_a[None, :])          # east strip
+            if code & 2:
+                f = f | ((lx < h)[:, None] & in_a[None, :])               # west strip
+            if code & 4:
+                f = f | (in_a[:, None] & (lx >= p - h)[None, :])          # south strip
+            if code & 8:
+                f = f | (in_a[:, None] & (lx < h)[None, :])               # north strip
+            tiles[code] = f
+        west = np.zeros((n, n), bool)
+        west[1:] = self.east[:-1]
+        north = np.zeros((n, n), bool)
+        north[:, 1:] = self.south[:, :-1]
+        code = self.east.astype(np.int64) | (west << 1) | (self.south.astype(np.int64) << 2) | (north << 3)
+        out = np.empty((n, p, n, p), dtype)
+        for cx0 in range(0, n, 16):                                       # bounded temporaries
+            out[cx0:cx0 + 16] = tiles[code[cx0:cx0 + 16]].transpose(0, 2, 1, 3)
+        return out.reshape(self.W, self.H)
 
     def raster_device(self, dev):
         """The same grid as a CUDA uint8 tensor [W][H] (for ImgCollisionChecker.from_free_mask)."""
