@@ -73,8 +73,8 @@ struct SbpNvtxRange {
 // ------------------------------------------------------------- handles -----
 // scratch slots: 0,1 kNN partial lists / near work-space; 2-4 staging of the *_host entry points
 // and the fused query; 5,6 cell grid and seeds; 7 append / read staging; 8,9 kNN filter lists;
-// 10,11 spare
-#define SBP_SCRATCH_SLOTS 12
+// 10,11 filter shadow / done flags; 12,13 sbp_prm_connect2d (row poses, kNN rows); 14,15 spare
+#define SBP_SCRATCH_SLOTS 16
 // Tuning / instrumentation knobs (sbp_ctx_tune): per context, so that two contexts -- or two
 // threads driving different contexts -- never see each other's settings.  None of them changes
 // a result; the defaults are the measured optima.
@@ -140,6 +140,17 @@ struct KernelTimer {          // RAII: records an event pair on the launching st
 };
 
 int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out);
+
+// sbp_prm_connect2d -> knn.cu: the queries are the stored rows themselves (X = their poses, row
+// major, all n of them), of which this call answers the cell-sorted positions [p0, p0 + count);
+// on return `ids` is the cell-sorted permutation of the node ids (NULL when no cell grid was
+// built: the rows were then all answered, in index order).
+struct KnnRowsPart {
+    int64_t p0 = 0, count = 0;
+    int deterministic = 0;           // order the ids inside every cell (all ranks see the same ids)
+    const int32_t *ids = nullptr;    // out
+};
+int32_t sbp_knn_rows_part(sbp_nodes *s, const double *X_all, int32_t k, int64_t *idx, KnnRowsPart *part);
 
 // Device view of the bit-packed occupancy map.
 //   pixel (x, y), 0 <= x < W, 0 <= y < H  (the reference's `_img[x, y]`)

@@ -837,6 +837,22 @@ __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity,
     }
 }
 
+// The scatter above places the nodes of a cell in the order their atomics happened to land.  Where
+// several devices must agree on the permutation (the rows of a roadmap split by position in `ids`
+// over the ranks), every cell's segment is sorted by node index: one thread per cell, segments are
+// a handful of entries.
+__global__ void k_cell_sort_segments(const int32_t *__restrict__ start, int64_t L, int32_t *__restrict__ ids) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < L; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t e0 = start[c], e1 = start[c + 1];
+        for (int32_t i = e0 + 1; i < e1; ++i) {
+            const int32_t v = ids[i];
+            int32_t j = i - 1;
+            while (j >= e0 && ids[j] > v) { ids[j + 1] = ids[j]; --j; }
+            ids[j + 1] = v;
+        }
+    }
+}
+
 // seed2[q] = K-th smallest exact fp64 d^2 among ALL nodes of a block of cells around the
 // query's cell that holds at least K nodes -- a subset of the nodes, so an upper bound of the
 // true K-th smallest -- inflated by 1e-9.  GS = 16 or 32 lanes per query.  The block grows ring by ring
@@ -1280,10 +1296,11 @@ k_knn_cells_t(const double *__restrict__ soa, int64_t capacity, const double *__
 
 template <int D, int K>
 static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
-                          double *dist) {
+                          double *dist, KnnRowsPart *part = nullptr) {
     sbp_ctx *ctx = s->ctx;
     const int64_t n = s->n;
     bool wide = m < 256;
+    if (part) part->ids = nullptr;
     int S, tpb = 128;
     if (wide) {
         int64_t want = (4 * (int64_t)ctx->sm_count + m - 1) / m;
@@ -1364,16 +1381,32 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         }
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
+        if (part && part->deterministic) {
+            int sbk = (int)((L + 255) / 256);
+            if (sbk > ctx->sm_count * 8) sbk = ctx->sm_count * 8;
+            k_cell_sort_segments<<<sbk, 256, 0, ctx->stream>>>(start, L, ids);
+            ctx->launches++;
+        }
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
         // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
         if (ctx->tune.knn_filter && ctx->tune.knn_cells) {
             rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
             if (rc) return rc;
+            // rows part: only the cell-sorted positions [p0, p0 + count) are answered here; every
+            // other row counts as done for the kernels behind (their work list is `done == 0`)
+            const bool rows_part = part != nullptr;
+            const int64_t m_cells = rows_part ? part->count : m;
+            const int32_t *order = rows_part ? ids + part->p0
+                                             : ((ctx->tune.knn_cells_order && m == n) ? ids : nullptr);
+            if (rows_part) {
+                SBP_CUDA(cudaMemsetAsync(donebuf, 1, (size_t)m, ctx->stream));
+                part->ids = ids;
+            }
             KernelTimer timer(ctx, 2);
             // (measured on 50 000 nodes, k = 11, whole call: 4096 queries 44 us warp form / 66 us thread
             // form, 16 384 queries 73 / 74 us, 50 000 queries 137 / 71 us: a one-warp CTA's chain of
             // 32 queries takes ~50 us however few CTAs there are)
-            if (ctx->tune.knn_cells >= 3 || (ctx->tune.knn_cells == 2 && m >= 20000)) {
+            if (rows_part || ctx->tune.knn_cells >= 3 || (ctx->tune.knn_cells == 2 && m >= 20000)) {
                 // first ring radius whose block is expected to hold 2 K nodes (then the rectangle of
                 // the K-th distance usually lies inside the block and there is no second pass)
                 const double per_cell = (double)n / ((double)G * (double)G);
@@ -1385,10 +1418,9 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                 // the kernel is bound by the instructions it issues, not by the length of a warp's chain)
                 if (qpw <= 0 || qpw > 32) qpw = 32;
                 // (8 nodes per lane and step were measured too: 0.077 instead of 0.076 ms on cfg2)
-                k_knn_cells_t<D, K, 4><<<(unsigned)((m + qpw - 1) / qpw), 32, 0, ctx->stream>>>(
-                    s->d_soa, s->capacity, X, m, b4, G, start, ids, k, r_init, ctx->tune.knn_cells_limit / 4, qpw,
-                    (ctx->tune.knn_cells_order && m == n) ? ids : nullptr, (double *)seedbuf, (uint8_t *)donebuf,
-                    pending_all, idx, dist);
+                k_knn_cells_t<D, K, 4><<<(unsigned)((m_cells + qpw - 1) / qpw), 32, 0, ctx->stream>>>(
+                    s->d_soa, s->capacity, X, m_cells, b4, G, start, ids, k, r_init, ctx->tune.knn_cells_limit / 4, qpw,
+                    order, (double *)seedbuf, (uint8_t *)donebuf, pending_all, idx, dist);
             } else {
                 k_knn_cells<D><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
                     s->d_soa, s->capacity, X, m, b4, G, start, ids, k, ctx->tune.knn_cells_limit, (double *)seedbuf,
@@ -1500,16 +1532,25 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
 
 template <int D>
 static int32_t knn_dispatch_k(sbp_nodes *s, const double *X, int64_t m, int32_t k, int64_t *idx,
-                              double *dist) {
+                              double *dist, KnnRowsPart *part = nullptr) {
     // list length K >= k; 11 and 21 are the PRM / RRT* cases (k = 10 or 20 plus self)
-    if (k <= 1) return knn_launch<D, 1>(s, X, m, k, idx, dist);
-    if (k <= 2) return knn_launch<D, 2>(s, X, m, k, idx, dist);
-    if (k <= 4) return knn_launch<D, 4>(s, X, m, k, idx, dist);
-    if (k <= 8) return knn_launch<D, 8>(s, X, m, k, idx, dist);
-    if (k <= 11) return knn_launch<D, 11>(s, X, m, k, idx, dist);
-    if (k <= 16) return knn_launch<D, 16>(s, X, m, k, idx, dist);
-    if (k <= 21) return knn_launch<D, 21>(s, X, m, k, idx, dist);
-    return knn_launch<D, 32>(s, X, m, k, idx, dist);
+    if (k <= 1) return knn_launch<D, 1>(s, X, m, k, idx, dist, part);
+    if (k <= 2) return knn_launch<D, 2>(s, X, m, k, idx, dist, part);
+    if (k <= 4) return knn_launch<D, 4>(s, X, m, k, idx, dist, part);
+    if (k <= 8) return knn_launch<D, 8>(s, X, m, k, idx, dist, part);
+    if (k <= 11) return knn_launch<D, 11>(s, X, m, k, idx, dist, part);
+    if (k <= 16) return knn_launch<D, 16>(s, X, m, k, idx, dist, part);
+    if (k <= 21) return knn_launch<D, 21>(s, X, m, k, idx, dist, part);
+    return knn_launch<D, 32>(s, X, m, k, idx, dist, part);
+}
+
+// kNN of the stored rows themselves for sbp_prm_connect2d (2-D stores): X_all = the n row poses,
+// idx [n][k]; see KnnRowsPart.  Without a cell grid (small stores, knobs off) every row is answered.
+int32_t sbp_knn_rows_part(sbp_nodes *s, const double *X_all, int32_t k, int64_t *idx, KnnRowsPart *part) {
+    sbp_ctx *ctx = s->ctx;
+    const bool grid = s->d == 2 && ctx->tune.knn_seed && ctx->tune.knn_filter && ctx->tune.knn_cells &&
+                      s->n >= 2048 && s->n >= 256;
+    return knn_dispatch_k<2>(s, X_all, s->n, k, idx, nullptr, grid ? part : nullptr);
 }
 
 __global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {

@@ -51,5 +51,19 @@ def kat_png():
     return f
 
 
+def draw_free_samples(free, n, seed, feasible_fn):
+    """First n accepted of default_rng(seed).random((., 2)) * [W, H] filtered by feasible
+    (SURVEY.md section 8(d), cfg2)."""
+    W, H = free.shape
+    rng = np.random.default_rng(seed)
+    out, have = [], 0
+    while have < n:
+        c = rng.random((2 * n, 2)) * [W, H]
+        c = c[feasible_fn(c)]
+        out.append(c)
+        have += len(c)
+    return np.ascontiguousarray(np.concatenate(out)[:n])
+
+
 def reference_present():
     return os.path.isdir("/root/reference/sbp_env")

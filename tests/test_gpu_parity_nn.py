@@ -675,14 +675,14 @@ def test_cfg2_full_size_connection_equals_oracle(sg):
     """BASELINE.json configs[1] at FULL size -- intel_lab, 50 000 free samples, k = 10, i.e. the
     bench workload itself: every neighbour row and every visibility bit of the 500 000
     candidate edges equals the oracle's (the oracle needs ~0.5 s on 16 cores for this)."""
-    import bench
+    from _util import draw_free_samples
 
-    free = bench.load_free()
+    free = load_map("intel_lab")
     cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
-    nodes = bench.draw_free_samples(free, bench.N_NODES, 0, cc.feasible_batch)
-    tree = sg.NodeStore(2, capacity=bench.N_NODES)
+    nodes = draw_free_samples(free, 50_000, 0, cc.feasible_batch)
+    tree = sg.NodeStore(2, capacity=50_000)
     tree.extend(nodes)
-    k = bench.K_NN
+    k = 10
     nbr, vis = sg.prm_connect_knn(cc, tree, k)
     oi, _ = orc.knn(nodes, nodes, k + 1)
     rows = np.arange(len(nodes))[:, None]

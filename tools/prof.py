@@ -40,14 +40,14 @@ def timeit(fn):
 
 
 if what == "step":
-    import bench
+    from _util import draw_free_samples
 
-    free = bench.load_free()
+    free = load_map("intel_lab")
     cc = sg.ImgCollisionChecker.from_free_mask(free.astype(np.uint8))
-    nodes = bench.draw_free_samples(free, bench.N_NODES, 0, cc.feasible_batch)
-    tree = sg.NodeStore(2, capacity=bench.N_NODES)
+    nodes = draw_free_samples(free, 50_000, 0, cc.feasible_batch)
+    tree = sg.NodeStore(2, capacity=50_000)
     tree.extend(nodes)
-    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, bench.K_NN))
+    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, 10))
     print(what, "ms (eager, host-bound)", ms)
 elif what == "cfg5":
     sys.path.insert(0, os.path.join(ROOT, "tools"))
