@@ -160,55 +160,55 @@ def run_ours(args):
     nodes_d = torch.from_numpy(nodes_h).to(dev)
     tree = sg.NodeStore(2, capacity=n, device=local)
     tree.extend(nodes_d)
-    first, count = sg.distributed.shard_range(n, rank, world)
+    _, count = sg.distributed.shard_range(n, rank, world)     # rows of this rank (a run of the cell-sorted order)
     edges_total = n * k
+    SENTINEL = -(1 << 31)
 
-    # N > 1: every rank's block of the packed adjacency is stored through the NVSwitch multicast
-    # mapping of a symmetric buffer by the visibility kernel itself; NVLink peer stores from a
-    # separate pack kernel, or an NCCL all-gather, when the fabric / torch lacks the mapping
+    # N > 1: the rows are split into `world` contiguous runs of the cell-sorted order (spatially
+    # compact shards); every rank's connection kernel stores the packed adjacency of its rows
+    # through the NVSwitch multicast mapping of a symmetric [n][k] buffer as the edges are decided,
+    # so every rank's copy is complete after the barrier.  Without the mapping (or without torch's
+    # symmetric memory) the ranks' rows are merged by an NCCL all-reduce(MAX) over a sentinel.
     peer, exchange = None, "none (N = 1): packed adjacency written to a local buffer"
     if world > 1:
-        if n % world == 0:
-            try:
-                peer = sg.distributed.PeerAdjacencyGather(count, k, device=local)
-            except Exception as e:      # noqa: BLE001
-                exchange = f"NCCL all-gather of the packed blocks (peer memory unavailable: {type(e).__name__})"
-        else:
-            exchange = "NCCL all-gather of the packed blocks (rows not divisible by the ranks)"
+        try:
+            peer = sg.distributed.PeerAdjacencyBuffer(n, k, device=local)
+        except Exception as e:      # noqa: BLE001
+            exchange = f"NCCL all-reduce(MAX) of the packed rows (peer memory unavailable: {type(e).__name__})"
     fused = peer is not None and peer.fused
-    if peer is not None:
-        exchange = ("fused: the visibility kernel stores the packed adjacency through the NVSwitch multicast "
-                    "mapping as edges are decided; symmetric-memory barrier" if fused else
-                    f"one pack + {peer.kind} kernel, symmetric-memory barrier")
-    packed_local = torch.empty((count, k), dtype=torch.int32, device=dev)
+    if fused:
+        exchange = ("fused: the connection kernel stores the packed adjacency of its rows through the NVSwitch "
+                    "multicast mapping as edges are decided; symmetric-memory barrier")
+    elif world > 1 and peer is not None:
+        exchange = "NCCL all-reduce(MAX) of the packed rows (no multicast mapping on this fabric)"
+    packed_local = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
     packed_full = {}                                  # filled by every step: int32 [n][k]
     peer_step = [0]
+    part = (rank, world)
+
+    def nccl_merge():
+        merged = packed_local.clone()
+        dist.all_reduce(merged, op=dist.ReduceOp.MAX)  # every row is written by exactly one rank
+        return merged
 
     def eager_step(mark=None):
         if fused:
             h = peer_step[0] & 1
             peer_step[0] += 1
-            nbr, vis = sg.prm_connect_knn(cc, tree, k, rows=(first, count), mark=mark, packed_out=peer.target(h))
+            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=peer.target(h), want_rows=False)
             packed_full["p"] = peer.complete(h)
         else:
-            nbr, vis = sg.prm_connect_knn(cc, tree, k, rows=(first, count), mark=mark, packed_out=packed_local)
-            if world == 1:
-                packed_full["p"] = packed_local
-            elif peer is not None:
-                packed_full["p"] = peer.gather(nbr, vis)
-            else:
-                packed_full["p"] = sg.distributed.all_gather_adjacency(
-                    nbr, vis, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
+            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=packed_local, want_rows=False)
+            packed_full["p"] = packed_local if world == 1 else nccl_merge()
         if mark:
             mark("exchange")
-        return nbr, vis
 
     # the timed loop replays the step from a CUDA graph captured by the library (one per buffer half
     # when the exchange is fused; the barrier is captured too where torch allows it)
     barrier_in_graph = False
     if fused:
         try:
-            gsteps = [sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=peer.target(h),
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False,
                                          after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
             barrier_in_graph = True
         except Exception as e:      # noqa: BLE001
@@ -217,28 +217,22 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         barrier_in_graph = bool(ok.item())
         if not barrier_in_graph:
-            gsteps = [sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=peer.target(h)) for h in (0, 1)]
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False)
+                      for h in (0, 1)]
         exchange += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
         dist.barrier()
     else:
-        gstep = sg.PRMConnectGraph(cc, tree, k, rows=(first, count), packed_out=packed_local)
+        gstep = sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=packed_local, want_rows=False)
 
     def step():
         if fused:
             h = peer_step[0] & 1
             peer_step[0] += 1
-            nbr, vis = gsteps[h].replay()
+            gsteps[h].replay()
             packed_full["p"] = peer.view(h) if barrier_in_graph else peer.complete(h)
         else:
-            nbr, vis = gstep.replay()
-            if world == 1:
-                packed_full["p"] = packed_local
-            elif peer is not None:
-                packed_full["p"] = peer.gather(nbr, vis)
-            else:
-                packed_full["p"] = sg.distributed.all_gather_adjacency(
-                    nbr, vis, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
-        return nbr, vis
+            gstep.replay()
+            packed_full["p"] = packed_local if world == 1 else nccl_merge()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -286,7 +280,7 @@ def run_ours(args):
     # ---- phase breakdown and the dominant kernel's own duration: the same step launched eagerly
     # behind a spin kernel (the host runs ahead, so the events measure the GPU); the visibility
     # kernel is bracketed by its own CUDA events on the launching stream
-    names = ("knn", "edges", "visible", "exchange")
+    names = ("knn", "edges", "visible", "exchange")     # marks of prm_connect_knn + the exchange
     psteps = min(args.steps, 10)
     for _ in range(2):
         eager_step()
@@ -311,6 +305,8 @@ def run_ours(args):
     for i, nme in enumerate(names):
         prev = [p_start[s] if i == 0 else phase_ev[s][i - 1] for s in range(psteps)]
         ph[nme] = float(np.mean([prev[s].elapsed_time(phase_ev[s][i]) for s in range(psteps)]))
+    # (the one-call connection marks its three phases together: their sum is the call)
+    ph = {"connect_call": ph["knn"] + ph["edges"] + ph["visible"], "exchange": ph["exchange"]}
     # the cell-grid kNN kernel the same way
     ctx.tune("time_kernels", 2)
     for s in range(3):
@@ -322,36 +318,50 @@ def run_ours(args):
     knn_kernel_ms = knn_ms_total / max(1, knn_n)
 
     # ---- parity of the timed configuration (outside the timed region) ----------------------
-    nbr, vis = step()
+    step()
     torch.cuda.synchronize()
-    nbr_e, vis_e = eager_step()
+    replayed = packed_full["p"].clone()
+    eager_step()
     torch.cuda.synchronize()
-    assert torch.equal(nbr, nbr_e) and torch.equal(vis, vis_e), "graph replay differs from the eager step"
     full = packed_full["p"]
     assert tuple(full.shape) == (n, k)
-    gn, gv = sg.distributed.unpack_adjacency(full[first:first + count])
-    assert torch.equal(gn, nbr_e) and torch.equal(gv, vis_e), "assembled adjacency differs from the local block"
+    assert torch.equal(replayed, full), "graph replay differs from the eager step"
+    # this rank's own rows, computed into a private sentinel buffer
+    own = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
+    sg.prm_connect_knn(cc, tree, k, part=part, packed_out=own, want_rows=False)
+    mine_rows = own[:, 0] != SENTINEL
+    assert int(mine_rows.sum().item()) == count, "this rank did not write exactly its share of the rows"
+    assert torch.equal(own[mine_rows], full[mine_rows]), "assembled adjacency differs from the local rows"
     adjacency_check = "single rank"
     if world > 1:
-        # the WHOLE assembled adjacency against an NCCL all-gather of the same blocks, on every rank
-        want = sg.distributed.all_gather_adjacency(
-            nbr_e, vis_e, counts=[sg.distributed.shard_range(n, r, world)[1] for r in range(world)], unpack=False)
-        same = torch.tensor([1 if torch.equal(want, full) else 0], device=dev)
+        # the WHOLE assembled adjacency against an NCCL merge of the ranks' rows, on every rank
+        want = own.clone()
+        dist.all_reduce(want, op=dist.ReduceOp.MAX)
+        owners = mine_rows.to(torch.int32)
+        dist.all_reduce(owners)
+        same = torch.tensor([1 if (torch.equal(want, full) and bool((owners == 1).all().item())) else 0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        assert bool(same.item()), "adjacency assembled through peer memory differs from the NCCL all-gather"
-        adjacency_check = f"equal to the NCCL all-gather of the {world} blocks on every rank"
+        assert bool(same.item()), "adjacency assembled through peer memory differs from the NCCL merge"
+        adjacency_check = f"every row written by exactly one rank; equal to the NCCL merge of the {world} ranks' rows on every rank"
+    # the new one-call path against the generic path (kNN call + general visibility kernel) on a
+    # slice of the rows, bit for bit
+    sl = (rank * 20_000 % max(1, n - 20_000), min(20_000, n))
+    nbr_g, vis_g = sg.prm_connect_knn(cc, tree, k, rows=sl)
+    gn, gv = sg.distributed.unpack_adjacency(full[sl[0]:sl[0] + sl[1]])
+    assert torch.equal(gn, nbr_g) and torch.equal(gv, vis_g), "one-call connection differs from the generic path"
     n_vis = int((full & 1).sum().item())
-    # size-independent properties at full size: the 2-D checker is direction symmetric, and a
-    # visible edge has feasible endpoints
-    rows_idx = torch.arange(first, first + count, device=dev).repeat_interleave(k)
-    P = nodes_d[nbr_e.reshape(-1).clamp(min=0)].contiguous()
-    Q = nodes_d[rows_idx].contiguous()
-    v_rev = cc.visible_batch(Q, P).reshape(count, k) & (nbr_e >= 0)
-    assert torch.equal(v_rev, vis_e), "visible(p, q) != visible(q, p)"
-    assert bool((~vis_e.reshape(-1) | (cc.feasible_batch(P) & cc.feasible_batch(Q))).all().item())
+    # size-independent properties at full size (this rank checks every world-th row): the 2-D
+    # checker is direction symmetric, and a visible edge has feasible endpoints
+    sel = torch.arange(rank, n, world, device=dev)
+    nbr_s, vis_s = sg.distributed.unpack_adjacency(full[sel])
+    P = nodes_d[nbr_s.reshape(-1).clamp(min=0)].contiguous()
+    Q = nodes_d[sel.repeat_interleave(k)].contiguous()
+    v_rev = cc.visible_batch(Q, P).reshape(-1, k) & (nbr_s >= 0)
+    assert torch.equal(v_rev, vis_s), "visible(p, q) != visible(q, p)"
+    assert bool((~vis_s.reshape(-1) | (cc.feasible_batch(P) & cc.feasible_batch(Q))).all().item())
     px_full = float((torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
                                    (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item())
-    del P, Q, rows_idx, v_rev
+    del P, Q, v_rev, nbr_s, vis_s, own
     px_t = torch.tensor([px_full], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(px_t)
@@ -412,8 +422,8 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers -------------------------------
     pinned = torch.from_numpy(nodes_h).pin_memory()
-    code_h = torch.empty((count, k), dtype=torch.int32).pin_memory()
-    code_dev = torch.empty((count, k), dtype=torch.int32, device=dev)
+    code_h = torch.full((n, k), SENTINEL, dtype=torch.int32).pin_memory()   # [n][k]; this rank fills its rows
+    code_dev = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
     x_dev = torch.empty((n, 2), dtype=torch.float64, device=dev)
     tree2 = sg.NodeStore(2, capacity=n, device=local)
     e2e_copy = os.environ.get("BENCH_E2E_COPY", "0") == "1"
@@ -428,7 +438,7 @@ def run_ours(args):
             x_dev.copy_(pinned, non_blocking=True)
         tree2.truncate(0)
         tree2.extend(x_dev if e2e_copy else pinned)
-        sg.prm_connect_knn(cc, tree2, k, rows=(first, count),
+        sg.prm_connect_knn(cc, tree2, k, part=part, want_rows=False,
                            packed_out=code_dev if e2e_copy else (code_h.data_ptr(), False))
         if e2e_copy:
             code_h.copy_(code_dev, non_blocking=True)
@@ -440,8 +450,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     e2e_ms = timed_loop(e2e_graph.replay, args.steps)
-    nb_e2e, vs_e2e = sg.distributed.unpack_adjacency(code_h)
-    assert torch.equal(nb_e2e, nbr_e.cpu()) and torch.equal(vs_e2e, vis_e.cpu()), \
+    mine_h = mine_rows.cpu()
+    assert torch.equal(code_h[mine_h], full[mine_rows].cpu()) and bool((code_h[~mine_h] == SENTINEL).all()), \
         "e2e result differs from the device-resident run"
 
     if rank != 0:
@@ -480,11 +490,14 @@ def run_ours(args):
     roof["gather"]["map_sector_rate_per_s"] = roof["gather"]["map_sectors_per_edge_model"] * edges_rank / vis_s
     roof["gather"]["frac_of_l2_gather_peak"] = roof["gather"]["map_sector_rate_per_s"] / l2_gather
 
-    sub = {"knn_queries_per_s_per_gpu": count / (ph["knn"] / 1e3),
+    knn_part_ms = max(ph["connect_call"] - vis_ms, 1e-6)       # cell grid + kNN kernels of the call
+    sub = {"knn_queries_per_s_per_gpu": count / (knn_part_ms / 1e3),
+           "knn_part_ms": knn_part_ms,
            "knn_kernel_ms": knn_kernel_ms, "knn_kernel_queries_per_s": count / (knn_kernel_ms / 1e3),
-           "knn_effective_pairs_per_s_per_gpu": float(count) * n / (ph["knn"] / 1e3),
-           "visible_batch_edges_per_s_per_gpu": edges_rank / (ph["visible"] / 1e3),
-           "interpolant_checks_per_s_per_gpu": px_total / world / (ph["visible"] / 1e3),
+           "knn_effective_pairs_per_s_per_gpu": float(count) * n / (knn_part_ms / 1e3),
+           "visible_kernel_ms": vis_ms,
+           "visible_batch_edges_per_s_per_gpu": edges_rank / (vis_ms / 1e3),
+           "interpolant_checks_per_s_per_gpu": px_total / world / (vis_ms / 1e3),
            "prm_build_ms": total_ms / args.steps,
            "roadmap_edges_visible": n_vis,
            "build_plus_queries_ms": total_ms / args.steps + q_ms}
@@ -518,7 +531,7 @@ def run_ours(args):
         "e2e": {"value": edges_total * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
-                "d2h_bytes_per_step": int(code_h.numel() * 4),
+                "d2h_bytes_per_step": int(count * k * 4),
                 "result": "packed adjacency int32 [rows of this rank][k] = (neighbour + 1) * 2 + visible",
                 "d2h": "copy from a device buffer" if e2e_copy else
                        "stored by the visibility kernel straight into the pinned host buffer (zero-copy)",

@@ -167,6 +167,7 @@ int32_t sbp_arm_visible_host(sbp_map *map, double L0, double L1, const double *C
 /* ---- node store: device-resident, append-only ------------------------------
  * replaces: the planners' pre-allocated `poses` arrays and their appends
  * (rrtPlanner.py:24-26, :106-113; birrtPlanner.py:24-31; rrdtPlanner.py:858-887). */
+/* d: 2, 3, 4 or 6 (the dimensions the query kernels are instantiated for). */
 int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, sbp_nodes **out);
 int32_t sbp_nodes_destroy(sbp_nodes *nodes);
 /* X: [m][d] fp64, row-major; on_device selects the address space of X.
@@ -253,6 +254,23 @@ int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *n
                                 int32_t k_in, int64_t first_row, const double *X,
                                 int64_t *nbr_out, uint8_t *vis, int32_t *packed,
                                 int32_t packed_multicast, const int64_t *rendezvous, int32_t *flags);
+
+/* The whole roadmap connection step in ONE call, for the 2-D image checker and the rows of the
+ * node store themselves.
+ * replaces: PRMPlanner.build_graph's double loop (prmPlanner.py:91-101) with the k nearest
+ * neighbours as candidate set: for every stored node v its k nearest OTHER nodes m_g (exact, fp64,
+ * ordered by (distance, index); the row's own entry dropped like `if m_g is v: continue`) and
+ * cc.visible(m_g.pos, v.pos) for each.
+ * Rows are processed in the cell-sorted order of the kNN's grid and split into `parts` contiguous
+ * runs of that order (spatially compact shards: one per rank; parts = 1: all rows); this call
+ * handles run `part`.  Outputs (each nullable, at least one given) are [n][k] in NODE order and
+ * only this part's rows are written: nbr_out int64, vis uint8 (1 = slot filled and edge free),
+ * packed int32 = (neighbour + 1) * 2 + visible.  packed may be pinned host memory, or with
+ * packed_multicast != 0 the NVSwitch multicast address of the ranks' symmetric [n][k] buffer:
+ * every rank's rows then land in every rank's copy as the edges are decided. */
+int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
+                          int64_t *nbr_out, uint8_t *vis, int32_t *packed, int32_t packed_multicast,
+                          int32_t *flags);
 
 /* Fused radius query + edge visibility in ONE launch, for the sequential planners.
  * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "sbp_nodes_gather_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp],
     "sbp_nodes_knn_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "sbp_knn_edges_visible2d": [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
+    "sbp_prm_connect2d": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp],
     "sbp_nodes_near_visible": [_vp, _vp, _i32, _dbl, _dbl, _vp, _i64, _dbl, _i32, _i32, _i32, _vp, _vp,
                                _i32, _vp, _vp],
     "sbp_nodes_near_visible_host": [_vp, _vp, _i32, _dbl, _dbl, _vp, _dbl, _i32, _i32, _i32, _vp, _vp,

@@ -275,7 +275,7 @@ class ImgCollisionChecker(_GridChecker):
 
         m = self.device_map
         m.ctx.use_torch_stream()
-        P = as_device_f64(P, 2)
+        P = as_device_f64(P, 2, device=self._device)
         n = P.shape[0]
         out = torch.empty(n, dtype=torch.uint8, device=P.device)
         flags = torch.zeros(1, dtype=torch.int32, device=P.device)
@@ -288,7 +288,7 @@ class ImgCollisionChecker(_GridChecker):
 
         m = self.device_map
         m.ctx.use_torch_stream()
-        P, Q = as_device_f64(P, 2), as_device_f64(Q, 2)
+        P, Q = as_device_f64(P, 2, device=self._device), as_device_f64(Q, 2, device=self._device)
         n = P.shape[0]
         if Q.shape[0] != n:
             raise ValueError("P and Q must have the same length")
@@ -315,7 +315,7 @@ class ImgCollisionChecker(_GridChecker):
         nbr = torch.empty((rows, k_out), dtype=torch.int64, device=dev)
         vis = torch.empty((rows, k_out), dtype=torch.uint8, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
-        X = as_device_f64(queries, 2) if queries is not None else None
+        X = as_device_f64(queries, 2, device=self._device) if queries is not None else None
         self.stats.visible_cnt += rows * k_out
         # packed adjacency written by the kernel itself: a local int32 tensor, or (address, True)
         # = the multicast address of a symmetric buffer (PeerAdjacencyGather.target)
@@ -335,6 +335,47 @@ class ImgCollisionChecker(_GridChecker):
                                                   p_ptr, p_mc, p_sync, ptr(flags)), "sbp_knn_edges_visible2d")
         self._last_flags = flags
         return nbr, vis.view(torch.bool)
+
+    def prm_connect(self, tree, k: int, part=(0, 1), packed_out=None, want_rows: bool = True):
+        """The whole roadmap connection step for the rows of ``tree`` in ONE library call
+        (``sbp_prm_connect2d``; prmPlanner.py:91-101 with the k nearest neighbours as candidates):
+        exact kNN of every stored node among all nodes, own entry dropped, and
+        ``visible(m_g.pos, v.pos)`` of the k candidates, rows walked in the cell-sorted order of
+        the kNN's grid.
+
+        ``part=(i, parts)``: only run i of the ``parts`` contiguous runs of that order (the shard
+        of rank i; the other rows of the outputs are left untouched).  ``packed_out``: int32 CUDA
+        tensor [n][k], or ``(address, multicast)`` -- pinned host memory, or the NVSwitch
+        multicast address of a symmetric buffer (``distributed.PeerAdjacencyBuffer.target``).
+        Returns ``(nbr int64 [n][k], vis bool [n][k])`` CUDA tensors, or ``None`` with
+        ``want_rows=False`` (only the packed adjacency is written)."""
+        import torch
+
+        m = self.device_map
+        m.ctx.use_torch_stream()
+        n = len(tree)
+        dev = torch.device("cuda", m.ctx.device)
+        nbr = torch.empty((n, k), dtype=torch.int64, device=dev) if want_rows else None
+        vis = torch.empty((n, k), dtype=torch.uint8, device=dev) if want_rows else None
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        p_ptr, p_mc = None, 0
+        if packed_out is not None:
+            if isinstance(packed_out, tuple):
+                p_ptr, p_mc = C.c_void_p(int(packed_out[0])), int(bool(packed_out[1]))
+            else:
+                if packed_out.dtype != torch.int32 or packed_out.numel() != n * k \
+                        or not packed_out.is_contiguous() or packed_out.device != dev:
+                    raise ValueError("packed_out must be a contiguous CUDA int32 tensor [n][k]")
+                p_ptr = ptr(packed_out)
+        elif not want_rows:
+            raise ValueError("nothing to compute: want_rows=False and no packed_out")
+        i, parts = int(part[0]), int(part[1])
+        base, rem = divmod(n, parts)
+        self.stats.visible_cnt += (base + (1 if i < rem else 0)) * k
+        check(_lib.load().sbp_prm_connect2d(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),
+                                            p_ptr, p_mc, ptr(flags)), "sbp_prm_connect2d")
+        self._last_flags = flags
+        return (nbr, vis.view(torch.bool)) if want_rows else None
 
     def check_device_flags(self, what="batch"):
         """Synchronise and raise what CPython would have raised for the last device-side
@@ -506,7 +547,7 @@ class RobotArm4dCollisionChecker(_GridChecker):
 
         m = self.device_map
         m.ctx.use_torch_stream()
-        Cfg = as_device_f64(Cfg, 4)
+        Cfg = as_device_f64(Cfg, 4, device=self._device)
         n = Cfg.shape[0]
         L0, L1 = self._lengths()
         out = torch.empty(n, dtype=torch.uint8, device=Cfg.device)
@@ -534,7 +575,7 @@ class RobotArm4dCollisionChecker(_GridChecker):
 
         m = self.device_map
         m.ctx.use_torch_stream()
-        C1, C2 = as_device_f64(C1, 4), as_device_f64(C2, 4)
+        C1, C2 = as_device_f64(C1, 4, device=self._device), as_device_f64(C2, 4, device=self._device)
         n = C1.shape[0]
         L0, L1 = self._lengths()
         out = torch.empty(n, dtype=torch.uint8, device=C1.device)

@@ -28,7 +28,9 @@
 // ------------------------------------------------------------ node store ----
 extern "C" int32_t sbp_nodes_create(sbp_ctx *ctx, int32_t d, int64_t capacity, sbp_nodes **out) {
     SBP_REQUIRE(ctx && out, "sbp_nodes_create: NULL argument");
-    SBP_REQUIRE(d >= 1 && d <= 8, "sbp_nodes_create: 1 <= d <= 8");
+    // the query kernels are instantiated for these dimensions (2-D image space, the 4-D arm, and
+    // 3 / 6 for free-flying bodies); a store of any other dimension could only fail at query time
+    SBP_REQUIRE(d == 2 || d == 3 || d == 4 || d == 6, "sbp_nodes_create: dimension must be 2, 3, 4 or 6");
     SBP_REQUIRE(capacity >= 0 && capacity < ((int64_t)1 << 31), "sbp_nodes_create: bad capacity");
     SBP_DEVICE(ctx);
     sbp_nodes *s = new sbp_nodes();

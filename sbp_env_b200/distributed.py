@@ -208,6 +208,65 @@ class PeerAdjacencyGather:
         return self.view(h)
 
 
+class PeerAdjacencyBuffer:
+    """The roadmap's packed adjacency ``int32 [n][k]`` (node order) replicated on every rank
+    through symmetric memory: every rank's connection kernel stores the rows it owns through the
+    NVSwitch multicast mapping (``target(h)`` -> ``packed_out`` of ``prm_connect_knn(part=...)``),
+    so every rank's copy is complete after the barrier (``complete(h)``); two halves alternate so
+    that step s may still be read while step s + 1 is written.
+
+    >>> buf = PeerAdjacencyBuffer(n, k, device=local_rank)
+    >>> prm_connect_knn(cc, tree, k, part=(rank, world), packed_out=buf.target(h), want_rows=False)
+    >>> packed = buf.complete(h)                 # int32 [n][k] on every rank
+    """
+
+    def __init__(self, n_rows: int, k: int, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from .runtime import get_context
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world > 64:
+            raise ValueError("PeerAdjacencyBuffer: at most 64 ranks")
+        self.n, self.k = int(n_rows), int(k)
+        self.ctx = get_context(device)
+        dev = torch.device("cuda", device)
+        self._half = (self.n * self.k + 3) // 4 * 4
+        self.buf = symm_mem.empty((2, self._half), dtype=torch.int32, device=dev)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)
+        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
+        self._mc = [mc + h * self._half * 4 for h in (0, 1)] if mc else None
+
+    @property
+    def fused(self) -> bool:
+        """True when the fabric offers the multicast mapping."""
+        return self._mc is not None
+
+    def target(self, h: int):
+        if self._mc is None:
+            raise RuntimeError("no multicast mapping on this fabric")
+        return (self._mc[h], True)
+
+    def local(self, h: int):
+        """This rank's own copy of half h as ``packed_out`` (no exchange: for fabrics without the
+        multicast mapping the blocks are then all-gathered by the caller)."""
+        return self.view(h)
+
+    def complete(self, h: int):
+        self.ctx.use_torch_stream()
+        self.hdl.barrier(channel=h)
+        return self.view(h)
+
+    def view(self, h: int):
+        return self.buf[h][: self.n * self.k].view(self.n, self.k)
+
+
 def sharded_visible_batch(visible_fn, P, Q, group=None, costs=None):
     """Every rank holds the full edge list (P, Q); each checks its chunk with
     ``visible_fn`` and the masks are all-gathered, so every rank returns the full mask.

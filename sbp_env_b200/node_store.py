@@ -49,16 +49,26 @@ class NodeStore:
 
     def extend(self, X) -> None:
         """Bulk append of rows (RRdT* ``extend_tree``, rrdtPlanner.py:878-887)."""
-        if _is_torch_tensor(X) and not X.is_cuda and not X.is_pinned():
-            X = X.detach().numpy()                        # pageable host tensor: the host path below
+        if _is_torch_tensor(X) and not X.is_cuda:
+            import torch
+
+            zero_copy = X.is_pinned() and X.dtype == torch.float64 and X.is_contiguous() and \
+                (X.dim() == 2 and X.shape[1] == self.dim or X.dim() == 1 and X.numel() == self.dim)
+            if not zero_copy:
+                # pageable, or a pinned tensor that would need a dtype / layout conversion (which
+                # yields a pageable temporary): the staged host path below
+                X = X.detach().to(torch.float64).contiguous().numpy()
         if _is_torch_tensor(X):
             # CUDA tensor, or PINNED host tensor: pinned memory is mapped into the device's address
             # space (UVA), so the append kernel reads it over PCIe itself -- the host-to-device
             # transfer and the AoS -> SoA conversion are one asynchronous, graph-capturable launch
             # (the caller must keep the tensor unchanged until the stream has passed the launch)
             self.ctx.use_torch_stream()
-            X = as_device_f64(X, self.dim)
+            X = as_device_f64(X, self.dim, device=self.ctx.device, allow_pinned=True)
             check(_lib.load().sbp_nodes_append(self._h, ptr(X), X.shape[0], 1), "sbp_nodes_append")
+            # the launch is asynchronous: keep the source alive (a pinned block handed back to
+            # torch's allocator could be recycled under the kernel) until the next append
+            self._keepalive = X
         else:
             X = as_host_f64(X, self.dim)
             n0 = len(self)
@@ -134,7 +144,7 @@ class NodeStore:
             import torch
 
             self.ctx.use_torch_stream()
-            X = as_device_f64(X, self.dim)
+            X = as_device_f64(X, self.dim, device=self.ctx.device)
             m = X.shape[0]
             idx = torch.empty((m, k), dtype=torch.int64, device=X.device)
             dist = torch.empty((m, k), dtype=torch.float64, device=X.device) if return_dist else None
@@ -162,7 +172,7 @@ class NodeStore:
             import torch
 
             self.ctx.use_torch_stream()
-            X = as_device_f64(X, self.dim)
+            X = as_device_f64(X, self.dim, device=self.ctx.device)
             m = X.shape[0]
             row_ptr = torch.empty(m + 1, dtype=torch.int64, device=X.device)
             needed = torch.zeros(1, dtype=torch.int64, device=X.device)
@@ -263,7 +273,7 @@ class NodeStore:
         P = torch.empty((m * k_out, self.dim), dtype=torch.float64, device=dev)
         Q = torch.empty((m * k_out, self.dim), dtype=torch.float64, device=dev)
         valid = torch.empty(m * k_out, dtype=torch.uint8, device=dev)
-        X = as_device_f64(queries, self.dim) if queries is not None else None
+        X = as_device_f64(queries, self.dim, device=self.ctx.device) if queries is not None else None
         check(_lib.load().sbp_nodes_knn_edges(self._h, ptr(nbr_in), m, k_in, int(first_row), ptr(X),
                                               ptr(nbr), ptr(P), ptr(Q), ptr(valid)),
               "sbp_nodes_knn_edges")

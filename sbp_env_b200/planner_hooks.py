@@ -228,10 +228,14 @@ def accelerate_prm(planner, store=None, chunk_rows: int = 4096):
         n = len(planner.nodes)
         radius = planner.gamma * np.power(np.log(n + 1) / (n + 1), 1 / d)       # :87-89
         poses = np.ascontiguousarray(planner.poses[:n], dtype=np.float64)
-        if len(store) != n:                          # (re)fill: PRM only appends between builds
-            if len(store) > n:
-                store.truncate(0)
-            store.extend(poses[len(store):])
+        have = len(store)
+        # the mirror is reused only when it is a bit-identical prefix of the planner's array
+        # (PRM appends between builds; anything else -- a rewritten array -- is mirrored afresh)
+        if have > n or (have and not np.array_equal(store.poses, poses[:have])):
+            store.truncate(0)
+            have = 0
+        if have < n:
+            store.extend(poses[have:])
         nodes, dist, graph = planner.nodes, args.engine.dist, planner.graph
         for first in range(0, n, chunk_rows):
             rows = poses[first:first + chunk_rows]

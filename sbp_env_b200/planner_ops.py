@@ -66,6 +66,11 @@ def rewire(cc, tree, costs, parents, new_idx, radius, dist=euclidean_dist, poses
         c = np.array([dist(newpos, p) for p in _rows(tree, poses, idx)], dtype=np.float64)
     else:
         idx, vis, c = candidates
+        # Stats parity: the reference's loop evaluates cc.visible(n.pos, new.pos) for every node
+        # that passed `n != newnode.parent and dist <= radius` (rrtPlanner.py:256-260); the reused
+        # candidate set already holds those answers, so only the counter moves
+        cc.stats.visible_cnt += sum(1 for j, n in enumerate(idx)
+                                    if int(n) != new_idx and int(n) != parents[new_idx] and c[j] <= radius)
     out = []
     for j, n in enumerate(idx):
         n = int(n)

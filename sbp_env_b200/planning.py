@@ -33,7 +33,7 @@ def near(tree, X, r, metric="full", closed=False):
 
 
 def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, queries=None,
-                    mark=None, packed_out=None):
+                    mark=None, packed_out=None, part=None, want_rows: bool = True):
     """Candidate roadmap edges of every stored node to its k nearest other nodes and
     their visibility, entirely on the device.
 
@@ -52,6 +52,10 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
         decided: a CUDA int32 tensor [m][k], or ``(address, True)`` for the NVSwitch multicast
         address of a symmetric buffer (``distributed.PeerAdjacencyGather.target``).  2-D image
         checker only.
+    :param part: ``(i, parts)``: connect only run i of the ``parts`` contiguous runs of the
+        CELL-SORTED row order (spatially compact shards, one per rank; outputs are [n][k] in node
+        order with only that run's rows written).  2-D image checker only.
+    :param want_rows: ``False`` skips the ``nbr`` / ``vis`` outputs (only ``packed_out`` is written).
     :param mark: optional callable ``mark(name)`` invoked between the phases
         ("knn", "edges", "visible") on the launching stream (bench.py records CUDA
         events there).
@@ -62,6 +66,17 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
     # the 2-D image checker resolves the kNN rows inside its visibility kernel (one launch)
     fused = (hasattr(cc, "knn_edges_visible") and hasattr(tree, "_h") and tree.dim == 2
              and not cc._mocked("visible"))
+    # all stored rows (or a cell-sorted part of them) with the 2-D checker: the whole step is one
+    # library call -- kNN on the cell grid, then the row-ordered visibility kernel
+    if fused and queries is None and rows is None and not return_dist and 1 <= k <= 31 \
+            and hasattr(cc, "prm_connect") and len(tree) > 0:
+        out = cc.prm_connect(tree, k, part=part or (0, 1), packed_out=packed_out, want_rows=want_rows)
+        if mark:
+            for name in ("knn", "edges", "visible"):
+                mark(name)
+        return out
+    if part is not None and tuple(part) != (0, 1):
+        raise ValueError("part= needs the 2-D image checker on a device node store (all rows)")
     if queries is not None:
         X = queries
         count = X.shape[0]
@@ -217,7 +232,7 @@ class PRMConnectGraph(CapturedStep):
     """
 
     def __init__(self, cc, tree, k: int, rows=None, queries=None, warmup: int = 2, packed_out=None,
-                 after=None):
+                 after=None, part=None, want_rows: bool = True):
         """``after``: optional callable run (and captured) right after the connection step, on
         the same stream -- e.g. the barrier of ``PeerAdjacencyGather.complete``."""
         if "visible" in getattr(cc, "__dict__", {}):
@@ -228,17 +243,18 @@ class PRMConnectGraph(CapturedStep):
 
         def fn():
             before[0] = int(cc.stats.visible_cnt)
-            out = prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries, packed_out=packed_out)
+            out = prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries, packed_out=packed_out,
+                                  part=part, want_rows=want_rows)
             if after is not None:
                 after()
             return out
 
         super().__init__(fn, device=tree.ctx.device, warmup=warmup)
         self._edges = int(cc.stats.visible_cnt) - before[0]     # edges checked by one step
-        self.nbr, self.vis = self.out
+        self.nbr, self.vis = self.out if self.out is not None else (None, None)
 
     def _recaptured(self):
-        self.nbr, self.vis = self.out
+        self.nbr, self.vis = self.out if self.out is not None else (None, None)
 
     def replay(self):
         if len(self.tree) != self._n:

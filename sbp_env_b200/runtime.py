@@ -160,10 +160,17 @@ def as_host_f64(a, cols: int) -> np.ndarray:
     return a
 
 
-def as_device_f64(t, cols: int):
-    """Contiguous float64 CUDA tensor [n][cols] (no host round trip)."""
+def as_device_f64(t, cols: int, device: int = None, allow_pinned: bool = False):
+    """Contiguous float64 CUDA tensor [n][cols] (no host round trip).  A host tensor is refused
+    (its address means nothing to a kernel) unless ``allow_pinned`` and it is pinned, float64 and
+    contiguous already -- any conversion would produce a pageable temporary."""
     import torch
 
+    if not t.is_cuda:
+        if not (allow_pinned and t.is_pinned() and t.dtype == torch.float64 and t.is_contiguous()):
+            raise ValueError("expected a CUDA tensor (host data goes through the numpy entry points)")
+    elif device is not None and t.device.index != int(device):
+        raise ValueError(f"tensor lives on cuda:{t.device.index}, the handle on cuda:{int(device)}")
     if t.dtype != torch.float64:
         t = t.to(torch.float64)
     if t.dim() == 1:

@@ -159,3 +159,80 @@ def test_prm_get_solution_on_device_roadmap(sg):
     assert len(path) == hops[0] + 1
     # a goal no roadmap node is within epsilon of
     assert sg.prm_get_solution(cc, tree, g, start, np.array([-500.0, -500.0]), eps) == (float("inf"), None)
+
+
+@pytest.mark.parametrize("name,n,k", [("maze1", 5000, 6), ("room1", 4000, 8)])
+def test_undirected_roadmap_matches_networkx(sg, name, n, k):
+    """The undirected form -- both directions of every visible candidate, what the reference's
+    symmetric radius rule puts into its DiGraph (prmPlanner.py:91-101) -- against networkx on 512
+    queries: the arc set (no arc twice), reachability, hop counts, component labels; the packed
+    adjacency builds the identical graph."""
+    import torch
+
+    cc, tree, pts, nbr, vis = _build(sg, name, n, k, 11)
+    g = sg.Roadmap.from_knn(nbr, vis, undirected=True)
+    nb, vs = nbr.cpu().numpy(), vis.cpu().numpy()
+    G = nx.DiGraph()
+    G.add_nodes_from(range(n))
+    for v in range(n):
+        for j in range(k):
+            if vs[v, j] and nb[v, j] >= 0:
+                G.add_edge(int(nb[v, j]), v)
+                G.add_edge(v, int(nb[v, j]))
+    want = np.array(sorted(G.edges()), np.int64).reshape(-1, 2)
+    assert g.n_edges == len(want)                                 # mirrored arcs are not stored twice
+    assert np.array_equal(g.edges(), want)
+    gp = sg.Roadmap.from_packed(sg.distributed.pack_adjacency(nbr, vis), undirected=True)
+    assert np.array_equal(gp.edges(), want)
+    gd = sg.Roadmap.from_packed(sg.distributed.pack_adjacency(nbr, vis))
+    assert np.array_equal(gd.edges(), sg.Roadmap.from_knn(nbr, vis).edges())
+    # components: label = smallest node index of the component
+    labels, n_comp = g.components()
+    comps = list(nx.weakly_connected_components(G))
+    assert n_comp == len(comps)
+    want_label = np.empty(n, np.int64)
+    for c in comps:
+        want_label[list(c)] = min(c)
+    assert np.array_equal(labels.cpu().numpy(), want_label)
+    rng = np.random.default_rng(1)
+    S, T = rng.integers(0, n, 512), rng.integers(0, n, 512)
+    S[:4] = T[:4]
+    hops = g.shortest_paths(S, T)
+    hops2, paths = g.shortest_paths(torch.from_numpy(S).cuda(), torch.from_numpy(T).cuda(), max_len=n)
+    assert np.array_equal(hops2.cpu().numpy(), hops)
+    paths = paths.cpu().numpy()
+    reach = 0
+    for q in range(len(S)):
+        s, t = int(S[q]), int(T[q])
+        if nx.has_path(G, s, t):
+            reach += 1
+            assert hops[q] == nx.shortest_path_length(G, s, t), (q, s, t)
+            got = paths[q, : hops[q] + 1]
+            assert got[0] == s and got[-1] == t
+            assert all(G.has_edge(int(a), int(b)) for a, b in zip(got[:-1], got[1:]))
+        else:
+            assert hops[q] == -1 and (paths[q] == -1).all()
+    assert 20 < reach
+    # the weak-component filter on a DIRECTED graph is only a necessary condition: pairs inside one
+    # weak component without a directed path must still come out as -1
+    gdir = sg.Roadmap.from_knn(nbr, vis)
+    Gd = nx.DiGraph()
+    Gd.add_nodes_from(range(n))
+    Gd.add_edges_from(gdir.edges().tolist())
+    hd = gdir.shortest_paths(S, T)
+    for q in range(128):
+        s, t = int(S[q]), int(T[q])
+        assert hd[q] == (nx.shortest_path_length(Gd, s, t) if nx.has_path(Gd, s, t) else -1)
+
+
+def test_undirected_edge_lists(sg):
+    n = 12
+    src = np.array([0, 1, 2, 5, 5], np.int64)
+    dst = np.array([1, 2, 0, 6, 5], np.int64)                      # 5 -> 5: a self loop is not mirrored
+    g = sg.Roadmap(n)
+    g.build_from_edges(src, dst, undirected=True)
+    want = sorted({(a, b) for a, b in zip(src, dst)} | {(b, a) for a, b in zip(src, dst)})
+    assert g.edges().tolist() == [list(e) for e in want]
+    labels, n_comp = g.components()
+    assert labels.cpu().tolist() == [0, 0, 0, 3, 4, 5, 5, 7, 8, 9, 10, 11] and n_comp == 9
+    assert g.shortest_paths(np.array([2, 6, 0, 3]), np.array([1, 5, 5, 3])).tolist() == [1, 1, -1, 0]
