@@ -195,6 +195,15 @@ int32_t sbp_nodes_rows_device(sbp_nodes *nodes, int64_t first, int64_t count, do
  * precision: 64 only (bit-exact); 32 is reserved. */
 int32_t sbp_nodes_knn(sbp_nodes *nodes, const double *X, int64_t m, int32_t k,
                       int32_t precision, int64_t *idx, double *dist);
+/* replaces: RRTPlanner.find_nearest_neighbour_idx (rrtPlanner.py:268-279) EXACTLY,
+ * np.argmin(np.linalg.norm(poses - pos, axis=1)): the first minimum -- and, like np.argmin, the
+ * FIRST node whose distance is NaN as soon as there is one (a NaN query, NaN / inf - inf node
+ * coordinates), where the argsort rule of sbp_nodes_knn would rank NaN distances last.
+ * X: device [m][dim]; idx device [m] (-1 for an empty store); dist device [m] (nullable). */
+int32_t sbp_nodes_nearest(sbp_nodes *nodes, const double *X, int64_t m, int64_t *idx, double *dist);
+int32_t sbp_nodes_nearest_host(sbp_nodes *nodes, const double *X, int64_t m, int64_t *idx,
+                               double *dist);
+
 /* replaces: prmPlanner.nearest_neighbours (prmPlanner.py:28-44; FULL, LT), the
  * radius gates of choose_least_cost_parent / rewire (rrtPlanner.py:177-181,
  * :236-239; XY, LE), birrtPlanner.py:82-85, rrdtPlanner.py:704-713.

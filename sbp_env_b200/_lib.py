@@ -61,6 +61,8 @@ _SIGNATURES = {
     "sbp_nodes_read": [_vp, _i64, _i64, _vp],
     "sbp_nodes_rows_device": [_vp, _i64, _i64, _vp],
     "sbp_nodes_knn": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
+    "sbp_nodes_nearest": [_vp, _vp, _i64, _vp, _vp],
+    "sbp_nodes_nearest_host": [_vp, _vp, _i64, _vp, _vp],
     "sbp_nodes_near": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, _vp],
     "sbp_nodes_knn_host": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "sbp_nodes_near_host": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, C.POINTER(_i64)],

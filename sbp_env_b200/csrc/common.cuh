@@ -179,16 +179,14 @@ struct sbp_map {
     uint32_t *d_rows = nullptr;
     MapView rows{};
     bool rows_smem_resident = false;
-    // Third copy for the PRM connection kernel (prm.cu; built on first use): 32 x 8-pixel sectors
-    // of row words, word = (((y >> 3) * SX + (x >> 5)) << 3) + (y & 7), bit = x & 31 -- cheap
-    // addressing like the row-major copy, 32-byte sector locality in both directions like the
-    // tiled one; `rows8.SX` = sectors per row of sectors.
-    uint32_t *d_rows8 = nullptr;
-    MapView rows8{};
+    // Third, column-major copy for the y-major lines of the PRM connection kernel (prm.cu; built
+    // on first use): word = x * HR + (y >> 5), bit = y & 31; `cols.SX` holds HR.
+    uint32_t *d_cols = nullptr;
+    MapView cols{};
 };
 
 int32_t sbp_map_ensure_rows(sbp_map *map);
-int32_t sbp_map_ensure_rows8(sbp_map *map);
+int32_t sbp_map_ensure_cols(sbp_map *map);
 
 struct sbp_nodes {
     sbp_ctx *ctx = nullptr;

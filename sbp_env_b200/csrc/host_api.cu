@@ -188,6 +188,25 @@ extern "C" int32_t sbp_nodes_knn_host(sbp_nodes *s, const double *X, int64_t m, 
     return st.rc;
 }
 
+extern "C" int32_t sbp_nodes_nearest_host(sbp_nodes *s, const double *X, int64_t m, int64_t *idx,
+                                          double *dist) {
+    SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_nearest_host: NULL argument");
+    SBP_REQUIRE(m >= 0, "sbp_nodes_nearest_host: m < 0");
+    if (m == 0) return SBP_OK;
+    sbp_ctx *ctx = s->ctx;
+    SBP_DEVICE(ctx);
+    Staging st(ctx);
+    double *dX = (double *)st.dev(2, (size_t)m * s->d * 8);
+    int64_t *dI = (int64_t *)st.dev(3, (size_t)m * 8);
+    double *dD = (double *)st.dev(4, (size_t)m * 8);
+    st.h2d(dX, X, (size_t)m * s->d * 8);
+    if (st.rc == SBP_OK) st.rc = sbp_nodes_nearest(s, dX, m, dI, dist ? dD : nullptr);
+    st.d2h(idx, dI, (size_t)m * 8);
+    if (dist) st.d2h(dist, dD, (size_t)m * 8);
+    st.sync();
+    return st.rc;
+}
+
 extern "C" int32_t sbp_nodes_near_host(sbp_nodes *s, const double *X, int64_t m, double r,
                                        int32_t metric, int32_t closed, int64_t *row_ptr,
                                        int64_t *idx, int64_t idx_capacity, int64_t *needed) {

@@ -1553,6 +1553,61 @@ int32_t sbp_knn_rows_part(sbp_nodes *s, const double *X_all, int32_t k, int64_t 
     return knn_dispatch_k<2>(s, X_all, s->n, k, idx, nullptr, grid ? part : nullptr);
 }
 
+// np.argmin semantics for find_nearest_neighbour_idx (rrtPlanner.py:278-279): a NaN distance is
+// returned as soon as it is seen, i.e. the FIRST node whose distance to the query is NaN wins
+// (the argsort rule of sbp_nodes_knn ranks NaN last).  One CTA per query; returns at once when
+// neither the store (maxabs, +inf once a non-finite coordinate was appended) nor the query can
+// produce a NaN distance.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_nearest_first_nan(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                    const double *__restrict__ maxabs, const double *__restrict__ X,
+                    int64_t *__restrict__ idx, double *__restrict__ dist) {
+    const int64_t q = blockIdx.x;
+    double qv[D];
+    bool q_finite = true;
+#pragma unroll
+    for (int j = 0; j < D; ++j) { qv[j] = X[q * D + j]; q_finite &= isfinite(qv[j]); }
+    if (q_finite && isfinite(*maxabs)) return;
+    __shared__ unsigned long long s_first;
+    if (threadIdx.x == 0) s_first = ~0ull;
+    __syncthreads();
+    unsigned long long mine = ~0ull;
+    for (int64_t t = threadIdx.x; t < n && (unsigned long long)t < mine; t += blockDim.x) {
+        double pv[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) pv[j] = soa[(int64_t)j * capacity + t];
+        const double d2 = dist2_full<D>(pv, qv);
+        if (d2 != d2) { mine = (unsigned long long)t; break; }
+    }
+    if (mine != ~0ull) atomicMin(&s_first, mine);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_first != ~0ull) {
+        idx[q] = (int64_t)s_first;
+        if (dist) dist[q] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+}
+
+extern "C" int32_t sbp_nodes_nearest(sbp_nodes *s, const double *X, int64_t m, int64_t *idx, double *dist) {
+    SBP_NVTX("sbp_nodes_nearest");
+    SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_nearest: NULL argument");
+    SBP_REQUIRE(m >= 0, "sbp_nodes_nearest: m < 0");
+    if (m == 0) return SBP_OK;
+    int32_t rc = sbp_nodes_knn(s, X, m, 1, 64, idx, dist);
+    if (rc || s->n == 0) return rc;
+    sbp_ctx *ctx = s->ctx;
+    SBP_DEVICE(ctx);
+    switch (s->d) {
+        case 2: k_nearest_first_nan<2><<<(unsigned)m, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d_maxabs, X, idx, dist); break;
+        case 3: k_nearest_first_nan<3><<<(unsigned)m, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d_maxabs, X, idx, dist); break;
+        case 4: k_nearest_first_nan<4><<<(unsigned)m, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d_maxabs, X, idx, dist); break;
+        default: k_nearest_first_nan<6><<<(unsigned)m, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, s->n, s->d_maxabs, X, idx, dist); break;
+    }
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
 __global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {

@@ -273,7 +273,7 @@ extern "C" int32_t sbp_map_destroy(sbp_map *map) {
     cudaStreamSynchronize(map->ctx->stream);
     if (map->d_words) cudaFree(map->d_words);
     if (map->d_rows) cudaFree(map->d_rows);
-    if (map->d_rows8) cudaFree(map->d_rows8);
+    // (d_cols is a view into the d_rows allocation)
     delete map;
     return SBP_OK;
 }

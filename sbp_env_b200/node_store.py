@@ -129,9 +129,30 @@ class NodeStore:
 
     # ---- queries -------------------------------------------------------------------
     def nearest(self, x) -> int:
-        """``np.argmin(np.linalg.norm(poses - pos, axis=1))`` (rrtPlanner.py:278-279)."""
-        idx, _ = self.knn(np.asarray(x, dtype=np.float64).reshape(1, self.dim), 1)
-        return int(idx[0, 0])
+        """``np.argmin(np.linalg.norm(poses - pos, axis=1))`` (rrtPlanner.py:278-279): the first
+        minimum, or -- like np.argmin -- the first node at a NaN distance when there is one."""
+        return int(self.nearest_batch(np.asarray(x, dtype=np.float64).reshape(1, self.dim))[0][0])
+
+    def nearest_batch(self, X, return_dist: bool = True):
+        """:meth:`nearest` for every row of X: ``(idx int64 [m], dist fp64 [m])``; numpy in ->
+        numpy out, CUDA tensor in -> CUDA tensors out."""
+        if _is_torch_tensor(X):
+            import torch
+
+            self.ctx.use_torch_stream()
+            X = as_device_f64(X, self.dim, device=self.ctx.device)
+            m = X.shape[0]
+            idx = torch.empty(m, dtype=torch.int64, device=X.device)
+            dist = torch.empty(m, dtype=torch.float64, device=X.device) if return_dist else None
+            check(_lib.load().sbp_nodes_nearest(self._h, ptr(X), m, ptr(idx), ptr(dist)), "sbp_nodes_nearest")
+            return idx, dist
+        X = as_host_f64(X, self.dim)
+        m = len(X)
+        idx = np.empty(m, np.int64)
+        dist = np.empty(m, np.float64) if return_dist else None
+        check(_lib.load().sbp_nodes_nearest_host(self._h, ptr(X), m, ptr(idx), ptr(dist)),
+              "sbp_nodes_nearest_host")
+        return idx, dist
 
     def knn(self, X, k: int, return_dist: bool = True):
         """k nearest nodes of every row of X, ordered by (distance, index).

@@ -66,15 +66,23 @@ def rewire(cc, tree, costs, parents, new_idx, radius, dist=euclidean_dist, poses
         c = np.array([dist(newpos, p) for p in _rows(tree, poses, idx)], dtype=np.float64)
     else:
         idx, vis, c = candidates
+    # The reference compares Node objects, and Node.__eq__ / __hash__ go by POSITION
+    # (utils/common.py:187-192): `x not in already_rewired` (= {newnode}) skips every node at the
+    # new node's position, `n != newnode.parent` every node at the parent's position (goal-biased
+    # sampling does produce such duplicates).
+    P = _rows(tree, poses, idx) if len(idx) else np.empty((0, len(newpos)))
+    ppos = _rows(tree, poses, [parents[new_idx]])[0] if parents[new_idx] is not None and parents[new_idx] >= 0 else None
+    skip = [int(n) == new_idx or bool(np.all(P[j] == newpos)) or
+            (ppos is not None and bool(np.all(P[j] == ppos))) for j, n in enumerate(idx)]
+    if candidates is not None and not arm:
         # Stats parity: the reference's loop evaluates cc.visible(n.pos, new.pos) for every node
         # that passed `n != newnode.parent and dist <= radius` (rrtPlanner.py:256-260); the reused
         # candidate set already holds those answers, so only the counter moves
-        cc.stats.visible_cnt += sum(1 for j, n in enumerate(idx)
-                                    if int(n) != new_idx and int(n) != parents[new_idx] and c[j] <= radius)
+        cc.stats.visible_cnt += sum(1 for j in range(len(idx)) if not skip[j] and c[j] <= radius)
     out = []
     for j, n in enumerate(idx):
         n = int(n)
-        if n == new_idx or n == parents[new_idx]:
+        if skip[j]:
             continue
         if c[j] <= radius and vis[j] and costs[new_idx] + c[j] < costs[n]:
             parents[n] = new_idx

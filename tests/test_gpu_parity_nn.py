@@ -729,3 +729,53 @@ def test_million_node_knn_properties(sg):
     rows = torch.randperm(m, generator=g, device="cuda")[:200].cpu().numpy()
     oi, od = orc.knn(P.cpu().numpy(), X.cpu().numpy()[rows], k)
     assert np.array_equal(idx.cpu().numpy()[rows], oi) and np.array_equal(dist.cpu().numpy()[rows], od)
+
+
+def test_nearest_is_np_argmin_also_on_nan(sg):
+    """find_nearest_neighbour_idx (rrtPlanner.py:278-279) is np.argmin: the FIRST node at a NaN
+    distance wins as soon as there is one -- NaN / inf - inf node coordinates, NaN or inf queries --
+    where kNN (stable argsort) ranks NaN last.  Against the oracle's orc_nearest and numpy."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    for d in (2, 4):
+        n = 5000
+        P = rng.random((n, d)) * 300
+        X = rng.random((40, d)) * 300
+        tree = sg.NodeStore(d)
+        tree.extend(P)
+        # finite store, finite queries: plain first minimum
+        gi, gd = tree.nearest_batch(X)
+        oi, od = orc.nearest(P, X)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        # NaN / inf queries against a finite store
+        Xb = X.copy()
+        Xb[0, 0] = np.nan
+        Xb[1, d - 1] = np.inf
+        Xb[2] = -np.inf
+        gi, gd = tree.nearest_batch(Xb)
+        oi, od = orc.nearest(P, Xb)
+        want = np.array([int(np.argmin(np.linalg.norm(P - x, axis=1))) for x in Xb])
+        assert np.array_equal(oi, want)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od, equal_nan=True)
+        assert tree.nearest(Xb[0]) == 0                      # every distance is NaN: index 0
+        # non-finite node coordinates: the first NaN-distance node, not the true minimum
+        P2 = P.copy()
+        P2[1234, 0] = np.nan
+        P2[77, 1] = np.inf                                   # inf - inf = NaN only for the inf query
+        P2[4000] = np.nan
+        t2 = sg.NodeStore(d)
+        t2.extend(P2)
+        gi, gd = t2.nearest_batch(Xb)
+        oi, od = orc.nearest(P2, Xb)
+        with np.errstate(invalid="ignore"):
+            want = np.array([int(np.argmin(np.linalg.norm(P2 - x, axis=1))) for x in Xb])
+        assert np.array_equal(oi, want)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od, equal_nan=True)
+        assert (gi[3:] == 1234).all() and gi[1] == 77
+        # device tensors in, device tensors out
+        di, dd = t2.nearest_batch(torch.from_numpy(Xb).cuda())
+        assert np.array_equal(di.cpu().numpy(), oi)
+        # kNN keeps the argsort rule (NaN last)
+        ki, _ = t2.knn(X[:5], 1)
+        assert (ki[:, 0] != 1234).all()

@@ -75,7 +75,7 @@ def test_rrt_star_trajectory_replay(sg, tag):
     assert parents == g[f"{tag}_parent"].tolist()
     assert costs == g[f"{tag}_cost"].tolist()
     assert c_max == float(g[f"{tag}_c_max"])
-    # Stats: the reference's visible() count of the run minus the two Env start / goal checks
+    # Stats: the reference's visible() count of the whole run (rrtPlanner.py:82, :96, :179, :260)
     assert cc.stats.visible_cnt - v0 == int(g[f"{tag}_counters"][0])
 
 
