@@ -762,7 +762,7 @@ def test_nearest_is_np_argmin_also_on_nan(sg):
         # non-finite node coordinates: the first NaN-distance node, not the true minimum
         P2 = P.copy()
         P2[1234, 0] = np.nan
-        P2[77, 1] = np.inf                                   # inf - inf = NaN only for the inf query
+        P2[77, d - 1] = np.inf                               # inf - inf = NaN only for the inf query (Xb[1])
         P2[4000] = np.nan
         t2 = sg.NodeStore(d)
         t2.extend(P2)
