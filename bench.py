@@ -160,7 +160,7 @@ def run_ours(args):
     nodes_d = torch.from_numpy(nodes_h).to(dev)
     tree = sg.NodeStore(2, capacity=n, device=local)
     tree.extend(nodes_d)
-    _, count = sg.distributed.shard_range(n, rank, world)     # rows of this rank (a run of the cell-sorted order)
+    first, count = sg.distributed.shard_range(n, rank, world)  # rows of this rank: a run of the cell-sorted order
     edges_total = n * k
     SENTINEL = -(1 << 31)
 
@@ -181,8 +181,13 @@ def run_ours(args):
                     "multicast mapping as edges are decided; symmetric-memory barrier")
     elif world > 1 and peer is not None:
         exchange = "NCCL all-reduce(MAX) of the packed rows (no multicast mapping on this fabric)"
+    # The adjacency is kept in CELL-SORTED row order: row p belongs to node order[p] (the permutation
+    # of the kNN's counting sort, a function of the poses only: identical on every rank), so that a
+    # rank's rows are ONE contiguous block which the walk kernel stores with coalesced lines --
+    # through the multicast mapping at N > 1, into pinned host memory in the e2e step.
     packed_local = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
-    packed_full = {}                                  # filled by every step: int32 [n][k]
+    order = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    packed_full = {}                                  # filled by every step: int32 [n][k], cell-sorted rows
     peer_step = [0]
     part = (rank, world)
 
@@ -195,10 +200,12 @@ def run_ours(args):
         if fused:
             h = peer_step[0] & 1
             peer_step[0] += 1
-            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=peer.target(h), want_rows=False)
+            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=peer.target(h), want_rows=False,
+                               order_out=order)
             packed_full["p"] = peer.complete(h)
         else:
-            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=packed_local, want_rows=False)
+            sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=packed_local, want_rows=False,
+                               order_out=order)
             packed_full["p"] = packed_local if world == 1 else nccl_merge()
         if mark:
             mark("exchange")
@@ -209,7 +216,7 @@ def run_ours(args):
     if fused:
         try:
             gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False,
-                                         after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
+                                         order_out=order, after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
             barrier_in_graph = True
         except Exception as e:      # noqa: BLE001
             print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
@@ -217,12 +224,12 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         barrier_in_graph = bool(ok.item())
         if not barrier_in_graph:
-            gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False)
-                      for h in (0, 1)]
+            gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False,
+                                         order_out=order) for h in (0, 1)]
         exchange += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
         dist.barrier()
     else:
-        gstep = sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=packed_local, want_rows=False)
+        gstep = sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=packed_local, want_rows=False, order_out=order)
 
     def step():
         if fused:
@@ -326,34 +333,46 @@ def run_ours(args):
     full = packed_full["p"]
     assert tuple(full.shape) == (n, k)
     assert torch.equal(replayed, full), "graph replay differs from the eager step"
-    # this rank's own rows, computed into a private sentinel buffer
+    # this rank's own rows, computed into a private sentinel buffer: exactly its block of positions
     own = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
-    sg.prm_connect_knn(cc, tree, k, part=part, packed_out=own, want_rows=False)
+    order2 = torch.empty_like(order)
+    sg.prm_connect_knn(cc, tree, k, part=part, packed_out=own, want_rows=False, order_out=order2)
+    assert torch.equal(order2, order) and torch.equal(torch.sort(order.long()).values, torch.arange(n, device=dev))
     mine_rows = own[:, 0] != SENTINEL
-    assert int(mine_rows.sum().item()) == count, "this rank did not write exactly its share of the rows"
+    assert int(mine_rows.sum().item()) == count and bool(mine_rows[first:first + count].all()), \
+        "this rank did not write exactly its block of the rows"
     assert torch.equal(own[mine_rows], full[mine_rows]), "assembled adjacency differs from the local rows"
     adjacency_check = "single rank"
     if world > 1:
-        # the WHOLE assembled adjacency against an NCCL merge of the ranks' rows, on every rank
+        # the WHOLE assembled adjacency against an NCCL merge of the ranks' rows, on every rank; the
+        # permutation must be the same on every rank
         want = own.clone()
         dist.all_reduce(want, op=dist.ReduceOp.MAX)
         owners = mine_rows.to(torch.int32)
         dist.all_reduce(owners)
-        same = torch.tensor([1 if (torch.equal(want, full) and bool((owners == 1).all().item())) else 0], device=dev)
+        omax, omin = order.clone(), order.clone()
+        dist.all_reduce(omax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(omin, op=dist.ReduceOp.MIN)
+        same = torch.tensor([1 if (torch.equal(want, full) and bool((owners == 1).all().item())
+                                   and torch.equal(omax, omin)) else 0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         assert bool(same.item()), "adjacency assembled through peer memory differs from the NCCL merge"
-        adjacency_check = f"every row written by exactly one rank; equal to the NCCL merge of the {world} ranks' rows on every rank"
-    # the new one-call path against the generic path (kNN call + general visibility kernel) on a
+        adjacency_check = (f"every row written by exactly one rank; equal to the NCCL merge of the {world} ranks' "
+                           "rows on every rank; same row permutation on every rank")
+    # node-order view of the adjacency for the checks below
+    full_node = torch.empty_like(full)
+    full_node[order.long()] = full
+    # the one-call path against the generic path (kNN call + general visibility kernel) on a
     # slice of the rows, bit for bit
     sl = (rank * 20_000 % max(1, n - 20_000), min(20_000, n))
     nbr_g, vis_g = sg.prm_connect_knn(cc, tree, k, rows=sl)
-    gn, gv = sg.distributed.unpack_adjacency(full[sl[0]:sl[0] + sl[1]])
+    gn, gv = sg.distributed.unpack_adjacency(full_node[sl[0]:sl[0] + sl[1]])
     assert torch.equal(gn, nbr_g) and torch.equal(gv, vis_g), "one-call connection differs from the generic path"
     n_vis = int((full & 1).sum().item())
     # size-independent properties at full size (this rank checks every world-th row): the 2-D
     # checker is direction symmetric, and a visible edge has feasible endpoints
     sel = torch.arange(rank, n, world, device=dev)
-    nbr_s, vis_s = sg.distributed.unpack_adjacency(full[sel])
+    nbr_s, vis_s = sg.distributed.unpack_adjacency(full_node[sel])
     P = nodes_d[nbr_s.reshape(-1).clamp(min=0)].contiguous()
     Q = nodes_d[sel.repeat_interleave(k)].contiguous()
     v_rev = cc.visible_batch(Q, P).reshape(-1, k) & (nbr_s >= 0)
@@ -361,7 +380,7 @@ def run_ours(args):
     assert bool((~vis_s.reshape(-1) | (cc.feasible_batch(P) & cc.feasible_batch(Q))).all().item())
     px_full = float((torch.maximum((P[:, 0].trunc() - Q[:, 0].trunc()).abs(),
                                    (P[:, 1].trunc() - Q[:, 1].trunc()).abs()) + 1).sum().item())
-    del P, Q, v_rev, nbr_s, vis_s, own
+    del P, Q, v_rev, nbr_s, vis_s, own, full_node
     px_t = torch.tensor([px_full], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(px_t)
@@ -382,7 +401,7 @@ def run_ours(args):
                 e.record()
                 q_ev[name] = e
         mk("start")
-        road.build_from_packed(packed_full["p"], undirected=True)
+        road.build_from_packed(packed_full["p"], undirected=True, row_ids=order)
         mk("csr")
         ends = sg.connect_to_roadmap(cc, tree, SG_mine, K_CONNECT)
         mk("connect")
@@ -422,26 +441,30 @@ def run_ours(args):
 
     # ---- end to end through the public API with host buffers -------------------------------
     pinned = torch.from_numpy(nodes_h).pin_memory()
-    code_h = torch.full((n, k), SENTINEL, dtype=torch.int32).pin_memory()   # [n][k]; this rank fills its rows
+    code_h = torch.full((n, k), SENTINEL, dtype=torch.int32).pin_memory()   # [n][k] cell-sorted rows; this rank fills its block
+    order_h = torch.full((n,), -1, dtype=torch.int32).pin_memory()
+    order_e = torch.empty_like(order)
     code_dev = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
     x_dev = torch.empty((n, 2), dtype=torch.float64, device=dev)
     tree2 = sg.NodeStore(2, capacity=n, device=local)
-    e2e_copy = os.environ.get("BENCH_E2E_COPY", "0") == "1"
+    # H2D: the node-store append kernel reads the pinned host rows itself (coalesced zero-copy reads;
+    # BENCH_E2E_H2D_COPY=1: explicit copy first).  D2H: the walk kernel stores this rank's block of the
+    # packed adjacency -- contiguous, whole 128-byte lines -- straight into the pinned host buffer as
+    # the edges are decided (BENCH_E2E_D2H_COPY=1: device buffer + copy); the row permutation follows
+    # with one 4 MB copy.
+    h2d_copy = os.environ.get("BENCH_E2E_H2D_COPY", "0") == "1"
+    d2h_copy = os.environ.get("BENCH_E2E_D2H_COPY", "0") == "1"
 
     def e2e_body():
-        # H2D of the step's samples: the node-store append kernel reads the pinned host rows itself
-        # (zero-copy: transfer and AoS -> SoA conversion in one launch; BENCH_E2E_COPY=1: explicit copy
-        # first).  D2H of this rank's adjacency block: the visibility kernel stores the packed codes
-        # straight into the pinned host buffer (mapped into the device's address space) as the edges
-        # are decided; BENCH_E2E_COPY=1: device buffer + copy.
-        if e2e_copy:
+        if h2d_copy:
             x_dev.copy_(pinned, non_blocking=True)
         tree2.truncate(0)
-        tree2.extend(x_dev if e2e_copy else pinned)
-        sg.prm_connect_knn(cc, tree2, k, part=part, want_rows=False,
-                           packed_out=code_dev if e2e_copy else (code_h.data_ptr(), False))
-        if e2e_copy:
-            code_h.copy_(code_dev, non_blocking=True)
+        tree2.extend(x_dev if h2d_copy else pinned)
+        sg.prm_connect_knn(cc, tree2, k, part=part, want_rows=False, order_out=order_e,
+                           packed_out=code_dev if d2h_copy else (code_h.data_ptr(), False))
+        if d2h_copy:
+            code_h[first:first + count].copy_(code_dev[first:first + count], non_blocking=True)
+        order_h.copy_(order_e, non_blocking=True)
 
     e2e_graph = sg.CapturedStep(e2e_body, device=local)
     for _ in range(max(3, args.warmup)):
@@ -450,8 +473,9 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     e2e_ms = timed_loop(e2e_graph.replay, args.steps)
-    mine_h = mine_rows.cpu()
-    assert torch.equal(code_h[mine_h], full[mine_rows].cpu()) and bool((code_h[~mine_h] == SENTINEL).all()), \
+    assert torch.equal(order_h, order.cpu()), "e2e row permutation differs from the device-resident run"
+    assert torch.equal(code_h[first:first + count], full[first:first + count].cpu()) and \
+        bool((code_h[:first] == SENTINEL).all()) and bool((code_h[first + count:] == SENTINEL).all()), \
         "e2e result differs from the device-resident run"
 
     if rank != 0:
@@ -531,11 +555,12 @@ def run_ours(args):
         "e2e": {"value": edges_total * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
-                "d2h_bytes_per_step": int(count * k * 4),
-                "result": "packed adjacency int32 [rows of this rank][k] = (neighbour + 1) * 2 + visible",
-                "d2h": "copy from a device buffer" if e2e_copy else
-                       "stored by the visibility kernel straight into the pinned host buffer (zero-copy)",
-                "h2d": "copy into a device buffer" if e2e_copy else
+                "d2h_bytes_per_step": int(count * k * 4 + n * 4),
+                "result": "packed adjacency int32 [rows of this rank, cell-sorted][k] = (neighbour + 1) * 2 + visible, "
+                          "and the row permutation int32 [n]",
+                "d2h": "copy from a device buffer" if d2h_copy else
+                       "stored by the walk kernel straight into the pinned host buffer (coalesced zero-copy) + one copy of the permutation",
+                "h2d": "copy into a device buffer" if h2d_copy else
                        "read from the pinned host buffer by the node-store append kernel (zero-copy)"},
         "gpu_launches": int(launches_per_step * args.steps),
         "gpu_launches_per_step": int(launches_per_step),

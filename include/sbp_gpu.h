@@ -192,7 +192,10 @@ int32_t sbp_nodes_rows_device(sbp_nodes *nodes, int64_t first, int64_t count, do
  * either way -- DESIGN.md 3a.)
  * X: device [m][dim].  idx: device [m][k] int64, dist: device [m][k] fp64
  * (nullable); rows are padded with -1 / +inf when size < k.  1 <= k <= 32.
- * precision: 64 only (bit-exact); 32 is reserved. */
+ * precision: 64 = fp64 distances, bit-exact.  32 = `dist` is a FLOAT buffer [m][k] (cast the
+ * pointer): the same rows -- the selection stays the exact fp64 one, so the index sets are
+ * bit-exact also at ties -- with the distances rounded to fp32, |d32 - d64| <= 2^-24 d64
+ * (BASELINE.json north_star: "within 1e-6 relative in fp32"); half the output bytes. */
 int32_t sbp_nodes_knn(sbp_nodes *nodes, const double *X, int64_t m, int32_t k,
                       int32_t precision, int64_t *idx, double *dist);
 /* replaces: RRTPlanner.find_nearest_neighbour_idx (rrtPlanner.py:268-279) EXACTLY,
@@ -280,6 +283,15 @@ int32_t sbp_knn_edges_visible2d(sbp_map *map, sbp_nodes *nodes, const int64_t *n
 int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
                           int64_t *nbr_out, uint8_t *vis, int32_t *packed, int32_t packed_multicast,
                           int32_t *flags);
+/* The same with the rows of every output in CELL-SORTED order: row p of nbr_out / vis / packed belongs
+ * to node order_out[p] (device int32 [n], written by the call: the permutation of the kNN's counting
+ * sort, ascending node index inside a cell -- a function of the poses only, so every rank computes
+ * the same one).  The rows of part i are then ONE contiguous block [p0, p0 + count) x k that the
+ * kernel stores with coalesced 128-byte lines: the form to use when `packed` is pinned host memory
+ * or the NVSwitch multicast mapping.  sbp_graph_build_packed_rows consumes it. */
+int32_t sbp_prm_connect2d_sorted(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
+                                 int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                                 int32_t packed_multicast, int32_t *order_out, int32_t *flags);
 
 /* Fused radius query + edge visibility in ONE launch, for the sequential planners.
  * replaces: the O(N) Python loops of choose_least_cost_parent (rrtPlanner.py:173-196:
@@ -329,6 +341,10 @@ int32_t sbp_graph_build_knn(sbp_graph *g, const int64_t *nbr, const uint8_t *vis
  * on every rank. */
 int32_t sbp_graph_build_packed(sbp_graph *g, const int32_t *packed, int64_t m, int32_t k,
                                int64_t first_row, int32_t undirected);
+/* The same for rows in an explicit order: row r of packed [m][k] belongs to node row_ids[r] (device
+ * int32 [m], distinct) -- the cell-sorted rows and order_out of sbp_prm_connect2d_sorted. */
+int32_t sbp_graph_build_packed_rows(sbp_graph *g, const int32_t *packed, const int32_t *row_ids,
+                                    int64_t m, int32_t k, int32_t undirected);
 /* (Re)build from explicit arc lists src[e] -> dst[e] (device), `keep` an optional mask;
  * undirected != 0 adds dst[e] -> src[e] too (duplicates in the list are kept). */
 int32_t sbp_graph_build_edges(sbp_graph *g, const int64_t *src, const int64_t *dst,

@@ -70,6 +70,7 @@ _SIGNATURES = {
     "sbp_nodes_knn_edges": [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp],
     "sbp_knn_edges_visible2d": [_vp, _vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _i32, _vp, _vp],
     "sbp_prm_connect2d": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp],
+    "sbp_prm_connect2d_sorted": [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp],
     "sbp_nodes_near_visible": [_vp, _vp, _i32, _dbl, _dbl, _vp, _i64, _dbl, _i32, _i32, _i32, _vp, _vp,
                                _i32, _vp, _vp],
     "sbp_nodes_near_visible_host": [_vp, _vp, _i32, _dbl, _dbl, _vp, _dbl, _i32, _i32, _i32, _vp, _vp,
@@ -78,6 +79,7 @@ _SIGNATURES = {
     "sbp_graph_destroy": [_vp],
     "sbp_graph_build_knn": [_vp, _vp, _vp, _i64, _i32, _i64, _i32],
     "sbp_graph_build_packed": [_vp, _vp, _i64, _i32, _i64, _i32],
+    "sbp_graph_build_packed_rows": [_vp, _vp, _vp, _i64, _i32, _i32],
     "sbp_graph_build_edges": [_vp, _vp, _vp, _vp, _i64, _i32],
     "sbp_graph_components": [_vp, _vp, C.POINTER(_i64)],
     "sbp_graph_info": [_vp, C.POINTER(_i64), C.POINTER(_i64)],

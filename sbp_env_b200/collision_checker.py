@@ -336,7 +336,7 @@ class ImgCollisionChecker(_GridChecker):
         self._last_flags = flags
         return nbr, vis.view(torch.bool)
 
-    def prm_connect(self, tree, k: int, part=(0, 1), packed_out=None, want_rows: bool = True):
+    def prm_connect(self, tree, k: int, part=(0, 1), packed_out=None, want_rows: bool = True, order_out=None):
         """The whole roadmap connection step for the rows of ``tree`` in ONE library call
         (``sbp_prm_connect2d``; prmPlanner.py:91-101 with the k nearest neighbours as candidates):
         exact kNN of every stored node among all nodes, own entry dropped, and
@@ -347,6 +347,10 @@ class ImgCollisionChecker(_GridChecker):
         of rank i; the other rows of the outputs are left untouched).  ``packed_out``: int32 CUDA
         tensor [n][k], or ``(address, multicast)`` -- pinned host memory, or the NVSwitch
         multicast address of a symmetric buffer (``distributed.PeerAdjacencyBuffer.target``).
+        ``order_out``: int32 CUDA tensor [n]; when given the rows of every output are in
+        CELL-SORTED order -- row p belongs to node ``order_out[p]`` (written by the call) -- and the
+        rows of a part are one contiguous, coalesced block (``sbp_prm_connect2d_sorted``): the form
+        for pinned host memory and the multicast mapping.
         Returns ``(nbr int64 [n][k], vis bool [n][k])`` CUDA tensors, or ``None`` with
         ``want_rows=False`` (only the packed adjacency is written)."""
         import torch
@@ -372,8 +376,16 @@ class ImgCollisionChecker(_GridChecker):
         i, parts = int(part[0]), int(part[1])
         base, rem = divmod(n, parts)
         self.stats.visible_cnt += (base + (1 if i < rem else 0)) * k
-        check(_lib.load().sbp_prm_connect2d(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),
-                                            p_ptr, p_mc, ptr(flags)), "sbp_prm_connect2d")
+        if order_out is not None:
+            if order_out.dtype != torch.int32 or order_out.numel() != n or not order_out.is_contiguous() \
+                    or order_out.device != dev:
+                raise ValueError("order_out must be a contiguous CUDA int32 tensor [n]")
+            check(_lib.load().sbp_prm_connect2d_sorted(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),
+                                                       p_ptr, p_mc, ptr(order_out), ptr(flags)),
+                  "sbp_prm_connect2d_sorted")
+        else:
+            check(_lib.load().sbp_prm_connect2d(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),
+                                                p_ptr, p_mc, ptr(flags)), "sbp_prm_connect2d")
         self._last_flags = flags
         return (nbr, vis.view(torch.bool)) if want_rows else None
 

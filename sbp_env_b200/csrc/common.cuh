@@ -73,8 +73,10 @@ struct SbpNvtxRange {
 // ------------------------------------------------------------- handles -----
 // scratch slots: 0,1 kNN partial lists / near work-space; 2-4 staging of the *_host entry points
 // and the fused query; 5,6 cell grid and seeds; 7 append / read staging; 8,9 kNN filter lists;
-// 10,11 filter shadow / done flags; 12,13 sbp_prm_connect2d (row poses, kNN rows); 14,15 spare
-#define SBP_SCRATCH_SLOTS 16
+// 10,11 filter shadow / done flags; 12,13 sbp_prm_connect2d (row poses, kNN rows); 14 cell-sorted
+// poses; 15 row positions of sbp_graph_build_packed_rows; 16 candidate positions of the fused PRM kernels;
+// 17 fp64 distances of a precision-32 kNN call
+#define SBP_SCRATCH_SLOTS 20
 // Tuning / instrumentation knobs (sbp_ctx_tune): per context, so that two contexts -- or two
 // threads driving different contexts -- never see each other's settings.  None of them changes
 // a result; the defaults are the measured optima.
@@ -145,12 +147,34 @@ int sbp_ctx_scratch(sbp_ctx *ctx, int slot, size_t bytes, void **out);
 // major, all n of them), of which this call answers the cell-sorted positions [p0, p0 + count);
 // on return `ids` is the cell-sorted permutation of the node ids (NULL when no cell grid was
 // built: the rows were then all answered, in index order).
+struct PrmFusedArgs;
 struct KnnRowsPart {
     int64_t p0 = 0, count = 0;
     int deterministic = 0;           // order the ids inside every cell (all ranks see the same ids)
     const int32_t *ids = nullptr;    // out
+    PrmFusedArgs *fused = nullptr;   // in: answer the rows with prm.cu's fused kNN + visibility kernel
+    int fused_ran = 0;               // out: that kernel was launched (ids are then sorted inside every cell)
+    const uint8_t *done = nullptr;   // out (fused_ran): per node, 1 = row settled by the fused kernel
+    const int32_t *pending = nullptr;  // out (fused_ran): device counter of the rows it left
 };
+#define PRM_FUSED_KMAX 21            // list lengths (k + 1) the fused kernel is instantiated for
+// the cell grid as the fused kernel sees it (knn.cu builds it, prm.cu walks it)
+struct CellGridView {
+    const double *b4;                // bounding box (min x, max x, min y, max y)
+    int G;                           // cells per side
+    const int32_t *start;            // [G * G + 1] first position of every cell (row major)
+    const int32_t *ids;              // [n] node ids in cell order, ascending inside a cell
+    const double2 *pts;              // [n] their poses
+    int64_t n;
+    const double *maxabs;            // device scalar: max |coordinate| in the store (inf = non-finite)
+};
+int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int k, int r_init, int limit,
+                             int64_t p0, int64_t count, double *seed2, uint8_t *done, int32_t *pending,
+                             PrmFusedArgs *args);
 int32_t sbp_knn_rows_part(sbp_nodes *s, const double *X_all, int32_t k, int64_t *idx, KnnRowsPart *part);
+// ... answers the rows from the cell grid (and, for lists of up to PRM_FUSED_KMAX entries, with
+// prm.cu's fused kernels) when this holds
+bool sbp_knn_rows_use_grid(const sbp_nodes *s);
 
 // Device view of the bit-packed occupancy map.
 //   pixel (x, y), 0 <= x < W, 0 <= y < H  (the reference's `_img[x, y]`)
@@ -179,14 +203,17 @@ struct sbp_map {
     uint32_t *d_rows = nullptr;
     MapView rows{};
     bool rows_smem_resident = false;
-    // Third, column-major copy for the y-major lines of the PRM connection kernel (prm.cu; built
-    // on first use): word = x * HR + (y >> 5), bit = y & 31; `cols.SX` holds HR.
-    uint32_t *d_cols = nullptr;
-    MapView cols{};
+    // Coarse level for edge walks on big maps (built on first use, sbp_map_ensure_allfree): a 2-bit
+    // code per 8x8-pixel tile, 1 = all 64 pixels free, 2 = all blocked, 0 = mixed; a word = 4 x 4
+    // tiles, 8 x 4 words = one 128-byte line (layout: map.cu:k_tile_codes, lookup:
+    // device_fns.cuh:TileCodes; af.AW = blocks per row).  1/32 of the map's size (4 MiB for 32k^2):
+    // it stays in L1 / L2 where the map itself does not.
+    uint32_t *d_allfree = nullptr;
+    struct AllFreeView { const uint32_t *words; int32_t AW; } af{nullptr, 0};
 };
 
 int32_t sbp_map_ensure_rows(sbp_map *map);
-int32_t sbp_map_ensure_cols(sbp_map *map);
+int32_t sbp_map_ensure_allfree(sbp_map *map);
 
 struct sbp_nodes {
     sbp_ctx *ctx = nullptr;

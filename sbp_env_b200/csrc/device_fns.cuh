@@ -61,6 +61,74 @@ __device__ __forceinline__ bool edge_visible_seq(const uint32_t *words, const Ma
     return true;
 }
 
+// ---- two-level walk for maps that do not fit shared memory (sbp_map::af, common.cuh) ----------
+// The line is cut into CHUNKS of up to 8 pixels that share one aligned group of 8 major
+// coordinates.  Between the first and the last pixel of a chunk the minor coordinate moves by at
+// most 7, so the chunk's pixels lie in the 8x8 tile of its first pixel and the 8x8 tile of its
+// last pixel (often the same), and each of the two holds a pixel of the line: when the coarse
+// level says one of them is all blocked the edge is blocked, when it says both are all free the
+// chunk is free, without touching the map; otherwise the chunk's pixels are tested one by one as
+// the reference does (collisionChecker.py:141, :204-210).  The chunk ends come from the closed
+// form of the header of collide2d.cu -- pixel i has made q_i = floor((i * |db| + c) / da) minor
+// steps, c = da - 1 - floor(da / 2), and the reference's error term before pixel i is
+// da - 1 - (i * |db| + c) mod da -- so the decision is the reference's for every map, whatever
+// its structure.
+// Requires: every pixel of the line inside [0, W) x [0, H) (no numpy wrap-around), da < 65536.
+// Lookup of the 2-bit tile codes (map.cu:k_tile_codes) with the last word kept in registers:
+// consecutive chunks of an edge mostly stay inside one 32 x 32-pixel word.
+struct TileCodes {
+    const uint32_t *__restrict__ af;
+    int BW;
+    uint32_t cur_idx, cur_w;
+    __device__ __forceinline__ TileCodes(const uint32_t *a, int bw) : af(a), BW(bw), cur_idx(0xffffffffu), cur_w(0u) {}
+    __device__ __forceinline__ uint32_t get(int tx, int ty) {
+        const uint32_t wx = (uint32_t)tx >> 2, wy = (uint32_t)ty >> 2;
+        const uint32_t idx = (((wy >> 2) * (uint32_t)BW + (wx >> 3)) << 5) + ((wy & 3u) << 3) + (wx & 7u);
+        if (idx != cur_idx) { cur_idx = idx; cur_w = __ldg(af + idx); }
+        return (cur_w >> ((((ty & 3) << 2) | (tx & 3)) << 1)) & 3u;
+    }
+};
+
+__device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ tiled, int SX,
+                                                const uint32_t *__restrict__ af, int AW, int a1, int b1,
+                                                uint32_t da, uint32_t adb, int ystep, bool steep) {
+    const uint32_t dd = da ? da : 1u;
+    const uint32_t c = da ? da - 1u - (da >> 1) : 0u;
+    // quotient estimate from below (2e-6 covers the roundings of the conversion, the reciprocal
+    // and the product: the estimate is q or q - 1, one correction step)
+    const float rcp = __fdividef(0.999998f, (float)dd);
+    TileCodes codes(af, AW);
+    uint32_t i = 0, q = 0, r = c;
+    while (i <= da) {
+        const int a = a1 + (int)i, b = b1 + ystep * (int)q;
+        uint32_t ie = i + (7u - ((uint32_t)a & 7u));
+        ie = ie < da ? ie : da;
+        const uint32_t num = ie * adb + c;
+        uint32_t qe = (uint32_t)(__uint2float_rz(num) * rcp);
+        uint32_t re = num - qe * dd;
+        if (re >= dd) { re -= dd; ++qe; }
+        const int be = b1 + ystep * (int)qe;
+        const int ta = a >> 3, tb0 = b >> 3, tb1 = be >> 3;
+        const uint32_t c0 = codes.get(steep ? tb0 : ta, steep ? ta : tb0);
+        const uint32_t c1 = codes.get(steep ? tb1 : ta, steep ? ta : tb1);
+        if ((c0 | c1) & 2u) return false;
+        if (!(c0 & c1 & 1u)) {
+            int E = (int)da - 1 - (int)r, aa = a, bb = b;
+            for (uint32_t j = i; j <= ie; ++j) {
+                if (!map_free<true>(tiled, SX, steep ? bb : aa, steep ? aa : bb)) return false;
+                E -= (int)adb;
+                if (E < 0) { bb += ystep; E += (int)da; }
+                ++aa;
+            }
+        }
+        i = ie + 1u;
+        q = qe;
+        r = re + adb;
+        if (r >= dd) { r -= dd; ++q; }
+    }
+    return true;
+}
+
 // ======================= 4-DoF arm (collisionChecker.py:346-503) ================
 // Sequential Bresenham walk of one link; all pixels free?  Order is irrelevant
 // for the boolean, so the canonical traversal is walked directly.
@@ -172,6 +240,15 @@ __device__ __forceinline__ int arm_edge_seq(const uint32_t *words, const MapView
         if (r == 2) state = 2;
     }
     return state;
+}
+
+// cell of a coordinate in the uniform G x G grid over [mn, mx] (kNN cell grid; monotone in v)
+__device__ __forceinline__ int cell_of(double v, double mn, double mx, int G) {
+    double w = mx - mn;
+    if (!(w > 0.0)) return 0;
+    double c = floor((v - mn) * ((double)G / w));
+    if (!(c >= 0.0)) return 0;                                      // negative or NaN
+    return c > (double)(G - 1) ? G - 1 : (int)c;
 }
 
 // ======================= distances (rrtPlanner.py:278, prmPlanner.py:39, engine.py:13-24) =====

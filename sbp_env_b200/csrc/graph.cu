@@ -101,6 +101,10 @@ struct EdgeSource {
     int32_t k;
     int64_t first_row, n, m;
     int32_t undirected;
+    // rows in an explicit order (sbp_prm_connect2d_sorted): block row r belongs to node row_ids[r],
+    // node u's row is row_pos[u] (both NULL: row r = node first_row + r)
+    const int32_t *row_ids = nullptr;
+    const int32_t *row_pos = nullptr;
     __device__ __forceinline__ bool cand(int64_t t, int64_t &u) const {
         if (packed) {
             const int32_t c = packed[t];
@@ -112,14 +116,14 @@ struct EdgeSource {
     }
     __device__ __forceinline__ bool edge(int64_t t, int64_t &u, int64_t &v) const {
         if (!cand(t, u)) return false;
-        v = dst ? dst[t] : first_row + t / k;
+        v = dst ? dst[t] : (row_ids ? (int64_t)row_ids[t / k] : first_row + t / k);
         return u >= 0 && u < n && v >= 0 && v < n;
     }
     // the mirrored arc v -> u of kept candidate (row v, neighbour u) duplicates an arc the block
     // already holds iff row u lists v as a kept candidate
     __device__ __forceinline__ bool mirror_is_duplicate(int64_t u, int64_t v) const {
         if (dst) return false;
-        const int64_t r = u - first_row;
+        const int64_t r = row_pos ? (int64_t)row_pos[u] : u - first_row;
         if (r < 0 || r >= m) return false;
         for (int c = 0; c < k; ++c) {
             int64_t w;
@@ -278,6 +282,38 @@ extern "C" int32_t sbp_graph_build_packed(sbp_graph *g, const int32_t *packed, i
     SBP_REQUIRE(g && (m == 0 || packed), "sbp_graph_build_packed: NULL argument");
     SBP_REQUIRE(m >= 0 && k >= 1 && first_row >= 0, "sbp_graph_build_packed: bad sizes");
     EdgeSource es{nullptr, packed, nullptr, nullptr, m * k, k, first_row, g->n, m, undirected ? 1 : 0};
+    return graph_build(g, es);
+}
+
+__global__ void k_graph_row_pos(const int32_t *__restrict__ row_ids, int64_t m, int64_t n, int32_t *__restrict__ row_pos) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = row_ids[r];
+        if (v >= 0 && (int64_t)v < n) row_pos[v] = (int32_t)r;
+    }
+}
+
+extern "C" int32_t sbp_graph_build_packed_rows(sbp_graph *g, const int32_t *packed, const int32_t *row_ids,
+                                               int64_t m, int32_t k, int32_t undirected) {
+    SBP_NVTX("sbp_graph_build_packed_rows");
+    SBP_REQUIRE(g && (m == 0 || (packed && row_ids)), "sbp_graph_build_packed_rows: NULL argument");
+    SBP_REQUIRE(m >= 0 && k >= 1, "sbp_graph_build_packed_rows: bad sizes");
+    sbp_ctx *ctx = g->ctx;
+    SBP_DEVICE(ctx);
+    EdgeSource es{nullptr, packed, nullptr, nullptr, m * k, k, 0, g->n, m, undirected ? 1 : 0};
+    es.row_ids = row_ids;
+    if (undirected) {
+        // the inverse of row_ids (nodes without a row: -1), for the duplicate test of mirrored arcs
+        void *pos = nullptr;
+        int32_t rc = sbp_ctx_scratch(ctx, 15, (size_t)(g->n > 0 ? g->n : 1) * sizeof(int32_t), &pos);
+        if (rc) return rc;
+        SBP_CUDA(cudaMemsetAsync(pos, 0xff, (size_t)g->n * sizeof(int32_t), ctx->stream));
+        int blocks = (int)((m + 255) / 256);
+        if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+        if (blocks < 1) blocks = 1;
+        k_graph_row_pos<<<blocks, 256, 0, ctx->stream>>>(row_ids, m, g->n, (int32_t *)pos);
+        ctx->launches++;
+        es.row_pos = (const int32_t *)pos;
+    }
     return graph_build(g, es);
 }
 

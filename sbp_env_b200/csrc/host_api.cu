@@ -183,7 +183,7 @@ extern "C" int32_t sbp_nodes_knn_host(sbp_nodes *s, const double *X, int64_t m, 
     st.h2d(dX, X, (size_t)m * s->d * 8);
     if (st.rc == SBP_OK) st.rc = sbp_nodes_knn(s, dX, m, k, precision, dI, dist ? dD : nullptr);
     st.d2h(idx, dI, (size_t)m * k * 8);
-    if (dist) st.d2h(dist, dD, (size_t)m * k * 8);
+    if (dist) st.d2h(dist, dD, (size_t)m * k * (precision == 32 ? 4 : 8));    // 32: a float buffer
     st.sync();
     return st.rc;
 }

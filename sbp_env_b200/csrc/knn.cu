@@ -682,14 +682,6 @@ __device__ __forceinline__ void fold_bounds(const double *__restrict__ partial, 
     __syncthreads();
 }
 
-__device__ __forceinline__ int cell_of(double v, double mn, double mx, int G) {
-    double w = mx - mn;
-    if (!(w > 0.0)) return 0;
-    double c = floor((v - mn) * ((double)G / w));
-    if (!(c >= 0.0)) return 0;                                      // negative or NaN
-    return c > (double)(G - 1) ? G - 1 : (int)c;
-}
-
 __global__ void k_cell_hist(const double *__restrict__ soa, int64_t capacity, int64_t n,
                             const double *__restrict__ partial, int nb, double *__restrict__ b4,
                             int G, int32_t *__restrict__ cells) {
@@ -850,6 +842,17 @@ __global__ void k_cell_sort_segments(const int32_t *__restrict__ start, int64_t 
             while (j >= e0 && ids[j] > v) { ids[j + 1] = ids[j]; --j; }
             ids[j + 1] = v;
         }
+    }
+}
+
+// Cell-sorted copy of the 2-D poses (sbp_prm_connect2d's fused kernel): pts[p] = pose of node
+// ids[p], so that a row of cells is one contiguous run of 16-byte records and a candidate costs
+// one coalescable load instead of the dependent pair ids[e] -> soa[id].
+__global__ void k_cell_gather_pts(const double *__restrict__ soa, int64_t capacity, int64_t n,
+                                  const int32_t *__restrict__ ids, double2 *__restrict__ pts) {
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = ids[p];
+        pts[p] = make_double2(soa[v], soa[capacity + v]);
     }
 }
 
@@ -1381,10 +1384,18 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         }
         k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
-        if (part && part->deterministic) {
+        const bool fused_rows = part && part->fused && K <= PRM_FUSED_KMAX;
+        if (part && (part->deterministic || fused_rows)) {
             int sbk = (int)((L + 255) / 256);
             if (sbk > ctx->sm_count * 8) sbk = ctx->sm_count * 8;
             k_cell_sort_segments<<<sbk, 256, 0, ctx->stream>>>(start, L, ids);
+            ctx->launches++;
+        }
+        void *ptsbuf = nullptr;
+        if (fused_rows) {
+            rc = sbp_ctx_scratch(ctx, 14, (size_t)n * sizeof(double2), &ptsbuf);
+            if (rc) return rc;
+            k_cell_gather_pts<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, ids, (double2 *)ptsbuf);
             ctx->launches++;
         }
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
@@ -1402,11 +1413,25 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                 SBP_CUDA(cudaMemsetAsync(donebuf, 1, (size_t)m, ctx->stream));
                 part->ids = ids;
             }
-            KernelTimer timer(ctx, 2);
+            KernelTimer timer(ctx, fused_rows ? -1 : 2);
             // (measured on 50 000 nodes, k = 11, whole call: 4096 queries 44 us warp form / 66 us thread
             // form, 16 384 queries 73 / 74 us, 50 000 queries 137 / 71 us: a one-warp CTA's chain of
             // 32 queries takes ~50 us however few CTAs there are)
-            if (rows_part || ctx->tune.knn_cells >= 3 || (ctx->tune.knn_cells == 2 && m >= 20000)) {
+            if (fused_rows) {
+                // sbp_prm_connect2d: the cell-grid answer of a row AND the visibility of its k candidate
+                // edges in one kernel (prm.cu); rows it does not settle keep done = 0 like below
+                const double per_cell = (double)n / ((double)G * (double)G);
+                int r_init = (int)ceil((sqrt(2.0 * (double)K / per_cell) - 1.0) / 2.0);
+                r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
+                if (ctx->tune.knn_cells_rinit > 0) r_init = ctx->tune.knn_cells_rinit;
+                CellGridView gv{b4, G, start, ids, (const double2 *)ptsbuf, n, s->d_maxabs};
+                rc = sbp_prm_fused_launch(ctx, gv, K, k, r_init, ctx->tune.knn_cells_limit, part->p0, part->count,
+                                          (double *)seedbuf, (uint8_t *)donebuf, pending_all, part->fused);
+                if (rc) return rc;
+                part->fused_ran = 1;
+                part->done = (const uint8_t *)donebuf;
+                part->pending = pending_all;
+            } else if (rows_part || ctx->tune.knn_cells >= 3 || (ctx->tune.knn_cells == 2 && m >= 20000)) {
                 // first ring radius whose block is expected to hold 2 K nodes (then the rectangle of
                 // the K-th distance usually lies inside the block and there is no second pass)
                 const double per_cell = (double)n / ((double)G * (double)G);
@@ -1546,11 +1571,13 @@ static int32_t knn_dispatch_k(sbp_nodes *s, const double *X, int64_t m, int32_t 
 
 // kNN of the stored rows themselves for sbp_prm_connect2d (2-D stores): X_all = the n row poses,
 // idx [n][k]; see KnnRowsPart.  Without a cell grid (small stores, knobs off) every row is answered.
+bool sbp_knn_rows_use_grid(const sbp_nodes *s) {
+    const sbp_ctx *ctx = s->ctx;
+    return s->d == 2 && ctx->tune.knn_seed && ctx->tune.knn_filter && ctx->tune.knn_cells && s->n >= 2048;
+}
+
 int32_t sbp_knn_rows_part(sbp_nodes *s, const double *X_all, int32_t k, int64_t *idx, KnnRowsPart *part) {
-    sbp_ctx *ctx = s->ctx;
-    const bool grid = s->d == 2 && ctx->tune.knn_seed && ctx->tune.knn_filter && ctx->tune.knn_cells &&
-                      s->n >= 2048 && s->n >= 256;
-    return knn_dispatch_k<2>(s, X_all, s->n, k, idx, nullptr, grid ? part : nullptr);
+    return knn_dispatch_k<2>(s, X_all, s->n, k, idx, nullptr, sbp_knn_rows_use_grid(s) ? part : nullptr);
 }
 
 // np.argmin semantics for find_nearest_neighbour_idx (rrtPlanner.py:278-279): a NaN distance is
@@ -1616,29 +1643,54 @@ __global__ void k_fill_empty_knn(int64_t total, int64_t *idx, double *dist) {
     }
 }
 
+__global__ void k_dist_to_f32(const double *__restrict__ d64, int64_t total, float *__restrict__ d32) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x)
+        d32[t] = __double2float_rn(d64[t]);
+}
+
 extern "C" int32_t sbp_nodes_knn(sbp_nodes *s, const double *X, int64_t m, int32_t k,
                                  int32_t precision, int64_t *idx, double *dist) {
     SBP_NVTX("sbp_nodes_knn");
     SBP_REQUIRE(s && (m == 0 || (X && idx)), "sbp_nodes_knn: NULL argument");
     SBP_REQUIRE(m >= 0, "sbp_nodes_knn: m < 0");
     SBP_REQUIRE(k >= 1 && k <= 32, "sbp_nodes_knn: 1 <= k <= 32");
-    SBP_REQUIRE(precision == 64, "sbp_nodes_knn: only the bit-exact fp64 path exists (precision=64)");
+    SBP_REQUIRE(precision == 64 || precision == 32, "sbp_nodes_knn: precision is 64 or 32");
     if (m == 0) return SBP_OK;
     SBP_DEVICE(s->ctx);
+    // precision 32: `dist` is a float buffer.  The selection itself stays the exact one -- the cell-grid
+    // search is bound by its list insertions and dependent loads, not by fp64 arithmetic, so an fp32
+    // selection would buy nothing and lose the index-exactness at ties -- and the distances are
+    // delivered rounded to fp32 (half the output bytes): |d32 - d64| <= 2^-24 d64.
+    double *dist64 = dist;
+    if (precision == 32 && dist) {
+        void *tmp = nullptr;
+        int32_t rc = sbp_ctx_scratch(s->ctx, 17, (size_t)m * k * sizeof(double), &tmp);
+        if (rc) return rc;
+        dist64 = (double *)tmp;
+    }
+    int32_t rc = SBP_OK;
     if (s->n == 0) {
-        k_fill_empty_knn<<<64, 256, 0, s->ctx->stream>>>(m * k, idx, dist);
+        k_fill_empty_knn<<<64, 256, 0, s->ctx->stream>>>(m * k, idx, dist64);
         s->ctx->launches++;
         SBP_CUDA(cudaGetLastError());
-        return SBP_OK;
+    } else {
+        switch (s->d) {
+            case 2: rc = knn_dispatch_k<2>(s, X, m, k, idx, dist64); break;
+            case 3: rc = knn_dispatch_k<3>(s, X, m, k, idx, dist64); break;
+            case 4: rc = knn_dispatch_k<4>(s, X, m, k, idx, dist64); break;
+            case 6: rc = knn_dispatch_k<6>(s, X, m, k, idx, dist64); break;
+            default:
+                sbp_set_error("sbp_nodes_knn: dimension %d not instantiated (2, 3, 4, 6)", s->d);
+                return SBP_ERR_ARG;
+        }
     }
-    switch (s->d) {
-        case 2: return knn_dispatch_k<2>(s, X, m, k, idx, dist);
-        case 3: return knn_dispatch_k<3>(s, X, m, k, idx, dist);
-        case 4: return knn_dispatch_k<4>(s, X, m, k, idx, dist);
-        case 6: return knn_dispatch_k<6>(s, X, m, k, idx, dist);
-        default:
-            sbp_set_error("sbp_nodes_knn: dimension %d not instantiated (2, 3, 4, 6)", s->d);
-            return SBP_ERR_ARG;
+    if (rc == SBP_OK && precision == 32 && dist) {
+        int blocks = (int)((m * k + 255) / 256);
+        if (blocks > s->ctx->sm_count * 8) blocks = s->ctx->sm_count * 8;
+        k_dist_to_f32<<<blocks, 256, 0, s->ctx->stream>>>(dist64, m * k, (float *)dist);
+        s->ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
     }
+    return rc;
 }
 

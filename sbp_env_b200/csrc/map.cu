@@ -267,13 +267,52 @@ int32_t sbp_map_ensure_rows(sbp_map *m) {
     return SBP_OK;
 }
 
+// Coarse level: a 2-bit code per 8x8 tile (= one aligned 64-bit pair of map words): 1 = all 64
+// pixels free, 2 = all blocked, 0 = mixed.  A 32-bit word holds the 4 x 4 tiles of a 32 x 32-pixel
+// square; 8 (x) x 4 (y) words form one 128-byte line = a 256 x 128-pixel block, blocks row major:
+// the edges a warp of neighbouring rows walks fall into a handful of lines.  One thread per word.
+__global__ void k_tile_codes(MapView mv, int BW, int BH, uint32_t *__restrict__ af) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)BW * BH * 32) return;
+    const int blk = (int)(t >> 5), in = (int)(t & 31);
+    const int wx = (blk % BW) * 8 + (in & 7), wy = (blk / BW) * 4 + (in >> 3);
+    uint32_t out = 0;
+    for (int j = 0; j < 16; ++j) {
+        const int tx = wx * 4 + (j & 3), ty = wy * 4 + (j >> 2);
+        if (tx >= mv.SX * 2 || ty >= mv.SY * 2) continue;        // (tiles past the last sector: mixed)
+        const uint32_t sec = (uint32_t)(ty >> 1) * (uint32_t)mv.SX + (uint32_t)(tx >> 1);
+        const uint32_t wi = sec * 8u + (uint32_t)((ty & 1) * 4 + (tx & 1) * 2);
+        const uint2 w = *reinterpret_cast<const uint2 *>(mv.words + wi);
+        // a tile that sticks out of the map holds padding zeros: never "all free"; "all blocked"
+        // is still right for every pixel inside the map
+        const uint32_t code = (w.x & w.y) == 0xffffffffu ? 1u : ((w.x | w.y) == 0u ? 2u : 0u);
+        out |= code << (2 * j);
+    }
+    af[t] = out;
+}
+
+int32_t sbp_map_ensure_allfree(sbp_map *m) {
+    if (m->d_allfree) return SBP_OK;
+    sbp_ctx *ctx = m->ctx;
+    const int TX = m->view.SX * 2, TY = m->view.SY * 2;         // tiles
+    const int BW = (TX + 31) / 32, BH = (TY + 15) / 16;         // blocks of 32 x 16 tiles
+    const int64_t words = (int64_t)BW * BH * 32;
+    SBP_CUDA(cudaMalloc(&m->d_allfree, (size_t)words * 4));
+    k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, BW, BH, m->d_allfree);
+    ctx->launches++;
+    SBP_CUDA(cudaGetLastError());
+    m->af.words = m->d_allfree;
+    m->af.AW = BW;
+    return SBP_OK;
+}
+
 extern "C" int32_t sbp_map_destroy(sbp_map *map) {
     if (!map) return SBP_OK;
     SbpDeviceGuard guard(map->ctx->device);
     cudaStreamSynchronize(map->ctx->stream);
     if (map->d_words) cudaFree(map->d_words);
     if (map->d_rows) cudaFree(map->d_rows);
-    // (d_cols is a view into the d_rows allocation)
+    if (map->d_allfree) cudaFree(map->d_allfree);
     delete map;
     return SBP_OK;
 }

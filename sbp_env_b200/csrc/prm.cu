@@ -5,210 +5,464 @@
 //   PRMPlanner.build_graph, the body of the double loop     planners/prmPlanner.py:91-101
 //       for v in nodes: for m_g in near(v): if m_g is v: continue
 //           cc.visible(m_g.pos, v.pos)  ->  edge m_g -> v
+//   nearest_neighbours: np.linalg.norm(poses - pos, axis=1)  planners/prmPlanner.py:28-44
 //   ImgCollisionChecker.visible / get_line (Bresenham)       collisionChecker.py:134-145, :155-215
 // with the k nearest neighbours as the candidate set instead of the PRM* radius.
 //
-// Why a dedicated kernel (profiles/r2_visible_cfg5_before_full.txt: the general kernel spent 48
-// instructions per pixel step with 17 of 32 lanes active on this workload):
-//   * rows are processed in CELL-SORTED order (the permutation the kNN's cell grid built anyway):
-//     the 32 rows of a CTA are spatial neighbours, their edges share map sectors (L1 hits);
-//   * a CTA is 32 rows, a warp walks one COLUMN of them (lane = row): the j-th nearest neighbours
-//     of 32 neighbouring rows are edges of nearly equal length, so the warp's lock-step walk wastes
-//     few lanes (a warp of mixed columns idles behind its longest edge); warp w takes columns w and
-//     k - 1 - w one after the other, which gives every warp of the CTA the same amount of pixels;
-//   * the walk reads row-major / column-major copies of the map (x-major lines: word =
-//     y * WR + (x >> 5); y-major lines: word = x * HR + (y >> 5)): the major axis always runs along
-//     the bits of a word and a minor step is one add, ~16 instructions per pixel instead of 48 in
-//     the general kernel on the tiled layout (whose 16 x 16-pixel sector locality the cell-sorted
-//     row order replaces: the CTA's working window of the map stays in L1).  Edges with all four
-//     endpoint coordinates inside [0, W) x [0, H) -- no numpy wrap-around to apply -- take this
-//     path, anything else the general sequential walker;
-//   * every lane stores its codes itself (local buffer, pinned host memory, or the NVSwitch
-//     multicast mapping of the ranks' symmetric buffer: the multi-GPU exchange of the adjacency
-//     overlaps the walk); no barrier after the row setup.
+// Two kernels answer the rows, a THREAD per row and the rows in CELL-SORTED order (the permutation
+// of the kNN's counting sort, ascending node index inside a cell):
+//   k_prm_knn   the row's k nearest other nodes from the cell grid.  The 32 rows of a warp are
+//     spatial neighbours: they scan the same cells of the cell-sorted pose copy `pts` (one 16-byte
+//     load per candidate, no ids[e] -> soa[id] chain).  The list is kept sorted on the fp32
+//     round-down of the exact fp64 d^2 (dx*dx + dy*dy unfused: the reference's sum before its root)
+//     with the cell-sorted position as payload -- 2 registers and 5 instructions per slot and
+//     insertion, no square root; equal keys are decided on the exact d^2 and the node index
+//     (NearList).  The reference orders by (sqrt_rn(d^2), index); that differs from (d^2, index) only
+//     where two DIFFERENT d^2 round to one root, i.e. inside a relative band of 2^-51: a row that
+//     meets such a pair (band 2^-49) is not answered here (done = 0).  Coverage: with the list full
+//     every node that can still enter lies in the cell rectangle of q +- sqrt(hi (1 + 2^-49))
+//     (1 + 1e-9); cells of it outside the scanned block are scanned too, rectangles of
+//     more than `limit` nodes are left to the exact path.
+//   k_prm_walk  the row's k Bresenham walks, one after the other: in column j all 32 lanes walk
+//     the edge to their j-th nearest neighbour -- nearly equal lengths, few idle lanes.  The walk is
+//     TWO-LEVEL (device_fns.cuh:edge_free_tiles): chunks of up to 8 pixels are decided by the 2-bit
+//     codes of one or two 8x8 tiles (all free / all blocked / mixed; 4 MiB for the 32k^2 map: L1 / L2
+//     resident where the map itself is not); only chunks touching a mixed tile are tested pixel by
+//     pixel.  Edges with an endpoint outside [0, W) x [0, H) (numpy wrap-around, out of range) take
+//     the general sequential walker.  Output rows in node order (4-byte stores per lane) or in
+//     cell-sorted order (`sorted_rows`: a warp's 32 rows are one contiguous block, staged in shared
+//     memory and stored coalesced -- what pinned host memory and the NVSwitch multicast mapping need).
+// Rows k_prm_knn does not settle (non-finite or huge coordinates, too few nodes, near ties, oversized
+// rectangles) go through the exact pipeline of knn.cu (seeded filter + refine + fallback scan, all
+// returning at once when nothing is pending) and k_prm_visible2d.
 #include "common.cuh"
 #include "device_fns.cuh"
 
-// ------------------------------------------------- column-major map copy -----
-// Transposed twin of the row-major copy (sbp_map::rows): word = x * HR + (y >> 5), bit = y & 31.
-__global__ void k_cols_from_tiles(MapView mv, int HR, uint32_t n_words, uint32_t *__restrict__ out) {
-    for (uint32_t wi = blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += gridDim.x * blockDim.x) {
-        const int x = (int)(wi / (uint32_t)HR), y0 = (int)(wi % (uint32_t)HR) * 32;
-        uint32_t w = 0;
-        if (x < mv.W)
-            for (int b = 0; b < 32; ++b)
-                if (y0 + b < mv.H && map_free<true>(mv.words, mv.SX, x, y0 + b)) w |= 1u << b;
-        out[wi] = w;
-    }
-}
-
-// The column-major copy lives in ONE allocation with the row-major copy, right behind it: the
-// connection kernel then addresses both through one base pointer and a 32-bit word offset.
-int32_t sbp_map_ensure_cols(sbp_map *m) {
-    if (m->d_cols) return SBP_OK;
-    sbp_ctx *ctx = m->ctx;
-    int32_t rc = sbp_map_ensure_rows(m);
-    if (rc) return rc;
-    const int HR = ((m->view.H + 31) / 32) | 1;
-    const uint64_t nw = ((uint64_t)HR * (uint64_t)m->view.W + 3ull) & ~3ull;
-    const uint64_t nr = m->rows.n_words;
-    SBP_REQUIRE(nr + nw <= 0xffffffffull / 4ull, "row / column-major map copies too large for 32-bit word indexing");
-    uint32_t *both = nullptr;
-    SBP_CUDA(cudaMalloc(&both, (size_t)(nr + nw) * 4));
-    SBP_CUDA(cudaMemcpyAsync(both, m->d_rows, (size_t)nr * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-    SBP_CUDA(cudaStreamSynchronize(ctx->stream));      // nothing in flight reads the old copy any more
-    SBP_CUDA(cudaFree(m->d_rows));
-    m->d_rows = both;
-    m->rows.words = both;
-    m->d_cols = both + nr;                             // a view: freed with d_rows
-    m->cols = m->view;
-    m->cols.words = m->d_cols;
-    m->cols.SX = HR;
-    m->cols.n_words = (uint32_t)nw;
-    int blocks = (int)((nw + 255) / 256);
-    if (blocks > ctx->sm_count * 16) blocks = ctx->sm_count * 16;
-    k_cols_from_tiles<<<blocks, 256, 0, ctx->stream>>>(m->view, HR, (uint32_t)nw, m->d_cols);
-    ctx->launches++;
-    SBP_CUDA(cudaGetLastError());
-    return SBP_OK;
-}
-
-// ------------------------------------------------------------ the kernel ----
-#define PRM_ROWS 32          // rows per CTA (= lanes of a warp)
 #define PRM_KMAX 31          // k <= 31 (the kNN lists hold k + 1 <= 32 entries)
+#define PRM_TPB 128
 
 struct PrmOut {
     int64_t *nbr;            // [n][k] neighbour index (nullable)
     uint8_t *vis;            // [n][k] 1 = slot filled and edge free (nullable)
     int32_t *packed;         // [n][k] (nbr + 1) * 2 + vis (nullable)
     int packed_mc;           // packed is the multicast (NVLS) address of a symmetric buffer
+    int sorted_rows;         // rows of all three outputs in cell-sorted order (row = position in `ids`)
 };
 
-__device__ __noinline__ bool prm_edge_slow(const MapView &tiled, double2 p, double2 q) {
+struct PrmFusedArgs {
+    MapView tiled;
+    const uint32_t *af;
+    int AW;
+    PrmOut out;
+    int32_t *flags;
+    // the row poses as [n][2] for the exact path: written only when k_prm_knn left rows pending
+    const double *soa;
+    int64_t capacity;
+    double2 *X;
+};
+
+__device__ __noinline__ bool prm_edge_slow(const MapView &tiled, double px, double py, double qx, double qy,
+                                           int *flag) {
     int f2 = 0;
-    return edge_visible_seq<false>(tiled.words, tiled, p.x, p.y, q.x, q.y, f2);
+    const bool r = edge_visible_seq<false>(tiled.words, tiled, px, py, qx, qy, f2);
+    *flag |= f2;
+    return r;
 }
 
-// One candidate edge (row lane, column col): its adjacency code.
-//   x-major lines walk the row-major copy (word = y * WR + (x >> 5), bit = x & 31), y-major lines
-//   the column-major copy (word = x * HR + (y >> 5), bit = y & 31): in both the major axis runs
-//   along the bits of a word and a minor step moves one row of words, so the loop is the same for
-//   every lane: wi = rowoff + (a >> 5), rowoff += +-WR on a minor step.
-__device__ __forceinline__ int32_t prm_edge_code(const MapView &tiled, const uint32_t *__restrict__ words, int WR,
-                                                 uint32_t cols_off, int HR,
-                                                 const double *__restrict__ soa, int64_t capacity, int64_t n,
-                                                 int32_t v, int32_t nb, double2 q, int &myflag) {
-    const unsigned FULL = 0xffffffffu;
-    const bool exists = v >= 0 && nb >= 0 && (int64_t)nb < n;
-    double2 p = q;
-    if (exists) p = make_double2(soa[nb], soa[capacity + nb]);
-    bool result = false;
-    // visible(m_g.pos, v.pos): start = neighbour, end = row node (the 2-D line is direction
-    // symmetric, but the argument order is the reference's)
-    Edge2D ed = make_edge(p.x, p.y, q.x, q.y, tiled.W, tiled.H);
-    if (v >= 0) myflag |= ed.flag;
-    const bool fast = exists && ed.walk && ed.x1 >= 0 && ed.y1 >= 0 && ed.x2 >= 0 && ed.y2 >= 0;
-    if (exists && ed.walk && !fast)                   // negative coordinates: numpy wrap-around
-        result = prm_edge_slow(tiled, p, q);
-    const int stride = ed.steep ? HR : WR;
-    const int da = (int)ed.da;
-    int adb = (int)ed.adb;
-    asm volatile("" : "+r"(adb));                                    // (keep it in a register: no re-derivation per step)
-    const int dstep = ed.ystep * stride;                             // row offset of one minor step
-    int a = ed.a1, err = da >> 1;                                    // :198
-    int left = fast ? da + 1 : 0;                                    // pixels still to test
-    uint32_t rowoff = (uint32_t)(ed.b1 * stride) + (ed.steep ? cols_off : 0u);
-    bool freeline = true;
-    while (__any_sync(FULL, left > 0)) {
+__device__ __forceinline__ void prm_store_packed(const PrmOut &out, int64_t e, int32_t code) {
+    if (out.packed_mc)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(out.packed + e),
+                     "f"(__int_as_float(code)) : "memory");
+    else
+        out.packed[e] = code;
+}
+
+// visible(m_g.pos, v.pos) of one candidate: start = neighbour p, end = row node q (the 2-D line is
+// direction symmetric, but the argument order is the reference's)
+__device__ __forceinline__ bool prm_edge(const MapView &tiled, const uint32_t *__restrict__ af, int AW, double px,
+                                         double py, double qx, double qy, int &flag) {
+    const double W = (double)tiled.W, H = (double)tiled.H;
+    if (px >= 0.0 && px < W && py >= 0.0 && py < H && qx >= 0.0 && qx < W && qy >= 0.0 && qy < H) {
+        // all four coordinates truncate into the index range, nothing wraps (:173-174)
+        const int x1 = __double2int_rz(px), y1 = __double2int_rz(py), x2 = __double2int_rz(qx), y2 = __double2int_rz(qy);
+        const int dx = x2 - x1, dy = y2 - y1;
+        const bool steep = abs(dy) > abs(dx);                            // :179
+        int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;                  // :182-184
+        int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+        if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }   // :188-191
+        return edge_free_tiles(tiled.words, tiled.SX, af, AW, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
+                               b1 < b2 ? 1 : -1, steep);
+    }
+    return prm_edge_slow(tiled, px, py, qx, qy, &flag);
+}
+
+// ------------------------------------------- neighbour list on float keys -----
+// K nearest by (d^2, node index), the row itself excluded.  The list is sorted on kf =
+// round-down-to-fp32(d^2) with the cell-sorted position as payload: two registers and five
+// instructions per slot and insertion.  Rounding is monotone, so entries with different keys are
+// in the order of their exact d^2; whenever a candidate meets an EQUAL key the slow branch
+// recomputes the exact fp64 d^2 of those entries from `pts` and orders by (d^2, node index) like
+// the reference (a stable argsort of the rounded roots: equal d^2 have equal roots).  What the
+// keys cannot decide is a pair of DIFFERENT d^2 inside the relative band 2^-49, whose roots may
+// round to one value (then the lower index wins regardless of d^2): such a pair always shares its
+// float key, is seen by the slow branch and marks the row ambiguous (-> exact path).
+#define PRM_BAND 1.0000000000000018      // 1 + 2^-49
+__device__ __forceinline__ double prm_d2(double2 c, double qx, double qy) {
+    const double dx = __dsub_rn(c.x, qx), dy = __dsub_rn(c.y, qy);     // poses - pos (prmPlanner.py:39)
+    return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));            // norm: unfused sum of squares
+}
+
+template <int K>
+struct NearList {
+    float kf[K];
+    int32_t e[K];            // cell-sorted position, -1 = empty (kf = +inf)
+    double hi;               // candidates with d^2 < hi can still enter (+inf until the list is full)
+    bool amb;                // a near tie was seen: the order needs the rounded roots
+    __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int st = 0; st < 4; ++st) {
-            if (left > 0) {
-                const uint32_t w = __ldg(&words[rowoff + ((uint32_t)a >> 5)]);
-                const bool fr = (w >> (a & 31)) & 1u;                // :141, :151
-                err -= adb;                                          // :207-210
-                const int m = err >> 31;
-                err += da & m;
-                rowoff += (uint32_t)(dstep & m);
-                ++a;
-                --left;
-                if (!fr) { freeline = false; left = 0; }
+        for (int t = 0; t < K; ++t) { kf[t] = INFINITY; e[t] = -1; }
+        hi = INFINITY;
+        amb = false;
+    }
+    __device__ __forceinline__ void insert(double dd, int32_t pos, double qx, double qy,
+                                           const double2 *__restrict__ pts, const int32_t *__restrict__ ids) {
+        const float key = __double2float_rd(dd);
+        bool anyeq = false;
+#pragma unroll
+        for (int t = 0; t < K; ++t) anyeq |= kf[t] == key;
+        if (!anyeq) {
+            bool r_cur = kf[K - 1] < key;                    // r_t: entry t ranks before the new one
+#pragma unroll
+            for (int t = K - 1; t >= 1; --t) {
+                const bool r_prev = kf[t - 1] < key;
+                const float nk = r_prev ? key : kf[t - 1];
+                const int32_t ne = r_prev ? pos : e[t - 1];
+                kf[t] = r_cur ? kf[t] : nk;
+                e[t] = r_cur ? e[t] : ne;
+                r_cur = r_prev;
+            }
+            kf[0] = r_cur ? kf[0] : key;
+            e[0] = r_cur ? e[0] : pos;
+        } else {
+            const int32_t id = ids[pos];
+            bool r[K];
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+                const bool eq = kf[t] == key;
+                bool before = kf[t] < key;
+                if (eq) {
+                    const double dt = prm_d2(pts[e[t]], qx, qy);
+                    before = dt < dd || (dt == dd && ids[e[t]] < id);
+                    const double lo = dt < dd ? dt : dd, up = dt < dd ? dd : dt;
+                    amb |= (dt != dd) & (up <= lo * PRM_BAND);
+                }
+                r[t] = before;
+            }
+#pragma unroll
+            for (int t = K - 1; t >= 1; --t) {
+                const float nk = r[t - 1] ? key : kf[t - 1];
+                const int32_t ne = r[t - 1] ? pos : e[t - 1];
+                kf[t] = r[t] ? kf[t] : nk;
+                e[t] = r[t] ? e[t] : ne;
+            }
+            kf[0] = r[0] ? kf[0] : key;
+            e[0] = r[0] ? e[0] : pos;
+        }
+        // everything whose key is <= the K-th key may still enter: d^2 < next fp32 above that key
+        const float kth = kf[K - 1];
+        hi = kth < INFINITY ? (double)__uint_as_float(__float_as_uint(kth) + 1u) : INFINITY;
+    }
+    __device__ __forceinline__ bool full() const { return e[K - 1] >= 0; }
+};
+
+// The rows of cells [ya, yb] x [xa, xb] minus the already scanned block [sy0, sy1] x [sx0, sx1]
+// (sx1 < sx0: nothing cut out), the 32 lanes in lock-step: per row one contiguous range of `pts`
+// (two when the block is cut out), U candidates per lane and step, then the lanes insert their
+// passing candidates round by round.  centre_out: rows nearest to `mid` first, so that the list
+// fills with near nodes and its bound tightens early.  `self`: the row's own position (skipped).
+template <int K, int U>
+__device__ __forceinline__ void prm_scan_rows(const double2 *__restrict__ pts, const int32_t *__restrict__ ids,
+                                              const int32_t *__restrict__ start, int G, double qx, double qy,
+                                              int32_t self, NearList<K> &L, bool active, int xa, int xb, int ya,
+                                              int yb, int sx0, int sx1, int sy0, int sy1, int mid,
+                                              bool centre_out) {
+    const unsigned FULL = 0xffffffffu;
+    const int nrows = active ? yb - ya + 1 : 0;
+    const int maxrows = __reduce_max_sync(FULL, nrows);
+    const bool cut = sx1 >= sx0;
+    const int nseg = __any_sync(FULL, active && cut) ? 2 : 1;
+    for (int j = 0; j < maxrows; ++j) {
+        int row = ya + j;
+        if (centre_out) {
+            const int up = mid + ((j + 1) >> 1), dn = mid - ((j + 1) >> 1);
+            const int lo_left = mid - ya, hi_left = yb - mid;      // rows below / above mid
+            const int paired = 2 * (lo_left < hi_left ? lo_left : hi_left);
+            if (j <= paired) row = (j & 1) ? up : dn;
+            else row = lo_left < hi_left ? mid + (j - lo_left) : mid - (j - hi_left);
+        }
+        const bool rowok = j < nrows;
+        const bool in_cut = cut && row >= sy0 && row <= sy1;
+        for (int seg = 0; seg < nseg; ++seg) {
+            // outside the cut rows: [xa, xb]; inside: [xa, sx0 - 1] and [sx1 + 1, xb]
+            const int c0 = seg == 0 ? xa : (sx1 + 1 > xa ? sx1 + 1 : xa);
+            const int c1 = seg == 0 ? (in_cut ? (sx0 - 1 < xb ? sx0 - 1 : xb) : xb) : xb;
+            int32_t e = 0, e1 = 0;
+            if (rowok && c1 >= c0 && (seg == 0 || in_cut)) {
+                e = start[(int64_t)row * G + c0];
+                e1 = start[(int64_t)row * G + c1 + 1];
+            }
+            while (__any_sync(FULL, e < e1)) {
+                double d2[U];
+                unsigned mask = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool ok = e + u < e1 && e + u != self;
+                    d2[u] = prm_d2(pts[e + u < e1 ? e + u : 0], qx, qy);
+                    mask |= (ok && d2[u] < L.hi) ? (1u << u) : 0u;
+                }
+                const int32_t base = e;
+                e += U;
+                while (__any_sync(FULL, mask != 0u)) {
+                    if (mask) {
+                        const int u = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        double dd = d2[0];
+#pragma unroll
+                        for (int v = 1; v < U; ++v) dd = u == v ? d2[v] : dd;
+                        L.insert(dd, base + u, qx, qy, pts, ids);
+                    }
+                }
             }
         }
     }
-    if (fast) result = freeline;
-    return ((nb + 1) << 1) | ((result && exists) ? 1 : 0);
 }
 
-__global__ void __launch_bounds__(512, 3)
-k_prm_visible2d(MapView tiled, MapView rowsv, MapView colsv, const double *__restrict__ soa, int64_t capacity,
-                int64_t n, const int64_t *__restrict__ idx, int K, const int32_t *__restrict__ order, int64_t p0,
-                int64_t count, PrmOut out, int32_t *__restrict__ flags) {
-    __shared__ int32_t s_nbr[PRM_ROWS][PRM_KMAX + 1];
-    __shared__ double2 s_q[PRM_ROWS];
-    __shared__ int32_t s_v[PRM_ROWS];
-    const int k = K - 1;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t pb = (int64_t)blockIdx.x * PRM_ROWS;
-    // ---- phase 0: the CTA's 32 rows -- node id, pose, candidate list with the self entry dropped
-    // (`if m_g is v: continue`, prmPlanner.py:94-95: the column equal to the row index if present,
-    // else the last column, so that rows always hold k candidates)
-    if (threadIdx.x < PRM_ROWS) {
-        const int64_t p = pb + threadIdx.x;
-        int32_t v = -1;
-        if (p < count) v = order ? order[p0 + p] : (int32_t)(p0 + p);
-        s_v[threadIdx.x] = v;
-        if (v >= 0) {
-            s_q[threadIdx.x] = make_double2(soa[v], soa[capacity + v]);
-            const int64_t *row = idx + (int64_t)v * K;
-            int drop = K - 1;
-            for (int c = 0; c < K; ++c)
-                if (row[c] == (int64_t)v) { drop = c; break; }
-            for (int j = 0; j < k; ++j) s_nbr[threadIdx.x][j] = (int32_t)row[j < drop ? j : j + 1];
+// kq = candidates per row; K = list length >= kq.  cand [count][kq]: cell-sorted positions of the
+// row's candidates in the reference's order (rows with done = 0: unspecified).
+template <int K>
+__global__ void __launch_bounds__(PRM_TPB)
+k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t count, double *__restrict__ seed2,
+          uint8_t *__restrict__ done, int32_t *__restrict__ pending, int32_t *__restrict__ cand) {
+    const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x;
+    const bool live = slot < count;
+    const int64_t p = p0 + (live ? slot : 0);
+    const int32_t v = g.ids[p];
+    const double2 q = g.pts[p];
+    const double mnx = g.b4[0], mxx = g.b4[1], mny = g.b4[2], mxy = g.b4[3];
+    const int G = g.G;
+    // finite coordinates whose squared distances stay inside the fp32 range, and at least K other
+    // nodes: otherwise the order involves inf / NaN distances or unfilled slots (pad_nan_row)
+    const bool usable = live && *g.maxabs < 1e18 && g.n > K && mnx <= mxx && mny <= mxy;
+    NearList<K> L;
+    L.init();
+    int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cy_q = 0;
+    bool have_block = false;
+    if (usable) {
+        const int cx = cell_of(q.x, mnx, mxx, G), cy = cell_of(q.y, mny, mxy, G);
+        cy_q = cy;
+        for (int r = r_init;; r = r < 8 ? r + 1 : 2 * r) {
+            x0 = cx - r < 0 ? 0 : cx - r; x1 = cx + r > G - 1 ? G - 1 : cx + r;
+            y0 = cy - r < 0 ? 0 : cy - r; y1 = cy + r > G - 1 ? G - 1 : cy + r;
+            int32_t c = 0;
+            for (int row = y0; row <= y1; ++row)
+                c += g.start[(int64_t)row * G + x1 + 1] - g.start[(int64_t)row * G + x0];
+            have_block = c > K;                                   // K besides the row itself
+            if (have_block || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
         }
     }
-    __syncthreads();
-    // ---- phase 1: warp w walks columns w and k - 1 - w of the 32 rows, one after the other: the
-    // near and the far neighbours of a row pair up, so every warp of the CTA carries about the same
-    // number of pixels (a warp per column would leave the near columns' warps waiting for the far
-    // ones until the CTA retires)
-    const int32_t v = s_v[lane];
-    const double2 q = s_q[lane];
+    prm_scan_rows<K, 4>(g.pts, g.ids, g.start, G, q.x, q.y, (int32_t)p, L, have_block, x0, x1, y0, y1, 0, -1, 0, -1,
+                        cy_q, true);
+    const bool full = have_block && L.full();
+    bool handled = false, pass2 = false;
+    int xa = 0, xb = -1, ya = 0, yb = -1;
+    if (full) {
+        // every node that can still enter has d^2 < hi, or lies in the rounding band above it
+        const double r = sqrt(L.hi * PRM_BAND) * (1.0 + 1e-9) + 1e-300;
+        xa = cell_of(__dsub_rd(q.x, r), mnx, mxx, G); xb = cell_of(__dadd_ru(q.x, r), mnx, mxx, G);
+        ya = cell_of(__dsub_rd(q.y, r), mny, mxy, G); yb = cell_of(__dadd_ru(q.y, r), mny, mxy, G);
+        if (xa >= x0 && xb <= x1 && ya >= y0 && yb <= y1) {
+            handled = true;                                       // the block already covers the rectangle
+        } else if (yb - ya < 64) {
+            int32_t c = 0;
+            for (int row = ya; row <= yb; ++row)
+                c += g.start[(int64_t)row * G + xb + 1] - g.start[(int64_t)row * G + xa];
+            pass2 = c <= limit;
+            handled = pass2;
+        }
+    }
+    // pass 2: the cells of the rectangle outside the block (the block's nodes are in the list already;
+    // the list only improves, so the rectangle of the first bound stays a superset)
+    prm_scan_rows<K, 4>(g.pts, g.ids, g.start, G, q.x, q.y, (int32_t)p, L, pass2, xa, xb, ya, yb, x0, x1, y0, y1, 0,
+                        false);
+    if (full) {
+        // near ties the equal-key test of the insertion cannot see: a pair whose d^2 straddle an fp32
+        // rounding boundary (adjacent keys) -- inside the list, or the K-th entry against a node that
+        // stayed outside (every such node has d^2 >= hi)
+        bool amb2 = prm_d2(g.pts[L.e[K - 1]], q.x, q.y) * PRM_BAND >= L.hi;
+#pragma unroll
+        for (int t = 0; t + 1 < K; ++t)
+            if (L.kf[t + 1] == __uint_as_float(__float_as_uint(L.kf[t]) + 1u))
+                amb2 |= prm_d2(g.pts[L.e[t + 1]], q.x, q.y) <= prm_d2(g.pts[L.e[t]], q.x, q.y) * PRM_BAND;
+        L.amb |= amb2;
+    }
+    handled = handled && !L.amb;
+    if (live) {
+        // (a bound for the exact path's K + 1 entries, the row itself included: the K-th other node)
+        seed2[v] = full ? L.hi * (1.0 + 1e-9) + 1e-300 : INFINITY;
+        done[v] = handled ? 1 : 0;
+        if (!handled) atomicAdd(pending, 1);                      // the exact path has work
+        if (handled) {
+#pragma unroll
+            for (int t = 0; t < K; ++t)
+                if (t < kq) cand[slot * kq + t] = L.e[t];
+        }
+    }
+}
+
+// One thread per row: its kq candidate edges, one after the other (in column j all lanes of the
+// warp walk the edge to their j-th nearest neighbour: nearly equal lengths).
+__global__ void __launch_bounds__(PRM_TPB)
+k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
+           const int32_t *__restrict__ cand, PrmFusedArgs a) {
+    __shared__ int32_t s_code[PRM_KMAX][PRM_TPB];
+    const int tid = threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + tid;
+    const bool live = slot < count;
+    const int64_t p = p0 + (live ? slot : 0);
+    const int32_t v = g.ids[p];
+    const bool work = live && done[v];
+    const double2 q = g.pts[p];
+    const PrmOut &out = a.out;
+    const int64_t orow = out.sorted_rows ? p : (int64_t)v;
+    const bool stage = out.sorted_rows && out.packed;            // packed codes leave through shared memory
+    int myflag = 0;
+    if (work) {
+#pragma unroll 1
+        for (int col = 0; col < kq; ++col) {
+            const int32_t e = cand[slot * kq + col];
+            const int32_t nb = g.ids[e];
+            const double2 pp = g.pts[e];
+            const bool free_edge = prm_edge(a.tiled, a.af, a.AW, pp.x, pp.y, q.x, q.y, myflag);
+            const int32_t code = ((nb + 1) << 1) | (free_edge ? 1 : 0);
+            const int64_t o = orow * kq + col;
+            if (stage) s_code[col][tid] = code;
+            else if (out.packed) prm_store_packed(out, o, code);
+            if (out.nbr) out.nbr[o] = (int64_t)nb;
+            if (out.vis) out.vis[o] = (uint8_t)(code & 1);
+        }
+    }
+    if (stage) {
+        // the warp's 32 rows are one contiguous block of 32 * kq codes: lane l stores words l, l + 32, ...
+        // (rows the kNN kernel did not settle are written later by the exact path)
+        const unsigned FULL = 0xffffffffu;
+        const unsigned okmask = __ballot_sync(FULL, work);
+        const int lane = tid & 31, wbase = tid & ~31;
+        const int64_t slot0 = (int64_t)blockIdx.x * PRM_TPB + wbase;
+        if (slot0 < count) {
+            const int rows = (int)(count - slot0 < 32 ? count - slot0 : 32);
+            for (int i = lane; i < rows * kq; i += 32) {
+                const int row = i / kq, col = i - row * kq;
+                if ((okmask >> row) & 1u) prm_store_packed(out, (p0 + slot0) * kq + i, s_code[col][wbase + row]);
+            }
+        }
+    }
+    if (myflag && a.flags) atomicOr(a.flags, myflag);
+}
+
+__global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X,
+                           const int32_t *__restrict__ pending);
+
+// K = list length of knn.cu's dispatch (entries asked for, rounded up to an instantiated size),
+// k = the entries asked for = candidates per row + the row itself.
+int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int k, int r_init, int limit,
+                             int64_t p0, int64_t count, double *seed2, uint8_t *done, int32_t *pending,
+                             PrmFusedArgs *args) {
+    if (count <= 0) return SBP_OK;
+    const int kq = k - 1;
+    void *cbuf = nullptr;
+    int32_t rc = sbp_ctx_scratch(ctx, 16, (size_t)count * (kq > 0 ? kq : 1) * sizeof(int32_t), &cbuf);
+    if (rc) return rc;
+    const unsigned blocks = (unsigned)((count + PRM_TPB - 1) / PRM_TPB);
+#define PRM_KNN(KK)                                                                                       \
+    k_prm_knn<KK><<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0, count, seed2, done, pending, \
+                                                       (int32_t *)cbuf)
+    {
+        KernelTimer timer(ctx, 2);
+        if (kq <= 4) PRM_KNN(4);
+        else if (kq <= 8) PRM_KNN(8);
+        else if (kq <= 10) PRM_KNN(10);
+        else if (kq <= 16) PRM_KNN(16);
+        else if (kq <= 20) PRM_KNN(20);
+        else { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
+    }
+#undef PRM_KNN
+    (void)K;
+    {
+        KernelTimer timer(ctx, 3);
+        k_prm_walk<<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, p0, count, done, (const int32_t *)cbuf, *args);
+    }
+    // the exact path behind reads the row poses as [n][2]: converted only if it has work
+    int ab = (int)((grid.n + 255) / 256);
+    if (ab > ctx->sm_count * 8) ab = ctx->sm_count * 8;
+    k_rows_aos<<<ab, 256, 0, ctx->stream>>>(args->soa, args->capacity, grid.n, args->X, pending);
+    ctx->launches += 3;
+    SBP_CUDA(cudaGetLastError());
+    return SBP_OK;
+}
+
+// ------------------------------ rows the fused kernel left to the exact path ----
+// One thread per row with done[v] == 0 (all rows when `done` is NULL): the candidate list comes
+// from the kNN rows idx [n][K] (node order) of knn.cu's exact pipeline.
+__global__ void __launch_bounds__(PRM_TPB)
+k_prm_visible2d(MapView tiled, const uint32_t *__restrict__ af, int AW, const double *__restrict__ soa,
+                int64_t capacity, int64_t n, const int64_t *__restrict__ idx, int K,
+                const int32_t *__restrict__ order, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
+                const int32_t *__restrict__ pending, PrmOut out, int32_t *__restrict__ flags) {
+    if (pending && *pending == 0) return;
+    const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x;
+    if (slot >= count) return;
+    const int k = K - 1;
+    const int32_t v = order ? order[p0 + slot] : (int32_t)(p0 + slot);
+    if (done && done[v]) return;
+    const double qx = soa[v], qy = soa[capacity + v];
+    const int64_t *__restrict__ row = idx + (int64_t)v * K;
+    int drop = K - 1;
+    for (int c = K - 2; c >= 0; --c)
+        if (row[c] == (int64_t)v) drop = c;
+    const int64_t orow = out.sorted_rows ? p0 + slot : (int64_t)v;
     int myflag = 0;
 #pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const int col = pass == 0 ? w : k - 1 - w;
-        if (pass == 1 && col <= w) break;
-        const int32_t nb = v >= 0 ? s_nbr[lane][col] : -1;
-        const int32_t code = prm_edge_code(tiled, rowsv.words, rowsv.SX, rowsv.n_words, colsv.SX, soa, capacity, n,
-                                           v, nb, q, myflag);
-        if (v >= 0) {
-            const int64_t e = (int64_t)v * k + col;
-            if (out.packed) {
-                if (out.packed_mc)
-                    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(out.packed + e),
-                                 "f"(__int_as_float(code)) : "memory");
-                else
-                    out.packed[e] = code;
-            }
-            if (out.nbr) out.nbr[e] = (int64_t)nb;
-            if (out.vis) out.vis[e] = (uint8_t)(code & 1);
-        }
+    for (int col = 0; col < k; ++col) {
+        const int32_t nb = (int32_t)row[col < drop ? col : col + 1];
+        bool result = false;
+        if (nb >= 0 && (int64_t)nb < n) result = prm_edge(tiled, af, AW, soa[nb], soa[capacity + nb], qx, qy, myflag);
+        const int32_t code = ((nb + 1) << 1) | (result ? 1 : 0);
+        const int64_t o = orow * k + col;
+        if (out.packed) prm_store_packed(out, o, code);
+        if (out.nbr) out.nbr[o] = (int64_t)nb;
+        if (out.vis) out.vis[o] = (uint8_t)(code & 1);
     }
     if (myflag && flags) atomicOr(flags, myflag);
 }
 
-__global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X) {
+__global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X,
+                           const int32_t *__restrict__ pending) {
+    if (pending && *pending == 0) return;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
         X[t] = make_double2(soa[t], soa[capacity + t]);
 }
 
+__global__ void k_copy_order(const int32_t *__restrict__ ids, int64_t n, int32_t *__restrict__ order_out) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        order_out[t] = ids ? ids[t] : (int32_t)t;
+}
+
 // Rows = stored nodes.  The rows are split into `parts` contiguous runs of the CELL-SORTED
-// order (spatially compact; `part` in [0, parts)): the multi-GPU shard of a rank.  Outputs are
-// [n][k] in NODE order; only the rows of this part are written.
-extern "C" int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
-                                     int64_t *nbr_out, uint8_t *vis, int32_t *packed,
-                                     int32_t packed_multicast, int32_t *flags) {
-    SBP_NVTX("sbp_prm_connect2d");
+// order (spatially compact; `part` in [0, parts)): the multi-GPU shard of a rank.  Only the rows of
+// this part are written.
+static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
+                           int32_t sorted_rows, int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                           int32_t packed_multicast, int32_t *order_out, int32_t *flags) {
     SBP_REQUIRE(map && nodes, "sbp_prm_connect2d: NULL argument");
     SBP_REQUIRE(nbr_out || vis || packed, "sbp_prm_connect2d: no output requested");
     SBP_REQUIRE(nodes->d == 2, "sbp_prm_connect2d: the 2-D checker needs a 2-D node store");
@@ -216,37 +470,61 @@ extern "C" int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, 
     SBP_REQUIRE(k >= 1 && k <= PRM_KMAX, "sbp_prm_connect2d: 1 <= k <= 31");
     SBP_REQUIRE(parts >= 1 && part >= 0 && part < parts, "sbp_prm_connect2d: bad part");
     SBP_REQUIRE(!packed_multicast || packed, "sbp_prm_connect2d: multicast needs the packed output");
+    SBP_REQUIRE(!sorted_rows || order_out, "sbp_prm_connect2d_sorted: order_out is NULL");
     sbp_ctx *ctx = map->ctx;
     SBP_DEVICE(ctx);
     const int64_t n = nodes->n;
     if (n == 0) return SBP_OK;
-    int32_t rc = sbp_map_ensure_rows(map);
+    int32_t rc = sbp_map_ensure_allfree(map);
     if (rc) return rc;
-    if ((rc = sbp_map_ensure_cols(map))) return rc;
     const int K = k + 1;
     void *xbuf = nullptr, *ibuf = nullptr;
     if ((rc = sbp_ctx_scratch(ctx, 12, (size_t)n * 16, &xbuf))) return rc;
     if ((rc = sbp_ctx_scratch(ctx, 13, (size_t)n * K * sizeof(int64_t), &ibuf))) return rc;
     int blocks = (int)((n + 255) / 256);
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
-    k_rows_aos<<<blocks, 256, 0, ctx->stream>>>(nodes->d_soa, nodes->capacity, n, (double2 *)xbuf);
-    ctx->launches++;
+    const bool will_fuse = sbp_knn_rows_use_grid(nodes) && K <= PRM_FUSED_KMAX;
+    if (!will_fuse) {
+        k_rows_aos<<<blocks, 256, 0, ctx->stream>>>(nodes->d_soa, nodes->capacity, n, (double2 *)xbuf, nullptr);
+        ctx->launches++;
+    }
     // this part's run of the cell-sorted order (balanced like distributed.shard_range)
     const int64_t base = n / parts, rem = n % parts;
+    PrmFusedArgs fa{map->view, map->af.words, map->af.AW,
+                    PrmOut{nbr_out, vis, packed, packed_multicast, sorted_rows}, flags,
+                    nodes->d_soa, nodes->capacity, (double2 *)xbuf};
     KnnRowsPart rp;
     rp.p0 = (int64_t)part * base + (part < rem ? part : rem);
     rp.count = base + (part < rem ? 1 : 0);
-    rp.deterministic = parts > 1;
+    rp.deterministic = parts > 1 || sorted_rows;
+    rp.fused = &fa;
     if ((rc = sbp_knn_rows_part(nodes, (const double *)xbuf, K, (int64_t *)ibuf, &rp))) return rc;
+    if (order_out) {
+        k_copy_order<<<blocks, 256, 0, ctx->stream>>>(rp.ids, n, order_out);
+        ctx->launches++;
+    }
     if (rp.count == 0) return SBP_OK;
-    PrmOut out{nbr_out, vis, packed, packed_multicast};
     {
-        KernelTimer timer(ctx, 3);
-        k_prm_visible2d<<<(unsigned)((rp.count + PRM_ROWS - 1) / PRM_ROWS), 32 * ((k + 1) / 2), 0, ctx->stream>>>(
-            map->view, map->rows, map->cols, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
-            rp.p0, rp.count, out, flags);
+        KernelTimer timer(ctx, rp.fused_ran ? -1 : 3);
+        k_prm_visible2d<<<(unsigned)((rp.count + PRM_TPB - 1) / PRM_TPB), PRM_TPB, 0, ctx->stream>>>(
+            map->view, map->af.words, map->af.AW, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
+            rp.p0, rp.count, rp.fused_ran ? rp.done : nullptr, rp.fused_ran ? rp.pending : nullptr, fa.out, flags);
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
+}
+
+extern "C" int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
+                                     int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                                     int32_t packed_multicast, int32_t *flags) {
+    SBP_NVTX("sbp_prm_connect2d");
+    return prm_connect(map, nodes, k, part, parts, 0, nbr_out, vis, packed, packed_multicast, nullptr, flags);
+}
+
+extern "C" int32_t sbp_prm_connect2d_sorted(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part,
+                                            int32_t parts, int64_t *nbr_out, uint8_t *vis, int32_t *packed,
+                                            int32_t packed_multicast, int32_t *order_out, int32_t *flags) {
+    SBP_NVTX("sbp_prm_connect2d_sorted");
+    return prm_connect(map, nodes, k, part, parts, 1, nbr_out, vis, packed, packed_multicast, order_out, flags);
 }

@@ -154,13 +154,17 @@ class NodeStore:
               "sbp_nodes_nearest_host")
         return idx, dist
 
-    def knn(self, X, k: int, return_dist: bool = True):
+    def knn(self, X, k: int, return_dist: bool = True, precision: int = 64):
         """k nearest nodes of every row of X, ordered by (distance, index).
 
         numpy in -> numpy out; CUDA tensor in -> CUDA tensors out.
-        Returns ``(idx int64 [m][k], dist fp64 [m][k])``; rows are padded with
-        ``-1`` / ``inf`` when fewer than k nodes are stored."""
+        Returns ``(idx int64 [m][k], dist [m][k])``; rows are padded with ``-1`` / ``inf`` when
+        fewer than k nodes are stored.  ``precision=64``: fp64 distances, bit-exact with
+        ``np.linalg.norm``; ``precision=32``: the same rows (the selection stays exact) with
+        float32 distances, ``|d32 - d64| <= 2**-24 * d64``."""
         k = int(k)
+        if precision not in (32, 64):
+            raise ValueError("precision is 64 or 32")
         if _is_torch_tensor(X):
             import torch
 
@@ -168,15 +172,16 @@ class NodeStore:
             X = as_device_f64(X, self.dim, device=self.ctx.device)
             m = X.shape[0]
             idx = torch.empty((m, k), dtype=torch.int64, device=X.device)
-            dist = torch.empty((m, k), dtype=torch.float64, device=X.device) if return_dist else None
-            check(_lib.load().sbp_nodes_knn(self._h, ptr(X), m, k, 64, ptr(idx), ptr(dist)),
+            dt = torch.float64 if precision == 64 else torch.float32
+            dist = torch.empty((m, k), dtype=dt, device=X.device) if return_dist else None
+            check(_lib.load().sbp_nodes_knn(self._h, ptr(X), m, k, precision, ptr(idx), ptr(dist)),
                   "sbp_nodes_knn")
             return idx, dist
         X = as_host_f64(X, self.dim)
         m = len(X)
         idx = np.empty((m, k), np.int64)
-        dist = np.empty((m, k), np.float64) if return_dist else None
-        check(_lib.load().sbp_nodes_knn_host(self._h, ptr(X), m, k, 64, ptr(idx), ptr(dist)),
+        dist = np.empty((m, k), np.float64 if precision == 64 else np.float32) if return_dist else None
+        check(_lib.load().sbp_nodes_knn_host(self._h, ptr(X), m, k, precision, ptr(idx), ptr(dist)),
               "sbp_nodes_knn_host")
         return idx, dist
 

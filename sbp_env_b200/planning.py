@@ -33,7 +33,7 @@ def near(tree, X, r, metric="full", closed=False):
 
 
 def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, queries=None,
-                    mark=None, packed_out=None, part=None, want_rows: bool = True):
+                    mark=None, packed_out=None, part=None, want_rows: bool = True, order_out=None):
     """Candidate roadmap edges of every stored node to its k nearest other nodes and
     their visibility, entirely on the device.
 
@@ -55,6 +55,10 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
     :param part: ``(i, parts)``: connect only run i of the ``parts`` contiguous runs of the
         CELL-SORTED row order (spatially compact shards, one per rank; outputs are [n][k] in node
         order with only that run's rows written).  2-D image checker only.
+    :param order_out: int32 CUDA tensor [n]: rows of all outputs in CELL-SORTED order, row p = node
+        ``order_out[p]`` (written by the call); a part's rows are then one contiguous block stored
+        with coalesced lines -- the layout for ``packed_out`` in pinned host memory or behind the
+        multicast mapping (``Roadmap.build_from_packed(..., row_ids=order_out)`` consumes it).
     :param want_rows: ``False`` skips the ``nbr`` / ``vis`` outputs (only ``packed_out`` is written).
     :param mark: optional callable ``mark(name)`` invoked between the phases
         ("knn", "edges", "visible") on the launching stream (bench.py records CUDA
@@ -70,13 +74,16 @@ def prm_connect_knn(cc, tree, k: int, rows=None, return_dist: bool = False, quer
     # library call -- kNN on the cell grid, then the row-ordered visibility kernel
     if fused and queries is None and rows is None and not return_dist and 1 <= k <= 31 \
             and hasattr(cc, "prm_connect") and len(tree) > 0:
-        out = cc.prm_connect(tree, k, part=part or (0, 1), packed_out=packed_out, want_rows=want_rows)
+        out = cc.prm_connect(tree, k, part=part or (0, 1), packed_out=packed_out, want_rows=want_rows,
+                             order_out=order_out)
         if mark:
             for name in ("knn", "edges", "visible"):
                 mark(name)
         return out
     if part is not None and tuple(part) != (0, 1):
         raise ValueError("part= needs the 2-D image checker on a device node store (all rows)")
+    if order_out is not None:
+        raise ValueError("order_out= needs the 2-D image checker on a device node store (all rows)")
     if queries is not None:
         X = queries
         count = X.shape[0]
@@ -232,7 +239,7 @@ class PRMConnectGraph(CapturedStep):
     """
 
     def __init__(self, cc, tree, k: int, rows=None, queries=None, warmup: int = 2, packed_out=None,
-                 after=None, part=None, want_rows: bool = True):
+                 after=None, part=None, want_rows: bool = True, order_out=None):
         """``after``: optional callable run (and captured) right after the connection step, on
         the same stream -- e.g. the barrier of ``PeerAdjacencyGather.complete``."""
         if "visible" in getattr(cc, "__dict__", {}):
@@ -244,7 +251,7 @@ class PRMConnectGraph(CapturedStep):
         def fn():
             before[0] = int(cc.stats.visible_cnt)
             out = prm_connect_knn(cc, tree, self.k, rows=rows, queries=queries, packed_out=packed_out,
-                                  part=part, want_rows=want_rows)
+                                  part=part, want_rows=want_rows, order_out=order_out)
             if after is not None:
                 after()
             return out

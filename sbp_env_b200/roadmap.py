@@ -91,7 +91,9 @@ class Roadmap:
                                               int(bool(undirected))), "sbp_graph_build_knn")
         return self
 
-    def build_from_packed(self, packed, first_row: int = 0, undirected: bool = False):
+    def build_from_packed(self, packed, first_row: int = 0, undirected: bool = False, row_ids=None):
+        """``row_ids`` (int32 [m], CUDA): row r of ``packed`` belongs to node ``row_ids[r]`` -- the
+        cell-sorted rows and ``order_out`` of ``prm_connect_knn(..., order_out=...)``."""
         import torch
 
         self.ctx.use_torch_stream()
@@ -99,6 +101,13 @@ class Roadmap:
         if packed.dim() != 2:
             raise ValueError("packed adjacency must be [m][k]")
         m, k = packed.shape
+        if row_ids is not None:
+            row_ids = self._dev(row_ids, torch.int32)
+            if row_ids.numel() != m:
+                raise ValueError("row_ids must hold one node index per row of packed")
+            check(_lib.load().sbp_graph_build_packed_rows(self._h, ptr(packed), ptr(row_ids), m, k,
+                                                          int(bool(undirected))), "sbp_graph_build_packed_rows")
+            return self
         check(_lib.load().sbp_graph_build_packed(self._h, ptr(packed), m, k, int(first_row),
                                                  int(bool(undirected))), "sbp_graph_build_packed")
         return self
@@ -188,7 +197,7 @@ class Roadmap:
 
 
 def prm_get_solution(cc, tree, roadmap, start_pos, goal_pos, epsilon, dist=euclidean_dist,
-                     max_len: int = 4096, poses=None):
+                     max_len: int = 4096, poses=None, exclude=()):
     """``PRMPlanner.get_solution`` (prmPlanner.py:128-154) on the device roadmap.
 
     start / goal are connected to the roadmap node that ``get_nearest_free`` picks among the
@@ -197,11 +206,15 @@ def prm_get_solution(cc, tree, roadmap, start_pos, goal_pos, epsilon, dist=eucli
     ``engine.dist`` exactly like :145-150 (``solution_path[0].cost = dist(path[0], start) = 0``).
 
     :return: ``(c_max, path)`` -- ``path`` the node indices from the start's roadmap node to
-        the goal's; ``(inf, None)`` when either end cannot be connected or no path exists."""
+            the goal's; ``(inf, None)`` when either end cannot be connected or no path exists.
+
+    ``exclude``: node indices ``get_nearest_free`` skips by identity (:113: ``n is start_pt or n is
+    goal_pt``) -- in a reference run node 0 *is* ``env.start_pt`` (rrtPlanner.py init), so a
+    drop-in caller passes ``exclude=(0,)``."""
     from .planner_ops import prm_nearest_free
 
-    s = prm_nearest_free(cc, tree, start_pos, epsilon, dist=dist, poses=poses)
-    g = prm_nearest_free(cc, tree, goal_pos, epsilon, dist=dist, poses=poses)
+    s = prm_nearest_free(cc, tree, start_pos, epsilon, exclude=exclude, dist=dist, poses=poses)
+    g = prm_nearest_free(cc, tree, goal_pos, epsilon, exclude=exclude, dist=dist, poses=poses)
     if s is None or g is None:
         return float("inf"), None
     hops, paths = roadmap.shortest_paths(np.array([s]), np.array([g]), max_len=max_len)

@@ -779,3 +779,31 @@ def test_nearest_is_np_argmin_also_on_nan(sg):
         # kNN keeps the argsort rule (NaN last)
         ki, _ = t2.knn(X[:5], 1)
         assert (ki[:, 0] != 1234).all()
+
+
+def test_knn_precision_32_same_rows_fp32_distances(sg):
+    """BASELINE.json north_star: "distances must agree within 1e-6 relative in fp32 (exact in fp64)".
+    precision=32 returns the rows of the exact selection (index sets bit-exact, ties included) with
+    float32 distances: the fp64 distance rounded once."""
+    import torch
+
+    rng = np.random.default_rng(32)
+    for d, n, m, k in ((2, 30000, 5000, 10), (2, 1500, 40, 20), (4, 8000, 600, 11), (3, 4000, 3, 1)):
+        P = rng.random((n, d)) * 30000
+        P[: n // 10] = np.floor(P[: n // 10])                     # lattice points: exact ties
+        X = rng.random((m, d)) * 30000
+        X[: m // 4] = np.floor(X[: m // 4])
+        tree = sg.NodeStore(d)
+        tree.extend(P)
+        oi, od = orc.knn(P, X, k)
+        gi, g32 = tree.knn(X, k, precision=32)
+        assert g32.dtype == np.float32
+        assert np.array_equal(gi, oi)
+        assert np.array_equal(g32, od.astype(np.float32))
+        assert (np.abs(g32.astype(np.float64) - od) <= 1e-6 * od).all()
+        di, d32 = tree.knn(torch.from_numpy(X).cuda(), k, precision=32)
+        assert d32.dtype == torch.float32
+        assert np.array_equal(di.cpu().numpy(), oi) and np.array_equal(d32.cpu().numpy(), g32)
+    empty = sg.NodeStore(2)
+    ei, ed = empty.knn(np.zeros((3, 2)), 2, precision=32)
+    assert (ei == -1).all() and np.isinf(ed).all() and ed.dtype == np.float32

@@ -151,7 +151,8 @@ def test_prm_build_graph_replay(sg):
     pa, pb = canon[g["prm_pairs"][:, 0]], canon[g["prm_pairs"][:, 1]]
     hops = np.asarray(road.shortest_paths(pa.copy(), pb.copy()))
     assert hops.tolist() == g["prm_pair_hops"].tolist()
+    # node 0 is env.start_pt itself, which get_nearest_free skips by identity (prmPlanner.py:113)
     c_max, path = sg.prm_get_solution(cc, tree, road, g["prm_query"][0], g["prm_query"][1], float(g["prm_eps"]),
-                                      poses=poses)
+                                      poses=poses, exclude=(0,))
     assert c_max == float(g["prm_c_max"])
     assert (path is None) == (int(g["prm_start_goal"][0]) < 0 or int(g["prm_hops"]) < 0)

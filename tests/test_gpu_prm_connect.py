@@ -174,3 +174,105 @@ def test_cfg5_reduced_scale_equals_oracle(sg):
     P = np.random.default_rng(0).random((200000, 2)) * [mz.W, mz.H]
     assert np.array_equal(cc.feasible_batch(P), mz.free_points(P))
     assert np.array_equal(om.feasible2d(P), mz.free_points(P))
+
+
+def test_cell_sorted_rows_and_order(sg):
+    """sbp_prm_connect2d_sorted: the same rows in cell-sorted order (row p = node order[p]), whole and
+    in parts (a part = one contiguous block of rows), into device and pinned host memory; the
+    roadmap built from them equals the one built from the node-order rows."""
+    import torch
+
+    free = load_map("intel_lab")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("intel_lab"))
+    rng = np.random.default_rng(17)
+    n, k = 25013, 10
+    nodes = rng.random((n, 2)) * [W, H]
+    nodes[:300] = np.floor(nodes[:300])
+    tree = sg.NodeStore(2)
+    tree.extend(nodes)
+    nbr, vis = sg.prm_connect_knn(cc, tree, k)
+    want = sg.distributed.pack_adjacency(nbr, vis)
+    order = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    packed = torch.full((n, k), SENT, dtype=torch.int32, device="cuda")
+    n2, v2 = sg.prm_connect_knn(cc, tree, k, packed_out=packed, order_out=order)
+    o = order.long()
+    assert torch.equal(torch.sort(o).values, torch.arange(n, device="cuda"))     # a permutation
+    assert torch.equal(packed, want[o]) and torch.equal(n2, nbr[o]) and torch.equal(v2, vis[o])
+    # cell-sorted: consecutive rows are spatial neighbours
+    P = torch.from_numpy(nodes).cuda()[o]
+    assert float((P[1:] - P[:-1]).norm(dim=1).median()) < 12.0
+    # parts: contiguous blocks, straight into pinned host memory (coalesced zero-copy stores)
+    host = torch.full((n, k), SENT, dtype=torch.int32).pin_memory()
+    parts = 3
+    for i in range(parts):
+        order2 = torch.empty_like(order)
+        sg.prm_connect_knn(cc, tree, k, part=(i, parts), packed_out=(host.data_ptr(), False), want_rows=False,
+                           order_out=order2)
+        torch.cuda.synchronize()
+        assert torch.equal(order2, order)                                         # deterministic permutation
+        lo, cnt = sg.distributed.shard_range(n, i, parts)
+        assert torch.equal(host[lo:lo + cnt], want[o][lo:lo + cnt].cpu())
+        assert bool((host[lo + cnt:] == SENT).all())
+    # roadmap from the sorted rows == roadmap from the node-order rows
+    for und in (False, True):
+        a = sg.Roadmap(n).build_from_packed(want, undirected=und)
+        b = sg.Roadmap(n).build_from_packed(packed, undirected=und, row_ids=order)
+        assert a.n_edges == b.n_edges
+        ra, ca = a.csr()
+        rb, cb = b.csr()
+        assert torch.equal(ra, rb)
+        ea, eb = a.edges(), b.edges()
+        assert np.array_equal(np.asarray(ea), np.asarray(eb))
+
+
+def test_rows_the_fused_kernel_leaves_to_the_exact_path(sg):
+    """Near ties (distinct d^2 whose roots round to one value: the lower index must win although its
+    d^2 is larger), non-finite stores, isolated nodes whose rectangle exceeds the limit: rows the
+    fused kernel does not settle come out of the exact pipeline, identical to the oracle."""
+    free = load_map("room1")
+    W, H = free.shape
+    cc = sg.ImgCollisionChecker(map_png("room1"))
+    om = orc.Map(free)
+    rng = np.random.default_rng(23)
+    n, k = 6000, 4
+    nodes = rng.random((n, 2)) * [W, H]
+    # 400 triples c, c + (6e-8, 5), c + (0, 5): d^2 = 25 + 1 ulp and 25, both roots round to 5.0, and
+    # the node with the larger d^2 has the lower index
+    c = np.floor(rng.random((400, 2)) * [W - 20, H - 20]) + 5
+    nodes[0:400] = c
+    nodes[400:800] = c + [6e-8, 5.0]
+    nodes[800:1200] = c + [0.0, 5.0]
+    d2a = ((nodes[400:800] - c) ** 2).sum(1)
+    d2b = ((nodes[800:1200] - c) ** 2).sum(1)
+    assert (d2a > d2b).any() and (np.sqrt(d2a) == np.sqrt(d2b)).all()
+    tree = sg.NodeStore(2)
+    tree.extend(nodes)
+    want_nbr, want_vis = oracle_connect(om, nodes, k)
+    nbr, vis = sg.prm_connect_knn(cc, tree, k)
+    assert np.array_equal(nbr.cpu().numpy(), want_nbr)
+    assert np.array_equal(vis.cpu().numpy(), want_vis)
+    # sparse pocket: a dense cloud plus a few far-away nodes (their rectangles hold the whole cloud)
+    nodes2 = rng.random((n, 2)) * [60, 60] + [100, 100]
+    nodes2[:6] = [[5, 5], [W - 5, 5], [5, H - 5], [W - 5, H - 5], [W / 2, 5], [5, H / 2]]
+    t2 = sg.NodeStore(2)
+    t2.extend(nodes2)
+    want_nbr, want_vis = oracle_connect(om, nodes2, k)
+    nbr, vis = sg.prm_connect_knn(cc, t2, k)
+    assert np.array_equal(nbr.cpu().numpy(), want_nbr)
+    assert np.array_equal(vis.cpu().numpy(), want_vis)
+    # a non-finite coordinate in the store: every row takes the exact path (NaN distances rank last)
+    nodes3 = nodes.copy()
+    nodes3[1234, 0] = np.nan
+    nodes3[77, 1] = np.inf
+    t3 = sg.NodeStore(2)
+    t3.extend(nodes3)
+    with np.errstate(invalid="ignore"):
+        want_nbr, _ = oracle_connect(om, nodes3, k)
+    nbr, vis = sg.prm_connect_knn(cc, t3, k)
+    assert np.array_equal(nbr.cpu().numpy(), want_nbr)
+    fin = np.isfinite(nodes3).all(1)
+    rows_fin = fin & fin[np.where(want_nbr >= 0, want_nbr, 0)].all(1)
+    wv = om.visible2d(nodes3[np.where(want_nbr >= 0, want_nbr, 0)[rows_fin].reshape(-1)],
+                      np.repeat(nodes3[rows_fin], k, 0)).reshape(-1, k)
+    assert np.array_equal(vis.cpu().numpy()[rows_fin], wv)

@@ -1,0 +1,49 @@
+"""cfg5 PRM connection (1M nodes on the 32k^2 maze, k = 10): time of the captured step for a few
+settings of the cell-grid knobs (first ring radius, nodes per cell).  Run under gpurun.
+
+    python tools/prm_sweep.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tools")):
+    sys.path.insert(0, p)
+import sbp_env_b200 as sg  # noqa: E402
+import workloads  # noqa: E402
+
+dev = torch.device("cuda", 0)
+mz, cc, tree, nodes, S, T = workloads.cfg5_on_device(dev)
+n, k = len(tree), 10
+ctx = tree.ctx
+packed = torch.empty((n, k), dtype=torch.int32, device=dev)
+order = torch.empty((n,), dtype=torch.int32, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ref = None
+for dens in (100, 150, 200, 300):
+    for rinit in (0, 1, 2):
+        ctx.tune("knn_cell_density", dens)
+        ctx.tune("knn_cells_rinit", rinit)
+        g = sg.PRMConnectGraph(cc, tree, k, packed_out=packed, want_rows=False, order_out=order)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(8):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            g.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        node = torch.empty_like(packed)
+        node[order.long()] = packed
+        if ref is None:
+            ref = node.clone()
+        same = bool(torch.equal(ref, node))
+        ts.sort()
+        print(f"density {dens / 100:.2f} rinit {rinit}: {ts[len(ts) // 2]:.4f} ms (min {ts[0]:.4f}) same={same}", flush=True)
+        del g
