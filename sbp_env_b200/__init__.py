@@ -12,7 +12,7 @@ from .node_store import NodeStore  # noqa: F401
 from .planning import (CapturedStep, PRMConnectGraph, connect_to_roadmap, feasible_batch,  # noqa: F401
                        knn, near, prm_connect_knn, prm_connect_radius, roadmap_edges_to_host,
                        visible_batch)
-from . import distributed, planner_hooks, planner_ops, samplers  # noqa: F401
+from . import distributed, planner_hooks, planner_ops, runtime, samplers  # noqa: F401
 from .roadmap import Roadmap, prm_get_solution  # noqa: F401
 from .stats import Stats  # noqa: F401
 

@@ -532,7 +532,7 @@ extern "C" int32_t sbp_ctx_tune(sbp_ctx *ctx, const char *key, int64_t value) {
     sbp_tuning &t = ctx->tune;
     struct { const char *name; int *slot; } table[] = {
         {"visible_group", &t.visible_group}, {"coop_below", &t.coop_below},
-        {"force_global", &t.force_global}, {"arm_group", &t.arm_group},
+        {"force_global", &t.force_global}, {"visible_tiles", &t.visible_tiles}, {"arm_group", &t.arm_group},
         {"near_filter", &t.near_filter}, {"knn_seed", &t.knn_seed}, {"knn_chunks", &t.knn_chunks},
         {"knn_prefilter", &t.knn_prefilter}, {"knn_filter", &t.knn_filter},
         {"knn_filter_chunks", &t.knn_filter_chunks}, {"knn_filter_variant", &t.knn_filter_variant},
@@ -569,6 +569,32 @@ static int32_t launch_visible(sbp_map *map, const double *P, const double *Q, in
     return SBP_OK;
 }
 
+// Maps that are read from L2 / HBM (too large for shared memory): one thread per edge, two-level
+// walk on the tile codes (device_fns.cuh:edge_free_tiles) -- an 8-pixel chunk of the line costs one
+// or two cached 2-bit lookups instead of 8 pixel tests on a 128 MiB array.  Same booleans as the
+// pixel walk for every map (the codes only summarise tiles that are uniformly free / blocked).
+__global__ void __launch_bounds__(256)
+k_visible2d_tiles(MapView mv, const uint32_t *__restrict__ af, int AW, const double2 *__restrict__ P,
+                  const double2 *__restrict__ Q, int64_t n, uint8_t *__restrict__ out, int32_t *__restrict__ flags) {
+    int myflag = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 p = P[i], q = Q[i];
+        const Edge2D ed = make_edge(p.x, p.y, q.x, q.y, mv.W, mv.H);
+        myflag |= ed.flag;
+        bool r = false;
+        if (ed.walk) {
+            if (ed.x1 >= 0 && ed.y1 >= 0 && ed.x2 >= 0 && ed.y2 >= 0)
+                r = edge_free_tiles(mv.words, mv.SX, af, AW, ed.a1, ed.b1, ed.da, ed.adb, ed.ystep, ed.steep);
+            else {                                       // negative coordinates: numpy wrap-around
+                int f2 = 0;
+                r = edge_visible_seq<false>(mv.words, mv, p.x, p.y, q.x, q.y, f2);
+            }
+        }
+        out[i] = r ? 1 : 0;
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
 extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q, int64_t n,
                                  uint8_t *out, int32_t *flags, uint64_t *px_tested) {
     SBP_NVTX("sbp_visible2d");
@@ -580,6 +606,18 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
     bool smem = !ctx->tune.force_global && map->smem_resident &&
                 n * 32 >= map->packed_bytes * (int64_t)ctx->sm_count / 4;
     unsigned long long *px = (unsigned long long *)px_tested;
+    if (!map->smem_resident && ctx->tune.visible_tiles && ctx->tune.visible_group == 0 && !px) {
+        int32_t rc = sbp_map_ensure_allfree(map);
+        if (rc) return rc;
+        int64_t need = (n + 255) / 256;
+        const int grid = (int)(need < (int64_t)ctx->sm_count * 32 ? need : (int64_t)ctx->sm_count * 32);
+        KernelTimer timer(ctx, 3);
+        k_visible2d_tiles<<<grid, 256, 0, ctx->stream>>>(map->view, map->af.words, map->af.AW, (const double2 *)P,
+                                                         (const double2 *)Q, n, out, flags);
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
     if (ctx->tune.visible_group == 0) {
         LaunchCfg c;
         if (smem) {                 // shared-memory resident: the row-major copy (cheaper index)

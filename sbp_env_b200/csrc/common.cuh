@@ -84,6 +84,7 @@ struct sbp_tuning {
     int visible_group = 0;        // 0 = adaptive kernel; 4/8/16/32 = lane-group kernel of that width
     int coop_below = 12;          // adaptive kernel: cap of the hand-over threshold (walkers)
     int force_global = 0;         // 1 = never stage the map in shared memory
+    int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
     int arm_group = 0;            // lanes per arm edge (0 = default 8)
     int near_filter = 1;          // filtered scan of the batched radius query
     int knn_seed = 1;             // grid-seeded a-priori bounds

@@ -151,21 +151,43 @@ def test_device_pointer_path_and_counter(sg):
 
 
 def test_synthetic_large_grid_l2_path(sg):
-    """A 4096^2 blocky-noise grid (SURVEY.md 8(d) style): too big for shared memory, so
-    the L2 / global path is exercised; built on the device, checked against the oracle."""
+    """A 4096^2 grid (SURVEY.md 8(d) style blocky noise, plus a region of per-pixel noise and thin
+    diagonal walls so that many 8x8 tiles are MIXED): too big for shared memory, so the L2 / global
+    paths are exercised -- the two-level walk on the tile codes (default) and the pixel walk --
+    built on the device, checked against the oracle, adversarial endpoints included."""
     import torch
 
     rng = np.random.default_rng(4096)
     coarse = rng.random((64, 64)) < 0.75
     free = np.kron(coarse, np.ones((64, 64), bool))
+    free[1024:1536, 2048:2560] &= rng.random((512, 512)) < 0.97          # per-pixel noise
+    i = np.arange(1500)
+    free[2000 + i, 500 + i // 2] = False                                  # thin diagonal walls
+    free[300 + i // 3, 1000 + i] = False
     W, H = free.shape
     cc = sg.ImgCollisionChecker.from_free_mask(torch.from_numpy(free.astype(np.uint8)).cuda())
     assert not cc.device_map.info()["smem_resident"]
     om = orc.Map(free)
-    n = 200_000
+    n = 300_000
     P, Q = rng.random((n, 2)) * [W, H], rng.random((n, 2)) * [W, H]
     Q[: n // 2] = P[: n // 2] + rng.standard_normal((n // 2, 2)) * 40
-    assert np.array_equal(cc.visible_batch(P, Q), om.visible2d(P, Q))
+    P[n // 2: n // 2 + 40000] = rng.random((40000, 2)) * 512 + [1024, 2048]     # inside the noisy region
+    Q[n // 2: n // 2 + 40000] = P[n // 2: n // 2 + 40000] + rng.standard_normal((40000, 2)) * 12
+    P[-20000:] = (rng.random((20000, 2)) * 2.4 - 1.2) * [W, H]            # wrap-around / out of range
+    Q[-10000:] = (rng.random((10000, 2)) * 2.4 - 1.2) * [W, H]
+    P[-30000:-20000] = np.floor(P[-30000:-20000])                         # integer endpoints
+    Q[-30000:-25000] = P[-30000:-25000]                                   # zero-length edges
+    want = om.visible2d(P, Q)
+    assert 0.02 < want.mean() < 0.9
+    try:
+        for tiles in (1, 0):
+            sg.runtime.tune("visible_tiles", tiles)
+            assert np.array_equal(cc.visible_batch(P, Q), want), tiles
+            dP, dQ = torch.from_numpy(P).cuda(), torch.from_numpy(Q).cuda()
+            assert np.array_equal(cc.visible_batch(dP, dQ).cpu().numpy(), want), tiles
+    finally:
+        sg.runtime.tune("visible_tiles", 1)
+    assert np.array_equal(cc.visible_batch(Q, P), want)                   # direction symmetry
     assert np.array_equal(cc.feasible_batch(P), om.feasible2d(P))
 
 
