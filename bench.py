@@ -191,9 +191,15 @@ def run_ours(args):
     peer_step = [0]
     part = (rank, world)
 
+    order_local = order                               # this rank's slice (N > 1) / the whole permutation (N = 1)
+    order_full = {"o": order}
+
     def nccl_merge():
         merged = packed_local.clone()
         dist.all_reduce(merged, op=dist.ReduceOp.MAX)  # every row is written by exactly one rank
+        om = order_local.clone()
+        dist.all_reduce(om, op=dist.ReduceOp.MAX)
+        order_full["o"] = om
         return merged
 
     def eager_step(mark=None):
@@ -201,11 +207,14 @@ def run_ours(args):
             h = peer_step[0] & 1
             peer_step[0] += 1
             sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=peer.target(h), want_rows=False,
-                               order_out=order)
+                               order_out=peer.order_target(h))
             packed_full["p"] = peer.complete(h)
+            order_full["o"] = peer.order_view(h)
         else:
+            if world > 1:
+                order_local.fill_(-1)
             sg.prm_connect_knn(cc, tree, k, part=part, mark=mark, packed_out=packed_local, want_rows=False,
-                               order_out=order)
+                               order_out=order_local)
             packed_full["p"] = packed_local if world == 1 else nccl_merge()
         if mark:
             mark("exchange")
@@ -216,7 +225,8 @@ def run_ours(args):
     if fused:
         try:
             gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False,
-                                         order_out=order, after=(lambda h=h: peer.complete(h))) for h in (0, 1)]
+                                         order_out=peer.order_target(h), after=(lambda h=h: peer.complete(h)))
+                      for h in (0, 1)]
             barrier_in_graph = True
         except Exception as e:      # noqa: BLE001
             print(f"[bench] barrier not capturable ({type(e).__name__}: {e}); eager barrier", file=sys.stderr)
@@ -225,11 +235,12 @@ def run_ours(args):
         barrier_in_graph = bool(ok.item())
         if not barrier_in_graph:
             gsteps = [sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=peer.target(h), want_rows=False,
-                                         order_out=order) for h in (0, 1)]
+                                         order_out=peer.order_target(h)) for h in (0, 1)]
         exchange += " (captured in the step's graph)" if barrier_in_graph else " (separate launch)"
         dist.barrier()
     else:
-        gstep = sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=packed_local, want_rows=False, order_out=order)
+        gstep = sg.PRMConnectGraph(cc, tree, k, part=part, packed_out=packed_local, want_rows=False,
+                                   order_out=order_local)
 
     def step():
         if fused:
@@ -237,6 +248,7 @@ def run_ours(args):
             peer_step[0] += 1
             gsteps[h].replay()
             packed_full["p"] = peer.view(h) if barrier_in_graph else peer.complete(h)
+            order_full["o"] = peer.order_view(h)
         else:
             gstep.replay()
             packed_full["p"] = packed_local if world == 1 else nccl_merge()
@@ -333,32 +345,40 @@ def run_ours(args):
     full = packed_full["p"]
     assert tuple(full.shape) == (n, k)
     assert torch.equal(replayed, full), "graph replay differs from the eager step"
+    order = order_full["o"].clone()                   # the whole permutation, as assembled by the step
+    assert torch.equal(torch.sort(order.long()).values, torch.arange(n, device=dev)), "row order is not a permutation"
     # this rank's own rows, computed into a private sentinel buffer: exactly its block of positions
     own = torch.full((n, k), SENTINEL, dtype=torch.int32, device=dev)
-    order2 = torch.empty_like(order)
+    order2 = torch.full((n,), -1, dtype=torch.int32, device=dev)
     sg.prm_connect_knn(cc, tree, k, part=part, packed_out=own, want_rows=False, order_out=order2)
-    assert torch.equal(order2, order) and torch.equal(torch.sort(order.long()).values, torch.arange(n, device=dev))
+    assert torch.equal(order2[first:first + count], order[first:first + count])
+    if world > 1:
+        assert bool((order2[:first] == -1).all()) and bool((order2[first + count:] == -1).all())
     mine_rows = own[:, 0] != SENTINEL
     assert int(mine_rows.sum().item()) == count and bool(mine_rows[first:first + count].all()), \
         "this rank did not write exactly its block of the rows"
     assert torch.equal(own[mine_rows], full[mine_rows]), "assembled adjacency differs from the local rows"
     adjacency_check = "single rank"
     if world > 1:
-        # the WHOLE assembled adjacency against an NCCL merge of the ranks' rows, on every rank; the
-        # permutation must be the same on every rank
+        # the WHOLE assembled adjacency and permutation against an NCCL merge of the ranks' rows, on
+        # every rank; and against the single-rank build of the whole roadmap on rank 0's device
         want = own.clone()
         dist.all_reduce(want, op=dist.ReduceOp.MAX)
+        owant = order2.clone()
+        dist.all_reduce(owant, op=dist.ReduceOp.MAX)
         owners = mine_rows.to(torch.int32)
         dist.all_reduce(owners)
-        omax, omin = order.clone(), order.clone()
-        dist.all_reduce(omax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(omin, op=dist.ReduceOp.MIN)
+        whole = torch.empty_like(own)
+        owhole = torch.empty_like(order2)
+        sg.prm_connect_knn(cc, tree, k, packed_out=whole, want_rows=False, order_out=owhole)
         same = torch.tensor([1 if (torch.equal(want, full) and bool((owners == 1).all().item())
-                                   and torch.equal(omax, omin)) else 0], device=dev)
+                                   and torch.equal(owant, order) and torch.equal(whole, full)
+                                   and torch.equal(owhole, order)) else 0], device=dev)
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         assert bool(same.item()), "adjacency assembled through peer memory differs from the NCCL merge"
-        adjacency_check = (f"every row written by exactly one rank; equal to the NCCL merge of the {world} ranks' "
-                           "rows on every rank; same row permutation on every rank")
+        adjacency_check = (f"every row written by exactly one rank; rows and permutation equal to the NCCL merge of the "
+                           f"{world} ranks' blocks and to the single-rank build, on every rank")
+        del whole, owhole, want, owant
     # node-order view of the adjacency for the checks below
     full_node = torch.empty_like(full)
     full_node[order.long()] = full
@@ -401,7 +421,7 @@ def run_ours(args):
                 e.record()
                 q_ev[name] = e
         mk("start")
-        road.build_from_packed(packed_full["p"], undirected=True, row_ids=order)
+        road.build_from_packed(packed_full["p"], undirected=True, row_ids=order_full["o"])
         mk("csr")
         ends = sg.connect_to_roadmap(cc, tree, SG_mine, K_CONNECT)
         mk("connect")
@@ -464,7 +484,7 @@ def run_ours(args):
                            packed_out=code_dev if d2h_copy else (code_h.data_ptr(), False))
         if d2h_copy:
             code_h[first:first + count].copy_(code_dev[first:first + count], non_blocking=True)
-        order_h.copy_(order_e, non_blocking=True)
+        order_h[first:first + count].copy_(order_e[first:first + count], non_blocking=True)
 
     e2e_graph = sg.CapturedStep(e2e_body, device=local)
     for _ in range(max(3, args.warmup)):
@@ -473,7 +493,8 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
     e2e_ms = timed_loop(e2e_graph.replay, args.steps)
-    assert torch.equal(order_h, order.cpu()), "e2e row permutation differs from the device-resident run"
+    assert torch.equal(order_h[first:first + count], order[first:first + count].cpu()), \
+        "e2e row permutation differs from the device-resident run"
     assert torch.equal(code_h[first:first + count], full[first:first + count].cpu()) and \
         bool((code_h[:first] == SENTINEL).all()) and bool((code_h[first + count:] == SENTINEL).all()), \
         "e2e result differs from the device-resident run"
@@ -555,9 +576,9 @@ def run_ours(args):
         "e2e": {"value": edges_total * args.steps / (e2e_ms / 1e3), "unit": UNIT,
                 "ms_per_step": e2e_ms / args.steps,
                 "h2d_bytes_per_step": int(pinned.numel() * 8),
-                "d2h_bytes_per_step": int(count * k * 4 + n * 4),
+                "d2h_bytes_per_step": int(count * k * 4 + count * 4),
                 "result": "packed adjacency int32 [rows of this rank, cell-sorted][k] = (neighbour + 1) * 2 + visible, "
-                          "and the row permutation int32 [n]",
+                          "and their node indices int32 [rows of this rank]",
                 "d2h": "copy from a device buffer" if d2h_copy else
                        "stored by the walk kernel straight into the pinned host buffer (coalesced zero-copy) + one copy of the permutation",
                 "h2d": "copy into a device buffer" if h2d_copy else

@@ -288,7 +288,11 @@ int32_t sbp_prm_connect2d(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t par
  * sort, ascending node index inside a cell -- a function of the poses only, so every rank computes
  * the same one).  The rows of part i are then ONE contiguous block [p0, p0 + count) x k that the
  * kernel stores with coalesced 128-byte lines: the form to use when `packed` is pinned host memory
- * or the NVSwitch multicast mapping.  sbp_graph_build_packed_rows consumes it. */
+ * or the NVSwitch multicast mapping.  sbp_graph_build_packed_rows consumes it.
+ * parts > 1: a rank builds the cell grid for the band of cell rows its part needs only (the part
+ * of the build that shrinks with the number of ranks), so only order_out[p0, p0 + count) is written,
+ * like the rows; with packed_multicast != 0 order_out is the multicast address of the ranks'
+ * symmetric order buffer as well, and every rank ends up with the whole permutation. */
 int32_t sbp_prm_connect2d_sorted(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t part, int32_t parts,
                                  int64_t *nbr_out, uint8_t *vis, int32_t *packed,
                                  int32_t packed_multicast, int32_t *order_out, int32_t *flags);

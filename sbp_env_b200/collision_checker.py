@@ -350,7 +350,10 @@ class ImgCollisionChecker(_GridChecker):
         ``order_out``: int32 CUDA tensor [n]; when given the rows of every output are in
         CELL-SORTED order -- row p belongs to node ``order_out[p]`` (written by the call) -- and the
         rows of a part are one contiguous, coalesced block (``sbp_prm_connect2d_sorted``): the form
-        for pinned host memory and the multicast mapping.
+        for pinned host memory and the multicast mapping.  With several parts only the part's own
+        slice ``order_out[p0 : p0 + count]`` is written (a rank builds the grid for its band of cell
+        rows only); with a multicast ``packed_out`` pass the multicast ADDRESS of the order buffer
+        (``PeerAdjacencyBuffer.order_target``).
         Returns ``(nbr int64 [n][k], vis bool [n][k])`` CUDA tensors, or ``None`` with
         ``want_rows=False`` (only the packed adjacency is written)."""
         import torch
@@ -377,11 +380,17 @@ class ImgCollisionChecker(_GridChecker):
         base, rem = divmod(n, parts)
         self.stats.visible_cnt += (base + (1 if i < rem else 0)) * k
         if order_out is not None:
-            if order_out.dtype != torch.int32 or order_out.numel() != n or not order_out.is_contiguous() \
-                    or order_out.device != dev:
-                raise ValueError("order_out must be a contiguous CUDA int32 tensor [n]")
+            if isinstance(order_out, int):               # raw address (the multicast mapping, with packed_out)
+                o_ptr = C.c_void_p(order_out)
+            else:
+                if order_out.dtype != torch.int32 or order_out.numel() != n or not order_out.is_contiguous() \
+                        or order_out.device != dev:
+                    raise ValueError("order_out must be a contiguous CUDA int32 tensor [n]")
+                if p_mc:
+                    raise ValueError("with a multicast packed_out, order_out must be a multicast address too")
+                o_ptr = ptr(order_out)
             check(_lib.load().sbp_prm_connect2d_sorted(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),
-                                                       p_ptr, p_mc, ptr(order_out), ptr(flags)),
+                                                       p_ptr, p_mc, o_ptr, ptr(flags)),
                   "sbp_prm_connect2d_sorted")
         else:
             check(_lib.load().sbp_prm_connect2d(m.handle, tree._h, int(k), i, parts, ptr(nbr), ptr(vis),

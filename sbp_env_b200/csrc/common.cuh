@@ -75,7 +75,7 @@ struct SbpNvtxRange {
 // and the fused query; 5,6 cell grid and seeds; 7 append / read staging; 8,9 kNN filter lists;
 // 10,11 filter shadow / done flags; 12,13 sbp_prm_connect2d (row poses, kNN rows); 14 cell-sorted
 // poses; 15 row positions of sbp_graph_build_packed_rows; 16 candidate positions of the fused PRM kernels;
-// 17 fp64 distances of a precision-32 kNN call
+// 17 fp64 distances of a precision-32 kNN call; 18 per-block partials of the cooperative grid build
 #define SBP_SCRATCH_SLOTS 20
 // Tuning / instrumentation knobs (sbp_ctx_tune): per context, so that two contexts -- or two
 // threads driving different contexts -- never see each other's settings.  None of them changes
@@ -154,6 +154,7 @@ struct KnnRowsPart {
     int deterministic = 0;           // order the ids inside every cell (all ranks see the same ids)
     const int32_t *ids = nullptr;    // out
     PrmFusedArgs *fused = nullptr;   // in: answer the rows with prm.cu's fused kNN + visibility kernel
+    int banded = 0;                  // in (fused): build the grid only for the band of cell rows the part needs
     int fused_ran = 0;               // out: that kernel was launched (ids are then sorted inside every cell)
     const uint8_t *done = nullptr;   // out (fused_ran): per node, 1 = row settled by the fused kernel
     const int32_t *pending = nullptr;  // out (fused_ran): device counter of the rows it left
@@ -168,6 +169,7 @@ struct CellGridView {
     const double2 *pts;              // [n] their poses
     int64_t n;
     const double *maxabs;            // device scalar: max |coordinate| in the store (inf = non-finite)
+    const int32_t *band;             // device [2]: first / last row of cells that ids / pts cover (NULL: all)
 };
 int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int k, int r_init, int limit,
                              int64_t p0, int64_t count, double *seed2, uint8_t *done, int32_t *pending,

@@ -16,11 +16,14 @@
 // The hot loop compares d^2 against round-up(d_k * d_k): sqrt_rn is monotone, so
 // a candidate with d^2 >= that bound cannot have sqrt < d_k; only candidates
 // below it take the slow path that computes the square root.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
 #include "device_fns.cuh"
 #include "filter.cuh"
+
+namespace cg = cooperative_groups;
 
 #define WIDE_TPB 256
 
@@ -171,12 +174,17 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
     // as the fallback of the filter path: only the flagged blocks of 32 queries (TPB == 32);
     // pending == 0: the cell-grid kernel answered every query, nothing can be flagged
     if (pending && *pending == 0) return;
-    if (redo && !redo[blockIdx.x]) return;
     constexpr int TILE = TPB * 8;     // nodes staged in shared memory per step
     __shared__ double tile[D][TILE];  // fp64 tile, or the fp32 tile in the same storage
     float(*tile32)[TILE] = reinterpret_cast<float(*)[TILE]>(&tile[0][0]);
-    const int64_t q = (int64_t)blockIdx.x * TPB + threadIdx.x;
-    const int s = blockIdx.y;
+    // the grid is capped (a launch that finds nothing pending must cost next to nothing): a CTA
+    // loops over the (query tile, node chunk) pairs bid = s * nbx + bx
+    const int64_t nbx = (m + TPB - 1) / TPB;
+    for (int64_t bid = blockIdx.x; bid < nbx * S; bid += gridDim.x) {
+    const int64_t bx = bid % nbx;
+    if (redo && !redo[bx]) continue;
+    const int64_t q = bx * TPB + threadIdx.x;
+    const int s = (int)(bid / nbx);
     const int64_t chunk = (n + S - 1) / S;
     const int64_t c0 = (int64_t)s * chunk;
     const int64_t c1 = c0 + chunk < n ? c0 + chunk : n;
@@ -283,6 +291,7 @@ k_knn_batched(const double *__restrict__ soa, const float *__restrict__ soa32,
 #pragma unroll
         for (int t = 0; t < K; ++t) { pd[base + t] = top.d[t]; pi[base + t] = top.i[t]; }
     }
+    }
 }
 
 // --------------------------------------- K4a': seeded filter + exact refine ---
@@ -350,9 +359,11 @@ k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
              const uint8_t *__restrict__ done, const int32_t *__restrict__ pending) {
     if (pending && *pending == 0) return;
     const unsigned FULL = 0xffffffffu;
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // (capped grid: a CTA loops over its blocks of 64 queries)
+    for (int64_t q0 = (int64_t)blockIdx.x * blockDim.x; q0 < m; q0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t q = q0 + threadIdx.x;
     bool live = q < m && !(done && done[q]);                     // done: row already written
-    if (!__any_sync(FULL, live)) return;
+    if (!__any_sync(FULL, live)) continue;
     if (live) {
         bool over = false;
         for (int s = 0; s < S; ++s) over |= ccount[q * S + s] > C;
@@ -398,7 +409,7 @@ k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
             }
         }
     }
-    if (!live) return;
+    if (!live) continue;
 #pragma unroll
     for (int t = 0; t < K; ++t)
         if (t < k) {
@@ -410,6 +421,7 @@ k_knn_refine(const double *__restrict__ soa, int64_t capacity, int64_t n,
     for (int t = 0; t < K; ++t) have += (t < k && top.i[t] >= 0) ? 1 : 0;
     if (have < k)
         pad_nan_row(soa, capacity, n, D, X + q * D, k, idx + q * k, dist ? dist + q * k : nullptr);
+    }
 }
 
 // ------------------------------------------------- K4b: wide, CTA/(q,chunk) ---
@@ -616,12 +628,12 @@ __global__ void k_knn_merge(const double *__restrict__ pd, const int32_t *__rest
                             const double *__restrict__ soa, int64_t capacity, int64_t n, int d,
                             const double *__restrict__ X, const int32_t *__restrict__ pending = nullptr) {
     if (pending && *pending == 0) return;
-    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= m) return;
-    if (redo && !redo[q >> 5]) return;
-    knn_merge_row(pd, pi, q, S, K, k, idx, dist);
-    if (idx[q * k + k - 1] < 0)
-        pad_nan_row(soa, capacity, n, d, X + q * d, k, idx + q * k, dist ? dist + q * k : nullptr);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < m; q += (int64_t)gridDim.x * blockDim.x) {
+        if (redo && !redo[q >> 5]) continue;
+        knn_merge_row(pd, pi, q, S, K, k, idx, dist);
+        if (idx[q * k + k - 1] < 0)
+            pad_nan_row(soa, capacity, n, d, X + q * d, k, idx + q * k, dist ? dist + q * k : nullptr);
+    }
 }
 
 // ---------------------------------------------------- kNN seeding (d = 2) ----
@@ -819,13 +831,63 @@ k_cell_scan_fused(const int32_t *__restrict__ cells, int64_t L, int32_t *__restr
     if (i0 <= L - 1 && L - 1 < i0 + 4) start[L] = run;            // total = start[L]
 }
 
+// band (nullable): [first, last] row of cells this rank needs (k_prm_band); nodes of other rows are
+// not placed (their slice of `ids` stays undefined on this rank).
 __global__ void k_cell_scatter(const double *__restrict__ soa, int64_t capacity, int64_t n,
                                const double *__restrict__ b4, int G, int32_t *__restrict__ cursor,
-                               int32_t *__restrict__ ids) {
+                               int32_t *__restrict__ ids, const int32_t *__restrict__ band) {
+    const int r0 = band ? band[0] : 0, r1 = band ? band[1] : G - 1;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n;
          t += (int64_t)gridDim.x * blockDim.x) {
-        int cx = cell_of(soa[t], b4[0], b4[1], G), cy = cell_of(soa[capacity + t], b4[2], b4[3], G);
+        const int cy = cell_of(soa[capacity + t], b4[2], b4[3], G);
+        if (cy < r0 || cy > r1) continue;
+        const int cx = cell_of(soa[t], b4[0], b4[1], G);
         ids[atomicAdd(cursor + (int64_t)cy * G + cx, 1)] = (int32_t)t;
+    }
+}
+
+// The rows of cells that hold the cell-sorted positions [p0, p0 + count), widened by `halo` rows on
+// both sides: all a rank that answers those rows needs of the grid (a row whose search leaves the
+// band is left to the exact path).  The cell counts / starts are global on every rank; placing the
+// nodes, ordering the cells and copying the poses is then done for the band only -- the part of the
+// grid build that shrinks with the number of ranks.
+__global__ void k_prm_band(const int32_t *__restrict__ start, int G, int64_t p0, int64_t count, int halo,
+                           int32_t *__restrict__ band) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int lo = 0, hi = G - 1;                                   // first row that ends beyond p0
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)start[(int64_t)(mid + 1) * G] > p0) hi = mid; else lo = mid + 1;
+    }
+    const int r0 = lo;
+    lo = 0; hi = G - 1;                                       // last row that begins before p0 + count
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int64_t)start[(int64_t)mid * G] < p0 + count) lo = mid; else hi = mid - 1;
+    }
+    band[0] = r0 - halo < 0 ? 0 : r0 - halo;
+    band[1] = lo + halo > G - 1 ? G - 1 : lo + halo;
+}
+
+// Last step of the grid build for the fused PRM kernels, one thread per cell (of the band): order the
+// cell's segment of `ids` by node index (the scatter places them in the order its atomics landed;
+// every rank must see the same permutation) and copy the poses into the cell-sorted array `pts`.
+__global__ void k_cell_finalize(const double *__restrict__ soa, int64_t capacity, const int32_t *__restrict__ start,
+                                int G, const int32_t *__restrict__ band, int32_t *__restrict__ ids,
+                                double2 *__restrict__ pts) {
+    const int64_t c0 = band ? (int64_t)band[0] * G : 0, c1 = band ? (int64_t)(band[1] + 1) * G : (int64_t)G * G;
+    for (int64_t c = c0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t e0 = start[c], e1 = start[c + 1];
+        for (int32_t i = e0 + 1; i < e1; ++i) {
+            const int32_t v = ids[i];
+            int32_t j = i - 1;
+            while (j >= e0 && ids[j] > v) { ids[j + 1] = ids[j]; --j; }
+            ids[j + 1] = v;
+        }
+        for (int32_t i = e0; i < e1; ++i) {
+            const int32_t v = ids[i];
+            pts[i] = make_double2(soa[v], soa[capacity + v]);
+        }
     }
 }
 
@@ -845,14 +907,162 @@ __global__ void k_cell_sort_segments(const int32_t *__restrict__ start, int64_t 
     }
 }
 
-// Cell-sorted copy of the 2-D poses (sbp_prm_connect2d's fused kernel): pts[p] = pose of node
-// ids[p], so that a row of cells is one contiguous run of 16-byte records and a candidate costs
-// one coalescable load instead of the dependent pair ids[e] -> soa[id].
-__global__ void k_cell_gather_pts(const double *__restrict__ soa, int64_t capacity, int64_t n,
-                                  const int32_t *__restrict__ ids, double2 *__restrict__ pts) {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-        const int32_t v = ids[p];
-        pts[p] = make_double2(soa[v], soa[capacity + v]);
+// The whole grid build of sbp_prm_connect2d in ONE cooperative launch (the separate kernels above cost
+// eight dependent launches, ~2 us of graph-node latency each on top of their work): bounding box and
+// zeroed counts -> histogram -> scan of the cell counts (per-block chunks) -> band of cell rows this
+// part needs (k_prm_band) -> placement of the band's nodes -> per-cell order + cell-sorted poses
+// (k_cell_finalize), separated by grid-wide barriers.  Also sets done[] = 1 (rows of other parts count
+// as settled for the exact path) and zeroes the pending counter.
+struct GridBuildArgs {
+    const double *soa;
+    int64_t capacity, n;
+    double *b4;               // out: bounding box
+    double *partial;          // [gridDim.x][4]
+    int G;
+    int32_t *hdr4;            // [0] pending (zeroed), [1..2] band (out)
+    int32_t *cells, *start, *cursor, *ids;
+    double2 *pts;
+    uint8_t *done;
+    int32_t *bsum;            // [gridDim.x]
+    int64_t p0, count;
+    int banded, halo;
+};
+
+#define GB_TPB 512
+__global__ void __launch_bounds__(GB_TPB, 3)
+k_prm_grid_build(GridBuildArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[4][GB_TPB / 32];
+    __shared__ double sb[4];
+    __shared__ int32_t ws[GB_TPB / 32];
+    __shared__ int32_t s_off, s_carry, s_r0, s_r1;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, nb = gridDim.x, b = blockIdx.x;
+    const int64_t gtid = (int64_t)b * GB_TPB + tid, gsz = (int64_t)nb * GB_TPB;
+    const int G = a.G;
+    const int64_t L = (int64_t)G * G;
+    // ---- phase 0: bounding-box partials, zeroed counts, done = 1
+    {
+        double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+        for (int64_t t = gtid; t < a.n; t += gsz) {
+            const double x = a.soa[t], y = a.soa[a.capacity + t];
+            mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
+            a.done[t] = 1;
+        }
+        for (int64_t i = gtid; i < L; i += gsz) a.cells[i] = 0;
+        if (gtid < 4) a.hdr4[gtid] = 0;
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fmin(mnx, __shfl_down_sync(FULL, mnx, o)); mxx = fmax(mxx, __shfl_down_sync(FULL, mxx, o));
+            mny = fmin(mny, __shfl_down_sync(FULL, mny, o)); mxy = fmax(mxy, __shfl_down_sync(FULL, mxy, o));
+        }
+        if (lane == 0) { sh[0][w] = mnx; sh[1][w] = mxx; sh[2][w] = mny; sh[3][w] = mxy; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int i = 1; i < GB_TPB / 32; ++i) {
+                mnx = fmin(mnx, sh[0][i]); mxx = fmax(mxx, sh[1][i]); mny = fmin(mny, sh[2][i]); mxy = fmax(mxy, sh[3][i]);
+            }
+            double *o = a.partial + 4 * b;
+            o[0] = mnx; o[1] = mxx; o[2] = mny; o[3] = mxy;
+        }
+    }
+    grid.sync();
+    fold_bounds(a.partial, nb, sb);                              // (ends with a __syncthreads)
+    if (b == 0 && tid < 4) a.b4[tid] = sb[tid];
+    const double b0 = sb[0], b1 = sb[1], b2 = sb[2], b3 = sb[3];
+    // ---- phase 1: histogram
+    for (int64_t t = gtid; t < a.n; t += gsz) {
+        const int cx = cell_of(a.soa[t], b0, b1, G), cy = cell_of(a.soa[a.capacity + t], b2, b3, G);
+        atomicAdd(a.cells + (int64_t)cy * G + cx, 1);
+    }
+    grid.sync();
+    // ---- phase 2: exclusive scan, a contiguous chunk of cells per block
+    const int64_t chunk = (L + nb - 1) / nb, c0 = (int64_t)b * chunk, c1 = c0 + chunk < L ? c0 + chunk : L;
+    {
+        int32_t v = 0;
+        for (int64_t i = c0 + tid; i < c1; i += GB_TPB) v += a.cells[i];
+        v = __reduce_add_sync(FULL, v);
+        if (lane == 0) ws[w] = v;
+        __syncthreads();
+        if (tid == 0) {
+            int32_t t = 0;
+            for (int i = 0; i < GB_TPB / 32; ++i) t += ws[i];
+            a.bsum[b] = t;
+        }
+    }
+    grid.sync();
+    {
+        int32_t v = 0;
+        for (int j = tid; j < b; j += GB_TPB) v += a.bsum[j];
+        v = __reduce_add_sync(FULL, v);
+        __syncthreads();
+        if (lane == 0) ws[w] = v;
+        __syncthreads();
+        if (tid == 0) {
+            int32_t t = 0;
+            for (int i = 0; i < GB_TPB / 32; ++i) t += ws[i];
+            s_off = t;
+            s_carry = 0;
+        }
+        __syncthreads();
+        for (int64_t base = c0; base < c1; base += GB_TPB) {
+            const int64_t i = base + tid;
+            const int32_t x = i < c1 ? a.cells[i] : 0;
+            int32_t inc = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+            if (lane == 31) ws[w] = inc;
+            __syncthreads();
+            if (w == 0) {
+                const int32_t y = lane < GB_TPB / 32 ? ws[lane] : 0;
+                int32_t yi = y;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int32_t u = __shfl_up_sync(FULL, yi, o); if (lane >= o) yi += u; }
+                if (lane < GB_TPB / 32) ws[lane] = yi - y;
+            }
+            __syncthreads();
+            const int32_t excl = s_off + s_carry + ws[w] + inc - x;
+            if (i < c1) { a.start[i] = excl; a.cursor[i] = excl; }
+            __syncthreads();
+            if (tid == GB_TPB - 1) s_carry = excl + x - s_off;
+            __syncthreads();
+        }
+        if (b == nb - 1 && tid == 0) a.start[L] = (int32_t)a.n;   // every node has a cell
+    }
+    grid.sync();
+    // ---- band of cell rows this part needs (see k_prm_band)
+    if (tid == 0) { s_r0 = G - 1; s_r1 = 0; }
+    __syncthreads();
+    if (a.banded) {
+        for (int r = tid; r < G; r += GB_TPB) {
+            if ((int64_t)a.start[(int64_t)(r + 1) * G] > a.p0) atomicMin(&s_r0, r);
+            if ((int64_t)a.start[(int64_t)r * G] < a.p0 + a.count) atomicMax(&s_r1, r);
+        }
+        __syncthreads();
+    }
+    const int r0 = a.banded ? (s_r0 - a.halo < 0 ? 0 : s_r0 - a.halo) : 0;
+    const int r1 = a.banded ? (s_r1 + a.halo > G - 1 ? G - 1 : s_r1 + a.halo) : G - 1;
+    if (b == 0 && tid == 0) { a.hdr4[1] = r0; a.hdr4[2] = r1; }
+    // ---- phase 3: placement of the band's nodes
+    for (int64_t t = gtid; t < a.n; t += gsz) {
+        const int cy = cell_of(a.soa[a.capacity + t], b2, b3, G);
+        if (cy < r0 || cy > r1) continue;
+        const int cx = cell_of(a.soa[t], b0, b1, G);
+        a.ids[atomicAdd(a.cursor + (int64_t)cy * G + cx, 1)] = (int32_t)t;
+    }
+    grid.sync();
+    // ---- phase 4: per-cell order by node index, cell-sorted poses
+    for (int64_t c = (int64_t)r0 * G + gtid; c < (int64_t)(r1 + 1) * G; c += gsz) {
+        const int32_t e0 = a.start[c], e1 = a.start[c + 1];
+        for (int32_t i = e0 + 1; i < e1; ++i) {
+            const int32_t v = a.ids[i];
+            int32_t j = i - 1;
+            while (j >= e0 && a.ids[j] > v) { a.ids[j + 1] = a.ids[j]; --j; }
+            a.ids[j + 1] = v;
+        }
+        for (int32_t i = e0; i < e1; ++i) {
+            const int32_t v = a.ids[i];
+            a.pts[i] = make_double2(a.soa[v], a.soa[a.capacity + v]);
+        }
     }
 }
 
@@ -1367,11 +1577,38 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         pending_all = (int32_t *)((char *)cellbuf + hdr);        // zeroed with the cell counts
         int32_t *cells = pending_all + 4, *start = cells + L, *cursor = start + L + 1,
                 *ids = cursor + L, *tsums = ids + n;
+        const bool fused_rows = part && part->fused && K <= PRM_FUSED_KMAX && ctx->tune.knn_filter &&
+                                ctx->tune.knn_cells;
+        int32_t *band = nullptr;
+        void *ptsbuf = nullptr;
+        int hb = (int)((n + 255) / 256);
+        if (hb > ctx->sm_count * 8) hb = ctx->sm_count * 8;
+        if (fused_rows) {
+            // sbp_prm_connect2d: the whole build in one cooperative launch (k_prm_grid_build)
+            rc = sbp_ctx_scratch(ctx, 14, (size_t)n * sizeof(double2), &ptsbuf);
+            if (rc) return rc;
+            rc = sbp_ctx_scratch(ctx, 11, (size_t)m, &donebuf);
+            if (rc) return rc;
+            int per_sm = 0;
+            SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prm_grid_build, GB_TPB, 0));
+            if (per_sm < 1) per_sm = 1;
+            if (per_sm > 3) per_sm = 3;
+            const int nblk = ctx->sm_count * per_sm;
+            void *gb = nullptr;
+            rc = sbp_ctx_scratch(ctx, 18, (size_t)nblk * (4 * sizeof(double) + sizeof(int32_t)), &gb);
+            if (rc) return rc;
+            band = pending_all + 1;                                  // two of the spare header ints
+            GridBuildArgs ga{s->d_soa, s->capacity, n, b4, (double *)gb, G, pending_all, cells, start, cursor, ids,
+                             (double2 *)ptsbuf, (uint8_t *)donebuf, (int32_t *)((double *)gb + 4 * (size_t)nblk),
+                             part->p0, part->count, part->banded, 12};
+            void *kargs[] = {&ga};
+            SBP_CUDA(cudaLaunchCooperativeKernel((void *)k_prm_grid_build, dim3(nblk), dim3(GB_TPB), kargs, 0,
+                                                 ctx->stream));
+            ctx->launches++;
+        } else {
         SBP_CUDA(cudaMemsetAsync(pending_all, 0, (size_t)(L + 4) * sizeof(int32_t), ctx->stream));
         double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
         k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
-        int hb = (int)((n + 255) / 256);
-        if (hb > ctx->sm_count * 8) hb = ctx->sm_count * 8;
         k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,
                                                  cells);
         const int nt = (int)((L + SCAN_TILE - 1) / SCAN_TILE);            // <= 1024 tiles (G <= 2048)
@@ -1383,20 +1620,14 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             k_cell_scan_sums<<<1, 1024, 0, ctx->stream>>>(tsums, nt, start + L);
             k_cell_scan_apply<<<nt, 1024, 0, ctx->stream>>>(cells, L, tsums, start, cursor);
         }
-        k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids);
-        const bool fused_rows = part && part->fused && K <= PRM_FUSED_KMAX;
-        if (part && (part->deterministic || fused_rows)) {
+        k_cell_scatter<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, b4, G, cursor, ids, nullptr);
+        if (part && part->deterministic) {
             int sbk = (int)((L + 255) / 256);
             if (sbk > ctx->sm_count * 8) sbk = ctx->sm_count * 8;
             k_cell_sort_segments<<<sbk, 256, 0, ctx->stream>>>(start, L, ids);
             ctx->launches++;
         }
-        void *ptsbuf = nullptr;
-        if (fused_rows) {
-            rc = sbp_ctx_scratch(ctx, 14, (size_t)n * sizeof(double2), &ptsbuf);
-            if (rc) return rc;
-            k_cell_gather_pts<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, ids, (double2 *)ptsbuf);
-            ctx->launches++;
+        ctx->launches += 6;
         }
         // (16 lanes per query were measured too: 53 us instead of 49 us on cfg2 -- the kernel is
         // bound by its chain of dependent loads start -> ids -> node, not by the lane count)
@@ -1410,7 +1641,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             const int32_t *order = rows_part ? ids + part->p0
                                              : ((ctx->tune.knn_cells_order && m == n) ? ids : nullptr);
             if (rows_part) {
-                SBP_CUDA(cudaMemsetAsync(donebuf, 1, (size_t)m, ctx->stream));
+                if (!fused_rows) SBP_CUDA(cudaMemsetAsync(donebuf, 1, (size_t)m, ctx->stream));
                 part->ids = ids;
             }
             KernelTimer timer(ctx, fused_rows ? -1 : 2);
@@ -1424,7 +1655,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                 int r_init = (int)ceil((sqrt(2.0 * (double)K / per_cell) - 1.0) / 2.0);
                 r_init = r_init < 1 ? 1 : r_init > 8 ? 8 : r_init;
                 if (ctx->tune.knn_cells_rinit > 0) r_init = ctx->tune.knn_cells_rinit;
-                CellGridView gv{b4, G, start, ids, (const double2 *)ptsbuf, n, s->d_maxabs};
+                CellGridView gv{b4, G, start, ids, (const double2 *)ptsbuf, n, s->d_maxabs, band};
                 rc = sbp_prm_fused_launch(ctx, gv, K, k, r_init, ctx->tune.knn_cells_limit, part->p0, part->count,
                                           (double *)seedbuf, (uint8_t *)donebuf, pending_all, part->fused);
                 if (rc) return rc;
@@ -1456,7 +1687,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             k_knn_seed<D, 32><<<(unsigned)((m * 32 + 255) / 256), 256, 0, ctx->stream>>>(
                 s->d_soa, s->capacity, X, m, b4, G, start, ids, K, (double *)seedbuf);
         }
-        ctx->launches += 7;
+        if (!fused_rows) ctx->launches += 1;
         SBP_CUDA(cudaGetLastError());
         seed = (const double *)seedbuf;
         seed_bounds = b4;
@@ -1524,7 +1755,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         }
 #undef SBP_FILTER_LAUNCH
         ctx->launches++;
-        k_knn_refine<D, K><<<(unsigned)((m + 63) / 64), 64, 0, ctx->stream>>>(
+        const int64_t rb = (m + 63) / 64, rcap = (int64_t)ctx->sm_count * 32;
+        k_knn_refine<D, K><<<(unsigned)(rb < rcap ? rb : rcap), 64, 0, ctx->stream>>>(
             s->d_soa, s->capacity, n, X, m, seed, (int)FS, C, (const int32_t *)cbuf, ccount, k, idx,
             dist, flags, (const uint8_t *)donebuf, pending);
         ctx->launches += 2;
@@ -1532,14 +1764,18 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         redo = flags;
         tpb = 32;
     }
+    // (1-D grids capped at 64 CTAs per SM: the kernels loop over their blocks)
+    const int64_t bcap = (int64_t)ctx->sm_count * 64;
     if (tpb == 32) {
-        dim3 grid((unsigned)((m + 31) / 32), (unsigned)S);
+        const int64_t nb = (m + 31) / 32 * S;
+        const unsigned grid = (unsigned)(nb < bcap ? nb : bcap);
         k_knn_batched<D, K, 32><<<grid, 32, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
                                                               ctx->tune.knn_prefilter, s->capacity, n, S, X,
                                                               m, seed, (double *)pd, (int32_t *)pi,
                                                               redo, redo ? pending : nullptr);
     } else {
-        dim3 grid((unsigned)((m + 127) / 128), (unsigned)S);
+        const int64_t nb = (m + 127) / 128 * S;
+        const unsigned grid = (unsigned)(nb < bcap ? nb : bcap);
         k_knn_batched<D, K, 128><<<grid, 128, 0, ctx->stream>>>(s->d_soa, s->d_soa32, s->d_maxabs,
                                                                 ctx->tune.knn_prefilter, s->capacity, n, S,
                                                                 X, m, seed, (double *)pd, (int32_t *)pi,
@@ -1547,7 +1783,8 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
     }
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
-    k_knn_merge<<<(unsigned)((m + 127) / 128), 128, 0, ctx->stream>>>(
+    const int64_t mb = (m + 127) / 128, mcap = (int64_t)ctx->sm_count * 16;
+    k_knn_merge<<<(unsigned)(mb < mcap ? mb : mcap), 128, 0, ctx->stream>>>(
         (const double *)pd, (const int32_t *)pi, m, S, K, k, idx, dist, redo, s->d_soa, s->capacity, n, D, X,
         redo ? pending : nullptr);
     ctx->launches++;

@@ -250,6 +250,7 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
     const double2 q = g.pts[p];
     const double mnx = g.b4[0], mxx = g.b4[1], mny = g.b4[2], mxy = g.b4[3];
     const int G = g.G;
+    const int band0 = g.band ? g.band[0] : 0, band1 = g.band ? g.band[1] : G - 1;
     // finite coordinates whose squared distances stay inside the fp32 range, and at least K other
     // nodes: otherwise the order involves inf / NaN distances or unfilled slots (pad_nan_row)
     const bool usable = live && *g.maxabs < 1e18 && g.n > K && mnx <= mxx && mny <= mxy;
@@ -269,6 +270,8 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
             have_block = c > K;                                   // K besides the row itself
             if (have_block || (x0 == 0 && y0 == 0 && x1 == G - 1 && y1 == G - 1)) break;
         }
+        // (a rank's grid covers a band of cell rows: a search that leaves it goes to the exact path)
+        have_block = have_block && y0 >= band0 && y1 <= band1;
     }
     prm_scan_rows<K, 4>(g.pts, g.ids, g.start, G, q.x, q.y, (int32_t)p, L, have_block, x0, x1, y0, y1, 0, -1, 0, -1,
                         cy_q, true);
@@ -282,7 +285,7 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
         ya = cell_of(__dsub_rd(q.y, r), mny, mxy, G); yb = cell_of(__dadd_ru(q.y, r), mny, mxy, G);
         if (xa >= x0 && xb <= x1 && ya >= y0 && yb <= y1) {
             handled = true;                                       // the block already covers the rectangle
-        } else if (yb - ya < 64) {
+        } else if (yb - ya < 64 && ya >= band0 && yb <= band1) {
             int32_t c = 0;
             for (int row = ya; row <= yb; ++row)
                 c += g.start[(int64_t)row * G + xb + 1] - g.start[(int64_t)row * G + xa];
@@ -419,18 +422,17 @@ k_prm_visible2d(MapView tiled, const uint32_t *__restrict__ af, int AW, const do
                 const int32_t *__restrict__ order, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
                 const int32_t *__restrict__ pending, PrmOut out, int32_t *__restrict__ flags) {
     if (pending && *pending == 0) return;
-    const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x;
-    if (slot >= count) return;
     const int k = K - 1;
+    int myflag = 0;
+    for (int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x; slot < count; slot += (int64_t)gridDim.x * PRM_TPB) {
     const int32_t v = order ? order[p0 + slot] : (int32_t)(p0 + slot);
-    if (done && done[v]) return;
+    if (done && done[v]) continue;
     const double qx = soa[v], qy = soa[capacity + v];
     const int64_t *__restrict__ row = idx + (int64_t)v * K;
     int drop = K - 1;
     for (int c = K - 2; c >= 0; --c)
         if (row[c] == (int64_t)v) drop = c;
     const int64_t orow = out.sorted_rows ? p0 + slot : (int64_t)v;
-    int myflag = 0;
 #pragma unroll 1
     for (int col = 0; col < k; ++col) {
         const int32_t nb = (int32_t)row[col < drop ? col : col + 1];
@@ -442,6 +444,7 @@ k_prm_visible2d(MapView tiled, const uint32_t *__restrict__ af, int AW, const do
         if (out.nbr) out.nbr[o] = (int64_t)nb;
         if (out.vis) out.vis[o] = (uint8_t)(code & 1);
     }
+    }
     if (myflag && flags) atomicOr(flags, myflag);
 }
 
@@ -452,9 +455,18 @@ __global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int
         X[t] = make_double2(soa[t], soa[capacity + t]);
 }
 
-__global__ void k_copy_order(const int32_t *__restrict__ ids, int64_t n, int32_t *__restrict__ order_out) {
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
-        order_out[t] = ids ? ids[t] : (int32_t)t;
+// order_out[p] = node of cell-sorted position p, for p in [p0, p0 + count) (through the multicast
+// mapping when the rows leave that way: the other ranks' slices arrive the same way)
+__global__ void k_copy_order(const int32_t *__restrict__ ids, int64_t p0, int64_t count, int32_t *__restrict__ order_out,
+                             int multicast) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = ids ? ids[p0 + t] : (int32_t)(p0 + t);
+        if (multicast)
+            asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(order_out + p0 + t),
+                         "f"(__int_as_float(v)) : "memory");
+        else
+            order_out[p0 + t] = v;
+    }
 }
 
 // Rows = stored nodes.  The rows are split into `parts` contiguous runs of the CELL-SORTED
@@ -498,15 +510,22 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
     rp.count = base + (part < rem ? 1 : 0);
     rp.deterministic = parts > 1 || sorted_rows;
     rp.fused = &fa;
+    rp.banded = parts > 1;
     if ((rc = sbp_knn_rows_part(nodes, (const double *)xbuf, K, (int64_t *)ibuf, &rp))) return rc;
-    if (order_out) {
-        k_copy_order<<<blocks, 256, 0, ctx->stream>>>(rp.ids, n, order_out);
+    if (order_out && rp.count > 0) {
+        // (several parts: a rank's grid -- and so its permutation -- covers its own rows only)
+        const int64_t o0 = parts > 1 ? rp.p0 : 0, oc = parts > 1 ? rp.count : n;
+        int ob = (int)((oc + 255) / 256);
+        if (ob > ctx->sm_count * 8) ob = ctx->sm_count * 8;
+        k_copy_order<<<ob, 256, 0, ctx->stream>>>(rp.ids, o0, oc, order_out, packed_multicast);
         ctx->launches++;
     }
     if (rp.count == 0) return SBP_OK;
     {
         KernelTimer timer(ctx, rp.fused_ran ? -1 : 3);
-        k_prm_visible2d<<<(unsigned)((rp.count + PRM_TPB - 1) / PRM_TPB), PRM_TPB, 0, ctx->stream>>>(
+        const int64_t vb = (rp.count + PRM_TPB - 1) / PRM_TPB, vcap = (int64_t)ctx->sm_count * 16;
+        // (after the fused kernels this one only has the rows they left: a capped grid that loops)
+        k_prm_visible2d<<<(unsigned)(rp.fused_ran && vb > vcap ? vcap : vb), PRM_TPB, 0, ctx->stream>>>(
             map->view, map->af.words, map->af.AW, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
             rp.p0, rp.count, rp.fused_ran ? rp.done : nullptr, rp.fused_ran ? rp.pending : nullptr, fa.out, flags);
     }

@@ -237,7 +237,10 @@ class PeerAdjacencyBuffer:
         self.n, self.k = int(n_rows), int(k)
         self.ctx = get_context(device)
         dev = torch.device("cuda", device)
-        self._half = (self.n * self.k + 3) // 4 * 4
+        # per half: the packed rows [n][k], then the row permutation [n] (every rank stores its own
+        # slice of both through the same mapping)
+        self._rows = (self.n * self.k + 3) // 4 * 4
+        self._half = self._rows + (self.n + 3) // 4 * 4
         self.buf = symm_mem.empty((2, self._half), dtype=torch.int32, device=dev)
         self.buf.zero_()
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
@@ -256,6 +259,12 @@ class PeerAdjacencyBuffer:
             raise RuntimeError("no multicast mapping on this fabric")
         return (self._mc[h], True)
 
+    def order_target(self, h: int) -> int:
+        """Multicast address of half h's row permutation (``order_out`` of ``prm_connect_knn``)."""
+        if self._mc is None:
+            raise RuntimeError("no multicast mapping on this fabric")
+        return self._mc[h] + self._rows * 4
+
     def local(self, h: int):
         """This rank's own copy of half h as ``packed_out`` (no exchange: for fabrics without the
         multicast mapping the blocks are then all-gathered by the caller)."""
@@ -268,6 +277,9 @@ class PeerAdjacencyBuffer:
 
     def view(self, h: int):
         return self.buf[h][: self.n * self.k].view(self.n, self.k)
+
+    def order_view(self, h: int):
+        return self.buf[h][self._rows: self._rows + self.n]
 
 
 def sharded_visible_batch(visible_fn, P, Q, group=None, costs=None):

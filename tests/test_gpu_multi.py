@@ -84,6 +84,37 @@ def _worker(rank, world, port, q):
                 want_n, want_v = D.all_gather_adjacency(nbr, vis)
                 got_n, got_v = D.unpack_adjacency(packed)
                 assert torch.equal(got_n, want_n) and torch.equal(got_v, want_v), ("rendezvous", step)
+        # the roadmap connection of the stored rows, split over the ranks: every rank builds the cell
+        # grid for its band of cell rows, answers its block of the cell-sorted rows and stores rows
+        # and permutation slice through the multicast mapping (PeerAdjacencyBuffer)
+        n2, k2 = 40013, 10
+        free2 = load_map("intel_lab")
+        cc2 = sg.ImgCollisionChecker(map_png("intel_lab"), device=rank)
+        nodes2 = np.random.default_rng(77).random((n2, 2)) * list(free2.shape)
+        nodes2[:300] = np.floor(nodes2[:300])
+        tree2 = sg.NodeStore(2, device=rank)
+        tree2.extend(nodes2)
+        whole = torch.empty((n2, k2), dtype=torch.int32, device=dev)
+        owhole = torch.empty((n2,), dtype=torch.int32, device=dev)
+        sg.prm_connect_knn(cc2, tree2, k2, packed_out=whole, order_out=owhole, want_rows=False)
+        buf = D.PeerAdjacencyBuffer(n2, k2, device=rank)
+        if buf.fused:
+            kinds.add("banded rows + permutation through the multicast mapping")
+            for step in range(4):
+                h = step & 1
+                sg.prm_connect_knn(cc2, tree2, k2, part=(rank, world), packed_out=buf.target(h), want_rows=False,
+                                   order_out=buf.order_target(h))
+                packed = buf.complete(h)
+                assert torch.equal(packed, whole) and torch.equal(buf.order_view(h), owhole), ("banded", step)
+        # the same through plain device buffers + NCCL (fabrics without the mapping)
+        mine = torch.full((n2, k2), -(1 << 31), dtype=torch.int32, device=dev)
+        omine = torch.full((n2,), -1, dtype=torch.int32, device=dev)
+        sg.prm_connect_knn(cc2, tree2, k2, part=(rank, world), packed_out=mine, want_rows=False, order_out=omine)
+        lo, cnt = D.shard_range(n2, rank, world)
+        assert bool((omine[:lo] == -1).all()) and bool((omine[lo + cnt:] == -1).all())
+        dist.all_reduce(mine, op=dist.ReduceOp.MAX)
+        dist.all_reduce(omine, op=dist.ReduceOp.MAX)
+        assert torch.equal(mine, whole) and torch.equal(omine, owhole)
         dist.barrier()
         dist.destroy_process_group()
         print("exchange kinds exercised:", sorted(kinds), flush=True)

@@ -54,7 +54,10 @@ elif what == "cfg5":
     import workloads
 
     mz, cc, tree, nodes, S, T = workloads.cfg5_on_device(dev)
-    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, 10))
+    # the bench's step: packed adjacency in cell-sorted row order (coalesced stores) + the permutation
+    packed = torch.empty((len(tree), 10), dtype=torch.int32, device=dev)
+    order = torch.empty((len(tree),), dtype=torch.int32, device=dev)
+    ms = timeit(lambda: sg.prm_connect_knn(cc, tree, 10, packed_out=packed, order_out=order, want_rows=False))
     print(what, "ms (eager)", ms)
 elif what in ("knn", "nearest"):
     free = load_map("intel_lab")
