@@ -46,9 +46,15 @@ K_NN = workloads.CFG5["k"]
 K_CONNECT = 8                                              # nearest roadmap nodes tried per query endpoint
 METRIC = "edge collision checks/sec (PRM candidate edges: exact kNN connect + visible_batch)"
 UNIT = "edges/s"
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the visibility kernel on this
-# workload (ncu --set full, profiles/r2_visible_cfg5_full.txt)
-VIS_DRAM_TRAFFIC = int(os.environ.get("BENCH_VIS_TRAFFIC", 872389632))
+# One launch of the two dominant kernels on this workload under `ncu --set full` (N = 1, full size;
+# profiles/r2_prm_walk_full.txt, profiles/r2_prm_knn_full.txt): dram__bytes_read.sum +
+# dram__bytes_write.sum, issue-slot utilisation, active lanes per warp instruction.
+NCU_WALK = {"dram_bytes": 91686912, "issue_active_pct": 77.8, "lanes_per_instruction": 22.7,
+            "warp_instructions": 244921835, "warps_active_pct": 55.9, "alu_pipe_pct": 76.8,
+            "source": "profiles/r2_prm_walk_full.txt"}
+NCU_KNN = {"dram_bytes": 30520832, "issue_active_pct": 66.7, "lanes_per_instruction": 23.2,
+           "warp_instructions": 169512771, "warps_active_pct": 38.7, "alu_pipe_pct": 74.0,
+           "source": "profiles/r2_prm_knn_full.txt"}
 
 
 def problem():
@@ -511,31 +517,40 @@ def run_ours(args):
     else:
         hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    # Dominant kernel: the 2-D visibility kernel on the L2 / HBM resident map.  ALGORITHMIC bytes
-    # per launch: 33 B per edge (two fp64 endpoints in, one byte out) + 0.125 B
-    # (one map bit) per interpolant of the full Bresenham line.
+    # Dominant kernel: k_prm_walk, the Bresenham visibility of the candidate edges on the 128 MiB map.
+    # ALGORITHMIC bytes per launch: 33 B per edge (two fp64 endpoints in, one byte
+    # out) + 0.125 B (one map bit) per interpolant of the full Bresenham line.
     edges_rank = count * k
     alg_bytes = 33.0 * edges_rank + 0.125 * px_total / world
     vis_s = vis_ms / 1e3
-    l2_gather = microbench(ctx, 1, 64 << 20, 512)
-    hbm_gather = microbench(ctx, 1, 8 << 30, 512)
-    roof = {"kernel": f"2-D visibility kernel, fused with the kNN-row edge gather ({100 * vis_ms / sum(ph.values()):.0f}% of "
+    step_ms = total_ms / args.steps
+    prof = NCU_WALK if world == 1 and SCALE == 1.0 else None
+    roof = {"kernel": f"k_prm_walk: two-level Bresenham walk of the kNN candidate edges ({100 * vis_ms / step_ms:.0f}% of "
                       f"the step): {edges_rank} edges, {px_total / world:.4g} interpolants per launch on the 128 MiB map",
             "bound": "hbm", "achieved": alg_bytes / vis_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": alg_bytes / vis_s / 1e9 / hbm_peak, "traffic": VIS_DRAM_TRAFFIC if world == 1 and SCALE == 1.0 else None,
+            "frac": alg_bytes / vis_s / 1e9 / hbm_peak, "traffic": prof["dram_bytes"] if prof else None,
             "peak_source": peak_src, "kernel_ms": vis_ms, "kernel_launches_timed": vis_n,
             "algorithmic_bytes_per_launch": alg_bytes,
             "edges_per_s_kernel": edges_rank / vis_s, "interpolants_per_s_kernel": px_total / world / vis_s,
-            "note": "a gather of map bits and node coordinates, bound by the integer pipe and by L2 sector gathers, "
-                    "not by the HBM stream: see gather (map sectors touched per second against the measured "
-                    "random-sector gather peaks of this GPU)",
-            "gather": {"map_sectors_per_edge_model": 1.0 + 37.0 / 16.0 * 1.27,
-                       "l2_random_sector_gathers_per_s_64MiB": l2_gather,
-                       "hbm_random_sector_gathers_per_s_8GiB": hbm_gather}}
-    roof["gather"]["map_sector_rate_per_s"] = roof["gather"]["map_sectors_per_edge_model"] * edges_rank / vis_s
-    roof["gather"]["frac_of_l2_gather_peak"] = roof["gather"]["map_sector_rate_per_s"] / l2_gather
+            "ncu": prof,
+            "note": "not an HBM stream: the walk decides 8-pixel chunks on 2-bit tile codes (4 MiB, L1 / L2 resident) and "
+                    "is bound by the instructions it issues (ncu: issue slots, lanes per instruction); the HBM figure "
+                    "says how far the algorithmic bytes are from mattering"}
+    # second kernel of the step: the cell-grid kNN (every input and output byte once: cell-sorted poses
+    # 16 B + ids 4 B per node, cell starts 4 B per cell, 4 k + 9 B out per row)
+    knn_bytes = 20.0 * n + 4.0 * (n / 1.5) + (4.0 * k + 9.0) * count
+    roof_knn = {"kernel": f"k_prm_knn: exact k nearest of {count} rows among {n} nodes from the cell grid "
+                          f"({100 * knn_kernel_ms / step_ms:.0f}% of the step)",
+                "bound": "hbm", "achieved": knn_bytes / (knn_kernel_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": knn_bytes / (knn_kernel_ms / 1e3) / 1e9 / hbm_peak,
+                "traffic": NCU_KNN["dram_bytes"] if world == 1 and SCALE == 1.0 else None,
+                "kernel_ms": knn_kernel_ms, "rows_per_s_kernel": count / (knn_kernel_ms / 1e3),
+                "effective_pairs_per_s": float(count) * n / (knn_kernel_ms / 1e3),
+                "ncu": NCU_KNN if world == 1 and SCALE == 1.0 else None,
+                "note": "a gather over L1 / L2 resident arrays bound by issued instructions (list insertions in "
+                        "lock-step over the warp), not by memory"}
 
-    knn_part_ms = max(ph["connect_call"] - vis_ms, 1e-6)       # cell grid + kNN kernels of the call
+    knn_part_ms = max(ph["connect_call"] - vis_ms, 1e-6)       # grid build + kNN kernel + the exact path's launches
     sub = {"knn_queries_per_s_per_gpu": count / (knn_part_ms / 1e3),
            "knn_part_ms": knn_part_ms,
            "knn_kernel_ms": knn_kernel_ms, "knn_kernel_queries_per_s": count / (knn_kernel_ms / 1e3),
@@ -590,6 +605,9 @@ def run_ours(args):
                   "launched eagerly",
         "multi_gpu": {"rows_per_rank": count, "exchange": exchange, "adjacency_check": adjacency_check},
         "roofline": roof,
+        "roofline_knn": roof_knn,
+        "measured_gather_peaks": {"l2_random_sector_gathers_per_s_64MiB": microbench(ctx, 1, 64 << 20, 512),
+                                  "hbm_random_sector_gathers_per_s_8GiB": microbench(ctx, 1, 8 << 30, 512)},
         "cpu_baseline": cpu,
         "phases_ms": ph,
         "submetrics": sub,

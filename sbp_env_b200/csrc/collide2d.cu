@@ -574,7 +574,7 @@ static int32_t launch_visible(sbp_map *map, const double *P, const double *Q, in
 // or two cached 2-bit lookups instead of 8 pixel tests on a 128 MiB array.  Same booleans as the
 // pixel walk for every map (the codes only summarise tiles that are uniformly free / blocked).
 __global__ void __launch_bounds__(256)
-k_visible2d_tiles(MapView mv, const uint32_t *__restrict__ af, int AW, const double2 *__restrict__ P,
+k_visible2d_tiles(MapView mv, TileCodeView af, const double2 *__restrict__ P,
                   const double2 *__restrict__ Q, int64_t n, uint8_t *__restrict__ out, int32_t *__restrict__ flags) {
     int myflag = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -584,7 +584,7 @@ k_visible2d_tiles(MapView mv, const uint32_t *__restrict__ af, int AW, const dou
         bool r = false;
         if (ed.walk) {
             if (ed.x1 >= 0 && ed.y1 >= 0 && ed.x2 >= 0 && ed.y2 >= 0)
-                r = edge_free_tiles(mv.words, mv.SX, af, AW, ed.a1, ed.b1, ed.da, ed.adb, ed.ystep, ed.steep);
+                r = edge_free_tiles(mv.words, mv.SX, af, ed.a1, ed.b1, ed.da, ed.adb, ed.ystep, ed.steep);
             else {                                       // negative coordinates: numpy wrap-around
                 int f2 = 0;
                 r = edge_visible_seq<false>(mv.words, mv, p.x, p.y, q.x, q.y, f2);
@@ -612,7 +612,7 @@ extern "C" int32_t sbp_visible2d(sbp_map *map, const double *P, const double *Q,
         int64_t need = (n + 255) / 256;
         const int grid = (int)(need < (int64_t)ctx->sm_count * 32 ? need : (int64_t)ctx->sm_count * 32);
         KernelTimer timer(ctx, 3);
-        k_visible2d_tiles<<<grid, 256, 0, ctx->stream>>>(map->view, map->af.words, map->af.AW, (const double2 *)P,
+        k_visible2d_tiles<<<grid, 256, 0, ctx->stream>>>(map->view, map->af, (const double2 *)P,
                                                          (const double2 *)Q, n, out, flags);
         ctx->launches++;
         SBP_CUDA(cudaGetLastError());

@@ -192,6 +192,11 @@ struct MapView {
     uint32_t n_words;     // 32-bit words (multiple of 8)
 };
 
+struct TileCodeView {
+    const uint32_t *words;    // two planes of AW x AH / AH x AW words (map.cu:k_tile_codes)
+    int32_t AW, AH;
+};
+
 struct sbp_map {
     sbp_ctx *ctx = nullptr;
     MapView view{};
@@ -208,11 +213,11 @@ struct sbp_map {
     bool rows_smem_resident = false;
     // Coarse level for edge walks on big maps (built on first use, sbp_map_ensure_allfree): a 2-bit
     // code per 8x8-pixel tile, 1 = all 64 pixels free, 2 = all blocked, 0 = mixed; a word = 4 x 4
-    // tiles, 8 x 4 words = one 128-byte line (layout: map.cu:k_tile_codes, lookup:
-    // device_fns.cuh:TileCodes; af.AW = blocks per row).  1/32 of the map's size (4 MiB for 32k^2):
-    // it stays in L1 / L2 where the map itself does not.
+    // tiles, words row major, in two planes (x-major and, transposed, y-major walks; layout:
+    // map.cu:k_tile_codes, lookup: device_fns.cuh:TileCodes; af.AW x af.AH words per plane).  1/16
+    // of the map's size (8 MiB for 32k^2): it stays in L1 / L2 where the map itself does not.
     uint32_t *d_allfree = nullptr;
-    struct AllFreeView { const uint32_t *words; int32_t AW; } af{nullptr, 0};
+    TileCodeView af{nullptr, 0, 0};
 };
 
 int32_t sbp_map_ensure_rows(sbp_map *map);

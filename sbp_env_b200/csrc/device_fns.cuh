@@ -74,30 +74,31 @@ __device__ __forceinline__ bool edge_visible_seq(const uint32_t *words, const Ma
 // da - 1 - (i * |db| + c) mod da -- so the decision is the reference's for every map, whatever
 // its structure.
 // Requires: every pixel of the line inside [0, W) x [0, H) (no numpy wrap-around), da < 65536.
-// Lookup of the 2-bit tile codes (map.cu:k_tile_codes) with the last word kept in registers:
-// consecutive chunks of an edge mostly stay inside one 32 x 32-pixel word.
+// Lookup of the 2-bit tile codes (map.cu:k_tile_codes) by (major tile u, minor tile v) in the plane
+// of the line's orientation, with the last word kept in registers: consecutive chunks of an edge
+// mostly stay inside one 32 x 32-pixel word.
 struct TileCodes {
-    const uint32_t *__restrict__ af;
-    int BW;
+    const uint32_t *__restrict__ plane;
+    int WW;
     uint32_t cur_idx, cur_w;
-    __device__ __forceinline__ TileCodes(const uint32_t *a, int bw) : af(a), BW(bw), cur_idx(0xffffffffu), cur_w(0u) {}
-    __device__ __forceinline__ uint32_t get(int tx, int ty) {
-        const uint32_t wx = (uint32_t)tx >> 2, wy = (uint32_t)ty >> 2;
-        const uint32_t idx = (((wy >> 2) * (uint32_t)BW + (wx >> 3)) << 5) + ((wy & 3u) << 3) + (wx & 7u);
-        if (idx != cur_idx) { cur_idx = idx; cur_w = __ldg(af + idx); }
-        return (cur_w >> ((((ty & 3) << 2) | (tx & 3)) << 1)) & 3u;
+    // AW x AH words in plane 0 (x-major lines); plane 1 (y-major lines) is its transpose
+    __device__ __forceinline__ TileCodes(const uint32_t *af, int AW, int AH, bool steep)
+        : plane(steep ? af + (size_t)AW * (size_t)AH : af), WW(steep ? AH : AW), cur_idx(0xffffffffu), cur_w(0u) {}
+    __device__ __forceinline__ uint32_t get(uint32_t uw, uint32_t ub2, int v) {   // uw = u >> 2, ub2 = (u & 3) * 2
+        const uint32_t idx = ((uint32_t)v >> 2) * (uint32_t)WW + uw;
+        if (idx != cur_idx) { cur_idx = idx; cur_w = __ldg(plane + idx); }
+        return (cur_w >> ((((uint32_t)v & 3u) << 3) | ub2)) & 3u;
     }
 };
 
-__device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ tiled, int SX,
-                                                const uint32_t *__restrict__ af, int AW, int a1, int b1,
-                                                uint32_t da, uint32_t adb, int ystep, bool steep) {
+__device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ tiled, int SX, const TileCodeView &af,
+                                                int a1, int b1, uint32_t da, uint32_t adb, int ystep, bool steep) {
     const uint32_t dd = da ? da : 1u;
     const uint32_t c = da ? da - 1u - (da >> 1) : 0u;
     // quotient estimate from below (2e-6 covers the roundings of the conversion, the reciprocal
     // and the product: the estimate is q or q - 1, one correction step)
     const float rcp = __fdividef(0.999998f, (float)dd);
-    TileCodes codes(af, AW);
+    TileCodes codes(af.words, af.AW, af.AH, steep);
     uint32_t i = 0, q = 0, r = c;
     while (i <= da) {
         const int a = a1 + (int)i, b = b1 + ystep * (int)q;
@@ -108,9 +109,9 @@ __device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ til
         uint32_t re = num - qe * dd;
         if (re >= dd) { re -= dd; ++qe; }
         const int be = b1 + ystep * (int)qe;
-        const int ta = a >> 3, tb0 = b >> 3, tb1 = be >> 3;
-        const uint32_t c0 = codes.get(steep ? tb0 : ta, steep ? ta : tb0);
-        const uint32_t c1 = codes.get(steep ? tb1 : ta, steep ? ta : tb1);
+        const uint32_t ta = (uint32_t)a >> 3, uw = ta >> 2, ub2 = (ta & 3u) << 1;
+        const uint32_t c0 = codes.get(uw, ub2, b >> 3);
+        const uint32_t c1 = codes.get(uw, ub2, be >> 3);
         if ((c0 | c1) & 2u) return false;
         if (!(c0 & c1 & 1u)) {
             int E = (int)da - 1 - (int)r, aa = a, bb = b;

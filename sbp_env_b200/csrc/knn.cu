@@ -1593,7 +1593,10 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prm_grid_build, GB_TPB, 0));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 3) per_sm = 3;
-            const int nblk = ctx->sm_count * per_sm;
+            // (a grid-wide barrier costs more the more CTAs meet at it: small stores get a small grid)
+            int nblk = ctx->sm_count * per_sm;
+            const int64_t want_blk = (n + 1023) / 1024;
+            if (want_blk < nblk) nblk = want_blk < 16 ? 16 : (int)want_blk;
             void *gb = nullptr;
             rc = sbp_ctx_scratch(ctx, 18, (size_t)nblk * (4 * sizeof(double) + sizeof(int32_t)), &gb);
             if (rc) return rc;

@@ -269,16 +269,19 @@ int32_t sbp_map_ensure_rows(sbp_map *m) {
 
 // Coarse level: a 2-bit code per 8x8 tile (= one aligned 64-bit pair of map words): 1 = all 64
 // pixels free, 2 = all blocked, 0 = mixed.  A 32-bit word holds the 4 x 4 tiles of a 32 x 32-pixel
-// square; 8 (x) x 4 (y) words form one 128-byte line = a 256 x 128-pixel block, blocks row major:
-// the edges a warp of neighbouring rows walks fall into a handful of lines.  One thread per word.
-__global__ void k_tile_codes(MapView mv, int BW, int BH, uint32_t *__restrict__ af) {
+// square, words row major.  Two planes: plane 0 indexed (u, v) = (x tile, y tile) for x-major lines,
+// plane 1 its transpose, indexed (u, v) = (y tile, x tile), for y-major lines -- a walk then indexes
+// its plane by (major tile, minor tile) whatever its orientation (device_fns.cuh:TileCodes):
+//   word = (v >> 2) * WW + (u >> 2),  shift = (((v & 3) << 2) | (u & 3)) * 2.
+// One thread per word.
+__global__ void k_tile_codes(MapView mv, int WW, int WH, int transposed, uint32_t *__restrict__ af) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)BW * BH * 32) return;
-    const int blk = (int)(t >> 5), in = (int)(t & 31);
-    const int wx = (blk % BW) * 8 + (in & 7), wy = (blk / BW) * 4 + (in >> 3);
+    if (t >= (int64_t)WW * WH) return;
+    const int wu = (int)(t % WW), wv = (int)(t / WW);
     uint32_t out = 0;
     for (int j = 0; j < 16; ++j) {
-        const int tx = wx * 4 + (j & 3), ty = wy * 4 + (j >> 2);
+        const int u = wu * 4 + (j & 3), v = wv * 4 + (j >> 2);
+        const int tx = transposed ? v : u, ty = transposed ? u : v;
         if (tx >= mv.SX * 2 || ty >= mv.SY * 2) continue;        // (tiles past the last sector: mixed)
         const uint32_t sec = (uint32_t)(ty >> 1) * (uint32_t)mv.SX + (uint32_t)(tx >> 1);
         const uint32_t wi = sec * 8u + (uint32_t)((ty & 1) * 4 + (tx & 1) * 2);
@@ -295,14 +298,16 @@ int32_t sbp_map_ensure_allfree(sbp_map *m) {
     if (m->d_allfree) return SBP_OK;
     sbp_ctx *ctx = m->ctx;
     const int TX = m->view.SX * 2, TY = m->view.SY * 2;         // tiles
-    const int BW = (TX + 31) / 32, BH = (TY + 15) / 16;         // blocks of 32 x 16 tiles
-    const int64_t words = (int64_t)BW * BH * 32;
-    SBP_CUDA(cudaMalloc(&m->d_allfree, (size_t)words * 4));
-    k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, BW, BH, m->d_allfree);
-    ctx->launches++;
+    const int WX = (TX + 3) / 4, WY = (TY + 3) / 4;             // words of 4 x 4 tiles
+    const int64_t words = (int64_t)WX * WY;
+    SBP_CUDA(cudaMalloc(&m->d_allfree, (size_t)words * 2 * 4));
+    k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, WX, WY, 0, m->d_allfree);
+    k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, WY, WX, 1, m->d_allfree + words);
+    ctx->launches += 2;
     SBP_CUDA(cudaGetLastError());
     m->af.words = m->d_allfree;
-    m->af.AW = BW;
+    m->af.AW = WX;
+    m->af.AH = WY;
     return SBP_OK;
 }
 

@@ -51,8 +51,7 @@ struct PrmOut {
 
 struct PrmFusedArgs {
     MapView tiled;
-    const uint32_t *af;
-    int AW;
+    TileCodeView af;
     PrmOut out;
     int32_t *flags;
     // the row poses as [n][2] for the exact path: written only when k_prm_knn left rows pending
@@ -79,8 +78,8 @@ __device__ __forceinline__ void prm_store_packed(const PrmOut &out, int64_t e, i
 
 // visible(m_g.pos, v.pos) of one candidate: start = neighbour p, end = row node q (the 2-D line is
 // direction symmetric, but the argument order is the reference's)
-__device__ __forceinline__ bool prm_edge(const MapView &tiled, const uint32_t *__restrict__ af, int AW, double px,
-                                         double py, double qx, double qy, int &flag) {
+__device__ __forceinline__ bool prm_edge(const MapView &tiled, const TileCodeView &af, double px, double py,
+                                         double qx, double qy, int &flag) {
     const double W = (double)tiled.W, H = (double)tiled.H;
     if (px >= 0.0 && px < W && py >= 0.0 && py < H && qx >= 0.0 && qx < W && qy >= 0.0 && qy < H) {
         // all four coordinates truncate into the index range, nothing wraps (:173-174)
@@ -90,7 +89,7 @@ __device__ __forceinline__ bool prm_edge(const MapView &tiled, const uint32_t *_
         int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;                  // :182-184
         int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
         if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }   // :188-191
-        return edge_free_tiles(tiled.words, tiled.SX, af, AW, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
+        return edge_free_tiles(tiled.words, tiled.SX, af, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
                                b1 < b2 ? 1 : -1, steep);
     }
     return prm_edge_slow(tiled, px, py, qx, qy, &flag);
@@ -124,9 +123,9 @@ struct NearList {
         hi = INFINITY;
         amb = false;
     }
-    __device__ __forceinline__ void insert(double dd, int32_t pos, double qx, double qy,
+    // key = round-down-to-fp32 of the candidate's exact d^2 (recomputed here where it is needed)
+    __device__ __forceinline__ void insert(float key, int32_t pos, double qx, double qy,
                                            const double2 *__restrict__ pts, const int32_t *__restrict__ ids) {
-        const float key = __double2float_rd(dd);
         bool anyeq = false;
 #pragma unroll
         for (int t = 0; t < K; ++t) anyeq |= kf[t] == key;
@@ -145,6 +144,7 @@ struct NearList {
             e[0] = r_cur ? e[0] : pos;
         } else {
             const int32_t id = ids[pos];
+            const double dd = prm_d2(pts[pos], qx, qy);
             bool r[K];
 #pragma unroll
             for (int t = 0; t < K; ++t) {
@@ -212,24 +212,27 @@ __device__ __forceinline__ void prm_scan_rows(const double2 *__restrict__ pts, c
                 e1 = start[(int64_t)row * G + c1 + 1];
             }
             while (__any_sync(FULL, e < e1)) {
-                double d2[U];
+                float key[U];
                 unsigned mask = 0;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool ok = e + u < e1 && e + u != self;
-                    d2[u] = prm_d2(pts[e + u < e1 ? e + u : 0], qx, qy);
-                    mask |= (ok && d2[u] < L.hi) ? (1u << u) : 0u;
+                    const double d2 = prm_d2(pts[e + u < e1 ? e + u : 0], qx, qy);
+                    key[u] = __double2float_rd(d2);
+                    mask |= (ok && d2 < L.hi) ? (1u << u) : 0u;
                 }
                 const int32_t base = e;
                 e += U;
-                while (__any_sync(FULL, mask != 0u)) {
+                // round r: every lane inserts its r-th passing candidate
+                const int rounds = __reduce_max_sync(FULL, __popc(mask));
+                for (int r = 0; r < rounds; ++r) {
                     if (mask) {
                         const int u = __ffs(mask) - 1;
                         mask &= mask - 1;
-                        double dd = d2[0];
+                        float kk = key[0];
 #pragma unroll
-                        for (int v = 1; v < U; ++v) dd = u == v ? d2[v] : dd;
-                        L.insert(dd, base + u, qx, qy, pts, ids);
+                        for (int v = 1; v < U; ++v) kk = u == v ? key[v] : kk;
+                        L.insert(kk, base + u, qx, qy, pts, ids);
                     }
                 }
             }
@@ -345,7 +348,7 @@ k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__r
             const int32_t e = cand[slot * kq + col];
             const int32_t nb = g.ids[e];
             const double2 pp = g.pts[e];
-            const bool free_edge = prm_edge(a.tiled, a.af, a.AW, pp.x, pp.y, q.x, q.y, myflag);
+            const bool free_edge = prm_edge(a.tiled, a.af, pp.x, pp.y, q.x, q.y, myflag);
             const int32_t code = ((nb + 1) << 1) | (free_edge ? 1 : 0);
             const int64_t o = orow * kq + col;
             if (stage) s_code[col][tid] = code;
@@ -417,7 +420,7 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
 // One thread per row with done[v] == 0 (all rows when `done` is NULL): the candidate list comes
 // from the kNN rows idx [n][K] (node order) of knn.cu's exact pipeline.
 __global__ void __launch_bounds__(PRM_TPB)
-k_prm_visible2d(MapView tiled, const uint32_t *__restrict__ af, int AW, const double *__restrict__ soa,
+k_prm_visible2d(MapView tiled, TileCodeView af, const double *__restrict__ soa,
                 int64_t capacity, int64_t n, const int64_t *__restrict__ idx, int K,
                 const int32_t *__restrict__ order, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
                 const int32_t *__restrict__ pending, PrmOut out, int32_t *__restrict__ flags) {
@@ -437,7 +440,7 @@ k_prm_visible2d(MapView tiled, const uint32_t *__restrict__ af, int AW, const do
     for (int col = 0; col < k; ++col) {
         const int32_t nb = (int32_t)row[col < drop ? col : col + 1];
         bool result = false;
-        if (nb >= 0 && (int64_t)nb < n) result = prm_edge(tiled, af, AW, soa[nb], soa[capacity + nb], qx, qy, myflag);
+        if (nb >= 0 && (int64_t)nb < n) result = prm_edge(tiled, af, soa[nb], soa[capacity + nb], qx, qy, myflag);
         const int32_t code = ((nb + 1) << 1) | (result ? 1 : 0);
         const int64_t o = orow * k + col;
         if (out.packed) prm_store_packed(out, o, code);
@@ -502,7 +505,7 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
     }
     // this part's run of the cell-sorted order (balanced like distributed.shard_range)
     const int64_t base = n / parts, rem = n % parts;
-    PrmFusedArgs fa{map->view, map->af.words, map->af.AW,
+    PrmFusedArgs fa{map->view, map->af,
                     PrmOut{nbr_out, vis, packed, packed_multicast, sorted_rows}, flags,
                     nodes->d_soa, nodes->capacity, (double2 *)xbuf};
     KnnRowsPart rp;
@@ -526,7 +529,7 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
         const int64_t vb = (rp.count + PRM_TPB - 1) / PRM_TPB, vcap = (int64_t)ctx->sm_count * 16;
         // (after the fused kernels this one only has the rows they left: a capped grid that loops)
         k_prm_visible2d<<<(unsigned)(rp.fused_ran && vb > vcap ? vcap : vb), PRM_TPB, 0, ctx->stream>>>(
-            map->view, map->af.words, map->af.AW, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
+            map->view, map->af, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
             rp.p0, rp.count, rp.fused_ran ? rp.done : nullptr, rp.fused_ran ? rp.pending : nullptr, fa.out, flags);
     }
     ctx->launches++;
