@@ -573,6 +573,9 @@ def run_ours(args):
                        "sample (about 40 places in this maze), so only a few percent of the random start/goal "
                        "pairs are connected; the component labels settle the others without a search"}
 
+    # the sequential planners' inner loop on the same 1M nodes taken as a tree:
+    # nearest + the one-launch extend step (radius 64: ~50 candidates per sample), host to host
+    rrt = rrt_extend_line(sg, cc, tree, nodes_h) if world == 1 and os.environ.get("BENCH_RRT", "1") == "1" else None
     # cfg2 (BASELINE configs[1], the round-1 headline) as a second line, N = 1 only
     cfg2 = cfg2_line(sg, dev, local, flush) if world == 1 and os.environ.get("BENCH_CFG2", "1") == "1" else None
     # CPU baseline: the unmodified reference on this box's host cores, in a child process (fork
@@ -612,6 +615,7 @@ def run_ours(args):
         "phases_ms": ph,
         "submetrics": sub,
         "query_stage": queries,
+        "rrt_extend": rrt,
         "cfg2": cfg2,
     }
     print(json.dumps(out))
@@ -662,6 +666,41 @@ def check_queries(road, ends, hops_mine, m_q, n_check=24):
         n_reach += want >= 0
     assert ok, "hop counts differ from scipy's BFS on the same graph"
     return f"hop counts of {len(order)} queries ({n_reach} reachable) equal scipy.sparse.csgraph BFS on the same CSR"
+
+
+def rrt_extend_line(sg, cc, tree, nodes_h, m=1500, radius=64.0):
+    """Per-sample latency of the RRT* inner loop on a 1M-node tree: NodeStore.nearest, then
+    DeviceTree.extend (choose parent + rewire decisions in one launch; nothing appended, so every
+    sample sees the same tree), against the two-call host path of round 1 (near_visible + host
+    arithmetic)."""
+    from sbp_env_b200 import planner_ops as ops
+
+    n = len(nodes_h)
+    rng = np.random.default_rng(8)
+    costs = np.linalg.norm(nodes_h - nodes_h[0], axis=1)
+    dt = sg.DeviceTree.from_arrays(cc, tree, nodes_h, costs, np.zeros(n, np.int32))
+    X = nodes_h[rng.integers(0, n, m)] + rng.standard_normal((m, 2)) * 3.0
+    X = X[cc.feasible_batch(X)]
+    for x in X[:20]:
+        dt.extend(x, tree.nearest(x), radius, append=False)
+    t0 = time.perf_counter()
+    for x in X:
+        tree.nearest(x)
+    tn = time.perf_counter() - t0
+    nns = [tree.nearest(x) for x in X]
+    t1 = time.perf_counter()
+    for x, nn in zip(X, nns):
+        dt.extend(x, nn, radius, append=False)
+    t2 = time.perf_counter()
+    v0 = cc.stats.visible_cnt
+    for x, nn in zip(X[:200], nns):
+        ops.choose_least_cost_parent(cc, tree, dt.costs, x, nn, radius, poses=nodes_h)
+    t3 = time.perf_counter()
+    cands = (cc.stats.visible_cnt - v0) / 200
+    return {"tree_nodes": n, "samples": int(len(X)), "radius": radius, "mean_candidates": float(cands),
+            "nearest_us": 1e6 * tn / len(X), "extend_us": 1e6 * (t2 - t1) / len(X),
+            "host_path_choose_parent_us": 1e6 * (t3 - t2) / 200,
+            "ambiguous_samples_settled_on_host": int(dt.ambiguous)}
 
 
 # ------------------------------------------------------------ cfg2 line --------

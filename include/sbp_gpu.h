@@ -322,6 +322,56 @@ int32_t sbp_nodes_near_visible_host(sbp_nodes *nodes, sbp_map *map, int32_t arm,
                                     uint8_t *out_vis, int32_t cap, int32_t *n_hits,
                                     int32_t *flags);
 
+/* replaces: RRTPlanner.find_nearest_neighbour_idx (rrtPlanner.py:268-279) for ONE query x (HOST [d]) in one
+ * launch: np.argmin(np.linalg.norm(poses - x, axis=1)) -- first index of the smallest rounded root; the
+ * first NaN distance wins when there is one (dist then NaN).  idx -1 for an empty store.  Synchronises. */
+int32_t sbp_nodes_nearest1_host(sbp_nodes *nodes, const double *x, int64_t *idx, double *dist);
+
+/* ---- device-resident RRT* tree: cost / parent arrays and the inner loop of one accepted sample
+ * in ONE launch.
+ * replaces: RRTPlanner.choose_least_cost_parent, linear path (rrtPlanner.py:173-196), add_newnode
+ * (:106-113) and the linear rewire (:250-266) for the 2-D image checker: radius scan of the tree
+ * (engine.dist(new, p) <= radius), visible(new.pos, p.pos) per candidate, arg-min of p.cost + c in the
+ * reference's order (nearest node first, ascending index, strict <), append of the new pose with its
+ * cost / parent, re-parenting of every candidate with new.cost + c < n.cost -- on device arrays.
+ * A comparison whose sides are within 64 ulp (the reference's libm-pow distance may differ from
+ * the device's correctly rounded one in the last bit) or a candidate within 4 ulp of the radius is
+ * not decided: status SBP_EXTEND_AMBIGUOUS, nothing written, the caller settles the sample with the
+ * host path and sbp_tree_set.  `fix_*`: exact costs the caller derived for nodes of earlier calls
+ * (engine.dist on the host), applied before any cost is read. */
+typedef struct sbp_tree sbp_tree;
+#define SBP_EXTEND_OK 0
+#define SBP_EXTEND_AMBIGUOUS 1
+#define SBP_EXTEND_NO_PARENT 2      /* nn == -1 and no visible node inside the radius (LookupError) */
+#define SBP_EXTEND_MAX_FIXES 24
+#define SBP_EXTEND_MAX_REWIRED 64
+typedef struct sbp_extend_result {
+    int32_t status;
+    int32_t n_candidates;           /* nodes inside the radius = visible() calls of the reference's loop */
+    int32_t n_rewired;
+    int32_t n_rewire_checked;       /* candidates the rewire pass looked at (not at the new node's / its parent's position) */
+    int64_t new_idx;                /* index of the appended node, -1 when nothing was appended */
+    int64_t parent;
+    double cost;                    /* cost[parent] + c_parent in device arithmetic */
+    double c_parent;
+    int32_t rewired[SBP_EXTEND_MAX_REWIRED];     /* unordered */
+    double rewired_c[SBP_EXTEND_MAX_REWIRED];    /* their distance to the new node (device arithmetic) */
+} sbp_extend_result;
+int32_t sbp_tree_create(sbp_nodes *nodes, sbp_tree **out);
+int32_t sbp_tree_destroy(sbp_tree *tree);
+/* cost (and parent, unless parent < -1) of one node; stream ordered */
+int32_t sbp_tree_set(sbp_tree *tree, int64_t idx, double cost, int64_t parent);
+/* bulk upload of HOST cost / parent arrays into [first, first + count) (an existing tree); synchronises */
+int32_t sbp_tree_write(sbp_tree *tree, int64_t first, int64_t count, const double *cost_host,
+                       const int32_t *parent_host);
+/* HOST copies of cost / parent [first, first + count); synchronises */
+int32_t sbp_tree_read(sbp_tree *tree, int64_t first, int64_t count, double *cost_host, int32_t *parent_host);
+/* newpos: HOST [2]; nn: current nearest node or -1; do_append / do_rewire: 0 / 1; synchronises */
+int32_t sbp_tree_extend_host(sbp_tree *tree, sbp_map *map, const double *newpos, int64_t nn, double radius,
+                             int32_t do_append, int32_t do_rewire, const int64_t *fix_idx,
+                             const double *fix_cost, int32_t n_fixes, sbp_extend_result *out);
+
+
 /* ---- roadmap graph ------------------------------- */
 /* The PRM roadmap as a device-resident CSR graph.
  * replaces: the networkx DiGraph PRMPlanner.build_graph fills edge by edge

@@ -8,6 +8,7 @@ from ._lib import SbpGpuError  # noqa: F401
 from .collision_checker import (CollisionChecker, ImgCollisionChecker,  # noqa: F401
                                 RobotArm4dCollisionChecker, bresenham_pixels)
 from .engine import Engine, ImageEngine, RobotArmEngine, euclidean_dist  # noqa: F401
+from .device_tree import DeviceTree  # noqa: F401
 from .node_store import NodeStore  # noqa: F401
 from .planning import (CapturedStep, PRMConnectGraph, connect_to_roadmap, feasible_batch,  # noqa: F401
                        knn, near, prm_connect_knn, prm_connect_radius, roadmap_edges_to_host,

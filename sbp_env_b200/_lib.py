@@ -63,6 +63,7 @@ _SIGNATURES = {
     "sbp_nodes_knn": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "sbp_nodes_nearest": [_vp, _vp, _i64, _vp, _vp],
     "sbp_nodes_nearest_host": [_vp, _vp, _i64, _vp, _vp],
+    "sbp_nodes_nearest1_host": [_vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)],
     "sbp_nodes_near": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, _vp],
     "sbp_nodes_knn_host": [_vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "sbp_nodes_near_host": [_vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i64, C.POINTER(_i64)],
@@ -75,6 +76,12 @@ _SIGNATURES = {
                                _i32, _vp, _vp],
     "sbp_nodes_near_visible_host": [_vp, _vp, _i32, _dbl, _dbl, _vp, _dbl, _i32, _i32, _i32, _vp, _vp,
                                     _i32, C.POINTER(_i32), C.POINTER(_i32)],
+    "sbp_tree_create": [_vp, C.POINTER(_vp)],
+    "sbp_tree_destroy": [_vp],
+    "sbp_tree_set": [_vp, _i64, _dbl, _i64],
+    "sbp_tree_read": [_vp, _i64, _i64, _vp, _vp],
+    "sbp_tree_write": [_vp, _i64, _i64, _vp, _vp],
+    "sbp_tree_extend_host": [_vp, _vp, _vp, _i64, _dbl, _i32, _i32, _vp, _vp, _i32, _vp],
     "sbp_graph_create": [_vp, _i64, C.POINTER(_vp)],
     "sbp_graph_destroy": [_vp],
     "sbp_graph_build_knn": [_vp, _vp, _vp, _i64, _i32, _i64, _i32],
@@ -93,6 +100,16 @@ _SIGNATURES = {
     "sbp_ctx_kernel_time": [_vp, C.POINTER(_dbl), C.POINTER(_i64)],
 }
 _RESTYPE = {"sbp_last_error": C.c_char_p}
+
+EXTEND_OK, EXTEND_AMBIGUOUS, EXTEND_NO_PARENT = 0, 1, 2
+EXTEND_MAX_FIXES, EXTEND_MAX_REWIRED = 24, 64
+
+
+class ExtendResult(C.Structure):
+    """``sbp_extend_result`` of include/sbp_gpu.h."""
+    _fields_ = [("status", _i32), ("n_candidates", _i32), ("n_rewired", _i32), ("n_rewire_checked", _i32),
+                ("new_idx", _i64), ("parent", _i64), ("cost", _dbl), ("c_parent", _dbl),
+                ("rewired", _i32 * EXTEND_MAX_REWIRED), ("rewired_c", _dbl * EXTEND_MAX_REWIRED)]
 
 #: every entry point the library exports is declared in include/sbp_gpu.h (the tuning /
 #: measurement hooks under "instrumentation")

@@ -233,6 +233,8 @@ struct sbp_nodes {
     double *d_maxabs = nullptr;      // device scalar: max |coordinate| ever appended (inf if non-finite)
 };
 
+int32_t nodes_reserve(sbp_nodes *s, int64_t need);      // capacity >= need (nodes.cu)
+
 // --------------------------------------------------------- device helpers ---
 #ifdef __CUDACC__
 

@@ -518,10 +518,13 @@ k_graph_bfs(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col
         // its parent is the minimum over the whole previous level.  s_tail / s_found are read
         // into registers between two barriers: every thread takes the same decision.
         while (head < tail && !found) {
-            for (int i = head + threadIdx.x; i < tail; i += BFS_TPB) {
+            // a warp per frontier node, its lanes over the node's arcs: a level is a handful of
+            // nodes with ~20 arcs each, and a thread walking them one by one would chain ~20
+            // dependent global atomics
+            for (int i = head + (threadIdx.x >> 5); i < tail; i += BFS_TPB / 32) {
                 const int32_t u = queue[i];
                 const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
-                for (int64_t e = e0; e < e1; ++e) {
+                for (int64_t e = e0 + (threadIdx.x & 31); e < e1; e += 32) {
                     const int32_t v = col[e];
                     int32_t lv = __ldcg(level + v);
                     if (lv < 0) {

@@ -944,6 +944,7 @@ k_prm_grid_build(GridBuildArgs a) {
     // ---- phase 0: bounding-box partials, zeroed counts, done = 1
     {
         double mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+#pragma unroll 4
         for (int64_t t = gtid; t < a.n; t += gsz) {
             const double x = a.soa[t], y = a.soa[a.capacity + t];
             mnx = fmin(mnx, x); mxx = fmax(mxx, x); mny = fmin(mny, y); mxy = fmax(mxy, y);
@@ -969,10 +970,19 @@ k_prm_grid_build(GridBuildArgs a) {
     fold_bounds(a.partial, nb, sb);                              // (ends with a __syncthreads)
     if (b == 0 && tid < 4) a.b4[tid] = sb[tid];
     const double b0 = sb[0], b1 = sb[1], b2 = sb[2], b3 = sb[3];
-    // ---- phase 1: histogram
-    for (int64_t t = gtid; t < a.n; t += gsz) {
-        const int cx = cell_of(a.soa[t], b0, b1, G), cy = cell_of(a.soa[a.capacity + t], b2, b3, G);
-        atomicAdd(a.cells + (int64_t)cy * G + cx, 1);
+    // ---- phase 1: histogram (four nodes per thread and step: their loads are in flight together)
+    for (int64_t t = gtid; t < a.n; t += 4 * gsz) {
+        double x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t tt = t + u * gsz;
+            x[u] = tt < a.n ? a.soa[tt] : 0.0;
+            y[u] = tt < a.n ? a.soa[a.capacity + tt] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (t + u * gsz < a.n)
+                atomicAdd(a.cells + (int64_t)cell_of(y[u], b2, b3, G) * G + cell_of(x[u], b0, b1, G), 1);
     }
     grid.sync();
     // ---- phase 2: exclusive scan, a contiguous chunk of cells per block
@@ -1043,11 +1053,24 @@ k_prm_grid_build(GridBuildArgs a) {
     const int r1 = a.banded ? (s_r1 + a.halo > G - 1 ? G - 1 : s_r1 + a.halo) : G - 1;
     if (b == 0 && tid == 0) { a.hdr4[1] = r0; a.hdr4[2] = r1; }
     // ---- phase 3: placement of the band's nodes
-    for (int64_t t = gtid; t < a.n; t += gsz) {
-        const int cy = cell_of(a.soa[a.capacity + t], b2, b3, G);
-        if (cy < r0 || cy > r1) continue;
-        const int cx = cell_of(a.soa[t], b0, b1, G);
-        a.ids[atomicAdd(a.cursor + (int64_t)cy * G + cx, 1)] = (int32_t)t;
+    for (int64_t t = gtid; t < a.n; t += 4 * gsz) {
+        double x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t tt = t + u * gsz;
+            x[u] = tt < a.n ? a.soa[tt] : 0.0;
+            y[u] = tt < a.n ? a.soa[a.capacity + tt] : 0.0;
+        }
+        int32_t slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int cy = cell_of(y[u], b2, b3, G);
+            const bool in = t + u * gsz < a.n && cy >= r0 && cy <= r1;
+            slot[u] = in ? atomicAdd(a.cursor + (int64_t)cy * G + cell_of(x[u], b0, b1, G), 1) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (slot[u] >= 0) a.ids[slot[u]] = (int32_t)(t + u * gsz);
     }
     grid.sync();
     // ---- phase 4: per-cell order by node index, cell-sorted poses

@@ -128,6 +128,8 @@ static int32_t nodes_grow(sbp_nodes *s, int64_t need) {
     return SBP_OK;
 }
 
+int32_t nodes_reserve(sbp_nodes *s, int64_t need) { return nodes_grow(s, need); }
+
 extern "C" int32_t sbp_nodes_append(sbp_nodes *s, const double *X, int64_t m, int32_t on_device) {
     SBP_NVTX("sbp_nodes_append");
     SBP_REQUIRE(s && (m == 0 || X), "sbp_nodes_append: NULL argument");

@@ -366,9 +366,24 @@ k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__r
         const int64_t slot0 = (int64_t)blockIdx.x * PRM_TPB + wbase;
         if (slot0 < count) {
             const int rows = (int)(count - slot0 < 32 ? count - slot0 : 32);
-            for (int i = lane; i < rows * kq; i += 32) {
-                const int row = i / kq, col = i - row * kq;
-                if ((okmask >> row) & 1u) prm_store_packed(out, (p0 + slot0) * kq + i, s_code[col][wbase + row]);
+            const int64_t base = (p0 + slot0) * kq;
+            if (out.packed_mc && okmask == 0xffffffffu && rows == 32 && (base & 3) == 0) {
+                // through the switch in 16-byte pieces (the block is 16-byte aligned and whole)
+                for (int i4 = lane * 4; i4 < 32 * kq; i4 += 128) {
+                    float f[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i4 + j, row = i / kq, col = i - row * kq;
+                        f[j] = __int_as_float(s_code[col][wbase + row]);
+                    }
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out.packed + base + i4),
+                                 "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+                }
+            } else {
+                for (int i = lane; i < rows * kq; i += 32) {
+                    const int row = i / kq, col = i - row * kq;
+                    if ((okmask >> row) & 1u) prm_store_packed(out, base + i, s_code[col][wbase + row]);
+                }
             }
         }
     }

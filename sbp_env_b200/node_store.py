@@ -131,7 +131,15 @@ class NodeStore:
     def nearest(self, x) -> int:
         """``np.argmin(np.linalg.norm(poses - pos, axis=1))`` (rrtPlanner.py:278-279): the first
         minimum, or -- like np.argmin -- the first node at a NaN distance when there is one."""
-        return int(self.nearest_batch(np.asarray(x, dtype=np.float64).reshape(1, self.dim))[0][0])
+        if _is_torch_tensor(x):
+            return int(self.nearest_batch(x.reshape(1, self.dim))[0][0])
+        # one host query: one launch, the answer comes back through pinned memory
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(self.dim)
+        self.ctx.use_torch_stream()
+        idx = C.c_int64()
+        check(_lib.load().sbp_nodes_nearest1_host(self._h, x.ctypes.data, C.byref(idx), None),
+              "sbp_nodes_nearest1_host")
+        return int(idx.value)
 
     def nearest_batch(self, X, return_dist: bool = True):
         """:meth:`nearest` for every row of X: ``(idx int64 [m], dist fp64 [m])``; numpy in ->
