@@ -85,6 +85,8 @@ struct sbp_tuning {
     int coop_below = 12;          // adaptive kernel: cap of the hand-over threshold (walkers)
     int force_global = 0;         // 1 = never stage the map in shared memory
     int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
+    int prm_slices = 1;           // sbp_prm_connect2d: row slices whose walk overlaps the next slice's kNN
+                                  // (measured on cfg5: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms with 1 / 2 / 3 / 4 / 8 slices)
     int arm_group = 0;            // lanes per arm edge (0 = default 8)
     int near_filter = 1;          // filtered scan of the batched radius query
     int knn_seed = 1;             // grid-seeded a-priori bounds
@@ -118,6 +120,8 @@ struct sbp_ctx {
     int32_t *d_flags = nullptr;      // 16 x int32
     int32_t *h_flags = nullptr;      // pinned mirror
     cudaEvent_t switch_event = nullptr;   // orders a new stream after the previous one
+    cudaStream_t aux_stream = nullptr;    // second stream of sbp_prm_connect2d (walk of slice i beside kNN of i + 1)
+    std::vector<cudaEvent_t> aux_events;  // fork / join events of that overlap
     int64_t scratch_generation = 0;  // bumped whenever a scratch slot is reallocated
     // bench instrumentation (sbp_tune("time_kernels", 1)): CUDA events around the dominant
     // kernel of the kNN path, read back with sbp_ctx_kernel_time

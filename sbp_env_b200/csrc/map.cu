@@ -66,6 +66,8 @@ extern "C" int32_t sbp_ctx_destroy(sbp_ctx *ctx) {
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
     if (ctx->switch_event) cudaEventDestroy(ctx->switch_event);
+    for (cudaEvent_t e : ctx->aux_events) cudaEventDestroy(e);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return SBP_OK;

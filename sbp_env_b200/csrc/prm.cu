@@ -403,30 +403,61 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
     void *cbuf = nullptr;
     int32_t rc = sbp_ctx_scratch(ctx, 16, (size_t)count * (kq > 0 ? kq : 1) * sizeof(int32_t), &cbuf);
     if (rc) return rc;
-    const unsigned blocks = (unsigned)((count + PRM_TPB - 1) / PRM_TPB);
-#define PRM_KNN(KK)                                                                                       \
-    k_prm_knn<KK><<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0, count, seed2, done, pending, \
-                                                       (int32_t *)cbuf)
-    {
-        KernelTimer timer(ctx, 2);
-        if (kq <= 4) PRM_KNN(4);
-        else if (kq <= 8) PRM_KNN(8);
-        else if (kq <= 10) PRM_KNN(10);
-        else if (kq <= 16) PRM_KNN(16);
-        else if (kq <= 20) PRM_KNN(20);
-        else { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
+    // Optionally (tune "prm_slices", default 1 = off) the rows go through the two kernels in SLICES,
+    // the walk of slice i on a second stream beside the kNN of slice i + 1.  Measured on cfg5 and
+    // rejected as the default: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms per step with 1 / 2 / 3 / 4 / 8 slices
+    // -- each kernel already fills the SMs, so the second stream only adds launch tails.
+    int slices = ctx->tune.prm_slices;
+    if (slices < 1 || ctx->tune.time_kernels != 0 || count < 65536) slices = 1;
+    if (slices > 16) slices = 16;
+    if (slices > 1) {
+        if (!ctx->aux_stream) SBP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+        while ((int)ctx->aux_events.size() < slices + 1) {
+            cudaEvent_t e;
+            SBP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->aux_events.push_back(e);
+        }
     }
+    if (kq > 20) { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
+    const int64_t per = ((count + slices - 1) / slices + PRM_TPB - 1) / PRM_TPB * PRM_TPB;   // whole CTAs (and warps)
+    for (int sl = 0; sl < slices; ++sl) {
+        const int64_t off = (int64_t)sl * per, cnt = count - off < per ? count - off : per;
+        if (cnt <= 0) break;
+        const unsigned blocks = (unsigned)((cnt + PRM_TPB - 1) / PRM_TPB);
+        int32_t *cand = (int32_t *)cbuf + off * kq;
+#define PRM_KNN(KK)                                                                                          \
+    k_prm_knn<KK><<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + off, cnt, seed2, done, pending, cand)
+        {
+            KernelTimer timer(ctx, 2);
+            if (kq <= 4) PRM_KNN(4);
+            else if (kq <= 8) PRM_KNN(8);
+            else if (kq <= 10) PRM_KNN(10);
+            else if (kq <= 16) PRM_KNN(16);
+            else PRM_KNN(20);
+        }
 #undef PRM_KNN
+        cudaStream_t ws = ctx->stream;
+        if (slices > 1) {
+            SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
+            SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
+            ws = ctx->aux_stream;
+        }
+        {
+            KernelTimer timer(ctx, 3);
+            k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, *args);
+        }
+        ctx->launches += 2;
+    }
     (void)K;
-    {
-        KernelTimer timer(ctx, 3);
-        k_prm_walk<<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, p0, count, done, (const int32_t *)cbuf, *args);
+    if (slices > 1) {                                         // join: everything behind sees all rows
+        SBP_CUDA(cudaEventRecord(ctx->aux_events[slices], ctx->aux_stream));
+        SBP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[slices], 0));
     }
     // the exact path behind reads the row poses as [n][2]: converted only if it has work
     int ab = (int)((grid.n + 255) / 256);
     if (ab > ctx->sm_count * 8) ab = ctx->sm_count * 8;
     k_rows_aos<<<ab, 256, 0, ctx->stream>>>(args->soa, args->capacity, grid.n, args->X, pending);
-    ctx->launches += 3;
+    ctx->launches += 1;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
 }

@@ -1,7 +1,8 @@
 """cfg5 PRM connection (1M nodes on the 32k^2 maze, k = 10): time of the captured step for a few
-settings of the cell-grid knobs (first ring radius, nodes per cell).  Run under gpurun.
+settings of the knobs: row slices whose walk overlaps the next slice's kNN (default sweep), or --
+with any argument -- first ring radius x nodes per cell.  Run under gpurun.
 
-    python tools/prm_sweep.py
+    python tools/prm_sweep.py [cells]
 """
 import os
 import sys
@@ -22,10 +23,15 @@ packed = torch.empty((n, k), dtype=torch.int32, device=dev)
 order = torch.empty((n,), dtype=torch.int32, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = None
-for dens in (100, 150, 200, 300):
-    for rinit in (0, 1, 2):
+import itertools
+
+grid = [(150, 0, sl) for sl in (1, 2, 3, 4, 6, 8)] if len(sys.argv) < 2 else \
+    [(d, r, 4) for d, r in itertools.product((100, 150, 200, 300), (0, 1, 2))]
+for dens, rinit, sl in grid:
+    if True:
         ctx.tune("knn_cell_density", dens)
         ctx.tune("knn_cells_rinit", rinit)
+        ctx.tune("prm_slices", sl)
         g = sg.PRMConnectGraph(cc, tree, k, packed_out=packed, want_rows=False, order_out=order)
         for _ in range(3):
             g.replay()
@@ -45,5 +51,5 @@ for dens in (100, 150, 200, 300):
             ref = node.clone()
         same = bool(torch.equal(ref, node))
         ts.sort()
-        print(f"density {dens / 100:.2f} rinit {rinit}: {ts[len(ts) // 2]:.4f} ms (min {ts[0]:.4f}) same={same}", flush=True)
+        print(f"density {dens / 100:.2f} rinit {rinit} slices {sl}: {ts[len(ts) // 2]:.4f} ms (min {ts[0]:.4f}) same={same}", flush=True)
         del g
