@@ -85,6 +85,7 @@ struct sbp_tuning {
     int coop_below = 12;          // adaptive kernel: cap of the hand-over threshold (walkers)
     int force_global = 0;         // 1 = never stage the map in shared memory
     int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
+    int prm_walk_sorted = 1;      // sbp_prm_connect2d: walk the CTA's edges sorted by length (0: a row's edges in order)
     int prm_slices = 1;           // sbp_prm_connect2d: row slices whose walk overlaps the next slice's kNN
                                   // (measured on cfg5: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms with 1 / 2 / 3 / 4 / 8 slices)
     int arm_group = 0;            // lanes per arm edge (0 = default 8)

@@ -80,14 +80,25 @@ __device__ __forceinline__ bool edge_visible_seq(const uint32_t *words, const Ma
 struct TileCodes {
     const uint32_t *__restrict__ plane;
     int WW;
-    uint32_t cur_idx, cur_w;
+    uint32_t idx0, w0, idx1, w1;       // two cached words: the one being walked and the line's last one
     // AW x AH words in plane 0 (x-major lines); plane 1 (y-major lines) is its transpose
     __device__ __forceinline__ TileCodes(const uint32_t *af, int AW, int AH, bool steep)
-        : plane(steep ? af + (size_t)AW * (size_t)AH : af), WW(steep ? AH : AW), cur_idx(0xffffffffu), cur_w(0u) {}
+        : plane(steep ? af + (size_t)AW * (size_t)AH : af), WW(steep ? AH : AW), idx0(0xffffffffu), w0(0u),
+          idx1(0xffffffffu), w1(0u) {}
+    // the words of the line's first and last tile, requested together before the walk starts (a line of
+    // a few dozen pixels rarely touches a third one): one memory round trip per edge instead of one
+    // per word
+    __device__ __forceinline__ void prefetch(uint32_t u_s, int v_s, uint32_t u_e, int v_e) {
+        idx0 = ((uint32_t)v_s >> 2) * (uint32_t)WW + (u_s >> 2);
+        idx1 = ((uint32_t)v_e >> 2) * (uint32_t)WW + (u_e >> 2);
+        w0 = __ldg(plane + idx0);
+        w1 = __ldg(plane + idx1);
+    }
     __device__ __forceinline__ uint32_t get(uint32_t uw, uint32_t ub2, int v) {   // uw = u >> 2, ub2 = (u & 3) * 2
         const uint32_t idx = ((uint32_t)v >> 2) * (uint32_t)WW + uw;
-        if (idx != cur_idx) { cur_idx = idx; cur_w = __ldg(plane + idx); }
-        return (cur_w >> ((((uint32_t)v & 3u) << 3) | ub2)) & 3u;
+        if (idx != idx0 && idx != idx1) { idx0 = idx; w0 = __ldg(plane + idx); }  // (the older word goes)
+        const uint32_t w = idx == idx0 ? w0 : w1;
+        return (w >> ((((uint32_t)v & 3u) << 3) | ub2)) & 3u;
     }
 };
 
@@ -99,6 +110,7 @@ __device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ til
     // and the product: the estimate is q or q - 1, one correction step)
     const float rcp = __fdividef(0.999998f, (float)dd);
     TileCodes codes(af.words, af.AW, af.AH, steep);
+    codes.prefetch((uint32_t)a1 >> 3, b1 >> 3, (uint32_t)(a1 + (int)da) >> 3, (b1 + ystep * (int)adb) >> 3);
     uint32_t i = 0, q = 0, r = c;
     while (i <= da) {
         const int a = a1 + (int)i, b = b1 + ystep * (int)q;

@@ -393,6 +393,146 @@ k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__r
 __global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X,
                            const int32_t *__restrict__ pending);
 
+// The same walk with the CTA's edges SORTED BY LENGTH first (the default): in k_prm_walk a warp's 32
+// lanes walk the j-th edges of 32 rows in lock-step and wait for the longest one (20.5 of 32 lanes
+// active in the chunk loop, profiles/r2_prm_walk_full.txt).  Here a CTA of 64 rows sets up its 64 k
+// edges (thread = row), counting-sorts them in shared memory by their number of 8-pixel chunks,
+// and the threads then walk the sorted list: the 32 edges of a warp step have the same length.
+// Results return to their (row, column) slot in shared memory; output as in k_prm_walk.
+#define PW_ROWS 64
+#define PW_BINS 32
+struct PwEdge {                // 12 bytes: all coordinates of a fast-path edge lie in [0, 65536)
+    uint16_t a1, b1;
+    uint16_t da, adb;
+    uint16_t slot;           // col * PW_ROWS + row
+    uint16_t flags;          // bit 0 steep, bit 1 minor step +1
+};
+
+__global__ void __launch_bounds__(PW_ROWS)
+k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
+                  const int32_t *__restrict__ cand, PrmFusedArgs a) {
+    extern __shared__ __align__(16) unsigned char pw_smem[];
+    PwEdge *s_edge = reinterpret_cast<PwEdge *>(pw_smem);                              // [kq * PW_ROWS]
+    int32_t *s_code = reinterpret_cast<int32_t *>(pw_smem + (size_t)kq * PW_ROWS * sizeof(PwEdge));   // [kq][PW_ROWS]
+    uint16_t *s_idx = reinterpret_cast<uint16_t *>(s_code + kq * PW_ROWS);            // [kq * PW_ROWS]
+    __shared__ int s_cnt[PW_BINS], s_off[PW_BINS], s_total;
+    const int tid = threadIdx.x;
+    const int64_t slot = (int64_t)blockIdx.x * PW_ROWS + tid;
+    const bool live = slot < count;
+    const int64_t p = p0 + (live ? slot : 0);
+    const int32_t v = g.ids[p];
+    const bool work = live && done[v];
+    const double2 q = g.pts[p];
+    const PrmOut &out = a.out;
+    if (tid < PW_BINS) s_cnt[tid] = 0;
+    __syncthreads();
+    // ---- phase 1: set up the row's edges, count them per length bin
+    const double W = (double)a.tiled.W, H = (double)a.tiled.H;
+    const bool q_in = q.x >= 0.0 && q.x < W && q.y >= 0.0 && q.y < H;
+    const int qxi = q_in ? __double2int_rz(q.x) : 0, qyi = q_in ? __double2int_rz(q.y) : 0;
+    int myflag = 0;
+    unsigned binbits_lo = 0, binbits_hi = 0;          // 5 bits per column would not fit: bins live in s_idx
+    (void)binbits_lo; (void)binbits_hi;
+    if (work) {
+#pragma unroll 1
+        for (int col = 0; col < kq; ++col) {
+            const int32_t e = cand[slot * kq + col];
+            const int32_t nb = g.ids[e];
+            const double2 pp = g.pts[e];
+            const int sl = col * PW_ROWS + tid;
+            int32_t code = (nb + 1) << 1;
+            int bin = -1;
+            if (q_in && pp.x >= 0.0 && pp.x < W && pp.y >= 0.0 && pp.y < H) {
+                // start = neighbour, end = row node (:173-174); steep / order swaps (:179-191)
+                const int x1 = __double2int_rz(pp.x), y1 = __double2int_rz(pp.y);
+                const int dx = qxi - x1, dy = qyi - y1;
+                const bool steep = abs(dy) > abs(dx);
+                int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+                int a2 = steep ? qyi : qxi, b2 = steep ? qxi : qyi;
+                if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+                PwEdge ed;
+                ed.a1 = (uint16_t)a1; ed.b1 = (uint16_t)b1;
+                ed.da = (uint16_t)(a2 - a1); ed.adb = (uint16_t)abs(b2 - b1);
+                ed.slot = (uint16_t)sl;
+                ed.flags = (uint16_t)((steep ? 1 : 0) | (b1 < b2 ? 2 : 0));
+                s_edge[sl] = ed;
+                const int nch = (a2 >> 3) - (a1 >> 3) + 1;
+                bin = nch < PW_BINS ? nch - 1 : PW_BINS - 1;
+                atomicAdd(&s_cnt[bin], 1);
+            } else {
+                code |= prm_edge_slow(a.tiled, pp.x, pp.y, q.x, q.y, &myflag) ? 1 : 0;   // wrap-around / out of range
+            }
+            s_code[sl] = code;
+            s_idx[sl] = (uint16_t)(bin + 1);          // (bin + 1 until the placement below; 0 = not walked here)
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = PW_BINS - 1; b >= 0; --b) { s_off[b] = acc; acc += s_cnt[b]; }   // longest edges first
+        s_total = acc;
+    }
+    __syncthreads();
+    // ---- placement: the sorted order of the edges (read the bins back before anything is overwritten)
+    int mybins[PRM_FUSED_KMAX - 1];
+#pragma unroll
+    for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col) mybins[col] = (work && col < kq) ? (int)s_idx[col * PW_ROWS + tid] - 1 : -1;
+    __syncthreads();
+#pragma unroll
+    for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col)
+        if (mybins[col] >= 0) s_idx[atomicAdd(&s_off[mybins[col]], 1)] = (uint16_t)(col * PW_ROWS + tid);
+    __syncthreads();
+    // ---- phase 2: walk the sorted edges
+    const int total = s_total;
+    for (int i = tid; i < total; i += PW_ROWS) {
+        const PwEdge ed = s_edge[s_idx[i]];
+        const bool fr = edge_free_tiles(a.tiled.words, a.tiled.SX, a.af, (int)ed.a1, (int)ed.b1, ed.da, ed.adb,
+                                        (ed.flags & 2) ? 1 : -1, (ed.flags & 1) != 0);
+        if (fr) s_code[ed.slot] |= 1;
+    }
+    __syncthreads();
+    // ---- output
+    const int64_t orow = out.sorted_rows ? p : (int64_t)v;
+    const bool stage = out.sorted_rows && out.packed;
+    if (work) {
+        for (int col = 0; col < kq; ++col) {
+            const int32_t code = s_code[col * PW_ROWS + tid];
+            const int64_t o = orow * kq + col;
+            if (!stage && out.packed) prm_store_packed(out, o, code);
+            if (out.nbr) out.nbr[o] = (int64_t)(code >> 1) - 1;
+            if (out.vis) out.vis[o] = (uint8_t)(code & 1);
+        }
+    }
+    if (stage) {
+        const unsigned FULL = 0xffffffffu;
+        const unsigned okmask = __ballot_sync(FULL, work);
+        const int lane = tid & 31, wbase = tid & ~31;
+        const int64_t slot0 = (int64_t)blockIdx.x * PW_ROWS + wbase;
+        if (slot0 < count) {
+            const int rows = (int)(count - slot0 < 32 ? count - slot0 : 32);
+            const int64_t base = (p0 + slot0) * kq;
+            if (out.packed_mc && okmask == 0xffffffffu && rows == 32 && (base & 3) == 0) {
+                for (int i4 = lane * 4; i4 < 32 * kq; i4 += 128) {
+                    float f[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = i4 + j, row = i / kq, col = i - row * kq;
+                        f[j] = __int_as_float(s_code[col * PW_ROWS + wbase + row]);
+                    }
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out.packed + base + i4),
+                                 "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+                }
+            } else {
+                for (int i = lane; i < rows * kq; i += 32) {
+                    const int row = i / kq, col = i - row * kq;
+                    if ((okmask >> row) & 1u) prm_store_packed(out, base + i, s_code[col * PW_ROWS + wbase + row]);
+                }
+            }
+        }
+    }
+    if (myflag && a.flags) atomicOr(a.flags, myflag);
+}
+
 // K = list length of knn.cu's dispatch (entries asked for, rounded up to an instantiated size),
 // k = the entries asked for = candidates per row + the row itself.
 int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int k, int r_init, int limit,
@@ -444,7 +584,13 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         }
         {
             KernelTimer timer(ctx, 3);
-            k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, *args);
+            if (ctx->tune.prm_walk_sorted) {
+                const size_t sm = (size_t)kq * PW_ROWS * (sizeof(PwEdge) + sizeof(int32_t) + sizeof(uint16_t));
+                k_prm_walk_sorted<<<(unsigned)((cnt + PW_ROWS - 1) / PW_ROWS), PW_ROWS, sm, ws>>>(grid, kq, p0 + off, cnt,
+                                                                                                  done, cand, *args);
+            } else {
+                k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, *args);
+            }
         }
         ctx->launches += 2;
     }

@@ -2,7 +2,7 @@
 settings of the knobs: row slices whose walk overlaps the next slice's kNN (default sweep), or --
 with any argument -- first ring radius x nodes per cell.  Run under gpurun.
 
-    python tools/prm_sweep.py [cells]
+    python tools/prm_sweep.py [walk | slices | cells]
 """
 import os
 import sys
@@ -25,13 +25,19 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 ref = None
 import itertools
 
-grid = [(150, 0, sl) for sl in (1, 2, 3, 4, 6, 8)] if len(sys.argv) < 2 else \
-    [(d, r, 4) for d, r in itertools.product((100, 150, 200, 300), (0, 1, 2))]
-for dens, rinit, sl in grid:
+mode = sys.argv[1] if len(sys.argv) > 1 else "walk"
+if mode == "slices":
+    grid = [(150, 0, sl, 1) for sl in (1, 2, 3, 4, 6, 8)]
+elif mode == "cells":
+    grid = [(d, r, 1, 1) for d, r in itertools.product((100, 150, 200, 300), (0, 1, 2))]
+else:
+    grid = [(150, 0, 1, ws) for ws in (0, 1, 0, 1)]
+for dens, rinit, sl, ws in grid:
     if True:
         ctx.tune("knn_cell_density", dens)
         ctx.tune("knn_cells_rinit", rinit)
         ctx.tune("prm_slices", sl)
+        ctx.tune("prm_walk_sorted", ws)
         g = sg.PRMConnectGraph(cc, tree, k, packed_out=packed, want_rows=False, order_out=order)
         for _ in range(3):
             g.replay()
@@ -51,5 +57,5 @@ for dens, rinit, sl in grid:
             ref = node.clone()
         same = bool(torch.equal(ref, node))
         ts.sort()
-        print(f"density {dens / 100:.2f} rinit {rinit} slices {sl}: {ts[len(ts) // 2]:.4f} ms (min {ts[0]:.4f}) same={same}", flush=True)
+        print(f"density {dens / 100:.2f} rinit {rinit} slices {sl} walk_sorted {ws}: {ts[len(ts) // 2]:.4f} ms (min {ts[0]:.4f}) same={same}", flush=True)
         del g
