@@ -474,10 +474,10 @@ def run_ours(args):
     x_dev = torch.empty((n, 2), dtype=torch.float64, device=dev)
     tree2 = sg.NodeStore(2, capacity=n, device=local)
     # H2D: the node-store append kernel reads the pinned host rows itself (coalesced zero-copy reads;
-    # BENCH_E2E_H2D_COPY=1: explicit copy first).  D2H: the walk kernel stores this rank's block of the
-    # packed adjacency -- contiguous, whole 128-byte lines -- straight into the pinned host buffer as
-    # the edges are decided (BENCH_E2E_D2H_COPY=1: device buffer + copy); the row permutation follows
-    # with one 4 MB copy.
+    # BENCH_E2E_H2D_COPY=1: explicit copy first).  D2H: the call is handed the pinned host buffers; the
+    # library computes this rank's block of the packed adjacency in slices and copies every slice out
+    # (DMA engine, second stream) while the next ones are computed, the row ids as soon as the grid is
+    # built (BENCH_E2E_D2H_COPY=1: device buffers + two copies after the call).
     h2d_copy = os.environ.get("BENCH_E2E_H2D_COPY", "0") == "1"
     d2h_copy = os.environ.get("BENCH_E2E_D2H_COPY", "0") == "1"
 
@@ -486,11 +486,12 @@ def run_ours(args):
             x_dev.copy_(pinned, non_blocking=True)
         tree2.truncate(0)
         tree2.extend(x_dev if h2d_copy else pinned)
-        sg.prm_connect_knn(cc, tree2, k, part=part, want_rows=False, order_out=order_e,
+        sg.prm_connect_knn(cc, tree2, k, part=part, want_rows=False,
+                           order_out=order_e if d2h_copy else order_h.data_ptr(),
                            packed_out=code_dev if d2h_copy else (code_h.data_ptr(), False))
         if d2h_copy:
             code_h[first:first + count].copy_(code_dev[first:first + count], non_blocking=True)
-        order_h[first:first + count].copy_(order_e[first:first + count], non_blocking=True)
+            order_h[first:first + count].copy_(order_e[first:first + count], non_blocking=True)
 
     e2e_graph = sg.CapturedStep(e2e_body, device=local)
     for _ in range(max(3, args.warmup)):
@@ -598,7 +599,7 @@ def run_ours(args):
                 "result": "packed adjacency int32 [rows of this rank, cell-sorted][k] = (neighbour + 1) * 2 + visible, "
                           "and their node indices int32 [rows of this rank]",
                 "d2h": "copy from a device buffer" if d2h_copy else
-                       "stored by the walk kernel straight into the pinned host buffer (coalesced zero-copy) + one copy of the permutation",
+                       "the call writes the pinned host buffers: per-slice DMA copies of the rows overlapping the next slices' kernels, row ids copied beside the kNN",
                 "h2d": "copy into a device buffer" if h2d_copy else
                        "read from the pinned host buffer by the node-store append kernel (zero-copy)"},
         "gpu_launches": int(launches_per_step * args.steps),

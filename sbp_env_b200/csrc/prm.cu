@@ -58,6 +58,11 @@ struct PrmFusedArgs {
     const double *soa;
     int64_t capacity;
     double2 *X;
+    int host_out;            // `packed` is (pinned) host memory: the walk's stores are PCIe bound
+    // the row permutation for the caller (nullable): positions [order_p0, order_p0 + order_count)
+    int32_t *order_out;
+    int64_t order_p0, order_count;
+    int order_host;          // order_out is host memory: copied by the DMA engine beside the kNN
 };
 
 __device__ __noinline__ bool prm_edge_slow(const MapView &tiled, double px, double py, double qx, double qy,
@@ -390,6 +395,8 @@ k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__r
     if (myflag && a.flags) atomicOr(a.flags, myflag);
 }
 
+__global__ void k_copy_order(const int32_t *__restrict__ ids, int64_t p0, int64_t count, int32_t *__restrict__ order_out,
+                             int multicast);
 __global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X,
                            const int32_t *__restrict__ pending);
 
@@ -547,16 +554,52 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
     // the walk of slice i on a second stream beside the kNN of slice i + 1.  Measured on cfg5 and
     // rejected as the default: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms per step with 1 / 2 / 3 / 4 / 8 slices
     // -- each kernel already fills the SMs, so the second stream only adds launch tails.
+    // When the packed rows go to HOST memory the slices serve another purpose: the kernels write a
+    // device staging buffer and every slice's block is copied out by the DMA engine (second stream)
+    // while the next slices are computed -- 40 MB take 0.70 ms over PCIe against 0.5 ms of compute,
+    // so the step costs the copy plus one slice instead of compute plus copy (zero-copy stores from
+    // the walk kernel reached only ~45 GB/s and 1.14 ms for the call; staged: 0.8x ms).
     int slices = ctx->tune.prm_slices;
+    const bool stage_host = args->host_out && args->out.packed && args->out.sorted_rows && ctx->tune.time_kernels == 0;
+    if (stage_host) slices = 8;
     if (slices < 1 || ctx->tune.time_kernels != 0 || count < 65536) slices = 1;
     if (slices > 16) slices = 16;
-    if (slices > 1) {
+    if (slices > 1 || stage_host || (args->order_out && args->order_host)) {
         if (!ctx->aux_stream) SBP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         while ((int)ctx->aux_events.size() < slices + 1) {
             cudaEvent_t e;
             SBP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ctx->aux_events.push_back(e);
         }
+    }
+    if (args->order_out && args->order_count > 0) {
+        // the permutation is known once the grid is built: out it goes before the kernels start
+        if (args->order_host) {
+            if (!ctx->aux_stream) SBP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+            if (ctx->aux_events.empty()) {
+                cudaEvent_t e;
+                SBP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->aux_events.push_back(e);
+            }
+            SBP_CUDA(cudaEventRecord(ctx->aux_events[0], ctx->stream));
+            SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[0], 0));
+            SBP_CUDA(cudaMemcpyAsync(args->order_out + args->order_p0, grid.ids + args->order_p0,
+                                     (size_t)args->order_count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->aux_stream));
+        } else {
+            int ob = (int)((args->order_count + 255) / 256);
+            if (ob > ctx->sm_count * 8) ob = ctx->sm_count * 8;
+            k_copy_order<<<ob, 256, 0, ctx->stream>>>(grid.ids, args->order_p0, args->order_count, args->order_out,
+                                                      args->out.packed_mc);
+            ctx->launches++;
+        }
+    }
+    PrmFusedArgs wargs = *args;
+    int32_t *host_packed = nullptr;
+    if (stage_host) {
+        void *stg = nullptr;
+        if ((rc = sbp_ctx_scratch(ctx, 19, (size_t)grid.n * kq * sizeof(int32_t), &stg))) return rc;
+        host_packed = args->out.packed;
+        wargs.out.packed = (int32_t *)stg;                    // [n][kq] like the caller's buffer
     }
     if (kq > 20) { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
     const int64_t per = ((count + slices - 1) / slices + PRM_TPB - 1) / PRM_TPB * PRM_TPB;   // whole CTAs (and warps)
@@ -577,7 +620,7 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         }
 #undef PRM_KNN
         cudaStream_t ws = ctx->stream;
-        if (slices > 1) {
+        if (slices > 1 && !stage_host) {
             SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
             SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
             ws = ctx->aux_stream;
@@ -587,15 +630,23 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
             if (ctx->tune.prm_walk_sorted) {
                 const size_t sm = (size_t)kq * PW_ROWS * (sizeof(PwEdge) + sizeof(int32_t) + sizeof(uint16_t));
                 k_prm_walk_sorted<<<(unsigned)((cnt + PW_ROWS - 1) / PW_ROWS), PW_ROWS, sm, ws>>>(grid, kq, p0 + off, cnt,
-                                                                                                  done, cand, *args);
+                                                                                                  done, cand, wargs);
             } else {
-                k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, *args);
+                k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, wargs);
             }
+        }
+        if (stage_host) {
+            // this slice's block of rows: device staging -> the caller's host buffer, on the copy stream
+            SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
+            SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
+            const int64_t r0 = (p0 + off) * kq;
+            SBP_CUDA(cudaMemcpyAsync(host_packed + r0, wargs.out.packed + r0, (size_t)cnt * kq * sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, ctx->aux_stream));
         }
         ctx->launches += 2;
     }
     (void)K;
-    if (slices > 1) {                                         // join: everything behind sees all rows
+    if (slices > 1 || stage_host || (args->order_out && args->order_host)) {   // join: everything behind sees all rows
         SBP_CUDA(cudaEventRecord(ctx->aux_events[slices], ctx->aux_stream));
         SBP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[slices], 0));
     }
@@ -699,15 +750,30 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
     const int64_t base = n / parts, rem = n % parts;
     PrmFusedArgs fa{map->view, map->af,
                     PrmOut{nbr_out, vis, packed, packed_multicast, sorted_rows}, flags,
-                    nodes->d_soa, nodes->capacity, (double2 *)xbuf};
+                    nodes->d_soa, nodes->capacity, (double2 *)xbuf, 0, nullptr, 0, 0, 0};
+    if (packed && !packed_multicast) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, packed) == cudaSuccess && attr.type == cudaMemoryTypeHost) fa.host_out = 1;
+        else cudaGetLastError();
+    }
     KnnRowsPart rp;
     rp.p0 = (int64_t)part * base + (part < rem ? part : rem);
     rp.count = base + (part < rem ? 1 : 0);
     rp.deterministic = parts > 1 || sorted_rows;
     rp.fused = &fa;
     rp.banded = parts > 1;
-    if ((rc = sbp_knn_rows_part(nodes, (const double *)xbuf, K, (int64_t *)ibuf, &rp))) return rc;
     if (order_out && rp.count > 0) {
+        // (several parts: a rank's grid -- and so its permutation -- covers its own rows only)
+        fa.order_out = order_out;
+        fa.order_p0 = parts > 1 ? rp.p0 : 0;
+        fa.order_count = parts > 1 ? rp.count : n;
+        cudaPointerAttributes attr{};
+        if (!packed_multicast && cudaPointerGetAttributes(&attr, order_out) == cudaSuccess && attr.type == cudaMemoryTypeHost)
+            fa.order_host = 1;
+        else cudaGetLastError();
+    }
+    if ((rc = sbp_knn_rows_part(nodes, (const double *)xbuf, K, (int64_t *)ibuf, &rp))) return rc;
+    if (order_out && rp.count > 0 && !rp.fused_ran) {
         // (several parts: a rank's grid -- and so its permutation -- covers its own rows only)
         const int64_t o0 = parts > 1 ? rp.p0 : 0, oc = parts > 1 ? rp.count : n;
         int ob = (int)((oc + 255) / 256);
