@@ -47,14 +47,14 @@ K_CONNECT = 8                                              # nearest roadmap nod
 METRIC = "edge collision checks/sec (PRM candidate edges: exact kNN connect + visible_batch)"
 UNIT = "edges/s"
 # One launch of the two dominant kernels on this workload under `ncu --set full` (N = 1, full size;
-# profiles/r2_prm_walk_full.txt, profiles/r2_prm_knn_full.txt): dram__bytes_read.sum +
+# profiles/r2_prm_walk_sorted_full.txt, profiles/r2_prm_knn_full.txt): dram__bytes_read.sum +
 # dram__bytes_write.sum, issue-slot utilisation, active lanes per warp instruction.
-NCU_WALK = {"dram_bytes": 91686912, "issue_active_pct": 77.8, "lanes_per_instruction": 22.7,
-            "warp_instructions": 244921835, "warps_active_pct": 55.9, "alu_pipe_pct": 76.8,
-            "source": "profiles/r2_prm_walk_full.txt"}
-NCU_KNN = {"dram_bytes": 30520832, "issue_active_pct": 66.7, "lanes_per_instruction": 23.2,
-           "warp_instructions": 169512771, "warps_active_pct": 38.7, "alu_pipe_pct": 74.0,
-           "source": "profiles/r2_prm_knn_full.txt"}
+NCU_WALK = {"kernel": "k_prm_walk_sorted", "dram_bytes": 94058496, "issue_active_pct": 69.6,
+            "lanes_per_instruction": 29.2, "warp_instructions": 201447164, "warps_active_pct": 52.9,
+            "alu_pipe_pct": 67.4, "source": "profiles/r2_prm_walk_sorted_full.txt"}
+NCU_KNN = {"kernel": "k_prm_knn<10>", "dram_bytes": 39021568, "issue_active_pct": 68.6,
+           "lanes_per_instruction": 23.5, "warp_instructions": 165410624, "warps_active_pct": 44.0,
+           "alu_pipe_pct": 75.6, "source": "profiles/r2_prm_knn_full.txt"}
 
 
 def problem():
@@ -518,7 +518,7 @@ def run_ours(args):
     else:
         hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    # Dominant kernel: k_prm_walk, the Bresenham visibility of the candidate edges on the 128 MiB map.
+    # Dominant kernel: k_prm_walk_sorted, the Bresenham visibility of the candidate edges on the 128 MiB map.
     # ALGORITHMIC bytes per launch: 33 B per edge (two fp64 endpoints in, one byte
     # out) + 0.125 B (one map bit) per interpolant of the full Bresenham line.
     edges_rank = count * k
@@ -526,7 +526,7 @@ def run_ours(args):
     vis_s = vis_ms / 1e3
     step_ms = total_ms / args.steps
     prof = NCU_WALK if world == 1 and SCALE == 1.0 else None
-    roof = {"kernel": f"k_prm_walk: two-level Bresenham walk of the kNN candidate edges ({100 * vis_ms / step_ms:.0f}% of "
+    roof = {"kernel": f"k_prm_walk_sorted: two-level Bresenham walk of the kNN candidate edges ({100 * vis_ms / step_ms:.0f}% of "
                       f"the step): {edges_rank} edges, {px_total / world:.4g} interpolants per launch on the 128 MiB map",
             "bound": "hbm", "achieved": alg_bytes / vis_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / vis_s / 1e9 / hbm_peak, "traffic": prof["dram_bytes"] if prof else None,
