@@ -131,6 +131,129 @@ k_arm_visible(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
     }
 }
 
+// visible, flattened form (the default): the lane-group kernel above leaves lanes idle whenever an
+// edge's number of interpolated configs is not a multiple of the group (RRT-style edges have 7-11:
+// 12.4 of 32 lanes active, profiles/r1_arm_visible_full.txt).  Here a CTA takes a block of
+// AF_EDGES edges, sets them up once (thread = edge: truncation, base line, angle steps, N), prefix-
+// sums their N, and then ALL threads walk the flattened list of (edge, config) pairs -- every lane
+// has a config until the block's last ones.  A config looks up its edge by binary search in the
+// prefix array; results are OR-ed into the edge's flags (bit 0 = some config blocked, bit 1 = some
+// config ambiguous: blocked wins, as in the kernel above); configs of an edge already known to be
+// blocked are skipped, which keeps most of the early exit.
+#define AF_EDGES 256
+struct ArmEdge {
+    int32_t a1, b1;
+    uint32_t da, adb, npx;
+    int32_t flags;            // bit 0 steep, bit 1 swapped, bit 2 minor step +1
+    double az, aw, st0, st1;
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_arm_visible_flat(MapView mv, double L0, double L1, const double4 *__restrict__ C1,
+                   const double4 *__restrict__ C2, int64_t n, uint8_t *__restrict__ out,
+                   int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    __shared__ ArmEdge s_e[AF_EDGES];
+    __shared__ uint32_t s_pref[AF_EDGES + 1];
+    __shared__ int32_t s_f[AF_EDGES];
+    __shared__ uint32_t s_ws[AF_EDGES / 32];
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int myflag = 0;
+    for (int64_t base = (int64_t)blockIdx.x * AF_EDGES; base < n; base += (int64_t)gridDim.x * AF_EDGES) {
+        // ---- phase 1: set up the block's edges
+        uint32_t N = 0;
+        if (tid < AF_EDGES) {
+            const int64_t eidx = base + tid;
+            const bool valid = eidx < n;
+            double4 a = make_double4(0, 0, 0, 0), b = make_double4(0, 0, 0, 0);
+            if (valid) { a = C1[eidx]; b = C2[eidx]; }
+            // base line between int()-truncated base points (:373, :461-462)
+            TruncResult t0 = trunc_index(a.x, mv.W), t1 = trunc_index(a.y, mv.H);
+            TruncResult t2 = trunc_index(b.x, mv.W), t3 = trunc_index(b.y, mv.H);
+            int f = t0.flag ? t0.flag : t1.flag ? t1.flag : t2.flag ? t2.flag : t3.flag;
+            if (!f && (isinf(a.z) || isinf(a.w) || isinf(b.z) || isinf(b.w) || a.z != a.z || a.w != a.w ||
+                       b.z != b.z || b.w != b.w))
+                f = SBP_FLAG_NAN;
+            if (valid) myflag |= f;
+            // an out-of-range base endpoint blocks the edge (configs 0 / N-1 sit on the base end pixels)
+            const bool walk = valid && !f && t0.in_range && t1.in_range && t2.in_range && t3.in_range;
+            int x1 = t0.i, y1 = t1.i, x2 = t2.i, y2 = t3.i;
+            int dx = x2 - x1, dy = y2 - y1;
+            const bool steep = abs(dy) > abs(dx);
+            int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+            int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+            const bool swapped = a1 > a2;
+            if (swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+            ArmEdge e;
+            e.a1 = a1; e.b1 = b1;
+            e.da = (uint32_t)(a2 - a1); e.adb = (uint32_t)abs(b2 - b1);
+            e.npx = e.da + 1u;
+            e.flags = (steep ? 1 : 0) | (swapped ? 2 : 0) | (b1 < b2 ? 4 : 0);
+            const uint32_t NN = e.npx < 2u ? 2u : e.npx;                 // :375-377
+            // create_ranges (:363-364): steps = (1.0/(N-1))*(stop-start); rot = steps*i + start
+            const double inv = __ddiv_rn(1.0, (double)(NN - 1u));
+            e.az = a.z; e.aw = a.w;
+            e.st0 = __dmul_rn(inv, __dsub_rn(b.z, a.z));
+            e.st1 = __dmul_rn(inv, __dsub_rn(b.w, a.w));
+            s_e[tid] = e;
+            N = walk ? NN : 0u;
+            s_f[tid] = walk ? 0 : 1;                                     // not walked = blocked
+        }
+        // exclusive prefix of N over the block's edges
+        if (tid < AF_EDGES) {
+            uint32_t inc = N;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+            if (lane == 31) s_ws[w] = inc;
+            s_pref[tid + 1] = inc;                                        // (warp-local for now)
+        }
+        __syncthreads();
+        if (tid < AF_EDGES) {
+            uint32_t off = 0;
+            for (int i = 0; i < w; ++i) off += s_ws[i];
+            s_pref[tid + 1] += off;
+            if (tid == 0) s_pref[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t T = s_pref[AF_EDGES];
+        // ---- phase 2: all threads over the flattened (edge, config) pairs
+        for (uint32_t c = tid; c < T; c += blockDim.x) {
+            int lo = 0, hi = AF_EDGES;                                   // largest j with s_pref[j] <= c
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_pref[mid] <= c) lo = mid; else hi = mid;
+            }
+            if (s_f[lo] & 1) continue;                                   // edge already blocked
+            const ArmEdge e = s_e[lo];
+            const uint32_t o = c - s_pref[lo];
+            const uint32_t po = e.npx == 1u ? 0u : o;                    // duplicated single pixel
+            const bool steep = e.flags & 1, swapped = e.flags & 2;
+            const uint64_t ci = swapped ? (uint64_t)(e.npx - 1u - po) : (uint64_t)po;
+            const uint32_t cc = e.da ? e.da - 1u - (e.da >> 1) : 0u;
+            const uint32_t k = e.da ? (uint32_t)((ci * e.adb + cc) / e.da) : 0u;
+            const int aa = e.a1 + (int)ci, bb = e.b1 + ((e.flags & 4) ? 1 : -1) * (int)k;
+            const double bx = (double)(steep ? bb : aa), by = (double)(steep ? aa : bb);
+            const double r0 = __dadd_rn(__dmul_rn(e.st0, (double)o), e.az);
+            const double r1 = __dadd_rn(__dmul_rn(e.st1, (double)o), e.aw);
+            const int r = arm_config<SMEM, true>(words, mv, L0, L1, bx, by, r0, r1, myflag);
+            if (r != 1) atomicOr(&s_f[lo], r == 0 ? 1 : 2);
+        }
+        __syncthreads();
+        // ---- phase 3: an unambiguous block decides the edge, else an ambiguous config leaves it open
+        if (tid < AF_EDGES && base + tid < n) {
+            const int f = s_f[tid];
+            out[base + tid] = (uint8_t)((f & 1) ? 0 : (f & 2) ? 2 : 1);
+        }
+        __syncthreads();
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
 // ------------------------------------------------------------ launchers -----
 
 // The arm kernels read the ROW-MAJOR copy of the map (sbp_map::rows, common.cuh).
@@ -217,6 +340,28 @@ extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const dou
     bool smem = !ctx->tune.force_global && map->rows_smem_resident &&
                 n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 16;
     unsigned long long *cnt = (unsigned long long *)cfg_tested;
+    if (!cnt && ctx->tune.arm_group == 0 && ctx->tune.arm_flat) {
+        size_t bytes = smem ? (size_t)map->rows.n_words * 4 : 0;
+        // static shared memory of the kernel (edge block, prefix, flags) next to the staged map
+        const size_t fixed = sizeof(ArmEdge) * AF_EDGES + 4 * (2 * AF_EDGES + 16) + 1024;
+        int per_sm = smem ? (int)((size_t)(227 * 1024) / (bytes + fixed)) : 2;
+        per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
+        const int threads = per_sm == 1 ? 1024 : 512;
+        int grid = ctx->sm_count * per_sm;
+        const int64_t need = (n + AF_EDGES - 1) / AF_EDGES;
+        if (need < grid) grid = (int)need;
+        const double4 *c1 = (const double4 *)C1, *c2 = (const double4 *)C2;
+        if (smem) {
+            if (bytes + fixed > 48 * 1024)
+                SBP_CUDA(cudaFuncSetAttribute(k_arm_visible_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            k_arm_visible_flat<true><<<grid, threads, bytes, ctx->stream>>>(map->rows, L0, L1, c1, c2, n, out, flags);
+        } else {
+            k_arm_visible_flat<false><<<grid, threads, 0, ctx->stream>>>(map->rows, L0, L1, c1, c2, n, out, flags);
+        }
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
     int G = ctx->tune.arm_group ? ctx->tune.arm_group : 8;
     switch (G) {
         case 4: return launch_arm_visible<4>(map, L0, L1, C1, C2, n, out, flags, cnt, smem);
