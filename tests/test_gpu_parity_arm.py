@@ -90,8 +90,10 @@ def test_random_vs_oracle(sg, name, L):
     lib = _lib.load()
     want_fwd, want_rev = om.arm_visible(C1, C2, *L), om.arm_visible(C2, C1, *L)
     try:
-        # lanes per edge of the lane-group kernel (0 = default, 8)
-        for group in (0, 4, 32):
+        # (flat, group): the flattened (edge, config) kernel (default), then the lane-group kernel with
+        # 8 (its default), 4 and 32 lanes per edge
+        for flat, group in ((1, 0), (0, 0), (0, 4), (0, 32)):
+            tune("arm_flat", flat)
             tune("arm_group", group)
             assert np.array_equal(cc.visible_batch(C1, C2), want_fwd), group
             # H8: argument order matters for the arm; check the reverse direction too
@@ -101,6 +103,7 @@ def test_random_vs_oracle(sg, name, L):
             assert np.array_equal(cc.visible_batch(C1[-1:], C2[-1:]), want_fwd[-1:]), group
     finally:
         tune("arm_group", 0)
+        tune("arm_flat", 1)
 
 
 def test_guard_band_is_resolved_exactly(sg):
