@@ -36,6 +36,7 @@ struct sbp_graph {
     // BFS work-space, grown on demand: per CTA slot level [n], parent [n], queue [n]
     int32_t *d_work = nullptr;
     int64_t work_slots = 0;
+    bool symmetric = false;          // last build added both directions of every arc (undirected)
 };
 
 #define GSCAN_TILE 4096
@@ -241,6 +242,7 @@ static int32_t graph_build(sbp_graph *g, EdgeSource es) {
     SBP_DEVICE(ctx);
     es.n = g->n;
     g->comp_valid = false;
+    g->symmetric = es.undirected != 0;
     // every candidate may become an arc (two when undirected): size `col` for all of them (no
     // host round trip)
     const int64_t need = es.total * (es.undirected ? 2 : 1);
@@ -462,7 +464,7 @@ extern "C" int32_t sbp_graph_components(sbp_graph *g, int32_t *labels, int64_t *
 }
 
 // ------------------------------------------------------------------- BFS ----
-#define BFS_TPB 512
+#define BFS_TPB 1024
 #define BFS_UNSET 0x7fffffff
 
 // Queries are taken from a device-side ticket counter (the ones the component labels settle
@@ -571,6 +573,90 @@ k_graph_bfs(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col
     }
 }
 
+// Hop counts only, on a SYMMETRIC graph (built undirected): the search runs from both ends at once.
+// Every step expands the current frontier of the start side AND of the goal side (a warp per
+// frontier node, lanes over its arcs); a node belongs to the side that claims it first
+// (level = depth * 2 + side).  An arc from a frontier node of one side (depth d) into a node of the
+// other side (depth d') closes a path of d + 1 + d' arcs; the minimum over the arcs seen in the
+// first step that closes any is the fewest-hop count -- every shorter path would have closed in an
+// earlier step -- so a search of L hops takes ~L / 2 steps (the maze roadmap's paths are ~1000
+// hops long and a step is a handful of nodes: the step count is the cost).
+// Work-space: level [n]; the start side's FIFO in `queue`, the goal side's in the `parent` array
+// (unused without paths; restored to BFS_UNSET afterwards).
+__global__ void __launch_bounds__(BFS_TPB)
+k_graph_bfs_bidir(const int64_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int64_t n,
+                  const int32_t *__restrict__ comp, const int64_t *__restrict__ start,
+                  const int64_t *__restrict__ goal, int64_t nq, int32_t *__restrict__ work,
+                  int32_t *__restrict__ hops, unsigned long long *__restrict__ ticket) {
+    int32_t *level = work + (int64_t)blockIdx.x * 3 * n, *qt = level + n, *qs = qt + n;
+    __shared__ int s_tail[2], s_best;
+    __shared__ long long s_q;
+    while (true) {
+        if (threadIdx.x == 0) {
+            long long q;
+            while (true) {
+                q = (long long)atomicAdd(ticket, 1ull);
+                if (q >= nq) break;
+                const int64_t s = start[q], t = goal[q];
+                const bool ok = s >= 0 && s < n && t >= 0 && t < n;
+                if (ok && s != t && comp[s] == comp[t]) break;          // needs the search
+                hops[q] = ok && s == t ? 0 : -1;
+            }
+            s_q = q;
+        }
+        __syncthreads();
+        const int64_t q = s_q;
+        if (q >= nq) return;
+        const int64_t s = start[q], t = goal[q];
+        if (threadIdx.x == 0) {
+            level[s] = 0;                                   // depth 0, side 0
+            level[t] = 1;                                   // depth 0, side 1
+            qs[0] = (int32_t)s;
+            qt[0] = (int32_t)t;
+            s_tail[0] = 1; s_tail[1] = 1;
+            s_best = 0x7fffffff;
+        }
+        __syncthreads();
+        int head0 = 0, head1 = 0, tail0 = 1, tail1 = 1, depth = 0;
+        int best = 0x7fffffff;
+        while (best == 0x7fffffff && head0 < tail0 && head1 < tail1) {
+            const int n0 = tail0 - head0, total = n0 + (tail1 - head1);
+            for (int i = threadIdx.x >> 5; i < total; i += BFS_TPB / 32) {
+                const int side = i < n0 ? 0 : 1;
+                const int32_t u = side == 0 ? qs[head0 + i] : qt[head1 + (i - n0)];
+                const int64_t e0 = row_ptr[u], e1 = row_ptr[u + 1];
+                const int32_t mine = ((depth + 1) << 1) | side;
+                for (int64_t e = e0 + (threadIdx.x & 31); e < e1; e += 32) {
+                    const int32_t v = col[e];
+                    int32_t lv = __ldcg(level + v);
+                    if (lv < 0) {
+                        lv = atomicCAS(level + v, -1, mine);
+                        if (lv < 0) {                            // claimed for this side: enqueue
+                            if (side == 0) qs[atomicAdd(&s_tail[0], 1)] = v;
+                            else qt[atomicAdd(&s_tail[1], 1)] = v;
+                            continue;
+                        }
+                    }
+                    if ((lv & 1) != side) atomicMin(&s_best, depth + 1 + (lv >> 1));   // the sides meet on this arc
+                }
+            }
+            __syncthreads();
+            head0 = tail0; head1 = tail1;
+            tail0 = s_tail[0]; tail1 = s_tail[1];
+            best = s_best;
+            ++depth;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) hops[q] = best == 0x7fffffff ? -1 : best;
+        // reset only what this query touched
+        for (int i = threadIdx.x; i < tail0; i += BFS_TPB) level[qs[i]] = -1;
+        for (int i = threadIdx.x; i < tail1; i += BFS_TPB) { level[qt[i]] = -1; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < tail1; i += BFS_TPB) qt[i] = BFS_UNSET;      // (the parent array again)
+        __syncthreads();
+    }
+}
+
 __global__ void k_graph_work_init(int32_t *__restrict__ work, int64_t n, int64_t slots) {
     const int64_t total = slots * 3 * n;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
@@ -613,8 +699,12 @@ extern "C" int32_t sbp_graph_bfs(sbp_graph *g, const int64_t *start, const int64
     }
     unsigned long long *ticket = (unsigned long long *)(ctx->d_flags + 14);      // 8-byte aligned slot
     SBP_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), ctx->stream));
-    k_graph_bfs<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, g->d_comp, start,
-                                                             goal, nq, g->d_work, hops, paths, max_len, ticket);
+    if (!paths && g->symmetric)
+        k_graph_bfs_bidir<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, g->d_comp, start,
+                                                                       goal, nq, g->d_work, hops, ticket);
+    else
+        k_graph_bfs<<<(unsigned)slots, BFS_TPB, 0, ctx->stream>>>(g->d_row_ptr, g->d_col, g->n, g->d_comp, start,
+                                                                 goal, nq, g->d_work, hops, paths, max_len, ticket);
     ctx->launches++;
     SBP_CUDA(cudaGetLastError());
     return SBP_OK;
