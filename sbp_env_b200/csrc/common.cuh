@@ -85,6 +85,8 @@ struct sbp_tuning {
     int coop_below = 12;          // adaptive kernel: cap of the hand-over threshold (walkers)
     int force_global = 0;         // 1 = never stage the map in shared memory
     int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
+    int tile_rect = 1;            // tile walks: settle an edge whose bounding box of tiles is all free from the run planes
+    int prm_mc_stage = 0;         // sbp_prm_connect2d: multicast outputs leave through a staging buffer + copy kernel
     int prm_walk_sorted = 1;      // sbp_prm_connect2d: walk the CTA's edges sorted by length (0: a row's edges in order)
     int prm_slices = 1;           // sbp_prm_connect2d: row slices whose walk overlaps the next slice's kNN
                                   // (measured on cfg5: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms with 1 / 2 / 3 / 4 / 8 slices)
@@ -201,6 +203,11 @@ struct MapView {
 struct TileCodeView {
     const uint32_t *words;    // two planes of AW x AH / AH x AW words (map.cu:k_tile_codes)
     int32_t AW, AH;
+    // free-run planes (map.cu:k_tile_runs, lookup: device_fns.cuh:tiles_rect_free): plane j in 0..3,
+    // word [j][k][u] bit b = "the 2^j tiles (u .. u + 2^j - 1, 16 k + b) are all free"; windows of 32
+    // tile rows every 16 (any span of <= 16 rows lies inside one word); RK windows x RU tile columns.
+    const uint32_t *runs;
+    int32_t RU, RK;
 };
 
 struct sbp_map {
@@ -223,8 +230,16 @@ struct sbp_map {
     // map.cu:k_tile_codes, lookup: device_fns.cuh:TileCodes; af.AW x af.AH words per plane).  1/16
     // of the map's size (8 MiB for 32k^2): it stays in L1 / L2 where the map itself does not.
     uint32_t *d_allfree = nullptr;
-    TileCodeView af{nullptr, 0, 0};
+    uint32_t *d_runs = nullptr;
+    TileCodeView af{nullptr, 0, 0, nullptr, 0, 0};
 };
+
+// the tile-code view a kernel is handed (knob tile_rect = 0: without the free-run planes)
+static inline TileCodeView sbp_map_codes(const sbp_map *m) {
+    TileCodeView v = m->af;
+    if (!m->ctx->tune.tile_rect) v.runs = nullptr;
+    return v;
+}
 
 int32_t sbp_map_ensure_rows(sbp_map *map);
 int32_t sbp_map_ensure_allfree(sbp_map *map);

@@ -102,8 +102,29 @@ struct TileCodes {
     }
 };
 
+// Rectangle of tiles [tu0, tu1] x [tv0, tv1] (x tiles, y tiles, inside the map): true = every pixel
+// of it is free, proven by two words of the free-run planes (common.cuh:TileCodeView::runs; spans of
+// up to 15 x 16 tiles); false = not decided.  A Bresenham line never leaves the bounding box of its
+// end pixels, so a free box settles visible() = True for every map without walking the line.
+__device__ __forceinline__ bool tiles_rect_free(const TileCodeView &af, int tu0, int tu1, int tv0, int tv1) {
+    const int w = tu1 - tu0 + 1, h = tv1 - tv0 + 1;
+    if (af.runs == nullptr || w > 15 || h > 16) return false;
+    const int j = 31 - __clz(w);                               // two runs of 2^j tiles cover [tu0, tu1]
+    const uint32_t mask = ((1u << h) - 1u) << (tv0 & 15);
+    const uint32_t *__restrict__ row = af.runs + ((size_t)j * af.RK + (tv0 >> 4)) * af.RU;
+    const uint32_t a = __ldg(row + tu0), b = __ldg(row + tu1 + 1 - (1 << j));
+    return (a & b & mask) == mask;
+}
+
+template <bool PRETEST = true>
 __device__ __forceinline__ bool edge_free_tiles(const uint32_t *__restrict__ tiled, int SX, const TileCodeView &af,
                                                 int a1, int b1, uint32_t da, uint32_t adb, int ystep, bool steep) {
+    if (PRETEST) {
+        const int a2 = a1 + (int)da, b2 = b1 + ystep * (int)adb;
+        const int bl = (ystep > 0 ? b1 : b2) >> 3, bh = (ystep > 0 ? b2 : b1) >> 3;
+        if (tiles_rect_free(af, steep ? bl : a1 >> 3, steep ? bh : a2 >> 3, steep ? a1 >> 3 : bl, steep ? a2 >> 3 : bh))
+            return true;
+    }
     const uint32_t dd = da ? da : 1u;
     const uint32_t c = da ? da - 1u - (da >> 1) : 0u;
     // quotient estimate from below (2e-6 covers the roundings of the conversion, the reciprocal

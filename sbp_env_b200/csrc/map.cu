@@ -296,20 +296,57 @@ __global__ void k_tile_codes(MapView mv, int WW, int WH, int transposed, uint32_
     af[t] = out;
 }
 
+// Free-run planes over the tile codes: does an axis-aligned rectangle of tiles hold free pixels only?
+// Plane 0: bit b of word [k][u] = tile (u, 16 k + b) is all free (0 past the map's last tile row).
+__global__ void k_tile_runs0(const uint32_t *__restrict__ codes, int AW, int TX, int TY, int RK, uint32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)RK * TX) return;
+    const int u = (int)(t % TX), k = (int)(t / TX);
+    uint32_t w = 0;
+    for (int b = 0; b < 32; ++b) {
+        const int v = 16 * k + b;
+        if (v >= TY) break;
+        const uint32_t c = codes[(size_t)(v >> 2) * AW + (u >> 2)] >> (((v & 3) << 3) | ((u & 3) << 1));
+        w |= (c & 1u) << b;
+    }
+    out[t] = w;
+}
+
+// Plane j from plane j - 1: a run of 2^j tiles = two runs of 2^(j-1), the second `half` columns on.
+__global__ void k_tile_runs_next(const uint32_t *__restrict__ in, int TX, int RK, int half, uint32_t *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)RK * TX) return;
+    const int u = (int)(t % TX);
+    out[t] = u + half < TX ? (in[t] & in[t + half]) : 0u;
+}
+
 int32_t sbp_map_ensure_allfree(sbp_map *m) {
-    if (m->d_allfree) return SBP_OK;
+    if (m->af.runs) return SBP_OK;
     sbp_ctx *ctx = m->ctx;
     const int TX = m->view.SX * 2, TY = m->view.SY * 2;         // tiles
     const int WX = (TX + 3) / 4, WY = (TY + 3) / 4;             // words of 4 x 4 tiles
     const int64_t words = (int64_t)WX * WY;
-    SBP_CUDA(cudaMalloc(&m->d_allfree, (size_t)words * 2 * 4));
+    if (!m->d_allfree) SBP_CUDA(cudaMalloc(&m->d_allfree, (size_t)words * 2 * 4));
     k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, WX, WY, 0, m->d_allfree);
     k_tile_codes<<<(unsigned)((words + 255) / 256), 256, 0, ctx->stream>>>(m->view, WY, WX, 1, m->d_allfree + words);
     ctx->launches += 2;
     SBP_CUDA(cudaGetLastError());
+    const int RK = (TY + 15) / 16;
+    const int64_t rwords = (int64_t)RK * TX;
+    if (!m->d_runs) SBP_CUDA(cudaMalloc(&m->d_runs, (size_t)rwords * 4 * 4));
+    const unsigned rb = (unsigned)((rwords + 255) / 256);
+    k_tile_runs0<<<rb, 256, 0, ctx->stream>>>(m->d_allfree, WX, TX, TY, RK, m->d_runs);
+    for (int j = 1; j < 4; ++j)
+        k_tile_runs_next<<<rb, 256, 0, ctx->stream>>>(m->d_runs + (size_t)(j - 1) * rwords, TX, RK, 1 << (j - 1),
+                                                      m->d_runs + (size_t)j * rwords);
+    ctx->launches += 4;
+    SBP_CUDA(cudaGetLastError());
     m->af.words = m->d_allfree;
     m->af.AW = WX;
     m->af.AH = WY;
+    m->af.runs = m->d_runs;
+    m->af.RU = TX;
+    m->af.RK = RK;
     return SBP_OK;
 }
 
@@ -320,6 +357,7 @@ extern "C" int32_t sbp_map_destroy(sbp_map *map) {
     if (map->d_words) cudaFree(map->d_words);
     if (map->d_rows) cudaFree(map->d_rows);
     if (map->d_allfree) cudaFree(map->d_allfree);
+    if (map->d_runs) cudaFree(map->d_runs);
     delete map;
     return SBP_OK;
 }

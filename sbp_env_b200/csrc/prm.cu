@@ -397,6 +397,23 @@ k_prm_walk(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__r
 
 __global__ void k_copy_order(const int32_t *__restrict__ ids, int64_t p0, int64_t count, int32_t *__restrict__ order_out,
                              int multicast);
+
+// A finished slice of the rank's rows, device staging -> every rank's copy through the NVSwitch
+// multicast mapping, 16 bytes per store (src / dst 16-byte aligned, `words` a multiple of 4 except
+// for the tail).
+__global__ void __launch_bounds__(256)
+k_mc_copy(const int32_t *__restrict__ src, int32_t *__restrict__ dst_mc, int64_t words) {
+    const int64_t quads = words >> 2;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < quads; t += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = *reinterpret_cast<const float4 *>(src + 4 * t);
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst_mc + 4 * t), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    for (int64_t i = (quads << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words;
+         i += (int64_t)gridDim.x * blockDim.x)
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst_mc + i), "f"(__int_as_float(src[i])) : "memory");
+}
+
 __global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int64_t n, double2 *__restrict__ X,
                            const int32_t *__restrict__ pending);
 
@@ -462,10 +479,16 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
                 ed.da = (uint16_t)(a2 - a1); ed.adb = (uint16_t)abs(b2 - b1);
                 ed.slot = (uint16_t)sl;
                 ed.flags = (uint16_t)((steep ? 1 : 0) | (b1 < b2 ? 2 : 0));
-                s_edge[sl] = ed;
-                const int nch = (a2 >> 3) - (a1 >> 3) + 1;
-                bin = nch < PW_BINS ? nch - 1 : PW_BINS - 1;
-                atomicAdd(&s_cnt[bin], 1);
+                // the bounding box of the end pixels in tiles: all free -> visible without a walk
+                const int xl = min(x1, qxi) >> 3, xh = max(x1, qxi) >> 3, yl = min(y1, qyi) >> 3, yh = max(y1, qyi) >> 3;
+                if (tiles_rect_free(a.af, xl, xh, yl, yh)) {
+                    code |= 1;
+                } else {
+                    s_edge[sl] = ed;
+                    const int nch = (a2 >> 3) - (a1 >> 3) + 1;
+                    bin = nch < PW_BINS ? nch - 1 : PW_BINS - 1;
+                    atomicAdd(&s_cnt[bin], 1);
+                }
             } else {
                 code |= prm_edge_slow(a.tiled, pp.x, pp.y, q.x, q.y, &myflag) ? 1 : 0;   // wrap-around / out of range
             }
@@ -493,7 +516,7 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
     const int total = s_total;
     for (int i = tid; i < total; i += PW_ROWS) {
         const PwEdge ed = s_edge[s_idx[i]];
-        const bool fr = edge_free_tiles(a.tiled.words, a.tiled.SX, a.af, (int)ed.a1, (int)ed.b1, ed.da, ed.adb,
+        const bool fr = edge_free_tiles<false>(a.tiled.words, a.tiled.SX, a.af, (int)ed.a1, (int)ed.b1, ed.da, ed.adb,
                                         (ed.flags & 2) ? 1 : -1, (ed.flags & 1) != 0);
         if (fr) s_code[ed.slot] |= 1;
     }
@@ -559,12 +582,20 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
     // while the next slices are computed -- 40 MB take 0.70 ms over PCIe against 0.5 ms of compute,
     // so the step costs the copy plus one slice instead of compute plus copy (zero-copy stores from
     // the walk kernel reached only ~45 GB/s and 1.14 ms for the call; staged: 0.8x ms).
+    // The same staging serves the multicast mapping (several ranks): stores through the switch issued
+    // by the walk kernel itself made it wait for NVLink (89 us for a rank's 125 000 rows at N = 8 where
+    // the walk alone takes 34); instead the walk runs in slices into the staging buffer and a copy
+    // kernel on the second stream pushes every finished slice through the mapping meanwhile.
     int slices = ctx->tune.prm_slices;
     const bool stage_host = args->host_out && args->out.packed && args->out.sorted_rows && ctx->tune.time_kernels == 0;
+    const bool stage_mc = args->out.packed_mc && args->out.packed && args->out.sorted_rows &&
+                          ctx->tune.time_kernels == 0 && ctx->tune.prm_mc_stage && count >= 32768 &&
+                          (((p0 * kq) & 3) == 0) && ((reinterpret_cast<uintptr_t>(args->out.packed) & 15) == 0);
     if (stage_host) slices = 8;
-    if (slices < 1 || ctx->tune.time_kernels != 0 || count < 65536) slices = 1;
+    if (stage_mc) slices = 4;
+    if (slices < 1 || ctx->tune.time_kernels != 0 || (count < 65536 && !stage_mc)) slices = 1;
     if (slices > 16) slices = 16;
-    if (slices > 1 || stage_host || (args->order_out && args->order_host)) {
+    if (slices > 1 || stage_host || stage_mc || (args->order_out && args->order_host)) {
         if (!ctx->aux_stream) SBP_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
         while ((int)ctx->aux_events.size() < slices + 1) {
             cudaEvent_t e;
@@ -595,11 +626,12 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
     }
     PrmFusedArgs wargs = *args;
     int32_t *host_packed = nullptr;
-    if (stage_host) {
+    if (stage_host || stage_mc) {
         void *stg = nullptr;
         if ((rc = sbp_ctx_scratch(ctx, 19, (size_t)grid.n * kq * sizeof(int32_t), &stg))) return rc;
-        host_packed = args->out.packed;
+        host_packed = args->out.packed;                       // (stage_mc: the multicast address)
         wargs.out.packed = (int32_t *)stg;                    // [n][kq] like the caller's buffer
+        wargs.out.packed_mc = 0;
     }
     if (kq > 20) { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
     const int64_t per = ((count + slices - 1) / slices + PRM_TPB - 1) / PRM_TPB * PRM_TPB;   // whole CTAs (and warps)
@@ -608,9 +640,14 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         if (cnt <= 0) break;
         const unsigned blocks = (unsigned)((cnt + PRM_TPB - 1) / PRM_TPB);
         int32_t *cand = (int32_t *)cbuf + off * kq;
+        // (multicast staging: the kNN of ALL the rank's rows in one launch -- a rank's share is too
+        // small to be cut further --, only the walk is sliced)
+        const int64_t koff = stage_mc ? 0 : off, kcnt = stage_mc ? count : cnt;
+        const unsigned kblocks = (unsigned)((kcnt + PRM_TPB - 1) / PRM_TPB);
+        int32_t *kcand = (int32_t *)cbuf + koff * kq;
 #define PRM_KNN(KK)                                                                                          \
-    k_prm_knn<KK><<<blocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + off, cnt, seed2, done, pending, cand)
-        {
+    k_prm_knn<KK><<<kblocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + koff, kcnt, seed2, done, pending, kcand)
+        if (!stage_mc || sl == 0) {
             KernelTimer timer(ctx, 2);
             if (kq <= 4) PRM_KNN(4);
             else if (kq <= 8) PRM_KNN(8);
@@ -620,7 +657,7 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         }
 #undef PRM_KNN
         cudaStream_t ws = ctx->stream;
-        if (slices > 1 && !stage_host) {
+        if (slices > 1 && !stage_host && !stage_mc) {
             SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
             SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
             ws = ctx->aux_stream;
@@ -635,18 +672,24 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
                 k_prm_walk<<<blocks, PRM_TPB, 0, ws>>>(grid, kq, p0 + off, cnt, done, cand, wargs);
             }
         }
-        if (stage_host) {
-            // this slice's block of rows: device staging -> the caller's host buffer, on the copy stream
+        if (stage_host || stage_mc) {
+            // this slice's block of rows: device staging -> the caller's host buffer (DMA engine) or the
+            // ranks' buffers (multicast stores), on the second stream
             SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
             SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
             const int64_t r0 = (p0 + off) * kq;
-            SBP_CUDA(cudaMemcpyAsync(host_packed + r0, wargs.out.packed + r0, (size_t)cnt * kq * sizeof(int32_t),
-                                     cudaMemcpyDeviceToHost, ctx->aux_stream));
+            if (stage_host) {
+                SBP_CUDA(cudaMemcpyAsync(host_packed + r0, wargs.out.packed + r0, (size_t)cnt * kq * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, ctx->aux_stream));
+            } else {
+                k_mc_copy<<<ctx->sm_count, 256, 0, ctx->aux_stream>>>(wargs.out.packed + r0, host_packed + r0, cnt * kq);
+                ctx->launches++;
+            }
         }
         ctx->launches += 2;
     }
     (void)K;
-    if (slices > 1 || stage_host || (args->order_out && args->order_host)) {   // join: everything behind sees all rows
+    if (slices > 1 || stage_host || stage_mc || (args->order_out && args->order_host)) {   // join: everything behind sees all rows
         SBP_CUDA(cudaEventRecord(ctx->aux_events[slices], ctx->aux_stream));
         SBP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[slices], 0));
     }
@@ -748,7 +791,7 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
     }
     // this part's run of the cell-sorted order (balanced like distributed.shard_range)
     const int64_t base = n / parts, rem = n % parts;
-    PrmFusedArgs fa{map->view, map->af,
+    PrmFusedArgs fa{map->view, sbp_map_codes(map),
                     PrmOut{nbr_out, vis, packed, packed_multicast, sorted_rows}, flags,
                     nodes->d_soa, nodes->capacity, (double2 *)xbuf, 0, nullptr, 0, 0, 0};
     if (packed && !packed_multicast) {
@@ -787,7 +830,7 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
         const int64_t vb = (rp.count + PRM_TPB - 1) / PRM_TPB, vcap = (int64_t)ctx->sm_count * 16;
         // (after the fused kernels this one only has the rows they left: a capped grid that loops)
         k_prm_visible2d<<<(unsigned)(rp.fused_ran && vb > vcap ? vcap : vb), PRM_TPB, 0, ctx->stream>>>(
-            map->view, map->af, nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
+            map->view, sbp_map_codes(map), nodes->d_soa, nodes->capacity, n, (const int64_t *)ibuf, K, rp.ids,
             rp.p0, rp.count, rp.fused_ran ? rp.done : nullptr, rp.fused_ran ? rp.pending : nullptr, fa.out, flags);
     }
     ctx->launches++;

@@ -180,13 +180,15 @@ def test_synthetic_large_grid_l2_path(sg):
     want = om.visible2d(P, Q)
     assert 0.02 < want.mean() < 0.9
     try:
-        for tiles in (1, 0):
+        for tiles, rect in ((1, 1), (1, 0), (0, 1)):
             sg.runtime.tune("visible_tiles", tiles)
-            assert np.array_equal(cc.visible_batch(P, Q), want), tiles
+            sg.runtime.tune("tile_rect", rect)       # (free-run planes: bounding box of tiles all free)
+            assert np.array_equal(cc.visible_batch(P, Q), want), (tiles, rect)
             dP, dQ = torch.from_numpy(P).cuda(), torch.from_numpy(Q).cuda()
-            assert np.array_equal(cc.visible_batch(dP, dQ).cpu().numpy(), want), tiles
+            assert np.array_equal(cc.visible_batch(dP, dQ).cpu().numpy(), want), (tiles, rect)
     finally:
         sg.runtime.tune("visible_tiles", 1)
+        sg.runtime.tune("tile_rect", 1)
     assert np.array_equal(cc.visible_batch(Q, P), want)                   # direction symmetry
     assert np.array_equal(cc.feasible_batch(P), om.feasible2d(P))
 

@@ -166,10 +166,22 @@ def test_cfg5_reduced_scale_equals_oracle(sg):
     om = orc.Map(mz.raster_host())
     k = 10
     want_nbr, want_vis = oracle_connect(om, nodes, k)
-    nbr, vis = sg.prm_connect_knn(cc, tree, k)
-    assert np.array_equal(nbr.cpu().numpy(), want_nbr)
-    assert np.array_equal(vis.cpu().numpy(), want_vis)
+    try:
+        # both walk kernels, with and without the free-run planes (bounding box of tiles all free)
+        for rect, srt in ((1, 1), (0, 1), (1, 0), (0, 0)):
+            sg.runtime.tune("tile_rect", rect)
+            sg.runtime.tune("prm_walk_sorted", srt)
+            nbr, vis = sg.prm_connect_knn(cc, tree, k)
+            assert np.array_equal(nbr.cpu().numpy(), want_nbr), (rect, srt)
+            assert np.array_equal(vis.cpu().numpy(), want_vis), (rect, srt)
+    finally:
+        sg.runtime.tune("tile_rect", 1)
+        sg.runtime.tune("prm_walk_sorted", 1)
     assert 0.5 < float(vis.float().mean()) < 0.99
+    # the generic batched entry on the same candidate edges (k_visible2d_tiles)
+    Pn = nodes[want_nbr.reshape(-1)]
+    Qn = np.repeat(nodes, k, axis=0)
+    assert np.array_equal(cc.visible_batch(Pn, Qn), want_vis.reshape(-1).astype(bool))
     # the analytic occupancy predicate, the device raster and the host raster agree
     P = np.random.default_rng(0).random((200000, 2)) * [mz.W, mz.H]
     assert np.array_equal(cc.feasible_batch(P), mz.free_points(P))
