@@ -86,6 +86,7 @@ struct sbp_tuning {
     int force_global = 0;         // 1 = never stage the map in shared memory
     int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
     int tile_rect = 1;            // tile walks: settle an edge whose bounding box of tiles is all free from the run planes
+    int prm_fuse = 1;             // sbp_prm_connect2d: the kNN kernel settles edges with an all-free bounding box and writes the rows (0: separate walk kernel over all edges)
     int prm_mc_stage = 0;         // sbp_prm_connect2d: multicast outputs leave through a staging buffer + copy kernel
     int prm_walk_sorted = 1;      // sbp_prm_connect2d: walk the CTA's edges sorted by length (0: a row's edges in order)
     int prm_slices = 1;           // sbp_prm_connect2d: row slices whose walk overlaps the next slice's kNN
@@ -167,6 +168,7 @@ struct KnnRowsPart {
     const uint8_t *done = nullptr;   // out (fused_ran): per node, 1 = row settled by the fused kernel
     const int32_t *pending = nullptr;  // out (fused_ran): device counter of the rows it left
 };
+#define GRID_HDR_INTS 20             // ints ahead of the cell counts: pending, band[2], spare, 16 slice counters (prm.cu)
 #define PRM_FUSED_KMAX 21            // list lengths (k + 1) the fused kernel is instantiated for
 // the cell grid as the fused kernel sees it (knn.cu builds it, prm.cu walks it)
 struct CellGridView {

@@ -111,8 +111,8 @@ __device__ __forceinline__ bool tiles_rect_free(const TileCodeView &af, int tu0,
     if (af.runs == nullptr || w > 15 || h > 16) return false;
     const int j = 31 - __clz(w);                               // two runs of 2^j tiles cover [tu0, tu1]
     const uint32_t mask = ((1u << h) - 1u) << (tv0 & 15);
-    const uint32_t *__restrict__ row = af.runs + ((size_t)j * af.RK + (tv0 >> 4)) * af.RU;
-    const uint32_t a = __ldg(row + tu0), b = __ldg(row + tu1 + 1 - (1 << j));
+    const uint32_t row = ((uint32_t)j * (uint32_t)af.RK + ((uint32_t)tv0 >> 4)) * (uint32_t)af.RU;   // (< 2^32 words)
+    const uint32_t a = __ldg(af.runs + (row + (uint32_t)tu0)), b = __ldg(af.runs + (row + (uint32_t)(tu1 + 1) - (1u << j)));
     return (a & b & mask) == mask;
 }
 

@@ -919,7 +919,7 @@ struct GridBuildArgs {
     double *b4;               // out: bounding box
     double *partial;          // [gridDim.x][4]
     int G;
-    int32_t *hdr4;            // [0] pending (zeroed), [1..2] band (out)
+    int32_t *hdr4;            // [0] pending (zeroed), [1..2] band (out), [4..19] per-slice counters of prm.cu (zeroed)
     int32_t *cells, *start, *cursor, *ids;
     double2 *pts;
     uint8_t *done;
@@ -951,7 +951,7 @@ k_prm_grid_build(GridBuildArgs a) {
             a.done[t] = 1;
         }
         for (int64_t i = gtid; i < L; i += gsz) a.cells[i] = 0;
-        if (gtid < 4) a.hdr4[gtid] = 0;
+        if (gtid < GRID_HDR_INTS) a.hdr4[gtid] = 0;
         for (int o = 16; o > 0; o >>= 1) {
             mnx = fmin(mnx, __shfl_down_sync(FULL, mnx, o)); mxx = fmax(mxx, __shfl_down_sync(FULL, mxx, o));
             mny = fmin(mny, __shfl_down_sync(FULL, mny, o)); mxy = fmax(mxy, __shfl_down_sync(FULL, mxy, o));
@@ -1590,15 +1590,15 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
         if (G < 1) G = 1;
         const int64_t L = (int64_t)G * G;
         void *cellbuf = nullptr, *seedbuf = nullptr;
-        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][pending: 4 ints][cells L][start L+1][cursor L][ids n][tile sums 1024]
+        // [bounds: 4 + 4*BOUNDS_BLOCKS doubles][pending + counters: GRID_HDR_INTS ints][cells L][start L+1][cursor L][ids n][tile sums 1024]
         const size_t hdr = (4 + 4 * BOUNDS_BLOCKS) * sizeof(double);
-        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(4 + 3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
+        rc = sbp_ctx_scratch(ctx, 5, hdr + (size_t)(GRID_HDR_INTS + 3 * L + 1 + n + 1024) * sizeof(int32_t), &cellbuf);
         if (rc) return rc;
         rc = sbp_ctx_scratch(ctx, 6, (size_t)m * sizeof(double), &seedbuf);
         if (rc) return rc;
         double *b4 = (double *)cellbuf;
         pending_all = (int32_t *)((char *)cellbuf + hdr);        // zeroed with the cell counts
-        int32_t *cells = pending_all + 4, *start = cells + L, *cursor = start + L + 1,
+        int32_t *cells = pending_all + GRID_HDR_INTS, *start = cells + L, *cursor = start + L + 1,
                 *ids = cursor + L, *tsums = ids + n;
         const bool fused_rows = part && part->fused && K <= PRM_FUSED_KMAX && ctx->tune.knn_filter &&
                                 ctx->tune.knn_cells;
@@ -1632,7 +1632,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
                                                  ctx->stream));
             ctx->launches++;
         } else {
-        SBP_CUDA(cudaMemsetAsync(pending_all, 0, (size_t)(L + 4) * sizeof(int32_t), ctx->stream));
+        SBP_CUDA(cudaMemsetAsync(pending_all, 0, (size_t)(L + GRID_HDR_INTS) * sizeof(int32_t), ctx->stream));
         double *partial = b4 + 4;                                  // needs 4 * BOUNDS_BLOCKS doubles
         k_bounds2d_partial<<<BOUNDS_BLOCKS, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial);
         k_cell_hist<<<hb, 256, 0, ctx->stream>>>(s->d_soa, s->capacity, n, partial, BOUNDS_BLOCKS, b4, G,

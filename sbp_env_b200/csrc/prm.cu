@@ -39,7 +39,9 @@
 #include "device_fns.cuh"
 
 #define PRM_KMAX 31          // k <= 31 (the kNN lists hold k + 1 <= 32 entries)
+#ifndef PRM_TPB
 #define PRM_TPB 128
+#endif
 
 struct PrmOut {
     int64_t *nbr;            // [n][k] neighbour index (nullable)
@@ -83,6 +85,7 @@ __device__ __forceinline__ void prm_store_packed(const PrmOut &out, int64_t e, i
 
 // visible(m_g.pos, v.pos) of one candidate: start = neighbour p, end = row node q (the 2-D line is
 // direction symmetric, but the argument order is the reference's)
+template <bool PRETEST = true>
 __device__ __forceinline__ bool prm_edge(const MapView &tiled, const TileCodeView &af, double px, double py,
                                          double qx, double qy, int &flag) {
     const double W = (double)tiled.W, H = (double)tiled.H;
@@ -94,11 +97,21 @@ __device__ __forceinline__ bool prm_edge(const MapView &tiled, const TileCodeVie
         int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;                  // :182-184
         int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
         if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }   // :188-191
-        return edge_free_tiles(tiled.words, tiled.SX, af, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
-                               b1 < b2 ? 1 : -1, steep);
+        return edge_free_tiles<PRETEST>(tiled.words, tiled.SX, af, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
+                                        b1 < b2 ? 1 : -1, steep);
     }
     return prm_edge_slow(tiled, px, py, qx, qy, &flag);
 }
+
+#define PW_ROWS 64
+#define PW_BINS 32
+struct PwEdge {                // 12 bytes: all coordinates of a fast-path edge lie in [0, 65536)
+    uint16_t a1, b1;
+    uint16_t da, adb;
+    uint16_t slot;           // col * PW_ROWS + row
+    uint16_t flags;          // bit 0 steep, bit 1 minor step +1
+};
+
 
 // ------------------------------------------- neighbour list on float keys -----
 // K nearest by (d^2, node index), the row itself excluded.  The list is sorted on kf =
@@ -173,7 +186,10 @@ struct NearList {
             kf[0] = r[0] ? kf[0] : key;
             e[0] = r[0] ? e[0] : pos;
         }
-        // everything whose key is <= the K-th key may still enter: d^2 < next fp32 above that key
+    }
+    // everything whose key is <= the K-th key may still enter: d^2 < next fp32 above that key
+    // (after a step's insertions: the step's candidates were filtered with the bound before it)
+    __device__ __forceinline__ void update_hi() {
         const float kth = kf[K - 1];
         hi = kth < INFINITY ? (double)__uint_as_float(__float_as_uint(kth) + 1u) : INFINITY;
     }
@@ -240,6 +256,7 @@ __device__ __forceinline__ void prm_scan_rows(const double2 *__restrict__ pts, c
                         L.insert(kk, base + u, qx, qy, pts, ids);
                     }
                 }
+                if (rounds) L.update_hi();
             }
         }
     }
@@ -247,10 +264,15 @@ __device__ __forceinline__ void prm_scan_rows(const double2 *__restrict__ pts, c
 
 // kq = candidates per row; K = list length >= kq.  cand [count][kq]: cell-sorted positions of the
 // row's candidates in the reference's order (rows with done = 0: unspecified).
-template <int K>
+// FUSE: the kernel also decides the row's candidate edges and writes the output rows itself.  An edge
+// whose bounding box of tiles is all free is visible (two words of the free-run planes,
+// device_fns.cuh:tiles_rect_free -- most edges of a roadmap); the others (near walls, most of them
+// blocked) are collected per CTA in shared memory and walked side by side over its threads (two-level
+// walk on the tile codes).  No candidate list in global memory, no second pass over all edges.
+template <int K, bool FUSE>
 __global__ void __launch_bounds__(PRM_TPB)
 k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t count, double *__restrict__ seed2,
-          uint8_t *__restrict__ done, int32_t *__restrict__ pending, int32_t *__restrict__ cand) {
+          uint8_t *__restrict__ done, int32_t *__restrict__ pending, int32_t *__restrict__ cand, PrmFusedArgs a) {
     const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x;
     const bool live = slot < count;
     const int64_t p = p0 + (live ? slot : 0);
@@ -322,10 +344,164 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
         seed2[v] = full ? L.hi * (1.0 + 1e-9) + 1e-300 : INFINITY;
         done[v] = handled ? 1 : 0;
         if (!handled) atomicAdd(pending, 1);                      // the exact path has work
-        if (handled) {
+        if (handled && !FUSE) {
 #pragma unroll
             for (int t = 0; t < K; ++t)
                 if (t < kq) cand[slot * kq + t] = L.e[t];
+        }
+    }
+    if (FUSE) {
+        __shared__ __align__(16) int32_t s_out[PRM_TPB * K];      // [row of the CTA][kq]: the output block
+        __shared__ uint32_t s_xy[PRM_TPB * K];                    // neighbour pixel x | y << 16 of every edge
+        __shared__ uint32_t s_q[PRM_TPB];                         // row pixel x | y << 16
+        __shared__ uint16_t s_list[PRM_TPB * K], s_list2[PRM_TPB * K];   // edges left after phase A / phase B
+        __shared__ int s_wsum[PRM_TPB / 32], s_n2;
+        const unsigned FULL = 0xffffffffu;
+        const PrmOut &out = a.out;
+        const bool work = live && handled;
+        const bool stage = out.sorted_rows && out.packed;
+        const int tid = threadIdx.x;
+        if (tid == 0) s_n2 = 0;
+        const double W = (double)a.tiled.W, H = (double)a.tiled.H;
+        const bool q_in = q.x >= 0.0 && q.x < W && q.y >= 0.0 && q.y < H;
+        const int qxi = q_in ? __double2int_rz(q.x) : 0, qyi = q_in ? __double2int_rz(q.y) : 0;
+        s_q[tid] = (uint32_t)qxi | ((uint32_t)qyi << 16);
+        int myflag = 0;
+        // ---- phase A: all edges of the row; bounding box of tiles all free -> visible
+        unsigned walk = 0;
+        if (work) {
+#pragma unroll
+            for (int t = 0; t < K; ++t) {
+                if (t < kq) {
+                    const int32_t e = L.e[t];
+                    const double2 pp = g.pts[e];
+                    int32_t code = (g.ids[e] + 1) << 1;
+                    if (q_in && pp.x >= 0.0 && pp.x < W && pp.y >= 0.0 && pp.y < H) {
+                        // start = neighbour, end = row node (:173-174)
+                        const int x1 = __double2int_rz(pp.x), y1 = __double2int_rz(pp.y);
+                        s_xy[tid * kq + t] = (uint32_t)x1 | ((uint32_t)y1 << 16);
+                        if (tiles_rect_free(a.af, min(x1, qxi) >> 3, max(x1, qxi) >> 3, min(y1, qyi) >> 3, max(y1, qyi) >> 3))
+                            code |= 1;
+                        else
+                            walk |= 1u << t;
+                    } else {
+                        code |= prm_edge_slow(a.tiled, pp.x, pp.y, q.x, q.y, &myflag) ? 1 : 0;   // wrap-around / out of range
+                    }
+                    s_out[tid * kq + t] = code;
+                }
+            }
+        }
+        // the undecided edges (near walls; most are blocked) as one list of the CTA (warp-local lists were
+        // measured: no barriers, but a walk round per warp instead of one or two per CTA: 0.345 instead of 0.330 ms)
+        int total;
+        {
+            const int mine = __popc(walk);
+            int inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, inc, o); if ((tid & 31) >= o) inc += u; }
+            if ((tid & 31) == 31) s_wsum[tid >> 5] = inc;
+            __syncthreads();
+            int base = inc - mine;
+            total = 0;
+#pragma unroll
+            for (int w = 0; w < PRM_TPB / 32; ++w) { const int c = s_wsum[w]; base += w < (tid >> 5) ? c : 0; total += c; }
+            while (walk) {
+                const int t = __ffs(walk) - 1;
+                walk &= walk - 1;
+                s_list[base++] = (uint16_t)(tid * kq + t);
+            }
+        }
+        __syncthreads();
+        const uint32_t inv_kq = (1u << 20) / (uint32_t)kq + 1u;    // slot / kq = (slot * inv_kq) >> 20 for slot < 4096, kq <= 31
+        // ---- phase B: probes.  Line pixels 16 apart along the major axis: one of them in an all-blocked
+        // tile (or a blocked pixel of a mixed one) settles the edge as blocked -- a line that crosses a wall
+        // of that thickness cannot miss them; what is left goes to the walk.
+        for (int i = tid; i < total; i += PRM_TPB) {
+            const int sl = s_list[i];
+            const uint32_t qq = s_q[((uint32_t)sl * inv_kq) >> 20], xy = s_xy[sl];
+            const int x1 = (int)(xy & 0xffffu), y1 = (int)(xy >> 16), x2 = (int)(qq & 0xffffu), y2 = (int)(qq >> 16);
+            const int dx = x2 - x1, dy = y2 - y1;
+            const bool steep = abs(dy) > abs(dx);                        // :179-191
+            int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+            int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+            if (a1 > a2) { int sw = a1; a1 = a2; a2 = sw; sw = b1; b1 = b2; b2 = sw; }
+            const uint32_t da = (uint32_t)(a2 - a1), adb = (uint32_t)abs(b2 - b1);
+            const int ystep = b1 < b2 ? 1 : -1;
+            const uint32_t dd = da ? da : 1u, c = da ? da - 1u - (da >> 1) : 0u;
+            const float rcp = __fdividef(0.999998f, (float)dd);
+            bool blocked = false;
+            for (uint32_t pi = 8; pi < da && !blocked; pi += 16) {
+                const uint32_t num = pi * adb + c;
+                uint32_t qe = (uint32_t)(__uint2float_rz(num) * rcp);
+                if (num - qe * dd >= dd) ++qe;
+                const int pa = a1 + (int)pi, pb = b1 + ystep * (int)qe;
+                const int px = steep ? pb : pa, py = steep ? pa : pb;
+                const uint32_t word = __ldg(a.af.words + ((uint32_t)py >> 5) * (uint32_t)a.af.AW + ((uint32_t)px >> 5));
+                const uint32_t cd = (word >> (((((uint32_t)py >> 3) & 3u) << 3) | ((((uint32_t)px >> 3) & 3u) << 1))) & 3u;
+                blocked = cd == 2u || (cd == 0u && !map_free<true>(a.tiled.words, a.tiled.SX, px, py));
+            }
+            if (!blocked) s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)sl;
+        }
+        __syncthreads();
+        // ---- phase C: the two-level walk of the rest, side by side over the threads
+        const int total2 = s_n2;
+        for (int i = tid; i < total2; i += PRM_TPB) {
+            const int sl = s_list2[i];
+            const uint32_t qq = s_q[((uint32_t)sl * inv_kq) >> 20], xy = s_xy[sl];
+            const int x1 = (int)(xy & 0xffffu), y1 = (int)(xy >> 16), x2 = (int)(qq & 0xffffu), y2 = (int)(qq >> 16);
+            const int dx = x2 - x1, dy = y2 - y1;
+            const bool steep = abs(dy) > abs(dx);
+            int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+            int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+            if (a1 > a2) { int sw = a1; a1 = a2; a2 = sw; sw = b1; b1 = b2; b2 = sw; }
+            if (edge_free_tiles<false>(a.tiled.words, a.tiled.SX, a.af, a1, b1, (uint32_t)(a2 - a1), (uint32_t)abs(b2 - b1),
+                                       b1 < b2 ? 1 : -1, steep))
+                s_out[sl] |= 1;
+        }
+        __syncthreads();
+        if (myflag && a.flags) atomicOr(a.flags, myflag);
+        if (work && (!stage || out.nbr || out.vis)) {
+            const int64_t orow = out.sorted_rows ? p : (int64_t)v;
+            for (int t = 0; t < kq; ++t) {
+                const int32_t code = s_out[tid * kq + t];
+                const int64_t o = orow * kq + t;
+                if (!stage && out.packed) prm_store_packed(out, o, code);
+                if (out.nbr) out.nbr[o] = (int64_t)(code >> 1) - 1;
+                if (out.vis) out.vis[o] = (uint8_t)(code & 1);
+            }
+        }
+        if (stage) {
+            // the warp's 32 rows are one contiguous block of 32 * kq codes, in shared memory as in the output
+            // (rows not settled here are written later by the exact path)
+            const unsigned okmask = __ballot_sync(FULL, work);
+            const int lane = tid & 31, wbase = tid & ~31;
+            const int64_t slot0 = (int64_t)blockIdx.x * PRM_TPB + wbase;
+            if (slot0 < count) {
+                const int rows = (int)(count - slot0 < 32 ? count - slot0 : 32);
+                const int64_t base = (p0 + slot0) * kq;
+                const int32_t *src = s_out + wbase * kq;                  // (32 * kq * 4 bytes per warp: 16-byte aligned)
+                int32_t *dst = out.packed + base;
+                if (okmask == FULL && rows == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    const int4 *src4 = reinterpret_cast<const int4 *>(src);
+                    for (int t = lane; t < 8 * kq; t += 32) {
+                        const int4 c = src4[t];
+                        if (out.packed_mc)      // through the switch in 16-byte pieces
+                            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * t),
+                                         "f"(__int_as_float(c.x)), "f"(__int_as_float(c.y)), "f"(__int_as_float(c.z)),
+                                         "f"(__int_as_float(c.w)) : "memory");
+                        else
+                            reinterpret_cast<int4 *>(dst)[t] = c;
+                    }
+                } else {
+                    int row = 0, col = lane;                             // word i = row * kq + col, i = lane, lane + 32, ...
+                    while (col >= kq) { col -= kq; ++row; }
+                    for (int i = lane; i < rows * kq; i += 32) {
+                        if ((okmask >> row) & 1u) prm_store_packed(out, base + i, src[i]);
+                        col += 32;
+                        while (col >= kq) { col -= kq; ++row; }
+                    }
+                }
+            }
         }
     }
 }
@@ -423,22 +599,13 @@ __global__ void k_rows_aos(const double *__restrict__ soa, int64_t capacity, int
 // edges (thread = row), counting-sorts them in shared memory by their number of 8-pixel chunks,
 // and the threads then walk the sorted list: the 32 edges of a warp step have the same length.
 // Results return to their (row, column) slot in shared memory; output as in k_prm_walk.
-#define PW_ROWS 64
-#define PW_BINS 32
-struct PwEdge {                // 12 bytes: all coordinates of a fast-path edge lie in [0, 65536)
-    uint16_t a1, b1;
-    uint16_t da, adb;
-    uint16_t slot;           // col * PW_ROWS + row
-    uint16_t flags;          // bit 0 steep, bit 1 minor step +1
-};
-
 __global__ void __launch_bounds__(PW_ROWS)
 k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8_t *__restrict__ done,
                   const int32_t *__restrict__ cand, PrmFusedArgs a) {
     extern __shared__ __align__(16) unsigned char pw_smem[];
-    PwEdge *s_edge = reinterpret_cast<PwEdge *>(pw_smem);                              // [kq * PW_ROWS]
-    int32_t *s_code = reinterpret_cast<int32_t *>(pw_smem + (size_t)kq * PW_ROWS * sizeof(PwEdge));   // [kq][PW_ROWS]
-    uint16_t *s_idx = reinterpret_cast<uint16_t *>(s_code + kq * PW_ROWS);            // [kq * PW_ROWS]
+    int32_t *s_code = reinterpret_cast<int32_t *>(pw_smem);                            // [PW_ROWS][kq]: the output block
+    PwEdge *s_edge = reinterpret_cast<PwEdge *>(s_code + kq * PW_ROWS);                // [PW_ROWS * kq]
+    uint16_t *s_idx = reinterpret_cast<uint16_t *>(s_edge + kq * PW_ROWS);             // [PW_ROWS * kq]
     __shared__ int s_cnt[PW_BINS], s_off[PW_BINS], s_total;
     const int tid = threadIdx.x;
     const int64_t slot = (int64_t)blockIdx.x * PW_ROWS + tid;
@@ -450,40 +617,51 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
     const PrmOut &out = a.out;
     if (tid < PW_BINS) s_cnt[tid] = 0;
     __syncthreads();
-    // ---- phase 1: set up the row's edges, count them per length bin
+    // ---- phase 1: set up the row's edges; an edge whose bounding box of tiles is all free is decided
+    // here (two words of the free-run planes), the others are counted per length bin.  The loads of
+    // the next columns are issued before the current one is worked on (candidate two columns ahead,
+    // its pose one ahead): one memory round trip per column instead of three.
     const double W = (double)a.tiled.W, H = (double)a.tiled.H;
     const bool q_in = q.x >= 0.0 && q.x < W && q.y >= 0.0 && q.y < H;
     const int qxi = q_in ? __double2int_rz(q.x) : 0, qyi = q_in ? __double2int_rz(q.y) : 0;
     int myflag = 0;
-    unsigned binbits_lo = 0, binbits_hi = 0;          // 5 bits per column would not fit: bins live in s_idx
-    (void)binbits_lo; (void)binbits_hi;
     if (work) {
+        const int32_t *__restrict__ crow = cand + slot * kq;
+        int32_t e_ahead = kq > 1 ? crow[1] : 0;
+        int32_t nb_next;
+        double2 pp_next;
+        {
+            const int32_t e0 = crow[0];
+            nb_next = g.ids[e0];
+            pp_next = g.pts[e0];
+        }
 #pragma unroll 1
         for (int col = 0; col < kq; ++col) {
-            const int32_t e = cand[slot * kq + col];
-            const int32_t nb = g.ids[e];
-            const double2 pp = g.pts[e];
-            const int sl = col * PW_ROWS + tid;
+            const int32_t nb = nb_next;
+            const double2 pp = pp_next;
+            if (col + 1 < kq) { nb_next = g.ids[e_ahead]; pp_next = g.pts[e_ahead]; }
+            if (col + 2 < kq) e_ahead = crow[col + 2];
+            const int sl = tid * kq + col;
             int32_t code = (nb + 1) << 1;
             int bin = -1;
             if (q_in && pp.x >= 0.0 && pp.x < W && pp.y >= 0.0 && pp.y < H) {
-                // start = neighbour, end = row node (:173-174); steep / order swaps (:179-191)
+                // start = neighbour, end = row node (:173-174)
                 const int x1 = __double2int_rz(pp.x), y1 = __double2int_rz(pp.y);
-                const int dx = qxi - x1, dy = qyi - y1;
-                const bool steep = abs(dy) > abs(dx);
-                int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
-                int a2 = steep ? qyi : qxi, b2 = steep ? qxi : qyi;
-                if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
-                PwEdge ed;
-                ed.a1 = (uint16_t)a1; ed.b1 = (uint16_t)b1;
-                ed.da = (uint16_t)(a2 - a1); ed.adb = (uint16_t)abs(b2 - b1);
-                ed.slot = (uint16_t)sl;
-                ed.flags = (uint16_t)((steep ? 1 : 0) | (b1 < b2 ? 2 : 0));
-                // the bounding box of the end pixels in tiles: all free -> visible without a walk
                 const int xl = min(x1, qxi) >> 3, xh = max(x1, qxi) >> 3, yl = min(y1, qyi) >> 3, yh = max(y1, qyi) >> 3;
                 if (tiles_rect_free(a.af, xl, xh, yl, yh)) {
                     code |= 1;
                 } else {
+                    // steep / order swaps (:179-191)
+                    const int dx = qxi - x1, dy = qyi - y1;
+                    const bool steep = abs(dy) > abs(dx);
+                    int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+                    int a2 = steep ? qyi : qxi, b2 = steep ? qxi : qyi;
+                    if (a1 > a2) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+                    PwEdge ed;
+                    ed.a1 = (uint16_t)a1; ed.b1 = (uint16_t)b1;
+                    ed.da = (uint16_t)(a2 - a1); ed.adb = (uint16_t)abs(b2 - b1);
+                    ed.slot = (uint16_t)sl;
+                    ed.flags = (uint16_t)((steep ? 1 : 0) | (b1 < b2 ? 2 : 0));
                     s_edge[sl] = ed;
                     const int nch = (a2 >> 3) - (a1 >> 3) + 1;
                     bin = nch < PW_BINS ? nch - 1 : PW_BINS - 1;
@@ -504,29 +682,31 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
     }
     __syncthreads();
     // ---- placement: the sorted order of the edges (read the bins back before anything is overwritten)
-    int mybins[PRM_FUSED_KMAX - 1];
-#pragma unroll
-    for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col) mybins[col] = (work && col < kq) ? (int)s_idx[col * PW_ROWS + tid] - 1 : -1;
-    __syncthreads();
-#pragma unroll
-    for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col)
-        if (mybins[col] >= 0) s_idx[atomicAdd(&s_off[mybins[col]], 1)] = (uint16_t)(col * PW_ROWS + tid);
-    __syncthreads();
-    // ---- phase 2: walk the sorted edges
     const int total = s_total;
-    for (int i = tid; i < total; i += PW_ROWS) {
-        const PwEdge ed = s_edge[s_idx[i]];
-        const bool fr = edge_free_tiles<false>(a.tiled.words, a.tiled.SX, a.af, (int)ed.a1, (int)ed.b1, ed.da, ed.adb,
-                                        (ed.flags & 2) ? 1 : -1, (ed.flags & 1) != 0);
-        if (fr) s_code[ed.slot] |= 1;
+    if (total > 0) {
+        int mybins[PRM_FUSED_KMAX - 1];
+#pragma unroll
+        for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col) mybins[col] = (work && col < kq) ? (int)s_idx[tid * kq + col] - 1 : -1;
+        __syncthreads();
+#pragma unroll
+        for (int col = 0; col < PRM_FUSED_KMAX - 1; ++col)
+            if (mybins[col] >= 0) s_idx[atomicAdd(&s_off[mybins[col]], 1)] = (uint16_t)(tid * kq + col);
+        __syncthreads();
+        // ---- phase 2: walk the sorted edges
+        for (int i = tid; i < total; i += PW_ROWS) {
+            const PwEdge ed = s_edge[s_idx[i]];
+            const bool fr = edge_free_tiles<false>(a.tiled.words, a.tiled.SX, a.af, (int)ed.a1, (int)ed.b1, ed.da, ed.adb,
+                                                   (ed.flags & 2) ? 1 : -1, (ed.flags & 1) != 0);
+            if (fr) s_code[ed.slot] |= 1;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- output
     const int64_t orow = out.sorted_rows ? p : (int64_t)v;
     const bool stage = out.sorted_rows && out.packed;
-    if (work) {
+    if (work && (!stage || out.nbr || out.vis)) {
         for (int col = 0; col < kq; ++col) {
-            const int32_t code = s_code[col * PW_ROWS + tid];
+            const int32_t code = s_code[tid * kq + col];
             const int64_t o = orow * kq + col;
             if (!stage && out.packed) prm_store_packed(out, o, code);
             if (out.nbr) out.nbr[o] = (int64_t)(code >> 1) - 1;
@@ -534,6 +714,8 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
         }
     }
     if (stage) {
+        // the warp's 32 rows are one contiguous block of 32 * kq codes, in shared memory as in the output
+        // (rows the kNN kernel did not settle are written later by the exact path)
         const unsigned FULL = 0xffffffffu;
         const unsigned okmask = __ballot_sync(FULL, work);
         const int lane = tid & 31, wbase = tid & ~31;
@@ -541,21 +723,26 @@ k_prm_walk_sorted(CellGridView g, int kq, int64_t p0, int64_t count, const uint8
         if (slot0 < count) {
             const int rows = (int)(count - slot0 < 32 ? count - slot0 : 32);
             const int64_t base = (p0 + slot0) * kq;
-            if (out.packed_mc && okmask == 0xffffffffu && rows == 32 && (base & 3) == 0) {
-                for (int i4 = lane * 4; i4 < 32 * kq; i4 += 128) {
-                    float f[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = i4 + j, row = i / kq, col = i - row * kq;
-                        f[j] = __int_as_float(s_code[col * PW_ROWS + wbase + row]);
-                    }
-                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out.packed + base + i4),
-                                 "f"(f[0]), "f"(f[1]), "f"(f[2]), "f"(f[3]) : "memory");
+            const int32_t *src = s_code + wbase * kq;                    // (32 * kq * 4 bytes per warp: 16-byte aligned)
+            int32_t *dst = out.packed + base;
+            if (okmask == FULL && rows == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                const int4 *src4 = reinterpret_cast<const int4 *>(src);
+                for (int t = lane; t < 8 * kq; t += 32) {
+                    const int4 c = src4[t];
+                    if (out.packed_mc)      // through the switch in 16-byte pieces
+                        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * t),
+                                     "f"(__int_as_float(c.x)), "f"(__int_as_float(c.y)), "f"(__int_as_float(c.z)),
+                                     "f"(__int_as_float(c.w)) : "memory");
+                    else
+                        reinterpret_cast<int4 *>(dst)[t] = c;
                 }
             } else {
+                int row = 0, col = lane;                                 // word i = row * kq + col, i = lane, lane + 32, ...
+                while (col >= kq) { col -= kq; ++row; }
                 for (int i = lane; i < rows * kq; i += 32) {
-                    const int row = i / kq, col = i - row * kq;
-                    if ((okmask >> row) & 1u) prm_store_packed(out, base + i, s_code[col * PW_ROWS + wbase + row]);
+                    if ((okmask >> row) & 1u) prm_store_packed(out, base + i, src[i]);
+                    col += 32;
+                    while (col >= kq) { col -= kq; ++row; }
                 }
             }
         }
@@ -570,8 +757,11 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
                              PrmFusedArgs *args) {
     if (count <= 0) return SBP_OK;
     const int kq = k - 1;
+    // fused form (default): the candidates never leave the kNN kernel (k_prm_knn<., true>); coordinates
+    // of a walked edge travel as 16-bit pixels
+    const bool fuse = ctx->tune.prm_fuse && args->tiled.W <= 65536 && args->tiled.H <= 65536;
     void *cbuf = nullptr;
-    int32_t rc = sbp_ctx_scratch(ctx, 16, (size_t)count * (kq > 0 ? kq : 1) * sizeof(int32_t), &cbuf);
+    int32_t rc = fuse ? SBP_OK : sbp_ctx_scratch(ctx, 16, (size_t)count * (kq > 0 ? kq : 1) * sizeof(int32_t), &cbuf);
     if (rc) return rc;
     // Optionally (tune "prm_slices", default 1 = off) the rows go through the two kernels in SLICES,
     // the walk of slice i on a second stream beside the kNN of slice i + 1.  Measured on cfg5 and
@@ -592,7 +782,8 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
                           ctx->tune.time_kernels == 0 && ctx->tune.prm_mc_stage && count >= 32768 &&
                           (((p0 * kq) & 3) == 0) && ((reinterpret_cast<uintptr_t>(args->out.packed) & 15) == 0);
     if (stage_host) slices = 8;
-    if (stage_mc) slices = 4;
+    if (stage_mc) slices = fuse ? 1 : 4;
+    if (fuse && !stage_host) slices = 1;
     if (slices < 1 || ctx->tune.time_kernels != 0 || (count < 65536 && !stage_mc)) slices = 1;
     if (slices > 16) slices = 16;
     if (slices > 1 || stage_host || stage_mc || (args->order_out && args->order_host)) {
@@ -635,6 +826,47 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
     }
     if (kq > 20) { sbp_set_error("sbp_prm_fused_launch: %d candidates per row not instantiated", kq); return SBP_ERR_ARG; }
     const int64_t per = ((count + slices - 1) / slices + PRM_TPB - 1) / PRM_TPB * PRM_TPB;   // whole CTAs (and warps)
+    if (fuse) {
+        for (int sl = 0; sl < slices; ++sl) {
+            const int64_t off = (int64_t)sl * per, cnt = count - off < per ? count - off : per;
+            if (cnt <= 0) break;
+            const unsigned kblocks = (unsigned)((cnt + PRM_TPB - 1) / PRM_TPB);
+#define PRM_KNN(KK)                                                                                            \
+    k_prm_knn<KK, true><<<kblocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + off, cnt, seed2, done, \
+                                                              pending, nullptr, wargs)
+            {
+                KernelTimer timer(ctx, ctx->tune.time_kernels == 3 ? 3 : 2);
+                if (kq <= 4) PRM_KNN(4);
+                else if (kq <= 8) PRM_KNN(8);
+                else if (kq <= 10) PRM_KNN(10);
+                else if (kq <= 16) PRM_KNN(16);
+                else PRM_KNN(20);
+            }
+#undef PRM_KNN
+            ctx->launches += 1;
+            const int64_t r0 = (p0 + off) * kq;
+            if (stage_host) {
+                // this slice's block of rows: device staging -> the caller's host buffer, on the copy stream
+                SBP_CUDA(cudaEventRecord(ctx->aux_events[sl], ctx->stream));
+                SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[sl], 0));
+                SBP_CUDA(cudaMemcpyAsync(host_packed + r0, wargs.out.packed + r0, (size_t)cnt * kq * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, ctx->aux_stream));
+            } else if (stage_mc) {
+                k_mc_copy<<<ctx->sm_count, 256, 0, ctx->stream>>>(wargs.out.packed + r0, host_packed + r0, cnt * kq);
+                ctx->launches++;
+            }
+        }
+        if (stage_host || (args->order_out && args->order_host)) {   // join: everything behind sees all rows
+            SBP_CUDA(cudaEventRecord(ctx->aux_events[slices], ctx->aux_stream));
+            SBP_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_events[slices], 0));
+        }
+        int ab = (int)((grid.n + 255) / 256);
+        if (ab > ctx->sm_count * 8) ab = ctx->sm_count * 8;
+        k_rows_aos<<<ab, 256, 0, ctx->stream>>>(args->soa, args->capacity, grid.n, args->X, pending);
+        ctx->launches += 1;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
     for (int sl = 0; sl < slices; ++sl) {
         const int64_t off = (int64_t)sl * per, cnt = count - off < per ? count - off : per;
         if (cnt <= 0) break;
@@ -646,7 +878,7 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         const unsigned kblocks = (unsigned)((kcnt + PRM_TPB - 1) / PRM_TPB);
         int32_t *kcand = (int32_t *)cbuf + koff * kq;
 #define PRM_KNN(KK)                                                                                          \
-    k_prm_knn<KK><<<kblocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + koff, kcnt, seed2, done, pending, kcand)
+    k_prm_knn<KK, false><<<kblocks, PRM_TPB, 0, ctx->stream>>>(grid, kq, r_init, limit, p0 + koff, kcnt, seed2, done, pending, kcand, wargs)
         if (!stage_mc || sl == 0) {
             KernelTimer timer(ctx, 2);
             if (kq <= 4) PRM_KNN(4);
@@ -664,8 +896,8 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         }
         {
             KernelTimer timer(ctx, 3);
-            if (ctx->tune.prm_walk_sorted) {
-                const size_t sm = (size_t)kq * PW_ROWS * (sizeof(PwEdge) + sizeof(int32_t) + sizeof(uint16_t));
+            if (ctx->tune.prm_walk_sorted && args->tiled.W <= 65536 && args->tiled.H <= 65536) {   // (16-bit pixel coordinates)
+                const size_t sm = (size_t)kq * PW_ROWS * (sizeof(int32_t) + sizeof(PwEdge) + sizeof(uint16_t));
                 k_prm_walk_sorted<<<(unsigned)((cnt + PW_ROWS - 1) / PW_ROWS), PW_ROWS, sm, ws>>>(grid, kq, p0 + off, cnt,
                                                                                                   done, cand, wargs);
             } else {

@@ -168,13 +168,21 @@ def test_cfg5_reduced_scale_equals_oracle(sg):
     want_nbr, want_vis = oracle_connect(om, nodes, k)
     try:
         # both walk kernels, with and without the free-run planes (bounding box of tiles all free)
-        for rect, srt in ((1, 1), (0, 1), (1, 0), (0, 0)):
+        # fused form (the kNN kernel settles all-free boxes, k_prm_walk_todo the rest) and the separate
+        # walk kernels, with and without the free-run planes
+        for fuse, rect, srt in ((1, 1, 1), (1, 0, 1), (0, 1, 1), (0, 0, 1), (0, 1, 0), (0, 0, 0)):
+            sg.runtime.tune("prm_fuse", fuse)
             sg.runtime.tune("tile_rect", rect)
             sg.runtime.tune("prm_walk_sorted", srt)
             nbr, vis = sg.prm_connect_knn(cc, tree, k)
-            assert np.array_equal(nbr.cpu().numpy(), want_nbr), (rect, srt)
-            assert np.array_equal(vis.cpu().numpy(), want_vis), (rect, srt)
+            assert np.array_equal(nbr.cpu().numpy(), want_nbr), (fuse, rect, srt)
+            assert np.array_equal(vis.cpu().numpy(), want_vis), (fuse, rect, srt)
+            packed = torch.full((len(nodes), k), -1, dtype=torch.int32, device=dev)
+            order = torch.full((len(nodes),), -1, dtype=torch.int32, device=dev)
+            sg.prm_connect_knn(cc, tree, k, packed_out=packed, order_out=order, want_rows=False)
+            assert torch.equal(packed, sg.distributed.pack_adjacency(nbr, vis)[order.long()]), (fuse, rect, srt)
     finally:
+        sg.runtime.tune("prm_fuse", 1)
         sg.runtime.tune("tile_rect", 1)
         sg.runtime.tune("prm_walk_sorted", 1)
     assert 0.5 < float(vis.float().mean()) < 0.99
