@@ -8,7 +8,7 @@ all nodes (the cell grid is rebuilt inside every step) + integer-Bresenham visib
 10 M candidate edges (map = 128 MiB bit-packed, L2 / HBM resident), the packed adjacency
 (4 bytes per candidate) complete on every rank at the end of the step.  At N GPUs the rows are
 split N ways (STRONG scaling: the total work is fixed) and every rank's block is written
-through the NVSwitch multicast mapping by the visibility kernel itself as the edges are
+through the NVSwitch multicast mapping by the connection kernel itself as the rows are
 decided; the only other synchronisation is the barrier at the end of the step.
 
 After the timed loop the query stage is timed separately (`query_stage`): CSR assembly of the
@@ -46,16 +46,15 @@ K_NN = workloads.CFG5["k"]
 K_CONNECT = 8                                              # nearest roadmap nodes tried per query endpoint
 METRIC = "edge collision checks/sec (PRM candidate edges: exact kNN connect + visible_batch)"
 UNIT = "edges/s"
-# One launch of the two dominant kernels on this workload under `ncu --set full` (N = 1, full size;
-# profiles/r2_prm_walk_sorted_full.txt, profiles/r2_prm_knn_full.txt): dram__bytes_read.sum +
-# dram__bytes_write.sum, issue-slot utilisation, active lanes per warp instruction.
-NCU_WALK = {"kernel": "k_prm_walk_sorted", "dram_bytes": 94058496, "issue_active_pct": 69.6,
-            "lanes_per_instruction": 29.2, "warp_instructions": 201447164, "warps_active_pct": 52.9,
-            "alu_pipe_pct": 67.4, "source": "profiles/r2_prm_walk_sorted_full.txt"}
-NCU_KNN = {"kernel": "k_prm_knn<10>", "dram_bytes": 39021568, "issue_active_pct": 68.6,
-           "lanes_per_instruction": 23.5, "warp_instructions": 165410624, "warps_active_pct": 44.0,
-           "alu_pipe_pct": 75.6, "source": "profiles/r2_prm_knn_full.txt"}
-
+# One launch of the dominant kernel on this workload under `ncu --set full` (N = 1, full size;
+# profiles/r2_prm_knn_fused_full.txt): dram__bytes_read.sum + dram__bytes_write.sum, issue-slot
+# utilisation, active lanes per warp instruction.
+NCU_FUSED = {"kernel": "k_prm_knn<10, true>", "dram_bytes": 89240832, "issue_active_pct": 58.4,
+             "lanes_per_instruction": 24.7, "warp_instructions": 212259722, "warps_active_pct": 41.7,
+             "alu_pipe_pct": 62.8, "l1_hit_pct": 65.2, "l2_hit_pct": 74.6,
+             "source": "profiles/r2_prm_knn_fused_full.txt"}
+NCU_BUILD = {"kernel": "k_prm_grid_build", "kernel_us": 70.9, "dram_bytes": 16874240, "issue_active_pct": 26.2,
+             "source": "profiles/r2_prm_grid_build_full.txt"}
 
 def problem():
     mz, nodes, S, T = workloads.cfg5_problem(SCALE)
@@ -303,8 +302,8 @@ def run_ours(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     # ---- phase breakdown and the dominant kernel's own duration: the same step launched eagerly
-    # behind a spin kernel (the host runs ahead, so the events measure the GPU); the visibility
-    # kernel is bracketed by its own CUDA events on the launching stream
+    # behind a spin kernel (the host runs ahead, so the events measure the GPU); the connection
+    # kernel (kNN + visibility fused) is bracketed by its own CUDA events on the launching stream
     names = ("knn", "edges", "visible", "exchange")     # marks of prm_connect_knn + the exchange
     psteps = min(args.steps, 10)
     for _ in range(2):
@@ -518,47 +517,48 @@ def run_ours(args):
     else:
         hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
-    # Dominant kernel: k_prm_walk_sorted, the Bresenham visibility of the candidate edges on the 128 MiB map.
-    # ALGORITHMIC bytes per launch: 33 B per edge (two fp64 endpoints in, one byte
-    # out) + 0.125 B (one map bit) per interpolant of the full Bresenham line.
+    # Dominant kernel: k_prm_knn<10, true> -- the row's exact k nearest from the cell grid AND the
+    # visibility of its k candidate edges (free bounding boxes from the run planes, probes, tile walk),
+    # output rows written from shared memory.  ALGORITHMIC bytes per launch:
+    # visibility 33 B per edge (two fp64 endpoints in, one byte out) + 0.125 B (one map bit) per
+    # interpolant of the full Bresenham line; kNN every input byte once (cell-sorted poses 16 B + ids
+    # 4 B per node, cell starts 4 B per cell) + 9 B per row (bound and flag for the exact path).
     edges_rank = count * k
-    alg_bytes = 33.0 * edges_rank + 0.125 * px_total / world
-    vis_s = vis_ms / 1e3
+    vis_bytes = 33.0 * edges_rank + 0.125 * px_total / world
+    knn_bytes = 20.0 * n + 4.0 * (n / 1.5) + 9.0 * count
+    alg_bytes = vis_bytes + knn_bytes
+    fused_ms = knn_kernel_ms                                    # (timers 2 and 3 bracket the same kernel)
+    vis_s = fused_ms / 1e3
     step_ms = total_ms / args.steps
-    prof = NCU_WALK if world == 1 and SCALE == 1.0 else None
-    roof = {"kernel": f"k_prm_walk_sorted: two-level Bresenham walk of the kNN candidate edges ({100 * vis_ms / step_ms:.0f}% of "
-                      f"the step): {edges_rank} edges, {px_total / world:.4g} interpolants per launch on the 128 MiB map",
+    prof = NCU_FUSED if world == 1 and SCALE == 1.0 else None
+    roof = {"kernel": f"k_prm_knn<{k}, true>: exact k nearest of {count} rows among {n} nodes from the cell grid + "
+                      f"visibility of their {edges_rank} candidate edges ({px_total / world:.4g} interpolants) on the "
+                      f"128 MiB map, rows written from shared memory ({100 * fused_ms / step_ms:.0f}% of the step)",
             "bound": "hbm", "achieved": alg_bytes / vis_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": alg_bytes / vis_s / 1e9 / hbm_peak, "traffic": prof["dram_bytes"] if prof else None,
-            "peak_source": peak_src, "kernel_ms": vis_ms, "kernel_launches_timed": vis_n,
+            "peak_source": peak_src, "kernel_ms": fused_ms, "kernel_launches_timed": knn_n,
             "algorithmic_bytes_per_launch": alg_bytes,
+            "algorithmic_bytes": {"visibility": vis_bytes, "knn": knn_bytes},
             "edges_per_s_kernel": edges_rank / vis_s, "interpolants_per_s_kernel": px_total / world / vis_s,
+            "rows_per_s_kernel": count / vis_s, "effective_pairs_per_s": float(count) * n / vis_s,
             "ncu": prof,
-            "note": "not an HBM stream: the walk decides 8-pixel chunks on 2-bit tile codes (4 MiB, L1 / L2 resident) and "
-                    "is bound by the instructions it issues (ncu: issue slots, lanes per instruction); the HBM figure "
+            "note": "not an HBM stream: the kernel gathers from L1 / L2 resident arrays (cell-sorted poses 16 MB, "
+                    "free-run planes 16 MiB, tile codes 8 MiB) and is bound by the instructions it issues (list "
+                    "insertions in lock-step over the warp; ncu: issue slots, lanes per instruction); the HBM figure "
                     "says how far the algorithmic bytes are from mattering"}
-    # second kernel of the step: the cell-grid kNN (every input and output byte once: cell-sorted poses
-    # 16 B + ids 4 B per node, cell starts 4 B per cell, 4 k + 9 B out per row)
-    knn_bytes = 20.0 * n + 4.0 * (n / 1.5) + (4.0 * k + 9.0) * count
-    roof_knn = {"kernel": f"k_prm_knn: exact k nearest of {count} rows among {n} nodes from the cell grid "
-                          f"({100 * knn_kernel_ms / step_ms:.0f}% of the step)",
-                "bound": "hbm", "achieved": knn_bytes / (knn_kernel_ms / 1e3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                "frac": knn_bytes / (knn_kernel_ms / 1e3) / 1e9 / hbm_peak,
-                "traffic": NCU_KNN["dram_bytes"] if world == 1 and SCALE == 1.0 else None,
-                "kernel_ms": knn_kernel_ms, "rows_per_s_kernel": count / (knn_kernel_ms / 1e3),
-                "effective_pairs_per_s": float(count) * n / (knn_kernel_ms / 1e3),
-                "ncu": NCU_KNN if world == 1 and SCALE == 1.0 else None,
-                "note": "a gather over L1 / L2 resident arrays bound by issued instructions (list insertions in "
-                        "lock-step over the warp), not by memory"}
+    roof_build = {"kernel": "k_prm_grid_build: bounding box, histogram, scan, placement, per-cell order + cell-sorted "
+                            "poses in one cooperative launch (the second kernel of the step)",
+                  "ncu": NCU_BUILD if SCALE == 1.0 else None,
+                  "note": "five grid-wide barriers and dependent-load latency; not timed inside bench.py (its time is "
+                          "phases_ms.connect_call minus the kernels timed here minus the short launches)"}
 
-    knn_part_ms = max(ph["connect_call"] - vis_ms, 1e-6)       # grid build + kNN kernel + the exact path's launches
-    sub = {"knn_queries_per_s_per_gpu": count / (knn_part_ms / 1e3),
-           "knn_part_ms": knn_part_ms,
-           "knn_kernel_ms": knn_kernel_ms, "knn_kernel_queries_per_s": count / (knn_kernel_ms / 1e3),
-           "knn_effective_pairs_per_s_per_gpu": float(count) * n / (knn_part_ms / 1e3),
-           "visible_kernel_ms": vis_ms,
-           "visible_batch_edges_per_s_per_gpu": edges_rank / (vis_ms / 1e3),
-           "interpolant_checks_per_s_per_gpu": px_total / world / (vis_ms / 1e3),
+    call_ms = ph["connect_call"]                               # grid build + fused kernel + the exact path's launches
+    sub = {"knn_queries_per_s_per_gpu": count / (call_ms / 1e3),
+           "connect_call_ms": call_ms,
+           "fused_kernel_ms": fused_ms, "fused_kernel_ms_second_timer": vis_ms,
+           "knn_effective_pairs_per_s_per_gpu": float(count) * n / (call_ms / 1e3),
+           "visible_batch_edges_per_s_per_gpu": edges_rank / (call_ms / 1e3),
+           "interpolant_checks_per_s_per_gpu": px_total / world / (call_ms / 1e3),
            "prm_build_ms": total_ms / args.steps,
            "roadmap_edges_visible": n_vis,
            "build_plus_queries_ms": total_ms / args.steps + q_ms}
@@ -609,7 +609,7 @@ def run_ours(args):
                   "launched eagerly",
         "multi_gpu": {"rows_per_rank": count, "exchange": exchange, "adjacency_check": adjacency_check},
         "roofline": roof,
-        "roofline_knn": roof_knn,
+        "roofline_build": roof_build,
         "measured_gather_peaks": {"l2_random_sector_gathers_per_s_64MiB": microbench(ctx, 1, 64 << 20, 512),
                                   "hbm_random_sector_gathers_per_s_8GiB": microbench(ctx, 1, 8 << 30, 512)},
         "cpu_baseline": cpu,

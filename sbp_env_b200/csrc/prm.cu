@@ -65,6 +65,8 @@ struct PrmFusedArgs {
     int32_t *order_out;
     int64_t order_p0, order_count;
     int order_host;          // order_out is host memory: copied by the DMA engine beside the kNN
+    int order_in_kernel;     // (set by the launcher) k_prm_knn<., true> writes order_out[p] for its rows itself ...
+    int order_mc;            // ... through the multicast mapping
 };
 
 __device__ __noinline__ bool prm_edge_slow(const MapView &tiled, double px, double py, double qx, double qy,
@@ -362,6 +364,12 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
         const bool stage = out.sorted_rows && out.packed;
         const int tid = threadIdx.x;
         if (tid == 0) s_n2 = 0;
+        if (live && a.order_in_kernel) {                          // the row permutation: node of cell-sorted position p
+            if (a.order_mc)
+                asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(a.order_out + p), "f"(__int_as_float(v)) : "memory");
+            else
+                a.order_out[p] = v;
+        }
         const double W = (double)a.tiled.W, H = (double)a.tiled.H;
         const bool q_in = q.x >= 0.0 && q.x < W && q.y >= 0.0 && q.y < H;
         const int qxi = q_in ? __double2int_rz(q.x) : 0, qyi = q_in ? __double2int_rz(q.y) : 0;
@@ -807,7 +815,7 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
             SBP_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_events[0], 0));
             SBP_CUDA(cudaMemcpyAsync(args->order_out + args->order_p0, grid.ids + args->order_p0,
                                      (size_t)args->order_count * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->aux_stream));
-        } else {
+        } else if (!(fuse && args->order_p0 == p0 && args->order_count == count)) {
             int ob = (int)((args->order_count + 255) / 256);
             if (ob > ctx->sm_count * 8) ob = ctx->sm_count * 8;
             k_copy_order<<<ob, 256, 0, ctx->stream>>>(grid.ids, args->order_p0, args->order_count, args->order_out,
@@ -816,6 +824,10 @@ int32_t sbp_prm_fused_launch(sbp_ctx *ctx, const CellGridView &grid, int K, int 
         }
     }
     PrmFusedArgs wargs = *args;
+    // (fused form: the kernel's rows are the rows of the permutation asked for, it writes them itself)
+    wargs.order_in_kernel = fuse && args->order_out && args->order_count > 0 && !args->order_host &&
+                            args->order_p0 == p0 && args->order_count == count;
+    wargs.order_mc = args->out.packed_mc;
     int32_t *host_packed = nullptr;
     if (stage_host || stage_mc) {
         void *stg = nullptr;
@@ -1025,7 +1037,7 @@ static int32_t prm_connect(sbp_map *map, sbp_nodes *nodes, int32_t k, int32_t pa
     const int64_t base = n / parts, rem = n % parts;
     PrmFusedArgs fa{map->view, sbp_map_codes(map),
                     PrmOut{nbr_out, vis, packed, packed_multicast, sorted_rows}, flags,
-                    nodes->d_soa, nodes->capacity, (double2 *)xbuf, 0, nullptr, 0, 0, 0};
+                    nodes->d_soa, nodes->capacity, (double2 *)xbuf, 0, nullptr, 0, 0, 0, 0, 0};
     if (packed && !packed_multicast) {
         cudaPointerAttributes attr{};
         if (cudaPointerGetAttributes(&attr, packed) == cudaSuccess && attr.type == cudaMemoryTypeHost) fa.host_out = 1;
