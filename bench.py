@@ -741,9 +741,10 @@ def cfg2_line(sg, dev, local, flush):
     ms = float(np.mean(ts))
     launches0 = tree.ctx.launches
     sg.prm_connect_knn(cc, tree, 10)
+    launches = int(tree.ctx.launches - launches0)
     micro = micro_edges(sg, cc, W, H, nodes, dev, flush)
     return {"micro": micro, "workload": "cfg2: PRM connection on intel_lab 579x581, 50000 free samples, k=10 -> 500000 candidate edges",
-            "ms_per_step": ms, "edges_per_s": 500_000 / (ms / 1e3), "gpu_launches_per_step": int(tree.ctx.launches - launches0),
+            "ms_per_step": ms, "edges_per_s": 500_000 / (ms / 1e3), "gpu_launches_per_step": launches,
             "roadmap_edges_visible": int(g.vis.sum().item())}
 
 

@@ -1073,18 +1073,29 @@ k_prm_grid_build(GridBuildArgs a) {
             if (slot[u] >= 0) a.ids[slot[u]] = (int32_t)(t + u * gsz);
     }
     grid.sync();
-    // ---- phase 4: per-cell order by node index, cell-sorted poses
-    for (int64_t c = (int64_t)r0 * G + gtid; c < (int64_t)(r1 + 1) * G; c += gsz) {
-        const int32_t e0 = a.start[c], e1 = a.start[c + 1];
-        for (int32_t i = e0 + 1; i < e1; ++i) {
-            const int32_t v = a.ids[i];
-            int32_t j = i - 1;
-            while (j >= e0 && a.ids[j] > v) { a.ids[j + 1] = a.ids[j]; --j; }
-            a.ids[j + 1] = v;
+    // ---- phase 4: per-cell order by node index (thread per cell), then the cell-sorted poses (thread per
+    // position: all lanes busy, coalesced stores); a CTA owns a contiguous chunk of the band's cells, so a
+    // CTA barrier separates the two
+    {
+        const int64_t cb0 = (int64_t)r0 * G, cb1 = (int64_t)(r1 + 1) * G;
+        const int64_t per = (cb1 - cb0 + nb - 1) / nb;
+        const int64_t k0 = cb0 + (int64_t)b * per, k1 = k0 + per < cb1 ? k0 + per : cb1;
+        for (int64_t c = k0 + tid; c < k1; c += GB_TPB) {
+            const int32_t e0 = a.start[c], e1 = a.start[c + 1];
+            for (int32_t i = e0 + 1; i < e1; ++i) {
+                const int32_t v = a.ids[i];
+                int32_t j = i - 1;
+                while (j >= e0 && a.ids[j] > v) { a.ids[j + 1] = a.ids[j]; --j; }
+                a.ids[j + 1] = v;
+            }
         }
-        for (int32_t i = e0; i < e1; ++i) {
-            const int32_t v = a.ids[i];
-            a.pts[i] = make_double2(a.soa[v], a.soa[a.capacity + v]);
+        __syncthreads();
+        if (k0 < k1) {
+            const int32_t e0 = a.start[k0], e1 = a.start[k1];
+            for (int32_t i = e0 + tid; i < e1; i += GB_TPB) {
+                const int32_t v = a.ids[i];
+                a.pts[i] = make_double2(a.soa[v], a.soa[a.capacity + v]);
+            }
         }
     }
 }
