@@ -81,7 +81,8 @@ int32_t sbp_ctx_scratch_generation(sbp_ctx *ctx, int64_t *generation);
  * Tuning knobs, PER CONTEXT: key is one of visible_group, coop_below, force_global, arm_group,
  * near_filter, knn_seed, knn_chunks, knn_prefilter, knn_filter, knn_filter_chunks,
  * knn_filter_variant, knn_cells, knn_cells_limit, knn_cells_qpw, knn_cells_rinit,
- * knn_cells_order, knn_cell_density, time_kernels (csrc/common.cuh: sbp_tuning). */
+ * knn_cells_order, knn_cell_density, visible_tiles, tile_rect, prm_fuse, prm_walk_sorted,
+ * prm_slices, prm_mc_stage, arm_flat, time_kernels (csrc/common.cuh: sbp_tuning). */
 int32_t sbp_ctx_tune(sbp_ctx *ctx, const char *key, int64_t value);
 /* With time_kernels = 1 (k_knn_filter), 2 (k_knn_cells*) or 3 (2-D visibility kernel) every
  * launch of that kernel is bracketed by a CUDA event pair on the launching stream; this returns
