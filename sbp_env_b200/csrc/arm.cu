@@ -254,6 +254,185 @@ k_arm_visible_flat(MapView mv, double L0, double L1, const double4 *__restrict__
     if (myflag && flags) atomicOr(flags, myflag);
 }
 
+// visible, flattened form WITH the free-box test of the 2-D path (the default where the map has tile
+// codes and fits 16-bit coordinates).  k_arm_visible_flat spends its time in the two link sweeps of
+// every config (<= 31 pixels each, lanes of different length, 18.4 of 32 active).  A link is a
+// Bresenham line: when the bounding box of its end pixels is free of blocked pixels (two words of
+// the free-run planes, device_fns.cuh:tiles_rect_free) it is free without a sweep -- 77 % of the
+// configs of tree-like edges on maps/4d.png have both links settled that way.  Phase A (thread =
+// config): lerp, forward kinematics, guard bands, ranges (arm_config_pre) and the two box tests;
+// configs with a link left are listed in shared memory.  Phase B, whenever the list holds a
+// block's worth of entries: the listed links are swept side by side (full lanes).  Same results
+// as arm_config for every map: a free box proves a free link, everything else is swept.
+struct ArmLink {               // 12 bytes; coordinates in [-W, W) fit 16 bits (W, H <= 32767)
+    int16_t x0, y0, x1, y1;
+    uint16_t edge, pad;      // edge of the CTA's block
+};
+#define AB_LIST 96             // entries per warp: fewer than 32 left over + at most 2 per lane and step
+
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_arm_visible_boxes(MapView mv, TileCodeView af, double L0, double L1, const double4 *__restrict__ C1,
+                    const double4 *__restrict__ C2, int64_t n, uint8_t *__restrict__ out,
+                    int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    __shared__ ArmEdge s_e[AF_EDGES];
+    __shared__ uint32_t s_pref[AF_EDGES + 1];
+    __shared__ int32_t s_f[AF_EDGES];
+    __shared__ uint32_t s_ws[AF_EDGES / 32];
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    // [AB_LIST per warp] entries behind the staged map (dynamic shared memory; the map is padded to 16 bytes)
+    ArmLink *s_todo = reinterpret_cast<ArmLink *>(smap + (SMEM ? mv.n_words : 0u));
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    int myflag = 0;
+    for (int64_t base = (int64_t)blockIdx.x * AF_EDGES; base < n; base += (int64_t)gridDim.x * AF_EDGES) {
+        // ---- phase 1: set up the block's edges (as in k_arm_visible_flat)
+        uint32_t N = 0;
+        if (tid < AF_EDGES) {
+            const int64_t eidx = base + tid;
+            const bool valid = eidx < n;
+            double4 a = make_double4(0, 0, 0, 0), b = make_double4(0, 0, 0, 0);
+            if (valid) { a = C1[eidx]; b = C2[eidx]; }
+            TruncResult t0 = trunc_index(a.x, mv.W), t1 = trunc_index(a.y, mv.H);
+            TruncResult t2 = trunc_index(b.x, mv.W), t3 = trunc_index(b.y, mv.H);
+            int f = t0.flag ? t0.flag : t1.flag ? t1.flag : t2.flag ? t2.flag : t3.flag;
+            if (!f && (isinf(a.z) || isinf(a.w) || isinf(b.z) || isinf(b.w) || a.z != a.z || a.w != a.w ||
+                       b.z != b.z || b.w != b.w))
+                f = SBP_FLAG_NAN;
+            if (valid) myflag |= f;
+            const bool walk = valid && !f && t0.in_range && t1.in_range && t2.in_range && t3.in_range;
+            int x1 = t0.i, y1 = t1.i, x2 = t2.i, y2 = t3.i;
+            int dx = x2 - x1, dy = y2 - y1;
+            const bool steep = abs(dy) > abs(dx);
+            int a1 = steep ? y1 : x1, b1 = steep ? x1 : y1;
+            int a2 = steep ? y2 : x2, b2 = steep ? x2 : y2;
+            const bool swapped = a1 > a2;
+            if (swapped) { int t = a1; a1 = a2; a2 = t; t = b1; b1 = b2; b2 = t; }
+            ArmEdge e;
+            e.a1 = a1; e.b1 = b1;
+            e.da = (uint32_t)(a2 - a1); e.adb = (uint32_t)abs(b2 - b1);
+            e.npx = e.da + 1u;
+            e.flags = (steep ? 1 : 0) | (swapped ? 2 : 0) | (b1 < b2 ? 4 : 0);
+            const uint32_t NN = e.npx < 2u ? 2u : e.npx;                 // :375-377
+            const double inv = __ddiv_rn(1.0, (double)(NN - 1u));        // create_ranges (:363-364)
+            e.az = a.z; e.aw = a.w;
+            e.st0 = __dmul_rn(inv, __dsub_rn(b.z, a.z));
+            e.st1 = __dmul_rn(inv, __dsub_rn(b.w, a.w));
+            s_e[tid] = e;
+            N = walk ? NN : 0u;
+            s_f[tid] = walk ? 0 : 1;                                     // not walked = blocked
+        }
+        if (tid < AF_EDGES) {
+            uint32_t inc = N;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += u; }
+            if (lane == 31) s_ws[w] = inc;
+            s_pref[tid + 1] = inc;                                        // (warp-local for now)
+        }
+        __syncthreads();
+        if (tid < AF_EDGES) {
+            uint32_t off = 0;
+            for (int i = 0; i < w; ++i) off += s_ws[i];
+            s_pref[tid + 1] += off;
+            if (tid == 0) s_pref[0] = 0;
+        }
+        __syncthreads();
+        const uint32_t T = s_pref[AF_EDGES];
+        // ---- phase 2: (edge, config) pairs, a warp's 32 at a time.  A config is blocked iff link 1 is
+        // blocked, or what follows link 1 says so (`after` = 0), or link 2 decides (`after` = 3) and is
+        // blocked; it is ambiguous iff link 1 is free and `after` = 2 -- and "blocked" wins for the edge,
+        // so the two links can be judged independently of each other.  Links without a free box go to
+        // the warp's own list and are swept, 32 at a time, whenever it holds that many: one sweep per
+        // lane, no CTA barrier inside.
+        ArmLink *wl = s_todo + w * AB_LIST;
+        int wn = 0;                                                      // (warp uniform)
+        for (uint32_t c0 = 0; c0 < T; c0 += blockDim.x) {
+            const uint32_t c = c0 + tid;
+            bool need1 = false, need2 = false;
+            ArmLink t1, t2;
+            if (c < T) {
+                int lo = 0, hi = AF_EDGES;                               // largest j with s_pref[j] <= c
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_pref[mid] <= c) lo = mid; else hi = mid;
+                }
+                if (!(s_f[lo] & 1)) {                                    // (edge not yet known blocked)
+                    const ArmEdge e = s_e[lo];
+                    const uint32_t o = c - s_pref[lo];
+                    const uint32_t po = e.npx == 1u ? 0u : o;            // duplicated single pixel
+                    const bool steep = e.flags & 1, swapped = e.flags & 2;
+                    const uint64_t ci = swapped ? (uint64_t)(e.npx - 1u - po) : (uint64_t)po;
+                    const uint32_t cc = e.da ? e.da - 1u - (e.da >> 1) : 0u;
+                    const uint32_t k = e.da ? (uint32_t)((ci * e.adb + cc) / e.da) : 0u;
+                    const int aa = e.a1 + (int)ci, bb = e.b1 + ((e.flags & 4) ? 1 : -1) * (int)k;
+                    const double bx = (double)(steep ? bb : aa), by = (double)(steep ? aa : bb);
+                    const double r0 = __dadd_rn(__dmul_rn(e.st0, (double)o), e.az);
+                    const double r1 = __dadd_rn(__dmul_rn(e.st1, (double)o), e.aw);
+                    const ArmPre p = arm_config_pre(mv, L0, L1, bx, by, r0, r1, myflag);
+                    int r = p.r;                                         // 0 / 2 final, -1: the links decide
+                    if (r < 0) {
+                        r = 1;
+                        // the links' end pixels first (base and elbow of link 1, the tip of link 2): most
+                        // blocked configs end here
+                        const bool ends1 = map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x0, mv.W), wrap_index(p.y0, mv.H)) &&
+                                           map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x1, mv.W), wrap_index(p.y1, mv.H));
+                        const bool tip = p.after != 3 ||
+                                         map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x2, mv.W), wrap_index(p.y2, mv.H));
+                        if (!ends1 || !tip || p.after == 0) {
+                            r = 0;
+                        } else {
+                            if (p.after == 2) r = 2;                      // (counts only if link 1 turns out free; else blocked wins)
+                            // (boxes only for coordinates that do not wrap around: :393-402 index the image with
+                            // negative values too, pixel by pixel)
+                            need1 = !((p.x0 | p.y0 | p.x1 | p.y1) >= 0 &&
+                                      tiles_rect_free(af, min(p.x0, p.x1) >> 3, max(p.x0, p.x1) >> 3, min(p.y0, p.y1) >> 3,
+                                                      max(p.y0, p.y1) >> 3));
+                            need2 = p.after == 3 && !((p.x1 | p.y1 | p.x2 | p.y2) >= 0 &&
+                                                      tiles_rect_free(af, min(p.x1, p.x2) >> 3, max(p.x1, p.x2) >> 3,
+                                                                      min(p.y1, p.y2) >> 3, max(p.y1, p.y2) >> 3));
+                            t1.x0 = (int16_t)p.x0; t1.y0 = (int16_t)p.y0; t1.x1 = (int16_t)p.x1; t1.y1 = (int16_t)p.y1;
+                            t2.x0 = (int16_t)p.x1; t2.y0 = (int16_t)p.y1; t2.x1 = (int16_t)p.x2; t2.y1 = (int16_t)p.y2;
+                            t1.edge = t2.edge = (uint16_t)lo;
+                            t1.pad = t2.pad = 0;
+                        }
+                    }
+                    if (r == 0 || r == 2) atomicOr(&s_f[lo], r == 0 ? 1 : 2);
+                }
+            }
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned m1 = __ballot_sync(FULL, need1), m2 = __ballot_sync(FULL, need2);
+            if (need1) wl[wn + __popc(m1 & lt)] = t1;
+            wn += __popc(m1);
+            if (need2) wl[wn + __popc(m2 & lt)] = t2;
+            wn += __popc(m2);
+            __syncwarp();
+            const bool last = c0 + blockDim.x >= T;
+            while (wn >= 32 || (last && wn > 0)) {
+                // ---- one listed link per lane (the LAST 32 entries: nothing to move)
+                const int take = wn < 32 ? wn : 32;
+                if (lane < take) {
+                    const ArmLink q = wl[wn - take + lane];
+                    if (!(s_f[q.edge] & 1) && !link_free<SMEM, true>(words, mv, q.x0, q.y0, q.x1, q.y1))   // :413-415, :422-424
+                        atomicOr(&s_f[q.edge], 1);
+                }
+                wn -= take;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: an unambiguous block decides the edge, else an ambiguous config leaves it open
+        if (tid < AF_EDGES && base + tid < n) {
+            const int f = s_f[tid];
+            out[base + tid] = (uint8_t)((f & 1) ? 0 : (f & 2) ? 2 : 1);
+        }
+        __syncthreads();
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
 // ------------------------------------------------------------ launchers -----
 
 // The arm kernels read the ROW-MAJOR copy of the map (sbp_map::rows, common.cuh).
@@ -342,8 +521,15 @@ extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const dou
     unsigned long long *cnt = (unsigned long long *)cfg_tested;
     if (!cnt && ctx->tune.arm_group == 0 && ctx->tune.arm_flat) {
         size_t bytes = smem ? (size_t)map->rows.n_words * 4 : 0;
-        // static shared memory of the kernel (edge block, prefix, flags) next to the staged map
-        const size_t fixed = sizeof(ArmEdge) * AF_EDGES + 4 * (2 * AF_EDGES + 16) + 1024;
+        // free-box form: needs the tile codes / free-run planes of the map and 16-bit coordinates
+        const bool boxes = ctx->tune.arm_flat >= 2 && ctx->tune.tile_rect && map->view.W <= 32767 && map->view.H <= 32767;
+        if (boxes) {
+            int32_t rc = sbp_map_ensure_allfree(map);
+            if (rc) return rc;
+        }
+        // static shared memory of the kernel (edge block, prefix, flags, todo list) next to the staged map
+        const size_t fixed = sizeof(ArmEdge) * AF_EDGES + 4 * (2 * AF_EDGES + 16) + 1024 + (boxes ? sizeof(ArmLink) * AB_LIST * 32 + 16 : 0);
+        const size_t todo_bytes = sizeof(ArmLink) * AB_LIST * 32;         // dynamic, behind the map (a list per warp)
         int per_sm = smem ? (int)((size_t)(227 * 1024) / (bytes + fixed)) : 2;
         per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
         const int threads = per_sm == 1 ? 1024 : 512;
@@ -351,6 +537,20 @@ extern "C" int32_t sbp_arm_visible(sbp_map *map, double L0, double L1, const dou
         const int64_t need = (n + AF_EDGES - 1) / AF_EDGES;
         if (need < grid) grid = (int)need;
         const double4 *c1 = (const double4 *)C1, *c2 = (const double4 *)C2;
+        if (boxes) {
+            const TileCodeView af = sbp_map_codes(map);
+            if (smem) {
+                SBP_CUDA(cudaFuncSetAttribute(k_arm_visible_boxes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(bytes + todo_bytes)));
+                k_arm_visible_boxes<true><<<grid, threads, bytes + todo_bytes, ctx->stream>>>(map->rows, af, L0, L1, c1, c2, n, out, flags);
+            } else {
+                SBP_CUDA(cudaFuncSetAttribute(k_arm_visible_boxes<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)todo_bytes));
+                k_arm_visible_boxes<false><<<grid, threads, todo_bytes, ctx->stream>>>(map->rows, af, L0, L1, c1, c2, n, out, flags);
+            }
+            ctx->launches++;
+            SBP_CUDA(cudaGetLastError());
+            return SBP_OK;
+        }
         if (smem) {
             if (bytes + fixed > 48 * 1024)
                 SBP_CUDA(cudaFuncSetAttribute(k_arm_visible_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

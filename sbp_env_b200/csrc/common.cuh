@@ -92,7 +92,7 @@ struct sbp_tuning {
     int prm_slices = 1;           // sbp_prm_connect2d: row slices whose walk overlaps the next slice's kNN
                                   // (measured on cfg5: 0.59 / 0.61 / 0.63 / 0.66 / 0.74 ms with 1 / 2 / 3 / 4 / 8 slices)
     int arm_group = 0;            // lanes per arm edge (0 = default 8)
-    int arm_flat = 1;             // arm visible: flattened (edge, config) pairs per CTA (0: lane groups per edge)
+    int arm_flat = 2;             // arm visible: flattened (edge, config) pairs per CTA; 2 = with the free-box test of the links (0: lane groups per edge)
     int near_filter = 1;          // filtered scan of the batched radius query
     int knn_seed = 1;             // grid-seeded a-priori bounds
     int knn_chunks = 0;           // node chunks of the batched kNN kernel (0 = auto)

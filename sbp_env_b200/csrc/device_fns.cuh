@@ -233,6 +233,51 @@ __device__ __forceinline__ int arm_config(const uint32_t *words, const MapView &
     return link_free<SMEM, ROWS>(words, mv, t2x.i, t2y.i, t3x.i, t3y.i) ? 1 : 0;   // :422-424
 }
 
+// The same configuration WITHOUT its two link sweeps (k_arm_visible_boxes): everything arm_config
+// decides before / between them.  r >= 0: final (0 blocked, 2 ambiguous).  r = -1: link 1 (base ->
+// elbow) has to be free, and then the result is `after` -- 0 / 2, or 3 = link 2 (elbow -> tip) decides.
+// (arm_config evaluates the tip's ambiguity / range only once link 1 is known free; taking them first
+// changes nothing: they are consulted only in that case.)
+struct ArmPre {
+    int r, after;
+    int x0, y0, x1, y1, x2, y2;
+};
+__device__ __forceinline__ ArmPre arm_config_pre(const MapView &mv, double L0, double L1, double bx, double by,
+                                                 double r0, double r1, int &flag) {
+    ArmPre p;
+    p.r = 0; p.after = 0;
+    p.x0 = p.y0 = p.x1 = p.y1 = p.x2 = p.y2 = 0;
+    if (isinf(r0) || isinf(r1) || r0 != r0 || r1 != r1) { flag |= SBP_FLAG_NAN; return p; }
+    double s0, c0, s1, c1;
+    sincos(r0, &s0, &c0);
+    sincos(r1, &s1, &c1);
+    double p2x = __dadd_rn(bx, __dmul_rn(L0, c0));      // :438
+    double p2y = __dadd_rn(by, __dmul_rn(L0, s0));      // :439
+    double p3x = __dadd_rn(p2x, __dmul_rn(L1, c1));     // :417-419
+    double p3y = __dadd_rn(p2y, __dmul_rn(L1, s1));
+    TruncResult tbx = trunc_index(bx, mv.W), tby = trunc_index(by, mv.H);
+    int f = tbx.flag ? tbx.flag : tby.flag;
+    if (f) { flag |= f; return p; }
+    if (!tbx.in_range || !tby.in_range) return p;
+    bool amb1 = near_pixel_boundary(p2x, L0) || near_pixel_boundary(p2y, L0);
+    TruncResult t2x = trunc_index(p2x, mv.W), t2y = trunc_index(p2y, mv.H);
+    if (t2x.flag || t2y.flag) { flag |= t2x.flag ? t2x.flag : t2y.flag; return p; }
+    if (amb1) { p.r = 2; return p; }
+    if (!t2x.in_range || !t2y.in_range) return p;
+    p.r = -1;
+    p.x0 = tbx.i; p.y0 = tby.i; p.x1 = t2x.i; p.y1 = t2y.i;
+    bool amb2 = near_pixel_boundary(p3x, L1) || near_pixel_boundary(p3y, L1);
+    TruncResult t3x = trunc_index(p3x, mv.W), t3y = trunc_index(p3y, mv.H);
+    // (a finite in-range elbow + a link length cannot give a non-finite tip: the flag case of
+    // arm_config is unreachable here; it is kept as "blocked" for safety)
+    if (t3x.flag || t3y.flag) { p.after = 0; return p; }
+    if (amb2) { p.after = 2; return p; }
+    if (!t3x.in_range || !t3y.in_range) { p.after = 0; return p; }
+    p.after = 3;
+    p.x2 = t3x.i; p.y2 = t3y.i;
+    return p;
+}
+
 
 // One thread checks one whole arm edge: 1 free, 0 blocked, 2 ambiguous (arm.cu header).
 template <bool SMEM>

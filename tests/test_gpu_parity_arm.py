@@ -92,7 +92,8 @@ def test_random_vs_oracle(sg, name, L):
     try:
         # (flat, group): the flattened (edge, config) kernel (default), then the lane-group kernel with
         # 8 (its default), 4 and 32 lanes per edge
-        for flat, group in ((1, 0), (0, 0), (0, 4), (0, 32)):
+        # (flat = 2: the flattened kernel with the free-box test of the links, the default)
+        for flat, group in ((2, 0), (1, 0), (0, 0), (0, 4), (0, 32)):
             tune("arm_flat", flat)
             tune("arm_group", group)
             assert np.array_equal(cc.visible_batch(C1, C2), want_fwd), group
@@ -103,7 +104,7 @@ def test_random_vs_oracle(sg, name, L):
             assert np.array_equal(cc.visible_batch(C1[-1:], C2[-1:]), want_fwd[-1:]), group
     finally:
         tune("arm_group", 0)
-        tune("arm_flat", 1)
+        tune("arm_flat", 2)
 
 
 def test_guard_band_is_resolved_exactly(sg):

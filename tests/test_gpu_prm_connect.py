@@ -39,7 +39,8 @@ def oracle_connect(om, nodes, k):
 
 
 @pytest.mark.parametrize("name,n,k", [("maze1", 6000, 7), ("intel_lab", 20000, 10), ("room1", 3000, 1),
-                                      ("room1", 2500, 31), ("maze1", 300, 5), ("maze1", 40, 10)])
+                                      ("room1", 2500, 31), ("maze1", 300, 5), ("maze1", 40, 10),
+                                      ("intel_lab", 8000, 14), ("maze1", 5000, 19)])
 def test_one_call_connection_equals_oracle(sg, name, n, k):
     import torch
 

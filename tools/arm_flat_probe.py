@@ -1,5 +1,5 @@
 """Arm edge visibility (1024^2 map, L = 30, 30): RRT-like edges and uniform 4-D pairs, lane-group kernel
-(arm_flat = 0) against the flattened kernel (arm_flat = 1).  Run under gpurun."""
+(arm_flat = 0) against the flattened kernel (arm_flat = 1) and the one with the free-box test of the links (2).  Run under gpurun."""
 import os
 import sys
 
@@ -35,7 +35,7 @@ for name, C2 in sets.items():
     else:
         a, b = C1, C2
     res = {}
-    for flat in (0, 1):
+    for flat in (0, 1, 2):
         sg.runtime.tune("arm_flat", flat)
         r = cc._visible_device(a, b, resolve=False)
         torch.cuda.synchronize()
@@ -51,5 +51,5 @@ for name, C2 in sets.items():
         npx = (torch.maximum((a[:, 0].trunc() - b[:, 0].trunc()).abs(), (a[:, 1].trunc() - b[:, 1].trunc()).abs()) + 1).clamp(min=2).sum().item()
         t = sorted(ts)[2]
         print(f"{name:32s} arm_flat {flat}: {t:.3f} ms  {len(a) / t * 1e3:.3e} edges/s  {npx / t * 1e3:.3e} configs/s  visible {float((r == 1).float().mean()):.3f}", flush=True)
-    assert torch.equal(res[0], res[1]), name
-sg.runtime.tune("arm_flat", 1)
+    assert torch.equal(res[0], res[1]) and torch.equal(res[0], res[2]), name
+sg.runtime.tune("arm_flat", 2)
