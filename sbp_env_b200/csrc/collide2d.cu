@@ -532,7 +532,7 @@ extern "C" int32_t sbp_ctx_tune(sbp_ctx *ctx, const char *key, int64_t value) {
     sbp_tuning &t = ctx->tune;
     struct { const char *name; int *slot; } table[] = {
         {"visible_group", &t.visible_group}, {"coop_below", &t.coop_below},
-        {"force_global", &t.force_global}, {"visible_tiles", &t.visible_tiles}, {"prm_slices", &t.prm_slices}, {"prm_walk_sorted", &t.prm_walk_sorted}, {"prm_mc_stage", &t.prm_mc_stage}, {"tile_rect", &t.tile_rect}, {"prm_fuse", &t.prm_fuse}, {"arm_group", &t.arm_group}, {"arm_flat", &t.arm_flat},
+        {"force_global", &t.force_global}, {"visible_tiles", &t.visible_tiles}, {"prm_slices", &t.prm_slices}, {"prm_walk_sorted", &t.prm_walk_sorted}, {"prm_mc_stage", &t.prm_mc_stage}, {"tile_rect", &t.tile_rect}, {"prm_fuse", &t.prm_fuse}, {"prm_build_ctas", &t.prm_build_ctas}, {"arm_group", &t.arm_group}, {"arm_flat", &t.arm_flat},
         {"near_filter", &t.near_filter}, {"knn_seed", &t.knn_seed}, {"knn_chunks", &t.knn_chunks},
         {"knn_prefilter", &t.knn_prefilter}, {"knn_filter", &t.knn_filter},
         {"knn_filter_chunks", &t.knn_filter_chunks}, {"knn_filter_variant", &t.knn_filter_variant},

@@ -86,6 +86,7 @@ struct sbp_tuning {
     int force_global = 0;         // 1 = never stage the map in shared memory
     int visible_tiles = 1;        // maps read from L2 / HBM: two-level walk on the 8x8-tile codes
     int tile_rect = 1;            // tile walks: settle an edge whose bounding box of tiles is all free from the run planes
+    int prm_build_ctas = 0;       // k_prm_grid_build: resident CTAs per SM (0 = as many as fit, at most 3)
     int prm_fuse = 1;             // sbp_prm_connect2d: the kNN kernel settles edges with an all-free bounding box and writes the rows (0: separate walk kernel over all edges)
     int prm_mc_stage = 0;         // sbp_prm_connect2d: multicast outputs leave through a staging buffer + copy kernel
     int prm_walk_sorted = 1;      // sbp_prm_connect2d: walk the CTA's edges sorted by length (0: a row's edges in order)

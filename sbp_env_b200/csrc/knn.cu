@@ -1627,6 +1627,7 @@ static int32_t knn_launch(sbp_nodes *s, const double *X, int64_t m, int32_t k, i
             SBP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_prm_grid_build, GB_TPB, 0));
             if (per_sm < 1) per_sm = 1;
             if (per_sm > 3) per_sm = 3;
+            if (ctx->tune.prm_build_ctas > 0 && ctx->tune.prm_build_ctas < per_sm) per_sm = ctx->tune.prm_build_ctas;
             // (a grid-wide barrier costs more the more CTAs meet at it: small stores get a small grid)
             int nblk = ctx->sm_count * per_sm;
             const int64_t want_blk = (n + 1023) / 1024;

@@ -272,7 +272,7 @@ __device__ __forceinline__ void prm_scan_rows(const double2 *__restrict__ pts, c
 // blocked) are collected per CTA in shared memory and walked side by side over its threads (two-level
 // walk on the tile codes).  No candidate list in global memory, no second pass over all edges.
 template <int K, bool FUSE>
-__global__ void __launch_bounds__(PRM_TPB)
+__global__ void __launch_bounds__(PRM_TPB, (FUSE && K <= 10) ? 8 : 1)
 k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t count, double *__restrict__ seed2,
           uint8_t *__restrict__ done, int32_t *__restrict__ pending, int32_t *__restrict__ cand, PrmFusedArgs a) {
     const int64_t slot = (int64_t)blockIdx.x * PRM_TPB + threadIdx.x;

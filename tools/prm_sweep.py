@@ -30,10 +30,15 @@ if mode == "slices":
     grid = [(150, 0, sl, 1) for sl in (1, 2, 3, 4, 6, 8)]
 elif mode == "cells":
     grid = [(d, r, 1, 1) for d, r in itertools.product((100, 150, 200, 300), (0, 1, 2))]
+elif mode == "build":
+    grid = [(150, 0, 1, 1)] * 4
 else:
     grid = [(150, 0, 1, ws) for ws in (0, 1, 0, 1)]
-for dens, rinit, sl, ws in grid:
+for it, (dens, rinit, sl, ws) in enumerate(grid):
     if True:
+        if mode == "build":
+            ctx.tune("prm_build_ctas", (3, 2, 1, 3)[it])
+            print("build CTAs per SM", (3, 2, 1, 3)[it], end=": ")
         ctx.tune("knn_cell_density", dens)
         ctx.tune("knn_cells_rinit", rinit)
         ctx.tune("prm_slices", sl)
