@@ -49,11 +49,11 @@ UNIT = "edges/s"
 # One launch of the dominant kernel on this workload under `ncu --set full` (N = 1, full size;
 # profiles/r2_prm_knn_fused_full.txt): dram__bytes_read.sum + dram__bytes_write.sum, issue-slot
 # utilisation, active lanes per warp instruction.
-NCU_FUSED = {"kernel": "k_prm_knn<10, true>", "dram_bytes": 89240832, "issue_active_pct": 58.4,
-             "lanes_per_instruction": 24.7, "warp_instructions": 212259722, "warps_active_pct": 41.7,
-             "alu_pipe_pct": 62.8, "l1_hit_pct": 65.2, "l2_hit_pct": 74.6,
+NCU_FUSED = {"kernel": "k_prm_knn<10, true>", "dram_bytes": 119872256, "issue_active_pct": 59.5,
+             "lanes_per_instruction": 24.6, "warp_instructions": 210052932, "warps_active_pct": 47.4,
+             "alu_pipe_pct": 64.7, "l1_hit_pct": 61.6, "l2_hit_pct": 73.8,
              "source": "profiles/r2_prm_knn_fused_full.txt"}
-NCU_BUILD = {"kernel": "k_prm_grid_build", "kernel_us": 70.9, "dram_bytes": 16874240, "issue_active_pct": 26.2,
+NCU_BUILD = {"kernel": "k_prm_grid_build", "kernel_us": 68.1, "dram_bytes": 16486656, "issue_active_pct": 25.3,
              "source": "profiles/r2_prm_grid_build_full.txt"}
 
 def problem():
