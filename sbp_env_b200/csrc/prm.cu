@@ -9,8 +9,12 @@
 //   ImgCollisionChecker.visible / get_line (Bresenham)       collisionChecker.py:134-145, :155-215
 // with the k nearest neighbours as the candidate set instead of the PRM* radius.
 //
-// Two kernels answer the rows, a THREAD per row and the rows in CELL-SORTED order (the permutation
-// of the kNN's counting sort, ascending node index inside a cell):
+// ONE kernel answers the rows (k_prm_knn<K, true>: the kNN below, then the row's candidate edges --
+// free bounding boxes from the free-run planes, probes, a CTA-local walk of the rest -- and the output
+// rows from shared memory; see the comment on its FUSE parameter).  The two-kernel form
+// (k_prm_knn<K, false> + k_prm_walk_sorted / k_prm_walk, tune "prm_fuse" = 0) is kept beside it.
+// A THREAD per row and the rows in CELL-SORTED order (the permutation of the kNN's counting sort,
+// ascending node index inside a cell):
 //   k_prm_knn   the row's k nearest other nodes from the cell grid.  The 32 rows of a warp are
 //     spatial neighbours: they scan the same cells of the cell-sorted pose copy `pts` (one 16-byte
 //     load per candidate, no ids[e] -> soa[id] chain).  The list is kept sorted on the fp32
