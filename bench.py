@@ -542,6 +542,12 @@ def run_ours(args):
             "edges_per_s_kernel": edges_rank / vis_s, "interpolants_per_s_kernel": px_total / world / vis_s,
             "rows_per_s_kernel": count / vis_s, "effective_pairs_per_s": float(count) * n / vis_s,
             "ncu": prof,
+            # what does bound it: warp instructions issued (ncu count of one launch) against 4 issue slots
+            # per SM and cycle at the clock sampled during the timed loop
+            "issue": ({"warp_instructions_per_s": prof["warp_instructions"] / vis_s,
+                       "peak": 148 * 4 * float(clocks["sm_mhz"]) * 1e6 if clocks and clocks.get("sm_mhz") else None,
+                       "frac": (prof["warp_instructions"] / vis_s) / (148 * 4 * float(clocks["sm_mhz"]) * 1e6)
+                       if clocks and clocks.get("sm_mhz") else None} if prof else None),
             "note": "not an HBM stream: the kernel gathers from L1 / L2 resident arrays (cell-sorted poses 16 MB, "
                     "free-run planes 16 MiB, tile codes 8 MiB) and is bound by the instructions it issues (list "
                     "insertions in lock-step over the warp; ncu: issue slots, lanes per instruction); the HBM figure "

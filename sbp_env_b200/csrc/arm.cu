@@ -433,6 +433,81 @@ k_arm_visible_boxes(MapView mv, TileCodeView af, double L0, double L1, const dou
     if (myflag && flags) atomicOr(flags, myflag);
 }
 
+// feasible with the same free-box test (thread = config, a warp's undecided links swept 32 at a time
+// from its own list; out[i] is written by the config's lane first -- 1, or 2 when only the tip's guard
+// band is open -- and set to 0 by whichever lane finds one of its links blocked: blocked wins, as in
+// arm_config, where a blocked link 1 returns before the tip is looked at).
+struct ArmLinkF {              // 12 bytes
+    int16_t x0, y0, x1, y1;
+    uint32_t idx;            // config
+};
+
+template <bool SMEM>
+__global__ void __launch_bounds__(1024)
+k_arm_feasible_boxes(MapView mv, TileCodeView af, double L0, double L1, const double4 *__restrict__ C, int64_t n,
+                     uint8_t *__restrict__ out, int32_t *__restrict__ flags) {
+    extern __shared__ __align__(16) uint32_t smap[];
+    __shared__ uint64_t bar;
+    if (SMEM) stage_map_to_smem(smap, mv, &bar);
+    const uint32_t *words = SMEM ? smap : mv.words;
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    ArmLinkF *wl = reinterpret_cast<ArmLinkF *>(smap + (SMEM ? mv.n_words : 0u)) + (tid >> 5) * AB_LIST;
+    int wn = 0;                                                          // (warp uniform)
+    int myflag = 0;
+    const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + (tid & ~31); i0 < n; i0 += gsz) {
+        const int64_t i = i0 + lane;
+        bool need1 = false, need2 = false;
+        ArmLinkF t1, t2;
+        if (i < n) {
+            const double4 c = C[i];
+            const ArmPre p = arm_config_pre(mv, L0, L1, c.x, c.y, c.z, c.w, myflag);
+            int r = p.r;
+            if (r < 0) {
+                r = 1;
+                const bool ends1 = map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x0, mv.W), wrap_index(p.y0, mv.H)) &&
+                                   map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x1, mv.W), wrap_index(p.y1, mv.H));
+                const bool tip = p.after != 3 ||
+                                 map_free_rows<!SMEM>(words, mv.SX, wrap_index(p.x2, mv.W), wrap_index(p.y2, mv.H));
+                if (!ends1 || !tip || p.after == 0) {
+                    r = 0;
+                } else {
+                    if (p.after == 2) r = 2;
+                    need1 = !((p.x0 | p.y0 | p.x1 | p.y1) >= 0 &&
+                              tiles_rect_free(af, min(p.x0, p.x1) >> 3, max(p.x0, p.x1) >> 3, min(p.y0, p.y1) >> 3,
+                                              max(p.y0, p.y1) >> 3));
+                    need2 = p.after == 3 && !((p.x1 | p.y1 | p.x2 | p.y2) >= 0 &&
+                                              tiles_rect_free(af, min(p.x1, p.x2) >> 3, max(p.x1, p.x2) >> 3,
+                                                              min(p.y1, p.y2) >> 3, max(p.y1, p.y2) >> 3));
+                    t1.x0 = (int16_t)p.x0; t1.y0 = (int16_t)p.y0; t1.x1 = (int16_t)p.x1; t1.y1 = (int16_t)p.y1;
+                    t2.x0 = (int16_t)p.x1; t2.y0 = (int16_t)p.y1; t2.x1 = (int16_t)p.x2; t2.y1 = (int16_t)p.y2;
+                    t1.idx = t2.idx = (uint32_t)i;
+                }
+            }
+            out[i] = (uint8_t)r;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const unsigned m1 = __ballot_sync(FULL, need1), m2 = __ballot_sync(FULL, need2);
+        if (need1) wl[wn + __popc(m1 & lt)] = t1;
+        wn += __popc(m1);
+        if (need2) wl[wn + __popc(m2 & lt)] = t2;
+        wn += __popc(m2);
+        __syncwarp();
+        const bool last = i0 + gsz >= n;
+        while (wn >= 32 || (last && wn > 0)) {
+            const int take = wn < 32 ? wn : 32;
+            if (lane < take) {
+                const ArmLinkF q = wl[wn - take + lane];
+                if (!link_free<SMEM, true>(words, mv, q.x0, q.y0, q.x1, q.y1)) out[q.idx] = 0;     // :413-415, :422-424
+            }
+            wn -= take;
+            __syncwarp();
+        }
+    }
+    if (myflag && flags) atomicOr(flags, myflag);
+}
+
 // ------------------------------------------------------------ launchers -----
 
 // The arm kernels read the ROW-MAJOR copy of the map (sbp_map::rows, common.cuh).
@@ -464,6 +539,32 @@ extern "C" int32_t sbp_arm_feasible(sbp_map *map, double L0, double L1, const do
     bool smem = !ctx->tune.force_global && map->rows_smem_resident &&
                 n * 64 >= (int64_t)map->rows.n_words * 4 * (int64_t)ctx->sm_count / 4;
     int grid, threads; size_t bytes;
+    if (ctx->tune.arm_flat >= 2 && ctx->tune.tile_rect && map->view.W <= 32767 && map->view.H <= 32767 &&
+        n < ((int64_t)1 << 32)) {
+        // free-box form: tile codes / free-run planes of the map, a list of undecided links per warp
+        int32_t rc = sbp_map_ensure_allfree(map);
+        if (rc) return rc;
+        const size_t map_bytes = smem ? (size_t)map->rows.n_words * 4 : 0, list_bytes = sizeof(ArmLinkF) * AB_LIST * 32;
+        int per_sm = smem ? (int)((size_t)(227 * 1024) / (map_bytes + list_bytes + 2048)) : 2;
+        per_sm = per_sm < 1 ? 1 : per_sm > 2 ? 2 : per_sm;
+        threads = per_sm == 1 ? 1024 : 512;
+        grid = ctx->sm_count * per_sm;
+        const int64_t want = (n + threads - 1) / threads;
+        if (want < grid) grid = (int)want;
+        const TileCodeView af = sbp_map_codes(map);
+        if (smem) {
+            SBP_CUDA(cudaFuncSetAttribute(k_arm_feasible_boxes<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(map_bytes + list_bytes)));
+            k_arm_feasible_boxes<true><<<grid, threads, map_bytes + list_bytes, ctx->stream>>>(map->rows, af, L0, L1,
+                                                                                             (const double4 *)C, n, out, flags);
+        } else {
+            k_arm_feasible_boxes<false><<<grid, threads, list_bytes, ctx->stream>>>(map->rows, af, L0, L1, (const double4 *)C,
+                                                                                   n, out, flags);
+        }
+        ctx->launches++;
+        SBP_CUDA(cudaGetLastError());
+        return SBP_OK;
+    }
     arm_cfg(map, smem, grid, threads, bytes);
     int64_t need = (n + threads - 1) / threads;
     if (need < grid) grid = (int)need;

@@ -96,6 +96,8 @@ def test_random_vs_oracle(sg, name, L):
         for flat, group in ((2, 0), (1, 0), (0, 0), (0, 4), (0, 32)):
             tune("arm_flat", flat)
             tune("arm_group", group)
+            assert np.array_equal(cc.feasible_batch(C1), om.arm_feasible(C1, *L)), (flat, group)
+            assert np.array_equal(cc.feasible_batch(C2[-3000:]), om.arm_feasible(C2[-3000:], *L)), (flat, group)
             assert np.array_equal(cc.visible_batch(C1, C2), want_fwd), group
             # H8: argument order matters for the arm; check the reverse direction too
             assert np.array_equal(cc.visible_batch(C2, C1), want_rev), group

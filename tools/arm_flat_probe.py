@@ -53,3 +53,25 @@ for name, C2 in sets.items():
         print(f"{name:32s} arm_flat {flat}: {t:.3f} ms  {len(a) / t * 1e3:.3e} edges/s  {npx / t * 1e3:.3e} configs/s  visible {float((r == 1).float().mean()):.3f}", flush=True)
     assert torch.equal(res[0], res[1]) and torch.equal(res[0], res[2]), name
 sg.runtime.tune("arm_flat", 2)
+
+# feasible_batch: 2^20 uniform configs (62 % infeasible) and the feasible ones among them
+Cu = torch.rand((1 << 20, 4), generator=g, device=dev, dtype=torch.float64) * (hi - lo) + lo
+for name, X in (("feasible, uniform configs", Cu), ("feasible, free configs", C1)):
+    res = {}
+    for flat in (1, 2):
+        sg.runtime.tune("arm_flat", flat)
+        r = cc._feasible_device(X, resolve=False)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = cc._feasible_device(X, resolve=False)
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res[flat] = r.clone()
+        t = sorted(ts)[2]
+        print(f"{name:32s} arm_flat {flat}: {t:.3f} ms  {len(X) / t * 1e3:.3e} configs/s  free {float((r == 1).float().mean()):.3f}", flush=True)
+    assert torch.equal(res[1], res[2]), name
+sg.runtime.tune("arm_flat", 2)
