@@ -346,10 +346,14 @@ k_prm_knn(CellGridView g, int kq, int r_init, int limit, int64_t p0, int64_t cou
     }
     handled = handled && !L.amb;
     if (live) {
-        // (a bound for the exact path's K + 1 entries, the row itself included: the K-th other node)
-        seed2[v] = full ? L.hi * (1.0 + 1e-9) + 1e-300 : INFINITY;
-        done[v] = handled ? 1 : 0;
-        if (!handled) atomicAdd(pending, 1);                      // the exact path has work
+        if (!handled) {
+            // the exact path has work: its bound for K + 1 entries, the row itself included (the K-th
+            // other node).  done[] is 1 for every row since the grid build, and the bound is read for
+            // rows with done = 0 only, so a settled row writes neither (1 M scattered stores less)
+            seed2[v] = full ? L.hi * (1.0 + 1e-9) + 1e-300 : INFINITY;
+            done[v] = 0;
+            atomicAdd(pending, 1);
+        }
         if (handled && !FUSE) {
 #pragma unroll
             for (int t = 0; t < K; ++t)
